@@ -1,0 +1,190 @@
+// oracle/_ref shim: a C-ABI window onto the UNMODIFIED reference mapping path.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is compiled together with the reference's own
+// sources where they lie under /root/reference (src/mapper.cpp, event_detector.cpp,
+// normalizer.cpp, seed_tracker.cpp, range.cpp, read_buffer.cpp, chunk.cpp,
+// event_profiler.cpp and the vendored submods/bwa C files) by oracle/ref_build/Makefile
+// into oracle/_ref/libuncalled_ref.so.  Nothing of the reference is copied into this
+// repository; this translation unit only *calls* it:
+//   Mapper::new_read / Mapper::map_read      (reference src/mapper.cpp:188-207)
+//   EventDetector::get_means / get_events    (reference src/event_detector.cpp:114-145)
+//   Normalizer::set_signal / pop             (reference src/normalizer.cpp:31-44,120-129)
+//   PoreModel::match_prob                    (reference src/pore_model.hpp:163-165)
+//   BwaIndex::get_neighbor/get_kmer_range/sa (reference src/bwa_index.hpp:158-178)
+//   BwaIndex::create -> bwa_idx_build        (reference src/bwa_index.hpp:92-101)
+// Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference)
+// may load the resulting library.
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_set>
+#include <vector>
+#include <cmath>
+#include <chrono>
+#include <cassert>
+#include <climits>
+#include <utility>
+#include <exception>
+
+// The shim needs to read Paf's coordinates and Mapper's event counter, which the
+// reference keeps private.  Access control does not change object layout.
+#define private public
+#include "mapper.hpp"
+#undef private
+
+extern "C" {
+
+typedef struct {
+    int32_t mapped, fwd, rid;
+    uint32_t n_events;     // events detected over the whole signal
+    uint32_t events_used;  // Mapper::event_i_ when map_read returned
+    uint32_t matches;
+    uint64_t rd_len, rd_st, rd_en, rf_st, rf_en, rf_len;
+    float map_ms;
+} ref_paf_rec;
+
+static std::vector<std::pair<std::string, u64>> g_seqs;
+
+int ref_load(const char *bwa_prefix, const char *preset) {
+    if (Mapper::fmi.is_loaded()) return 1;  // static index: one load per process
+    Mapper::PRMS.bwa_prefix = bwa_prefix;
+    Mapper::PRMS.idx_preset = preset ? preset : "default";
+    Mapper m;  // triggers Mapper::load_static()
+    g_seqs = Mapper::fmi.get_seqs();
+    return 0;
+}
+
+void ref_set_max_events(uint32_t v) { Mapper::PRMS.max_events = v; }
+void ref_set_max_paths(uint32_t v) { Mapper::PRMS.max_paths = v; }
+uint32_t ref_get_max_events() { return Mapper::PRMS.max_events; }
+
+uint64_t ref_fmi_size() { return Mapper::fmi.size(); }
+uint64_t ref_sa(uint64_t i) { return Mapper::fmi.sa(i); }
+void ref_kmer_range(uint16_t kmer, uint64_t *st, uint64_t *en) {
+    Range r = Mapper::fmi.get_kmer_range(kmer);
+    *st = r.start_; *en = r.end_;
+}
+void ref_get_neighbor(uint64_t st, uint64_t en, uint8_t base, uint64_t *ost, uint64_t *oen) {
+    Range r = Mapper::fmi.get_neighbor(Range(st, en), base);
+    *ost = r.start_; *oen = r.end_;
+}
+float ref_prob_thresh(int bin) { return Mapper::prob_threshes_[bin]; }
+float ref_match_prob(float samp, uint16_t kmer) { return Mapper::model.match_prob(samp, kmer); }
+float ref_model_mean() { return Mapper::model.get_means_mean(); }
+float ref_model_stdv() { return Mapper::model.get_means_stdv(); }
+int ref_n_seqs() { return (int) g_seqs.size(); }
+const char *ref_seq_name(int i) { return g_seqs[i].first.c_str(); }
+uint64_t ref_seq_len(int i) { return g_seqs[i].second; }
+
+// EventDetector over a whole signal.  means/starts/lens must hold n entries.
+uint32_t ref_get_events(const float *raw, uint32_t n, float *means, uint32_t *starts,
+                        uint32_t *lens, float *mean_event_len) {
+    EventDetector ed;
+    std::vector<float> sig(raw, raw + n);
+    std::vector<Event> ev = ed.get_events(sig);
+    for (size_t i = 0; i < ev.size(); i++) {
+        means[i] = ev[i].mean; starts[i] = ev[i].start; lens[i] = ev[i].length;
+    }
+    if (mean_event_len) *mean_event_len = ed.mean_event_len();
+    return (uint32_t) ev.size();
+}
+
+// Offline normaliser as Mapper::map_read drives it (set_signal then pop()).
+void ref_normalize(const float *events, uint32_t n, float *out) {
+    if (n == 0) return;  // the reference divides by zero here (normalizer.cpp:123)
+    Normalizer norm(Mapper::model.get_means_mean(), Mapper::model.get_means_stdv());
+    std::vector<float> ev(events, events + n);
+    norm.set_signal(ev);
+    for (uint32_t i = 0; i < n; i++) out[i] = norm.pop();
+}
+
+static void fill_rec(Mapper &m, Paf &p, uint32_t n_events, ref_paf_rec *out) {
+    memset(out, 0, sizeof(*out));
+    out->mapped = p.is_mapped_;
+    out->fwd = p.fwd_;
+    out->rid = -1;
+    if (p.is_mapped_) {
+        for (size_t i = 0; i < g_seqs.size(); i++)
+            if (g_seqs[i].first == p.rf_name_) { out->rid = (int32_t) i; break; }
+    }
+    out->n_events = n_events;
+    out->events_used = m.event_i_;
+    out->matches = p.matches_;
+    out->rd_len = p.rd_len_; out->rd_st = p.rd_st_; out->rd_en = p.rd_en_;
+    out->rf_st = p.rf_st_; out->rf_en = p.rf_en_; out->rf_len = p.rf_len_;
+    out->map_ms = p.float_tags_.empty() ? 0.f : p.float_tags_.back().second;
+}
+
+static void map_one(Mapper &m, const float *sig, uint32_t n, ref_paf_rec *out) {
+    uint32_t n_events;
+    {
+        EventDetector ed;
+        std::vector<float> s(sig, sig + n);
+        n_events = (uint32_t) ed.get_means(s).size();
+    }
+    ReadBuffer rb;
+    rb.id_ = "r";
+    rb.channel_idx_ = 0;
+    rb.number_ = 0;
+    rb.start_sample_ = 0;
+    rb.chunk_processed_ = false;
+    rb.full_signal_.assign(sig, sig + n);
+    rb.loc_ = Paf(rb.id_, 1, 0);
+    rb.set_raw_len(n);
+    if (n_events == 0) {  // reference would SIGFPE (normalizer.cpp:123); report unmapped
+        fill_rec(m, rb.loc_, 0, out);
+        out->events_used = 0;
+        return;
+    }
+    m.new_read(rb);
+    Paf p = m.map_read();
+    fill_rec(m, p, n_events, out);
+}
+
+// One read through a FRESH Mapper (no state carried from earlier reads).
+int ref_map_read(const float *sig, uint32_t n, ref_paf_rec *out) {
+    Mapper m;
+    map_one(m, sig, n, out);
+    return 0;
+}
+
+// Many reads over n_threads worker threads, one long-lived Mapper per thread exactly as
+// MapPool::MapperThread keeps one (reference src/map_pool.cpp:104-158).  Used for timing.
+int ref_map_batch_mt(const float *samples, const uint64_t *offsets, const uint32_t *lens,
+                     uint32_t n_reads, int n_threads, ref_paf_rec *out) {
+    if (n_threads < 1) n_threads = 1;
+    std::atomic<uint32_t> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) {
+        th.emplace_back([&]() {
+            Mapper m;
+            for (;;) {
+                uint32_t i = next.fetch_add(1);
+                if (i >= n_reads) break;
+                map_one(m, samples + offsets[i], lens[i], out + i);
+            }
+        });
+    }
+    for (auto &t : th) t.join();
+    return 0;
+}
+
+// bwa index build exactly as `uncalled index` performs it (bwa_idx_build).
+int ref_index_build(const char *fasta, const char *prefix) {
+    BwaIndex<KLEN>::create(fasta, prefix);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+/* include/unc_b200.h -- C-ABI of the B200-native `uncalled map` hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no
+ * exceptions or abort() across it, every call returns 0 or a negative unc_status.
+ * The library (uncalled_b200/libunc_b200.so) contains ONLY the CUDA path; there is no
+ * CPU fallback -- if no CUDA device is usable every compute entry point fails with
+ * UNC_E_CUDA / UNC_E_NO_DEVICE.
+ *
+ * Each entry point names the reference interface it replaces (paths under the reference
+ * tree, skovaka/UNCALLED v2.3.0):
+ *
+ *   unc_index_load      Mapper::load_static            src/mapper.cpp:109-159
+ *                       BwaIndex::load_index           src/bwa_index.hpp:116-135
+ *   unc_index_build     BwaIndex::create -> bwa_idx_build
+ *                                                      src/bwa_index.hpp:92-101
+ *   unc_params_default  Mapper::PRMS and sub-structs   src/mapper.cpp:29-52,
+ *                       seed_tracker.cpp:28-32, event_detector.cpp:17-26,
+ *                       read_buffer.cpp:26-32          (what Conf binds, src/conf.hpp:57-95)
+ *   unc_pool_create     MapPool::MapPool(Conf&)        src/map_pool.cpp:28-43
+ *   unc_map_batch       MapPool::update -> MapperThread::run -> Mapper::new_read/map_read
+ *                                                      src/map_pool.cpp:45-69,130-158,
+ *                                                      src/mapper.cpp:188-207
+ *   unc_events_batch    EventDetector::get_means + Normalizer::set_signal/pop
+ *                                                      src/event_detector.cpp:133-145,
+ *                                                      src/normalizer.cpp:31-44,114-129
+ *   unc_pool_free       MapPool::stop                  src/map_pool.cpp:71-82
+ */
+#ifndef UNC_B200_H
+#define UNC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    UNC_OK = 0,
+    UNC_E_ARG = -1,          /* bad argument */
+    UNC_E_IO = -2,           /* index file missing / unreadable / inconsistent */
+    UNC_E_CUDA = -3,         /* CUDA runtime error (see unc_last_error) */
+    UNC_E_NO_DEVICE = -4,    /* no usable CUDA device */
+    UNC_E_TOO_LARGE = -5,    /* index or batch exceeds what the device image supports */
+    UNC_E_NOMEM = -6,
+    UNC_E_OVERFLOW = -7      /* a per-read device workspace overflowed (record status says which) */
+} unc_status;
+
+/* Mirror of the reference's process-global parameter structs (Conf binds references to
+ * them, src/conf.hpp:66-72); snapshot by value at unc_pool_create. */
+typedef struct {
+    /* Mapper::PRMS, src/mapper.cpp:29-52 */
+    uint32_t seed_len;        /* 22; the device image supports seed_len == 22 only */
+    uint32_t min_rep_len;     /* 0 */
+    uint32_t max_rep_copy;    /* 50 */
+    uint32_t max_paths;       /* 10000 (<= 32767) */
+    uint32_t max_consec_stay; /* 8 */
+    uint32_t max_events;      /* 30000 */
+    float max_stay_frac;      /* 0.5 */
+    float min_seed_prob;      /* -3.75 */
+    /* SeedTracker::PRMS_DEF, src/seed_tracker.cpp:28-32 */
+    uint32_t min_map_len;     /* 25 */
+    float min_mean_conf;      /* 6.00 */
+    float min_top_conf;       /* 1.85 */
+    /* EventDetector::PRMS_DEF, src/event_detector.cpp:17-26 (window lengths 3/6 are fixed
+     * in the device image) */
+    uint32_t window_length1, window_length2;
+    float threshold1, threshold2, peak_height, min_mean, max_mean;
+    /* ReadBuffer::PRMS, src/read_buffer.cpp:26-32 */
+    float bp_per_sec, sample_rate;
+} unc_params;
+
+/* One read of a batch.  `offset` counts samples (not bytes) from the start of `samples`. */
+typedef struct {
+    uint64_t offset;
+    uint32_t n_samples;
+    uint32_t dtype; /* UNC_DTYPE_F32: calibrated pA; UNC_DTYPE_I16: raw DAC values calibrated on
+                       the device as src/read_buffer.cpp:239-242 does (u16 reinterpretation) */
+    float cal_range, cal_offset, cal_digit; /* used for UNC_DTYPE_I16 only */
+} unc_read_desc;
+
+#define UNC_DTYPE_F32 0
+#define UNC_DTYPE_I16 1
+
+/* What Paf::set_mapped / set_read_len receive (src/read_buffer.cpp:133-155) plus counters. */
+typedef struct {
+    int32_t mapped;       /* Paf::is_mapped_ */
+    int32_t fwd;          /* '+' / '-' */
+    int32_t rid;          /* index into the .ann sequences, -1 when unmapped / untranslatable */
+    int32_t status;       /* 0, or UNC_E_OVERFLOW when a device workspace overflowed for this read */
+    uint32_t n_events;    /* valid events detected over the whole (possibly truncated) signal */
+    uint32_t events_used; /* Mapper::event_i_ when mapping stopped */
+    uint32_t matches;
+    uint32_t n_clusters;
+    uint64_t rd_len, rd_st, rd_en, rf_st, rf_en, rf_len;
+    /* exact work counters (algorithmic bytes of the roofline) */
+    uint64_t n_children, n_sources, n_occ_blocks, n_sa_steps, n_seeds;
+} unc_paf_rec;
+
+typedef struct {
+    float h2d_ms, k1_ms, k2_ms, d2h_ms, total_ms; /* CUDA events on the pool's stream */
+    uint32_t kernel_launches;                      /* launches of this library's kernels */
+    uint64_t h2d_bytes, d2h_bytes;
+} unc_timing;
+
+typedef struct {
+    uint64_t n_rows;  /* FM-index length (fwd + revcomp) */
+    int32_t n_seqs;
+    int32_t device;
+    uint64_t device_bytes;
+    uint32_t n_kmer_groups;
+} unc_index_info;
+
+typedef struct unc_index unc_index;
+typedef struct unc_pool unc_pool;
+
+const char *unc_strerror(int status);
+const char *unc_last_error(void); /* thread-local detail of the last failure */
+int unc_device_count(void);
+/* Select the CUDA device used by subsequent unc_index_load / unc_pool_create calls of
+ * this process (one process per GPU). */
+int unc_init(int device);
+
+int unc_params_default(unc_params *p);
+
+/* Parses <prefix>.bwt/.sa/.ann/.amb and the <preset> line of <prefix>.uncl on the host,
+ * builds the device image (Occ blocks, u32 sampled SA, 1024 k-mer FM ranges, pore model,
+ * thresholds) and uploads it.  model_path == NULL selects the built-in r9.4 5-mer model
+ * table file given by model_table_path (1024 x {mean, stdv} f32, template order). */
+int unc_index_load(const char *bwa_prefix, const char *preset, const char *model_table_path,
+                   unc_index **out);
+int unc_index_get_info(const unc_index *idx, unc_index_info *info);
+int unc_index_seq(const unc_index *idx, int rid, const char **name, uint64_t *len);
+/* Host-side copies of device tables, for parity tests. */
+int unc_index_kmer_range(const unc_index *idx, uint32_t kmer, uint64_t *start, uint64_t *end);
+int unc_index_thresholds(const unc_index *idx, float out[64]);
+void unc_index_free(unc_index *idx);
+
+/* bwa-compatible FM-index construction (.pac .ann .amb .bwt .sa), host C++. */
+int unc_index_build(const char *fasta_path, const char *prefix);
+
+/* Device workspace for batches of at most max_reads reads / max_samples samples in total. */
+int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_reads,
+                    uint64_t max_samples, unc_pool **out);
+void unc_pool_free(unc_pool *pool);
+
+/* Whole path over a batch held in HOST memory (pinned or pageable): H2D of the samples,
+ * event detection + normalisation kernel, mapping kernel, D2H of the records.  Synchronous. */
+int unc_map_batch(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads, const void *samples,
+                  unc_paf_rec *out);
+/* Same, with the samples already resident in device memory (`d_samples` is a device
+ * pointer on the pool's device); descriptors and results stay on the host. */
+int unc_map_batch_device(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads,
+                         const void *d_samples, unc_paf_rec *out);
+
+/* Event detection + normalisation alone.  events/normed hold `stride` floats per read
+ * (stride >= the longest read's n_samples); n_events, mean_event_len one entry per read. */
+int unc_events_batch(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads, const void *samples,
+                     uint32_t stride, float *events, float *normed, uint32_t *n_events,
+                     float *mean_event_len);
+
+/* pore-model log-probabilities of one normalised event against all 1024 k-mers, computed
+ * on the device with the mapper's own routine (parity probe). */
+int unc_match_probs(const unc_index *idx, float event, float out[1024]);
+/* FM probes computed on the device (parity probes): one backward step per entry, and SA. */
+int unc_fm_neighbors(const unc_index *idx, uint32_t n, const uint64_t *start, const uint64_t *end,
+                     const uint8_t *base, uint64_t *ostart, uint64_t *oend);
+int unc_fm_sa(const unc_index *idx, uint32_t n, const uint64_t *rows, uint64_t *out);
+
+int unc_pool_last_timing(const unc_pool *pool, unc_timing *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,125 @@
+// tests/emul/emul_main.cpp -- runs the DEVICE source (uncalled_b200/csrc/unc_device.cuh,
+// compiled with -DUNC_EMUL) on the CPU under the 32-fiber warp emulator.  Test vehicle only:
+// it lets the CPU-only test tier compare the warp-cooperative kernel logic with the oracle.
+#include "unc_device.cuh"   // UNC_EMUL is defined on the command line
+#include "../../include/unc_b200.h"
+#include "unc_host_index.hpp"
+#include "unc_host_params.hpp"
+
+thread_local WarpEmu *g_warp = nullptr;
+
+struct EmuIndex {
+    HostIndex h;
+    DevIndex ix;
+    std::vector<uint2> kmer_range;
+    K2Tables tb;
+};
+
+extern "C" {
+
+void *emu_index_load(const char *prefix, const char *preset, const char *model_table) {
+    EmuIndex *e = new EmuIndex();
+    if (!hix_load_model(e->h, model_table) || !hix_load(e->h, prefix, preset ? preset : "default")) {
+        fprintf(stderr, "emu_index_load: %s\n", e->h.error.c_str());
+        delete e;
+        return nullptr;
+    }
+    HostIndex &h = e->h;
+    DevIndex &ix = e->ix;
+    ix.bwt = (const uint4 *) h.bwt.data();
+    ix.sa = h.sa32.data();
+    ix.lv_mean = h.lv_mean.data(); ix.lv_var2 = h.lv_var2.data(); ix.lognorm = h.lognorm.data();
+    ix.thresh = h.thresh;
+    ix.primary = (u32) h.primary; ix.seq_len = (u32) h.seq_len;
+    for (int i = 0; i < 5; i++) ix.L2[i] = (u32) h.L2[i];
+    ix.start_bits = 64 - __builtin_clzll(h.seq_len);
+    e->kmer_range.resize(1024);
+    for (u32 k = 0; k < 1024; k++) e->kmer_range[k] = unc_kmer_range_compute(ix, k);
+    ix.kmer_range = e->kmer_range.data();
+    for (u32 k = 0; k < 1024; k++) {
+        e->tb.lv_mean[k] = h.lv_mean[k]; e->tb.lv_var2[k] = h.lv_var2[k]; e->tb.lognorm[k] = h.lognorm[k];
+        e->tb.kmer_range[k] = e->kmer_range[k];
+    }
+    for (int i = 0; i < 64; i++) e->tb.thresh[i] = h.thresh[i];
+    return e;
+}
+
+void emu_index_free(void *p) { delete (EmuIndex *) p; }
+
+void emu_kmer_range(void *p, uint32_t k, uint64_t *st, uint64_t *en) {
+    EmuIndex *e = (EmuIndex *) p;
+    *st = e->kmer_range[k].x; *en = e->kmer_range[k].y;
+}
+
+struct WarpArgs {
+    const DevIndex *ix; const DevParams *p; const DevBatch *B; const DevWork *W; K2Shared *sh; const K2Tables *tb; u32 r;
+};
+static void warp_entry(void *a) {
+    WarpArgs *w = (WarpArgs *) a;
+    unc_k2_map_read(*w->ix, *w->p, *w->B, *w->W, w->sh, w->tb, w->r);
+}
+
+// events (optional, n_reads x stride) / normed (optional) are filled like unc_events_batch.
+int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads, uint32_t n_reads,
+                  const void *samples, unc_paf_rec *out, uint32_t stride, float *events_out, float *normed_out,
+                  uint32_t *n_events_out, float *mel_out, int run_k2, uint32_t max_blocks) {
+    EmuIndex *e = (EmuIndex *) pidx;
+    std::string err;
+    if (unc_check_params(*prm, err)) { fprintf(stderr, "%s\n", err.c_str()); return UNC_E_ARG; }
+    DevParams dp = unc_make_dev_params(*prm, e->h);
+    u32 max_n = 0;
+    for (u32 i = 0; i < n_reads; i++) if (reads[i].n_samples > max_n) max_n = reads[i].n_samples;
+    if (stride < max_n) stride = max_n;
+    std::vector<DevReadDesc> rd(n_reads);
+    for (u32 i = 0; i < n_reads; i++) {
+        rd[i].offset = reads[i].offset; rd[i].n_samples = reads[i].n_samples; rd[i].dtype = reads[i].dtype;
+        rd[i].cal_range = reads[i].cal_range; rd[i].cal_offset = reads[i].cal_offset; rd[i].cal_digit = reads[i].cal_digit;
+        rd[i].pad = 0;
+    }
+    std::vector<float> events((size_t) n_reads * stride + 1), normed((size_t) n_reads * stride + 1);
+    std::vector<u32> n_events(n_reads);
+    std::vector<float> scale(n_reads), shift(n_reads), mel(n_reads);
+    std::vector<u64> seq_off(e->h.offsets.begin(), e->h.offsets.end());
+    DevBatch B;
+    B.samples = samples; B.reads = rd.data(); B.n_reads = n_reads;
+    B.events = events.data(); B.normed = normed.data(); B.ev_stride = stride;
+    B.n_events = n_events.data(); B.scale = scale.data(); B.shift = shift.data(); B.mean_event_len = mel.data();
+    u32 queue = 0;
+    B.queue = &queue; B.out = (DevRec *) out;
+    B.seq_offsets = seq_off.data(); B.seq_lens = e->h.lens.data(); B.n_seqs = (u32) e->h.names.size();
+    B.l_pac = (u64) e->h.l_pac;
+    for (u32 r = 0; r < n_reads; r++) unc_k1_read(B, dp, r);
+    if (events_out) memcpy(events_out, events.data(), (size_t) n_reads * stride * 4);
+    if (normed_out) memcpy(normed_out, normed.data(), (size_t) n_reads * stride * 4);
+    if (n_events_out) memcpy(n_events_out, n_events.data(), n_reads * 4);
+    if (mel_out) memcpy(mel_out, mel.data(), n_reads * 4);
+    if (!run_k2) return 0;
+
+    u32 maxp = dp.max_paths;
+    std::vector<uint4> paths((size_t) 2 * maxp * 8), ckey((size_t) 2 * maxp);
+    std::vector<u16> order((size_t) 2 * maxp);
+    std::vector<uint4> clu((size_t) max_blocks * 32 * 2), dir(max_blocks + 1);
+    DevWork W;
+    W.paths = paths.data(); W.ckey = ckey.data(); W.order = order.data(); W.clu = clu.data(); W.dir = dir.data();
+    W.max_blocks = max_blocks;
+    K2Shared *sh = new K2Shared();
+    for (u32 r = 0; r < n_reads; r++) {
+        WarpArgs a = {&e->ix, &dp, &B, &W, sh, &e->tb, r};
+        emu_run_warp(warp_entry, &a);
+    }
+    delete sh;
+    return 0;
+}
+
+void emu_match_probs(void *pidx, float event, float *out) {
+    EmuIndex *e = (EmuIndex *) pidx;
+    for (u32 k = 0; k < 1024; k++) out[k] = unc_match_prob(event, e->tb.lv_mean[k], e->tb.lv_var2[k], e->tb.lognorm[k]);
+}
+
+uint64_t emu_sa(void *pidx, uint64_t row) {
+    EmuIndex *e = (EmuIndex *) pidx;
+    u32 a = 0, b = 0;
+    return unc_sa(e->ix, (u32) row, &a, &b);
+}
+
+}  // extern "C"

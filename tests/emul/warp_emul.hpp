@@ -1,0 +1,168 @@
+// tests/emul/warp_emul.hpp -- 32-fiber lockstep emulation of one CUDA warp on the CPU.
+//
+// TEST VEHICLE ONLY.  It lets tests run the device source of uncalled_b200/csrc/*.cuh
+// (compiled with -DUNC_EMUL) on a box without a GPU, so the warp-cooperative logic can be
+// compared with the oracle before any GPU time is spent.  Every warp collective is a
+// rendezvous of all 32 fibers (full-mask semantics); a lane that skips a collective the
+// others reach is reported as a deadlock, which is exactly the bug it would be on the GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#define UNC_DEV static inline
+#define UNC_DEV_NOINLINE static
+#define UNC_FULL 0xffffffffu
+
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = {x, y}; return r; }
+
+struct WarpEmu {
+    ucontext_t ctx[32], main_ctx;
+    char *stacks[32];
+    int cur;
+    int done[32];
+    int n_done;
+    uint64_t slot[32], result[32];
+    int arrived;
+    uint64_t gen;
+    void (*fn)(void *);
+    void *arg;
+};
+extern thread_local WarpEmu *g_warp;
+
+static inline void emu_yield() {
+    WarpEmu *w = g_warp;
+    int from = w->cur, nxt = from;
+    for (int i = 0; i < 32; i++) {
+        nxt = (nxt + 1) & 31;
+        if (!w->done[nxt]) break;
+    }
+    if (nxt == from) return;
+    w->cur = nxt;
+    swapcontext(&w->ctx[from], &w->ctx[nxt]);
+}
+
+// all-lane exchange: every lane posts v, then may read any lane's value from result[]
+static inline const uint64_t *emu_exchange(uint64_t v) {
+    WarpEmu *w = g_warp;
+    if (w->n_done) { fprintf(stderr, "warp_emul: collective reached after %d lane(s) exited\n", w->n_done); abort(); }
+    int lane = w->cur;
+    w->slot[lane] = v;
+    uint64_t mygen = w->gen;
+    if (++w->arrived == 32) {
+        memcpy(w->result, w->slot, sizeof(w->slot));
+        w->arrived = 0;
+        w->gen++;
+    } else {
+        int spins = 0;
+        while (w->gen == mygen) {
+            emu_yield();
+            if (++spins > 100000) { fprintf(stderr, "warp_emul: deadlock at a collective (lane %d)\n", lane); abort(); }
+        }
+    }
+    return w->result;
+}
+
+static inline int w_lane() { return g_warp->cur; }
+static inline void w_sync() { emu_exchange(0); }
+static inline uint32_t w_ballot(int p) {
+    // copy out immediately: result[] is overwritten by the next collective
+    uint64_t tmp[32];
+    memcpy(tmp, emu_exchange(p ? 1 : 0), sizeof(tmp));
+    uint32_t m = 0;
+    for (int i = 0; i < 32; i++) m |= (uint32_t) (tmp[i] & 1) << i;
+    return m;
+}
+static inline uint32_t w_shfl(uint32_t v, int src) { return (uint32_t) emu_exchange(v)[src & 31]; }
+static inline float w_shflf(float v, int src) {
+    uint32_t b; memcpy(&b, &v, 4);
+    b = w_shfl(b, src);
+    float r; memcpy(&r, &b, 4);
+    return r;
+}
+static inline uint32_t w_shfl_up(uint32_t v, int d) {
+    int lane = w_lane();
+    const uint64_t *r = emu_exchange(v);
+    return lane >= d ? (uint32_t) r[lane - d] : v;
+}
+static inline uint32_t w_shfl_down(uint32_t v, int d) {
+    int lane = w_lane();
+    const uint64_t *r = emu_exchange(v);
+    return lane + d < 32 ? (uint32_t) r[lane + d] : v;
+}
+static inline uint32_t w_match(uint32_t v) {
+    uint64_t tmp[32];
+    memcpy(tmp, emu_exchange(v), sizeof(tmp));
+    uint32_t m = 0;
+    for (int i = 0; i < 32; i++) if ((uint32_t) tmp[i] == v) m |= 1u << i;
+    return m;
+}
+static inline uint32_t d_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t s_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t s_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+static inline int d_popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int d_popcll(uint64_t v) { return __builtin_popcountll(v); }
+static inline int d_clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+static inline int d_ffs(uint32_t v) { return __builtin_ffs((int) v); }
+// compiled with -ffp-contract=off: plain IEEE operations
+static inline float f_mul(float a, float b) { return a * b; }
+static inline float f_add(float a, float b) { return a + b; }
+static inline float f_sub(float a, float b) { return a - b; }
+static inline float f_div(float a, float b) { return a / b; }
+static inline float f_sqrt(float a) { return sqrtf(a); }
+static inline double d_mul(double a, double b) { return a * b; }
+static inline double d_add(double a, double b) { return a + b; }
+static inline double d_sub(double a, double b) { return a - b; }
+static inline double d_div(double a, double b) { return a / b; }
+static inline double d_sqrt(double a) { return sqrt(a); }
+static inline uint32_t f_to_u32_x86(float v) { return (uint32_t) (long long) v; }
+static inline uint64_t f_to_u64(float v) { return (uint64_t) v; }
+template <typename T> static inline T d_ldg(const T *p) { return *p; }
+static inline float u2f(uint32_t v) { float r; memcpy(&r, &v, 4); return r; }
+static inline uint32_t f2u(float v) { uint32_t r; memcpy(&r, &v, 4); return r; }
+
+static void emu_trampoline() {
+    WarpEmu *w = g_warp;
+    w->fn(w->arg);
+    int me = w->cur;
+    w->done[me] = 1;
+    w->n_done++;
+    if (w->n_done == 32) {
+        swapcontext(&w->ctx[me], &w->main_ctx);
+    } else {
+        // a lane left early: the others must not touch a collective any more (checked there)
+        int nxt = me;
+        for (int i = 0; i < 32; i++) { nxt = (nxt + 1) & 31; if (!w->done[nxt]) break; }
+        w->cur = nxt;
+        swapcontext(&w->ctx[me], &w->ctx[nxt]);
+    }
+}
+
+// run fn(arg) on 32 lockstep lanes
+static inline void emu_run_warp(void (*fn)(void *), void *arg) {
+    WarpEmu *w = (WarpEmu *) calloc(1, sizeof(WarpEmu));
+    WarpEmu *saved = g_warp;
+    g_warp = w;
+    w->fn = fn;
+    w->arg = arg;
+    const size_t STK = 1 << 20;
+    for (int i = 0; i < 32; i++) {
+        w->stacks[i] = (char *) malloc(STK);
+        getcontext(&w->ctx[i]);
+        w->ctx[i].uc_stack.ss_sp = w->stacks[i];
+        w->ctx[i].uc_stack.ss_size = STK;
+        w->ctx[i].uc_link = &w->main_ctx;
+        makecontext(&w->ctx[i], (void (*)()) emu_trampoline, 0);
+    }
+    w->cur = 0;
+    swapcontext(&w->main_ctx, &w->ctx[0]);
+    for (int i = 0; i < 32; i++) free(w->stacks[i]);
+    g_warp = saved;
+    free(w);
+}

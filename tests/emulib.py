@@ -1,0 +1,133 @@
+"""ctypes binding of tests/emul/libunc_emul.so: the DEVICE source run on the CPU under the
+32-fiber warp emulator (test vehicle; see tests/emul/warp_emul.hpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+MODEL_TABLE = os.path.join(ROOT, "uncalled_b200", "data", "r94_5mer_template.f32")
+
+
+class UncParams(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in
+                ("seed_len", "min_rep_len", "max_rep_copy", "max_paths", "max_consec_stay", "max_events")] + \
+               [("max_stay_frac", C.c_float), ("min_seed_prob", C.c_float),
+                ("min_map_len", C.c_uint32), ("min_mean_conf", C.c_float), ("min_top_conf", C.c_float),
+                ("window_length1", C.c_uint32), ("window_length2", C.c_uint32),
+                ("threshold1", C.c_float), ("threshold2", C.c_float), ("peak_height", C.c_float),
+                ("min_mean", C.c_float), ("max_mean", C.c_float),
+                ("bp_per_sec", C.c_float), ("sample_rate", C.c_float)]
+
+
+class UncReadDesc(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("n_samples", C.c_uint32), ("dtype", C.c_uint32),
+                ("cal_range", C.c_float), ("cal_offset", C.c_float), ("cal_digit", C.c_float)]
+
+
+class UncPaf(C.Structure):
+    _fields_ = [("mapped", C.c_int32), ("fwd", C.c_int32), ("rid", C.c_int32), ("status", C.c_int32),
+                ("n_events", C.c_uint32), ("events_used", C.c_uint32), ("matches", C.c_uint32),
+                ("n_clusters", C.c_uint32),
+                ("rd_len", C.c_uint64), ("rd_st", C.c_uint64), ("rd_en", C.c_uint64),
+                ("rf_st", C.c_uint64), ("rf_en", C.c_uint64), ("rf_len", C.c_uint64),
+                ("n_children", C.c_uint64), ("n_sources", C.c_uint64), ("n_occ_blocks", C.c_uint64),
+                ("n_sa_steps", C.c_uint64), ("n_seeds", C.c_uint64)]
+
+
+def default_params():
+    p = UncParams()
+    (p.seed_len, p.min_rep_len, p.max_rep_copy, p.max_paths, p.max_consec_stay, p.max_events) = (22, 0, 50, 10000, 8, 30000)
+    p.max_stay_frac, p.min_seed_prob = 0.5, -3.75
+    p.min_map_len, p.min_mean_conf, p.min_top_conf = 25, 6.0, 1.85
+    p.window_length1, p.window_length2 = 3, 6
+    p.threshold1, p.threshold2, p.peak_height, p.min_mean, p.max_mean = 1.4, 9.0, 0.2, 0, 400
+    p.bp_per_sec, p.sample_rate = 450, 4000
+    return p
+
+
+def make_descs(lens, dtype=0, cal=(1.0, 0.0, 1.0)):
+    n = len(lens)
+    d = (UncReadDesc * n)()
+    off = 0
+    for i, L in enumerate(lens):
+        d[i].offset, d[i].n_samples, d[i].dtype = off, int(L), dtype
+        d[i].cal_range, d[i].cal_offset, d[i].cal_digit = cal
+        off += int(L)
+    return d
+
+
+def build():
+    src = os.path.join(EMUL_DIR, "emul_main.cpp")
+    out = os.path.join(EMUL_DIR, "libunc_emul.so")
+    deps = [src, os.path.join(EMUL_DIR, "warp_emul.hpp")] + \
+           [os.path.join(ROOT, "uncalled_b200", "csrc", f) for f in
+            ("unc_device.cuh", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp")]
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-DUNC_EMUL", "-fPIC", "-shared",
+                    "-I" + EMUL_DIR, "-I" + os.path.join(ROOT, "uncalled_b200", "csrc"), "-o", out, src],
+                   check=True, capture_output=True)
+    return out
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.emu_index_load.restype = C.c_void_p
+        L.emu_index_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+        L.emu_index_free.argtypes = [C.c_void_p]
+        L.emu_kmer_range.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.emu_map_batch.argtypes = [C.c_void_p, C.POINTER(UncParams), C.POINTER(UncReadDesc), C.c_uint32, C.c_void_p,
+                                    C.POINTER(UncPaf), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_uint32]
+        L.emu_match_probs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+        L.emu_sa.argtypes = [C.c_void_p, C.c_uint64]
+        L.emu_sa.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+class Emu:
+    def __init__(self, prefix, preset="default"):
+        self.L = lib()
+        self.idx = self.L.emu_index_load(prefix.encode(), preset.encode(), MODEL_TABLE.encode())
+        if not self.idx:
+            raise RuntimeError("emu_index_load failed")
+        self.params = default_params()
+
+    def map_batch(self, signals, run_k2=True, max_blocks=4096, dtype=0, cal=(1.0, 0.0, 1.0)):
+        """signals: list of 1-D arrays.  Returns (recs, events list, normed list, mean_event_len)."""
+        lens = [len(s) for s in signals]
+        npdt = np.float32 if dtype == 0 else np.int16
+        flat = np.ascontiguousarray(np.concatenate(signals).astype(npdt))
+        n = len(lens)
+        d = make_descs(lens, dtype, cal)
+        stride = max(lens)
+        out = (UncPaf * n)()
+        ev = np.zeros((n, stride), np.float32)
+        nm = np.zeros((n, stride), np.float32)
+        ne = np.zeros(n, np.uint32)
+        mel = np.zeros(n, np.float32)
+        rc = self.L.emu_map_batch(self.idx, C.byref(self.params), d, n, flat.ctypes.data, out, stride,
+                                  ev.ctypes.data, nm.ctypes.data, ne.ctypes.data, mel.ctypes.data,
+                                  1 if run_k2 else 0, max_blocks)
+        if rc != 0:
+            raise RuntimeError("emu_map_batch rc=%d" % rc)
+        return list(out), [ev[i, :ne[i]].copy() for i in range(n)], [nm[i, :ne[i]].copy() for i in range(n)], mel
+
+
+PAF_KEYS = ("mapped", "fwd", "rid", "n_events", "events_used", "matches",
+            "rd_len", "rd_st", "rd_en", "rf_st", "rf_en", "rf_len")
+
+
+def paf_tuple(r):
+    if not r.mapped:
+        return (0, int(r.rd_len), int(r.n_events), int(r.events_used))
+    return tuple(int(getattr(r, k)) for k in PAF_KEYS)

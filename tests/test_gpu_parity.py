@@ -1,0 +1,176 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the golden vectors of
+the real reference and against the oracle on the same seeded inputs.  Bit-exact throughout
+(integer/index work; the float pipeline reproduces the reference's rounding exactly, so the
+1e-4 tolerance of the north star is tightened to equality here)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def U():
+    import uncalled_b200
+    uncalled_b200._native.lib()
+    return uncalled_b200
+
+
+@pytest.fixture(scope="module")
+def ex(U, example_prefix):
+    idx = U.Index(example_prefix, device=0)
+    bm = U.BatchMapper(idx, max_reads=64, max_samples=64 * 32000)
+    return idx, bm
+
+
+def test_events_and_normalisation_match_reference_golden(U, ex, golden_read):
+    idx, bm = ex
+    raw = golden_read["raw"]
+    offs = [0, 4000, 8000, 20000]
+    sigs = [raw] + [raw[o:o + 4000] for o in offs]
+    ev, nm, ne, mel = bm.events(np.concatenate(sigs), U.make_descs([len(s) for s in sigs]))
+    assert ne[0] == len(golden_read["ev_mean"]) == 6171
+    assert np.array_equal(ev[0, :ne[0]], golden_read["ev_mean"])
+    assert np.array_equal(nm[0, :ne[0]], golden_read["normed"])     # bit-exact (tolerance 0 <= 1e-4)
+    assert mel[0] == golden_read["mean_event_len"]
+    assert list(ne[1:]) == list(golden_read["win_counts"])
+
+
+def test_events_i16_calibration(U, ex, golden_read):
+    """raw DAC input calibrated on the device as read_buffer.cpp:239-242 (u16 reinterpretation)."""
+    import orclib
+    idx, bm = ex
+    rng = np.random.default_rng(3)
+    i16 = rng.integers(200, 1200, 6000).astype(np.int16)
+    i16[100:110] = -5  # negative DAC values wrap to ~65k and are rejected by max_mean
+    cal = (1467.61, 10.0, 8192.0)
+    pa = (np.float32(cal[0]) * (i16.astype(np.uint16).astype(np.float32) + np.float32(cal[1]))) / np.float32(cal[2])
+    ev, nm, ne, mel = bm.events(i16, U.make_descs([len(i16)], dtype=1, cal=cal))
+    O = orclib.Oracle()
+    m, s, l, omel = O.detect(pa.astype(np.float32))
+    assert ne[0] == len(m) and np.array_equal(ev[0, :ne[0]], m) and mel[0] == omel
+
+
+def test_pore_model_matches_reference_golden(U, ex):
+    idx, _ = ex
+    g = np.load(os.path.join(ROOT, "tests", "golden", "example_model.npz"))
+    for e, want in zip(g["events"], g["probs"]):
+        assert np.array_equal(idx.match_probs(e), want)
+
+
+def test_fm_index_matches_reference_golden(U, ex, example_prefix):
+    import orclib
+    idx, _ = ex
+    g = np.load(os.path.join(ROOT, "tests", "golden", "example_index.npz"))
+    st, en = idx.kmer_ranges()
+    assert np.array_equal(en - st + 1, g["kmer_count"])
+    n = int(g["size"])
+    assert idx.n_rows == n
+    assert np.array_equal(idx.sa(np.arange(1, n + 1)), g["sa_1_to_n"])
+    O = orclib.Oracle(example_prefix)
+    rng = np.random.default_rng(11)
+    s = rng.integers(1, n, 4000).astype(np.uint64)
+    e = np.minimum(s + rng.integers(0, 40, 4000).astype(np.uint64), n)
+    b = rng.integers(0, 4, 4000).astype(np.uint8)
+    os_, oe = idx.neighbors(s, e, b)
+    import ctypes as C
+    a, c = C.c_uint64(), C.c_uint64()
+    for i in range(4000):
+        O.lib.orc_get_neighbor(O.idx, int(s[i]), int(e[i]), int(b[i]), C.byref(a), C.byref(c))
+        assert (a.value, c.value) == (int(os_[i]), int(oe[i])), i
+
+
+def _golden_fields(key):
+    f = json.load(open(os.path.join(ROOT, "tests", "golden", "example_paf.json")))[key]["fields"]
+    return f
+
+
+def test_map_example_read_matches_reference_paf(U, ex, golden_read):
+    """config 1: the example read's PAF line, field for field, as `uncalled map` prints it."""
+    idx, bm = ex
+    raw = golden_read["raw"]
+    out = bm.map(np.concatenate([raw, raw[:4000]]), U.make_descs([len(raw), 4000]))
+    for r, key in ((out[0], "default"), (out[1], "max_chunks_1")):
+        f = _golden_fields(key)
+        assert r["mapped"] == 1 and r["status"] == 0
+        got = [str(int(r["rd_len"])), str(int(r["rd_st"])), str(int(r["rd_en"])), "+" if r["fwd"] else "-",
+               idx.seqs[r["rid"]][0], str(int(r["rf_len"])), str(int(r["rf_st"])), str(int(r["rf_en"])),
+               str(int(r["matches"])), str(int(r["rf_en"] - r["rf_st"] + 1)), "255"]
+        assert got == f[1:], (got, f)
+
+
+def test_map_example_max_events(U, example_prefix, golden_read):
+    idx = U.Index(example_prefix, device=0)
+    p = U.default_params()
+    p.max_events = 100
+    bm = U.BatchMapper(idx, params=p, max_reads=4, max_samples=40000)
+    raw = golden_read["raw"]
+    out = bm.map(raw, U.make_descs([len(raw)]))
+    f = _golden_fields("max_events_100")
+    assert out[0]["mapped"] == 0 and str(int(out[0]["rd_len"])) == f[1] and out[0]["events_used"] == 100
+
+
+def _compare_with_oracle(U, name, n_reads, n_samples, seed, threads=8, params_mod=None):
+    import orclib
+    import synth
+    import synthdata
+    prefix, g = synthdata.get_index(name)
+    sig, truth = synth.reads(g, n_reads, n_samples, seed=seed)
+    idx = U.Index(prefix, device=0)
+    p = U.default_params()
+    O = orclib.Oracle(prefix)
+    if params_mod:
+        params_mod(p)
+        params_mod(O.params)
+    bm = U.BatchMapper(idx, params=p, max_reads=n_reads, max_samples=n_reads * n_samples)
+    out = bm.map(sig.ravel(), U.make_descs([n_samples] * n_reads))
+    offs = np.arange(n_reads, dtype=np.uint64) * n_samples
+    want = O.map_batch(sig.ravel(), offs, np.full(n_reads, n_samples, np.uint32), threads)
+    bad = []
+    for i in range(n_reads):
+        a, b = orclib.paf_tuple(want[i]), U.paf_key(out[i])
+        ca = (want[i].n_children, want[i].n_sources, want[i].n_seeds, want[i].n_clusters)
+        cb = (int(out[i]["n_children"]), int(out[i]["n_sources"]), int(out[i]["n_seeds"]), int(out[i]["n_clusters"]))
+        if a != b or ca != cb or out[i]["status"] != 0:
+            bad.append((i, a, b, ca, cb, int(out[i]["status"])))
+    assert not bad, bad[:5]
+    return out, want
+
+
+def test_map_synthetic_200k_matches_oracle(U):
+    out, want = _compare_with_oracle(U, "g200k", 256, 4000, seed=7)
+    assert sum(r.mapped for r in want) > 150
+
+
+def test_map_synthetic_4m7_matches_oracle(U):
+    """E. coli-sized index (4.7 Mb): includes reads that hit the max_paths cap."""
+    out, want = _compare_with_oracle(U, "g4m7", 48, 4000, seed=21)
+    assert max(r.max_paths_seen for r in want) == 10000
+
+
+def test_map_ragged_and_tiny_reads(U):
+    """ragged batch: empty-event reads, very short reads, long reads in one call."""
+    import orclib
+    import synth
+    import synthdata
+    prefix, g = synthdata.get_index("g200k")
+    sig, _ = synth.reads(g, 6, 12000, seed=5)
+    lens = [12000, 0 + 5, 40, 300, 4000, 7777]
+    sigs = [sig[i, :L] for i, L in enumerate(lens)]
+    idx = U.Index(prefix, device=0)
+    bm = U.BatchMapper(idx, max_reads=8, max_samples=sum(lens) + 16)
+    out = bm.map(np.concatenate(sigs), U.make_descs(lens))
+    O = orclib.Oracle(prefix)
+    for i, s in enumerate(sigs):
+        assert orclib.paf_tuple(O.map_read(s)) == U.paf_key(out[i]), i
+
+
+def test_small_max_paths_overflow_semantics(U):
+    """max_paths tiny: exercises the full-buffer break, stale sources_added_ flags and the
+    source caps on every event."""
+    def mod(p):
+        p.max_paths = 300
+    _compare_with_oracle(U, "g200k", 64, 3000, seed=13, params_mod=mod)

@@ -1,0 +1,6 @@
+"""uncalled_b200: B200-native implementation of the `uncalled map` hot path
+(skovaka/UNCALLED) behind a C-ABI (include/unc_b200.h)."""
+from ._native import UncError, build, default_params  # noqa: F401
+from .mapper import BatchMapper, Index, make_descs, paf_key  # noqa: F401
+
+__version__ = "0.1.0"

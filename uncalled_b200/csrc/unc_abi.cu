@@ -1,0 +1,572 @@
+// unc_abi.cu -- kernels + C-ABI (include/unc_b200.h) of the B200-native `uncalled map` path.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false --shared
+// This translation unit contains NO CPU implementation of the path: every compute entry
+// point launches the sm_100a kernels below or fails with a CUDA status.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "unc_device.cuh"
+#include "../../include/unc_b200.h"
+#include "unc_host_index.hpp"
+#include "unc_host_params.hpp"
+
+static_assert(sizeof(DevRec) == sizeof(unc_paf_rec), "DevRec must mirror unc_paf_rec");
+static_assert(sizeof(DevReadDesc) == 32, "DevReadDesc layout");
+
+// ------------------------------------------------------------------ kernels
+
+#define K2_WARPS 8
+#define K2_THREADS (K2_WARPS * 32)
+
+struct K2Smem {
+    K2Tables tb;
+    K2Shared sh[K2_WARPS];
+};
+
+__global__ void k_kmer_ranges(DevIndex ix, uint2 *out) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < UNC_NKMER) out[k] = unc_kmer_range_compute(ix, k);
+}
+
+__global__ void __launch_bounds__(128) k1_events(DevBatch B, DevParams p) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < B.n_reads) unc_k1_read(B, p, r);
+}
+
+// Persistent warp-per-read mapper.  Each CTA stages the pore model, the 1024 k-mer FM ranges
+// and the thresholds in shared memory; each warp then pulls reads from a global queue.
+__global__ void __launch_bounds__(K2_THREADS, 2)
+k2_map(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t ckey_stride, size_t order_stride,
+       size_t clu_stride, size_t dir_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K2Smem *sm = (K2Smem *) smem_raw;
+    for (u32 k = threadIdx.x; k < UNC_NKMER; k += blockDim.x) {
+        sm->tb.lv_mean[k] = ix.lv_mean[k];
+        sm->tb.lv_var2[k] = ix.lv_var2[k];
+        sm->tb.lognorm[k] = ix.lognorm[k];
+        sm->tb.kmer_range[k] = ix.kmer_range[k];
+    }
+    if (threadIdx.x < 64) sm->tb.thresh[threadIdx.x] = ix.thresh[threadIdx.x];
+    __syncthreads();
+
+    const u32 warp = threadIdx.x >> 5;
+    const size_t slot = (size_t) blockIdx.x * K2_WARPS + warp;
+    DevWork W;
+    W.paths = W0.paths + slot * paths_stride;
+    W.ckey = W0.ckey + slot * ckey_stride;
+    W.order = W0.order + slot * order_stride;
+    W.clu = W0.clu + slot * clu_stride;
+    W.dir = W0.dir + slot * dir_stride;
+    W.max_blocks = W0.max_blocks;
+    K2Shared *sh = &sm->sh[warp];
+    for (;;) {
+        u32 r = 0;
+        if ((threadIdx.x & 31) == 0) r = atomicAdd(B.queue, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= B.n_reads) break;
+        unc_k2_map_read(ix, p, B, W, sh, &sm->tb, r);
+    }
+}
+
+__global__ void k_match_probs(DevIndex ix, float event, float *out) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < UNC_NKMER) out[k] = unc_match_prob(event, ix.lv_mean[k], ix.lv_var2[k], ix.lognorm[k]);
+}
+
+__global__ void k_fm_neighbors(DevIndex ix, u32 n, const u64 *st, const u64 *en, const u8 *base, u64 *ost, u64 *oen) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 ns[4], ne[4], nb = 0;
+    unc_neighbors(ix, (u32) st[i], (u32) en[i], 1u << base[i], ns, ne, &nb);
+    ost[i] = ns[base[i]];
+    oen[i] = ne[base[i]];
+}
+
+__global__ void k_fm_sa(DevIndex ix, u32 n, const u64 *rows, u64 *out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 a = 0, b = 0;
+    // widen like the reference: sa[0] = (u64)-1
+    u32 v = unc_sa(ix, (u32) rows[i], &a, &b);
+    out[i] = v;
+}
+
+// ------------------------------------------------------------------ host state
+
+static thread_local std::string g_err;
+static int g_device = 0;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (x);                                                                         \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(UNC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e));                  \
+    } while (0)
+
+struct unc_index {
+    HostIndex h;
+    DevIndex ix;
+    int device = 0;
+    std::vector<uint2> kmer_range;  // host copy
+    void *d_bwt = nullptr, *d_sa = nullptr, *d_kr = nullptr, *d_model = nullptr, *d_thresh = nullptr;
+    void *d_seq_off = nullptr, *d_seq_len = nullptr;
+    size_t device_bytes = 0;
+};
+
+struct unc_pool {
+    const unc_index *idx = nullptr;
+    unc_params prm;
+    DevParams dp;
+    uint32_t max_reads = 0;
+    uint64_t max_samples = 0;
+    uint32_t ev_stride = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // batch buffers
+    void *d_samples = nullptr;
+    DevReadDesc *d_reads = nullptr, *h_reads = nullptr;
+    float *d_events = nullptr, *d_normed = nullptr, *d_scale = nullptr, *d_shift = nullptr, *d_mel = nullptr;
+    u32 *d_n_events = nullptr, *d_queue = nullptr;
+    DevRec *d_out = nullptr;
+    unc_paf_rec *h_out = nullptr;  // pinned staging
+    // workspaces
+    DevWork W;
+    size_t paths_stride = 0, ckey_stride = 0, order_stride = 0, clu_stride = 0, dir_stride = 0;
+    uint32_t n_slots = 0, grid = 0;
+    size_t smem = 0;
+    unc_timing last;
+};
+
+extern "C" {
+
+const char *unc_strerror(int s) {
+    switch (s) {
+        case UNC_OK: return "ok";
+        case UNC_E_ARG: return "bad argument";
+        case UNC_E_IO: return "index I/O error";
+        case UNC_E_CUDA: return "CUDA error";
+        case UNC_E_NO_DEVICE: return "no CUDA device";
+        case UNC_E_TOO_LARGE: return "index or batch too large for the device image";
+        case UNC_E_NOMEM: return "out of memory";
+        case UNC_E_OVERFLOW: return "per-read device workspace overflow";
+    }
+    return "unknown status";
+}
+
+const char *unc_last_error(void) { return g_err.c_str(); }
+
+int unc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int unc_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(UNC_E_NO_DEVICE, "no CUDA device (the product has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(UNC_E_ARG, "device out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    g_device = device;
+    return UNC_OK;
+}
+
+int unc_params_default(unc_params *p) {
+    if (!p) return fail(UNC_E_ARG, "null params");
+    unc_fill_default_params(p);
+    return UNC_OK;
+}
+
+static int upload(void **dst, const void *src, size_t bytes, size_t pad, size_t *total) {
+    CUDA_TRY(cudaMalloc(dst, bytes + pad));
+    if (pad) CUDA_TRY(cudaMemset((char *) *dst + bytes, 0, pad));
+    CUDA_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    *total += bytes + pad;
+    return UNC_OK;
+}
+
+int unc_index_load(const char *bwa_prefix, const char *preset, const char *model_table_path, unc_index **out) {
+    if (!bwa_prefix || !out || !model_table_path) return fail(UNC_E_ARG, "null argument");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        return fail(UNC_E_NO_DEVICE, "no CUDA device (the product has no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(g_device));
+    unc_index *x = new unc_index();
+    x->device = g_device;
+    if (!hix_load_model(x->h, model_table_path) || !hix_load(x->h, bwa_prefix, preset ? preset : "default")) {
+        std::string e = x->h.error;
+        delete x;
+        return fail(UNC_E_IO, e);
+    }
+    HostIndex &h = x->h;
+    if (h.seq_len >= 0xFFFFFF00ull) {
+        delete x;
+        return fail(UNC_E_TOO_LARGE, "FM index longer than 2^32 rows is not supported by the u32 device image");
+    }
+    int rc;
+#define UP(dst, src, bytes, pad) if ((rc = upload(&(dst), (src), (bytes), (pad), &x->device_bytes)) != UNC_OK) { unc_index_free(x); return rc; }
+    UP(x->d_bwt, h.bwt.data(), h.bwt.size() * 4, 64);
+    UP(x->d_sa, h.sa32.data(), h.sa32.size() * 4, 16);
+    std::vector<float> model(3 * 1024);
+    std::copy(h.lv_mean.begin(), h.lv_mean.end(), model.begin());
+    std::copy(h.lv_var2.begin(), h.lv_var2.end(), model.begin() + 1024);
+    std::copy(h.lognorm.begin(), h.lognorm.end(), model.begin() + 2048);
+    UP(x->d_model, model.data(), model.size() * 4, 0);
+    UP(x->d_thresh, h.thresh, 64 * 4, 0);
+    std::vector<u64> so(h.offsets.begin(), h.offsets.end());
+    if (so.empty()) so.push_back(0);
+    std::vector<u32> sl(h.lens.begin(), h.lens.end());
+    if (sl.empty()) sl.push_back(0);
+    UP(x->d_seq_off, so.data(), so.size() * 8, 0);
+    UP(x->d_seq_len, sl.data(), sl.size() * 4, 0);
+#undef UP
+    if (cudaMalloc(&x->d_kr, 1024 * sizeof(uint2)) != cudaSuccess) { unc_index_free(x); return fail(UNC_E_CUDA, "cudaMalloc kmer ranges"); }
+    x->device_bytes += 1024 * sizeof(uint2);
+    DevIndex &ix = x->ix;
+    ix.bwt = (const uint4 *) x->d_bwt;
+    ix.sa = (const u32 *) x->d_sa;
+    ix.kmer_range = (const uint2 *) x->d_kr;
+    ix.lv_mean = (const float *) x->d_model;
+    ix.lv_var2 = ix.lv_mean + 1024;
+    ix.lognorm = ix.lv_mean + 2048;
+    ix.thresh = (const float *) x->d_thresh;
+    ix.primary = (u32) h.primary;
+    ix.seq_len = (u32) h.seq_len;
+    for (int i = 0; i < 5; i++) ix.L2[i] = (u32) h.L2[i];
+    ix.start_bits = 64 - __builtin_clzll(h.seq_len ? h.seq_len : 1);
+    k_kmer_ranges<<<4, 256>>>(ix, (uint2 *) x->d_kr);
+    x->kmer_range.resize(1024);
+    cudaError_t e = cudaMemcpy(x->kmer_range.data(), x->d_kr, 1024 * sizeof(uint2), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { unc_index_free(x); return fail(UNC_E_CUDA, std::string("k_kmer_ranges: ") + cudaGetErrorString(e)); }
+    *out = x;
+    return UNC_OK;
+}
+
+int unc_index_get_info(const unc_index *x, unc_index_info *info) {
+    if (!x || !info) return fail(UNC_E_ARG, "null argument");
+    info->n_rows = x->h.seq_len;
+    info->n_seqs = (int32_t) x->h.names.size();
+    info->device = x->device;
+    info->device_bytes = x->device_bytes;
+    info->n_kmer_groups = 1024;
+    return UNC_OK;
+}
+
+int unc_index_seq(const unc_index *x, int rid, const char **name, uint64_t *len) {
+    if (!x || rid < 0 || rid >= (int) x->h.names.size()) return fail(UNC_E_ARG, "rid out of range");
+    if (name) *name = x->h.names[rid].c_str();
+    if (len) *len = x->h.lens[rid];
+    return UNC_OK;
+}
+
+int unc_index_kmer_range(const unc_index *x, uint32_t kmer, uint64_t *start, uint64_t *end) {
+    if (!x || kmer >= 1024) return fail(UNC_E_ARG, "bad kmer");
+    *start = x->kmer_range[kmer].x;
+    *end = x->kmer_range[kmer].y;
+    return UNC_OK;
+}
+
+int unc_index_thresholds(const unc_index *x, float out[64]) {
+    if (!x || !out) return fail(UNC_E_ARG, "null argument");
+    memcpy(out, x->h.thresh, 64 * sizeof(float));
+    return UNC_OK;
+}
+
+void unc_index_free(unc_index *x) {
+    if (!x) return;
+    cudaFree(x->d_bwt); cudaFree(x->d_sa); cudaFree(x->d_kr); cudaFree(x->d_model); cudaFree(x->d_thresh);
+    cudaFree(x->d_seq_off); cudaFree(x->d_seq_len);
+    delete x;
+}
+
+int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_reads, uint64_t max_samples,
+                    unc_pool **out) {
+    if (!idx || !prm || !out || max_reads == 0 || max_samples == 0) return fail(UNC_E_ARG, "null/zero argument");
+    std::string err;
+    if (unc_check_params(*prm, err)) return fail(UNC_E_ARG, err);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    unc_pool *P = new unc_pool();
+    P->idx = idx;
+    P->prm = *prm;
+    P->dp = unc_make_dev_params(*prm, idx->h);
+    P->max_reads = max_reads;
+    P->max_samples = max_samples;
+    memset(&P->last, 0, sizeof(P->last));
+    int rc = UNC_OK;
+    auto bail = [&](int code, const std::string &m) { unc_pool_free(P); return fail(code, m); };
+#define PT(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return bail(UNC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } while (0)
+    PT(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 5; i++) PT(cudaEventCreate(&P->ev[i]));
+    cudaDeviceProp prop;
+    PT(cudaGetDeviceProperties(&prop, idx->device));
+    P->smem = sizeof(K2Smem);
+    PT(cudaFuncSetAttribute(k2_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
+    int per_sm = 0;
+    PT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_map, K2_THREADS, P->smem));
+    if (per_sm < 1) return bail(UNC_E_CUDA, "k2_map does not fit on an SM");
+    uint32_t grid = (uint32_t) prop.multiProcessorCount * (uint32_t) per_sm;
+    uint32_t need = (max_reads + K2_WARPS - 1) / K2_WARPS;
+    if (grid > need) grid = need;
+    // per-slot workspace sizes
+    const size_t maxp = prm->max_paths;
+    P->paths_stride = 2 * maxp * 8;   // uint4
+    P->ckey_stride = 2 * maxp;        // uint4
+    P->order_stride = 2 * maxp;       // u16
+    uint64_t longest = max_samples < 0xFFFFFFFFull ? max_samples : 0xFFFFFFFFull;
+    // seed clusters: at most a few per event in practice; blocks are >= half full after splits
+    uint64_t ev_cap = std::min<uint64_t>(prm->max_events, longest / 3 + 16);
+    uint64_t mb = std::max<uint64_t>(1024, ev_cap * 2);
+    mb = std::min<uint64_t>(mb, 1u << 17);
+    size_t per_slot = P->paths_stride * 16 + P->ckey_stride * 16 + P->order_stride * 2 + mb * (UNC_BLK * 32 + 16);
+    size_t free_b = 0, total_b = 0;
+    PT(cudaMemGetInfo(&free_b, &total_b));
+    size_t fixed = max_samples * 4 + (size_t) max_reads * (sizeof(DevReadDesc) + sizeof(DevRec) + 20) + (64u << 20);
+    P->ev_stride = 0;
+    if (free_b < fixed + per_slot * K2_WARPS) return bail(UNC_E_NOMEM, "not enough device memory for the pool");
+    size_t budget = (size_t) ((free_b - fixed) * 0.85);
+    while ((size_t) grid * K2_WARPS * per_slot > budget && grid > 1) grid--;
+    P->grid = grid;
+    P->n_slots = grid * K2_WARPS;
+    P->clu_stride = (size_t) mb * UNC_BLK * 2;
+    P->dir_stride = (size_t) mb + 1;
+    P->W.max_blocks = (u32) mb;
+    PT(cudaMalloc(&P->W.paths, (size_t) P->n_slots * P->paths_stride * 16));
+    PT(cudaMalloc(&P->W.ckey, (size_t) P->n_slots * P->ckey_stride * 16));
+    PT(cudaMalloc(&P->W.order, (size_t) P->n_slots * P->order_stride * 2));
+    PT(cudaMalloc(&P->W.clu, (size_t) P->n_slots * P->clu_stride * 16));
+    PT(cudaMalloc(&P->W.dir, (size_t) P->n_slots * P->dir_stride * 16));
+    PT(cudaMalloc(&P->d_samples, max_samples * 4));
+    PT(cudaMalloc(&P->d_reads, (size_t) max_reads * sizeof(DevReadDesc)));
+    PT(cudaMallocHost(&P->h_reads, (size_t) max_reads * sizeof(DevReadDesc)));
+    PT(cudaMalloc(&P->d_scale, (size_t) max_reads * 4));
+    PT(cudaMalloc(&P->d_shift, (size_t) max_reads * 4));
+    PT(cudaMalloc(&P->d_mel, (size_t) max_reads * 4));
+    PT(cudaMalloc(&P->d_n_events, (size_t) max_reads * 4));
+    PT(cudaMalloc(&P->d_queue, 4));
+    PT(cudaMalloc(&P->d_out, (size_t) max_reads * sizeof(DevRec)));
+    PT(cudaMallocHost(&P->h_out, (size_t) max_reads * sizeof(unc_paf_rec)));
+#undef PT
+    (void) rc;
+    *out = P;
+    return UNC_OK;
+}
+
+void unc_pool_free(unc_pool *P) {
+    if (!P) return;
+    cudaFree(P->W.paths); cudaFree(P->W.ckey); cudaFree(P->W.order); cudaFree(P->W.clu); cudaFree(P->W.dir);
+    cudaFree(P->d_samples); cudaFree(P->d_reads); cudaFreeHost(P->h_reads);
+    cudaFree(P->d_events); cudaFree(P->d_normed);
+    cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue);
+    cudaFree(P->d_out); cudaFreeHost(P->h_out);
+    for (int i = 0; i < 5; i++) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
+    if (P->stream) cudaStreamDestroy(P->stream);
+    delete P;
+}
+
+// validates descriptors, stages them, (re)allocates the events buffer; returns the sample span
+static int stage_reads(unc_pool *P, const unc_read_desc *reads, uint32_t n, uint64_t *span_bytes, uint32_t *max_n,
+                       bool want_normed) {
+    if (n == 0 || n > P->max_reads) return fail(UNC_E_ARG, "n_reads outside 1..max_reads");
+    uint64_t hi = 0;
+    uint32_t mx = 0;
+    uint32_t dtype = reads[0].dtype;
+    for (uint32_t i = 0; i < n; i++) {
+        if (reads[i].dtype != dtype || dtype > 1) return fail(UNC_E_ARG, "mixed or unknown dtype in a batch");
+        hi = std::max<uint64_t>(hi, reads[i].offset + reads[i].n_samples);
+        mx = std::max(mx, reads[i].n_samples);
+        DevReadDesc &d = P->h_reads[i];
+        d.offset = reads[i].offset; d.n_samples = reads[i].n_samples; d.dtype = reads[i].dtype;
+        d.cal_range = reads[i].cal_range; d.cal_offset = reads[i].cal_offset; d.cal_digit = reads[i].cal_digit;
+        d.pad = 0;
+    }
+    if (hi > P->max_samples) return fail(UNC_E_TOO_LARGE, "batch exceeds the pool's max_samples");
+    *span_bytes = hi * (dtype == UNC_DTYPE_F32 ? 4 : 2);
+    *max_n = mx;
+    uint32_t stride = (mx + 3u) & ~3u;
+    if (stride == 0) stride = 4;
+    if (stride > P->ev_stride || (want_normed && !P->d_normed)) {
+        if (stride > P->ev_stride) {
+            cudaFree(P->d_events); P->d_events = nullptr;
+            cudaFree(P->d_normed); P->d_normed = nullptr;
+            P->ev_stride = stride;
+            CUDA_TRY(cudaMalloc(&P->d_events, (size_t) P->max_reads * P->ev_stride * 4));
+        }
+        if (want_normed && !P->d_normed) CUDA_TRY(cudaMalloc(&P->d_normed, (size_t) P->max_reads * P->ev_stride * 4));
+    }
+    return UNC_OK;
+}
+
+static DevBatch make_batch(unc_pool *P, const void *d_samples, uint32_t n, bool normed) {
+    DevBatch B;
+    B.samples = d_samples;
+    B.reads = P->d_reads;
+    B.n_reads = n;
+    B.events = P->d_events;
+    B.normed = normed ? P->d_normed : nullptr;
+    B.ev_stride = P->ev_stride;
+    B.n_events = P->d_n_events;
+    B.scale = P->d_scale; B.shift = P->d_shift; B.mean_event_len = P->d_mel;
+    B.queue = P->d_queue;
+    B.out = P->d_out;
+    B.seq_offsets = (const u64 *) P->idx->d_seq_off;
+    B.seq_lens = (const u32 *) P->idx->d_seq_len;
+    B.n_seqs = (u32) P->idx->h.names.size();
+    B.l_pac = (u64) P->idx->h.l_pac;
+    return B;
+}
+
+static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, bool on_device,
+                     unc_paf_rec *out) {
+    if (!P || !reads || !samples || !out) return fail(UNC_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(P->idx->device));
+    uint64_t span = 0;
+    uint32_t mx = 0;
+    int rc = stage_reads(P, reads, n, &span, &mx, false);
+    if (rc) return rc;
+    cudaStream_t s = P->stream;
+    CUDA_TRY(cudaEventRecord(P->ev[0], s));
+    const void *d_samples = samples;
+    uint64_t h2d = (uint64_t) n * sizeof(DevReadDesc);
+    if (!on_device) {
+        CUDA_TRY(cudaMemcpyAsync(P->d_samples, samples, span, cudaMemcpyHostToDevice, s));
+        d_samples = P->d_samples;
+        h2d += span;
+    }
+    CUDA_TRY(cudaMemcpyAsync(P->d_reads, P->h_reads, (size_t) n * sizeof(DevReadDesc), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(P->d_queue, 0, 4, s));
+    CUDA_TRY(cudaEventRecord(P->ev[1], s));
+    DevBatch B = make_batch(P, d_samples, n, false);
+    k1_events<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(P->ev[2], s));
+    uint32_t grid = std::min<uint32_t>(P->grid, (n + K2_WARPS - 1) / K2_WARPS);
+    k2_map<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->ckey_stride, P->order_stride,
+                                             P->clu_stride, P->dir_stride);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(P->ev[3], s));
+    CUDA_TRY(cudaMemcpyAsync(P->h_out, P->d_out, (size_t) n * sizeof(DevRec), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(P->ev[4], s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    memcpy(out, P->h_out, (size_t) n * sizeof(unc_paf_rec));
+    unc_timing &t = P->last;
+    cudaEventElapsedTime(&t.h2d_ms, P->ev[0], P->ev[1]);
+    cudaEventElapsedTime(&t.k1_ms, P->ev[1], P->ev[2]);
+    cudaEventElapsedTime(&t.k2_ms, P->ev[2], P->ev[3]);
+    cudaEventElapsedTime(&t.d2h_ms, P->ev[3], P->ev[4]);
+    cudaEventElapsedTime(&t.total_ms, P->ev[0], P->ev[4]);
+    t.kernel_launches = 2;
+    t.h2d_bytes = h2d;
+    t.d2h_bytes = (uint64_t) n * sizeof(DevRec);
+    int worst = UNC_OK;
+    for (uint32_t i = 0; i < n; i++) if (out[i].status != 0) worst = UNC_E_OVERFLOW;
+    if (worst) return fail(worst, "a read overflowed its seed-cluster workspace (see unc_paf_rec.status)");
+    return UNC_OK;
+}
+
+int unc_map_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, unc_paf_rec *out) {
+    return run_batch(P, reads, n, samples, false, out);
+}
+
+int unc_map_batch_device(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *d_samples, unc_paf_rec *out) {
+    return run_batch(P, reads, n, d_samples, true, out);
+}
+
+int unc_events_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, uint32_t stride,
+                     float *events, float *normed, uint32_t *n_events, float *mean_event_len) {
+    if (!P || !reads || !samples) return fail(UNC_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(P->idx->device));
+    uint64_t span = 0;
+    uint32_t mx = 0;
+    int rc = stage_reads(P, reads, n, &span, &mx, true);
+    if (rc) return rc;
+    if (stride < mx) return fail(UNC_E_ARG, "stride smaller than the longest read");
+    cudaStream_t s = P->stream;
+    CUDA_TRY(cudaEventRecord(P->ev[0], s));
+    CUDA_TRY(cudaMemcpyAsync(P->d_samples, samples, span, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(P->d_reads, P->h_reads, (size_t) n * sizeof(DevReadDesc), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(P->ev[1], s));
+    DevBatch B = make_batch(P, P->d_samples, n, true);
+    k1_events<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(P->ev[2], s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<uint32_t> ne(n);
+    CUDA_TRY(cudaMemcpy(ne.data(), P->d_n_events, (size_t) n * 4, cudaMemcpyDeviceToHost));
+    if (n_events) memcpy(n_events, ne.data(), (size_t) n * 4);
+    if (mean_event_len) CUDA_TRY(cudaMemcpy(mean_event_len, P->d_mel, (size_t) n * 4, cudaMemcpyDeviceToHost));
+    if (events)
+        CUDA_TRY(cudaMemcpy2D(events, (size_t) stride * 4, P->d_events, (size_t) P->ev_stride * 4, (size_t) mx * 4, n,
+                              cudaMemcpyDeviceToHost));
+    if (normed)
+        CUDA_TRY(cudaMemcpy2D(normed, (size_t) stride * 4, P->d_normed, (size_t) P->ev_stride * 4, (size_t) mx * 4, n,
+                              cudaMemcpyDeviceToHost));
+    unc_timing &t = P->last;
+    memset(&t, 0, sizeof(t));
+    cudaEventElapsedTime(&t.h2d_ms, P->ev[0], P->ev[1]);
+    cudaEventElapsedTime(&t.k1_ms, P->ev[1], P->ev[2]);
+    t.total_ms = t.h2d_ms + t.k1_ms;
+    t.kernel_launches = 1;
+    t.h2d_bytes = span + (uint64_t) n * sizeof(DevReadDesc);
+    return UNC_OK;
+}
+
+int unc_match_probs(const unc_index *x, float event, float out[1024]) {
+    if (!x || !out) return fail(UNC_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(x->device));
+    float *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 1024 * 4));
+    k_match_probs<<<4, 256>>>(x->ix, event, d);
+    cudaError_t e = cudaMemcpy(out, d, 1024 * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(UNC_E_CUDA, cudaGetErrorString(e));
+    return UNC_OK;
+}
+
+int unc_fm_neighbors(const unc_index *x, uint32_t n, const uint64_t *start, const uint64_t *end, const uint8_t *base,
+                     uint64_t *ostart, uint64_t *oend) {
+    if (!x || !n) return fail(UNC_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(x->device));
+    u64 *ds, *de, *dos, *doe;
+    u8 *db;
+    CUDA_TRY(cudaMalloc(&ds, n * 8)); CUDA_TRY(cudaMalloc(&de, n * 8)); CUDA_TRY(cudaMalloc(&dos, n * 8));
+    CUDA_TRY(cudaMalloc(&doe, n * 8)); CUDA_TRY(cudaMalloc(&db, n));
+    cudaMemcpy(ds, start, n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(de, end, n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, base, n, cudaMemcpyHostToDevice);
+    k_fm_neighbors<<<(n + 127) / 128, 128>>>(x->ix, n, ds, de, db, dos, doe);
+    cudaMemcpy(ostart, dos, n * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(oend, doe, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(ds); cudaFree(de); cudaFree(dos); cudaFree(doe); cudaFree(db);
+    if (e != cudaSuccess) return fail(UNC_E_CUDA, cudaGetErrorString(e));
+    return UNC_OK;
+}
+
+int unc_fm_sa(const unc_index *x, uint32_t n, const uint64_t *rows, uint64_t *out) {
+    if (!x || !n) return fail(UNC_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(x->device));
+    u64 *dr, *dout;
+    CUDA_TRY(cudaMalloc(&dr, n * 8)); CUDA_TRY(cudaMalloc(&dout, n * 8));
+    cudaMemcpy(dr, rows, n * 8, cudaMemcpyHostToDevice);
+    k_fm_sa<<<(n + 127) / 128, 128>>>(x->ix, n, dr, dout);
+    cudaError_t e = cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dr); cudaFree(dout);
+    if (e != cudaSuccess) return fail(UNC_E_CUDA, cudaGetErrorString(e));
+    return UNC_OK;
+}
+
+int unc_pool_last_timing(const unc_pool *P, unc_timing *t) {
+    if (!P || !t) return fail(UNC_E_ARG, "null argument");
+    *t = P->last;
+    return UNC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1039 @@
+// unc_device.cuh -- device code of the B200-native `uncalled map` hot path.
+//
+//   K1  unc_k1_read()      thread-per-read event detection + whole-read normalisation stats
+//                          (reference src/event_detector.cpp:83-319, src/normalizer.cpp:31-44)
+//   K2  unc_k2_map_read()  warp-per-read mapper: pore-model scoring, FM-index path extension,
+//                          child sort/dedup, gap + fresh sources, seed clustering, PAF coords
+//                          (reference src/mapper.cpp:433-728, src/seed_tracker.cpp:56-262,
+//                           submods/bwa/bwt.c:53-163)
+//
+// Written against unc_warp.cuh so the same source runs under nvcc (sm_100a) and under the
+// CPU warp emulator used by the tests.  All arithmetic that the reference performs in
+// float/double is spelled with explicit round-to-nearest operations (no FMA contraction).
+#pragma once
+#include "unc_warp.cuh"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef int32_t i32;
+typedef uint64_t u64;
+
+#define UNC_NKMER 1024
+#define UNC_KMASK 0x3FFu
+#define UNC_SEED_LEN 22u
+#define UNC_RING 23u
+#define UNC_PATH_MASK 0x3FFFFFu
+#define UNC_PATH_TAIL 0x200000u
+#define UNC_INVALID 0x8000u     /* flag in the order[] array: path invalidated by dedup */
+#define UNC_BLK 32u             /* seed-cluster block capacity (one entry per lane) */
+
+// ------------------------------------------------------------------ device image
+
+struct DevIndex {
+    const uint4 *bwt;      // 64-byte Occ blocks as in the .bwt file: 4 x u64 counts, 8 x u32 BWT words
+    const u32 *sa;         // sampled SA (every 32 rows) narrowed to u32; sa[0] = 0xFFFFFFFF
+    const uint2 *kmer_range;  // 1024 x (start, end) FM ranges
+    const float *lv_mean, *lv_var2, *lognorm;  // pore model tables (complement order)
+    const float *thresh;   // 64 probability thresholds indexed by clzll(range length)
+    u32 primary, seq_len;
+    u32 L2[5];
+    u32 start_bits;        // bits needed to represent seq_len (radix-sort passes)
+};
+
+struct DevParams {
+    u32 max_rep_copy, max_paths, max_consec_stay, max_events, min_rep_len;
+    float max_stay_frac, min_seed_prob;
+    u32 min_map_len;
+    float min_mean_conf, min_top_conf;
+    float threshold1, threshold2, peak_height, min_mean, max_mean;
+    float bp_per_sec, sample_rate;
+    float tgt_mean, tgt_stdv;   // model means mean / stdv (normaliser target)
+};
+
+struct DevReadDesc {
+    u64 offset;
+    u32 n_samples, dtype;
+    float cal_range, cal_offset, cal_digit;
+    u32 pad;
+};
+
+struct DevRec {   // == unc_paf_rec
+    i32 mapped, fwd, rid, status;
+    u32 n_events, events_used, matches, n_clusters;
+    u64 rd_len, rd_st, rd_en, rf_st, rf_en, rf_len;
+    u64 n_children, n_sources, n_occ_blocks, n_sa_steps, n_seeds;
+};
+
+struct DevBatch {
+    const void *samples;
+    const DevReadDesc *reads;
+    u32 n_reads;
+    // K1 outputs
+    float *events;       // n_reads x ev_stride valid event means (raw, un-normalised)
+    float *normed;       // optional (may be null): normalised means
+    u32 ev_stride;
+    u32 *n_events;
+    float *scale, *shift, *mean_event_len;
+    // K2
+    u32 *queue;          // atomic read counter
+    DevRec *out;
+    const u64 *seq_offsets;  // .ann offsets / lens for translate_loc
+    const u32 *seq_lens;
+    u32 n_seqs;
+    u64 l_pac;
+};
+
+struct DevWork {   // per-slot (per-warp) workspaces; slot s uses [s*stride, (s+1)*stride)
+    uint4 *paths;      // 2 x max_paths x 8 uint4
+    uint4 *ckey;       // 2 x max_paths uint4 (radix ping-pong)
+    u16 *order;        // 2 x max_paths
+    uint4 *clu;        // max_blocks x 32 x 2 uint4
+    uint4 *dir;        // max_blocks
+    u32 max_blocks;
+};
+
+// ------------------------------------------------------------------ pore model
+
+// reference src/pore_model.hpp:163-165: float subtract, double square/divide/subtract, one
+// rounding to float.
+UNC_DEV float unc_match_prob(float samp, float mean, float var2, float lognorm) {
+    float d = f_sub(samp, mean);
+    double dd = (double) d;
+    double q = d_div(-d_mul(dd, dd), (double) var2);
+    return (float) d_sub(q, (double) lognorm);
+}
+
+// ------------------------------------------------------------------ FM index
+
+// count of 2-bit symbols equal to c in y (reference submods/bwa/bwt.c:98-105), as match bits
+UNC_DEV u64 unc_match_bits(u64 y, u32 c) {
+    return (((c & 2) ? y : ~y) >> 1) & ((c & 1) ? y : ~y) & 0x5555555555555555ull;
+}
+
+// Occ(k, c) for a row k that is NOT seq_len and NOT (u64)-1, given its 64-byte block already
+// in registers (b0,b1 = counts; b2,b3 = BWT words).  kk = k - (k >= primary).
+// Equivalent to reference submods/bwa/bwt.c:107-129 (masking the match bits of the partial
+// word instead of the data removes the need for the c==0 correction).
+UNC_DEV u32 unc_occ_in_block(uint4 b0, uint4 b1, uint4 b2, uint4 b3, u32 kk, u32 c) {
+    u32 cnt = (c == 0) ? b0.x : (c == 1) ? b0.z : (c == 2) ? b1.x : b1.z;  // low words of the u64 counts
+    u32 q = (kk & 127u) >> 5;  // index of the 64-bit word holding symbol kk
+    u64 w0 = ((u64) b2.x << 32) | b2.y, w1 = ((u64) b2.z << 32) | b2.w;
+    u64 w2 = ((u64) b3.x << 32) | b3.y, w3 = ((u64) b3.z << 32) | b3.w;
+    u64 part = ~((1ull << ((~kk & 31u) << 1)) - 1ull);
+    u64 m0 = q > 0 ? ~0ull : part;
+    u64 m1 = q > 1 ? ~0ull : (q == 1 ? part : 0ull);
+    u64 m2 = q > 2 ? ~0ull : (q == 2 ? part : 0ull);
+    u64 m3 = q == 3 ? part : 0ull;
+    cnt += d_popcll(unc_match_bits(w0, c) & m0);
+    cnt += d_popcll(unc_match_bits(w1, c) & m1);
+    cnt += d_popcll(unc_match_bits(w2, c) & m2);
+    cnt += d_popcll(unc_match_bits(w3, c) & m3);
+    return cnt;
+}
+
+struct OccBlock { uint4 b0, b1, b2, b3; };
+
+UNC_DEV OccBlock unc_load_block(const DevIndex &ix, u32 kk) {
+    const uint4 *p = ix.bwt + ((size_t) (kk >> 7) << 2);
+    OccBlock b;
+    b.b0 = d_ldg(p); b.b1 = d_ldg(p + 1); b.b2 = d_ldg(p + 2); b.b3 = d_ldg(p + 3);
+    return b;
+}
+
+// bwt_occ (reference submods/bwa/bwt.c:107-129) for a single row
+UNC_DEV u32 unc_occ(const DevIndex &ix, u32 k, u32 c, u32 *n_blocks) {
+    if (k == ix.seq_len) return ix.L2[c + 1] - ix.L2[c];
+    if (k == 0xFFFFFFFFu) return 0;
+    u32 kk = k - (k >= ix.primary);
+    OccBlock b = unc_load_block(ix, kk);
+    (*n_blocks)++;
+    return unc_occ_in_block(b.b0, b.b1, b.b2, b.b3, kk, c);
+}
+
+// One backward-search step for all four bases at once: BwaIndex::get_neighbor
+// (reference src/bwa_index.hpp:158-162) over bwt_2occ (submods/bwa/bwt.c:132-163).
+// `want` has bit b set for each base whose range is needed.  Paths always have start >= 1.
+UNC_DEV void unc_neighbors(const DevIndex &ix, u32 start, u32 end, u32 want, u32 ns[4], u32 ne[4], u32 *n_blocks) {
+    u32 k = start - 1, l = end;
+    u32 kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
+    bool l_is_end = (l == ix.seq_len);
+    OccBlock bk = unc_load_block(ix, kk);
+    (*n_blocks)++;
+    OccBlock bl = bk;
+    if (!l_is_end && (ll >> 7) != (kk >> 7)) { bl = unc_load_block(ix, ll); (*n_blocks)++; }
+#pragma unroll
+    for (u32 c = 0; c < 4; c++) {
+        if (!((want >> c) & 1u)) continue;
+        u32 ok = unc_occ_in_block(bk.b0, bk.b1, bk.b2, bk.b3, kk, c);
+        u32 ol = l_is_end ? (ix.L2[c + 1] - ix.L2[c]) : unc_occ_in_block(bl.b0, bl.b1, bl.b2, bl.b3, ll, c);
+        ns[c] = ix.L2[c] + ok + 1;
+        ne[c] = ix.L2[c] + ol;
+    }
+}
+
+// bwt_sa (reference submods/bwa/bwt.c:86-96) with bwt_invPsi (:53-59); sa_intv == 32
+UNC_DEV u32 unc_sa(const DevIndex &ix, u32 k, u32 *n_steps, u32 *n_blocks) {
+    u32 steps = 0;
+    while (k & 31u) {
+        ++steps;
+        u32 x = k - (k > ix.primary);
+        const u32 *wp = (const u32 *) ix.bwt + (((size_t) (x >> 7)) << 4) + 8 + ((x & 0x7fu) >> 4);
+        u32 c = (d_ldg(wp) >> ((~x & 0xfu) << 1)) & 3u;
+        u32 r = ix.L2[c] + unc_occ(ix, k, c, n_blocks);
+        k = (k == ix.primary) ? 0u : r;
+    }
+    *n_steps += steps;
+    return steps + d_ldg(ix.sa + (k >> 5));
+}
+
+// The 1024 k-mer FM ranges (reference src/bwa_index.hpp:124-132): get_base_range(head) -- whose
+// start is L2[b], NOT L2[b]+1 (:172-174) -- followed by four get_neighbor steps.
+UNC_DEV uint2 unc_kmer_range_compute(const DevIndex &ix, u32 kmer) {
+    u32 head = (kmer >> 8) & 3u;
+    u32 st = ix.L2[head], en = ix.L2[head + 1];
+    u32 nb = 0;
+    for (u32 i = 1; i < 5; i++) {
+        u32 base = (kmer >> (2 * (4 - i))) & 3u;
+        u32 ok = unc_occ(ix, st - 1u, base, &nb), ol = unc_occ(ix, en, base, &nb);
+        st = ix.L2[base] + ok + 1u;
+        en = ix.L2[base] + ol;
+    }
+    return make_uint2(st, en);
+}
+
+// ------------------------------------------------------------------ K1: events + normalisation
+
+struct DevDetector {
+    u32 masked_to;
+    i32 peak_pos;
+    float peak_value;
+    int valid_peak;
+};
+
+// reference src/event_detector.cpp:174-219 (compute_tstat), exact mixed precision
+UNC_DEV float unc_tstat(const double *sum, const double *sumsq, u32 t, u32 buf_mid, u32 w) {
+    const float wf = (float) w;
+    if (t <= 2 * w) return 0.0f;
+    u32 i = buf_mid % 13u, st = (buf_mid - w) % 13u, en = (buf_mid + w) % 13u;
+    double sum1 = d_sub(sum[i], sum[st]);
+    double sumsq1 = d_sub(sumsq[i], sumsq[st]);
+    float sum2 = (float) d_sub(sum[en], sum[i]);
+    float sumsq2 = (float) d_sub(sumsq[en], sumsq[i]);
+    float mean1 = (float) d_div(sum1, (double) wf);
+    float mean2 = f_div(sum2, wf);
+    float m1sq = f_mul(mean1, mean1), m2sq = f_mul(mean2, mean2);
+    float q2 = f_div(sumsq2, wf);
+    double cv = d_sub(d_add(d_sub(d_div(sumsq1, (double) wf), (double) m1sq), (double) q2), (double) m2sq);
+    float combined_var = (float) cv;
+    combined_var = fmaxf(combined_var, 1.17549435e-38f);
+    float delta = f_sub(mean2, mean1);
+    return f_div(fabsf(delta), f_sqrt(f_div(combined_var, wf)));
+}
+
+// reference src/event_detector.cpp:221-279 (peak_detect).  `is_short` selects the branch that
+// lets the short detector mask/reset the long one.
+UNC_DEV bool unc_peak(DevDetector &d, DevDetector &longd, bool is_short, float cur, u32 buf_mid, u32 wlen,
+                      float threshold, float peak_height) {
+    if (d.masked_to >= buf_mid) return false;
+    if (d.peak_pos == -1) {
+        if (cur < d.peak_value) {
+            d.peak_value = cur;
+        } else if (f_sub(cur, d.peak_value) > peak_height) {
+            d.peak_value = cur;
+            d.peak_pos = (i32) buf_mid;
+        }
+    } else {
+        if (cur > d.peak_value) {
+            d.peak_value = cur;
+            d.peak_pos = (i32) buf_mid;
+        }
+        if (is_short) {
+            if (d.peak_value > threshold) {
+                longd.masked_to = (u32) d.peak_pos + wlen;
+                longd.peak_pos = -1;
+                longd.peak_value = 3.402823466e+38f;
+                longd.valid_peak = 0;
+            }
+        }
+        if (f_sub(d.peak_value, cur) > peak_height && d.peak_value > threshold) d.valid_peak = 1;
+        if (d.valid_peak && (buf_mid - (u32) d.peak_pos) > wlen / 2) {
+            d.peak_pos = -1;
+            d.peak_value = cur;
+            d.valid_peak = 0;
+            return true;
+        }
+    }
+    return false;
+}
+
+struct DevEvdt {
+    double sum[13], sumsq[13];
+    u32 t, evt_st;
+    double evt_st_sum, evt_st_sumsq;
+    float len_sum;
+    u32 total_events;
+    DevDetector sd, ld;
+};
+
+UNC_DEV void unc_evdt_reset(DevEvdt &e) {
+    for (int i = 0; i < 13; i++) { e.sum[i] = 0.0; e.sumsq[i] = 0.0; }
+    e.t = 1;
+    e.evt_st = 0;
+    e.evt_st_sum = e.evt_st_sumsq = 0.0;
+    e.len_sum = 0.0f;
+    e.total_events = 0;
+    e.sd.masked_to = 0; e.sd.peak_pos = -1; e.sd.peak_value = 3.402823466e+38f; e.sd.valid_peak = 0;
+    e.ld = e.sd;
+}
+
+// reference src/event_detector.cpp:83-112 (add_sample) + :296-319 (create_event).
+// Returns true and sets *mean when a valid event (min_mean <= mean <= max_mean) is emitted.
+UNC_DEV bool unc_evdt_add(DevEvdt &e, const DevParams &p, float s, float *mean_out) {
+    u32 t_mod = e.t % 13u;
+    u32 prev = t_mod > 0 ? t_mod - 1 : 12u;
+    float ss = f_mul(s, s);
+    e.sum[t_mod] = d_add(e.sum[prev], (double) s);
+    e.sumsq[t_mod] = d_add(e.sumsq[prev], (double) ss);
+    e.t++;
+    u32 buf_mid = e.t - 6u - 1u;
+    float t1 = unc_tstat(e.sum, e.sumsq, e.t, buf_mid, 3u);
+    float t2 = unc_tstat(e.sum, e.sumsq, e.t, buf_mid, 6u);
+    bool p1 = unc_peak(e.sd, e.ld, true, t1, buf_mid, 3u, p.threshold1, p.peak_height);
+    bool p2 = unc_peak(e.ld, e.ld, false, t2, buf_mid, 6u, p.threshold2, p.peak_height);
+    if (!(p1 || p2)) return false;
+    u32 evt_en = buf_mid - 3u + 1u;
+    u32 eb = evt_en % 13u;
+    u32 length = (u32) (float) (evt_en - e.evt_st);
+    float mean = (float) d_div(d_sub(e.sum[eb], e.evt_st_sum), (double) length);
+    e.evt_st = evt_en;
+    e.evt_st_sum = e.sum[eb];
+    e.evt_st_sumsq = e.sumsq[eb];
+    e.len_sum = f_add(e.len_sum, (float) length);
+    e.total_events++;
+    *mean_out = mean;
+    return mean >= p.min_mean && mean <= p.max_mean;
+}
+
+// calibrated pA sample i of a read (reference src/read_buffer.cpp:239-242 for raw i16 input)
+UNC_DEV float unc_sample(const void *samples, const DevReadDesc &rd, u32 i) {
+    if (rd.dtype == 0) return d_ldg((const float *) samples + rd.offset + i);
+    u16 raw = (u16) d_ldg((const int16_t *) samples + rd.offset + i);
+    return f_div(f_mul(rd.cal_range, f_add((float) raw, rd.cal_offset)), rd.cal_digit);
+}
+
+// One read, one thread.  Writes the read's valid event means, their count, the normaliser's
+// scale/shift (reference src/normalizer.cpp:31-44 + :114-118) and mean_event_len
+// (reference src/event_detector.cpp:151-153).
+UNC_DEV void unc_k1_read(const DevBatch &B, const DevParams &p, u32 r) {
+    DevReadDesc rd = B.reads[r];
+    DevEvdt e;
+    unc_evdt_reset(e);
+    float *ev = B.events + (size_t) r * B.ev_stride;
+    u32 ne = 0;
+    for (u32 i = 0; i < rd.n_samples; i++) {
+        float mean;
+        if (unc_evdt_add(e, p, unc_sample(B.samples, rd, i), &mean)) ev[ne++] = mean;
+    }
+    B.n_events[r] = ne;
+    B.mean_event_len[r] = f_div(e.len_sum, (float) e.total_events);
+    float scale = 0.0f, shift = 0.0f;
+    if (ne > 0) {
+        double mean = 0.0;
+        for (u32 i = 0; i < ne; i++) mean = d_add(mean, (double) ev[i]);
+        mean = d_div(mean, (double) ne);
+        double varsum = 0.0;
+        for (u32 i = 0; i < ne; i++) {
+            double d = d_sub((double) ev[i], mean);
+            varsum = d_add(varsum, d_mul(d, d));
+        }
+        scale = (float) d_div((double) p.tgt_stdv, d_sqrt(d_div(varsum, (double) ne)));
+        shift = (float) d_sub((double) p.tgt_mean, d_mul((double) scale, mean));
+        if (B.normed) {
+            float *nm = B.normed + (size_t) r * B.ev_stride;
+            for (u32 i = 0; i < ne; i++) nm[i] = f_add(f_mul(scale, ev[i]), shift);
+        }
+    }
+    B.scale[r] = scale;
+    B.shift[r] = shift;
+}
+
+// ------------------------------------------------------------------ K2: seed tracker
+
+// A cluster entry is two uint4:  A = (ren_start, evt_en, ref_st, ren_end)  B = (evt_st, total_len, 0, 0)
+// std::set order (reference src/seed_tracker.cpp:97-102): ren_start descending, evt_en descending.
+UNC_DEV bool clu_less(u32 as, u32 ae, u32 bs, u32 be) { return as > bs || (as == bs && ae > be); }
+
+struct Clu { u32 ren_start, evt_en, ref_st, ren_end, evt_st, total_len; };
+
+struct Tracker {     // all fields warp-uniform (replicated in every lane)
+    uint4 *blocks;   // slot base: block b entry i at blocks[(b*32 + i)*2 + {0,1}]
+    uint4 *dir;      // sorted directory: (first ren_start, first evt_en, block id, count)
+    u32 nb, n_alloc, max_blocks;
+    u32 n_live, n_lens, top1, top2;
+    float len_sum;
+    Clu max_map;
+    u32 overflow;
+};
+
+UNC_DEV void trk_reset(Tracker &t) {
+    t.nb = 0; t.n_alloc = 0; t.n_live = 0; t.n_lens = 0; t.top1 = 0; t.top2 = 0;
+    t.len_sum = 0.0f;
+    t.max_map.ren_start = 1; t.max_map.ren_end = 0; t.max_map.ref_st = 0;
+    t.max_map.evt_st = 1; t.max_map.evt_en = 0; t.max_map.total_len = 0;  // NULL_ALN
+    t.overflow = 0;
+}
+
+UNC_DEV Clu trk_load(const Tracker &t, u32 blk, u32 i) {
+    uint4 a = t.blocks[((size_t) blk * UNC_BLK + i) * 2], b = t.blocks[((size_t) blk * UNC_BLK + i) * 2 + 1];
+    Clu c; c.ren_start = a.x; c.evt_en = a.y; c.ref_st = a.z; c.ren_end = a.w; c.evt_st = b.x; c.total_len = b.y;
+    return c;
+}
+UNC_DEV void trk_store(const Tracker &t, u32 blk, u32 i, const Clu &c) {
+    t.blocks[((size_t) blk * UNC_BLK + i) * 2] = make_uint4(c.ren_start, c.evt_en, c.ref_st, c.ren_end);
+    t.blocks[((size_t) blk * UNC_BLK + i) * 2 + 1] = make_uint4(c.evt_st, c.total_len, 0, 0);
+}
+
+// Global lower_bound of key (ks, ke): returns directory index d and position pos inside
+// block d (pos may equal the block's count => the bound is the first entry of block d+1).
+// On return *cnt_out = count of block d, and `mine` holds entry `lane` of block d (if lane < count).
+UNC_DEV void trk_lower_bound(const Tracker &t, u32 ks, u32 ke, u32 *d_out, u32 *pos_out, u32 *blk_out, u32 *cnt_out,
+                             Clu *mine) {
+    int lane = w_lane();
+    // number of directory entries whose first key is < key
+    u32 lo = 0, hi = t.nb, c = 0;
+    for (;;) {
+        u32 span = hi - lo;
+        if (span == 0) { c = lo; break; }
+        u32 step = (span + 31u) / 32u;
+        u32 idx = lo + (u32) lane * step;
+        bool less = false;
+        if (idx < hi) { uint4 e = t.dir[idx]; less = clu_less(e.x, e.y, ks, ke); }
+        u32 nl = (u32) d_popc(w_ballot(less));
+        if (step == 1) { c = lo + nl; break; }
+        if (nl == 0) { c = lo; break; }
+        u32 nlo = lo + (nl - 1) * step + 1;
+        u32 nhi = lo + nl * step; if (nhi > hi) nhi = hi;
+        lo = nlo; hi = nhi;
+    }
+    u32 d = c > 0 ? c - 1 : 0;
+    uint4 de = t.dir[d];
+    u32 blk = de.z, cnt = de.w;
+    Clu m; m.ren_start = 0; m.evt_en = 0; m.ref_st = 0; m.ren_end = 0; m.evt_st = 0; m.total_len = 0;
+    bool less = false;
+    if ((u32) lane < cnt) { m = trk_load(t, blk, (u32) lane); less = clu_less(m.ren_start, m.evt_en, ks, ke); }
+    *pos_out = (u32) d_popc(w_ballot(less));
+    *d_out = d; *blk_out = blk; *cnt_out = cnt; *mine = m;
+}
+
+// shift directory entries [from, nb) up by one (warp memmove, top-down)
+UNC_DEV void trk_dir_open(Tracker &t, u32 from) {
+    int lane = w_lane();
+    u32 n = t.nb - from;  // entries to move
+    for (u32 done = 0; done < n; done += 32) {
+        u32 chunk_hi = t.nb - done;                 // exclusive
+        u32 idx = chunk_hi - 1 - (u32) lane;        // process from the top
+        bool act = ((u32) lane < n - done) && ((u32) lane < 32);
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (act) e = t.dir[idx];
+        w_sync();
+        if (act) t.dir[idx + 1] = e;
+        w_sync();
+    }
+}
+// remove directory entry d (shift [d+1, nb) down by one)
+UNC_DEV void trk_dir_close(Tracker &t, u32 d) {
+    int lane = w_lane();
+    for (u32 base = d + 1; base < t.nb; base += 32) {
+        u32 idx = base + (u32) lane;
+        bool act = idx < t.nb;
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (act) e = t.dir[idx];
+        w_sync();
+        if (act) t.dir[idx - 1] = e;
+        w_sync();
+    }
+    t.nb--;
+}
+
+// std::set::erase of entry (d, pos)
+UNC_DEV void trk_erase(Tracker &t, u32 d, u32 pos) {
+    int lane = w_lane();
+    uint4 de = t.dir[d];
+    u32 blk = de.z, cnt = de.w;
+    Clu m; m.ren_start = 0; m.evt_en = 0;
+    bool have = (u32) lane < cnt;
+    if (have) m = trk_load(t, blk, (u32) lane);
+    w_sync();
+    if (have && (u32) lane > pos) trk_store(t, blk, (u32) lane - 1, m);
+    w_sync();
+    cnt--;
+    t.n_live--;
+    if (cnt == 0) {
+        trk_dir_close(t, d);
+    } else {
+        // new first key: entry that is now at slot 0
+        u32 src = pos == 0 ? 1u : 0u;
+        u32 fs = w_shfl(m.ren_start, (int) src), fe = w_shfl(m.evt_en, (int) src);
+        if (lane == 0) t.dir[d] = make_uint4(fs, fe, blk, cnt);
+        w_sync();
+    }
+}
+
+// std::set::insert (unique keys): returns false when an equivalent key is already present
+UNC_DEV bool trk_insert_unique(Tracker &t, const Clu &c) {
+    int lane = w_lane();
+    if (t.nb == 0) {
+        if (t.n_alloc >= t.max_blocks) { t.overflow = 1; return false; }
+        u32 blk = t.n_alloc++;
+        if (lane == 0) { trk_store(t, blk, 0, c); t.dir[0] = make_uint4(c.ren_start, c.evt_en, blk, 1); }
+        w_sync();
+        t.nb = 1; t.n_live++;
+        return true;
+    }
+    for (;;) {
+        u32 d, pos, blk, cnt; Clu m;
+        trk_lower_bound(t, c.ren_start, c.evt_en, &d, &pos, &blk, &cnt, &m);
+        // element at the bound
+        u32 bs, be; bool have_bound = true;
+        if (pos < cnt) { bs = w_shfl(m.ren_start, (int) pos); be = w_shfl(m.evt_en, (int) pos); }
+        else if (d + 1 < t.nb) { uint4 nx = t.dir[d + 1]; bs = nx.x; be = nx.y; }
+        else { have_bound = false; bs = be = 0; }
+        if (have_bound && bs == c.ren_start && be == c.evt_en) return false;
+        if (cnt < UNC_BLK) {
+            w_sync();
+            if ((u32) lane < cnt && (u32) lane >= pos) trk_store(t, blk, (u32) lane + 1, m);
+            if (lane == 0) trk_store(t, blk, pos, c);
+            w_sync();
+            u32 fs = pos == 0 ? c.ren_start : w_shfl(m.ren_start, 0);
+            u32 fe = pos == 0 ? c.evt_en : w_shfl(m.evt_en, 0);
+            if (lane == 0) t.dir[d] = make_uint4(fs, fe, blk, cnt + 1);
+            w_sync();
+            t.n_live++;
+            return true;
+        }
+        // full block: split the upper half into a new block, then retry
+        if (t.n_alloc >= t.max_blocks) { t.overflow = 1; return false; }
+        u32 nblk = t.n_alloc++;
+        if (lane >= 16) trk_store(t, nblk, (u32) lane - 16, m);
+        w_sync();
+        trk_dir_open(t, d + 1);
+        u32 s16 = w_shfl(m.ren_start, 16), e16 = w_shfl(m.evt_en, 16);
+        u32 s0 = w_shfl(m.ren_start, 0), e0 = w_shfl(m.evt_en, 0);
+        if (lane == 0) {
+            t.dir[d] = make_uint4(s0, e0, blk, 16);
+            t.dir[d + 1] = make_uint4(s16, e16, nblk, 16);
+        }
+        w_sync();
+        t.nb++;
+    }
+}
+
+// std::multiset<u32> all_lens_: only its size and two largest values are ever read
+// (reference src/seed_tracker.cpp:129-143).  Values only arrive by insert(v) or by replacing
+// one instance of `oldv` with a strictly larger `newv` (:199-203), so the top two can be
+// maintained exactly without storing the multiset.
+UNC_DEV void lens_insert(Tracker &t, u32 v) {
+    t.n_lens++;
+    if (v > t.top1) { t.top2 = t.top1; t.top1 = v; }
+    else if (v > t.top2) t.top2 = v;
+}
+UNC_DEV void lens_replace(Tracker &t, u32 oldv, u32 newv) {
+    if (oldv == t.top1) { t.top1 = newv; }                       // top2 unchanged (other copy or smaller)
+    else if (oldv == t.top2) { if (newv > t.top1) { t.top2 = t.top1; t.top1 = newv; } else t.top2 = newv; }
+    else { if (newv > t.top1) { t.top2 = t.top1; t.top1 = newv; } else if (newv > t.top2) t.top2 = newv; }
+}
+
+// SeedCluster::update (reference src/seed_tracker.cpp:56-73), growth truncated to u8
+UNC_DEV void clu_update(Clu &a, const Clu &ns) {
+    u32 growth = 0;
+    if (ns.ren_start < a.ren_end) {
+        if (ns.ren_end > a.ren_end) {
+            growth = (ns.ren_end - a.ren_end) & 0xFFu;
+            a.ren_start = ns.ren_start; a.ren_end = ns.ren_end;
+        } else {
+            a.ren_start = ns.ren_start;
+        }
+    } else {
+        growth = ns.total_len & 0xFFu;
+        a.ren_start = ns.ren_start; a.ren_end = ns.ren_end;
+    }
+    a.evt_en = ns.evt_en;
+    a.total_len += growth;
+}
+
+// SeedTracker::add_seed (reference src/seed_tracker.cpp:157-232), executed cooperatively by
+// the warp with uniform control flow.
+UNC_DEV void trk_add_seed(Tracker &t, const DevParams &p, u32 ref_en, u32 ref_len, u32 evt) {
+    Clu ns;
+    ns.ren_start = ref_en - ref_len + 1; ns.ren_end = ref_en; ns.ref_st = ns.ren_start;
+    ns.evt_st = evt; ns.evt_en = evt; ns.total_len = ref_len;
+    const u32 e2 = evt, r2 = ns.ren_start;
+    bool found = false; u32 md = 0, mpos = 0, best_len = 0;
+
+    if (t.nb > 0) {
+        u32 d, pos, blk, cnt; Clu m;
+        trk_lower_bound(t, ns.ren_start, ns.evt_en, &d, &pos, &blk, &cnt, &m);
+        int lane = w_lane();
+        bool broke = false;
+        u32 first = pos;
+        while (!broke && d < t.nb) {
+            bool valid = (u32) lane < cnt && (u32) lane >= first;
+            u32 e1 = m.evt_en, r1 = m.ren_start;
+            bool inr = valid && e1 <= e2 && (r2 - r1) <= (e2 - e1) && (r2 - r1) >= (e2 - e1) / 12u;
+            bool brk = valid && (r2 - r1) >= e2;
+            u32 m_inr = w_ballot(inr), m_brk = w_ballot(brk);
+            u32 cand = m_inr | m_brk;
+            while (cand) {
+                int l = d_ffs(cand) - 1;
+                cand &= cand - 1;
+                bool matched = false;
+                if ((m_inr >> l) & 1u) {
+                    u32 tl = w_shfl(m.total_len, l);
+                    if (!found || best_len < tl) { found = true; best_len = tl; md = d; mpos = (u32) l; matched = true; }
+                }
+                if (!matched && ((m_brk >> l) & 1u)) { broke = true; break; }
+            }
+            if (broke) break;
+            d++;
+            if (d < t.nb) {
+                uint4 de = t.dir[d];
+                blk = de.z; cnt = de.w; first = 0;
+                if ((u32) lane < cnt) m = trk_load(t, blk, (u32) lane);
+            }
+        }
+    }
+
+    if (found) {
+        uint4 de = t.dir[md];
+        Clu a = trk_load(t, de.z, mpos);
+        u32 prev_len = a.total_len;
+        clu_update(a, ns);
+        if (a.total_len != prev_len) {
+            t.len_sum = f_add(t.len_sum, (float) (a.total_len - prev_len));
+            lens_replace(t, prev_len, a.total_len);
+            if (a.total_len >= p.min_map_len && a.total_len > t.max_map.total_len) t.max_map = a;
+        }
+        trk_erase(t, md, mpos);
+        trk_insert_unique(t, a);
+    } else {
+        lens_insert(t, ns.total_len);
+        t.len_sum = f_add(t.len_sum, (float) ns.total_len);
+        if (ns.total_len >= p.min_map_len && ns.total_len > t.max_map.total_len) t.max_map = ns;
+        trk_insert_unique(t, ns);
+    }
+}
+
+// SeedTracker::get_final + check_map_conf (reference src/seed_tracker.cpp:129-143,259-262)
+UNC_DEV bool trk_get_final(const Tracker &t, const DevParams &p) {
+    if (t.max_map.total_len < p.min_map_len || t.n_lens < 2) return false;
+    float mean_len = f_div(t.len_sum, (float) t.n_live);
+    float second_len = (float) t.top2;
+    float sl = (float) t.max_map.total_len;
+    return (p.min_mean_conf > 0 && f_div(sl, mean_len) >= p.min_mean_conf) ||
+           (p.min_top_conf > 0 && f_div(sl, second_len) >= p.min_top_conf);
+}
+
+// ------------------------------------------------------------------ K2: mapper
+
+// Path record = 8 uint4 (128 B):
+//   q0 = (fm_start, fm_end, kmer | length<<16 | consec_stays<<24, event_moves)
+//   q1 = (seed_prob bits, sa_checked, 0, 0)
+//   q2..q7 = 23-float ring of cumulative log-probs since the path's source, slot = event % 23
+//            (the reference's prob_sums_ window, src/mapper.cpp:792-801, without the shift)
+struct K2Shared {          // per warp
+    float probs[UNC_NKMER];
+    u32 hist[256];
+    u32 flags[32];         // sources_added_ bits (reference src/mapper.cpp:88), kmer k -> word k>>5
+};
+struct K2Tables {          // per CTA
+    float lv_mean[UNC_NKMER], lv_var2[UNC_NKMER], lognorm[UNC_NKMER];
+    uint2 kmer_range[UNC_NKMER];
+    float thresh[64];
+};
+
+struct K2Counters { u64 n_children, n_sources, n_occ_blocks, n_sa_steps, n_seeds; };
+
+UNC_DEV uint4 *path_rec(uint4 *paths, u32 gen, u32 maxp, u32 idx) { return paths + ((size_t) gen * maxp + idx) * 8; }
+
+// PathBuffer::make_source (reference src/mapper.cpp:751-772)
+UNC_DEV void write_source(uint4 *rec, u32 st, u32 en, u32 kmer, float prob, u32 ev) {
+    rec[0] = make_uint4(st, en, kmer | (1u << 16), 1u);
+    rec[1] = make_uint4(f2u(prob), 0u, 0u, 0u);
+    float *ring = (float *) (rec + 2);
+    ring[(ev + 22u) % UNC_RING] = 0.0f;
+    ring[ev % UNC_RING] = prob;
+}
+
+// Mapper::event_to_bp (reference src/mapper.cpp:703-706)
+UNC_DEV u32 unc_event_to_bp(u32 evt_i, bool last, float mean_event_len, float bp_per_samp) {
+    float v = f_add(f_mul(f_mul((float) evt_i, mean_event_len), bp_per_samp), (float) (last ? 4 : 0));
+    return f_to_u32_x86(v);
+}
+
+// One read mapped by one warp.  reference src/mapper.cpp:188-200 (map_read) driving
+// :433-663 (map_next).  `sh`/`tb` are shared-memory scratch/tables; `W` the slot's workspaces.
+UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
+                             K2Shared *sh, const K2Tables *tb, u32 r) {
+    const int lane = w_lane();
+    const u32 maxp = p.max_paths;
+    const u32 n_ev = B.n_events[r];
+    const float scale = B.scale[r], shift = B.shift[r], mel = B.mean_event_len[r];
+    const float *events = B.events + (size_t) r * B.ev_stride;
+    const float source_prob = tb->thresh[0];
+    const float bp_per_samp = f_div(p.bp_per_sec, p.sample_rate);
+    K2Counters cn; cn.n_children = cn.n_sources = cn.n_occ_blocks = cn.n_sa_steps = cn.n_seeds = 0;
+    u32 my_blocks = 0, my_steps = 0;   // per-lane counters, reduced at the end
+
+    Tracker trk;
+    trk.blocks = W.clu; trk.dir = W.dir; trk.max_blocks = W.max_blocks;
+    trk_reset(trk);
+    sh->flags[lane] = 0;
+    w_sync();
+
+    u32 prev_size = 0, gen = 0, event_i = 0;
+    bool mapped = false;
+    u32 n_limit = n_ev < p.max_events ? n_ev : p.max_events;
+
+    for (; event_i < n_limit; event_i++) {
+        const float ev_raw = events[event_i];
+        const float event = f_add(f_mul(scale, ev_raw), shift);
+
+        // ---- A. pore-model probabilities (reference src/mapper.cpp:443-445)
+        for (u32 j = 0; j < 32; j++) {
+            u32 k = j * 32 + (u32) lane;
+            sh->probs[k] = unc_match_prob(event, tb->lv_mean[k], tb->lv_var2[k], tb->lognorm[k]);
+        }
+        w_sync();
+
+        uint4 *prev = W.paths + (size_t) gen * maxp * 8, *next = W.paths + (size_t) (gen ^ 1u) * maxp * 8;
+        const u16 *oprev = W.order + (size_t) gen * maxp;
+        u16 *onext = W.order + (size_t) (gen ^ 1u) * maxp;
+        uint4 *ckA = W.ckey, *ckB = W.ckey + maxp;
+        const u32 slot_prev = (event_i + 22u) % UNC_RING, slot_new = event_i % UNC_RING, slot_old = (event_i + 1u) % UNC_RING;
+
+        // ---- B. extend every previous path (reference src/mapper.cpp:455-524)
+        u32 nn = 0;
+        for (u32 base = 0; base < prev_size && nn < maxp; base += 32) {
+            u32 pi = base + (u32) lane;
+            bool act = pi < prev_size;
+            u32 oi = act ? oprev[pi] : UNC_INVALID;
+            bool valid = act && !(oi & UNC_INVALID);
+            const uint4 *prec = prev + (size_t) (oi & 0x7FFFu) * 8;
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+            if (valid) { q0 = prec[0]; q1 = prec[1]; }
+            u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
+            u32 moves = q0.w, sa_checked = q1.y;
+            float thr = 0.0f;
+            u32 want = 0; bool stay_ok = false;
+            float cprob[5]; u32 cst[5], cen[5], ckm[5];
+            if (valid) {
+                u32 len = en - st + 1u;
+                thr = tb->thresh[32 + d_clz(len)];
+                float pk = sh->probs[kmer];
+                stay_ok = stays < p.max_consec_stay && pk >= thr;
+                cprob[0] = pk; cst[0] = st; cen[0] = en; ckm[0] = kmer;
+#pragma unroll
+                for (u32 b = 0; b < 4; b++) {
+                    u32 nk = ((kmer << 2) & UNC_KMASK) | b;
+                    float pb = sh->probs[nk];
+                    ckm[b + 1] = nk; cprob[b + 1] = pb;
+                    if (!(pb < thr)) want |= 1u << b;   // `if (prob < thresh) continue;`
+                }
+            }
+            u32 cmask = stay_ok ? 1u : 0u;
+            if (want) {
+                u32 ns[4], ne[4];
+                unc_neighbors(ix, st, en, want, ns, ne, &my_blocks);
+#pragma unroll
+                for (u32 b = 0; b < 4; b++)
+                    if (((want >> b) & 1u) && ns[b] <= ne[b]) { cmask |= 2u << b; cst[b + 1] = ns[b]; cen[b + 1] = ne[b]; }
+            }
+            u32 cc = (u32) d_popc(cmask), total;
+            u32 off = w_exscan(cc, &total);
+            // sequential semantics of the full buffer: parent is reached iff the buffer was not
+            // yet full when the scan arrived at it
+            bool reached = valid && (nn + off < maxp);
+            if (reached && cc > 0) {
+                uint4 r2 = prec[2], r3 = prec[3], r4 = prec[4], r5 = prec[5], r6 = prec[6], r7 = prec[7];
+                const float *pring = (const float *) (prec + 2);
+                float prevC = pring[slot_prev], oldC = pring[slot_old];
+                u32 ci = nn + off;
+#pragma unroll
+                for (u32 j = 0; j < 5; j++) {
+                    if (!((cmask >> j) & 1u) || ci >= maxp) continue;
+                    u32 move = j > 0 ? 1u : 0u;
+                    u32 nlen = plen + (plen < UNC_SEED_LEN ? 1u : 0u);
+                    u32 nmoves = ((moves << 1) | move) & UNC_PATH_MASK;
+                    u32 nstays = move ? 0u : stays + 1u;
+                    float newC = f_add(prevC, cprob[j]);
+                    float sp;
+                    if (plen == UNC_SEED_LEN) { sp = f_div(f_sub(newC, oldC), 22.0f); nmoves |= UNC_PATH_TAIL; }
+                    else sp = f_div(newC, (float) nlen);
+                    u32 spb = f2u(sp);
+                    uint4 *crec = next + (size_t) ci * 8;
+                    crec[0] = make_uint4(cst[j], cen[j], ckm[j] | (nlen << 16) | (nstays << 24), nmoves);
+                    crec[1] = make_uint4(spb, sa_checked, 0u, 0u);
+                    crec[2] = r2; crec[3] = r3; crec[4] = r4; crec[5] = r5; crec[6] = r6; crec[7] = r7;
+                    ((float *) (crec + 2))[slot_new] = newC;
+                    // is_seed_valid(path_ended = false) of the child (reference src/mapper.cpp:842-863)
+                    u32 mc = (u32) d_popc(nmoves);
+                    u32 stay_count = (nlen - mc) & 0xFFu;
+                    bool seedable = nlen == UNC_SEED_LEN && sp >= p.min_seed_prob && cst[j] == cen[j] && (nmoves & 1u) &&
+                                    (float) stay_count <= f_mul(p.max_stay_frac, 22.0f);
+                    ckA[ci] = make_uint4(cst[j], cen[j], spb, ckm[j] | (seedable ? 1u << 10 : 0u) | (mc << 11) | (ci << 16));
+                    ci++;
+                }
+            }
+            // childless, not yet SA-checked parents emit their seeds now, in parent order
+            // (reference src/mapper.cpp:513-519 -> update_seeds(path, true))
+            bool ended = false;
+            if (reached && cc == 0 && !sa_checked) {
+                u32 mc = (u32) d_popc(moves);
+                u32 len = en - st + 1u;
+                ended = plen == UNC_SEED_LEN && u2f(q1.x) >= p.min_seed_prob &&
+                        ((len == 1 && (moves & 1u) && (float) ((plen - mc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f)) ||
+                         (len <= p.max_rep_copy && mc >= p.min_rep_len));
+            }
+            u32 m_end = w_ballot(ended);
+            while (m_end) {
+                int l = d_ffs(m_end) - 1;
+                m_end &= m_end - 1;
+                u32 s0 = w_shfl(st, l), s1 = w_shfl(en, l), mcl = (u32) d_popc(w_shfl(moves, l));
+                for (u32 rb = s0; rb <= s1; rb += 32) {
+                    u32 row = rb + (u32) lane;
+                    u32 sav = 0;
+                    bool have = row <= s1;
+                    if (have) sav = unc_sa(ix, row, &my_steps, &my_blocks);
+                    u32 nrow = s1 - rb + 1u; if (nrow > 32) nrow = 32;
+                    for (u32 j = 0; j < nrow; j++) {
+                        u32 sv = w_shfl(sav, (int) j);
+                        trk_add_seed(trk, p, ix.seq_len - sv, mcl, event_i - 1u);
+                        cn.n_seeds++;
+                    }
+                    if (s1 - rb < 32) break;   // also guards rb + 32 wrap
+                }
+            }
+            nn += total;
+            if (nn > maxp) nn = maxp;
+        }
+        const u32 nc = nn;
+        cn.n_children += nc;
+        w_sync();
+
+        u32 ns_added = 0;   // sources appended after the children
+        if (nc > 0) {
+            // ---- C. order children by (fm_start, fm_end, seed_prob, emission index)
+            //         (reference src/mapper.cpp:531 pdqsort + operator< :866-871)
+            uint4 *src = ckA, *dst = ckB;
+            for (u32 shiftb = 0; shiftb < ix.start_bits; shiftb += 8) {
+                for (u32 j = (u32) lane; j < 256; j += 32) sh->hist[j] = 0;
+                w_sync();
+                for (u32 base = 0; base < nc; base += 32) {
+                    u32 g = base + (u32) lane;
+                    if (g < nc) s_atomic_add(&sh->hist[(src[g].x >> shiftb) & 0xFFu], 1u);
+                }
+                w_sync();
+                // exclusive scan of the 256 bins (8 per lane)
+                u32 loc[8], sum = 0;
+#pragma unroll
+                for (u32 j = 0; j < 8; j++) { loc[j] = sh->hist[(u32) lane * 8 + j]; sum += loc[j]; }
+                u32 tot, basev = w_exscan(sum, &tot);
+#pragma unroll
+                for (u32 j = 0; j < 8; j++) { sh->hist[(u32) lane * 8 + j] = basev; basev += loc[j]; }
+                w_sync();
+                for (u32 base = 0; base < nc; base += 32) {
+                    u32 g = base + (u32) lane;
+                    bool a = g < nc;
+                    uint4 k = make_uint4(0, 0, 0, 0);
+                    if (a) k = src[g];
+                    u32 dg = a ? ((k.x >> shiftb) & 0xFFu) : 0x100u + (u32) lane;  // inactive lanes: unique digit
+                    u32 peers = w_match(dg);
+                    u32 rank = (u32) d_popc(peers & w_lanemask_lt());
+                    int leader = d_ffs(peers) - 1;
+                    u32 bpos = 0;
+                    if (a && lane == leader) bpos = s_atomic_add(&sh->hist[dg], (u32) d_popc(peers));
+                    bpos = w_shfl(bpos, leader);
+                    if (a) dst[bpos + rank] = k;
+                    w_sync();
+                }
+                uint4 *tmp = src; src = dst; dst = tmp;
+            }
+            // runs of equal fm_start: order by (fm_end, seed_prob, emission index)
+            for (u32 base = 0; base < nc; base += 32) {
+                u32 g = base + (u32) lane;
+                bool head = false;
+                if (g < nc) {
+                    u32 s = src[g].x;
+                    head = (g == 0 || src[g - 1].x != s) && (g + 1 < nc && src[g + 1].x == s);
+                }
+                if (head) {
+                    u32 s = src[g].x;
+                    u32 e = g + 1;
+                    while (e < nc && src[e].x == s) e++;
+                    for (u32 i = g + 1; i < e; i++) {
+                        uint4 key = src[i];
+                        float kp = u2f(key.z);
+                        u32 j = i;
+                        while (j > g) {
+                            uint4 o = src[j - 1];
+                            float op = u2f(o.z);
+                            bool gt = o.y > key.y || (o.y == key.y && (kp < op || (!(op < kp) && (o.w >> 16) > (key.w >> 16))));
+                            if (!gt) break;
+                            src[j] = o;
+                            j--;
+                        }
+                        src[j] = key;
+                    }
+                }
+                w_sync();
+            }
+            const uint4 *sk = src;   // sorted keys
+
+            // ---- D. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603)
+            u32 carry_kmer = UNC_NKMER, carry_maxend = 0;
+            for (u32 base = 0; base < nc; base += 32) {
+                u32 g = base + (u32) lane;
+                bool a = g < nc;
+                uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+                if (a) cur = sk[g];
+                bool has_next = a && g + 1 < nc;
+                if (has_next) nxt = sk[g + 1];
+                u32 kmer = cur.w & UNC_KMASK;
+                u32 pk = w_shfl_up(kmer, 1);
+                if (lane == 0) pk = carry_kmer;
+                bool run_start = a && kmer != pk;
+                bool same_next = has_next && (nxt.w & UNC_KMASK) == kmer;
+                bool dup = has_next && nxt.x == cur.x && nxt.y == cur.y;
+                bool prob_ok = a && sh->probs[kmer] >= source_prob;
+                // segmented inclusive max-scan of fm_end over the run
+                u32 mx = cur.y; bool hd = run_start || !a;
+                if (lane == 0 && a && !run_start) { mx = mx > carry_maxend ? mx : carry_maxend; }
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 omx = w_shfl_up(mx, d); u32 ohd = w_shfl_up(hd ? 1u : 0u, d);
+                    if (lane >= d && !hd) { mx = omx > mx ? omx : mx; hd = ohd != 0; }
+                }
+                uint2 kr = tb->kmer_range[kmer];
+                bool begin_v = run_start && prob_ok && kr.x <= cur.x - 1u;
+                u32 as = mx + 1u, ae = same_next ? nxt.x - 1u : kr.y;
+                bool after_v = a && !dup && prob_ok && as <= ae;
+                u32 cnt = (begin_v ? 1u : 0u) + (after_v ? 1u : 0u), tot;
+                u32 off = w_exscan(cnt, &tot);
+                u32 sidx = ns_added + off;    // sources (that would be) added before this element
+                // sources_added_[kmer] is set at a run start while the buffer is not full
+                if (run_start && prob_ok && nc + sidx < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
+                if (begin_v && nc + sidx < maxp) {
+                    write_source(next + (size_t) (nc + sidx) * 8, kr.x, cur.x - 1u, kmer, sh->probs[kmer], event_i);
+                    onext[nc + sidx] = (u16) (nc + sidx);
+                }
+                u32 sidx2 = sidx + (begin_v ? 1u : 0u);
+                if (after_v && nc + sidx2 < maxp) {
+                    write_source(next + (size_t) (nc + sidx2) * 8, as, ae, kmer, sh->probs[kmer], event_i);
+                    onext[nc + sidx2] = (u16) (nc + sidx2);
+                }
+                ns_added += tot;
+                if (nc + ns_added > maxp) ns_added = maxp - nc;
+                u32 emit = cur.w >> 16;
+                if (a) onext[g] = (u16) (emit | (dup ? UNC_INVALID : 0u));
+                // update_seeds(child, false): unique, move-headed, full-length, probable paths
+                bool seed = a && !dup && ((cur.w >> 10) & 1u);
+                u32 sav = 0;
+                if (seed) {
+                    next[(size_t) emit * 8 + 1].y = 1u;   // sa_checked_
+                    sav = unc_sa(ix, cur.x, &my_steps, &my_blocks);
+                }
+                u32 m_seed = w_ballot(seed);
+                while (m_seed) {
+                    int l = d_ffs(m_seed) - 1;
+                    m_seed &= m_seed - 1;
+                    u32 sv = w_shfl(sav, l), mc = (w_shfl(cur.w, l) >> 11) & 0x1Fu;
+                    trk_add_seed(trk, p, ix.seq_len - sv, mc, event_i);
+                    cn.n_seeds++;
+                }
+                carry_kmer = w_shfl(kmer, 31);
+                carry_maxend = w_shfl(mx, 31);
+            }
+        }
+        w_sync();
+        nn = nc + ns_added;
+
+        // ---- E. fresh sources for every sufficiently probable k-mer without one
+        //         (reference src/mapper.cpp:605-624)
+        for (u32 j = 0; j < 32 && nn < maxp; j++) {
+            u32 k = j * 32 + (u32) lane;
+            u32 fw = sh->flags[j];
+            uint2 kr = tb->kmer_range[k];
+            float pk = sh->probs[k];
+            bool add = !((fw >> lane) & 1u) && pk >= source_prob && kr.x <= kr.y;
+            u32 m_add = w_ballot(add);
+            u32 room = maxp - nn;
+            u32 visited = 0xFFFFFFFFu;
+            if ((u32) d_popc(m_add) >= room) {
+                // the room-th add fills the buffer; k-mers after it are never visited
+                u32 mm = m_add;
+                for (u32 q = 1; q < room; q++) mm &= mm - 1;
+                int last = d_ffs(mm) - 1;
+                visited = last == 31 ? 0xFFFFFFFFu : ((2u << last) - 1u);
+                m_add &= visited;
+            }
+            u32 rank = (u32) d_popc(m_add & w_lanemask_lt());
+            if ((m_add >> lane) & 1u) {
+                write_source(next + (size_t) (nn + rank) * 8, kr.x, kr.y, k, pk, event_i);
+                onext[nn + rank] = (u16) (nn + rank);
+            }
+            w_sync();
+            if (lane == 0) sh->flags[j] = fw & ~visited;
+            nn += (u32) d_popc(m_add);
+        }
+        w_sync();
+        cn.n_sources += nn - nc;
+        prev_size = nn;
+        gen ^= 1u;
+
+        // ---- F. confident mapping? (reference src/mapper.cpp:631-653)
+        if (trk.overflow) break;
+        if (trk_get_final(trk, p)) { mapped = true; break; }
+    }
+
+    // ---- PAF coordinates (reference src/mapper.cpp:708-728, bwa_index.hpp:213-220)
+    for (int d = 16; d > 0; d >>= 1) { my_blocks += w_shfl(my_blocks, lane ^ d); my_steps += w_shfl(my_steps, lane ^ d); }
+    if (lane == 0) {
+        DevRec o;
+        o.mapped = 0; o.fwd = 0; o.rid = -1; o.status = trk.overflow ? -7 : 0;
+        o.n_events = n_ev; o.events_used = event_i; o.matches = 0; o.n_clusters = trk.n_live;
+        o.rd_len = f_to_u64(f_mul((float) (u64) B.reads[r].n_samples, bp_per_samp));
+        o.rd_st = o.rd_en = o.rf_st = o.rf_en = o.rf_len = 0;
+        if (mapped) {
+            const Clu &sc = trk.max_map;
+            bool fwd = sc.ref_st < ix.seq_len / 2u;
+            u64 sa_st = fwd ? (u64) sc.ref_st : (u64) ix.seq_len - ((u64) sc.ren_end + 4u);
+            o.rd_st = unc_event_to_bp(sc.evt_st - UNC_SEED_LEN, false, mel, bp_per_samp);
+            o.rd_en = unc_event_to_bp(sc.evt_en, true, mel, bp_per_samp);
+            o.rd_len = unc_event_to_bp(event_i, true, mel, bp_per_samp);
+            // bns_pos2rid (reference submods/bwa/bntseq.c:354-368)
+            int rid = -1;
+            if ((long long) sa_st < (long long) B.l_pac) {
+                int left = 0, mid = 0, right = (int) B.n_seqs;
+                while (left < right) {
+                    mid = (left + right) >> 1;
+                    if (sa_st >= B.seq_offsets[mid]) {
+                        if (mid == (int) B.n_seqs - 1) break;
+                        if (sa_st < B.seq_offsets[mid + 1]) break;
+                        left = mid + 1;
+                    } else right = mid;
+                }
+                rid = mid;
+            }
+            u64 rf_st = 0, rf_len = 0;
+            if (rid >= 0) { rf_st = sa_st - B.seq_offsets[rid]; rf_len = B.seq_lens[rid]; }
+            o.mapped = 1; o.fwd = fwd ? 1 : 0; o.rid = rid;
+            o.rf_st = rf_st; o.rf_len = rf_len;
+            o.rf_en = rf_st + ((u64) sc.ren_end - (u64) sc.ref_st + 5u);
+            o.matches = (sc.total_len + 4u) & 0xFFFFu;
+        }
+        o.n_children = cn.n_children; o.n_sources = cn.n_sources; o.n_seeds = cn.n_seeds;
+        o.n_occ_blocks = my_blocks; o.n_sa_steps = my_steps;
+        B.out[r] = o;
+    }
+    w_sync();
+}

@@ -1,0 +1,71 @@
+// unc_warp.cuh -- the thin warp-primitive layer the device code is written against.
+//
+// Under nvcc these are the sm_100a warp intrinsics.  Under -DUNC_EMUL (host build used by
+// tests/test_emul_*.py) they are provided by tests/emul/warp_emul.hpp, a 32-fiber lockstep
+// emulator, so that the *same* kernel source is exercised on a CPU-only box.  The emulator
+// is a test vehicle for the device code, not a product path: libunc_b200.so never contains it.
+#pragma once
+#include <stdint.h>
+
+#ifdef UNC_EMUL
+#include "warp_emul.hpp"
+#else
+#include <cuda_runtime.h>
+#define UNC_DEV __device__ __forceinline__
+#define UNC_DEV_NOINLINE __device__ __noinline__
+#define UNC_FULL 0xffffffffu
+
+UNC_DEV int w_lane() { return (int) (threadIdx.x & 31); }
+UNC_DEV void w_sync() { __syncwarp(); }
+UNC_DEV uint32_t w_ballot(int p) { return __ballot_sync(UNC_FULL, p); }
+UNC_DEV uint32_t w_shfl(uint32_t v, int src) { return __shfl_sync(UNC_FULL, v, src); }
+UNC_DEV float w_shflf(float v, int src) { return __shfl_sync(UNC_FULL, v, src); }
+UNC_DEV uint32_t w_shfl_up(uint32_t v, int d) { return __shfl_up_sync(UNC_FULL, v, d); }
+UNC_DEV uint32_t w_shfl_down(uint32_t v, int d) { return __shfl_down_sync(UNC_FULL, v, d); }
+UNC_DEV uint32_t w_match(uint32_t v) { return __match_any_sync(UNC_FULL, v); }
+UNC_DEV uint32_t d_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+UNC_DEV uint32_t s_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+UNC_DEV uint32_t s_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
+UNC_DEV int d_popc(uint32_t v) { return __popc(v); }
+UNC_DEV int d_popcll(uint64_t v) { return __popcll(v); }
+UNC_DEV int d_clz(uint32_t v) { return __clz((int) v); }
+UNC_DEV int d_ffs(uint32_t v) { return __ffs((int) v); }
+// IEEE round-to-nearest, never contracted into FMA (the reference build has no FMA)
+UNC_DEV float f_mul(float a, float b) { return __fmul_rn(a, b); }
+UNC_DEV float f_add(float a, float b) { return __fadd_rn(a, b); }
+UNC_DEV float f_sub(float a, float b) { return __fsub_rn(a, b); }
+UNC_DEV float f_div(float a, float b) { return __fdiv_rn(a, b); }
+UNC_DEV float f_sqrt(float a) { return __fsqrt_rn(a); }
+UNC_DEV double d_mul(double a, double b) { return __dmul_rn(a, b); }
+UNC_DEV double d_add(double a, double b) { return __dadd_rn(a, b); }
+UNC_DEV double d_sub(double a, double b) { return __dsub_rn(a, b); }
+UNC_DEV double d_div(double a, double b) { return __ddiv_rn(a, b); }
+UNC_DEV double d_sqrt(double a) { return __dsqrt_rn(a); }
+// x86-64 float -> u32 conversion as gcc emits it (cvttss2si to 64 bit, low half kept)
+UNC_DEV uint32_t f_to_u32_x86(float v) { return (uint32_t) (long long) v; }
+UNC_DEV uint64_t f_to_u64(float v) { return (uint64_t) v; }
+template <typename T> UNC_DEV T d_ldg(const T *p) { return __ldg(p); }
+UNC_DEV float u2f(uint32_t v) { return __uint_as_float(v); }
+UNC_DEV uint32_t f2u(float v) { return __float_as_uint(v); }
+#endif
+
+UNC_DEV uint32_t w_lanemask_lt() { return (1u << w_lane()) - 1u; }
+
+// exclusive prefix sum over the warp; *total receives the warp sum (uniform)
+UNC_DEV uint32_t w_exscan(uint32_t v, uint32_t *total) {
+    uint32_t x = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = w_shfl_up(x, d);
+        if (w_lane() >= d) x += y;
+    }
+    *total = w_shfl(x, 31);
+    return x - v;
+}
+
+UNC_DEV uint32_t w_max(uint32_t v) {
+    for (int d = 16; d > 0; d >>= 1) {
+        uint32_t y = w_shfl(v, w_lane() ^ d);
+        v = y > v ? y : v;
+    }
+    return v;
+}

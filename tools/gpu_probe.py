@@ -13,7 +13,7 @@ t = time.time(); sig, truth = synth.reads(g, n_reads, n_samples, seed=7); print(
 idx = U.Index(prefix, device=0)
 bm = U.BatchMapper(idx, max_reads=n_reads, max_samples=n_reads * n_samples)
 d = U.make_descs([n_samples] * n_reads)
-for it in range(3):
+for it in range(int(os.environ.get('PROBE_ITERS', '3'))):
     t = time.time(); out = bm.map(sig.ravel(), d); wall = time.time() - t
     tm = bm.timing()
     print("iter", it, "wall %.3fs" % wall, {k: round(v, 3) if isinstance(v, float) else v for k, v in tm.items()},

@@ -12,7 +12,7 @@ struct EmuIndex {
     HostIndex h;
     DevIndex ix;
     std::vector<uint2> kmer_range;
-    K2Tables tb;
+    std::vector<float> lv_mean, lv_var2, lognorm;
 };
 
 extern "C" {
@@ -36,11 +36,6 @@ void *emu_index_load(const char *prefix, const char *preset, const char *model_t
     e->kmer_range.resize(1024);
     for (u32 k = 0; k < 1024; k++) e->kmer_range[k] = unc_kmer_range_compute(ix, k);
     ix.kmer_range = e->kmer_range.data();
-    for (u32 k = 0; k < 1024; k++) {
-        e->tb.lv_mean[k] = h.lv_mean[k]; e->tb.lv_var2[k] = h.lv_var2[k]; e->tb.lognorm[k] = h.lognorm[k];
-        e->tb.kmer_range[k] = e->kmer_range[k];
-    }
-    for (int i = 0; i < 64; i++) e->tb.thresh[i] = h.thresh[i];
     return e;
 }
 
@@ -51,18 +46,18 @@ void emu_kmer_range(void *p, uint32_t k, uint64_t *st, uint64_t *en) {
     *st = e->kmer_range[k].x; *en = e->kmer_range[k].y;
 }
 
-struct WarpArgs {
-    const DevIndex *ix; const DevParams *p; const DevBatch *B; const DevWork *W; K2Shared *sh; const K2Tables *tb; u32 r;
+struct CtaArgs {
+    const DevIndex *ix; const DevParams *p; const DevBatch *B; const DevWork *W; K2Shared *sh;
 };
-static void warp_entry(void *a) {
-    WarpArgs *w = (WarpArgs *) a;
-    unc_k2_map_read(*w->ix, *w->p, *w->B, *w->W, w->sh, w->tb, w->r);
+static void cta_entry(void *a) {
+    CtaArgs *w = (CtaArgs *) a;
+    unc_k2_cta_main(*w->ix, *w->p, *w->B, *w->W, w->sh);
 }
 
 // events (optional, n_reads x stride) / normed (optional) are filled like unc_events_batch.
 int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads, uint32_t n_reads,
                   const void *samples, unc_paf_rec *out, uint32_t stride, float *events_out, float *normed_out,
-                  uint32_t *n_events_out, float *mel_out, int run_k2, uint32_t max_blocks) {
+                  uint32_t *n_events_out, float *mel_out, int run_k2, uint32_t max_blocks, int n_warps) {
     EmuIndex *e = (EmuIndex *) pidx;
     std::string err;
     if (unc_check_params(*prm, err)) { fprintf(stderr, "%s\n", err.c_str()); return UNC_E_ARG; }
@@ -85,7 +80,7 @@ int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads,
     B.events = events.data(); B.normed = normed.data(); B.ev_stride = stride;
     B.n_events = n_events.data(); B.scale = scale.data(); B.shift = shift.data(); B.mean_event_len = mel.data();
     u32 queue = 0;
-    B.queue = &queue; B.out = (DevRec *) out;
+    B.queue = &queue; B.out = (DevRec *) out; B.dbg = nullptr;
     B.seq_offsets = seq_off.data(); B.seq_lens = e->h.lens.data(); B.n_seqs = (u32) e->h.names.size();
     B.l_pac = (u64) e->h.l_pac;
     for (u32 r = 0; r < n_reads; r++) unc_k1_read(B, dp, r);
@@ -99,21 +94,22 @@ int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads,
     std::vector<uint4> paths((size_t) 2 * maxp * 8), ckey((size_t) 2 * maxp);
     std::vector<u16> order((size_t) 2 * maxp);
     std::vector<uint4> clu((size_t) max_blocks * 32 * 2), dir(max_blocks + 1);
+    const u32 rl_cap = 16384;
+    std::vector<uint2> rlist(2 * rl_cap);
     DevWork W;
-    W.paths = paths.data(); W.ckey = ckey.data(); W.order = order.data(); W.clu = clu.data(); W.dir = dir.data();
-    W.max_blocks = max_blocks;
-    K2Shared *sh = new K2Shared();
-    for (u32 r = 0; r < n_reads; r++) {
-        WarpArgs a = {&e->ix, &dp, &B, &W, sh, &e->tb, r};
-        emu_run_warp(warp_entry, &a);
-    }
-    delete sh;
+    W.paths = paths.data(); W.ckey = ckey.data(); W.order = order.data(); W.rlist = rlist.data();
+    W.clu = clu.data(); W.dir = dir.data();
+    W.max_blocks = max_blocks; W.rl_cap = rl_cap;
+    K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((maxp + 31) / 32) * sizeof(uint4));
+    CtaArgs a = {&e->ix, &dp, &B, &W, sh};
+    emu_run_cta(cta_entry, &a, 32 * (n_warps > 0 ? n_warps : 8));   // one persistent CTA maps the whole batch
+    free(sh);
     return 0;
 }
 
 void emu_match_probs(void *pidx, float event, float *out) {
     EmuIndex *e = (EmuIndex *) pidx;
-    for (u32 k = 0; k < 1024; k++) out[k] = unc_match_prob(event, e->tb.lv_mean[k], e->tb.lv_var2[k], e->tb.lognorm[k]);
+    for (u32 k = 0; k < 1024; k++) out[k] = unc_match_prob(event, e->h.lv_mean[k], e->h.lv_var2[k], e->h.lognorm[k]);
 }
 
 uint64_t emu_sa(void *pidx, uint64_t row) {

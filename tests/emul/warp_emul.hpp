@@ -22,15 +22,24 @@ struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = {x, y}; return r; }
 
-struct WarpEmu {
-    ucontext_t ctx[32], main_ctx;
-    char *stacks[32];
-    int cur;
-    int done[32];
-    int n_done;
+#define EMU_MAX_THREADS 1024
+struct WarpRv {      // per-warp rendezvous state
     uint64_t slot[32], result[32];
     int arrived;
     uint64_t gen;
+};
+struct WarpEmu {     // one CTA: n_threads fibers, 32 per warp
+    ucontext_t ctx[EMU_MAX_THREADS], main_ctx;
+    char *stacks[EMU_MAX_THREADS];
+    int n_threads;
+    int cur;
+    int done[EMU_MAX_THREADS];
+    int n_done;
+    WarpRv rv[EMU_MAX_THREADS / 32];
+    int cta_arrived;
+    uint64_t cta_gen;
+    int sub_arrived[16];
+    uint64_t sub_gen[16];
     void (*fn)(void *);
     void *arg;
 };
@@ -39,8 +48,8 @@ extern thread_local WarpEmu *g_warp;
 static inline void emu_yield() {
     WarpEmu *w = g_warp;
     int from = w->cur, nxt = from;
-    for (int i = 0; i < 32; i++) {
-        nxt = (nxt + 1) & 31;
+    for (int i = 0; i < w->n_threads; i++) {
+        nxt = nxt + 1 == w->n_threads ? 0 : nxt + 1;
         if (!w->done[nxt]) break;
     }
     if (nxt == from) return;
@@ -48,28 +57,66 @@ static inline void emu_yield() {
     swapcontext(&w->ctx[from], &w->ctx[nxt]);
 }
 
-// all-lane exchange: every lane posts v, then may read any lane's value from result[]
+// all-lane exchange within the calling fiber's warp: every lane posts v, then may read any
+// lane's value from result[]
 static inline const uint64_t *emu_exchange(uint64_t v) {
     WarpEmu *w = g_warp;
-    if (w->n_done) { fprintf(stderr, "warp_emul: collective reached after %d lane(s) exited\n", w->n_done); abort(); }
-    int lane = w->cur;
-    w->slot[lane] = v;
-    uint64_t mygen = w->gen;
-    if (++w->arrived == 32) {
-        memcpy(w->result, w->slot, sizeof(w->slot));
-        w->arrived = 0;
-        w->gen++;
+    if (w->n_done) { fprintf(stderr, "warp_emul: collective reached after %d thread(s) exited\n", w->n_done); abort(); }
+    int lane = w->cur & 31;
+    WarpRv *r = &w->rv[w->cur >> 5];
+    r->slot[lane] = v;
+    uint64_t mygen = r->gen;
+    if (++r->arrived == 32) {
+        memcpy(r->result, r->slot, sizeof(r->slot));
+        r->arrived = 0;
+        r->gen++;
     } else {
-        int spins = 0;
-        while (w->gen == mygen) {
+        long spins = 0;
+        while (r->gen == mygen) {
             emu_yield();
-            if (++spins > 100000) { fprintf(stderr, "warp_emul: deadlock at a collective (lane %d)\n", lane); abort(); }
+            if (++spins > 50000000L) { fprintf(stderr, "warp_emul: deadlock at a warp collective (thread %d)\n", w->cur); abort(); }
         }
     }
-    return w->result;
+    return r->result;
 }
 
-static inline int w_lane() { return g_warp->cur; }
+static inline int w_lane() { return g_warp->cur & 31; }
+static inline int c_tid() { return g_warp->cur; }
+static inline int c_nthreads() { return g_warp->n_threads; }
+// __syncthreads()
+static inline void c_sync() {
+    WarpEmu *w = g_warp;
+    if (w->n_done) { fprintf(stderr, "warp_emul: CTA barrier reached after %d thread(s) exited\n", w->n_done); abort(); }
+    uint64_t mygen = w->cta_gen;
+    if (++w->cta_arrived == w->n_threads) {
+        w->cta_arrived = 0;
+        w->cta_gen++;
+    } else {
+        long spins = 0;
+        while (w->cta_gen == mygen) {
+            emu_yield();
+            if (++spins > 50000000L) { fprintf(stderr, "warp_emul: deadlock at a CTA barrier (thread %d)\n", w->cur); abort(); }
+        }
+    }
+}
+// bar.sync id, count : named barrier over `count` threads
+static inline void c_sync_sub(int id, int count) {
+    WarpEmu *w = g_warp;
+    uint64_t mygen = w->sub_gen[id];
+    if (++w->sub_arrived[id] == count) {
+        w->sub_arrived[id] = 0;
+        w->sub_gen[id]++;
+    } else {
+        long spins = 0;
+        while (w->sub_gen[id] == mygen) {
+            emu_yield();
+            if (++spins > 50000000L) { fprintf(stderr, "warp_emul: deadlock at named barrier %d (thread %d)\n", id, w->cur); abort(); }
+        }
+    }
+}
+// inside a spin-wait on shared memory written by another warp: let the others run
+static inline void w_spin() { emu_yield(); }
+static inline void c_fence() {}
 static inline void w_sync() { emu_exchange(0); }
 static inline uint32_t w_ballot(int p) {
     // copy out immediately: result[] is overwritten by the next collective
@@ -124,6 +171,8 @@ static inline double d_sqrt(double a) { return sqrt(a); }
 static inline uint32_t f_to_u32_x86(float v) { return (uint32_t) (long long) v; }
 static inline uint64_t f_to_u64(float v) { return (uint64_t) v; }
 template <typename T> static inline T d_ldg(const T *p) { return *p; }
+static inline uint4 s_load_v4(const uint4 *p) { return *p; }
+static inline void s_store_v4(uint4 *p, uint4 v) { *p = v; }
 static inline float u2f(uint32_t v) { float r; memcpy(&r, &v, 4); return r; }
 static inline uint32_t f2u(float v) { uint32_t r; memcpy(&r, &v, 4); return r; }
 
@@ -133,26 +182,27 @@ static void emu_trampoline() {
     int me = w->cur;
     w->done[me] = 1;
     w->n_done++;
-    if (w->n_done == 32) {
+    if (w->n_done == w->n_threads) {
         swapcontext(&w->ctx[me], &w->main_ctx);
     } else {
-        // a lane left early: the others must not touch a collective any more (checked there)
+        // a thread left early: the others must not touch a collective any more (checked there)
         int nxt = me;
-        for (int i = 0; i < 32; i++) { nxt = (nxt + 1) & 31; if (!w->done[nxt]) break; }
+        for (int i = 0; i < w->n_threads; i++) { nxt = nxt + 1 == w->n_threads ? 0 : nxt + 1; if (!w->done[nxt]) break; }
         w->cur = nxt;
         swapcontext(&w->ctx[me], &w->ctx[nxt]);
     }
 }
 
-// run fn(arg) on 32 lockstep lanes
-static inline void emu_run_warp(void (*fn)(void *), void *arg) {
+// run fn(arg) on a CTA of n_threads (multiple of 32) fibers
+static inline void emu_run_cta(void (*fn)(void *), void *arg, int n_threads) {
     WarpEmu *w = (WarpEmu *) calloc(1, sizeof(WarpEmu));
     WarpEmu *saved = g_warp;
     g_warp = w;
     w->fn = fn;
     w->arg = arg;
-    const size_t STK = 1 << 20;
-    for (int i = 0; i < 32; i++) {
+    w->n_threads = n_threads;
+    const size_t STK = 1 << 19;
+    for (int i = 0; i < n_threads; i++) {
         w->stacks[i] = (char *) malloc(STK);
         getcontext(&w->ctx[i]);
         w->ctx[i].uc_stack.ss_sp = w->stacks[i];
@@ -162,7 +212,8 @@ static inline void emu_run_warp(void (*fn)(void *), void *arg) {
     }
     w->cur = 0;
     swapcontext(&w->main_ctx, &w->ctx[0]);
-    for (int i = 0; i < 32; i++) free(w->stacks[i]);
+    for (int i = 0; i < n_threads; i++) free(w->stacks[i]);
     g_warp = saved;
     free(w);
 }
+static inline void emu_run_warp(void (*fn)(void *), void *arg) { emu_run_cta(fn, arg, 32); }

@@ -67,7 +67,7 @@ def build():
             ("unc_device.cuh", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-DUNC_EMUL", "-fPIC", "-shared",
+    subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-DUNC_EMUL", "-DK2_MAXSEG=16u", "-fPIC", "-shared",
                     "-I" + EMUL_DIR, "-I" + os.path.join(ROOT, "uncalled_b200", "csrc"), "-o", out, src],
                    check=True, capture_output=True)
     return out
@@ -86,7 +86,7 @@ def lib():
         L.emu_kmer_range.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.emu_map_batch.argtypes = [C.c_void_p, C.POINTER(UncParams), C.POINTER(UncReadDesc), C.c_uint32, C.c_void_p,
                                     C.POINTER(UncPaf), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_int, C.c_uint32]
+                                    C.c_int, C.c_uint32, C.c_int]
         L.emu_match_probs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
         L.emu_sa.argtypes = [C.c_void_p, C.c_uint64]
         L.emu_sa.restype = C.c_uint64
@@ -102,7 +102,7 @@ class Emu:
             raise RuntimeError("emu_index_load failed")
         self.params = default_params()
 
-    def map_batch(self, signals, run_k2=True, max_blocks=4096, dtype=0, cal=(1.0, 0.0, 1.0)):
+    def map_batch(self, signals, run_k2=True, max_blocks=4096, dtype=0, cal=(1.0, 0.0, 1.0), n_warps=8):
         """signals: list of 1-D arrays.  Returns (recs, events list, normed list, mean_event_len)."""
         lens = [len(s) for s in signals]
         npdt = np.float32 if dtype == 0 else np.int16
@@ -117,7 +117,7 @@ class Emu:
         mel = np.zeros(n, np.float32)
         rc = self.L.emu_map_batch(self.idx, C.byref(self.params), d, n, flat.ctypes.data, out, stride,
                                   ev.ctypes.data, nm.ctypes.data, ne.ctypes.data, mel.ctypes.data,
-                                  1 if run_k2 else 0, max_blocks)
+                                  1 if run_k2 else 0, max_blocks, n_warps)
         if rc != 0:
             raise RuntimeError("emu_map_batch rc=%d" % rc)
         return list(out), [ev[i, :ne[i]].copy() for i in range(n)], [nm[i, :ne[i]].copy() for i in range(n)], mel

@@ -1,0 +1,33 @@
+"""Debug: per-phase cycle breakdown of the mapper kernel (needs the -DUNC_PHASE_TIMING build
+uncalled_b200/libunc_b200_pt.so; see DESIGN.md 'measurement')."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
+import numpy as np
+import uncalled_b200._native as N
+N.LIB_PATH = os.path.join(ROOT, "uncalled_b200", "libunc_b200_pt.so")
+import uncalled_b200 as U
+import synth, synthdata
+name = sys.argv[1] if len(sys.argv) > 1 else "g4m7"
+n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 2368
+prefix, g = synthdata.get_index(name)
+sig, truth = synth.reads(g, n_reads, 4000, seed=7)
+idx = U.Index(prefix, device=0)
+bm = U.BatchMapper(idx, max_reads=n_reads, max_samples=n_reads * 4000)
+d = U.make_descs([4000] * n_reads)
+for it in range(2):
+    out = bm.map(sig.ravel(), d)
+    print("iter", it, bm.timing())
+ph = np.zeros((n_reads, 8), np.uint64)
+L = N.lib()
+L.unc_pool_debug_phases.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+N.check(L.unc_pool_debug_phases(bm.h, n_reads, ph.ctypes.data))
+names = ["A probs", "B extend", "C sort", "C fixup", "D dedup/src", "S sa + E", "X barrier(tracker)", "loop head"]
+ev = out["events_used"].astype(np.float64) + 1
+tot = ph.sum(axis=0).astype(np.float64)
+print("total events", ev.sum())
+for i, nm in enumerate(names):
+    print("%-20s %6.1f%%  %8.0f cycles/event" % (nm, 100 * tot[i] / tot.sum(), tot[i] / ev.sum()))
+print("cycles/event total %.0f" % (tot.sum() / ev.sum()))
+nm = out["mapped"] == 0
+print("non-mapping reads: cycles/event %.0f ; mapping: %.0f" % (ph[nm].sum() / ev[nm].sum(), ph[~nm].sum() / ev[~nm].sum()))

@@ -4,6 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np
 import synth, synthdata
+import uncalled_b200._native as _N
+if os.environ.get('UNC_LIB'): _N.LIB_PATH = os.path.join(ROOT, os.environ['UNC_LIB'])
 import uncalled_b200 as U
 name = sys.argv[1] if len(sys.argv) > 1 else "g4m7"
 n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 2048

@@ -20,13 +20,14 @@ static_assert(sizeof(DevReadDesc) == 32, "DevReadDesc layout");
 
 // ------------------------------------------------------------------ kernels
 
-#define K2_WARPS 8
+#ifndef K2_WARPS
+#define K2_WARPS 4          /* 1 tracker warp + (K2_WARPS-1) worker warps per read */
+#endif
+#ifndef K2_MIN_CTAS
+#define K2_MIN_CTAS 4
+#endif
 #define K2_THREADS (K2_WARPS * 32)
-
-struct K2Smem {
-    K2Tables tb;
-    K2Shared sh[K2_WARPS];
-};
+static_assert(K2_WARPS >= 2 && K2_WARPS - 1 <= K2_MAXSEG, "worker warps must fit the sort segments");
 
 __global__ void k_kmer_ranges(DevIndex ix, uint2 *out) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,39 +39,25 @@ __global__ void __launch_bounds__(128) k1_events(DevBatch B, DevParams p) {
     if (r < B.n_reads) unc_k1_read(B, p, r);
 }
 
-// Persistent warp-per-read mapper.  Each CTA stages the pore model, the 1024 k-mer FM ranges
-// and the thresholds in shared memory; each warp then pulls reads from a global queue.
-__global__ void __launch_bounds__(K2_THREADS, 2)
+// Persistent CTA-per-read mapper.  Each CTA stages the pore model, the 1024 k-mer FM ranges
+// and the thresholds in shared memory, then pulls reads from a global queue; the K2_WARPS warps
+// of the CTA cooperate on every event of the read (chained scans through shared memory).
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
 k2_map(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t ckey_stride, size_t order_stride,
-       size_t clu_stride, size_t dir_stride) {
+       size_t rlist_stride, size_t clu_stride, size_t dir_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    K2Smem *sm = (K2Smem *) smem_raw;
-    for (u32 k = threadIdx.x; k < UNC_NKMER; k += blockDim.x) {
-        sm->tb.lv_mean[k] = ix.lv_mean[k];
-        sm->tb.lv_var2[k] = ix.lv_var2[k];
-        sm->tb.lognorm[k] = ix.lognorm[k];
-        sm->tb.kmer_range[k] = ix.kmer_range[k];
-    }
-    if (threadIdx.x < 64) sm->tb.thresh[threadIdx.x] = ix.thresh[threadIdx.x];
-    __syncthreads();
-
-    const u32 warp = threadIdx.x >> 5;
-    const size_t slot = (size_t) blockIdx.x * K2_WARPS + warp;
+    K2Shared *sh = (K2Shared *) smem_raw;
+    const size_t slot = blockIdx.x;
     DevWork W;
     W.paths = W0.paths + slot * paths_stride;
     W.ckey = W0.ckey + slot * ckey_stride;
     W.order = W0.order + slot * order_stride;
+    W.rlist = W0.rlist + slot * rlist_stride;
     W.clu = W0.clu + slot * clu_stride;
     W.dir = W0.dir + slot * dir_stride;
     W.max_blocks = W0.max_blocks;
-    K2Shared *sh = &sm->sh[warp];
-    for (;;) {
-        u32 r = 0;
-        if ((threadIdx.x & 31) == 0) r = atomicAdd(B.queue, 1u);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= B.n_reads) break;
-        unc_k2_map_read(ix, p, B, W, sh, &sm->tb, r);
-    }
+    W.rl_cap = W0.rl_cap;
+    unc_k2_cta_main(ix, p, B, W, sh);
 }
 
 __global__ void k_match_probs(DevIndex ix, float event, float *out) {
@@ -81,10 +68,14 @@ __global__ void k_match_probs(DevIndex ix, float event, float *out) {
 __global__ void k_fm_neighbors(DevIndex ix, u32 n, const u64 *st, const u64 *en, const u8 *base, u64 *ost, u64 *oen) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    u32 ns[4], ne[4], nb = 0;
-    unc_neighbors(ix, (u32) st[i], (u32) en[i], 1u << base[i], ns, ne, &nb);
-    ost[i] = ns[base[i]];
-    oen[i] = ne[base[i]];
+    u32 ns[4], ne[4], nb = 0, c = base[i];
+    u32 ok = unc_neighbors(ix, (u32) st[i], (u32) en[i], 1u << c, ns, ne, &nb);
+    if (!((ok >> c) & 1u)) {   // empty range: report it the way get_neighbor does (start = end + 1 ...)
+        ns[c] = ix.L2[c] + unc_occ(ix, (u32) st[i] - 1u, c, &nb) + 1u;
+        ne[c] = ix.L2[c] + unc_occ(ix, (u32) en[i], c, &nb);
+    }
+    ost[i] = ns[c];
+    oen[i] = ne[c];
 }
 
 __global__ void k_fm_sa(DevIndex ix, u32 n, const u64 *rows, u64 *out) {
@@ -137,10 +128,11 @@ struct unc_pool {
     float *d_events = nullptr, *d_normed = nullptr, *d_scale = nullptr, *d_shift = nullptr, *d_mel = nullptr;
     u32 *d_n_events = nullptr, *d_queue = nullptr;
     DevRec *d_out = nullptr;
+    unsigned long long *d_dbg = nullptr;
     unc_paf_rec *h_out = nullptr;  // pinned staging
     // workspaces
     DevWork W;
-    size_t paths_stride = 0, ckey_stride = 0, order_stride = 0, clu_stride = 0, dir_stride = 0;
+    size_t paths_stride = 0, ckey_stride = 0, order_stride = 0, rlist_stride = 0, clu_stride = 0, dir_stride = 0;
     uint32_t n_slots = 0, grid = 0;
     size_t smem = 0;
     unc_timing last;
@@ -308,14 +300,13 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     for (int i = 0; i < 5; i++) PT(cudaEventCreate(&P->ev[i]));
     cudaDeviceProp prop;
     PT(cudaGetDeviceProperties(&prop, idx->device));
-    P->smem = sizeof(K2Smem);
+    P->smem = sizeof(K2Shared) + 16 + (size_t) ((prm->max_paths + 31) / 32) * sizeof(uint4);
     PT(cudaFuncSetAttribute(k2_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
     int per_sm = 0;
     PT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_map, K2_THREADS, P->smem));
     if (per_sm < 1) return bail(UNC_E_CUDA, "k2_map does not fit on an SM");
     uint32_t grid = (uint32_t) prop.multiProcessorCount * (uint32_t) per_sm;
-    uint32_t need = (max_reads + K2_WARPS - 1) / K2_WARPS;
-    if (grid > need) grid = need;
+    if (grid > max_reads) grid = max_reads;
     // per-slot workspace sizes
     const size_t maxp = prm->max_paths;
     P->paths_stride = 2 * maxp * 8;   // uint4
@@ -326,22 +317,26 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     uint64_t ev_cap = std::min<uint64_t>(prm->max_events, longest / 3 + 16);
     uint64_t mb = std::max<uint64_t>(1024, ev_cap * 2);
     mb = std::min<uint64_t>(mb, 1u << 17);
-    size_t per_slot = P->paths_stride * 16 + P->ckey_stride * 16 + P->order_stride * 2 + mb * (UNC_BLK * 32 + 16);
+    const size_t rl_cap = 64 * 1024;   // seed rows of one event (typically tens)
+    size_t per_slot = P->paths_stride * 16 + P->ckey_stride * 16 + P->order_stride * 2 + 2 * rl_cap * 8 + mb * (UNC_BLK * 32 + 16);
     size_t free_b = 0, total_b = 0;
     PT(cudaMemGetInfo(&free_b, &total_b));
     size_t fixed = max_samples * 4 + (size_t) max_reads * (sizeof(DevReadDesc) + sizeof(DevRec) + 20) + (64u << 20);
     P->ev_stride = 0;
-    if (free_b < fixed + per_slot * K2_WARPS) return bail(UNC_E_NOMEM, "not enough device memory for the pool");
+    if (free_b < fixed + per_slot) return bail(UNC_E_NOMEM, "not enough device memory for the pool");
     size_t budget = (size_t) ((free_b - fixed) * 0.85);
-    while ((size_t) grid * K2_WARPS * per_slot > budget && grid > 1) grid--;
+    while ((size_t) grid * per_slot > budget && grid > 1) grid--;
     P->grid = grid;
-    P->n_slots = grid * K2_WARPS;
+    P->n_slots = grid;
+    P->rlist_stride = 2 * rl_cap;
+    P->W.rl_cap = (u32) rl_cap;
     P->clu_stride = (size_t) mb * UNC_BLK * 2;
     P->dir_stride = (size_t) mb + 1;
     P->W.max_blocks = (u32) mb;
     PT(cudaMalloc(&P->W.paths, (size_t) P->n_slots * P->paths_stride * 16));
     PT(cudaMalloc(&P->W.ckey, (size_t) P->n_slots * P->ckey_stride * 16));
     PT(cudaMalloc(&P->W.order, (size_t) P->n_slots * P->order_stride * 2));
+    PT(cudaMalloc(&P->W.rlist, (size_t) P->n_slots * P->rlist_stride * 8));
     PT(cudaMalloc(&P->W.clu, (size_t) P->n_slots * P->clu_stride * 16));
     PT(cudaMalloc(&P->W.dir, (size_t) P->n_slots * P->dir_stride * 16));
     PT(cudaMalloc(&P->d_samples, max_samples * 4));
@@ -353,6 +348,10 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     PT(cudaMalloc(&P->d_n_events, (size_t) max_reads * 4));
     PT(cudaMalloc(&P->d_queue, 4));
     PT(cudaMalloc(&P->d_out, (size_t) max_reads * sizeof(DevRec)));
+#ifdef UNC_PHASE_TIMING
+    PT(cudaMalloc(&P->d_dbg, (size_t) max_reads * 64));
+    PT(cudaMemset(P->d_dbg, 0, (size_t) max_reads * 64));
+#endif
     PT(cudaMallocHost(&P->h_out, (size_t) max_reads * sizeof(unc_paf_rec)));
 #undef PT
     (void) rc;
@@ -362,11 +361,11 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
 
 void unc_pool_free(unc_pool *P) {
     if (!P) return;
-    cudaFree(P->W.paths); cudaFree(P->W.ckey); cudaFree(P->W.order); cudaFree(P->W.clu); cudaFree(P->W.dir);
+    cudaFree(P->W.paths); cudaFree(P->W.ckey); cudaFree(P->W.order); cudaFree(P->W.rlist); cudaFree(P->W.clu); cudaFree(P->W.dir);
     cudaFree(P->d_samples); cudaFree(P->d_reads); cudaFreeHost(P->h_reads);
     cudaFree(P->d_events); cudaFree(P->d_normed);
     cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue);
-    cudaFree(P->d_out); cudaFreeHost(P->h_out);
+    cudaFree(P->d_out); cudaFreeHost(P->h_out); cudaFree(P->d_dbg);
     for (int i = 0; i < 5; i++) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
     if (P->stream) cudaStreamDestroy(P->stream);
     delete P;
@@ -416,6 +415,7 @@ static DevBatch make_batch(unc_pool *P, const void *d_samples, uint32_t n, bool 
     B.n_events = P->d_n_events;
     B.scale = P->d_scale; B.shift = P->d_shift; B.mean_event_len = P->d_mel;
     B.queue = P->d_queue;
+    B.dbg = P->d_dbg;
     B.out = P->d_out;
     B.seq_offsets = (const u64 *) P->idx->d_seq_off;
     B.seq_lens = (const u32 *) P->idx->d_seq_len;
@@ -448,9 +448,9 @@ static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     k1_events<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[2], s));
-    uint32_t grid = std::min<uint32_t>(P->grid, (n + K2_WARPS - 1) / K2_WARPS);
+    uint32_t grid = std::min<uint32_t>(P->grid, n);
     k2_map<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->ckey_stride, P->order_stride,
-                                             P->clu_stride, P->dir_stride);
+                                             P->rlist_stride, P->clu_stride, P->dir_stride);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[3], s));
     CUDA_TRY(cudaMemcpyAsync(P->h_out, P->d_out, (size_t) n * sizeof(DevRec), cudaMemcpyDeviceToHost, s));
@@ -560,6 +560,13 @@ int unc_fm_sa(const unc_index *x, uint32_t n, const uint64_t *rows, uint64_t *ou
     cudaError_t e = cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost);
     cudaFree(dr); cudaFree(dout);
     if (e != cudaSuccess) return fail(UNC_E_CUDA, cudaGetErrorString(e));
+    return UNC_OK;
+}
+
+// debug builds (-DUNC_PHASE_TIMING): per-read cycle counters of the mapper's phases
+int unc_pool_debug_phases(const unc_pool *P, uint32_t n, unsigned long long *out) {
+    if (!P || !out || !P->d_dbg) return fail(UNC_E_ARG, "phase timing not compiled in");
+    CUDA_TRY(cudaMemcpy(out, P->d_dbg, (size_t) n * 64, cudaMemcpyDeviceToHost));
     return UNC_OK;
 }
 

@@ -2,7 +2,7 @@
 //
 //   K1  unc_k1_read()      thread-per-read event detection + whole-read normalisation stats
 //                          (reference src/event_detector.cpp:83-319, src/normalizer.cpp:31-44)
-//   K2  unc_k2_map_read()  warp-per-read mapper: pore-model scoring, FM-index path extension,
+//   K2  unc_k2_map_read()  CTA-per-read mapper: pore-model scoring, FM-index path extension,
 //                          child sort/dedup, gap + fresh sources, seed clustering, PAF coords
 //                          (reference src/mapper.cpp:433-728, src/seed_tracker.cpp:56-262,
 //                           submods/bwa/bwt.c:53-163)
@@ -78,19 +78,21 @@ struct DevBatch {
     // K2
     u32 *queue;          // atomic read counter
     DevRec *out;
+    unsigned long long *dbg;  // optional (may be null): 8 phase-cycle counters per read (UNC_PHASE_TIMING builds)
     const u64 *seq_offsets;  // .ann offsets / lens for translate_loc
     const u32 *seq_lens;
     u32 n_seqs;
     u64 l_pac;
 };
 
-struct DevWork {   // per-slot (per-warp) workspaces; slot s uses [s*stride, (s+1)*stride)
+struct DevWork {   // per-slot (per-CTA) workspaces; slot s uses [s*stride, (s+1)*stride)
     uint4 *paths;      // 2 x max_paths x 8 uint4
     uint4 *ckey;       // 2 x max_paths uint4 (radix ping-pong)
     u16 *order;        // 2 x max_paths
+    uint2 *rlist;      // 2 x rl_cap (double buffered by event parity) seed rows: (FM row -> ref end, move_count | ended<<8)
     uint4 *clu;        // max_blocks x 32 x 2 uint4
     uint4 *dir;        // max_blocks
-    u32 max_blocks;
+    u32 max_blocks, rl_cap;
 };
 
 // ------------------------------------------------------------------ pore model
@@ -153,13 +155,39 @@ UNC_DEV u32 unc_occ(const DevIndex &ix, u32 k, u32 c, u32 *n_blocks) {
 
 // One backward-search step for all four bases at once: BwaIndex::get_neighbor
 // (reference src/bwa_index.hpp:158-162) over bwt_2occ (submods/bwa/bwt.c:132-163).
-// `want` has bit b set for each base whose range is needed.  Paths always have start >= 1.
-UNC_DEV void unc_neighbors(const DevIndex &ix, u32 start, u32 end, u32 want, u32 ns[4], u32 ne[4], u32 *n_blocks) {
+// `want` has bit b set for each base whose range is needed; on return bit b of the result is
+// set iff base b yields a valid (non-empty) range, stored in ns[b]..ne[b].
+// Paths always have start >= 1.  Instead of two Occ values per base, the symbols of rows
+// (k, l] are counted first: only bases that occur there have a non-empty range (for a
+// unique path that is exactly one base), and only for those the prefix Occ(k, c) is needed:
+//   ns = L2[c] + Occ(k,c) + 1,  ne = L2[c] + Occ(l,c) = ns + count_c(k,l] - 1.
+UNC_DEV u32 unc_neighbors(const DevIndex &ix, u32 start, u32 end, u32 want, u32 ns[4], u32 ne[4], u32 *n_blocks) {
     u32 k = start - 1, l = end;
     u32 kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
     bool l_is_end = (l == ix.seq_len);
     OccBlock bk = unc_load_block(ix, kk);
     (*n_blocks)++;
+    u32 valid = 0;
+    if (!l_is_end && (ll >> 5) == (kk >> 5)) {
+        // rows k and l fall into the same 64-bit BWT word: count symbols of (kk, ll] directly
+        u32 q = (kk & 127u) >> 5;
+        u32 hi = q == 0 ? bk.b2.x : q == 1 ? bk.b2.z : q == 2 ? bk.b3.x : bk.b3.z;
+        u32 lo = q == 0 ? bk.b2.y : q == 1 ? bk.b2.w : q == 2 ? bk.b3.y : bk.b3.w;
+        u64 w = ((u64) hi << 32) | lo;
+        u64 le_k = ~((1ull << ((~kk & 31u) << 1)) - 1ull), le_l = ~((1ull << ((~ll & 31u) << 1)) - 1ull);
+        u64 between = le_l & ~le_k;
+#pragma unroll
+        for (u32 c = 0; c < 4; c++) {
+            if (!((want >> c) & 1u)) continue;
+            u32 cnt = (u32) d_popcll(unc_match_bits(w, c) & between);
+            if (cnt == 0) continue;
+            u32 ok = unc_occ_in_block(bk.b0, bk.b1, bk.b2, bk.b3, kk, c);
+            ns[c] = ix.L2[c] + ok + 1;
+            ne[c] = ns[c] + cnt - 1;
+            valid |= 1u << c;
+        }
+        return valid;
+    }
     OccBlock bl = bk;
     if (!l_is_end && (ll >> 7) != (kk >> 7)) { bl = unc_load_block(ix, ll); (*n_blocks)++; }
 #pragma unroll
@@ -169,7 +197,9 @@ UNC_DEV void unc_neighbors(const DevIndex &ix, u32 start, u32 end, u32 want, u32
         u32 ol = l_is_end ? (ix.L2[c + 1] - ix.L2[c]) : unc_occ_in_block(bl.b0, bl.b1, bl.b2, bl.b3, ll, c);
         ns[c] = ix.L2[c] + ok + 1;
         ne[c] = ix.L2[c] + ol;
+        if (ns[c] <= ne[c]) valid |= 1u << c;
     }
+    return valid;
 }
 
 // bwt_sa (reference submods/bwa/bwt.c:86-96) with bwt_invPsi (:53-59); sa_intv == 32
@@ -634,27 +664,97 @@ UNC_DEV bool trk_get_final(const Tracker &t, const DevParams &p) {
            (p.min_top_conf > 0 && f_div(sl, second_len) >= p.min_top_conf);
 }
 
-// ------------------------------------------------------------------ K2: mapper
-
+// ------------------------------------------------------------------ K2: mapper (one CTA per read)
+//
+// Warp 0 of the CTA is the TRACKER: it owns the seed-cluster set (sequential by nature) and
+// runs one event behind the other warps.  Warps 1.. are WORKERS: per event they score the 1024
+// k-mers, extend all paths (chunks of 32 paths per warp, order kept by a lane-0 relay chain
+// through shared memory), radix-sort the children, dedup + emit sources, and look up the
+// suffix array for the event's seeds, which they hand to the tracker through a double-buffered
+// list.
+//
 // Path record = 8 uint4 (128 B):
 //   q0 = (fm_start, fm_end, kmer | length<<16 | consec_stays<<24, event_moves)
 //   q1 = (seed_prob bits, sa_checked, 0, 0)
 //   q2..q7 = 23-float ring of cumulative log-probs since the path's source, slot = event % 23
 //            (the reference's prob_sums_ window, src/mapper.cpp:792-801, without the shift)
-struct K2Shared {          // per warp
-    float probs[UNC_NKMER];
-    u32 hist[256];
-    u32 flags[32];         // sources_added_ bits (reference src/mapper.cpp:88), kmer k -> word k>>5
-};
-struct K2Tables {          // per CTA
-    float lv_mean[UNC_NKMER], lv_var2[UNC_NKMER], lognorm[UNC_NKMER];
+// Sort key (ckey) = (fm_start, fm_end, seed_prob bits, kmer | seedable<<10 | move_count<<11 | emission idx<<16)
+#define K2_MAXCH 1024u     /* chunks of 32 paths (max_paths <= 32767) */
+#define K2_RBITS 8u        /* radix digit width of the child sort */
+#define K2_RB 256u
+#ifndef K2_MAXSEG
+#define K2_MAXSEG 8u       /* max worker warps (sort segments) */
+#endif
+
+struct K2Tables {
     uint2 kmer_range[UNC_NKMER];
     float thresh[64];
 };
+// Relay chain across the worker warps: chunk c publishes its inclusive carry, chunk c+1
+// (handled by the next warp) waits for it.  Carry and epoch travel in ONE 128-bit shared-memory
+// word (x = epoch, y/z/w = payload) so that no fence is needed: a thread's single 16-byte
+// shared store becomes visible as a whole.
+struct K2Chain {
+    uint4 *slot;           // ceil(max_paths / 32) entries, carved from dynamic shared memory
+};
+struct K2Shared {          // per CTA (~29 KB + 16 B per 32 max_paths of relay slots)
+    K2Tables tb;
+    float probs[UNC_NKMER];
+    u32 flags[32];         // sources_added_ bits (reference src/mapper.cpp:88), kmer k -> word k>>5
+    u32 hist_cur[K2_RB * K2_MAXSEG];    // [digit][segment]
+    u32 hist_next[K2_RB * K2_MAXSEG];
+    K2Chain ch;
+    u32 bc[8];             // CTA broadcast scalars
+    u32 scan_tmp[32];
+    u32 n_rows[2];         // worker -> tracker: seed rows of event e in rlist[e & 1]
+    u32 verdict[2];        // tracker -> workers: outcome of event e in verdict[e & 1]
+    u32 wk_overflow;
+    u32 cnt_blocks, cnt_steps;
+    u32 tot_children[2], tot_sources[2];   // u64 as two words, written by a worker at the end
+};
 
-struct K2Counters { u64 n_children, n_sources, n_occ_blocks, n_sa_steps, n_seeds; };
+// lane 0 only: wait for chunk c-1 and fetch its carry (zeros for the first chunk)
+UNC_DEV uint4 k2_relay_wait(K2Chain *ch, u32 c, u32 epoch) {
+    if (c == 0) return make_uint4(epoch, 0, 0, 0);
+    uint4 v;
+    do {
+        v = s_load_v4(&ch->slot[c - 1]);
+        if (v.x == epoch) break;
+        w_spin();
+    } while (true);
+    return v;
+}
+// lane 0 only
+UNC_DEV void k2_relay_publish(K2Chain *ch, u32 c, u32 epoch, u32 v0, u32 v1, u32 v2) {
+    s_store_v4(&ch->slot[c], make_uint4(epoch, v0, v1, v2));
+}
 
-UNC_DEV uint4 *path_rec(uint4 *paths, u32 gen, u32 maxp, u32 idx) { return paths + ((size_t) gen * maxp + idx) * 8; }
+// exclusive scan over the K2_RB*K2_MAXSEG sort counters by the worker threads:
+// dst[i] = sum(src[0..i)); src := 0.   wt = worker thread index, nwt = worker thread count.
+UNC_DEV void k2_wk_exscan_bins(K2Shared *sh, u32 *src, u32 *dst, u32 wt, u32 nwt) {
+    const u32 n = K2_RB * K2_MAXSEG;
+    const u32 per = (n + nwt - 1) / nwt;
+    const u32 lo = wt * per < n ? wt * per : n, hi = lo + per < n ? lo + per : n;
+    u32 sum = 0;
+    for (u32 j = lo; j < hi; j++) sum += src[j];
+    u32 wtot, woff = w_exscan(sum, &wtot);
+    if (w_lane() == 31) sh->scan_tmp[wt >> 5] = wtot;
+    c_sync_sub(1, (int) nwt);
+    if (wt < 32) {
+        u32 v = wt < (nwt >> 5) ? sh->scan_tmp[wt] : 0, t;
+        u32 e = w_exscan(v, &t);
+        sh->scan_tmp[wt] = e;
+    }
+    c_sync_sub(1, (int) nwt);
+    u32 run = sh->scan_tmp[wt >> 5] + woff;
+    for (u32 j = lo; j < hi; j++) {
+        u32 cnt = src[j];
+        dst[j] = run;
+        src[j] = 0;
+        run += cnt;
+    }
+    c_sync_sub(1, (int) nwt);
+}
 
 // PathBuffer::make_source (reference src/mapper.cpp:751-772)
 UNC_DEV void write_source(uint4 *rec, u32 st, u32 en, u32 kmer, float prob, u32 ev) {
@@ -671,345 +771,63 @@ UNC_DEV u32 unc_event_to_bp(u32 evt_i, bool last, float mean_event_len, float bp
     return f_to_u32_x86(v);
 }
 
-// One read mapped by one warp.  reference src/mapper.cpp:188-200 (map_read) driving
-// :433-663 (map_next).  `sh`/`tb` are shared-memory scratch/tables; `W` the slot's workspaces.
-UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
-                             K2Shared *sh, const K2Tables *tb, u32 r) {
-    const int lane = w_lane();
-    const u32 maxp = p.max_paths;
-    const u32 n_ev = B.n_events[r];
-    const float scale = B.scale[r], shift = B.shift[r], mel = B.mean_event_len[r];
-    const float *events = B.events + (size_t) r * B.ev_stride;
-    const float source_prob = tb->thresh[0];
-    const float bp_per_samp = f_div(p.bp_per_sec, p.sample_rate);
-    K2Counters cn; cn.n_children = cn.n_sources = cn.n_occ_blocks = cn.n_sa_steps = cn.n_seeds = 0;
-    u32 my_blocks = 0, my_steps = 0;   // per-lane counters, reduced at the end
+// stage the pore model, k-mer FM ranges and thresholds in shared memory (once per CTA)
+UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *sh) {
+    if (c_tid() == 0) sh->ch.slot = (uint4 *) ((((size_t) (sh + 1)) + 15) & ~(size_t) 15);   // dynamic shared memory follows the struct
+    c_sync();
+    const u32 n_slots = (p.max_paths + 31u) >> 5;
+    for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) {
+        sh->tb.kmer_range[k] = ix.kmer_range[k];
+    }
+    for (u32 k = (u32) c_tid(); k < 64; k += (u32) c_nthreads()) sh->tb.thresh[k] = ix.thresh[k];
+    for (u32 c = (u32) c_tid(); c < n_slots; c += (u32) c_nthreads()) sh->ch.slot[c] = make_uint4(0, 0, 0, 0);
+    c_sync();
+}
 
+// ---- tracker warp (warp 0): reference src/mapper.cpp:513-519,601 (update_seeds order),
+//      :631-653 (get_final -> set_ref_loc), :708-728, bwa_index.hpp:213-220
+UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
+                            K2Shared *sh, u32 r, u32 n_limit) {
+    const int lane = w_lane();
     Tracker trk;
     trk.blocks = W.clu; trk.dir = W.dir; trk.max_blocks = W.max_blocks;
     trk_reset(trk);
-    sh->flags[lane] = 0;
-    w_sync();
-
-    u32 prev_size = 0, gen = 0, event_i = 0;
-    bool mapped = false;
-    u32 n_limit = n_ev < p.max_events ? n_ev : p.max_events;
-
-    for (; event_i < n_limit; event_i++) {
-        const float ev_raw = events[event_i];
-        const float event = f_add(f_mul(scale, ev_raw), shift);
-
-        // ---- A. pore-model probabilities (reference src/mapper.cpp:443-445)
-        for (u32 j = 0; j < 32; j++) {
-            u32 k = j * 32 + (u32) lane;
-            sh->probs[k] = unc_match_prob(event, tb->lv_mean[k], tb->lv_var2[k], tb->lognorm[k]);
+    u32 verdict = 0, i = 0, final_event = n_limit;
+    u64 n_seeds = 0;
+    for (;;) {
+        c_sync();                                  // b_i: workers finished event i (or this is the final barrier)
+        if (i == n_limit) break;
+        if (verdict) { c_sync(); break; }          // event i is discarded; final barrier
+        const uint2 *rl = W.rlist + (size_t) (i & 1u) * W.rl_cap;
+        const u32 n = *(volatile u32 *) &sh->n_rows[i & 1u];
+        // seed clustering is sequential: ended paths' seeds (event i-1) in parent order, then the
+        // children's (event i) in sorted order
+        for (u32 j = 0; j < n; j++) {
+            uint2 e = rl[j];
+            trk_add_seed(trk, p, e.x, e.y & 0xFFu, (e.y & 0x100u) ? i - 1u : i);
         }
-        w_sync();
-
-        uint4 *prev = W.paths + (size_t) gen * maxp * 8, *next = W.paths + (size_t) (gen ^ 1u) * maxp * 8;
-        const u16 *oprev = W.order + (size_t) gen * maxp;
-        u16 *onext = W.order + (size_t) (gen ^ 1u) * maxp;
-        uint4 *ckA = W.ckey, *ckB = W.ckey + maxp;
-        const u32 slot_prev = (event_i + 22u) % UNC_RING, slot_new = event_i % UNC_RING, slot_old = (event_i + 1u) % UNC_RING;
-
-        // ---- B. extend every previous path (reference src/mapper.cpp:455-524)
-        u32 nn = 0;
-        for (u32 base = 0; base < prev_size && nn < maxp; base += 32) {
-            u32 pi = base + (u32) lane;
-            bool act = pi < prev_size;
-            u32 oi = act ? oprev[pi] : UNC_INVALID;
-            bool valid = act && !(oi & UNC_INVALID);
-            const uint4 *prec = prev + (size_t) (oi & 0x7FFFu) * 8;
-            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
-            if (valid) { q0 = prec[0]; q1 = prec[1]; }
-            u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
-            u32 moves = q0.w, sa_checked = q1.y;
-            float thr = 0.0f;
-            u32 want = 0; bool stay_ok = false;
-            float cprob[5]; u32 cst[5], cen[5], ckm[5];
-            if (valid) {
-                u32 len = en - st + 1u;
-                thr = tb->thresh[32 + d_clz(len)];
-                float pk = sh->probs[kmer];
-                stay_ok = stays < p.max_consec_stay && pk >= thr;
-                cprob[0] = pk; cst[0] = st; cen[0] = en; ckm[0] = kmer;
-#pragma unroll
-                for (u32 b = 0; b < 4; b++) {
-                    u32 nk = ((kmer << 2) & UNC_KMASK) | b;
-                    float pb = sh->probs[nk];
-                    ckm[b + 1] = nk; cprob[b + 1] = pb;
-                    if (!(pb < thr)) want |= 1u << b;   // `if (prob < thresh) continue;`
-                }
-            }
-            u32 cmask = stay_ok ? 1u : 0u;
-            if (want) {
-                u32 ns[4], ne[4];
-                unc_neighbors(ix, st, en, want, ns, ne, &my_blocks);
-#pragma unroll
-                for (u32 b = 0; b < 4; b++)
-                    if (((want >> b) & 1u) && ns[b] <= ne[b]) { cmask |= 2u << b; cst[b + 1] = ns[b]; cen[b + 1] = ne[b]; }
-            }
-            u32 cc = (u32) d_popc(cmask), total;
-            u32 off = w_exscan(cc, &total);
-            // sequential semantics of the full buffer: parent is reached iff the buffer was not
-            // yet full when the scan arrived at it
-            bool reached = valid && (nn + off < maxp);
-            if (reached && cc > 0) {
-                uint4 r2 = prec[2], r3 = prec[3], r4 = prec[4], r5 = prec[5], r6 = prec[6], r7 = prec[7];
-                const float *pring = (const float *) (prec + 2);
-                float prevC = pring[slot_prev], oldC = pring[slot_old];
-                u32 ci = nn + off;
-#pragma unroll
-                for (u32 j = 0; j < 5; j++) {
-                    if (!((cmask >> j) & 1u) || ci >= maxp) continue;
-                    u32 move = j > 0 ? 1u : 0u;
-                    u32 nlen = plen + (plen < UNC_SEED_LEN ? 1u : 0u);
-                    u32 nmoves = ((moves << 1) | move) & UNC_PATH_MASK;
-                    u32 nstays = move ? 0u : stays + 1u;
-                    float newC = f_add(prevC, cprob[j]);
-                    float sp;
-                    if (plen == UNC_SEED_LEN) { sp = f_div(f_sub(newC, oldC), 22.0f); nmoves |= UNC_PATH_TAIL; }
-                    else sp = f_div(newC, (float) nlen);
-                    u32 spb = f2u(sp);
-                    uint4 *crec = next + (size_t) ci * 8;
-                    crec[0] = make_uint4(cst[j], cen[j], ckm[j] | (nlen << 16) | (nstays << 24), nmoves);
-                    crec[1] = make_uint4(spb, sa_checked, 0u, 0u);
-                    crec[2] = r2; crec[3] = r3; crec[4] = r4; crec[5] = r5; crec[6] = r6; crec[7] = r7;
-                    ((float *) (crec + 2))[slot_new] = newC;
-                    // is_seed_valid(path_ended = false) of the child (reference src/mapper.cpp:842-863)
-                    u32 mc = (u32) d_popc(nmoves);
-                    u32 stay_count = (nlen - mc) & 0xFFu;
-                    bool seedable = nlen == UNC_SEED_LEN && sp >= p.min_seed_prob && cst[j] == cen[j] && (nmoves & 1u) &&
-                                    (float) stay_count <= f_mul(p.max_stay_frac, 22.0f);
-                    ckA[ci] = make_uint4(cst[j], cen[j], spb, ckm[j] | (seedable ? 1u << 10 : 0u) | (mc << 11) | (ci << 16));
-                    ci++;
-                }
-            }
-            // childless, not yet SA-checked parents emit their seeds now, in parent order
-            // (reference src/mapper.cpp:513-519 -> update_seeds(path, true))
-            bool ended = false;
-            if (reached && cc == 0 && !sa_checked) {
-                u32 mc = (u32) d_popc(moves);
-                u32 len = en - st + 1u;
-                ended = plen == UNC_SEED_LEN && u2f(q1.x) >= p.min_seed_prob &&
-                        ((len == 1 && (moves & 1u) && (float) ((plen - mc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f)) ||
-                         (len <= p.max_rep_copy && mc >= p.min_rep_len));
-            }
-            u32 m_end = w_ballot(ended);
-            while (m_end) {
-                int l = d_ffs(m_end) - 1;
-                m_end &= m_end - 1;
-                u32 s0 = w_shfl(st, l), s1 = w_shfl(en, l), mcl = (u32) d_popc(w_shfl(moves, l));
-                for (u32 rb = s0; rb <= s1; rb += 32) {
-                    u32 row = rb + (u32) lane;
-                    u32 sav = 0;
-                    bool have = row <= s1;
-                    if (have) sav = unc_sa(ix, row, &my_steps, &my_blocks);
-                    u32 nrow = s1 - rb + 1u; if (nrow > 32) nrow = 32;
-                    for (u32 j = 0; j < nrow; j++) {
-                        u32 sv = w_shfl(sav, (int) j);
-                        trk_add_seed(trk, p, ix.seq_len - sv, mcl, event_i - 1u);
-                        cn.n_seeds++;
-                    }
-                    if (s1 - rb < 32) break;   // also guards rb + 32 wrap
-                }
-            }
-            nn += total;
-            if (nn > maxp) nn = maxp;
-        }
-        const u32 nc = nn;
-        cn.n_children += nc;
-        w_sync();
-
-        u32 ns_added = 0;   // sources appended after the children
-        if (nc > 0) {
-            // ---- C. order children by (fm_start, fm_end, seed_prob, emission index)
-            //         (reference src/mapper.cpp:531 pdqsort + operator< :866-871)
-            uint4 *src = ckA, *dst = ckB;
-            for (u32 shiftb = 0; shiftb < ix.start_bits; shiftb += 8) {
-                for (u32 j = (u32) lane; j < 256; j += 32) sh->hist[j] = 0;
-                w_sync();
-                for (u32 base = 0; base < nc; base += 32) {
-                    u32 g = base + (u32) lane;
-                    if (g < nc) s_atomic_add(&sh->hist[(src[g].x >> shiftb) & 0xFFu], 1u);
-                }
-                w_sync();
-                // exclusive scan of the 256 bins (8 per lane)
-                u32 loc[8], sum = 0;
-#pragma unroll
-                for (u32 j = 0; j < 8; j++) { loc[j] = sh->hist[(u32) lane * 8 + j]; sum += loc[j]; }
-                u32 tot, basev = w_exscan(sum, &tot);
-#pragma unroll
-                for (u32 j = 0; j < 8; j++) { sh->hist[(u32) lane * 8 + j] = basev; basev += loc[j]; }
-                w_sync();
-                for (u32 base = 0; base < nc; base += 32) {
-                    u32 g = base + (u32) lane;
-                    bool a = g < nc;
-                    uint4 k = make_uint4(0, 0, 0, 0);
-                    if (a) k = src[g];
-                    u32 dg = a ? ((k.x >> shiftb) & 0xFFu) : 0x100u + (u32) lane;  // inactive lanes: unique digit
-                    u32 peers = w_match(dg);
-                    u32 rank = (u32) d_popc(peers & w_lanemask_lt());
-                    int leader = d_ffs(peers) - 1;
-                    u32 bpos = 0;
-                    if (a && lane == leader) bpos = s_atomic_add(&sh->hist[dg], (u32) d_popc(peers));
-                    bpos = w_shfl(bpos, leader);
-                    if (a) dst[bpos + rank] = k;
-                    w_sync();
-                }
-                uint4 *tmp = src; src = dst; dst = tmp;
-            }
-            // runs of equal fm_start: order by (fm_end, seed_prob, emission index)
-            for (u32 base = 0; base < nc; base += 32) {
-                u32 g = base + (u32) lane;
-                bool head = false;
-                if (g < nc) {
-                    u32 s = src[g].x;
-                    head = (g == 0 || src[g - 1].x != s) && (g + 1 < nc && src[g + 1].x == s);
-                }
-                if (head) {
-                    u32 s = src[g].x;
-                    u32 e = g + 1;
-                    while (e < nc && src[e].x == s) e++;
-                    for (u32 i = g + 1; i < e; i++) {
-                        uint4 key = src[i];
-                        float kp = u2f(key.z);
-                        u32 j = i;
-                        while (j > g) {
-                            uint4 o = src[j - 1];
-                            float op = u2f(o.z);
-                            bool gt = o.y > key.y || (o.y == key.y && (kp < op || (!(op < kp) && (o.w >> 16) > (key.w >> 16))));
-                            if (!gt) break;
-                            src[j] = o;
-                            j--;
-                        }
-                        src[j] = key;
-                    }
-                }
-                w_sync();
-            }
-            const uint4 *sk = src;   // sorted keys
-
-            // ---- D. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603)
-            u32 carry_kmer = UNC_NKMER, carry_maxend = 0;
-            for (u32 base = 0; base < nc; base += 32) {
-                u32 g = base + (u32) lane;
-                bool a = g < nc;
-                uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
-                if (a) cur = sk[g];
-                bool has_next = a && g + 1 < nc;
-                if (has_next) nxt = sk[g + 1];
-                u32 kmer = cur.w & UNC_KMASK;
-                u32 pk = w_shfl_up(kmer, 1);
-                if (lane == 0) pk = carry_kmer;
-                bool run_start = a && kmer != pk;
-                bool same_next = has_next && (nxt.w & UNC_KMASK) == kmer;
-                bool dup = has_next && nxt.x == cur.x && nxt.y == cur.y;
-                bool prob_ok = a && sh->probs[kmer] >= source_prob;
-                // segmented inclusive max-scan of fm_end over the run
-                u32 mx = cur.y; bool hd = run_start || !a;
-                if (lane == 0 && a && !run_start) { mx = mx > carry_maxend ? mx : carry_maxend; }
-                for (int d = 1; d < 32; d <<= 1) {
-                    u32 omx = w_shfl_up(mx, d); u32 ohd = w_shfl_up(hd ? 1u : 0u, d);
-                    if (lane >= d && !hd) { mx = omx > mx ? omx : mx; hd = ohd != 0; }
-                }
-                uint2 kr = tb->kmer_range[kmer];
-                bool begin_v = run_start && prob_ok && kr.x <= cur.x - 1u;
-                u32 as = mx + 1u, ae = same_next ? nxt.x - 1u : kr.y;
-                bool after_v = a && !dup && prob_ok && as <= ae;
-                u32 cnt = (begin_v ? 1u : 0u) + (after_v ? 1u : 0u), tot;
-                u32 off = w_exscan(cnt, &tot);
-                u32 sidx = ns_added + off;    // sources (that would be) added before this element
-                // sources_added_[kmer] is set at a run start while the buffer is not full
-                if (run_start && prob_ok && nc + sidx < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
-                if (begin_v && nc + sidx < maxp) {
-                    write_source(next + (size_t) (nc + sidx) * 8, kr.x, cur.x - 1u, kmer, sh->probs[kmer], event_i);
-                    onext[nc + sidx] = (u16) (nc + sidx);
-                }
-                u32 sidx2 = sidx + (begin_v ? 1u : 0u);
-                if (after_v && nc + sidx2 < maxp) {
-                    write_source(next + (size_t) (nc + sidx2) * 8, as, ae, kmer, sh->probs[kmer], event_i);
-                    onext[nc + sidx2] = (u16) (nc + sidx2);
-                }
-                ns_added += tot;
-                if (nc + ns_added > maxp) ns_added = maxp - nc;
-                u32 emit = cur.w >> 16;
-                if (a) onext[g] = (u16) (emit | (dup ? UNC_INVALID : 0u));
-                // update_seeds(child, false): unique, move-headed, full-length, probable paths
-                bool seed = a && !dup && ((cur.w >> 10) & 1u);
-                u32 sav = 0;
-                if (seed) {
-                    next[(size_t) emit * 8 + 1].y = 1u;   // sa_checked_
-                    sav = unc_sa(ix, cur.x, &my_steps, &my_blocks);
-                }
-                u32 m_seed = w_ballot(seed);
-                while (m_seed) {
-                    int l = d_ffs(m_seed) - 1;
-                    m_seed &= m_seed - 1;
-                    u32 sv = w_shfl(sav, l), mc = (w_shfl(cur.w, l) >> 11) & 0x1Fu;
-                    trk_add_seed(trk, p, ix.seq_len - sv, mc, event_i);
-                    cn.n_seeds++;
-                }
-                carry_kmer = w_shfl(kmer, 31);
-                carry_maxend = w_shfl(mx, 31);
-            }
-        }
-        w_sync();
-        nn = nc + ns_added;
-
-        // ---- E. fresh sources for every sufficiently probable k-mer without one
-        //         (reference src/mapper.cpp:605-624)
-        for (u32 j = 0; j < 32 && nn < maxp; j++) {
-            u32 k = j * 32 + (u32) lane;
-            u32 fw = sh->flags[j];
-            uint2 kr = tb->kmer_range[k];
-            float pk = sh->probs[k];
-            bool add = !((fw >> lane) & 1u) && pk >= source_prob && kr.x <= kr.y;
-            u32 m_add = w_ballot(add);
-            u32 room = maxp - nn;
-            u32 visited = 0xFFFFFFFFu;
-            if ((u32) d_popc(m_add) >= room) {
-                // the room-th add fills the buffer; k-mers after it are never visited
-                u32 mm = m_add;
-                for (u32 q = 1; q < room; q++) mm &= mm - 1;
-                int last = d_ffs(mm) - 1;
-                visited = last == 31 ? 0xFFFFFFFFu : ((2u << last) - 1u);
-                m_add &= visited;
-            }
-            u32 rank = (u32) d_popc(m_add & w_lanemask_lt());
-            if ((m_add >> lane) & 1u) {
-                write_source(next + (size_t) (nn + rank) * 8, kr.x, kr.y, k, pk, event_i);
-                onext[nn + rank] = (u16) (nn + rank);
-            }
-            w_sync();
-            if (lane == 0) sh->flags[j] = fw & ~visited;
-            nn += (u32) d_popc(m_add);
-        }
-        w_sync();
-        cn.n_sources += nn - nc;
-        prev_size = nn;
-        gen ^= 1u;
-
-        // ---- F. confident mapping? (reference src/mapper.cpp:631-653)
-        if (trk.overflow) break;
-        if (trk_get_final(trk, p)) { mapped = true; break; }
+        n_seeds += n;
+        u32 v = (trk.overflow || *(volatile u32 *) &sh->wk_overflow) ? 2u : (trk_get_final(trk, p) ? 1u : 0u);
+        if (v) { verdict = v; final_event = i; }
+        if (lane == 0) *(volatile u32 *) &sh->verdict[i & 1u] = v;
+        i++;
     }
-
-    // ---- PAF coordinates (reference src/mapper.cpp:708-728, bwa_index.hpp:213-220)
-    for (int d = 16; d > 0; d >>= 1) { my_blocks += w_shfl(my_blocks, lane ^ d); my_steps += w_shfl(my_steps, lane ^ d); }
+    // all workers have passed the final barrier: their counters are in shared memory
     if (lane == 0) {
+        const float mel = B.mean_event_len[r];
+        const float bp_per_samp = f_div(p.bp_per_sec, p.sample_rate);
         DevRec o;
-        o.mapped = 0; o.fwd = 0; o.rid = -1; o.status = trk.overflow ? -7 : 0;
-        o.n_events = n_ev; o.events_used = event_i; o.matches = 0; o.n_clusters = trk.n_live;
+        o.mapped = 0; o.fwd = 0; o.rid = -1; o.status = verdict == 2u ? -7 : 0;
+        o.n_events = B.n_events[r]; o.events_used = final_event; o.matches = 0; o.n_clusters = trk.n_live;
         o.rd_len = f_to_u64(f_mul((float) (u64) B.reads[r].n_samples, bp_per_samp));
         o.rd_st = o.rd_en = o.rf_st = o.rf_en = o.rf_len = 0;
-        if (mapped) {
+        if (verdict == 1u) {
             const Clu &sc = trk.max_map;
             bool fwd = sc.ref_st < ix.seq_len / 2u;
             u64 sa_st = fwd ? (u64) sc.ref_st : (u64) ix.seq_len - ((u64) sc.ren_end + 4u);
             o.rd_st = unc_event_to_bp(sc.evt_st - UNC_SEED_LEN, false, mel, bp_per_samp);
             o.rd_en = unc_event_to_bp(sc.evt_en, true, mel, bp_per_samp);
-            o.rd_len = unc_event_to_bp(event_i, true, mel, bp_per_samp);
+            o.rd_len = unc_event_to_bp(final_event, true, mel, bp_per_samp);
             // bns_pos2rid (reference submods/bwa/bntseq.c:354-368)
             int rid = -1;
             if ((long long) sa_st < (long long) B.l_pac) {
@@ -1031,9 +849,447 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
             o.rf_en = rf_st + ((u64) sc.ren_end - (u64) sc.ref_st + 5u);
             o.matches = (sc.total_len + 4u) & 0xFFFFu;
         }
-        o.n_children = cn.n_children; o.n_sources = cn.n_sources; o.n_seeds = cn.n_seeds;
-        o.n_occ_blocks = my_blocks; o.n_sa_steps = my_steps;
+        o.n_children = ((u64) sh->tot_children[1] << 32) | sh->tot_children[0];
+        o.n_sources = ((u64) sh->tot_sources[1] << 32) | sh->tot_sources[0];
+        o.n_seeds = n_seeds;
+        o.n_occ_blocks = sh->cnt_blocks; o.n_sa_steps = sh->cnt_steps;
         B.out[r] = o;
     }
-    w_sync();
+}
+
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+#define PT_DECL unsigned long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = clock64();
+#define PT_MARK(i) { long long _n = clock64(); pt_acc[i] += (unsigned long long) (_n - pt_t); pt_t = _n; }
+#define PT_FLUSH(B, r) if (wt == 0 && (B).dbg) { for (int _i = 0; _i < 8; _i++) (B).dbg[(size_t) (r) * 8 + _i] = pt_acc[_i]; }
+#else
+#define PT_DECL
+#define PT_MARK(i)
+#define PT_FLUSH(B, r)
+#endif
+
+// ---- worker warps: reference src/mapper.cpp:433-663 (map_next) minus the seed clustering
+UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
+                            K2Shared *sh, u32 r, u32 n_limit, u32 *epoch_io) {
+    const int lane = w_lane();
+    const u32 wt = (u32) c_tid() - 32u, nwt = (u32) c_nthreads() - 32u;   // worker thread index / count
+    const u32 ww = wt >> 5, nwk = nwt >> 5;                               // worker warp index / count
+    const K2Tables *tb = &sh->tb;
+    const u32 maxp = p.max_paths;
+    const float scale = B.scale[r], shift = B.shift[r];
+    const float *events = B.events + (size_t) r * B.ev_stride;
+    const float source_prob = tb->thresh[0];
+    u64 n_children = 0, n_sources = 0;                 // committed (events confirmed by the tracker)
+    u32 pend_children = 0, pend_sources = 0;           // of the event in flight
+    u32 my_blocks = 0, my_steps = 0, pend_blocks = 0, pend_steps = 0;
+    u32 epoch = *epoch_io;
+    u32 prev_size = 0, gen = 0, event_i = 0;
+    const u32 npass = (ix.start_bits + K2_RBITS - 1) / K2_RBITS;
+    PT_DECL
+
+    for (; event_i < n_limit; event_i++) {
+        const float event = f_add(f_mul(scale, events[event_i]), shift);
+        PT_MARK(7)
+
+        // ---- A. pore-model probabilities (reference src/mapper.cpp:443-445)
+        for (u32 k = wt; k < UNC_NKMER; k += nwt)
+            sh->probs[k] = unc_match_prob(event, d_ldg(ix.lv_mean + k), d_ldg(ix.lv_var2 + k), d_ldg(ix.lognorm + k));
+        c_sync_sub(1, (int) nwt);
+        PT_MARK(0)
+
+        uint4 *prev = W.paths + (size_t) gen * maxp * 8, *next = W.paths + (size_t) (gen ^ 1u) * maxp * 8;
+        const u16 *oprev = W.order + (size_t) gen * maxp;
+        u16 *onext = W.order + (size_t) (gen ^ 1u) * maxp;
+        uint4 *ckA = W.ckey, *ckB = W.ckey + maxp;
+        uint2 *rlist = W.rlist + (size_t) (event_i & 1u) * W.rl_cap;
+        const u32 slot_prev = (event_i + 22u) % UNC_RING, slot_new = event_i % UNC_RING, slot_old = (event_i + 1u) % UNC_RING;
+
+        // ---- B. extend every previous path (reference src/mapper.cpp:455-524).
+        //      relay carry: [0] children emitted so far (capped at max_paths), [1] seed rows of
+        //      ended paths so far
+        epoch++;
+        const u32 nch_prev = (prev_size + 31u) >> 5;
+        {
+            // software prefetch of the next chunk's order entry + record head
+            u32 oi_n = UNC_INVALID; uint4 q0_n = make_uint4(0, 0, 0, 0), q1_n = make_uint4(0, 0, 0, 0);
+            if (ww < nch_prev) {
+                u32 pi = ww * 32 + (u32) lane;
+                if (pi < prev_size) oi_n = oprev[pi];
+                if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) (oi_n & 0x7FFFu) * 8; q0_n = pr[0]; q1_n = pr[1]; }
+            }
+            for (u32 c = ww; c < nch_prev; c += nwk) {
+                const u32 oi = oi_n;
+                const uint4 q0 = q0_n, q1 = q1_n;
+                const bool valid = !(oi & UNC_INVALID);
+                const uint4 *prec = prev + (size_t) (oi & 0x7FFFu) * 8;
+                if (c + nwk < nch_prev) {
+                    u32 pi = (c + nwk) * 32 + (u32) lane;
+                    oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
+                    if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) (oi_n & 0x7FFFu) * 8; q0_n = pr[0]; q1_n = pr[1]; }
+                }
+                u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
+                u32 moves = q0.w, sa_checked = q1.y;
+                u32 want = 0; bool stay_ok = false;
+                float cprob[5]; u32 cst[5], cen[5], ckm[5];
+                if (valid) {
+                    u32 len = en - st + 1u;
+                    float thr = tb->thresh[32 + d_clz(len)];
+                    float pk = sh->probs[kmer];
+                    stay_ok = stays < p.max_consec_stay && pk >= thr;
+                    cprob[0] = pk; cst[0] = st; cen[0] = en; ckm[0] = kmer;
+#pragma unroll
+                    for (u32 b = 0; b < 4; b++) {
+                        u32 nk = ((kmer << 2) & UNC_KMASK) | b;
+                        float pb = sh->probs[nk];
+                        ckm[b + 1] = nk; cprob[b + 1] = pb;
+                        if (!(pb < thr)) want |= 1u << b;   // `if (prob < thresh) continue;`
+                    }
+                }
+                u32 cmask = stay_ok ? 1u : 0u;
+                if (want) {
+                    u32 ns[4], ne[4];
+                    u32 ok = unc_neighbors(ix, st, en, want, ns, ne, &pend_blocks);
+#pragma unroll
+                    for (u32 b = 0; b < 4; b++)
+                        if ((ok >> b) & 1u) { cmask |= 2u << b; cst[b + 1] = ns[b]; cen[b + 1] = ne[b]; }
+                }
+                u32 cc = (u32) d_popc(cmask), total;
+                u32 off = w_exscan(cc, &total);
+                // a childless, not yet SA-checked path may end here with seeds
+                // (reference src/mapper.cpp:513-519 -> update_seeds(path, true), is_seed_valid :842-863)
+                u32 rcnt = 0, mc = (u32) d_popc(moves);
+                if (valid && cc == 0 && !sa_checked) {
+                    u32 len = en - st + 1u;
+                    bool ended = plen == UNC_SEED_LEN && u2f(q1.x) >= p.min_seed_prob &&
+                                 ((len == 1 && (moves & 1u) && (float) ((plen - mc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f)) ||
+                                  (len <= p.max_rep_copy && mc >= p.min_rep_len));
+                    if (ended) rcnt = len;
+                }
+                u32 rtot, roff = w_exscan(rcnt, &rtot);
+                // ring + the two cumulative sums the children need (issued before the relay wait)
+                uint4 r2, r3, r4, r5, r6, r7;
+                float prevC = 0.0f, oldC = 0.0f;
+                if (valid && cc > 0) {
+                    r2 = prec[2]; r3 = prec[3]; r4 = prec[4]; r5 = prec[5]; r6 = prec[6]; r7 = prec[7];
+                    const float *pring = (const float *) (prec + 2);
+                    prevC = pring[slot_prev]; oldC = pring[slot_old];
+                }
+                // relay (lane 0 only on the critical path).  Fast case: the buffer cannot fill inside
+                // this chunk, so every valid parent is reached and the carry-out is known at once.
+                u32 nn = 0, rows_before = 0, fast = 1;
+                if (lane == 0) {
+                    uint4 cin = k2_relay_wait(&sh->ch, c, epoch);
+                    nn = cin.y; rows_before = cin.z;
+                    fast = nn + total < maxp ? 1u : 0u;
+                    if (fast) k2_relay_publish(&sh->ch, c, epoch, nn + total, rows_before + rtot, 0);
+                }
+                nn = w_shfl(nn, 0); rows_before = w_shfl(rows_before, 0); fast = w_shfl(fast, 0);
+                // sequential semantics of the full buffer: a parent is reached iff the buffer was not
+                // yet full when the scan arrived at it
+                bool reached = valid && (nn + off < maxp);
+                if (!fast) {
+                    if (!reached) rcnt = 0;
+                    roff = w_exscan(rcnt, &rtot);
+                    if (lane == 0)
+                        k2_relay_publish(&sh->ch, c, epoch, nn + total > maxp ? maxp : nn + total, rows_before + rtot, 0);
+                }
+                if (reached && cc > 0) {
+                    u32 ci = nn + off;
+#pragma unroll
+                    for (u32 j = 0; j < 5; j++) {
+                        if (!((cmask >> j) & 1u) || ci >= maxp) continue;
+                        u32 move = j > 0 ? 1u : 0u;
+                        u32 nlen = plen + (plen < UNC_SEED_LEN ? 1u : 0u);
+                        u32 nmoves = ((moves << 1) | move) & UNC_PATH_MASK;
+                        u32 nstays = move ? 0u : stays + 1u;
+                        float newC = f_add(prevC, cprob[j]);
+                        float sp;
+                        if (plen == UNC_SEED_LEN) { sp = f_div(f_sub(newC, oldC), 22.0f); nmoves |= UNC_PATH_TAIL; }
+                        else sp = f_div(newC, (float) nlen);
+                        u32 spb = f2u(sp);
+                        uint4 *crec = next + (size_t) ci * 8;
+                        crec[0] = make_uint4(cst[j], cen[j], ckm[j] | (nlen << 16) | (nstays << 24), nmoves);
+                        crec[1] = make_uint4(spb, sa_checked, 0u, 0u);
+                        crec[2] = r2; crec[3] = r3; crec[4] = r4; crec[5] = r5; crec[6] = r6; crec[7] = r7;
+                        ((float *) (crec + 2))[slot_new] = newC;
+                        // is_seed_valid(path_ended = false) of the child (reference src/mapper.cpp:842-863)
+                        u32 cmc = (u32) d_popc(nmoves);
+                        u32 stay_count = (nlen - cmc) & 0xFFu;
+                        bool seedable = nlen == UNC_SEED_LEN && sp >= p.min_seed_prob && cst[j] == cen[j] && (nmoves & 1u) &&
+                                        (float) stay_count <= f_mul(p.max_stay_frac, 22.0f);
+                        ckA[ci] = make_uint4(cst[j], cen[j], spb, ckm[j] | (seedable ? 1u << 10 : 0u) | (cmc << 11) | (ci << 16));
+                        ci++;
+                    }
+                }
+                if (rcnt) {   // seed rows of an ended path, in parent order: (row, move_count | ended flag)
+                    if (rows_before + roff + rcnt <= W.rl_cap) {
+                        for (u32 i = 0; i < rcnt; i++) rlist[rows_before + roff + i] = make_uint2(st + i, mc | 0x100u);
+                    } else sh->wk_overflow = 1;
+                }
+            }
+        }
+        c_sync_sub(1, (int) nwt);
+        PT_MARK(1)
+        u32 nc = 0, n_rows = 0;
+        if (nch_prev) { uint4 fin = s_load_v4(&sh->ch.slot[nch_prev - 1]); nc = fin.y; n_rows = fin.z; }
+        if (n_rows > W.rl_cap) n_rows = W.rl_cap;
+        const u32 n_ended_rows = n_rows;
+        pend_children = nc;
+
+        u32 ns_added = 0;   // sources appended after the children
+        u32 n_child_seeds = 0;
+        if (nc > 0) {
+            // ---- C. order children by (fm_start, fm_end, seed_prob, emission index)
+            //         (reference src/mapper.cpp:531 pdqsort + operator< :866-871): LSD radix sort on
+            //         fm_start, 8-bit digits; worker warp w owns the w-th contiguous segment of the
+            //         array in every pass, so the scatter is stable without inter-warp ordering
+            uint4 *src = ckA, *dst = ckB;
+            const u32 nch = (nc + 31u) >> 5;
+            const u32 seg_ch = (nch + nwk - 1) / nwk, seg_len = seg_ch * 32u;
+            const u32 c_lo = ww * seg_ch, c_hi = (c_lo + seg_ch < nch) ? c_lo + seg_ch : nch;
+            // digit counts of pass 0
+            for (u32 c = c_lo; c < c_hi; c++) {
+                u32 g = c * 32 + (u32) lane;
+                bool a = g < nc;
+                u32 dg = a ? (src[g].x & (K2_RB - 1u)) : K2_RB + (u32) lane;
+                u32 peers = w_match(dg);
+                if (a && lane == d_ffs(peers) - 1) sh->hist_next[dg * K2_MAXSEG + ww] += (u32) d_popc(peers);
+                w_sync();
+            }
+            c_sync_sub(1, (int) nwt);
+            for (u32 pass = 0; pass < npass; pass++) {
+                const u32 sb = pass * K2_RBITS;
+                k2_wk_exscan_bins(sh, sh->hist_next, sh->hist_cur, wt, nwt);
+                uint4 kn = make_uint4(0, 0, 0, 0);
+                if (c_lo < c_hi && c_lo * 32 + (u32) lane < nc) kn = src[c_lo * 32 + (u32) lane];
+                for (u32 c = c_lo; c < c_hi; c++) {
+                    u32 g = c * 32 + (u32) lane;
+                    bool a = g < nc;
+                    uint4 k = kn;
+                    if (c + 1 < c_hi && g + 32 < nc) kn = src[g + 32];
+                    u32 dg = a ? ((k.x >> sb) & (K2_RB - 1u)) : K2_RB + (u32) lane;  // inactive lanes: unique digit
+                    u32 peers = w_match(dg);
+                    u32 rank = (u32) d_popc(peers & w_lanemask_lt());
+                    int leader = d_ffs(peers) - 1;
+                    u32 bpos = 0;
+                    if (a && lane == leader) {
+                        bpos = sh->hist_cur[dg * K2_MAXSEG + ww];
+                        sh->hist_cur[dg * K2_MAXSEG + ww] = bpos + (u32) d_popc(peers);
+                    }
+                    w_sync();                      // the next chunk's leaders read these counters
+                    bpos = w_shfl(bpos, leader);
+                    if (a) {
+                        u32 pos = bpos + rank;
+                        dst[pos] = k;
+                        if (pass + 1 < npass)
+                            s_atomic_add(&sh->hist_next[((k.x >> (sb + K2_RBITS)) & (K2_RB - 1u)) * K2_MAXSEG + pos / seg_len], 1u);
+                    }
+                }
+                c_sync_sub(1, (int) nwt);
+                uint4 *tmp = src; src = dst; dst = tmp;
+            }
+            PT_MARK(2)
+            // runs of equal fm_start: order by (fm_end, seed_prob, emission index)
+            for (u32 g = wt; g < nc; g += nwt) {
+                u32 s = src[g].x;
+                bool head = (g == 0 || src[g - 1].x != s) && (g + 1 < nc && src[g + 1].x == s);
+                if (head) {
+                    u32 e = g + 1;
+                    while (e < nc && src[e].x == s) e++;
+                    for (u32 i = g + 1; i < e; i++) {
+                        uint4 key = src[i];
+                        float kp = u2f(key.z);
+                        u32 j = i;
+                        while (j > g) {
+                            uint4 o = src[j - 1];
+                            float op = u2f(o.z);
+                            bool gt = o.y > key.y || (o.y == key.y && (kp < op || (!(op < kp) && (o.w >> 16) > (key.w >> 16))));
+                            if (!gt) break;
+                            src[j] = o;
+                            j--;
+                        }
+                        src[j] = key;
+                    }
+                }
+            }
+            c_sync_sub(1, (int) nwt);
+            PT_MARK(3)
+            const uint4 *sk = src;   // sorted keys
+
+            // ---- D. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603).
+            //      relay carry: k-mer of the previous element, running max fm_end of its k-mer run,
+            //      sources added so far, child seeds so far
+            epoch++;
+            for (u32 c = ww; c < nch; c += nwk) {
+                u32 g = c * 32 + (u32) lane;
+                bool a = g < nc;
+                uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+                if (a) cur = sk[g];
+                bool has_next = a && g + 1 < nc;
+                if (has_next) nxt = sk[g + 1];
+                u32 kmer = a ? (cur.w & UNC_KMASK) : UNC_NKMER + 1u;
+                bool same_next = has_next && (nxt.w & UNC_KMASK) == kmer;
+                bool dup = has_next && nxt.x == cur.x && nxt.y == cur.y;
+                bool prob_ok = a && sh->probs[kmer & UNC_KMASK] >= source_prob;
+                uint2 kr = tb->kmer_range[kmer & UNC_KMASK];
+                u32 pk = w_shfl_up(kmer, 1);
+                bool seed = a && !dup && ((cur.w >> 10) & 1u);
+                u32 m_seed = w_ballot(seed);
+                // local (carry-free) k-mer run structure: lane 0 is treated as a run head here
+                bool lhead = lane == 0 || kmer != pk || !a;
+                u32 m_lhead = w_ballot(lhead);
+                u32 mx = cur.y; bool hd = lhead;
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 omx = w_shfl_up(mx, d); u32 ohd = w_shfl_up(hd ? 1u : 0u, d);
+                    if (lane >= d && !hd) { mx = omx > mx ? omx : mx; hd = ohd != 0; }
+                }
+                // lanes of the leading run (before the first local head after lane 0)
+                u32 first_head = (m_lhead & ~1u) ? (u32) d_ffs(m_lhead & ~1u) - 1u : 32u;
+                bool in_lead = a && (u32) lane < first_head;
+                u32 kmer0 = w_shfl(kmer, 0);
+                u32 ckmer = UNC_NKMER, cmax = 0, ns_before = 0, seeds_before = 0;
+                if (lane == 0) {
+                    uint4 cin = k2_relay_wait(&sh->ch, c, epoch);
+                    if (c > 0) { cmax = cin.y; ckmer = cin.z & 0x7FFu; ns_before = cin.z >> 11; seeds_before = cin.w; }
+                }
+                ckmer = w_shfl(ckmer, 0); cmax = w_shfl(cmax, 0);
+                const bool cont = kmer0 == ckmer;              // the leading run continues the previous chunk's
+                if (in_lead && cont) mx = mx > cmax ? mx : cmax;
+                bool run_start = a && (lane == 0 ? !cont : (kmer != pk));
+                bool begin_v = run_start && prob_ok && kr.x <= cur.x - 1u;
+                u32 as = mx + 1u, ae = same_next ? nxt.x - 1u : kr.y;
+                bool after_v = a && !dup && prob_ok && as <= ae;
+                u32 m_b = w_ballot(begin_v), m_a = w_ballot(after_v);
+                u32 tot = (u32) d_popc(m_b) + (u32) d_popc(m_a);
+                u32 kmer31 = w_shfl(kmer, 31), mx31 = w_shfl(mx, 31);
+                if (lane == 0) {
+                    u32 nsn = nc + ns_before + tot > maxp ? maxp - nc : ns_before + tot;
+                    k2_relay_publish(&sh->ch, c, epoch, mx31, (kmer31 & 0x7FFu) | (nsn << 11), seeds_before + (u32) d_popc(m_seed));
+                }
+                ns_before = w_shfl(ns_before, 0); seeds_before = w_shfl(seeds_before, 0);
+                const u32 lt = w_lanemask_lt();
+                u32 off = (u32) d_popc(m_b & lt) + (u32) d_popc(m_a & lt);
+                u32 sidx = ns_before + off;    // sources (that would be) added before this element
+                // sources_added_[kmer] is set at a run start while the buffer is not full
+                if (run_start && prob_ok && nc + sidx < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
+                if (begin_v && nc + sidx < maxp) {
+                    write_source(next + (size_t) (nc + sidx) * 8, kr.x, cur.x - 1u, kmer, sh->probs[kmer], event_i);
+                    onext[nc + sidx] = (u16) (nc + sidx);
+                }
+                u32 sidx2 = sidx + (begin_v ? 1u : 0u);
+                if (after_v && nc + sidx2 < maxp) {
+                    write_source(next + (size_t) (nc + sidx2) * 8, as, ae, kmer, sh->probs[kmer], event_i);
+                    onext[nc + sidx2] = (u16) (nc + sidx2);
+                }
+                u32 emit = cur.w >> 16;
+                if (a) onext[g] = (u16) (emit | (dup ? UNC_INVALID : 0u));
+                // update_seeds(child, false): unique, move-headed, full-length, probable paths
+                if (seed) {
+                    next[(size_t) emit * 8 + 1].y = 1u;   // sa_checked_
+                    u32 ri = n_ended_rows + seeds_before + (u32) d_popc(m_seed & lt);
+                    if (ri < W.rl_cap) rlist[ri] = make_uint2(cur.x, (cur.w >> 11) & 0x1Fu);
+                    else sh->wk_overflow = 1;
+                }
+            }
+            c_sync_sub(1, (int) nwt);
+            PT_MARK(4)
+            { uint4 fin = s_load_v4(&sh->ch.slot[nch - 1]); ns_added = fin.z >> 11; n_child_seeds = fin.w; }
+        }
+        n_rows = n_ended_rows + n_child_seeds;
+        if (n_rows > W.rl_cap) n_rows = W.rl_cap;
+        u32 nn = nc + ns_added;
+
+        // ---- S. suffix-array lookups for all seed rows of the event
+        //         (reference src/mapper.cpp:673-681: sa_end = fmi.size() - fmi.sa(s))
+        for (u32 i = wt; i < n_rows; i += nwt) {
+            uint2 e = rlist[i];
+            e.x = ix.seq_len - unc_sa(ix, e.x, &pend_steps, &pend_blocks);
+            rlist[i] = e;
+        }
+        if (ww == 0) {
+            // ---- E. fresh sources for every sufficiently probable k-mer without one
+            //         (reference src/mapper.cpp:605-624)
+            for (u32 j = 0; j < 32 && nn < maxp; j++) {
+                u32 k = j * 32 + (u32) lane;
+                u32 fw = sh->flags[j];
+                uint2 kr = tb->kmer_range[k];
+                float pk = sh->probs[k];
+                bool add = !((fw >> lane) & 1u) && pk >= source_prob && kr.x <= kr.y;
+                u32 m_add = w_ballot(add);
+                u32 room = maxp - nn;
+                u32 visited = 0xFFFFFFFFu;
+                if ((u32) d_popc(m_add) >= room) {
+                    // the room-th add fills the buffer; k-mers after it are never visited
+                    u32 mm = m_add;
+                    for (u32 q = 1; q < room; q++) mm &= mm - 1;
+                    int last = d_ffs(mm) - 1;
+                    visited = last == 31 ? 0xFFFFFFFFu : ((2u << last) - 1u);
+                    m_add &= visited;
+                }
+                u32 rank = (u32) d_popc(m_add & w_lanemask_lt());
+                if ((m_add >> lane) & 1u) {
+                    write_source(next + (size_t) (nn + rank) * 8, kr.x, kr.y, k, pk, event_i);
+                    onext[nn + rank] = (u16) (nn + rank);
+                }
+                w_sync();
+                if (lane == 0) sh->flags[j] = fw & ~visited;
+                nn += (u32) d_popc(m_add);
+            }
+            if (lane == 0) { sh->bc[1] = nn; *(volatile u32 *) &sh->n_rows[event_i & 1u] = n_rows; }
+        }
+        PT_MARK(5)
+        // ---- hand the event's seeds to the tracker; learn the outcome of the previous event
+        c_sync();                                                     // X_e
+        PT_MARK(6)
+        nn = sh->bc[1];
+        pend_sources = nn - nc;
+        const u32 v = event_i > 0 ? *(volatile u32 *) &sh->verdict[(event_i - 1u) & 1u] : 0u;
+        if (v) break;                                                 // event_i's work is discarded
+        n_children += pend_children; n_sources += pend_sources;
+        my_blocks += pend_blocks; my_steps += pend_steps;
+        pend_children = pend_sources = pend_blocks = pend_steps = 0;
+        prev_size = nn;
+        gen ^= 1u;
+    }
+    *epoch_io = epoch;
+    PT_FLUSH(B, r)
+    for (int d = 16; d > 0; d >>= 1) { my_blocks += w_shfl(my_blocks, lane ^ d); my_steps += w_shfl(my_steps, lane ^ d); }
+    if (lane == 0) { s_atomic_add(&sh->cnt_blocks, my_blocks); s_atomic_add(&sh->cnt_steps, my_steps); }
+    if (wt == 0) {
+        sh->tot_children[0] = (u32) n_children; sh->tot_children[1] = (u32) (n_children >> 32);
+        sh->tot_sources[0] = (u32) n_sources; sh->tot_sources[1] = (u32) (n_sources >> 32);
+    }
+    c_sync();                                                         // Y: final barrier
+}
+
+// One read mapped by one CTA.  reference src/mapper.cpp:188-200 (map_read).
+UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
+                             K2Shared *sh, u32 r, u32 *epoch_io) {
+    const u32 tid = (u32) c_tid();
+    const u32 n_ev = B.n_events[r];
+    const u32 n_limit = n_ev < p.max_events ? n_ev : p.max_events;
+    if (tid < 32) sh->flags[tid] = 0;
+    if (tid == 0) {
+        sh->cnt_blocks = 0; sh->cnt_steps = 0; sh->wk_overflow = 0;
+        sh->verdict[0] = sh->verdict[1] = 0; sh->n_rows[0] = sh->n_rows[1] = 0; sh->bc[1] = 0;
+    }
+    for (u32 b = tid; b < K2_RB * K2_MAXSEG; b += (u32) c_nthreads()) sh->hist_next[b] = 0;
+    c_sync();
+    if (tid < 32) unc_k2_tracker(ix, p, B, W, sh, r, n_limit);
+    else unc_k2_workers(ix, p, B, W, sh, r, n_limit, epoch_io);
+    c_sync();
+}
+
+// Persistent CTA body: stage the tables, then pull reads from the global queue.
+// Needs at least 2 warps (tracker + >= 1 worker) and at most 1 + K2_MAXSEG.
+UNC_DEV void unc_k2_cta_main(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W, K2Shared *sh) {
+    unc_k2_cta_setup(ix, p, sh);
+    u32 epoch = 0;
+    for (;;) {
+        if (c_tid() == 0) sh->bc[0] = d_atomic_add(B.queue, 1u);
+        c_sync();
+        u32 r = sh->bc[0];
+        c_sync();
+        if (r >= B.n_reads) break;
+        unc_k2_map_read(ix, p, B, W, sh, r, &epoch);
+    }
 }

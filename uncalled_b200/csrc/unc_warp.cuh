@@ -16,6 +16,16 @@
 #define UNC_FULL 0xffffffffu
 
 UNC_DEV int w_lane() { return (int) (threadIdx.x & 31); }
+UNC_DEV int c_tid() { return (int) threadIdx.x; }
+UNC_DEV int c_nthreads() { return (int) blockDim.x; }
+UNC_DEV void c_sync() { __syncthreads(); }
+// named barrier `id` (1..15) over `count` threads (a multiple of 32): bar.sync id, count
+UNC_DEV void c_sync_sub(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+UNC_DEV void c_fence() { __threadfence_block(); }
+#ifndef K2_SPIN_NS
+#define K2_SPIN_NS 40
+#endif
+UNC_DEV void w_spin() { if (K2_SPIN_NS) __nanosleep(K2_SPIN_NS); }
 UNC_DEV void w_sync() { __syncwarp(); }
 UNC_DEV uint32_t w_ballot(int p) { return __ballot_sync(UNC_FULL, p); }
 UNC_DEV uint32_t w_shfl(uint32_t v, int src) { return __shfl_sync(UNC_FULL, v, src); }
@@ -45,6 +55,17 @@ UNC_DEV double d_sqrt(double a) { return __dsqrt_rn(a); }
 UNC_DEV uint32_t f_to_u32_x86(float v) { return (uint32_t) (long long) v; }
 UNC_DEV uint64_t f_to_u64(float v) { return (uint64_t) v; }
 template <typename T> UNC_DEV T d_ldg(const T *p) { return __ldg(p); }
+// single 128-bit volatile shared-memory accesses (one transaction: payload + flag together)
+UNC_DEV uint4 s_load_v4(const uint4 *p) {
+    uint4 v;
+    unsigned a = (unsigned) __cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+UNC_DEV void s_store_v4(uint4 *p, uint4 v) {
+    unsigned a = (unsigned) __cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 UNC_DEV float u2f(uint32_t v) { return __uint_as_float(v); }
 UNC_DEV uint32_t f2u(float v) { return __float_as_uint(v); }
 #endif

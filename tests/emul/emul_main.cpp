@@ -28,6 +28,7 @@ void *emu_index_load(const char *prefix, const char *preset, const char *model_t
     DevIndex &ix = e->ix;
     ix.bwt = (const uint4 *) h.bwt.data();
     ix.sa = h.sa32.data();
+    ix.sa_full = nullptr;
     ix.lv_mean = h.lv_mean.data(); ix.lv_var2 = h.lv_var2.data(); ix.lognorm = h.lognorm.data();
     ix.thresh = h.thresh;
     ix.primary = (u32) h.primary; ix.seq_len = (u32) h.seq_len;
@@ -91,16 +92,17 @@ int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads,
     if (!run_k2) return 0;
 
     u32 maxp = dp.max_paths;
-    std::vector<uint4> paths((size_t) 2 * maxp * 8), ckey((size_t) 2 * maxp);
-    std::vector<u16> order((size_t) 2 * maxp);
+    const size_t nchmax = (maxp + 31) / 32;
+    std::vector<uint4> paths((size_t) 2 * (nchmax * 160 + maxp) * 8), ckey((size_t) 2 * maxp), cks(nchmax * 160), elist(nchmax * 32);
+    std::vector<u32> order((size_t) 2 * maxp);
     std::vector<uint4> clu((size_t) max_blocks * 32 * 2), dir(max_blocks + 1);
     const u32 rl_cap = 16384;
     std::vector<uint2> rlist(2 * rl_cap);
     DevWork W;
-    W.paths = paths.data(); W.ckey = ckey.data(); W.order = order.data(); W.rlist = rlist.data();
+    W.paths = paths.data(); W.ckey = ckey.data(); W.cks = cks.data(); W.elist = elist.data(); W.order = order.data(); W.rlist = rlist.data();
     W.clu = clu.data(); W.dir = dir.data();
     W.max_blocks = max_blocks; W.rl_cap = rl_cap;
-    K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((maxp + 31) / 32) * sizeof(uint4));
+    K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((maxp + 31) / 32) * 24);
     CtaArgs a = {&e->ix, &dp, &B, &W, sh};
     emu_run_cta(cta_entry, &a, 32 * (n_warps > 0 ? n_warps : 8));   // one persistent CTA maps the whole batch
     free(sh);

@@ -21,10 +21,10 @@ static_assert(sizeof(DevReadDesc) == 32, "DevReadDesc layout");
 // ------------------------------------------------------------------ kernels
 
 #ifndef K2_WARPS
-#define K2_WARPS 4          /* 1 tracker warp + (K2_WARPS-1) worker warps per read */
+#define K2_WARPS 8          /* 1 tracker warp + (K2_WARPS-1) worker warps per read */
 #endif
 #ifndef K2_MIN_CTAS
-#define K2_MIN_CTAS 4
+#define K2_MIN_CTAS 2
 #endif
 #define K2_THREADS (K2_WARPS * 32)
 static_assert(K2_WARPS >= 2 && K2_WARPS - 1 <= K2_MAXSEG, "worker warps must fit the sort segments");
@@ -32,6 +32,14 @@ static_assert(K2_WARPS >= 2 && K2_WARPS - 1 <= K2_MAXSEG, "worker warps must fit
 __global__ void k_kmer_ranges(DevIndex ix, uint2 *out) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < UNC_NKMER) out[k] = unc_kmer_range_compute(ix, k);
+}
+
+// bwt_sa(k) for every row: turns the mapper's <=31-step LF walk per seed into one load.
+__global__ void k_sa_expand(DevIndex ix, u32 *out, u32 n_rows) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_rows) return;
+    u32 a = 0, b = 0;
+    out[k] = unc_sa(ix, k, &a, &b);
 }
 
 __global__ void __launch_bounds__(128) k1_events(DevBatch B, DevParams p) {
@@ -43,14 +51,16 @@ __global__ void __launch_bounds__(128) k1_events(DevBatch B, DevParams p) {
 // and the thresholds in shared memory, then pulls reads from a global queue; the K2_WARPS warps
 // of the CTA cooperate on every event of the read (chained scans through shared memory).
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
-k2_map(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t ckey_stride, size_t order_stride,
-       size_t rlist_stride, size_t clu_stride, size_t dir_stride) {
+k2_map(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t ckey_stride, size_t cks_stride,
+       size_t elist_stride, size_t order_stride, size_t rlist_stride, size_t clu_stride, size_t dir_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K2Shared *sh = (K2Shared *) smem_raw;
     const size_t slot = blockIdx.x;
     DevWork W;
     W.paths = W0.paths + slot * paths_stride;
     W.ckey = W0.ckey + slot * ckey_stride;
+    W.cks = W0.cks + slot * cks_stride;
+    W.elist = W0.elist + slot * elist_stride;
     W.order = W0.order + slot * order_stride;
     W.rlist = W0.rlist + slot * rlist_stride;
     W.clu = W0.clu + slot * clu_stride;
@@ -109,7 +119,7 @@ struct unc_index {
     int device = 0;
     std::vector<uint2> kmer_range;  // host copy
     void *d_bwt = nullptr, *d_sa = nullptr, *d_kr = nullptr, *d_model = nullptr, *d_thresh = nullptr;
-    void *d_seq_off = nullptr, *d_seq_len = nullptr;
+    void *d_seq_off = nullptr, *d_seq_len = nullptr, *d_sa_full = nullptr;
     size_t device_bytes = 0;
 };
 
@@ -132,7 +142,7 @@ struct unc_pool {
     unc_paf_rec *h_out = nullptr;  // pinned staging
     // workspaces
     DevWork W;
-    size_t paths_stride = 0, ckey_stride = 0, order_stride = 0, rlist_stride = 0, clu_stride = 0, dir_stride = 0;
+    size_t paths_stride = 0, ckey_stride = 0, cks_stride = 0, elist_stride = 0, order_stride = 0, rlist_stride = 0, clu_stride = 0, dir_stride = 0;
     uint32_t n_slots = 0, grid = 0;
     size_t smem = 0;
     unc_timing last;
@@ -235,6 +245,18 @@ int unc_index_load(const char *bwa_prefix, const char *preset, const char *model
     ix.seq_len = (u32) h.seq_len;
     for (int i = 0; i < 5; i++) ix.L2[i] = (u32) h.L2[i];
     ix.start_bits = 64 - __builtin_clzll(h.seq_len ? h.seq_len : 1);
+    ix.sa_full = nullptr;
+    {   // expanded suffix array (4 bytes per FM row); skipped when device memory is short
+        size_t free_b = 0, total_b = 0;
+        const size_t need = ((size_t) h.seq_len + 1) * 4;
+        if (!getenv("UNC_NO_SA_EXPAND") && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need < free_b / 4 &&
+            cudaMalloc(&x->d_sa_full, need) == cudaSuccess) {
+            u32 n_rows = (u32) h.seq_len + 1u;
+            k_sa_expand<<<(n_rows + 255) / 256, 256>>>(ix, (u32 *) x->d_sa_full, n_rows);
+            if (cudaDeviceSynchronize() == cudaSuccess) { ix.sa_full = (const u32 *) x->d_sa_full; x->device_bytes += need; }
+            else { unc_index_free(x); return fail(UNC_E_CUDA, "k_sa_expand failed"); }
+        }
+    }
     k_kmer_ranges<<<4, 256>>>(ix, (uint2 *) x->d_kr);
     x->kmer_range.resize(1024);
     cudaError_t e = cudaMemcpy(x->kmer_range.data(), x->d_kr, 1024 * sizeof(uint2), cudaMemcpyDeviceToHost);
@@ -276,7 +298,7 @@ int unc_index_thresholds(const unc_index *x, float out[64]) {
 void unc_index_free(unc_index *x) {
     if (!x) return;
     cudaFree(x->d_bwt); cudaFree(x->d_sa); cudaFree(x->d_kr); cudaFree(x->d_model); cudaFree(x->d_thresh);
-    cudaFree(x->d_seq_off); cudaFree(x->d_seq_len);
+    cudaFree(x->d_seq_off); cudaFree(x->d_seq_len); cudaFree(x->d_sa_full);
     delete x;
 }
 
@@ -300,7 +322,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     for (int i = 0; i < 5; i++) PT(cudaEventCreate(&P->ev[i]));
     cudaDeviceProp prop;
     PT(cudaGetDeviceProperties(&prop, idx->device));
-    P->smem = sizeof(K2Shared) + 16 + (size_t) ((prm->max_paths + 31) / 32) * sizeof(uint4);
+    P->smem = sizeof(K2Shared) + 16 + (size_t) ((prm->max_paths + 31) / 32) * 24;
     PT(cudaFuncSetAttribute(k2_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
     int per_sm = 0;
     PT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_map, K2_THREADS, P->smem));
@@ -309,16 +331,19 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     if (grid > max_reads) grid = max_reads;
     // per-slot workspace sizes
     const size_t maxp = prm->max_paths;
-    P->paths_stride = 2 * maxp * 8;   // uint4
+    const size_t nchmax = (maxp + 31) / 32;
+    P->paths_stride = 2 * (nchmax * 160 + maxp) * 8;   // uint4: chunk-local child slots + sources, two generations
     P->ckey_stride = 2 * maxp;        // uint4
-    P->order_stride = 2 * maxp;       // u16
+    P->cks_stride = nchmax * 160;     // uint4
+    P->elist_stride = nchmax * 32;    // uint4
+    P->order_stride = 2 * maxp;       // u32
     uint64_t longest = max_samples < 0xFFFFFFFFull ? max_samples : 0xFFFFFFFFull;
     // seed clusters: at most a few per event in practice; blocks are >= half full after splits
     uint64_t ev_cap = std::min<uint64_t>(prm->max_events, longest / 3 + 16);
     uint64_t mb = std::max<uint64_t>(1024, ev_cap * 2);
     mb = std::min<uint64_t>(mb, 1u << 17);
     const size_t rl_cap = 64 * 1024;   // seed rows of one event (typically tens)
-    size_t per_slot = P->paths_stride * 16 + P->ckey_stride * 16 + P->order_stride * 2 + 2 * rl_cap * 8 + mb * (UNC_BLK * 32 + 16);
+    size_t per_slot = (P->paths_stride + P->ckey_stride + P->cks_stride + P->elist_stride) * 16 + P->order_stride * 4 + 2 * rl_cap * 8 + mb * (UNC_BLK * 32 + 16);
     size_t free_b = 0, total_b = 0;
     PT(cudaMemGetInfo(&free_b, &total_b));
     size_t fixed = max_samples * 4 + (size_t) max_reads * (sizeof(DevReadDesc) + sizeof(DevRec) + 20) + (64u << 20);
@@ -335,7 +360,9 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     P->W.max_blocks = (u32) mb;
     PT(cudaMalloc(&P->W.paths, (size_t) P->n_slots * P->paths_stride * 16));
     PT(cudaMalloc(&P->W.ckey, (size_t) P->n_slots * P->ckey_stride * 16));
-    PT(cudaMalloc(&P->W.order, (size_t) P->n_slots * P->order_stride * 2));
+    PT(cudaMalloc(&P->W.cks, (size_t) P->n_slots * P->cks_stride * 16));
+    PT(cudaMalloc(&P->W.elist, (size_t) P->n_slots * P->elist_stride * 16));
+    PT(cudaMalloc(&P->W.order, (size_t) P->n_slots * P->order_stride * 4));
     PT(cudaMalloc(&P->W.rlist, (size_t) P->n_slots * P->rlist_stride * 8));
     PT(cudaMalloc(&P->W.clu, (size_t) P->n_slots * P->clu_stride * 16));
     PT(cudaMalloc(&P->W.dir, (size_t) P->n_slots * P->dir_stride * 16));
@@ -361,7 +388,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
 
 void unc_pool_free(unc_pool *P) {
     if (!P) return;
-    cudaFree(P->W.paths); cudaFree(P->W.ckey); cudaFree(P->W.order); cudaFree(P->W.rlist); cudaFree(P->W.clu); cudaFree(P->W.dir);
+    cudaFree(P->W.paths); cudaFree(P->W.ckey); cudaFree(P->W.cks); cudaFree(P->W.elist); cudaFree(P->W.order); cudaFree(P->W.rlist); cudaFree(P->W.clu); cudaFree(P->W.dir);
     cudaFree(P->d_samples); cudaFree(P->d_reads); cudaFreeHost(P->h_reads);
     cudaFree(P->d_events); cudaFree(P->d_normed);
     cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue);
@@ -449,8 +476,8 @@ static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[2], s));
     uint32_t grid = std::min<uint32_t>(P->grid, n);
-    k2_map<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->ckey_stride, P->order_stride,
-                                             P->rlist_stride, P->clu_stride, P->dir_stride);
+    k2_map<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->ckey_stride, P->cks_stride,
+                                             P->elist_stride, P->order_stride, P->rlist_stride, P->clu_stride, P->dir_stride);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[3], s));
     CUDA_TRY(cudaMemcpyAsync(P->h_out, P->d_out, (size_t) n * sizeof(DevRec), cudaMemcpyDeviceToHost, s));

@@ -25,7 +25,7 @@ typedef uint64_t u64;
 #define UNC_RING 23u
 #define UNC_PATH_MASK 0x3FFFFFu
 #define UNC_PATH_TAIL 0x200000u
-#define UNC_INVALID 0x8000u     /* flag in the order[] array: path invalidated by dedup */
+#define UNC_INVALID 0x80000000u /* flag in the order[] array: path invalidated by dedup */
 #define UNC_BLK 32u             /* seed-cluster block capacity (one entry per lane) */
 
 // ------------------------------------------------------------------ device image
@@ -33,6 +33,7 @@ typedef uint64_t u64;
 struct DevIndex {
     const uint4 *bwt;      // 64-byte Occ blocks as in the .bwt file: 4 x u64 counts, 8 x u32 BWT words
     const u32 *sa;         // sampled SA (every 32 rows) narrowed to u32; sa[0] = 0xFFFFFFFF
+    const u32 *sa_full;    // optional: bwt_sa(k) for every row k, expanded on the device at index load
     const uint2 *kmer_range;  // 1024 x (start, end) FM ranges
     const float *lv_mean, *lv_var2, *lognorm;  // pore model tables (complement order)
     const float *thresh;   // 64 probability thresholds indexed by clzll(range length)
@@ -86,9 +87,11 @@ struct DevBatch {
 };
 
 struct DevWork {   // per-slot (per-CTA) workspaces; slot s uses [s*stride, (s+1)*stride)
-    uint4 *paths;      // 2 x max_paths x 8 uint4
-    uint4 *ckey;       // 2 x max_paths uint4 (radix ping-pong)
-    u16 *order;        // 2 x max_paths
+    uint4 *paths;      // 2 generations x (ceil(max_paths/32)*160 chunk-local child slots + max_paths sources) x 8 uint4
+    uint4 *ckey;       // 2 x max_paths uint4 (radix ping-pong, compact)
+    uint4 *cks;        // ceil(max_paths/32)*160 chunk-local sort keys written by the extension phase
+    uint4 *elist;      // ceil(max_paths/32)*32 chunk-local ended-path entries (start, end, moves, children before)
+    u32 *order;        // 2 x max_paths: logical path order -> record index (| UNC_INVALID)
     uint2 *rlist;      // 2 x rl_cap (double buffered by event parity) seed rows: (FM row -> ref end, move_count | ended<<8)
     uint4 *clu;        // max_blocks x 32 x 2 uint4
     uint4 *dir;        // max_blocks
@@ -215,6 +218,12 @@ UNC_DEV u32 unc_sa(const DevIndex &ix, u32 k, u32 *n_steps, u32 *n_blocks) {
     }
     *n_steps += steps;
     return steps + d_ldg(ix.sa + (k >> 5));
+}
+
+// SA lookup as the mapper uses it: one load when the expanded table exists, else the LF walk
+UNC_DEV u32 unc_sa_lookup(const DevIndex &ix, u32 k, u32 *n_steps, u32 *n_blocks) {
+    if (ix.sa_full) return d_ldg(ix.sa_full + k);
+    return unc_sa(ix, k, n_steps, n_blocks);
 }
 
 // The 1024 k-mer FM ranges (reference src/bwa_index.hpp:124-132): get_base_range(head) -- whose
@@ -668,8 +677,8 @@ UNC_DEV bool trk_get_final(const Tracker &t, const DevParams &p) {
 //
 // Warp 0 of the CTA is the TRACKER: it owns the seed-cluster set (sequential by nature) and
 // runs one event behind the other warps.  Warps 1.. are WORKERS: per event they score the 1024
-// k-mers, extend all paths (chunks of 32 paths per warp, order kept by a lane-0 relay chain
-// through shared memory), radix-sort the children, dedup + emit sources, and look up the
+// k-mers, extend all paths (chunks of 32 paths per warp into chunk-local slots; emission order
+// restored by a scan), radix-sort the children, dedup + emit sources, and look up the
 // suffix array for the event's seeds, which they hand to the tracker through a double-buffered
 // list.
 //
@@ -690,20 +699,16 @@ struct K2Tables {
     uint2 kmer_range[UNC_NKMER];
     float thresh[64];
 };
-// Relay chain across the worker warps: chunk c publishes its inclusive carry, chunk c+1
-// (handled by the next warp) waits for it.  Carry and epoch travel in ONE 128-bit shared-memory
-// word (x = epoch, y/z/w = payload) so that no fence is needed: a thread's single 16-byte
-// shared store becomes visible as a whole.
-struct K2Chain {
-    uint4 *slot;           // ceil(max_paths / 32) entries, carved from dynamic shared memory
-};
-struct K2Shared {          // per CTA (~29 KB + 16 B per 32 max_paths of relay slots)
+struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
     K2Tables tb;
     float probs[UNC_NKMER];
     u32 flags[32];         // sources_added_ bits (reference src/mapper.cpp:88), kmer k -> word k>>5
     u32 hist_cur[K2_RB * K2_MAXSEG];    // [digit][segment]
     u32 hist_next[K2_RB * K2_MAXSEG];
-    K2Chain ch;
+    // per-chunk arrays carved from dynamic shared memory (ceil(max_paths/32) entries each)
+    uint2 *agg;            // D1 aggregates of the k-mer run structure
+    u64 *pre;              // D2 look-back prefix words: (epoch<<2 | state) << 32 | sources | seeds<<16
+    u32 *bcnt, *ecnt;      // children per chunk (then exclusive prefix), ended paths per chunk
     u32 bc[8];             // CTA broadcast scalars
     u32 scan_tmp[32];
     u32 n_rows[2];         // worker -> tracker: seed rows of event e in rlist[e & 1]
@@ -712,22 +717,6 @@ struct K2Shared {          // per CTA (~29 KB + 16 B per 32 max_paths of relay s
     u32 cnt_blocks, cnt_steps;
     u32 tot_children[2], tot_sources[2];   // u64 as two words, written by a worker at the end
 };
-
-// lane 0 only: wait for chunk c-1 and fetch its carry (zeros for the first chunk)
-UNC_DEV uint4 k2_relay_wait(K2Chain *ch, u32 c, u32 epoch) {
-    if (c == 0) return make_uint4(epoch, 0, 0, 0);
-    uint4 v;
-    do {
-        v = s_load_v4(&ch->slot[c - 1]);
-        if (v.x == epoch) break;
-        w_spin();
-    } while (true);
-    return v;
-}
-// lane 0 only
-UNC_DEV void k2_relay_publish(K2Chain *ch, u32 c, u32 epoch, u32 v0, u32 v1, u32 v2) {
-    s_store_v4(&ch->slot[c], make_uint4(epoch, v0, v1, v2));
-}
 
 // exclusive scan over the K2_RB*K2_MAXSEG sort counters by the worker threads:
 // dst[i] = sum(src[0..i)); src := 0.   wt = worker thread index, nwt = worker thread count.
@@ -773,14 +762,20 @@ UNC_DEV u32 unc_event_to_bp(u32 evt_i, bool last, float mean_event_len, float bp
 
 // stage the pore model, k-mer FM ranges and thresholds in shared memory (once per CTA)
 UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *sh) {
-    if (c_tid() == 0) sh->ch.slot = (uint4 *) ((((size_t) (sh + 1)) + 15) & ~(size_t) 15);   // dynamic shared memory follows the struct
-    c_sync();
     const u32 n_slots = (p.max_paths + 31u) >> 5;
+    if (c_tid() == 0) {   // dynamic shared memory follows the struct
+        char *base = (char *) ((((size_t) (sh + 1)) + 15) & ~(size_t) 15);
+        sh->pre = (u64 *) base; base += (size_t) n_slots * 8;
+        sh->agg = (uint2 *) base; base += (size_t) n_slots * 8;
+        sh->bcnt = (u32 *) base; base += (size_t) n_slots * 4;
+        sh->ecnt = (u32 *) base;
+    }
+    c_sync();
     for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) {
         sh->tb.kmer_range[k] = ix.kmer_range[k];
     }
     for (u32 k = (u32) c_tid(); k < 64; k += (u32) c_nthreads()) sh->tb.thresh[k] = ix.thresh[k];
-    for (u32 c = (u32) c_tid(); c < n_slots; c += (u32) c_nthreads()) sh->ch.slot[c] = make_uint4(0, 0, 0, 0);
+    for (u32 c = (u32) c_tid(); c < n_slots; c += (u32) c_nthreads()) sh->pre[c] = 0;
     c_sync();
 }
 
@@ -868,6 +863,15 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
 #endif
 
 // ---- worker warps: reference src/mapper.cpp:433-663 (map_next) minus the seed clustering
+//
+// No inter-warp ordering on the hot loops: phase B writes each chunk's children to chunk-local
+// ("sparse") slots, a small scan + key compaction restores the emission order afterwards; phase D
+// resolves the k-mer-run carry from per-chunk aggregates and the source/seed positions with a
+// decoupled look-back prefix sum.
+#define K2_CH_SLOTS 160u    /* 32 parents x at most 5 children */
+
+UNC_DEV u32 k2_pre_pack(u32 epoch, u32 state) { return (epoch << 2) | state; }
+
 UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
                             K2Shared *sh, u32 r, u32 n_limit, u32 *epoch_io) {
     const int lane = w_lane();
@@ -875,6 +879,8 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
     const u32 ww = wt >> 5, nwk = nwt >> 5;                               // worker warp index / count
     const K2Tables *tb = &sh->tb;
     const u32 maxp = p.max_paths;
+    const u32 S0 = ((maxp + 31u) >> 5) * K2_CH_SLOTS;                     // record index of the first source
+    const size_t gen_recs = (size_t) S0 + maxp;
     const float scale = B.scale[r], shift = B.shift[r];
     const float *events = B.events + (size_t) r * B.ev_stride;
     const float source_prob = tb->thresh[0];
@@ -884,6 +890,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
     u32 epoch = *epoch_io;
     u32 prev_size = 0, gen = 0, event_i = 0;
     const u32 npass = (ix.start_bits + K2_RBITS - 1) / K2_RBITS;
+    const u32 lt = w_lanemask_lt();
     PT_DECL
 
     for (; event_i < n_limit; event_i++) {
@@ -896,17 +903,15 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         c_sync_sub(1, (int) nwt);
         PT_MARK(0)
 
-        uint4 *prev = W.paths + (size_t) gen * maxp * 8, *next = W.paths + (size_t) (gen ^ 1u) * maxp * 8;
-        const u16 *oprev = W.order + (size_t) gen * maxp;
-        u16 *onext = W.order + (size_t) (gen ^ 1u) * maxp;
-        uint4 *ckA = W.ckey, *ckB = W.ckey + maxp;
+        uint4 *prev = W.paths + (size_t) gen * gen_recs * 8, *next = W.paths + (size_t) (gen ^ 1u) * gen_recs * 8;
+        const u32 *oprev = W.order + (size_t) gen * maxp;
+        u32 *onext = W.order + (size_t) (gen ^ 1u) * maxp;
+        uint4 *ckA = W.ckey, *ckB = W.ckey + maxp, *cks = W.cks;
         uint2 *rlist = W.rlist + (size_t) (event_i & 1u) * W.rl_cap;
         const u32 slot_prev = (event_i + 22u) % UNC_RING, slot_new = event_i % UNC_RING, slot_old = (event_i + 1u) % UNC_RING;
 
-        // ---- B. extend every previous path (reference src/mapper.cpp:455-524).
-        //      relay carry: [0] children emitted so far (capped at max_paths), [1] seed rows of
-        //      ended paths so far
-        epoch++;
+        // ---- B. extend every previous path (reference src/mapper.cpp:455-524): chunk c of 32
+        //      parents writes its children, in emission order, to records/keys [c*160, c*160+count)
         const u32 nch_prev = (prev_size + 31u) >> 5;
         {
             // software prefetch of the next chunk's order entry + record head
@@ -914,17 +919,17 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             if (ww < nch_prev) {
                 u32 pi = ww * 32 + (u32) lane;
                 if (pi < prev_size) oi_n = oprev[pi];
-                if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) (oi_n & 0x7FFFu) * 8; q0_n = pr[0]; q1_n = pr[1]; }
+                if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 8; q0_n = pr[0]; q1_n = pr[1]; }
             }
             for (u32 c = ww; c < nch_prev; c += nwk) {
                 const u32 oi = oi_n;
                 const uint4 q0 = q0_n, q1 = q1_n;
                 const bool valid = !(oi & UNC_INVALID);
-                const uint4 *prec = prev + (size_t) (oi & 0x7FFFu) * 8;
+                const uint4 *prec = prev + (size_t) (oi & ~UNC_INVALID) * 8;
                 if (c + nwk < nch_prev) {
                     u32 pi = (c + nwk) * 32 + (u32) lane;
                     oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
-                    if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) (oi_n & 0x7FFFu) * 8; q0_n = pr[0]; q1_n = pr[1]; }
+                    if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 8; q0_n = pr[0]; q1_n = pr[1]; }
                 }
                 u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
                 u32 moves = q0.w, sa_checked = q1.y;
@@ -956,47 +961,25 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 u32 off = w_exscan(cc, &total);
                 // a childless, not yet SA-checked path may end here with seeds
                 // (reference src/mapper.cpp:513-519 -> update_seeds(path, true), is_seed_valid :842-863)
-                u32 rcnt = 0, mc = (u32) d_popc(moves);
+                bool ended = false;
+                u32 mc = (u32) d_popc(moves);
                 if (valid && cc == 0 && !sa_checked) {
                     u32 len = en - st + 1u;
-                    bool ended = plen == UNC_SEED_LEN && u2f(q1.x) >= p.min_seed_prob &&
-                                 ((len == 1 && (moves & 1u) && (float) ((plen - mc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f)) ||
-                                  (len <= p.max_rep_copy && mc >= p.min_rep_len));
-                    if (ended) rcnt = len;
+                    ended = plen == UNC_SEED_LEN && u2f(q1.x) >= p.min_seed_prob &&
+                            ((len == 1 && (moves & 1u) && (float) ((plen - mc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f)) ||
+                             (len <= p.max_rep_copy && mc >= p.min_rep_len));
                 }
-                u32 rtot, roff = w_exscan(rcnt, &rtot);
-                // ring + the two cumulative sums the children need (issued before the relay wait)
-                uint4 r2, r3, r4, r5, r6, r7;
-                float prevC = 0.0f, oldC = 0.0f;
+                u32 m_ended = w_ballot(ended);
+                if (ended) W.elist[(size_t) c * 32 + (u32) d_popc(m_ended & lt)] = make_uint4(st, en, mc, off);
+                if (lane == 0) { sh->bcnt[c] = total; sh->ecnt[c] = (u32) d_popc(m_ended); }
                 if (valid && cc > 0) {
-                    r2 = prec[2]; r3 = prec[3]; r4 = prec[4]; r5 = prec[5]; r6 = prec[6]; r7 = prec[7];
+                    uint4 r2 = prec[2], r3 = prec[3], r4 = prec[4], r5 = prec[5], r6 = prec[6], r7 = prec[7];
                     const float *pring = (const float *) (prec + 2);
-                    prevC = pring[slot_prev]; oldC = pring[slot_old];
-                }
-                // relay (lane 0 only on the critical path).  Fast case: the buffer cannot fill inside
-                // this chunk, so every valid parent is reached and the carry-out is known at once.
-                u32 nn = 0, rows_before = 0, fast = 1;
-                if (lane == 0) {
-                    uint4 cin = k2_relay_wait(&sh->ch, c, epoch);
-                    nn = cin.y; rows_before = cin.z;
-                    fast = nn + total < maxp ? 1u : 0u;
-                    if (fast) k2_relay_publish(&sh->ch, c, epoch, nn + total, rows_before + rtot, 0);
-                }
-                nn = w_shfl(nn, 0); rows_before = w_shfl(rows_before, 0); fast = w_shfl(fast, 0);
-                // sequential semantics of the full buffer: a parent is reached iff the buffer was not
-                // yet full when the scan arrived at it
-                bool reached = valid && (nn + off < maxp);
-                if (!fast) {
-                    if (!reached) rcnt = 0;
-                    roff = w_exscan(rcnt, &rtot);
-                    if (lane == 0)
-                        k2_relay_publish(&sh->ch, c, epoch, nn + total > maxp ? maxp : nn + total, rows_before + rtot, 0);
-                }
-                if (reached && cc > 0) {
-                    u32 ci = nn + off;
+                    float prevC = pring[slot_prev], oldC = pring[slot_old];
+                    u32 ci = c * K2_CH_SLOTS + off;
 #pragma unroll
                     for (u32 j = 0; j < 5; j++) {
-                        if (!((cmask >> j) & 1u) || ci >= maxp) continue;
+                        if (!((cmask >> j) & 1u)) continue;
                         u32 move = j > 0 ? 1u : 0u;
                         u32 nlen = plen + (plen < UNC_SEED_LEN ? 1u : 0u);
                         u32 nmoves = ((moves << 1) | move) & UNC_PATH_MASK;
@@ -1016,24 +999,77 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                         u32 stay_count = (nlen - cmc) & 0xFFu;
                         bool seedable = nlen == UNC_SEED_LEN && sp >= p.min_seed_prob && cst[j] == cen[j] && (nmoves & 1u) &&
                                         (float) stay_count <= f_mul(p.max_stay_frac, 22.0f);
-                        ckA[ci] = make_uint4(cst[j], cen[j], spb, ckm[j] | (seedable ? 1u << 10 : 0u) | (cmc << 11) | (ci << 16));
+                        cks[ci] = make_uint4(cst[j], cen[j], spb, ckm[j] | (seedable ? 1u << 10 : 0u) | (cmc << 11) | (ci << 16));
                         ci++;
                     }
-                }
-                if (rcnt) {   // seed rows of an ended path, in parent order: (row, move_count | ended flag)
-                    if (rows_before + roff + rcnt <= W.rl_cap) {
-                        for (u32 i = 0; i < rcnt; i++) rlist[rows_before + roff + i] = make_uint2(st + i, mc | 0x100u);
-                    } else sh->wk_overflow = 1;
                 }
             }
         }
         c_sync_sub(1, (int) nwt);
         PT_MARK(1)
-        u32 nc = 0, n_rows = 0;
-        if (nch_prev) { uint4 fin = s_load_v4(&sh->ch.slot[nch_prev - 1]); nc = fin.y; n_rows = fin.z; }
+
+        // ---- B2. restore the emission order: exclusive scan of the chunk counts, the buffer cap
+        //      (reference src/mapper.cpp:480-482,507-509,521-523: extension stops when max_paths
+        //      children exist), ended-path seed rows, and compaction of the sort keys
+        if (ww == 0) {
+            u32 carry = 0;
+            for (u32 i0 = 0; i0 < nch_prev; i0 += 32) {
+                u32 v = i0 + (u32) lane < nch_prev ? sh->bcnt[i0 + lane] : 0u, t;
+                u32 ex = w_exscan(v, &t);
+                if (i0 + (u32) lane < nch_prev) sh->bcnt[i0 + lane] = carry + ex;
+                carry += t;
+            }
+            if (lane == 0) sh->bc[2] = carry;
+        }
+        c_sync_sub(1, (int) nwt);
+        const u32 nc_total = nch_prev ? sh->bc[2] : 0u;
+        const u32 nc = nc_total < maxp ? nc_total : maxp;
+        const u32 nch = (nc + 31u) >> 5;
+        const u32 seg_ch = nch ? (nch + nwk - 1) / nwk : 1u, seg_len = seg_ch * 32u;
+        if (ww == 0) {
+            // seed rows of ended paths, in parent order.  A parent counts only if the buffer was not
+            // yet full when the sequential scan reached it (children before it < max_paths).
+            u32 rows = 0;
+            for (u32 i0 = 0; i0 < nch_prev; i0 += 32) {
+                u32 ec = i0 + (u32) lane < nch_prev ? sh->ecnt[i0 + lane] : 0u;
+                u32 m = w_ballot(ec != 0);
+                while (m) {
+                    int l = d_ffs(m) - 1;
+                    m &= m - 1;
+                    u32 c = i0 + (u32) l, n = w_shfl(ec, l), base = sh->bcnt[c];
+                    for (u32 j = 0; j < n; j++) {
+                        uint4 e = W.elist[(size_t) c * 32 + j];
+                        if (base + e.w < maxp) {
+                            u32 len = e.y - e.x + 1u;
+                            if (rows + len <= W.rl_cap) {
+                                for (u32 i = (u32) lane; i < len; i += 32) rlist[rows + i] = make_uint2(e.x + i, e.z | 0x100u);
+                            } else sh->wk_overflow = 1;
+                            rows += len;
+                        }
+                    }
+                }
+            }
+            if (lane == 0) sh->bc[3] = rows;
+        }
+        {
+            // compact the chunk-local keys into emission order: destination-major so that each
+            // iteration is an independent gather (the loads of several iterations overlap)
+            const u32 d_lo = ww * seg_len < nc ? ww * seg_len : nc, d_hi = (ww + 1) * seg_len < nc ? (ww + 1) * seg_len : nc;
+#pragma unroll 4
+            for (u32 di = d_lo + (u32) lane; di < d_hi; di += 32) {
+                u32 lo = 0, hi = nch_prev;              // largest chunk c with bcnt[c] <= di
+                while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (sh->bcnt[mid] <= di) lo = mid; else hi = mid; }
+                uint4 key = cks[(size_t) lo * K2_CH_SLOTS + (di - sh->bcnt[lo])];
+                ckA[di] = key;
+                s_atomic_add(&sh->hist_next[(key.x & (K2_RB - 1u)) * K2_MAXSEG + ww], 1u);
+            }
+        }
+        c_sync_sub(1, (int) nwt);
+        u32 n_rows = sh->bc[3];
         if (n_rows > W.rl_cap) n_rows = W.rl_cap;
         const u32 n_ended_rows = n_rows;
         pend_children = nc;
+        PT_MARK(2)
 
         u32 ns_added = 0;   // sources appended after the children
         u32 n_child_seeds = 0;
@@ -1043,32 +1079,22 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             //         fm_start, 8-bit digits; worker warp w owns the w-th contiguous segment of the
             //         array in every pass, so the scatter is stable without inter-warp ordering
             uint4 *src = ckA, *dst = ckB;
-            const u32 nch = (nc + 31u) >> 5;
-            const u32 seg_ch = (nch + nwk - 1) / nwk, seg_len = seg_ch * 32u;
             const u32 c_lo = ww * seg_ch, c_hi = (c_lo + seg_ch < nch) ? c_lo + seg_ch : nch;
-            // digit counts of pass 0
-            for (u32 c = c_lo; c < c_hi; c++) {
-                u32 g = c * 32 + (u32) lane;
-                bool a = g < nc;
-                u32 dg = a ? (src[g].x & (K2_RB - 1u)) : K2_RB + (u32) lane;
-                u32 peers = w_match(dg);
-                if (a && lane == d_ffs(peers) - 1) sh->hist_next[dg * K2_MAXSEG + ww] += (u32) d_popc(peers);
-                w_sync();
-            }
-            c_sync_sub(1, (int) nwt);
             for (u32 pass = 0; pass < npass; pass++) {
                 const u32 sb = pass * K2_RBITS;
                 k2_wk_exscan_bins(sh, sh->hist_next, sh->hist_cur, wt, nwt);
-                uint4 kn = make_uint4(0, 0, 0, 0);
+                uint4 kn = make_uint4(0, 0, 0, 0), kn2 = make_uint4(0, 0, 0, 0);
                 if (c_lo < c_hi && c_lo * 32 + (u32) lane < nc) kn = src[c_lo * 32 + (u32) lane];
+                if (c_lo + 1 < c_hi && (c_lo + 1) * 32 + (u32) lane < nc) kn2 = src[(c_lo + 1) * 32 + (u32) lane];
                 for (u32 c = c_lo; c < c_hi; c++) {
                     u32 g = c * 32 + (u32) lane;
                     bool a = g < nc;
                     uint4 k = kn;
-                    if (c + 1 < c_hi && g + 32 < nc) kn = src[g + 32];
+                    kn = kn2;
+                    if (c + 2 < c_hi && g + 64 < nc) kn2 = src[g + 64];
                     u32 dg = a ? ((k.x >> sb) & (K2_RB - 1u)) : K2_RB + (u32) lane;  // inactive lanes: unique digit
                     u32 peers = w_match(dg);
-                    u32 rank = (u32) d_popc(peers & w_lanemask_lt());
+                    u32 rank = (u32) d_popc(peers & lt);
                     int leader = d_ffs(peers) - 1;
                     u32 bpos = 0;
                     if (a && lane == leader) {
@@ -1087,7 +1113,6 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 c_sync_sub(1, (int) nwt);
                 uint4 *tmp = src; src = dst; dst = tmp;
             }
-            PT_MARK(2)
             // runs of equal fm_start: order by (fm_end, seed_prob, emission index)
             for (u32 g = wt; g < nc; g += nwt) {
                 u32 s = src[g].x;
@@ -1116,16 +1141,50 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             const uint4 *sk = src;   // sorted keys
 
             // ---- D. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603).
-            //      relay carry: k-mer of the previous element, running max fm_end of its k-mer run,
-            //      sources added so far, child seeds so far
+            // D1: per-chunk aggregate of the k-mer run structure: (max fm_end of the trailing run,
+            //     first k-mer | last k-mer << 11 | whole-chunk-is-one-run << 22)
+            uint4 d1n = make_uint4(0, 0, 0, 0);
+            if (ww < nch && ww * 32 + (u32) lane < nc) d1n = sk[ww * 32 + (u32) lane];
+            for (u32 c = ww; c < nch; c += nwk) {
+                u32 g = c * 32 + (u32) lane;
+                bool a = g < nc;
+                u32 kmer = UNC_NKMER + 1u, endv = 0;
+                if (a) { kmer = d1n.w & UNC_KMASK; endv = d1n.y; }
+                if (c + nwk < nch && g + nwk * 32 < nc) d1n = sk[g + nwk * 32];
+                u32 pk = w_shfl_up(kmer, 1);
+                bool lhead = lane == 0 || kmer != pk || !a;
+                u32 m_lhead = w_ballot(lhead), m_act = w_ballot(a);
+                u32 mx = endv; bool hd = lhead;
+                for (int d = 1; d < 32; d <<= 1) {
+                    u32 omx = w_shfl_up(mx, d); u32 ohd = w_shfl_up(hd ? 1u : 0u, d);
+                    if (lane >= d && !hd) { mx = omx > mx ? omx : mx; hd = ohd != 0; }
+                }
+                int last = 31 - d_clz(m_act);   // last active lane (m_act != 0)
+                u32 kl = w_shfl(kmer, last), ml = w_shfl(mx, last), kf = w_shfl(kmer, 0);
+                bool single = (m_lhead & m_act & ~1u) == 0;
+                if (lane == 0) sh->agg[c] = make_uint2(ml, kf | (kl << 11) | (single ? 1u << 22 : 0u));
+            }
+            c_sync_sub(1, (int) nwt);
+            // D2: everything else; source / seed positions from a decoupled look-back prefix sum
             epoch++;
+            uint4 d2c = make_uint4(0, 0, 0, 0), d2n = make_uint4(0, 0, 0, 0);
+            if (ww < nch) {
+                u32 g0 = ww * 32 + (u32) lane;
+                if (g0 < nc) d2c = sk[g0];
+                if (g0 + 1 < nc) d2n = sk[g0 + 1];
+            }
             for (u32 c = ww; c < nch; c += nwk) {
                 u32 g = c * 32 + (u32) lane;
                 bool a = g < nc;
                 uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
-                if (a) cur = sk[g];
+                if (a) cur = d2c;
                 bool has_next = a && g + 1 < nc;
-                if (has_next) nxt = sk[g + 1];
+                if (has_next) nxt = d2n;
+                if (c + nwk < nch) {
+                    u32 gn = g + nwk * 32;
+                    if (gn < nc) d2c = sk[gn];
+                    if (gn + 1 < nc) d2n = sk[gn + 1];
+                }
                 u32 kmer = a ? (cur.w & UNC_KMASK) : UNC_NKMER + 1u;
                 bool same_next = has_next && (nxt.w & UNC_KMASK) == kmer;
                 bool dup = has_next && nxt.x == cur.x && nxt.y == cur.y;
@@ -1134,7 +1193,6 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 u32 pk = w_shfl_up(kmer, 1);
                 bool seed = a && !dup && ((cur.w >> 10) & 1u);
                 u32 m_seed = w_ballot(seed);
-                // local (carry-free) k-mer run structure: lane 0 is treated as a run head here
                 bool lhead = lane == 0 || kmer != pk || !a;
                 u32 m_lhead = w_ballot(lhead);
                 u32 mx = cur.y; bool hd = lhead;
@@ -1142,46 +1200,77 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                     u32 omx = w_shfl_up(mx, d); u32 ohd = w_shfl_up(hd ? 1u : 0u, d);
                     if (lane >= d && !hd) { mx = omx > mx ? omx : mx; hd = ohd != 0; }
                 }
-                // lanes of the leading run (before the first local head after lane 0)
                 u32 first_head = (m_lhead & ~1u) ? (u32) d_ffs(m_lhead & ~1u) - 1u : 32u;
                 bool in_lead = a && (u32) lane < first_head;
-                u32 kmer0 = w_shfl(kmer, 0);
-                u32 ckmer = UNC_NKMER, cmax = 0, ns_before = 0, seeds_before = 0;
-                if (lane == 0) {
-                    uint4 cin = k2_relay_wait(&sh->ch, c, epoch);
-                    if (c > 0) { cmax = cin.y; ckmer = cin.z & 0x7FFu; ns_before = cin.z >> 11; seeds_before = cin.w; }
+                // carry of the leading run: does it continue the previous chunk's trailing run, and
+                // what is the max fm_end over that run's earlier elements?
+                u32 cont = 0, cmax = 0;
+                if (lane == 0 && c > 0) {
+                    uint2 ag = sh->agg[c - 1];
+                    if (((ag.y >> 11) & 0x7FFu) == kmer) {
+                        cont = 1; cmax = ag.x;
+                        u32 pc = c - 1;
+                        while (pc > 0 && ((ag.y >> 22) & 1u)) {            // that chunk was a single run: look further back
+                            uint2 pg = sh->agg[pc - 1];
+                            if (((pg.y >> 11) & 0x7FFu) != (ag.y & 0x7FFu)) break;
+                            cmax = pg.x > cmax ? pg.x : cmax;
+                            ag = pg; pc--;
+                        }
+                    }
                 }
-                ckmer = w_shfl(ckmer, 0); cmax = w_shfl(cmax, 0);
-                const bool cont = kmer0 == ckmer;              // the leading run continues the previous chunk's
+                cont = w_shfl(cont, 0); cmax = w_shfl(cmax, 0);
                 if (in_lead && cont) mx = mx > cmax ? mx : cmax;
                 bool run_start = a && (lane == 0 ? !cont : (kmer != pk));
                 bool begin_v = run_start && prob_ok && kr.x <= cur.x - 1u;
                 u32 as = mx + 1u, ae = same_next ? nxt.x - 1u : kr.y;
                 bool after_v = a && !dup && prob_ok && as <= ae;
                 u32 m_b = w_ballot(begin_v), m_a = w_ballot(after_v);
-                u32 tot = (u32) d_popc(m_b) + (u32) d_popc(m_a);
-                u32 kmer31 = w_shfl(kmer, 31), mx31 = w_shfl(mx, 31);
-                if (lane == 0) {
-                    u32 nsn = nc + ns_before + tot > maxp ? maxp - nc : ns_before + tot;
-                    k2_relay_publish(&sh->ch, c, epoch, mx31, (kmer31 & 0x7FFu) | (nsn << 11), seeds_before + (u32) d_popc(m_seed));
+                const u32 mine = ((u32) d_popc(m_b) + (u32) d_popc(m_a)) | ((u32) d_popc(m_seed) << 16);   // sources | seeds<<16
+                // decoupled look-back: exclusive prefix of `mine` over the preceding chunks
+                u32 excl = 0;
+                if (c == 0) {
+                    if (lane == 0) s_store_u64(&sh->pre[0], ((u64) k2_pre_pack(epoch, 2u) << 32) | mine);
+                } else {
+                    if (lane == 0) s_store_u64(&sh->pre[c], ((u64) k2_pre_pack(epoch, 1u) << 32) | mine);
+                    int look = (int) c;
+                    for (;;) {
+                        int j = look - 1 - lane;
+                        u64 w = 0;
+                        if (j >= 0) {
+                            for (;;) {
+                                w = s_load_u64(&sh->pre[j]);
+                                if ((u32) (w >> 34) == (epoch & 0x3FFFFFFFu)) break;
+                                w_spin();
+                            }
+                        }
+                        u32 state = (u32) (w >> 32) & 3u, val = (u32) w;
+                        u32 mP = w_ballot(j >= 0 && state == 2u);
+                        u32 upto = mP ? (u32) d_ffs(mP) : 32u;            // lanes [0, upto) contribute
+                        u32 contrib = (j >= 0 && (u32) lane < upto) ? val : 0u;
+                        for (int d = 16; d > 0; d >>= 1) contrib += w_shfl(contrib, lane ^ d);
+                        excl += contrib;
+                        if (mP) break;
+                        look -= 32;
+                        if (look <= 0) break;
+                    }
+                    if (lane == 0) s_store_u64(&sh->pre[c], ((u64) k2_pre_pack(epoch, 2u) << 32) | (excl + mine));
                 }
-                ns_before = w_shfl(ns_before, 0); seeds_before = w_shfl(seeds_before, 0);
-                const u32 lt = w_lanemask_lt();
+                const u32 ns_before = excl & 0xFFFFu, seeds_before = excl >> 16;
                 u32 off = (u32) d_popc(m_b & lt) + (u32) d_popc(m_a & lt);
                 u32 sidx = ns_before + off;    // sources (that would be) added before this element
                 // sources_added_[kmer] is set at a run start while the buffer is not full
                 if (run_start && prob_ok && nc + sidx < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
                 if (begin_v && nc + sidx < maxp) {
-                    write_source(next + (size_t) (nc + sidx) * 8, kr.x, cur.x - 1u, kmer, sh->probs[kmer], event_i);
-                    onext[nc + sidx] = (u16) (nc + sidx);
+                    write_source(next + (size_t) (S0 + nc + sidx) * 8, kr.x, cur.x - 1u, kmer, sh->probs[kmer], event_i);
+                    onext[nc + sidx] = S0 + nc + sidx;
                 }
                 u32 sidx2 = sidx + (begin_v ? 1u : 0u);
                 if (after_v && nc + sidx2 < maxp) {
-                    write_source(next + (size_t) (nc + sidx2) * 8, as, ae, kmer, sh->probs[kmer], event_i);
-                    onext[nc + sidx2] = (u16) (nc + sidx2);
+                    write_source(next + (size_t) (S0 + nc + sidx2) * 8, as, ae, kmer, sh->probs[kmer], event_i);
+                    onext[nc + sidx2] = S0 + nc + sidx2;
                 }
                 u32 emit = cur.w >> 16;
-                if (a) onext[g] = (u16) (emit | (dup ? UNC_INVALID : 0u));
+                if (a) onext[g] = emit | (dup ? UNC_INVALID : 0u);
                 // update_seeds(child, false): unique, move-headed, full-length, probable paths
                 if (seed) {
                     next[(size_t) emit * 8 + 1].y = 1u;   // sa_checked_
@@ -1192,7 +1281,12 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             }
             c_sync_sub(1, (int) nwt);
             PT_MARK(4)
-            { uint4 fin = s_load_v4(&sh->ch.slot[nch - 1]); ns_added = fin.z >> 11; n_child_seeds = fin.w; }
+            {
+                u32 fin = (u32) s_load_u64(&sh->pre[nch - 1]);
+                u32 tot_src = fin & 0xFFFFu;
+                ns_added = nc + tot_src > maxp ? maxp - nc : tot_src;
+                n_child_seeds = fin >> 16;
+            }
         }
         n_rows = n_ended_rows + n_child_seeds;
         if (n_rows > W.rl_cap) n_rows = W.rl_cap;
@@ -1202,7 +1296,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         //         (reference src/mapper.cpp:673-681: sa_end = fmi.size() - fmi.sa(s))
         for (u32 i = wt; i < n_rows; i += nwt) {
             uint2 e = rlist[i];
-            e.x = ix.seq_len - unc_sa(ix, e.x, &pend_steps, &pend_blocks);
+            e.x = ix.seq_len - unc_sa_lookup(ix, e.x, &pend_steps, &pend_blocks);
             rlist[i] = e;
         }
         if (ww == 0) {
@@ -1225,10 +1319,10 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                     visited = last == 31 ? 0xFFFFFFFFu : ((2u << last) - 1u);
                     m_add &= visited;
                 }
-                u32 rank = (u32) d_popc(m_add & w_lanemask_lt());
+                u32 rank = (u32) d_popc(m_add & lt);
                 if ((m_add >> lane) & 1u) {
-                    write_source(next + (size_t) (nn + rank) * 8, kr.x, kr.y, k, pk, event_i);
-                    onext[nn + rank] = (u16) (nn + rank);
+                    write_source(next + (size_t) (S0 + nn + rank) * 8, kr.x, kr.y, k, pk, event_i);
+                    onext[nn + rank] = S0 + nn + rank;
                 }
                 w_sync();
                 if (lane == 0) sh->flags[j] = fw & ~visited;

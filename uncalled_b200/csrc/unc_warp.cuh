@@ -66,6 +66,16 @@ UNC_DEV void s_store_v4(uint4 *p, uint4 v) {
     unsigned a = (unsigned) __cvta_generic_to_shared(p);
     asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+UNC_DEV uint64_t s_load_u64(const uint64_t *p) {
+    uint64_t v;
+    unsigned a = (unsigned) __cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+UNC_DEV void s_store_u64(uint64_t *p, uint64_t v) {
+    unsigned a = (unsigned) __cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
 UNC_DEV float u2f(uint32_t v) { return __uint_as_float(v); }
 UNC_DEV uint32_t f2u(float v) { return __float_as_uint(v); }
 #endif

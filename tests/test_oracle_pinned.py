@@ -1,0 +1,110 @@
+"""CPU tier: the oracle (oracle/unc_oracle.c) is pinned against (a) golden vectors produced by
+the real reference (tests/golden, tools/make_golden.py) and (b) oracle/_ref -- the reference's
+own mapper sources compiled unmodified -- when that library is present."""
+import ctypes as C
+import json
+import os
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+import orclib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def O(example_prefix):
+    return orclib.Oracle(example_prefix)
+
+
+def test_events_match_reference_golden(O, golden_read):
+    m, s, l, mel = O.detect(golden_read["raw"])
+    assert len(m) == 6171
+    assert np.array_equal(m, golden_read["ev_mean"])
+    assert np.array_equal(s, golden_read["ev_start"]) and np.array_equal(l, golden_read["ev_len"])
+    assert mel == golden_read["mean_event_len"]
+    raw = golden_read["raw"]
+    for off, want in zip(golden_read["win_offsets"], golden_read["win_counts"]):
+        assert len(O.detect(raw[off:off + 4000])[0]) == want
+
+
+def test_normaliser_and_model_match_reference_golden(O, golden_read):
+    assert np.float32(O.model.model_mean) == golden_read["model_mean"]
+    assert np.float32(O.model.model_stdv) == golden_read["model_stdv"]
+    assert np.array_equal(O.normalize(golden_read["ev_mean"]), golden_read["normed"])
+    g = np.load(os.path.join(ROOT, "tests", "golden", "example_model.npz"))
+    for e, want in zip(g["events"], g["probs"]):
+        assert np.array_equal(O.match_probs(e), want)
+
+
+def test_fm_index_matches_reference_golden(O):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "example_index.npz"))
+    st, en = O.kmer_ranges()
+    assert np.array_equal(en - st + 1, g["kmer_count"])
+    n = int(g["size"])
+    assert O.lib.orc_fmi_size(O.idx) == n
+    sa = np.array([O.lib.orc_sa(O.idx, i) for i in range(1, n + 1)], dtype=np.uint64)
+    assert np.array_equal(sa, g["sa_1_to_n"])
+
+
+def _fields(rec, O):
+    return [str(int(rec.rd_len)), str(int(rec.rd_st)), str(int(rec.rd_en)), "+" if rec.fwd else "-",
+            O.lib.orc_seq_name(O.idx, rec.rid).decode(), str(int(rec.rf_len)), str(int(rec.rf_st)),
+            str(int(rec.rf_en)), str(int(rec.matches)), str(int(rec.rf_en - rec.rf_st + 1)), "255"]
+
+
+def test_paf_lines_match_reference_golden(example_prefix, golden_read):
+    """The three PAF lines `uncalled map` prints for the example read (default, -c 1, -e 100)."""
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "example_paf.json")))
+    raw = golden_read["raw"]
+    O = orclib.Oracle(example_prefix)
+    assert _fields(O.map_read(raw), O) == gold["default"]["fields"][1:]
+    assert _fields(O.map_read(raw[:4000]), O) == gold["max_chunks_1"]["fields"][1:]
+    O.params.max_events = 100
+    r = O.map_read(raw)
+    assert not r.mapped and str(int(r.rd_len)) == gold["max_events_100"]["fields"][1] and r.events_used == 100
+
+
+def test_empty_and_tiny_reads(O):
+    for n in (0, 1, 5, 30):
+        r = O.map_read(np.full(n, 90.0, np.float32))
+        assert not r.mapped and r.rd_len == int(np.float32(n) * (np.float32(450) / np.float32(4000)))
+
+
+@pytest.mark.skipif(not orclib.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_equals_unmodified_reference_on_synthetic_reads():
+    """Bit-for-bit PAF agreement with the reference's own Mapper (fresh Mapper per read) on
+    seeded synthetic reads, incl. reads that never map.  Runs in a child: _ref is static."""
+    code = textwrap.dedent("""
+        import sys, ctypes as C, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import orclib as o, synth, synthdata
+        prefix, g = synthdata.get_index("g200k")
+        sig, truth = synth.reads(g, 96, 4000, seed=11)
+        O = o.Oracle(prefix)
+        R = o.ref(); R.ref_load(prefix.encode(), b"default")
+        offs = np.arange(96, dtype=np.uint64) * 4000
+        po = O.map_batch(sig.ravel(), offs, np.full(96, 4000, np.uint32), 4)
+        bad = 0
+        for i in range(96):
+            out = o.RefPaf()
+            R.ref_map_read(o.fp(sig[i]), 4000, C.byref(out))
+            if o.paf_tuple(po[i]) != o.paf_tuple(out): bad += 1
+        # events / normalisation / model straight from the reference classes
+        ev = np.zeros(4001, np.float32); st = np.zeros(4001, np.uint32); ln = np.zeros(4001, np.uint32); mel = C.c_float()
+        ne = R.ref_get_events(o.fp(sig[0]), 4000, o.fp(ev), st.ctypes.data_as(o.u32p), ln.ctypes.data_as(o.u32p), C.byref(mel))
+        m, s, l, omel = O.detect(sig[0])
+        assert ne == len(m) and np.array_equal(ev[:ne], m) and np.float32(mel.value) == omel
+        nm = np.zeros(ne, np.float32); R.ref_normalize(o.fp(m), ne, o.fp(nm))
+        assert np.array_equal(nm, O.normalize(m))
+        assert all(R.ref_match_prob(float(e), k) == O.lib.orc_match_prob(C.byref(O.model), float(e), k)
+                   for e in (61.5, 90.25, 118.0) for k in range(1024))
+        assert all(R.ref_prob_thresh(b) == O.lib.orc_prob_thresh(O.idx, b) or
+                   (np.isnan(R.ref_prob_thresh(b)) and np.isnan(O.lib.orc_prob_thresh(O.idx, b))) for b in range(64))
+        print("MISMATCHES", bad, "MAPPED", sum(r.mapped for r in po))
+    """ % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")))
+    out = orclib.run_in_subprocess(code, timeout=900)
+    assert "MISMATCHES 0" in out, out

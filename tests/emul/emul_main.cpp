@@ -93,13 +93,14 @@ int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads,
 
     u32 maxp = dp.max_paths;
     const size_t nchmax = (maxp + 31) / 32;
-    std::vector<uint4> paths((size_t) 2 * (nchmax * 160 + maxp) * 8), ckey((size_t) 2 * maxp), cks(nchmax * 160), elist(nchmax * 32);
+    std::vector<uint4> paths((size_t) 2 * (nchmax * 160 + maxp) * 2), ckey((size_t) 2 * maxp), cks(nchmax * 160), elist(nchmax * 32), wlist(nchmax * 160);
+    std::vector<uint2> hist((size_t) 24 * (nchmax * 160 + maxp));
     std::vector<u32> order((size_t) 2 * maxp);
     std::vector<uint4> clu((size_t) max_blocks * 32 * 2), dir(max_blocks + 1);
     const u32 rl_cap = 16384;
     std::vector<uint2> rlist(2 * rl_cap);
     DevWork W;
-    W.paths = paths.data(); W.ckey = ckey.data(); W.cks = cks.data(); W.elist = elist.data(); W.order = order.data(); W.rlist = rlist.data();
+    W.paths = paths.data(); W.hist = hist.data(); W.wlist = wlist.data(); W.ckey = ckey.data(); W.cks = cks.data(); W.elist = elist.data(); W.order = order.data(); W.rlist = rlist.data();
     W.clu = clu.data(); W.dir = dir.data();
     W.max_blocks = max_blocks; W.rl_cap = rl_cap;
     K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((maxp + 31) / 32) * 24);

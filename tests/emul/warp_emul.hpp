@@ -151,6 +151,7 @@ static inline uint32_t w_match(uint32_t v) {
     return m;
 }
 static inline uint32_t d_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t d_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 static inline uint32_t s_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline uint32_t s_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 static inline int d_popc(uint32_t v) { return __builtin_popcount(v); }

@@ -51,13 +51,15 @@ __global__ void __launch_bounds__(128) k1_events(DevBatch B, DevParams p) {
 // and the thresholds in shared memory, then pulls reads from a global queue; the K2_WARPS warps
 // of the CTA cooperate on every event of the read (chained scans through shared memory).
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
-k2_map(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t ckey_stride, size_t cks_stride,
+k2_map(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t hist_stride, size_t ckey_stride, size_t cks_stride,
        size_t elist_stride, size_t order_stride, size_t rlist_stride, size_t clu_stride, size_t dir_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K2Shared *sh = (K2Shared *) smem_raw;
     const size_t slot = blockIdx.x;
     DevWork W;
     W.paths = W0.paths + slot * paths_stride;
+    W.hist = W0.hist + slot * hist_stride;
+    W.wlist = W0.wlist + slot * cks_stride;
     W.ckey = W0.ckey + slot * ckey_stride;
     W.cks = W0.cks + slot * cks_stride;
     W.elist = W0.elist + slot * elist_stride;
@@ -142,7 +144,7 @@ struct unc_pool {
     unc_paf_rec *h_out = nullptr;  // pinned staging
     // workspaces
     DevWork W;
-    size_t paths_stride = 0, ckey_stride = 0, cks_stride = 0, elist_stride = 0, order_stride = 0, rlist_stride = 0, clu_stride = 0, dir_stride = 0;
+    size_t paths_stride = 0, hist_stride = 0, ckey_stride = 0, cks_stride = 0, elist_stride = 0, order_stride = 0, rlist_stride = 0, clu_stride = 0, dir_stride = 0;
     uint32_t n_slots = 0, grid = 0;
     size_t smem = 0;
     unc_timing last;
@@ -332,7 +334,8 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     // per-slot workspace sizes
     const size_t maxp = prm->max_paths;
     const size_t nchmax = (maxp + 31) / 32;
-    P->paths_stride = 2 * (nchmax * 160 + maxp) * 8;   // uint4: chunk-local child slots + sources, two generations
+    P->paths_stride = 2 * (nchmax * 160 + maxp) * 2;   // uint4: chunk-local child slots + sources, two generations
+    P->hist_stride = 24 * (nchmax * 160 + maxp);      // uint2: (C, parent) per record index, 24 generations
     P->ckey_stride = 2 * maxp;        // uint4
     P->cks_stride = nchmax * 160;     // uint4
     P->elist_stride = nchmax * 32;    // uint4
@@ -343,7 +346,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     uint64_t mb = std::max<uint64_t>(1024, ev_cap * 2);
     mb = std::min<uint64_t>(mb, 1u << 17);
     const size_t rl_cap = 64 * 1024;   // seed rows of one event (typically tens)
-    size_t per_slot = (P->paths_stride + P->ckey_stride + P->cks_stride + P->elist_stride) * 16 + P->order_stride * 4 + 2 * rl_cap * 8 + mb * (UNC_BLK * 32 + 16);
+    size_t per_slot = (P->paths_stride + P->ckey_stride + 2 * P->cks_stride + P->elist_stride) * 16 + P->hist_stride * 8 + P->order_stride * 4 + 2 * rl_cap * 8 + mb * (UNC_BLK * 32 + 16);
     size_t free_b = 0, total_b = 0;
     PT(cudaMemGetInfo(&free_b, &total_b));
     size_t fixed = max_samples * 4 + (size_t) max_reads * (sizeof(DevReadDesc) + sizeof(DevRec) + 20) + (64u << 20);
@@ -360,6 +363,9 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     P->W.max_blocks = (u32) mb;
     PT(cudaMalloc(&P->W.paths, (size_t) P->n_slots * P->paths_stride * 16));
     PT(cudaMalloc(&P->W.ckey, (size_t) P->n_slots * P->ckey_stride * 16));
+    PT(cudaMalloc(&P->W.hist, (size_t) P->n_slots * P->hist_stride * 8));
+    PT(cudaMemset(P->W.hist, 0, (size_t) P->n_slots * P->hist_stride * 8));
+    PT(cudaMalloc(&P->W.wlist, (size_t) P->n_slots * P->cks_stride * 16));
     PT(cudaMalloc(&P->W.cks, (size_t) P->n_slots * P->cks_stride * 16));
     PT(cudaMalloc(&P->W.elist, (size_t) P->n_slots * P->elist_stride * 16));
     PT(cudaMalloc(&P->W.order, (size_t) P->n_slots * P->order_stride * 4));
@@ -388,7 +394,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
 
 void unc_pool_free(unc_pool *P) {
     if (!P) return;
-    cudaFree(P->W.paths); cudaFree(P->W.ckey); cudaFree(P->W.cks); cudaFree(P->W.elist); cudaFree(P->W.order); cudaFree(P->W.rlist); cudaFree(P->W.clu); cudaFree(P->W.dir);
+    cudaFree(P->W.paths); cudaFree(P->W.hist); cudaFree(P->W.wlist); cudaFree(P->W.ckey); cudaFree(P->W.cks); cudaFree(P->W.elist); cudaFree(P->W.order); cudaFree(P->W.rlist); cudaFree(P->W.clu); cudaFree(P->W.dir);
     cudaFree(P->d_samples); cudaFree(P->d_reads); cudaFreeHost(P->h_reads);
     cudaFree(P->d_events); cudaFree(P->d_normed);
     cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue);
@@ -476,7 +482,7 @@ static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[2], s));
     uint32_t grid = std::min<uint32_t>(P->grid, n);
-    k2_map<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->ckey_stride, P->cks_stride,
+    k2_map<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->hist_stride, P->ckey_stride, P->cks_stride,
                                              P->elist_stride, P->order_stride, P->rlist_stride, P->clu_stride, P->dir_stride);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[3], s));

@@ -22,7 +22,7 @@ typedef uint64_t u64;
 #define UNC_NKMER 1024
 #define UNC_KMASK 0x3FFu
 #define UNC_SEED_LEN 22u
-#define UNC_RING 23u
+#define UNC_NGEN 24u            /* generations of (C, parent) history kept: need e-22 .. e */
 #define UNC_PATH_MASK 0x3FFFFFu
 #define UNC_PATH_TAIL 0x200000u
 #define UNC_INVALID 0x80000000u /* flag in the order[] array: path invalidated by dedup */
@@ -87,7 +87,9 @@ struct DevBatch {
 };
 
 struct DevWork {   // per-slot (per-CTA) workspaces; slot s uses [s*stride, (s+1)*stride)
-    uint4 *paths;      // 2 generations x (ceil(max_paths/32)*160 chunk-local child slots + max_paths sources) x 8 uint4
+    uint4 *paths;      // 2 generations x (ceil(max_paths/32)*160 chunk-local child slots + max_paths sources) x 2 uint4
+    uint2 *hist;       // 24 generations x the same record index space: (cumulative log-prob C, parent record index)
+    uint4 *wlist;      // ceil(max_paths/32)*160 deferred window look-ups: (child idx, parent idx, C bits, moves)
     uint4 *ckey;       // 2 x max_paths uint4 (radix ping-pong, compact)
     uint4 *cks;        // ceil(max_paths/32)*160 chunk-local sort keys written by the extension phase
     uint4 *elist;      // ceil(max_paths/32)*32 chunk-local ended-path entries (start, end, moves, children before)
@@ -682,11 +684,14 @@ UNC_DEV bool trk_get_final(const Tracker &t, const DevParams &p) {
 // suffix array for the event's seeds, which they hand to the tracker through a double-buffered
 // list.
 //
-// Path record = 8 uint4 (128 B):
-//   q0 = (fm_start, fm_end, kmer | length<<16 | consec_stays<<24, event_moves)
-//   q1 = (seed_prob bits, sa_checked, 0, 0)
-//   q2..q7 = 23-float ring of cumulative log-probs since the path's source, slot = event % 23
-//            (the reference's prob_sums_ window, src/mapper.cpp:792-801, without the shift)
+// Path record = 2 uint4 (32 B):
+//   q0 = (fm_start, fm_end, kmer | length<<16 | consec_stays<<24, event_moves | sa_checked<<31)
+//   q1 = (seed_prob bits, C = cumulative log-prob since the path's source, 0, 0)
+// The reference's 23-float prob_sums_ window (src/mapper.cpp:792-801) is only ever read at its two
+// ends: C(e-1) to extend and C(e-22) once the path is seed_len long.  C(e-1) is the parent's C.
+// C(e-22) is the C of the ancestor 22 generations back, found through hist[generation % 24][idx] =
+// (C, parent idx); only ~2 % of children have a full-length parent, and those look-ups are
+// deferred to a separate pass so the extension loop never waits on the 22-hop walk.
 // Sort key (ckey) = (fm_start, fm_end, seed_prob bits, kmer | seedable<<10 | move_count<<11 | emission idx<<16)
 #define K2_MAXCH 1024u     /* chunks of 32 paths (max_paths <= 32767) */
 #define K2_RBITS 8u        /* radix digit width of the child sort */
@@ -714,6 +719,7 @@ struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
     u32 n_rows[2];         // worker -> tracker: seed rows of event e in rlist[e & 1]
     u32 verdict[2];        // tracker -> workers: outcome of event e in verdict[e & 1]
     u32 wk_overflow;
+    u32 wl_cnt;            // deferred window look-ups of the event in flight
     u32 cnt_blocks, cnt_steps;
     u32 tot_children[2], tot_sources[2];   // u64 as two words, written by a worker at the end
 };
@@ -745,13 +751,11 @@ UNC_DEV void k2_wk_exscan_bins(K2Shared *sh, u32 *src, u32 *dst, u32 wt, u32 nwt
     c_sync_sub(1, (int) nwt);
 }
 
-// PathBuffer::make_source (reference src/mapper.cpp:751-772)
-UNC_DEV void write_source(uint4 *rec, u32 st, u32 en, u32 kmer, float prob, u32 ev) {
-    rec[0] = make_uint4(st, en, kmer | (1u << 16), 1u);
-    rec[1] = make_uint4(f2u(prob), 0u, 0u, 0u);
-    float *ring = (float *) (rec + 2);
-    ring[(ev + 22u) % UNC_RING] = 0.0f;
-    ring[ev % UNC_RING] = prob;
+// PathBuffer::make_source (reference src/mapper.cpp:751-772): prob_sums_ = {0, prob}
+UNC_DEV void write_source(uint4 *rec, uint2 *hist_e, u32 idx, u32 st, u32 en, u32 kmer, float prob) {
+    rec[(size_t) idx * 2] = make_uint4(st, en, kmer | (1u << 16), 1u);
+    rec[(size_t) idx * 2 + 1] = make_uint4(f2u(prob), f2u(prob), 0u, 0u);
+    hist_e[idx] = make_uint2(f2u(prob), 0xFFFFFFFFu);
 }
 
 // Mapper::event_to_bp (reference src/mapper.cpp:703-706)
@@ -903,12 +907,12 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         c_sync_sub(1, (int) nwt);
         PT_MARK(0)
 
-        uint4 *prev = W.paths + (size_t) gen * gen_recs * 8, *next = W.paths + (size_t) (gen ^ 1u) * gen_recs * 8;
+        uint4 *prev = W.paths + (size_t) gen * gen_recs * 2, *next = W.paths + (size_t) (gen ^ 1u) * gen_recs * 2;
+        uint2 *hist_e = W.hist + (size_t) (event_i % UNC_NGEN) * gen_recs;
         const u32 *oprev = W.order + (size_t) gen * maxp;
         u32 *onext = W.order + (size_t) (gen ^ 1u) * maxp;
         uint4 *ckA = W.ckey, *ckB = W.ckey + maxp, *cks = W.cks;
         uint2 *rlist = W.rlist + (size_t) (event_i & 1u) * W.rl_cap;
-        const u32 slot_prev = (event_i + 22u) % UNC_RING, slot_new = event_i % UNC_RING, slot_old = (event_i + 1u) % UNC_RING;
 
         // ---- B. extend every previous path (reference src/mapper.cpp:455-524): chunk c of 32
         //      parents writes its children, in emission order, to records/keys [c*160, c*160+count)
@@ -919,20 +923,19 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             if (ww < nch_prev) {
                 u32 pi = ww * 32 + (u32) lane;
                 if (pi < prev_size) oi_n = oprev[pi];
-                if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 8; q0_n = pr[0]; q1_n = pr[1]; }
+                if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = pr[1]; }
             }
             for (u32 c = ww; c < nch_prev; c += nwk) {
                 const u32 oi = oi_n;
                 const uint4 q0 = q0_n, q1 = q1_n;
                 const bool valid = !(oi & UNC_INVALID);
-                const uint4 *prec = prev + (size_t) (oi & ~UNC_INVALID) * 8;
                 if (c + nwk < nch_prev) {
                     u32 pi = (c + nwk) * 32 + (u32) lane;
                     oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
-                    if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 8; q0_n = pr[0]; q1_n = pr[1]; }
+                    if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = pr[1]; }
                 }
                 u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
-                u32 moves = q0.w, sa_checked = q1.y;
+                u32 moves = q0.w & UNC_PATH_MASK, sa_checked = q0.w >> 31;
                 u32 want = 0; bool stay_ok = false;
                 float cprob[5]; u32 cst[5], cen[5], ckm[5];
                 if (valid) {
@@ -973,9 +976,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 if (ended) W.elist[(size_t) c * 32 + (u32) d_popc(m_ended & lt)] = make_uint4(st, en, mc, off);
                 if (lane == 0) { sh->bcnt[c] = total; sh->ecnt[c] = (u32) d_popc(m_ended); }
                 if (valid && cc > 0) {
-                    uint4 r2 = prec[2], r3 = prec[3], r4 = prec[4], r5 = prec[5], r6 = prec[6], r7 = prec[7];
-                    const float *pring = (const float *) (prec + 2);
-                    float prevC = pring[slot_prev], oldC = pring[slot_old];
+                    const float prevC = u2f(q1.y);
                     u32 ci = c * K2_CH_SLOTS + off;
 #pragma unroll
                     for (u32 j = 0; j < 5; j++) {
@@ -985,27 +986,53 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                         u32 nmoves = ((moves << 1) | move) & UNC_PATH_MASK;
                         u32 nstays = move ? 0u : stays + 1u;
                         float newC = f_add(prevC, cprob[j]);
-                        float sp;
-                        if (plen == UNC_SEED_LEN) { sp = f_div(f_sub(newC, oldC), 22.0f); nmoves |= UNC_PATH_TAIL; }
-                        else sp = f_div(newC, (float) nlen);
+                        float sp = 0.0f;
+                        bool seedable = false;
+                        if (plen == UNC_SEED_LEN) {
+                            // seed_prob = (C(e) - C(e-22)) / 22 needs the ancestor 22 generations back: deferred
+                            nmoves |= UNC_PATH_TAIL;
+                            W.wlist[s_atomic_add(&sh->wl_cnt, 1u)] = make_uint4(ci, oi, f2u(newC), nmoves);
+                        } else {
+                            sp = f_div(newC, (float) nlen);
+                            // is_seed_valid(path_ended = false) of the child (reference src/mapper.cpp:842-863)
+                            u32 cmc = (u32) d_popc(nmoves);
+                            seedable = nlen == UNC_SEED_LEN && sp >= p.min_seed_prob && cst[j] == cen[j] && (nmoves & 1u) &&
+                                       (float) ((nlen - cmc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f);
+                        }
                         u32 spb = f2u(sp);
-                        uint4 *crec = next + (size_t) ci * 8;
-                        crec[0] = make_uint4(cst[j], cen[j], ckm[j] | (nlen << 16) | (nstays << 24), nmoves);
-                        crec[1] = make_uint4(spb, sa_checked, 0u, 0u);
-                        crec[2] = r2; crec[3] = r3; crec[4] = r4; crec[5] = r5; crec[6] = r6; crec[7] = r7;
-                        ((float *) (crec + 2))[slot_new] = newC;
-                        // is_seed_valid(path_ended = false) of the child (reference src/mapper.cpp:842-863)
-                        u32 cmc = (u32) d_popc(nmoves);
-                        u32 stay_count = (nlen - cmc) & 0xFFu;
-                        bool seedable = nlen == UNC_SEED_LEN && sp >= p.min_seed_prob && cst[j] == cen[j] && (nmoves & 1u) &&
-                                        (float) stay_count <= f_mul(p.max_stay_frac, 22.0f);
-                        cks[ci] = make_uint4(cst[j], cen[j], spb, ckm[j] | (seedable ? 1u << 10 : 0u) | (cmc << 11) | (ci << 16));
+                        next[(size_t) ci * 2] = make_uint4(cst[j], cen[j], ckm[j] | (nlen << 16) | (nstays << 24), nmoves | (sa_checked << 31));
+                        next[(size_t) ci * 2 + 1] = make_uint4(spb, f2u(newC), 0u, 0u);
+                        hist_e[ci] = make_uint2(f2u(newC), oi);
+                        cks[ci] = make_uint4(cst[j], cen[j], spb, ckm[j] | (seedable ? 1u << 10 : 0u) | ((u32) d_popc(nmoves) << 11) | (ci << 16));
                         ci++;
                     }
                 }
             }
         }
         c_sync_sub(1, (int) nwt);
+        // ---- B1. deferred seed_prob of children whose parent was already seed_len long:
+        //      C(e-22) is the C of the ancestor 22 generations back (21 parent hops from the parent)
+        {
+            const u32 nwl = *(volatile u32 *) &sh->wl_cnt;
+            for (u32 i = wt; i < nwl; i += nwt) {
+                uint4 w = W.wlist[i];
+                u32 idx = w.y;
+                for (u32 j = 1; j <= 21; j++)
+                    idx = W.hist[(size_t) ((event_i + UNC_NGEN - j) % UNC_NGEN) * gen_recs + idx].y;
+                float oldC = u2f(W.hist[(size_t) ((event_i + UNC_NGEN - 22u) % UNC_NGEN) * gen_recs + idx].x);
+                float sp = f_div(f_sub(u2f(w.z), oldC), 22.0f);
+                uint4 key = cks[w.x];
+                u32 cmc = (u32) d_popc(w.w);
+                bool seedable = sp >= p.min_seed_prob && key.x == key.y && (w.w & 1u) &&
+                                (float) ((UNC_SEED_LEN - cmc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f);
+                key.z = f2u(sp);
+                if (seedable) key.w |= 1u << 10;
+                cks[w.x] = key;
+                next[(size_t) w.x * 2 + 1].x = f2u(sp);
+            }
+        }
+        c_sync_sub(1, (int) nwt);
+        if (wt == 0) sh->wl_cnt = 0;
         PT_MARK(1)
 
         // ---- B2. restore the emission order: exclusive scan of the chunk counts, the buffer cap
@@ -1261,19 +1288,19 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 // sources_added_[kmer] is set at a run start while the buffer is not full
                 if (run_start && prob_ok && nc + sidx < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
                 if (begin_v && nc + sidx < maxp) {
-                    write_source(next + (size_t) (S0 + nc + sidx) * 8, kr.x, cur.x - 1u, kmer, sh->probs[kmer], event_i);
+                    write_source(next, hist_e, S0 + nc + sidx, kr.x, cur.x - 1u, kmer, sh->probs[kmer]);
                     onext[nc + sidx] = S0 + nc + sidx;
                 }
                 u32 sidx2 = sidx + (begin_v ? 1u : 0u);
                 if (after_v && nc + sidx2 < maxp) {
-                    write_source(next + (size_t) (S0 + nc + sidx2) * 8, as, ae, kmer, sh->probs[kmer], event_i);
+                    write_source(next, hist_e, S0 + nc + sidx2, as, ae, kmer, sh->probs[kmer]);
                     onext[nc + sidx2] = S0 + nc + sidx2;
                 }
                 u32 emit = cur.w >> 16;
                 if (a) onext[g] = emit | (dup ? UNC_INVALID : 0u);
                 // update_seeds(child, false): unique, move-headed, full-length, probable paths
                 if (seed) {
-                    next[(size_t) emit * 8 + 1].y = 1u;   // sa_checked_
+                    d_atomic_or(&((u32 *) (next + (size_t) emit * 2))[3], 0x80000000u);   // sa_checked_
                     u32 ri = n_ended_rows + seeds_before + (u32) d_popc(m_seed & lt);
                     if (ri < W.rl_cap) rlist[ri] = make_uint2(cur.x, (cur.w >> 11) & 0x1Fu);
                     else sh->wk_overflow = 1;
@@ -1321,7 +1348,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 }
                 u32 rank = (u32) d_popc(m_add & lt);
                 if ((m_add >> lane) & 1u) {
-                    write_source(next + (size_t) (S0 + nn + rank) * 8, kr.x, kr.y, k, pk, event_i);
+                    write_source(next, hist_e, S0 + nn + rank, kr.x, kr.y, k, pk);
                     onext[nn + rank] = S0 + nn + rank;
                 }
                 w_sync();
@@ -1363,7 +1390,7 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
     const u32 n_limit = n_ev < p.max_events ? n_ev : p.max_events;
     if (tid < 32) sh->flags[tid] = 0;
     if (tid == 0) {
-        sh->cnt_blocks = 0; sh->cnt_steps = 0; sh->wk_overflow = 0;
+        sh->cnt_blocks = 0; sh->cnt_steps = 0; sh->wk_overflow = 0; sh->wl_cnt = 0;
         sh->verdict[0] = sh->verdict[1] = 0; sh->n_rows[0] = sh->n_rows[1] = 0; sh->bc[1] = 0;
     }
     for (u32 b = tid; b < K2_RB * K2_MAXSEG; b += (u32) c_nthreads()) sh->hist_next[b] = 0;

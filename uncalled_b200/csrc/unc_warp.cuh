@@ -34,6 +34,7 @@ UNC_DEV uint32_t w_shfl_up(uint32_t v, int d) { return __shfl_up_sync(UNC_FULL, 
 UNC_DEV uint32_t w_shfl_down(uint32_t v, int d) { return __shfl_down_sync(UNC_FULL, v, d); }
 UNC_DEV uint32_t w_match(uint32_t v) { return __match_any_sync(UNC_FULL, v); }
 UNC_DEV uint32_t d_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+UNC_DEV uint32_t d_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
 UNC_DEV uint32_t s_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 UNC_DEV uint32_t s_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
 UNC_DEV int d_popc(uint32_t v) { return __popc(v); }

@@ -166,6 +166,9 @@ int unc_fm_neighbors(const unc_index *idx, uint32_t n, const uint64_t *start, co
 int unc_fm_sa(const unc_index *idx, uint32_t n, const uint64_t *rows, uint64_t *out);
 
 int unc_pool_last_timing(const unc_pool *pool, unc_timing *t);
+/* Counters of the event-detection kernel over the last batch: tiles processed, speculative-FSM
+ * re-run rounds, lanes re-run, reads redone by the serial routine (exactness condition failed). */
+int unc_pool_k1_stats(const unc_pool *pool, uint32_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -2,6 +2,7 @@
 // compiled with -DUNC_EMUL) on the CPU under the 32-fiber warp emulator.  Test vehicle only:
 // it lets the CPU-only test tier compare the warp-cooperative kernel logic with the oracle.
 #include "unc_device.cuh"   // UNC_EMUL is defined on the command line
+#include "unc_k1.cuh"
 #include "../../include/unc_b200.h"
 #include "unc_host_index.hpp"
 #include "unc_host_params.hpp"
@@ -50,6 +51,14 @@ void emu_kmer_range(void *p, uint32_t k, uint64_t *st, uint64_t *en) {
 struct CtaArgs {
     const DevIndex *ix; const DevParams *p; const DevBatch *B; const DevWork *W; K2Shared *sh;
 };
+struct K1Args { const DevBatch *B; const DevParams *p; K1WarpSmem *sm; };
+static void k1_entry(void *a) {
+    K1Args *w = (K1Args *) a;
+    unc_k1_warp_main(*w->B, *w->p, w->sm + (c_tid() >> 5));
+}
+static uint32_t g_k1_stats[4];
+extern "C" void emu_k1_stats(uint32_t *out) { memcpy(out, g_k1_stats, sizeof(g_k1_stats)); }
+
 static void cta_entry(void *a) {
     CtaArgs *w = (CtaArgs *) a;
     unc_k2_cta_main(*w->ix, *w->p, *w->B, *w->W, w->sh);
@@ -84,7 +93,30 @@ int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads,
     B.queue = &queue; B.out = (DevRec *) out; B.dbg = nullptr;
     B.seq_offsets = seq_off.data(); B.seq_lens = e->h.lens.data(); B.n_seqs = (u32) e->h.names.size();
     B.l_pac = (u64) e->h.l_pac;
-    for (u32 r = 0; r < n_reads; r++) unc_k1_read(B, dp, r);
+    u64 total_bytes = 0;
+    for (u32 i = 0; i < n_reads; i++) {
+        u64 e = (reads[i].offset + reads[i].n_samples) * (reads[i].dtype ? 2 : 4);
+        if (e > total_bytes) total_bytes = e;
+    }
+    B.samples_bytes = total_bytes;
+    u32 k1_queue = 0;
+    std::vector<u32> k1_flags(n_reads);
+    memset(g_k1_stats, 0, sizeof(g_k1_stats));
+    B.k1_queue = &k1_queue; B.k1_flags = k1_flags.data(); B.k1_stats = g_k1_stats;
+    if (getenv("UNC_EMU_K1_SERIAL")) {
+        for (u32 r = 0; r < n_reads; r++) unc_k1_read(B, dp, r);
+    } else {
+        // the event-detection kernel (warp per read), then the serial redo of flagged reads and the
+        // normaliser statistics, exactly as launch_k1() in unc_abi.cu orders them
+        const int k1_warps = getenv("UNC_EMU_K1_WARPS") ? atoi(getenv("UNC_EMU_K1_WARPS")) : 2;
+        K1WarpSmem *ksm = (K1WarpSmem *) aligned_alloc(16, sizeof(K1WarpSmem) * k1_warps);
+        memset(ksm, 0, sizeof(K1WarpSmem) * k1_warps);
+        K1Args ka = {&B, &dp, ksm};
+        emu_run_cta(k1_entry, &ka, 32 * k1_warps);
+        free(ksm);
+        for (u32 r = 0; r < n_reads; r++) if (k1_flags[r]) unc_k1_read(B, dp, r);
+        for (u32 r = 0; r < n_reads; r++) if (!k1_flags[r]) unc_k1_norm_read(B, dp, r);
+    }
     if (events_out) memcpy(events_out, events.data(), (size_t) n_reads * stride * 4);
     if (normed_out) memcpy(normed_out, normed.data(), (size_t) n_reads * stride * 4);
     if (n_events_out) memcpy(n_events_out, n_events.data(), n_reads * 4);

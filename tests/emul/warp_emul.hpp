@@ -35,6 +35,7 @@ struct WarpEmu {     // one CTA: n_threads fibers, 32 per warp
     int cur;
     int done[EMU_MAX_THREADS];
     int n_done;
+    int warp_done[EMU_MAX_THREADS / 32];   // exited threads per warp
     WarpRv rv[EMU_MAX_THREADS / 32];
     int cta_arrived;
     uint64_t cta_gen;
@@ -61,7 +62,7 @@ static inline void emu_yield() {
 // lane's value from result[]
 static inline const uint64_t *emu_exchange(uint64_t v) {
     WarpEmu *w = g_warp;
-    if (w->n_done) { fprintf(stderr, "warp_emul: collective reached after %d thread(s) exited\n", w->n_done); abort(); }
+    if (w->warp_done[w->cur >> 5]) { fprintf(stderr, "warp_emul: collective reached after %d thread(s) of the warp exited\n", w->warp_done[w->cur >> 5]); abort(); }
     int lane = w->cur & 31;
     WarpRv *r = &w->rv[w->cur >> 5];
     r->slot[lane] = v;
@@ -158,6 +159,8 @@ static inline int d_popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int d_popcll(uint64_t v) { return __builtin_popcountll(v); }
 static inline int d_clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline int d_ffs(uint32_t v) { return __builtin_ffs((int) v); }
+static inline int d_clzll(uint64_t v) { return v ? __builtin_clzll(v) : 64; }
+static inline int d_ctzll(uint64_t v) { return v ? __builtin_ctzll(v) : -1; }
 // compiled with -ffp-contract=off: plain IEEE operations
 static inline float f_mul(float a, float b) { return a * b; }
 static inline float f_add(float a, float b) { return a + b; }
@@ -178,6 +181,18 @@ static inline uint4 s_load_v4(const uint4 *p) { return *p; }
 static inline void s_store_v4(uint4 *p, uint4 v) { *p = v; }
 static inline float u2f(uint32_t v) { float r; memcpy(&r, &v, 4); return r; }
 static inline uint32_t f2u(float v) { uint32_t r; memcpy(&r, &v, 4); return r; }
+static inline double d_fma(double a, double b, double c) { return fma(a, b, c); }
+static inline float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
+static inline double u2d(uint64_t v) { double r; memcpy(&r, &v, 8); return r; }
+static inline uint64_t d2u(double v) { uint64_t r; memcpy(&r, &v, 8); return r; }
+// bulk async copy: performed at issue; the barrier wait is a no-op
+static inline void t_bar_init(uint64_t *bar) { *bar = 0; }
+static inline void t_fence_async() {}
+static inline void t_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    if (((uintptr_t) dst & 15) || ((uintptr_t) src & 15) || (bytes & 15)) { fprintf(stderr, "warp_emul: misaligned bulk copy\n"); abort(); }
+    memcpy(dst, src, bytes); (*bar)++;
+}
+static inline void t_bar_wait(uint64_t *bar, uint32_t parity) { (void) bar; (void) parity; }
 
 static void emu_trampoline() {
     WarpEmu *w = g_warp;
@@ -185,6 +200,7 @@ static void emu_trampoline() {
     int me = w->cur;
     w->done[me] = 1;
     w->n_done++;
+    w->warp_done[me >> 5]++;
     if (w->n_done == w->n_threads) {
         swapcontext(&w->ctx[me], &w->main_ctx);
     } else {

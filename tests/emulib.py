@@ -64,7 +64,7 @@ def build():
     out = os.path.join(EMUL_DIR, "libunc_emul.so")
     deps = [src, os.path.join(EMUL_DIR, "warp_emul.hpp")] + \
            [os.path.join(ROOT, "uncalled_b200", "csrc", f) for f in
-            ("unc_device.cuh", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp")]
+            ("unc_device.cuh", "unc_k1.cuh", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-DUNC_EMUL", "-DK2_MAXSEG=16u", "-fPIC", "-shared",
@@ -90,6 +90,7 @@ def lib():
         L.emu_match_probs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
         L.emu_sa.argtypes = [C.c_void_p, C.c_uint64]
         L.emu_sa.restype = C.c_uint64
+        L.emu_k1_stats.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -121,6 +122,13 @@ class Emu:
         if rc != 0:
             raise RuntimeError("emu_map_batch rc=%d" % rc)
         return list(out), [ev[i, :ne[i]].copy() for i in range(n)], [nm[i, :ne[i]].copy() for i in range(n)], mel
+
+
+def k1_stats():
+    """(tiles, FSM re-run rounds, re-run lanes, reads flagged for the serial routine) of the last emu_map_batch."""
+    a = (C.c_uint32 * 4)()
+    lib().emu_k1_stats(a)
+    return tuple(a)
 
 
 PAF_KEYS = ("mapped", "fwd", "rid", "n_events", "events_used", "matches",

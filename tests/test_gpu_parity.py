@@ -54,6 +54,70 @@ def test_events_i16_calibration(U, ex, golden_read):
     assert ne[0] == len(m) and np.array_equal(ev[0, :ne[0]], m) and mel[0] == omel
 
 
+def _events_vs_oracle(U, bm, sigs, dtype=0, cal=(1.0, 0.0, 1.0), pas=None, offsets=None):
+    import orclib
+    O = orclib.Oracle()
+    lens = [len(s) for s in sigs]
+    flat = np.concatenate(sigs) if offsets is None else offsets[1]
+    d = U.make_descs(lens, dtype=dtype, cal=cal, offsets=None if offsets is None else offsets[0])
+    ev, nm, ne, mel = bm.events(flat, d)
+    for i, s in enumerate(sigs):
+        x = pas[i] if pas is not None else np.ascontiguousarray(s, np.float32)
+        m, _, _, omel = O.detect(x)
+        assert ne[i] == len(m) and np.array_equal(ev[i, :ne[i]], m), i
+        assert mel[i] == omel or (np.isnan(mel[i]) and np.isnan(omel)), i
+        if len(m):
+            assert np.array_equal(nm[i, :ne[i]], O.normalize(m), equal_nan=True), i
+    return bm.k1_stats()
+
+
+def test_events_edge_lengths_unaligned_and_tile_boundaries(U, ex, golden_read):
+    """warp-parallel event detector: empty/tiny reads, lengths around the 1152-position tile
+    boundary, reads starting at odd sample offsets (unaligned bulk-copy sources, buffer tail)."""
+    idx, bm = ex
+    raw = golden_read["raw"]
+    lens = [0, 1, 5, 6, 7, 11, 12, 13, 40, 1151, 1152, 1153, 1157, 1158, 1159, 2304, 2309, 2310, 3461]
+    sigs = [raw[7 * i:7 * i + L] for i, L in enumerate(lens)]
+    st = _events_vs_oracle(U, bm, sigs)
+    assert st[3] == 0
+
+
+def test_events_inexact_sums_take_the_serial_path(U, ex):
+    import synth
+    import synthdata
+    idx, bm = ex
+    prefix, g = synthdata.get_index("g200k")
+    sig, _ = synth.reads(g, 3, 5000, seed=2)
+    s = sig[0].copy(); s[1000] = 1e-20; s[2000] = 3e7
+    t = sig[1].copy(); t[10] = np.float32(1e-41)
+    z = np.zeros(3000, np.float32)
+    c = np.full(3000, 87.25, np.float32); c[1500:] = 90.5
+    st = _events_vs_oracle(U, bm, [s, z, c, t, sig[2]])
+    assert st[3] == 2
+
+
+def test_events_many_synthetic_reads_f32_and_i16(U, ex):
+    import synth
+    import synthdata
+    idx, bm = ex
+    prefix, g = synthdata.get_index("g200k")
+    sig, _ = synth.reads(g, 60, 9000, seed=11)
+    rng = np.random.default_rng(5)
+    lens = [int(x) for x in rng.integers(100, 9000, 60)]
+    sigs = [sig[i, :L] for i, L in enumerate(lens)]
+    st = _events_vs_oracle(U, bm, sigs)
+    assert st[3] == 0
+    for cal in [(1467.61, 10.0, 8192.0), (1534.14, 3.0, 8000.0)]:
+        i16s, pas = [], []
+        for s in sigs[:24]:
+            raw = np.clip(np.round(s.astype(np.float64) * cal[2] / cal[0] - cal[1]), -50, 32000).astype(np.int16)
+            raw[50:53] = -7
+            i16s.append(raw)
+            pas.append(((np.float32(cal[0]) * (raw.astype(np.uint16).astype(np.float32) + np.float32(cal[1]))) /
+                        np.float32(cal[2])).astype(np.float32))
+        _events_vs_oracle(U, bm, i16s, dtype=1, cal=cal, pas=pas)
+
+
 def test_pore_model_matches_reference_golden(U, ex):
     idx, _ = ex
     g = np.load(os.path.join(ROOT, "tests", "golden", "example_model.npz"))

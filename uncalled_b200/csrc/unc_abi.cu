@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "unc_device.cuh"
+#include "unc_k1.cuh"
 #include "../../include/unc_b200.h"
 #include "unc_host_index.hpp"
 #include "unc_host_params.hpp"
@@ -42,9 +43,25 @@ __global__ void k_sa_expand(DevIndex ix, u32 *out, u32 n_rows) {
     out[k] = unc_sa(ix, k, &a, &b);
 }
 
-__global__ void __launch_bounds__(128) k1_events(DevBatch B, DevParams p) {
+// K1: warp-per-read event detection (unc_k1.cuh).  K1_WARPS independent warps per CTA, each
+// with its own shared-memory tile buffers and mbarrier; reads are pulled from an atomic queue.
+#ifndef K1_WARPS
+#define K1_WARPS 4
+#endif
+__global__ void __launch_bounds__(K1_WARPS * 32) k1_events(DevBatch B, DevParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K1WarpSmem *sm = (K1WarpSmem *) smem_raw + (threadIdx.x >> 5);
+    unc_k1_warp_main(B, p, sm);
+}
+// reads whose samples fail the exactness condition of the warp-parallel sums: serial routine
+__global__ void __launch_bounds__(128) k1_fallback(DevBatch B, DevParams p) {
     u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < B.n_reads) unc_k1_read(B, p, r);
+    if (r < B.n_reads && B.k1_flags[r]) unc_k1_read(B, p, r);
+}
+// normaliser statistics (sequential double reductions), one thread per read
+__global__ void __launch_bounds__(128) k1_norm(DevBatch B, DevParams p) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < B.n_reads && !B.k1_flags[r]) unc_k1_norm_read(B, p, r);
 }
 
 // Persistent CTA-per-read mapper.  Each CTA stages the pore model, the 1024 k-mer FM ranges
@@ -83,8 +100,8 @@ __global__ void k_fm_neighbors(DevIndex ix, u32 n, const u64 *st, const u64 *en,
     u32 ns[4], ne[4], nb = 0, c = base[i];
     u32 ok = unc_neighbors(ix, (u32) st[i], (u32) en[i], 1u << c, ns, ne, &nb);
     if (!((ok >> c) & 1u)) {   // empty range: report it the way get_neighbor does (start = end + 1 ...)
-        ns[c] = ix.L2[c] + unc_occ(ix, (u32) st[i] - 1u, c, &nb) + 1u;
-        ne[c] = ix.L2[c] + unc_occ(ix, (u32) en[i], c, &nb);
+        ns[c] = unc_L2(ix, c) + unc_occ(ix, (u32) st[i] - 1u, c, &nb) + 1u;
+        ne[c] = unc_L2(ix, c) + unc_occ(ix, (u32) en[i], c, &nb);
     }
     ost[i] = ns[c];
     oen[i] = ne[c];
@@ -138,7 +155,8 @@ struct unc_pool {
     void *d_samples = nullptr;
     DevReadDesc *d_reads = nullptr, *h_reads = nullptr;
     float *d_events = nullptr, *d_normed = nullptr, *d_scale = nullptr, *d_shift = nullptr, *d_mel = nullptr;
-    u32 *d_n_events = nullptr, *d_queue = nullptr;
+    u32 *d_n_events = nullptr, *d_queue = nullptr, *d_k1_flags = nullptr;   // d_queue: [k2 queue, k1 queue, 4 x k1 stats]
+    uint32_t k1_grid = 0;
     DevRec *d_out = nullptr;
     unsigned long long *d_dbg = nullptr;
     unc_paf_rec *h_out = nullptr;  // pinned staging
@@ -331,6 +349,14 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     if (per_sm < 1) return bail(UNC_E_CUDA, "k2_map does not fit on an SM");
     uint32_t grid = (uint32_t) prop.multiProcessorCount * (uint32_t) per_sm;
     if (grid > max_reads) grid = max_reads;
+    {
+        const size_t k1_smem = (size_t) K1_WARPS * sizeof(K1WarpSmem);
+        PT(cudaFuncSetAttribute(k1_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k1_smem));
+        int k1_per_sm = 0;
+        PT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1_per_sm, k1_events, K1_WARPS * 32, k1_smem));
+        if (k1_per_sm < 1) return bail(UNC_E_CUDA, "k1_events does not fit on an SM");
+        P->k1_grid = (uint32_t) prop.multiProcessorCount * (uint32_t) k1_per_sm;
+    }
     // per-slot workspace sizes
     const size_t maxp = prm->max_paths;
     const size_t nchmax = (maxp + 31) / 32;
@@ -372,14 +398,15 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     PT(cudaMalloc(&P->W.rlist, (size_t) P->n_slots * P->rlist_stride * 8));
     PT(cudaMalloc(&P->W.clu, (size_t) P->n_slots * P->clu_stride * 16));
     PT(cudaMalloc(&P->W.dir, (size_t) P->n_slots * P->dir_stride * 16));
-    PT(cudaMalloc(&P->d_samples, max_samples * 4));
+    PT(cudaMalloc(&P->d_samples, max_samples * 4 + 64));
     PT(cudaMalloc(&P->d_reads, (size_t) max_reads * sizeof(DevReadDesc)));
     PT(cudaMallocHost(&P->h_reads, (size_t) max_reads * sizeof(DevReadDesc)));
     PT(cudaMalloc(&P->d_scale, (size_t) max_reads * 4));
     PT(cudaMalloc(&P->d_shift, (size_t) max_reads * 4));
     PT(cudaMalloc(&P->d_mel, (size_t) max_reads * 4));
     PT(cudaMalloc(&P->d_n_events, (size_t) max_reads * 4));
-    PT(cudaMalloc(&P->d_queue, 4));
+    PT(cudaMalloc(&P->d_queue, 32));
+    PT(cudaMalloc(&P->d_k1_flags, (size_t) max_reads * 4));
     PT(cudaMalloc(&P->d_out, (size_t) max_reads * sizeof(DevRec)));
 #ifdef UNC_PHASE_TIMING
     PT(cudaMalloc(&P->d_dbg, (size_t) max_reads * 64));
@@ -397,7 +424,7 @@ void unc_pool_free(unc_pool *P) {
     cudaFree(P->W.paths); cudaFree(P->W.hist); cudaFree(P->W.wlist); cudaFree(P->W.ckey); cudaFree(P->W.cks); cudaFree(P->W.elist); cudaFree(P->W.order); cudaFree(P->W.rlist); cudaFree(P->W.clu); cudaFree(P->W.dir);
     cudaFree(P->d_samples); cudaFree(P->d_reads); cudaFreeHost(P->h_reads);
     cudaFree(P->d_events); cudaFree(P->d_normed);
-    cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue);
+    cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue); cudaFree(P->d_k1_flags);
     cudaFree(P->d_out); cudaFreeHost(P->h_out); cudaFree(P->d_dbg);
     for (int i = 0; i < 5; i++) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
     if (P->stream) cudaStreamDestroy(P->stream);
@@ -437,9 +464,13 @@ static int stage_reads(unc_pool *P, const unc_read_desc *reads, uint32_t n, uint
     return UNC_OK;
 }
 
-static DevBatch make_batch(unc_pool *P, const void *d_samples, uint32_t n, bool normed) {
+static DevBatch make_batch(unc_pool *P, const void *d_samples, uint64_t samples_bytes, uint32_t n, bool normed) {
     DevBatch B;
     B.samples = d_samples;
+    B.samples_bytes = samples_bytes;
+    B.k1_queue = P->d_queue + 1;
+    B.k1_flags = P->d_k1_flags;
+    B.k1_stats = P->d_queue + 2;
     B.reads = P->d_reads;
     B.n_reads = n;
     B.events = P->d_events;
@@ -455,6 +486,14 @@ static DevBatch make_batch(unc_pool *P, const void *d_samples, uint32_t n, bool 
     B.n_seqs = (u32) P->idx->h.names.size();
     B.l_pac = (u64) P->idx->h.l_pac;
     return B;
+}
+
+// event detection (warp per read) -> serial redo of flagged reads -> normaliser statistics
+static void launch_k1(unc_pool *P, const DevBatch &B, uint32_t n, cudaStream_t s) {
+    uint32_t g = std::min<uint32_t>(P->k1_grid, (n + K1_WARPS - 1) / K1_WARPS);
+    k1_events<<<g, K1_WARPS * 32, (size_t) K1_WARPS * sizeof(K1WarpSmem), s>>>(B, P->dp);
+    k1_fallback<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
+    k1_norm<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
 }
 
 static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, bool on_device,
@@ -475,10 +514,11 @@ static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
         h2d += span;
     }
     CUDA_TRY(cudaMemcpyAsync(P->d_reads, P->h_reads, (size_t) n * sizeof(DevReadDesc), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemsetAsync(P->d_queue, 0, 4, s));
+    CUDA_TRY(cudaMemsetAsync(P->d_queue, 0, 32, s));
     CUDA_TRY(cudaEventRecord(P->ev[1], s));
-    DevBatch B = make_batch(P, d_samples, n, false);
-    k1_events<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
+    // the pool's own staging buffer is padded, so whole 16-byte bulk copies may run past `span`
+    DevBatch B = make_batch(P, d_samples, on_device ? span : ((span + 15) & ~(uint64_t) 15), n, false);
+    launch_k1(P, B, n, s);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[2], s));
     uint32_t grid = std::min<uint32_t>(P->grid, n);
@@ -496,7 +536,7 @@ static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     cudaEventElapsedTime(&t.k2_ms, P->ev[2], P->ev[3]);
     cudaEventElapsedTime(&t.d2h_ms, P->ev[3], P->ev[4]);
     cudaEventElapsedTime(&t.total_ms, P->ev[0], P->ev[4]);
-    t.kernel_launches = 2;
+    t.kernel_launches = 4;
     t.h2d_bytes = h2d;
     t.d2h_bytes = (uint64_t) n * sizeof(DevRec);
     int worst = UNC_OK;
@@ -527,8 +567,9 @@ int unc_events_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     CUDA_TRY(cudaMemcpyAsync(P->d_samples, samples, span, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(P->d_reads, P->h_reads, (size_t) n * sizeof(DevReadDesc), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(P->ev[1], s));
-    DevBatch B = make_batch(P, P->d_samples, n, true);
-    k1_events<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
+    CUDA_TRY(cudaMemsetAsync(P->d_queue, 0, 32, s));
+    DevBatch B = make_batch(P, P->d_samples, (span + 15) & ~(uint64_t) 15, n, true);
+    launch_k1(P, B, n, s);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[2], s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -547,7 +588,7 @@ int unc_events_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     cudaEventElapsedTime(&t.h2d_ms, P->ev[0], P->ev[1]);
     cudaEventElapsedTime(&t.k1_ms, P->ev[1], P->ev[2]);
     t.total_ms = t.h2d_ms + t.k1_ms;
-    t.kernel_launches = 1;
+    t.kernel_launches = 3;
     t.h2d_bytes = span + (uint64_t) n * sizeof(DevReadDesc);
     return UNC_OK;
 }
@@ -600,6 +641,12 @@ int unc_fm_sa(const unc_index *x, uint32_t n, const uint64_t *rows, uint64_t *ou
 int unc_pool_debug_phases(const unc_pool *P, uint32_t n, unsigned long long *out) {
     if (!P || !out || !P->d_dbg) return fail(UNC_E_ARG, "phase timing not compiled in");
     CUDA_TRY(cudaMemcpy(out, P->d_dbg, (size_t) n * 64, cudaMemcpyDeviceToHost));
+    return UNC_OK;
+}
+
+int unc_pool_k1_stats(const unc_pool *P, uint32_t out[4]) {
+    if (!P || !out) return fail(UNC_E_ARG, "null argument");
+    CUDA_TRY(cudaMemcpy(out, P->d_queue + 2, 16, cudaMemcpyDeviceToHost));
     return UNC_OK;
 }
 

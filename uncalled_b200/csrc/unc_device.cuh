@@ -42,6 +42,12 @@ struct DevIndex {
     u32 start_bits;        // bits needed to represent seq_len (radix-sort passes)
 };
 
+// L2[c] through selects: a dynamically indexed member would force the whole kernel-parameter
+// struct into local memory (LDL on the extension loop's critical path)
+UNC_DEV u32 unc_L2(const DevIndex &ix, u32 c) {
+    return c == 0 ? ix.L2[0] : c == 1 ? ix.L2[1] : c == 2 ? ix.L2[2] : c == 3 ? ix.L2[3] : ix.L2[4];
+}
+
 struct DevParams {
     u32 max_rep_copy, max_paths, max_consec_stay, max_events, min_rep_len;
     float max_stay_frac, min_seed_prob;
@@ -68,8 +74,12 @@ struct DevRec {   // == unc_paf_rec
 
 struct DevBatch {
     const void *samples;
+    u64 samples_bytes;   // extent of the sample buffer (bulk copies never read past it)
     const DevReadDesc *reads;
     u32 n_reads;
+    u32 *k1_queue;       // atomic read counter of the event-detection kernel
+    u32 *k1_flags;       // per read: 1 = redo with the serial routine (exactness condition failed)
+    u32 *k1_stats;       // optional (may be null): tiles, FSM re-run rounds, re-run lanes, flagged reads
     // K1 outputs
     float *events;       // n_reads x ev_stride valid event means (raw, un-normalised)
     float *normed;       // optional (may be null): normalised means
@@ -150,7 +160,7 @@ UNC_DEV OccBlock unc_load_block(const DevIndex &ix, u32 kk) {
 
 // bwt_occ (reference submods/bwa/bwt.c:107-129) for a single row
 UNC_DEV u32 unc_occ(const DevIndex &ix, u32 k, u32 c, u32 *n_blocks) {
-    if (k == ix.seq_len) return ix.L2[c + 1] - ix.L2[c];
+    if (k == ix.seq_len) return unc_L2(ix, c + 1) - unc_L2(ix, c);
     if (k == 0xFFFFFFFFu) return 0;
     u32 kk = k - (k >= ix.primary);
     OccBlock b = unc_load_block(ix, kk);
@@ -187,7 +197,7 @@ UNC_DEV u32 unc_neighbors(const DevIndex &ix, u32 start, u32 end, u32 want, u32 
             u32 cnt = (u32) d_popcll(unc_match_bits(w, c) & between);
             if (cnt == 0) continue;
             u32 ok = unc_occ_in_block(bk.b0, bk.b1, bk.b2, bk.b3, kk, c);
-            ns[c] = ix.L2[c] + ok + 1;
+            ns[c] = unc_L2(ix, c) + ok + 1;
             ne[c] = ns[c] + cnt - 1;
             valid |= 1u << c;
         }
@@ -199,9 +209,9 @@ UNC_DEV u32 unc_neighbors(const DevIndex &ix, u32 start, u32 end, u32 want, u32 
     for (u32 c = 0; c < 4; c++) {
         if (!((want >> c) & 1u)) continue;
         u32 ok = unc_occ_in_block(bk.b0, bk.b1, bk.b2, bk.b3, kk, c);
-        u32 ol = l_is_end ? (ix.L2[c + 1] - ix.L2[c]) : unc_occ_in_block(bl.b0, bl.b1, bl.b2, bl.b3, ll, c);
-        ns[c] = ix.L2[c] + ok + 1;
-        ne[c] = ix.L2[c] + ol;
+        u32 ol = l_is_end ? (unc_L2(ix, c + 1) - unc_L2(ix, c)) : unc_occ_in_block(bl.b0, bl.b1, bl.b2, bl.b3, ll, c);
+        ns[c] = unc_L2(ix, c) + ok + 1;
+        ne[c] = unc_L2(ix, c) + ol;
         if (ns[c] <= ne[c]) valid |= 1u << c;
     }
     return valid;
@@ -215,7 +225,7 @@ UNC_DEV u32 unc_sa(const DevIndex &ix, u32 k, u32 *n_steps, u32 *n_blocks) {
         u32 x = k - (k > ix.primary);
         const u32 *wp = (const u32 *) ix.bwt + (((size_t) (x >> 7)) << 4) + 8 + ((x & 0x7fu) >> 4);
         u32 c = (d_ldg(wp) >> ((~x & 0xfu) << 1)) & 3u;
-        u32 r = ix.L2[c] + unc_occ(ix, k, c, n_blocks);
+        u32 r = unc_L2(ix, c) + unc_occ(ix, k, c, n_blocks);
         k = (k == ix.primary) ? 0u : r;
     }
     *n_steps += steps;
@@ -232,13 +242,13 @@ UNC_DEV u32 unc_sa_lookup(const DevIndex &ix, u32 k, u32 *n_steps, u32 *n_blocks
 // start is L2[b], NOT L2[b]+1 (:172-174) -- followed by four get_neighbor steps.
 UNC_DEV uint2 unc_kmer_range_compute(const DevIndex &ix, u32 kmer) {
     u32 head = (kmer >> 8) & 3u;
-    u32 st = ix.L2[head], en = ix.L2[head + 1];
+    u32 st = unc_L2(ix, head), en = unc_L2(ix, head + 1);
     u32 nb = 0;
     for (u32 i = 1; i < 5; i++) {
         u32 base = (kmer >> (2 * (4 - i))) & 3u;
         u32 ok = unc_occ(ix, st - 1u, base, &nb), ol = unc_occ(ix, en, base, &nb);
-        st = ix.L2[base] + ok + 1u;
-        en = ix.L2[base] + ol;
+        st = unc_L2(ix, base) + ok + 1u;
+        en = unc_L2(ix, base) + ol;
     }
     return make_uint2(st, en);
 }
@@ -1140,26 +1150,48 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 c_sync_sub(1, (int) nwt);
                 uint4 *tmp = src; src = dst; dst = tmp;
             }
-            // runs of equal fm_start: order by (fm_end, seed_prob, emission index)
-            for (u32 g = wt; g < nc; g += nwt) {
-                u32 s = src[g].x;
-                bool head = (g == 0 || src[g - 1].x != s) && (g + 1 < nc && src[g + 1].x == s);
-                if (head) {
-                    u32 e = g + 1;
-                    while (e < nc && src[e].x == s) e++;
-                    for (u32 i = g + 1; i < e; i++) {
-                        uint4 key = src[i];
-                        float kp = u2f(key.z);
-                        u32 j = i;
-                        while (j > g) {
-                            uint4 o = src[j - 1];
-                            float op = u2f(o.z);
-                            bool gt = o.y > key.y || (o.y == key.y && (kp < op || (!(op < kp) && (o.w >> 16) > (key.w >> 16))));
-                            if (!gt) break;
-                            src[j] = o;
-                            j--;
+            // runs of equal fm_start: order by (fm_end, seed_prob, emission index).  Run heads are
+            // found chunk-wise (one coalesced load per 32 keys, neighbours by shuffle); the rare
+            // runs are then insertion-sorted by their head lane.
+            {
+                uint4 kq = make_uint4(0, 0, 0, 0); u32 bx = 0, ax = 0;   // key, fm_start before / after the chunk
+                if (ww < nch) {
+                    u32 g0 = ww * 32 + (u32) lane;
+                    if (g0 < nc) kq = src[g0];
+                    if (lane == 0 && g0 > 0) bx = src[g0 - 1].x;
+                    if (lane == 31 && g0 + 1 < nc) ax = src[g0 + 1].x;
+                }
+                for (u32 c = ww; c < nch; c += nwk) {
+                    const u32 g = c * 32 + (u32) lane;
+                    const uint4 k = kq; const u32 bxc = bx, axc = ax;
+                    if (c + nwk < nch) {
+                        u32 gn = g + nwk * 32;
+                        if (gn < nc) kq = src[gn];
+                        if (lane == 0) bx = src[gn - 1].x;
+                        if (lane == 31 && gn + 1 < nc) ax = src[gn + 1].x;
+                    }
+                    u32 px = w_shfl_up(k.x, 1), nx = w_shfl_down(k.x, 1);
+                    if (lane == 0) px = bxc;
+                    if (lane == 31) nx = axc;
+                    const u32 s = k.x;
+                    bool head = g < nc && (g == 0 || px != s) && (g + 1 < nc && nx == s);
+                    if (head) {
+                        u32 e = g + 1;
+                        while (e < nc && src[e].x == s) e++;
+                        for (u32 i = g + 1; i < e; i++) {
+                            uint4 key = src[i];
+                            float kp = u2f(key.z);
+                            u32 j = i;
+                            while (j > g) {
+                                uint4 o = src[j - 1];
+                                float op = u2f(o.z);
+                                bool gt = o.y > key.y || (o.y == key.y && (kp < op || (!(op < kp) && (o.w >> 16) > (key.w >> 16))));
+                                if (!gt) break;
+                                src[j] = o;
+                                j--;
+                            }
+                            src[j] = key;
                         }
-                        src[j] = key;
                     }
                 }
             }

@@ -41,6 +41,8 @@ UNC_DEV int d_popc(uint32_t v) { return __popc(v); }
 UNC_DEV int d_popcll(uint64_t v) { return __popcll(v); }
 UNC_DEV int d_clz(uint32_t v) { return __clz((int) v); }
 UNC_DEV int d_ffs(uint32_t v) { return __ffs((int) v); }
+UNC_DEV int d_clzll(uint64_t v) { return __clzll((long long) v); }
+UNC_DEV int d_ctzll(uint64_t v) { return __ffsll((long long) v) - 1; }
 // IEEE round-to-nearest, never contracted into FMA (the reference build has no FMA)
 UNC_DEV float f_mul(float a, float b) { return __fmul_rn(a, b); }
 UNC_DEV float f_add(float a, float b) { return __fadd_rn(a, b); }
@@ -79,6 +81,32 @@ UNC_DEV void s_store_u64(uint64_t *p, uint64_t v) {
 }
 UNC_DEV float u2f(uint32_t v) { return __uint_as_float(v); }
 UNC_DEV uint32_t f2u(float v) { return __float_as_uint(v); }
+// explicit fused multiply-add (used only where the reference result is reproduced through an exactly
+// rounded division sequence, never as a contraction of a*b+c)
+UNC_DEV double d_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+UNC_DEV float f_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+UNC_DEV double u2d(uint64_t v) { return __longlong_as_double((long long) v); }
+UNC_DEV uint64_t d2u(double v) { return (uint64_t) __double_as_longlong(v); }
+// ---- bulk asynchronous copy global -> shared (TMA, cp.async.bulk) completing on an mbarrier
+UNC_DEV void t_bar_init(uint64_t *bar) {
+    unsigned a = (unsigned) __cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy ones
+UNC_DEV void t_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one thread: arm the barrier with `bytes` and start the copy (dst, src 16-byte aligned, bytes % 16 == 0)
+UNC_DEV void t_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    unsigned b = (unsigned) __cvta_generic_to_shared(bar), d = (unsigned) __cvta_generic_to_shared(dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+UNC_DEV void t_bar_wait(uint64_t *bar, uint32_t parity) {
+    unsigned b = (unsigned) __cvta_generic_to_shared(bar);
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+                 ::"r"(b), "r"(parity) : "memory");
+}
 #endif
 
 UNC_DEV uint32_t w_lanemask_lt() { return (1u << w_lane()) - 1u; }
@@ -92,6 +120,13 @@ UNC_DEV uint32_t w_exscan(uint32_t v, uint32_t *total) {
     }
     *total = w_shfl(x, 31);
     return x - v;
+}
+
+UNC_DEV uint64_t w_shfl64(uint64_t v, int src) {
+    return ((uint64_t) w_shfl((uint32_t) (v >> 32), src) << 32) | w_shfl((uint32_t) v, src);
+}
+UNC_DEV uint64_t w_shfl_up64(uint64_t v, int d) {
+    return ((uint64_t) w_shfl_up((uint32_t) (v >> 32), d) << 32) | w_shfl_up((uint32_t) v, d);
 }
 
 UNC_DEV uint32_t w_max(uint32_t v) {

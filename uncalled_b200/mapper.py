@@ -131,6 +131,12 @@ class BatchMapper:
                                         nm.ctypes.data, ne.ctypes.data, mel.ctypes.data))
         return ev, nm, ne, mel
 
+    def k1_stats(self):
+        """(tiles, FSM re-run rounds, lanes re-run, reads redone serially) of the last batch's event detection."""
+        a = (C.c_uint32 * 4)()
+        N.check(self.L.unc_pool_k1_stats(self.h, a))
+        return tuple(a)
+
     def timing(self):
         t = N.Timing()
         N.check(self.L.unc_pool_last_timing(self.h, C.byref(t)))

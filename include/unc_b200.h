@@ -99,6 +99,9 @@ typedef struct {
     float h2d_ms, k1_ms, k2_ms, d2h_ms, total_ms; /* CUDA events on the pool's stream */
     uint32_t kernel_launches;                      /* launches of this library's kernels */
     uint64_t h2d_bytes, d2h_bytes;
+    float k1_events_ms;                            /* the event-detection kernel alone (k1_ms also covers the
+                                                      serial-redo and normaliser-statistics launches) */
+    float pad_;
 } unc_timing;
 
 typedef struct {

@@ -1,0 +1,83 @@
+"""The reference-shaped Python surface (uncalled_b200/api.py: Conf, Paf, MapPool) against the
+golden PAF lines of the real `uncalled map` (tests/golden/example_paf.json)."""
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "example_paf.json")))
+
+
+def test_paf_formats_like_the_reference():
+    from uncalled_b200.api import Paf
+    f = GOLD["default"]["fields"]
+    p = Paf(f[0], 486, 257117)
+    p.set_read_len(106)
+    p.set_mapped(73, 106, f[5], 6938, 6976, 10000, False, 38)
+    assert p.line() == GOLD["default"]["line"]
+    p.set_float(Paf.Tag.MAP_TIME, 12.5)
+    assert p.line() == GOLD["default"]["line"] + "\tmt:f:12.500000"
+    u = Paf("r1", 3, 9)
+    u.set_read_len(3562)
+    assert u.line() == "r1\t3562" + "\t*" * 9 + "\t255\tch:i:3\tst:i:9"
+    assert not u.is_mapped() and p.is_mapped() and not p.is_ended()
+    assert Paf.MAP_TIME == Paf.Tag.MAP_TIME and Paf.KEEP == 11      # export_values()
+    buf = io.StringIO()
+    u.print_paf(buf)
+    assert buf.getvalue().endswith("st:i:9\n")
+
+
+def test_conf_has_real_properties_with_docs():
+    from uncalled_b200.api import Conf
+    for name in ("read_list", "max_reads", "fast5_list", "bwa_prefix", "max_events", "max_chunks", "threads"):
+        assert isinstance(getattr(Conf, name), property) and getattr(Conf, name).__doc__
+    c = Conf()
+    c.max_events = "100"                       # args.load_conf assigns parsed values (uncalled/args.py:296-302)
+    assert c.max_events == 100 and c.chunk_time == 1.0 and c.idx_preset == "default"
+
+
+@pytest.mark.gpu
+def test_map_pool_prints_the_reference_paf_lines(example_prefix, golden_read):
+    """`uncalled map`, `-c 1` and `-e 100` on the example read (config 1), line for line up to the mt tag."""
+    from uncalled_b200.api import Conf, MapPool
+    raw = golden_read["raw"]
+    rid, ch, st = str(golden_read["read_id"]), int(golden_read["channel"]), int(golden_read["start"])
+    for key, mod in (("default", {}), ("max_chunks_1", {"max_chunks": 1}), ("max_events_100", {"max_events": 100})):
+        conf = Conf()
+        conf.bwa_prefix = example_prefix
+        for k, v in mod.items():
+            setattr(conf, k, v)
+        pool = MapPool(conf)
+        assert not pool.running()
+        pool.add_read(rid, raw, channel=ch, number=0, start_sample=st)
+        lines = []
+        while pool.running():
+            lines += [p.line() for p in pool.update()]
+        pool.stop()
+        assert len(lines) == 1
+        body, mt = lines[0].rsplit("\t", 1)
+        assert body == GOLD[key]["line"] and mt.startswith("mt:f:"), (key, lines[0])
+
+
+@pytest.mark.gpu
+def test_map_pool_i16_reads_and_filters(example_prefix, golden_read, tmp_path):
+    from uncalled_b200.api import Conf, MapPool
+    raw = golden_read["raw"]
+    cal = (1534.14, 10.0, 8192.0)       # the example read's calibration attributes
+    dac = np.round(raw.astype(np.float64) * cal[2] / cal[0] - cal[1]).astype(np.int64)
+    dac16 = dac.astype(np.uint16).astype(np.int16)       # the >32767 spike wraps like the fast5 payload does
+    pa = (np.float32(cal[0]) * (dac16.astype(np.uint16).astype(np.float32) + np.float32(cal[1]))) / np.float32(cal[2])
+    assert np.array_equal(pa.astype(np.float32), raw)
+    rl = tmp_path / "reads.txt"
+    rl.write_text("keep_me\n")
+    conf = Conf()
+    conf.bwa_prefix, conf.read_list = example_prefix, str(rl)
+    pool = MapPool(conf)
+    assert pool.add_read("keep_me", dac16, channel=486, start_sample=257117, calibration=cal)
+    assert not pool.add_read("drop_me", dac16, calibration=cal)
+    out = pool.update()
+    pool.stop()
+    assert len(out) == 1 and out[0].fields()[1:] == GOLD["default"]["fields"][1:]

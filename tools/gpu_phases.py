@@ -22,12 +22,12 @@ ph = np.zeros((n_reads, 8), np.uint64)
 L = N.lib()
 L.unc_pool_debug_phases.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
 N.check(L.unc_pool_debug_phases(bm.h, n_reads, ph.ctypes.data))
-names = ["A probs", "B extend", "C sort", "C fixup", "D dedup/src", "S sa + E", "X barrier(tracker)", "loop head"]
+names = ["A probs", "B extend + B1 deferred seed_prob", "B2 scan/ended rows/key compaction", "C radix sort + fix-up", "D dedup/src", "S sa + E", "X barrier(tracker)", "loop head"]
 ev = out["events_used"].astype(np.float64) + 1
 tot = ph.sum(axis=0).astype(np.float64)
 print("total events", ev.sum())
 for i, nm in enumerate(names):
-    print("%-20s %6.1f%%  %8.0f cycles/event" % (nm, 100 * tot[i] / tot.sum(), tot[i] / ev.sum()))
+    print("%-36s %6.1f%%  %8.0f cycles/event" % (nm, 100 * tot[i] / tot.sum(), tot[i] / ev.sum()))
 print("cycles/event total %.0f" % (tot.sum() / ev.sum()))
 nm = out["mapped"] == 0
 print("non-mapping reads: cycles/event %.0f ; mapping: %.0f" % (ph[nm].sum() / ev[nm].sum(), ph[~nm].sum() / ev[~nm].sum()))

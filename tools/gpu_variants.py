@@ -33,5 +33,10 @@ if __name__ == "__main__":
         vdir = os.path.join(ROOT, "uncalled_b200", "variants")
         for f in sorted(os.listdir(vdir)):
             if f.endswith(".so"):
-                r = subprocess.run([sys.executable, __file__, "--one", os.path.join(vdir, f), str(n)], capture_output=True, text=True, timeout=600)
+                # name__ENV=VAL__ENV2=VAL2.so sets environment knobs for that run
+                env = dict(os.environ)
+                for kv in f[:-3].split("__")[1:]:
+                    k, v = kv.split("=")
+                    env[k] = v
+                r = subprocess.run([sys.executable, __file__, "--one", os.path.join(vdir, f), str(n)], capture_output=True, text=True, timeout=600, env=env)
                 print(r.stdout.strip() or ("FAILED %s: %s" % (f, r.stderr[-400:])), flush=True)

@@ -63,7 +63,7 @@ assert PAF_DTYPE.itemsize == C.sizeof(PafRec) and DESC_DTYPE.itemsize == C.sizeo
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("k1_ms", C.c_float), ("k2_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("k1_events_ms", C.c_float), ("pad_", C.c_float)]
 
 
 class IndexInfo(C.Structure):

@@ -1,0 +1,276 @@
+"""Host-side mirror of the reference's Python surface for the map path: `Conf`, `Paf`, `MapPool`
+(what `_uncalled` exports through reference src/pybinder.cpp:14-91 and what `scripts/uncalled
+map` drives, scripts/uncalled:127-167).
+
+Same names, argument meaning and error behaviour; every mapping result comes from the CUDA
+kernels behind include/unc_b200.h (uncalled_b200/libunc_b200.so).  There is no CPU fallback:
+constructing a MapPool without a usable CUDA device raises UncError.
+
+Differences a caller can observe (documented, not hidden):
+  * `MapPool(conf)` maps batches on the GPU instead of one read per CPU thread; `conf.threads`
+    is accepted and ignored by the mapper (reference src/map_pool.cpp:31).
+  * fast5 input needs an HDF5 reader.  The reference vendors libhdf5; this image has no
+    HDF5 binding, so `add_fast5()` works only when `h5py` is importable and otherwise raises
+    RuntimeError (like the reference does for an unreadable file, src/fast5_reader.cpp).  Reads
+    can always be queued as arrays with `add_read()`, which is what `Fast5Reader` hands to
+    `MapPool::update` after decoding (reference src/read_buffer.cpp:160-246).
+"""
+import enum
+import sys
+import time
+
+import numpy as np
+
+from . import _native as N
+from .mapper import BatchMapper, Index, make_descs
+
+
+class Conf:
+    """reference src/conf.hpp:296-340 -- the attributes `uncalled map` sets (uncalled/args.py:296-302).
+    They are real properties so that `Conf.<name>.__doc__` works as uncalled/args.py:223-260 expects."""
+
+    _FIELDS = {
+        # name: (default, doc)           defaults: src/mapper.cpp:29-52, read_buffer.cpp:26-32, fast5_reader.cpp:26-31
+        "threads": (1, "Number of threads (accepted; the GPU mapper does not use CPU mapping threads)"),
+        "bwa_prefix": ("", "BWA prefix to map to"),
+        "idx_preset": ("default", "Mapping mode preset line of the .uncl file"),
+        "model_path": ("", "k-mer model file (empty: built-in r9.4 5-mer template model)"),
+        "max_events": (30000, "Will give up on a read after this many events have been processed"),
+        "seed_len": (22, "Seed length in events"),
+        "max_paths": (10000, "Maximum number of paths to consider per event"),
+        "chunk_time": (1.0, "Length of chunks in seconds"),
+        "max_chunks": (1000000, "Will give up on a read after this many chunks have been processed"),
+        "sample_rate": (4000.0, "Raw samples per second"),
+        "bp_per_sec": (450.0, "Expected bases sequenced per second"),
+        "num_channels": (512, "Number of channels used in sequencing"),
+        "fast5_list": ("", "File containing a list of paths to fast5 files, one per line"),
+        "read_list": ("", "Only map reads listed in this file"),
+        "max_reads": (0, "Maximum number of reads to map"),
+        "max_buffer": (100, "Maximum number of reads to store in memory"),
+        "device": (0, "CUDA device of this process (one process per GPU)"),
+        "batch_reads": (4096, "Reads per GPU batch"),
+    }
+
+    def __init__(self):
+        self._v = {k: d for k, (d, _) in self._FIELDS.items()}
+
+
+def _conf_prop(name, doc):
+    def g(self):
+        return self._v[name]
+
+    def s(self, val):
+        self._v[name] = type(Conf._FIELDS[name][0])(val)
+    return property(g, s, doc=doc)
+
+
+for _n, (_d, _doc) in Conf._FIELDS.items():
+    setattr(Conf, _n, _conf_prop(_n, _doc))
+
+
+class Paf:
+    """reference src/read_buffer.hpp:40-128, src/read_buffer.cpp:34-155."""
+
+    class Tag(enum.IntEnum):
+        MAP_TIME = 0
+        WAIT_TIME = 1
+        QUEUE_TIME = 2
+        RECEIVE_TIME = 3
+        CHANNEL = 4
+        EJECT = 5
+        READ_START = 6
+        IN_SCAN = 7
+        TOP_RATIO = 8
+        MEAN_RATIO = 9
+        ENDED = 10
+        KEEP = 11
+        DELAY = 12
+        SEED_CLUSTER = 13
+        CONFIDENT_EVENT = 14
+
+    PAF_TAGS = ["mt", "wt", "qt", "rt", "ch", "ej", "st", "mx", "tr", "mr", "en", "kp", "dl", "sc", "ce"]
+
+    def __init__(self, rd_name="", channel=None, start_sample=None):
+        self.rd_name, self.rf_name = rd_name, ""
+        self._mapped = self._ended = False
+        self.rd_st = self.rd_en = self.rd_len = self.rf_st = self.rf_en = self.rf_len = 0
+        self.fwd, self.matches = False, 0
+        self.int_tags, self.float_tags, self.str_tags = [], [], []
+        if channel is not None:                         # Paf(rd_name, channel, start_sample), :66-82
+            self.set_int(Paf.Tag.CHANNEL, channel)
+            self.set_int(Paf.Tag.READ_START, start_sample or 0)
+
+    def is_mapped(self):
+        return self._mapped
+
+    def is_ended(self):
+        return self._ended
+
+    def set_read_len(self, n):
+        self.rd_len = int(n)
+
+    def set_mapped(self, rd_st, rd_en, rf_name, rf_st, rf_en, rf_len, fwd, matches):
+        self._mapped = True
+        self.rd_st, self.rd_en, self.rf_name = int(rd_st), int(rd_en), rf_name
+        self.rf_st, self.rf_en, self.rf_len = int(rf_st), int(rf_en), int(rf_len)
+        self.fwd, self.matches = bool(fwd), int(matches) & 0xFFFF
+
+    def set_int(self, t, v):
+        self.int_tags.append((int(t), int(v)))
+
+    def set_float(self, t, v):
+        self.float_tags.append((int(t), float(np.float32(v))))
+
+    def set_str(self, t, v):
+        self.str_tags.append((int(t), str(v)))
+
+    def fields(self):
+        """The 12 PAF columns as strings (src/read_buffer.cpp:92-126)."""
+        f = [self.rd_name, str(self.rd_len)]
+        if self._mapped:
+            f += [str(self.rd_st), str(self.rd_en), "+" if self.fwd else "-", self.rf_name, str(self.rf_len),
+                  str(self.rf_st), str(self.rf_en), str(self.matches), str(self.rf_en - self.rf_st + 1), "255"]
+        else:
+            f += ["*"] * 9 + ["255"]
+        return f
+
+    def line(self):
+        f = self.fields()
+        f += ["%s:i:%d" % (self.PAF_TAGS[t], v) for t, v in self.int_tags]
+        f += ["%s:f:%.6f" % (self.PAF_TAGS[t], v) for t, v in self.float_tags]      # std::fixed
+        f += ["%s:Z:%s" % (self.PAF_TAGS[t], v) for t, v in self.str_tags]
+        return "\t".join(f)
+
+    def print_paf(self, file=None):
+        (file or sys.stdout).write(self.line() + "\n")
+
+
+# export the enum values into class scope like pybind11's export_values() (read_buffer.hpp:104-112)
+for _t in Paf.Tag:
+    setattr(Paf, _t.name, _t)
+
+
+class _Read:
+    __slots__ = ("id", "channel", "number", "start", "signal", "dtype", "cal")
+
+    def __init__(self, rid, signal, channel, number, start, dtype, cal):
+        self.id, self.signal, self.channel, self.number, self.start = rid, signal, channel, number, start
+        self.dtype, self.cal = dtype, cal
+
+
+class MapPool:
+    """reference src/map_pool.hpp:33-53: MapPool(conf), add_fast5, update() -> [Paf], running(), stop()."""
+
+    def __init__(self, conf):
+        self.conf = conf
+        if not conf.bwa_prefix:
+            raise RuntimeError("Conf.bwa_prefix is not set")
+        self.index = Index(conf.bwa_prefix, preset=conf.idx_preset, device=conf.device,
+                           model_table=conf.model_path or None)
+        p = N.default_params()
+        p.max_events, p.max_paths, p.seed_len = conf.max_events, conf.max_paths, conf.seed_len
+        p.bp_per_sec, p.sample_rate = conf.bp_per_sec, conf.sample_rate
+        self.params = p
+        self._queue, self._mapper, self._cap = [], None, (0, 0)
+        self._n_added, self._stopped = 0, False
+        self._read_filter = None
+        if conf.read_list:
+            self._read_filter = set(l.strip() for l in open(conf.read_list) if l.strip())
+
+    # -- input ---------------------------------------------------------------------------
+    def _max_len(self):
+        # the fast5 constructor truncates the signal to max_chunks * chunk_len samples
+        # (reference src/read_buffer.cpp:229-234; chunk_len = chunk_time * sample_rate, read_buffer.hpp:135-137)
+        chunk_len = int(np.float32(self.conf.chunk_time) * np.float32(self.conf.sample_rate))
+        return int(self.conf.max_chunks) * chunk_len
+
+    def add_read(self, read_id, signal, channel=0, number=0, start_sample=0, calibration=None):
+        """Queue one read.  signal: float32 pA, or int16 DAC values with calibration=(range, offset, digitisation)
+        (calibrated on the device exactly as reference src/read_buffer.cpp:239-242)."""
+        if self._read_filter is not None and read_id not in self._read_filter:
+            return False
+        if self.conf.max_reads and self._n_added >= self.conf.max_reads:
+            return False
+        sig = np.asarray(signal)
+        if calibration is None:
+            sig, dtype, cal = np.ascontiguousarray(sig, np.float32), 0, (1.0, 0.0, 1.0)
+        else:
+            if sig.dtype != np.int16:
+                raise TypeError("calibration given: the signal must be int16 DAC values")
+            sig, dtype, cal = np.ascontiguousarray(sig), 1, tuple(float(np.float32(x)) for x in calibration)
+        sig = sig[:self._max_len()]
+        self._queue.append(_Read(read_id, sig, int(channel), int(number), int(start_sample), dtype, cal))
+        self._n_added += 1
+        return True
+
+    def add_fast5(self, fast5_name):
+        try:
+            import h5py
+        except ImportError:
+            raise RuntimeError("add_fast5('%s'): no HDF5 reader in this environment (h5py); queue decoded reads "
+                               "with MapPool.add_read()" % fast5_name)
+        with h5py.File(fast5_name, "r") as f:             # layouts: reference src/fast5_reader.cpp:134-210
+            def one(raw_grp, ch_grp):
+                a, c = raw_grp.attrs, ch_grp.attrs
+                rid = a["read_id"]
+                rid = rid.decode() if isinstance(rid, bytes) else str(rid)
+                # attributes pass through 6-significant-digit text in the reference (hdf5_tools.hpp:1124-1141)
+                cal = tuple(float(np.float32(float("%g" % float(c[k])))) for k in ("range", "offset", "digitisation"))
+                self.add_read(rid, raw_grp["Signal"][()].astype(np.int16), int(c["channel_number"]),
+                              int(a["read_number"]), int(a["start_time"]), calibration=cal)
+            if "Raw" in f:                                # single-read file
+                for name in f["Raw/Reads"]:
+                    one(f["Raw/Reads"][name], f["UniqueGlobalKey/channel_id"])
+            else:
+                for name in f:
+                    if name.startswith("read_"):
+                        one(f[name]["Raw"], f[name]["channel_id"])
+
+    # -- output --------------------------------------------------------------------------
+    def update(self):
+        """Maps up to conf.batch_reads queued reads on the GPU and returns their Paf records
+        (the reference returns whatever its threads finished since the last call, src/map_pool.cpp:45-69)."""
+        if self._stopped or not self._queue:
+            return []
+        out = []
+        for dtype in (0, 1):
+            batch = [r for r in self._queue[:self.conf.batch_reads] if r.dtype == dtype]
+            if not batch:
+                continue
+            # one calibration per i16 batch call would over-constrain callers: descriptors carry it per read
+            lens = [len(r.signal) for r in batch]
+            total = int(sum(lens))
+            if self._mapper is None or len(batch) > self._cap[0] or total > self._cap[1]:
+                self._cap = (max(len(batch), self._cap[0], 64), max(total, self._cap[1], 1 << 20))
+                if self._mapper is not None:
+                    self._mapper.close()
+                self._mapper = BatchMapper(self.index, params=self.params, max_reads=self._cap[0], max_samples=self._cap[1])
+            d = make_descs(lens, dtype=dtype)
+            for i, r in enumerate(batch):
+                d["cal_range"][i], d["cal_offset"][i], d["cal_digit"][i] = r.cal
+            flat = np.concatenate([r.signal for r in batch]) if total else np.zeros(1, np.float32 if dtype == 0 else np.int16)
+            t0 = time.time()
+            recs = self._mapper.map(flat, d)
+            ms = (time.time() - t0) * 1e3 / len(batch)
+            for r, rec in zip(batch, recs):
+                p = Paf(r.id, r.channel, r.start)
+                p.set_read_len(int(rec["rd_len"]))
+                if rec["mapped"]:
+                    rid = int(rec["rid"])
+                    name = self.index.seqs[rid][0] if 0 <= rid < len(self.index.seqs) else ""
+                    p.set_mapped(rec["rd_st"], rec["rd_en"], name, rec["rf_st"], rec["rf_en"], rec["rf_len"],
+                                 bool(rec["fwd"]), int(rec["matches"]))
+                p.set_float(Paf.Tag.MAP_TIME, ms)
+                out.append(p)
+        n = min(len(self._queue), self.conf.batch_reads)
+        del self._queue[:n]
+        return out
+
+    def running(self):
+        return not self._stopped and len(self._queue) > 0
+
+    def stop(self):
+        self._stopped = True
+        if self._mapper is not None:
+            self._mapper.close()
+            self._mapper = None

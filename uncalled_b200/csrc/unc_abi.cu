@@ -150,7 +150,7 @@ struct unc_pool {
     uint64_t max_samples = 0;
     uint32_t ev_stride = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [5]: end of k1_events
     // batch buffers
     void *d_samples = nullptr;
     DevReadDesc *d_reads = nullptr, *h_reads = nullptr;
@@ -339,7 +339,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     auto bail = [&](int code, const std::string &m) { unc_pool_free(P); return fail(code, m); };
 #define PT(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return bail(UNC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } while (0)
     PT(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 5; i++) PT(cudaEventCreate(&P->ev[i]));
+    for (int i = 0; i < 6; i++) PT(cudaEventCreate(&P->ev[i]));
     cudaDeviceProp prop;
     PT(cudaGetDeviceProperties(&prop, idx->device));
     P->smem = sizeof(K2Shared) + 16 + (size_t) ((prm->max_paths + 31) / 32) * 24;
@@ -347,6 +347,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     int per_sm = 0;
     PT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_map, K2_THREADS, P->smem));
     if (per_sm < 1) return bail(UNC_E_CUDA, "k2_map does not fit on an SM");
+    if (const char *e = getenv("UNC_K2_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // tuning knob
     uint32_t grid = (uint32_t) prop.multiProcessorCount * (uint32_t) per_sm;
     if (grid > max_reads) grid = max_reads;
     {
@@ -426,7 +427,7 @@ void unc_pool_free(unc_pool *P) {
     cudaFree(P->d_events); cudaFree(P->d_normed);
     cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue); cudaFree(P->d_k1_flags);
     cudaFree(P->d_out); cudaFreeHost(P->h_out); cudaFree(P->d_dbg);
-    for (int i = 0; i < 5; i++) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
+    for (int i = 0; i < 6; i++) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
     if (P->stream) cudaStreamDestroy(P->stream);
     delete P;
 }
@@ -492,6 +493,7 @@ static DevBatch make_batch(unc_pool *P, const void *d_samples, uint64_t samples_
 static void launch_k1(unc_pool *P, const DevBatch &B, uint32_t n, cudaStream_t s) {
     uint32_t g = std::min<uint32_t>(P->k1_grid, (n + K1_WARPS - 1) / K1_WARPS);
     k1_events<<<g, K1_WARPS * 32, (size_t) K1_WARPS * sizeof(K1WarpSmem), s>>>(B, P->dp);
+    cudaEventRecord(P->ev[5], s);
     k1_fallback<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
     k1_norm<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
 }
@@ -533,6 +535,7 @@ static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     unc_timing &t = P->last;
     cudaEventElapsedTime(&t.h2d_ms, P->ev[0], P->ev[1]);
     cudaEventElapsedTime(&t.k1_ms, P->ev[1], P->ev[2]);
+    cudaEventElapsedTime(&t.k1_events_ms, P->ev[1], P->ev[5]);
     cudaEventElapsedTime(&t.k2_ms, P->ev[2], P->ev[3]);
     cudaEventElapsedTime(&t.d2h_ms, P->ev[3], P->ev[4]);
     cudaEventElapsedTime(&t.total_ms, P->ev[0], P->ev[4]);
@@ -587,6 +590,7 @@ int unc_events_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     memset(&t, 0, sizeof(t));
     cudaEventElapsedTime(&t.h2d_ms, P->ev[0], P->ev[1]);
     cudaEventElapsedTime(&t.k1_ms, P->ev[1], P->ev[2]);
+    cudaEventElapsedTime(&t.k1_events_ms, P->ev[1], P->ev[5]);
     t.total_ms = t.h2d_ms + t.k1_ms;
     t.kernel_launches = 3;
     t.h2d_bytes = span + (uint64_t) n * sizeof(DevReadDesc);

@@ -1089,16 +1089,23 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             if (lane == 0) sh->bc[3] = rows;
         }
         {
-            // compact the chunk-local keys into emission order: destination-major so that each
-            // iteration is an independent gather (the loads of several iterations overlap)
-            const u32 d_lo = ww * seg_len < nc ? ww * seg_len : nc, d_hi = (ww + 1) * seg_len < nc ? (ww + 1) * seg_len : nc;
-#pragma unroll 4
-            for (u32 di = d_lo + (u32) lane; di < d_hi; di += 32) {
-                u32 lo = 0, hi = nch_prev;              // largest chunk c with bcnt[c] <= di
-                while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (sh->bcnt[mid] <= di) lo = mid; else hi = mid; }
-                uint4 key = cks[(size_t) lo * K2_CH_SLOTS + (di - sh->bcnt[lo])];
-                ckA[di] = key;
-                s_atomic_add(&sh->hist_next[(key.x & (K2_RB - 1u)) * K2_MAXSEG + ww], 1u);
+            // compact the chunk-local keys into emission order: each warp copies the chunks it
+            // extended (their keys are still in its L1) to [bcnt[c], bcnt[c+1]) -- coalesced on both
+            // sides -- and counts the first radix digit for the destination's sort segment
+            for (u32 c = ww; c < nch_prev; c += nwk) {
+                const u32 base = sh->bcnt[c];
+                if (base >= nc) break;                              // later chunks lie beyond the max_paths cut
+                const u32 end = c + 1 < nch_prev ? sh->bcnt[c + 1] : nc_total;
+                u32 seg = base / seg_len, bound = (seg + 1u) * seg_len;
+                for (u32 i = (u32) lane; base + i < end; i += 32) {
+                    const u32 di = base + i;
+                    if (di < nc) {
+                        uint4 key = cks[(size_t) c * K2_CH_SLOTS + i];
+                        ckA[di] = key;
+                        while (di >= bound) { seg++; bound += seg_len; }
+                        s_atomic_add(&sh->hist_next[(key.x & (K2_RB - 1u)) * K2_MAXSEG + seg], 1u);
+                    }
+                }
             }
         }
         c_sync_sub(1, (int) nwt);

@@ -30,7 +30,7 @@
 #include "unc_device.cuh"
 
 #ifndef K1_CH
-#define K1_CH 36u              /* positions per lane per tile: a multiple of 12 */
+#define K1_CH 36u              /* positions per lane per tile: a multiple of 3 (even) */
 #endif
 #ifndef K1_WARM
 #define K1_WARM 12u            /* speculative warm-up length (<= K1_CH) */
@@ -75,33 +75,48 @@ UNC_DEV K1Fsm k1_fsm_bcast(const K1Fsm &a, int src) {
 }
 
 // One step of both detectors at position m (= buf_mid) with t-statistics t1, t2: reference
-// src/event_detector.cpp:221-279 (peak_detect, short then long) as called from add_sample :94-98.
+// src/event_detector.cpp:221-279 (peak_detect, short then long) as called from add_sample :94-98,
+// written with selects (the lanes of a warp walk different chunks, so branches would diverge).
+// The short detector's `masked_to (0) >= buf_mid` skip at buf_mid == 0 is reproduced by feeding
+// t1 = 0 there (k1_fix_head): its state is then {pos -1, value 0} and a zero input changes nothing.
 // Returns true when either detector fires.
 UNC_DEV bool k1_fsm_step(K1Fsm &f, float t1, float t2, u32 m, float thr1, float thr2, float h) {
-    bool p1 = false, p2 = false;
-    if (m != 0u) {                                   // short.masked_to (0) >= buf_mid only at buf_mid == 0
-        if (f.s_pos == -1) {
-            if (t1 < f.s_val) f.s_val = t1;
-            else if (f_sub(t1, f.s_val) > h) { f.s_val = t1; f.s_pos = (i32) m; }
-        } else {
-            if (t1 > f.s_val) { f.s_val = t1; f.s_pos = (i32) m; }
-            if (f.s_val > thr1) {                    // the short detector masks and resets the long one
-                f.l_masked = (u32) f.s_pos + 3u; f.l_pos = -1; f.l_val = 3.402823466e+38f; f.l_valid = 0;
-            }
-            if (f_sub(f.s_val, t1) > h && f.s_val > thr1) f.s_valid = 1;
-            if (f.s_valid && (m - (u32) f.s_pos) > 1u) { f.s_pos = -1; f.s_val = t1; f.s_valid = 0; p1 = true; }
-        }
-    }
-    if (!(f.l_masked >= m)) {
-        if (f.l_pos == -1) {
-            if (t2 < f.l_val) f.l_val = t2;
-            else if (f_sub(t2, f.l_val) > h) { f.l_val = t2; f.l_pos = (i32) m; }
-        } else {
-            if (t2 > f.l_val) { f.l_val = t2; f.l_pos = (i32) m; }
-            if (f_sub(f.l_val, t2) > h && f.l_val > thr2) f.l_valid = 1;
-            if (f.l_valid && (m - (u32) f.l_pos) > 3u) { f.l_pos = -1; f.l_val = t2; f.l_valid = 0; p2 = true; }
-        }
-    }
+    // ---- short detector (window 3: fires when buf_mid - peak_pos > 3/2)
+    const bool inA = f.s_pos < 0;
+    const bool ltA = t1 < f.s_val;
+    const bool riseA = !ltA && f_sub(t1, f.s_val) > h;
+    const bool gtB = t1 > f.s_val;
+    const float valB = gtB ? t1 : f.s_val;
+    const i32 posB = gtB ? (i32) m : f.s_pos;
+    const bool overB = valB > thr1;
+    const bool resetL = !inA && overB;                            // the short detector masks and resets the long one
+    const bool validB = f.s_valid || (f_sub(valB, t1) > h && overB);
+    const bool p1 = !inA && validB && (m - (u32) posB) > 1u;
+    const float nsv = inA ? ((ltA || riseA) ? t1 : f.s_val) : (p1 ? t1 : valB);
+    const i32 nsp = inA ? (riseA ? (i32) m : -1) : (p1 ? -1 : posB);
+    f.s_valid = (!inA && !p1 && validB) ? 1u : 0u;
+    f.s_val = nsv; f.s_pos = nsp;
+    // ---- long detector (window 6: fires when buf_mid - peak_pos > 6/2), after the short one's reset
+    const u32 lm = resetL ? (u32) posB + 3u : f.l_masked;
+    const i32 lp = resetL ? -1 : f.l_pos;
+    const float lv = resetL ? 3.402823466e+38f : f.l_val;
+    const bool lvalid = resetL ? false : (f.l_valid != 0u);
+    const bool act = lm < m;                                      // !(masked_to >= buf_mid)
+    const bool inAL = lp < 0;
+    const bool ltAL = t2 < lv;
+    const bool riseAL = !ltAL && f_sub(t2, lv) > h;
+    const bool gtBL = t2 > lv;
+    const float valBL = gtBL ? t2 : lv;
+    const i32 posBL = gtBL ? (i32) m : lp;
+    const bool validBL = lvalid || (f_sub(valBL, t2) > h && valBL > thr2);
+    const bool p2 = act && !inAL && validBL && (m - (u32) posBL) > 3u;
+    const float nlv = inAL ? ((ltAL || riseAL) ? t2 : lv) : (p2 ? t2 : valBL);
+    const i32 nlp = inAL ? (riseAL ? (i32) m : -1) : (p2 ? -1 : posBL);
+    const bool nlvalid = !inAL && !p2 && validBL;
+    f.l_masked = lm;
+    f.l_val = act ? nlv : lv;
+    f.l_pos = act ? nlp : lp;
+    f.l_valid = (act ? nlvalid : lvalid) ? 1u : 0u;
     return p1 || p2;
 }
 
@@ -113,9 +128,12 @@ template <u32 W> UNC_DEV double k1_ddiv_w(double a) {
     double e = d_fma(-(double) W, q, a);
     return d_fma(e, r, q);
 }
-template <u32 W> UNC_DEV float k1_fdiv_w(float a) {
+// GUARD: operands below 2^-100 take the IEEE division (subnormal quotients can tie, where the
+// sequence is not exact).  The window sums never need it: the fast path requires every non-zero
+// sample to be >= 2^-38 (k1_exact_ok), so a non-zero float sum or sum of squares is >= 2^-99.
+template <u32 W, bool GUARD> UNC_DEV float k1_fdiv_w(float a) {
     const float r = W == 3u ? 0.333333343f : 0.166666672f;                  // RN(1/W)
-    if (fabsf(a) < 7.8886090522101181e-31f) return f_div(a, (float) W);     // < 2^-100: subnormal quotients can tie
+    if (GUARD && fabsf(a) < 7.8886090522101181e-31f) return f_div(a, (float) W);
     float q = f_mul(a, r);
     float e = f_fma(-(float) W, q, a);
     return f_fma(e, r, q);
@@ -126,13 +144,13 @@ template <u32 W> UNC_DEV float k1_fdiv_w(float a) {
 template <u32 W> UNC_DEV float k1_tstat(double sum1, double sumsq1, double sum2d, double sumsq2d) {
     float sum2 = (float) sum2d, sumsq2 = (float) sumsq2d;
     float mean1 = (float) k1_ddiv_w<W>(sum1);
-    float mean2 = k1_fdiv_w<W>(sum2);
+    float mean2 = k1_fdiv_w<W, false>(sum2);
     float m1sq = f_mul(mean1, mean1), m2sq = f_mul(mean2, mean2);
-    float q2 = k1_fdiv_w<W>(sumsq2);
+    float q2 = k1_fdiv_w<W, false>(sumsq2);
     double cv = d_sub(d_add(d_sub(k1_ddiv_w<W>(sumsq1), (double) m1sq), (double) q2), (double) m2sq);
     float var = fmaxf((float) cv, 1.17549435e-38f);
     float delta = f_sub(mean2, mean1);
-    return f_div(fabsf(delta), f_sqrt(k1_fdiv_w<W>(var)));
+    return f_div(fabsf(delta), f_sqrt(k1_fdiv_w<W, true>(var)));
 }
 
 struct K1Read {                    // warp-uniform description of the read being processed
@@ -141,15 +159,16 @@ struct K1Read {                    // warp-uniform description of the read being
     u32 n;                         // samples
     u32 n_pos;                     // FSM positions: m in [0, n_pos), n_pos = n >= 6 ? n - 5 : 0
     float cal_range, cal_offset, cal_digit, cal_inv;   // cal_inv != 0: digitisation is a power of two
+    bool i16;                      // raw DAC input (calibrated on the fly) instead of f32 pA
 };
 
 struct K1Tile {
     i32 base_idx;                  // sample index of raw element 0
 };
 
-template <bool I16> UNC_DEV float k1_sample(const K1WarpSmem *sm, const K1Read &R, const K1Tile &T, i32 j) {
+UNC_DEV float k1_sample(const K1WarpSmem *sm, const K1Read &R, const K1Tile &T, i32 j) {
     i32 e = j - T.base_idx;
-    if (!I16) return sm->raw[e];
+    if (!R.i16) return sm->raw[e];
     u16 raw = ((const u16 *) sm->raw)[e];
     float v = f_mul(R.cal_range, f_add((float) raw, R.cal_offset));     // reference src/read_buffer.cpp:239-242
     return R.cal_inv != 0.0f ? f_mul(v, R.cal_inv) : f_div(v, R.cal_digit);
@@ -167,53 +186,60 @@ UNC_DEV void k1_exact_add(K1Exact &x, float s, float ss) {
 // true when every partial sum of non-negative values with total `tot` and smallest non-zero bit
 // pattern mn+1 is exactly representable in double: all values are multiples of 2^(emin-150) and
 // every sum is < 2 * tot < 2^(etot-125)
-UNC_DEV bool k1_exact_ok(float tot, u32 mn) {
+UNC_DEV bool k1_exact_ok(float tot, u32 mn, i32 emin_floor) {
     if (mn == 0xFFFFFFFFu) return true;                   // all zero
     i32 etot = (i32) (f2u(tot) >> 23), emin = (i32) ((mn + 1u) >> 23);
-    if (etot >= 254 || emin == 0) return false;           // inf/nan (or a negative "sum"), or a subnormal value
+    if (etot >= 254 || emin < emin_floor) return false;   // inf/nan (or a negative "sum"), or a value too small
     return etot + 2 <= 53 + emin - 23;
 }
 
-// ---- T pass: lane's chunk [a, a + K1_CH)
-template <bool I16>
+// ---- T pass: lane's chunk [a, a + K1_CH).  D3[j] = s[j]+s[j+1]+s[j+2] (and E3 for the float squares)
+// are kept in three 3-deep register windows, one per residue class of the position: at position m
+// the class window holds D3[m-6], D3[m-3], D3[m]; the step adds D3[m+3] and shifts.  Window sums
+// (reference src/event_detector.cpp:195-205, differences of the double prefix sums -- exact here):
+//   w=3: left D3[m-3], right D3[m];   w=6: left D3[m-6]+D3[m-3], right D3[m]+D3[m+3].
 UNC_DEV void k1_tpass(K1WarpSmem *sm, const K1Read &R, const K1Tile &T, i32 a, int lane, double *chunk_sum, K1Exact &X) {
-    double D[12], E[12];          // 3-sample sums of the samples / of their float squares: slot (j - (a-6)) % 12
-    double xd[11], qd[11];
+    double D[3][3], E[3][3];
+    double p2, p1, r2, r1;
+    {
+        double xd[11], qd[11];
 #pragma unroll
-    for (int t = 0; t < 11; t++) {
-        i32 j = a - 6 + t;
-        float s = j >= 0 ? k1_sample<I16>(sm, R, T, j) : 0.0f;
-        float ss = f_mul(s, s);
-        if (j >= 0 && (u32) j < R.n) k1_exact_add(X, s, ss);
-        xd[t] = (double) s; qd[t] = (double) ss;
-    }
+        for (int t = 0; t < 11; t++) {
+            i32 j = a - 6 + t;
+            float s = j >= 0 ? k1_sample(sm, R, T, j) : 0.0f;
+            float ss = f_mul(s, s);
+            if (j >= 0 && (u32) j < R.n) k1_exact_add(X, s, ss);
+            xd[t] = (double) s; qd[t] = (double) ss;
+        }
 #pragma unroll
-    for (int t = 0; t < 9; t++) {
-        D[t] = d_add(d_add(xd[t], xd[t + 1]), xd[t + 2]);
-        E[t] = d_add(d_add(qd[t], qd[t + 1]), qd[t + 2]);
+        for (int t = 0; t < 9; t++) {
+            D[t % 3][t / 3] = d_add(d_add(xd[t], xd[t + 1]), xd[t + 2]);
+            E[t % 3][t / 3] = d_add(d_add(qd[t], qd[t + 1]), qd[t + 2]);
+        }
+        p2 = xd[9]; p1 = xd[10]; r2 = qd[9]; r1 = qd[10];
     }
-    D[9] = D[10] = D[11] = 0.0; E[9] = E[10] = E[11] = 0.0;
-    double p2 = xd[9], p1 = xd[10], r2 = qd[9], r1 = qd[10];
     double acc = 0.0;
     float *row1 = sm->t1 + (u32) lane * K1_TS, *row2 = sm->t2 + (u32) lane * K1_TS;
-    for (u32 i0 = 0; i0 < K1_CH; i0 += 12) {
+#pragma unroll 1
+    for (u32 i0 = 0; i0 < K1_CH; i0 += 3) {
 #pragma unroll
-        for (u32 u = 0; u < 12; u++) {
-            const i32 m = a + (i32) (i0 + u);
+        for (u32 c = 0; c < 3; c++) {
+            const i32 m = a + (i32) (i0 + c);
             const i32 j = m + 5;
-            float s = k1_sample<I16>(sm, R, T, j);
+            float s = k1_sample(sm, R, T, j);
             float ss = f_mul(s, s);
             if ((u32) j < R.n) k1_exact_add(X, s, ss);
             double sd = (double) s, sq = (double) ss;
-            D[(u + 9) % 12] = d_add(d_add(p2, p1), sd);     // samples m+3, m+4, m+5
-            E[(u + 9) % 12] = d_add(d_add(r2, r1), sq);
+            const double dn = d_add(d_add(p2, p1), sd);      // D3[m+3]: samples m+3, m+4, m+5
+            const double en = d_add(d_add(r2, r1), sq);
             p2 = p1; p1 = sd; r2 = r1; r1 = sq;
-            float v1 = k1_tstat<3>(D[(u + 3) % 12], E[(u + 3) % 12], D[(u + 6) % 12], E[(u + 6) % 12]);
-            float v2 = k1_tstat<6>(d_add(D[u], D[(u + 3) % 12]), d_add(E[u], E[(u + 3) % 12]),
-                                   d_add(D[(u + 6) % 12], D[(u + 9) % 12]), d_add(E[(u + 6) % 12], E[(u + 9) % 12]));
-            if (u % 3 == 0) acc = d_add(acc, D[(u + 6) % 12]);   // samples m, m+1, m+2
-            row1[i0 + u] = v1;
-            row2[i0 + u] = v2;
+            float v1 = k1_tstat<3>(D[c][1], E[c][1], D[c][2], E[c][2]);
+            float v2 = k1_tstat<6>(d_add(D[c][0], D[c][1]), d_add(E[c][0], E[c][1]), d_add(D[c][2], dn), d_add(E[c][2], en));
+            if (c == 0) acc = d_add(acc, D[c][2]);           // samples m, m+1, m+2
+            D[c][0] = D[c][1]; D[c][1] = D[c][2]; D[c][2] = dn;
+            E[c][0] = E[c][1]; E[c][1] = E[c][2]; E[c][2] = en;
+            row1[i0 + c] = v1;
+            row2[i0 + c] = v2;
         }
     }
     *chunk_sum = acc;
@@ -222,12 +248,11 @@ UNC_DEV void k1_tpass(K1WarpSmem *sm, const K1Read &R, const K1Tile &T, i32 a, i
 // t-statistics of the first positions, where the reference's ring indices wrap (u32 buf_mid - w
 // for buf_mid < w reads the slot written last, src/event_detector.cpp:195-197) or the window is
 // not yet full (t <= 2w -> 0, :185-187).  Tile 0, lane 0 only.
-template <bool I16>
 UNC_DEV void k1_fix_head(K1WarpSmem *sm, const K1Read &R, const K1Tile &T) {
     double P[10], Q[10];           // prefix sums P[j] = sum of samples < j, j = 0..9
     P[0] = 0.0; Q[0] = 0.0;
     for (int j = 0; j < 9; j++) {
-        float s = (u32) j < R.n ? k1_sample<I16>(sm, R, T, j) : 0.0f;
+        float s = (u32) j < R.n ? k1_sample(sm, R, T, j) : 0.0f;
         P[j + 1] = d_add(P[j], (double) s);
         Q[j + 1] = d_add(Q[j], (double) f_mul(s, s));
     }
@@ -236,6 +261,7 @@ UNC_DEV void k1_fix_head(K1WarpSmem *sm, const K1Read &R, const K1Tile &T) {
         sm->t1[m] = k1_tstat<3>(d_sub(P[m], P[m + 6]), d_sub(Q[m], Q[m + 6]), d_sub(P[m + 3], P[m]), d_sub(Q[m + 3], Q[m]));
     }
     for (u32 m = 0; m < 6 && m < R.n_pos; m++) sm->t2[m] = 0.0f;
+    if (R.n_pos) sm->t1[0] = 0.0f;     // the short detector skips buf_mid == 0 (see k1_fsm_step)
 }
 
 // ---- FSM over positions [from, to) of the tile, reading the T rows; fire bits relative to `a`
@@ -263,20 +289,20 @@ struct K1Carry {                   // warp-uniform state carried across the tile
 };
 
 // One read by one warp.  Returns false when the read must be redone by the serial routine.
-template <bool I16>
 UNC_DEV bool k1_warp_read(const DevBatch &B, const DevParams &p, u32 r, K1WarpSmem *sm, u32 *bar_phase) {
     u32 *stats = B.k1_stats;
     const int lane = w_lane();
     const DevReadDesc rd = B.reads[r];
-    const u32 esz = I16 ? 2u : 4u;
     K1Read R;
+    R.i16 = rd.dtype != 0u;
+    const u32 esz = R.i16 ? 2u : 4u;
     R.src = (const unsigned char *) B.samples + (size_t) rd.offset * esz;
     R.buf_end = (const unsigned char *) B.samples + B.samples_bytes;
     R.n = rd.n_samples;
     R.n_pos = R.n >= 6u ? R.n - 5u : 0u;
     R.cal_range = rd.cal_range; R.cal_offset = rd.cal_offset; R.cal_digit = rd.cal_digit;
     R.cal_inv = 0.0f;
-    if (I16) {
+    if (R.i16) {
         u32 db = f2u(rd.cal_digit);
         // power of two in [2^-60, 2^60]: multiplying by the exact reciprocal equals the division
         if ((db & 0x807FFFFFu) == 0u && (db >> 23) > 67u && (db >> 23) < 187u) R.cal_inv = u2f((254u << 23) - db);
@@ -319,9 +345,9 @@ UNC_DEV bool k1_warp_read(const DevBatch &B, const DevParams &p, u32 r, K1WarpSm
         const i32 a = (i32) (lo + (u32) lane * K1_CH);
         const u32 steps = (u32) a >= R.n_pos ? 0u : (R.n_pos - (u32) a < K1_CH ? R.n_pos - (u32) a : K1_CH);
         double csum = 0.0;
-        if (steps) k1_tpass<I16>(sm, R, T, a, lane, &csum, C.X);
+        if (steps) k1_tpass(sm, R, T, a, lane, &csum, C.X);
         w_sync();
-        if (t == 0 && lane == 0) k1_fix_head<I16>(sm, R, T);
+        if (t == 0 && lane == 0) k1_fix_head(sm, R, T);
         w_sync();
         // exclusive scan of the chunk sums -> prefix sum at the lane's chunk start
         double incl = csum;
@@ -362,8 +388,8 @@ UNC_DEV bool k1_warp_read(const DevBatch &B, const DevParams &p, u32 r, K1WarpSm
         if (fires) {
             // P[a-2], P[a-1], P[a]: exact subtractions of the two samples before the chunk
             double q0 = lane_base, q1 = lane_base, q2 = lane_base;
-            if (a >= 1) { q1 = d_sub(q0, (double) k1_sample<I16>(sm, R, T, a - 1)); q2 = q1; }
-            if (a >= 2) q2 = d_sub(q1, (double) k1_sample<I16>(sm, R, T, a - 2));
+            if (a >= 1) { q1 = d_sub(q0, (double) k1_sample(sm, R, T, a - 1)); q2 = q1; }
+            if (a >= 2) q2 = d_sub(q1, (double) k1_sample(sm, R, T, a - 2));
             for (u32 i = 0; i < steps; i++) {
                 if ((fires >> i) & 1ull) {                   // the event ends at buf_mid - w1 + 1 = m - 2 (:105)
                     u64 bits = d2u(q2);
@@ -372,7 +398,7 @@ UNC_DEV bool k1_warp_read(const DevBatch &B, const DevParams &p, u32 r, K1WarpSm
                     cnt++;
                 }
                 q2 = q1; q1 = q0;
-                q0 = d_add(q0, (double) k1_sample<I16>(sm, R, T, a + (i32) i));
+                q0 = d_add(q0, (double) k1_sample(sm, R, T, a + (i32) i));
             }
         }
         w_sync();
@@ -426,7 +452,7 @@ UNC_DEV bool k1_warp_read(const DevBatch &B, const DevParams &p, u32 r, K1WarpSm
         float tot = C.X.sum, tot2 = C.X.sum2;
         for (int d = 16; d > 0; d >>= 1) { tot = f_add(tot, w_shflf(tot, lane ^ d)); tot2 = f_add(tot2, w_shflf(tot2, lane ^ d)); }
         u32 mn = ~w_max(~C.X.mn), mn2 = ~w_max(~C.X.mn2);
-        ok = ok && k1_exact_ok(tot, mn) && k1_exact_ok(tot2, mn2);
+        ok = ok && k1_exact_ok(tot, mn, 127 - 38) && k1_exact_ok(tot2, mn2, 127 - 76);
     }
     if (lane == 0) {
         B.n_events[r] = C.ne;
@@ -475,7 +501,6 @@ UNC_DEV void unc_k1_warp_main(const DevBatch &B, const DevParams &p, K1WarpSmem 
         if (lane == 0) r = d_atomic_add(B.k1_queue, 1u);
         r = w_shfl(r, 0);
         if (r >= B.n_reads) break;
-        if (B.reads[r].dtype == 0) k1_warp_read<false>(B, p, r, sm, &phase);
-        else k1_warp_read<true>(B, p, r, sm, &phase);
+        k1_warp_read(B, p, r, sm, &phase);
     }
 }

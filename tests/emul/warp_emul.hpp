@@ -193,6 +193,9 @@ static inline void t_bulk_load(void *dst, const void *src, uint32_t bytes, uint6
     memcpy(dst, src, bytes); (*bar)++;
 }
 static inline void t_bar_wait(uint64_t *bar, uint32_t parity) { (void) bar; (void) parity; }
+static inline void a_copy16(void *dst, const void *src) { memcpy(dst, src, 16); }
+static inline void a_commit() {}
+static inline void a_wait_all() {}
 
 static void emu_trampoline() {
     WarpEmu *w = g_warp;

@@ -215,6 +215,28 @@ def test_map_synthetic_4m7_matches_oracle(U):
     assert max(r.max_paths_seen for r in want) == 10000
 
 
+def test_map_long_reads_on_20mb_index(U):
+    """config-4-like at reduced scale: a 20 Mb genome (40 M FM rows: 26-bit keys -> 4 radix passes,
+    160 MB expanded SA) and 30 000-sample reads (~5 800 events, 26 K1 tiles) incl. never-mapping
+    reads that sit at the max_paths cap for thousands of events."""
+    import orclib
+    import synth
+    import synthdata
+    prefix, g = synthdata.get_index("g20m")
+    n, L = 12, 30000
+    sig, truth = synth.reads(g, n, L, seed=41, frac_random=0.25)
+    idx = U.Index(prefix, device=0)
+    bm = U.BatchMapper(idx, max_reads=n, max_samples=n * L)
+    out = bm.map(sig.ravel(), U.make_descs([L] * n))
+    O = orclib.Oracle(prefix)
+    want = O.map_batch(sig.ravel(), np.arange(n, dtype=np.uint64) * L, np.full(n, L, np.uint32), 8)
+    for i in range(n):
+        assert orclib.paf_tuple(want[i]) == U.paf_key(out[i]) and out[i]["status"] == 0, i
+        assert (want[i].n_children, want[i].n_sources, want[i].n_seeds) == \
+               (int(out[i]["n_children"]), int(out[i]["n_sources"]), int(out[i]["n_seeds"])), i
+    assert any(w.mapped == 0 and w.events_used > 5000 for w in want) and sum(w.mapped for w in want) >= 6
+
+
 def test_map_ragged_and_tiny_reads(U):
     """ragged batch: empty-event reads, very short reads, long reads in one call."""
     import orclib

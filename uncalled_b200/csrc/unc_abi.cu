@@ -367,6 +367,10 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     P->cks_stride = nchmax * 160;     // uint4
     P->elist_stride = nchmax * 32;    // uint4
     P->order_stride = 2 * maxp;       // u32
+    if (const char *e = getenv("UNC_K2_SLOT_PAD")) {   // experiment knob: spread the slots over a larger address span
+        size_t f = (size_t) atoi(e);
+        if (f >= 2 && f <= 8) { P->paths_stride *= f; P->hist_stride *= f; P->ckey_stride *= f; P->cks_stride *= f; P->elist_stride *= f; P->order_stride *= f; }
+    }
     uint64_t longest = max_samples < 0xFFFFFFFFull ? max_samples : 0xFFFFFFFFull;
     // seed clusters: at most a few per event in practice; blocks are >= half full after splits
     uint64_t ev_cap = std::min<uint64_t>(prm->max_events, longest / 3 + 16);

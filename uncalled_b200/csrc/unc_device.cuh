@@ -176,11 +176,13 @@ UNC_DEV u32 unc_occ(const DevIndex &ix, u32 k, u32 c, u32 *n_blocks) {
 // (k, l] are counted first: only bases that occur there have a non-empty range (for a
 // unique path that is exactly one base), and only for those the prefix Occ(k, c) is needed:
 //   ns = L2[c] + Occ(k,c) + 1,  ne = L2[c] + Occ(l,c) = ns + count_c(k,l] - 1.
-UNC_DEV u32 unc_neighbors(const DevIndex &ix, u32 start, u32 end, u32 want, u32 ns[4], u32 ne[4], u32 *n_blocks) {
+// `pre` (optional): the Occ block of row start-1, already fetched (staged by cp.async in the extension loop)
+UNC_DEV u32 unc_neighbors(const DevIndex &ix, u32 start, u32 end, u32 want, u32 ns[4], u32 ne[4], u32 *n_blocks,
+                          const OccBlock *pre = nullptr) {
     u32 k = start - 1, l = end;
     u32 kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
     bool l_is_end = (l == ix.seq_len);
-    OccBlock bk = unc_load_block(ix, kk);
+    OccBlock bk = pre ? *pre : unc_load_block(ix, kk);
     (*n_blocks)++;
     u32 valid = 0;
     if (!l_is_end && (ll >> 5) == (kk >> 5)) {
@@ -718,6 +720,9 @@ struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
     K2Tables tb;
     float probs[UNC_NKMER];
     u32 flags[32];         // sources_added_ bits (reference src/mapper.cpp:88), kmer k -> word k>>5
+#ifdef K2_OCC_STAGE
+    uint4 occ_stage[K2_MAXSEG * 32 * 5];   // per worker warp: 32 lanes x (64-byte Occ block + 16 B pad: conflict-free LDS.128)
+#endif
     u32 hist_cur[K2_RB * K2_MAXSEG];    // [digit][segment]
     u32 hist_next[K2_RB * K2_MAXSEG];
     // per-chunk arrays carved from dynamic shared memory (ceil(max_paths/32) entries each)
@@ -928,6 +933,54 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         //      parents writes its children, in emission order, to records/keys [c*160, c*160+count)
         const u32 nch_prev = (prev_size + 31u) >> 5;
         {
+#ifdef K2_OCC_STAGE
+            // three-stage software pipeline per warp: (order entry, record head) two chunks ahead in
+            // registers; the Occ block of row start-1 one chunk ahead by cp.async into shared memory
+            // (no registers held while it is in flight); the current chunk is consumed.
+            uint4 *stage = sh->occ_stage + ((size_t) ww * 32 + (u32) lane) * 5;
+            u32 oi_a = UNC_INVALID, oi_b = UNC_INVALID;
+            uint4 q0_a = make_uint4(0, 0, 0, 0), q0_b = make_uint4(0, 0, 0, 0);
+            if (ww < nch_prev) {
+                u32 pi = ww * 32 + (u32) lane;
+                if (pi < prev_size) oi_a = oprev[pi];
+                if (!(oi_a & UNC_INVALID)) q0_a = prev[(size_t) oi_a * 2];
+            }
+            if (ww + nwk < nch_prev) {
+                u32 pi = (ww + nwk) * 32 + (u32) lane;
+                if (pi < prev_size) oi_b = oprev[pi];
+                if (!(oi_b & UNC_INVALID)) q0_b = prev[(size_t) oi_b * 2];
+            }
+            if (!(oi_a & UNC_INVALID)) {
+                u32 k0 = q0_a.x - 1u, kk0 = k0 - (k0 >= ix.primary);
+                const uint4 *bp = ix.bwt + ((size_t) (kk0 >> 7) << 2);
+                a_copy16(stage, bp); a_copy16(stage + 1, bp + 1); a_copy16(stage + 2, bp + 2); a_copy16(stage + 3, bp + 3);
+            }
+            a_commit();
+            for (u32 c = ww; c < nch_prev; c += nwk) {
+                const u32 oi = oi_a;
+                const uint4 q0 = q0_a;
+                const bool valid = !(oi & UNC_INVALID);
+                uint4 q1 = make_uint4(0, 0, 0, 0);
+                if (valid) q1 = prev[(size_t) oi * 2 + 1];
+                a_wait_all();
+                OccBlock pre;
+                pre.b0 = stage[0]; pre.b1 = stage[1]; pre.b2 = stage[2]; pre.b3 = stage[3];
+                // rotate the pipeline: chunk c+nwk becomes current-next (its Occ block is requested
+                // now), chunk c+2*nwk's order entry and record head are requested
+                oi_a = oi_b; q0_a = q0_b;
+                oi_b = UNC_INVALID;
+                if (c + 2 * nwk < nch_prev) {
+                    u32 pi = (c + 2 * nwk) * 32 + (u32) lane;
+                    if (pi < prev_size) oi_b = oprev[pi];
+                    if (!(oi_b & UNC_INVALID)) q0_b = prev[(size_t) oi_b * 2];
+                }
+                if (!(oi_a & UNC_INVALID)) {
+                    u32 k0 = q0_a.x - 1u, kk0 = k0 - (k0 >= ix.primary);
+                    const uint4 *bp = ix.bwt + ((size_t) (kk0 >> 7) << 2);
+                    a_copy16(stage, bp); a_copy16(stage + 1, bp + 1); a_copy16(stage + 2, bp + 2); a_copy16(stage + 3, bp + 3);
+                }
+                a_commit();
+#else
             // software prefetch of the next chunk's order entry + record head
             u32 oi_n = UNC_INVALID; uint4 q0_n = make_uint4(0, 0, 0, 0), q1_n = make_uint4(0, 0, 0, 0);
             if (ww < nch_prev) {
@@ -944,6 +997,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                     oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
                     if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = pr[1]; }
                 }
+#endif
                 u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
                 u32 moves = q0.w & UNC_PATH_MASK, sa_checked = q0.w >> 31;
                 u32 want = 0; bool stay_ok = false;
@@ -965,7 +1019,11 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 u32 cmask = stay_ok ? 1u : 0u;
                 if (want) {
                     u32 ns[4], ne[4];
+#ifdef K2_OCC_STAGE
+                    u32 ok = unc_neighbors(ix, st, en, want, ns, ne, &pend_blocks, &pre);
+#else
                     u32 ok = unc_neighbors(ix, st, en, want, ns, ne, &pend_blocks);
+#endif
 #pragma unroll
                     for (u32 b = 0; b < 4; b++)
                         if ((ok >> b) & 1u) { cmask |= 2u << b; cst[b + 1] = ns[b]; cen[b + 1] = ne[b]; }
@@ -1020,11 +1078,26 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             }
         }
         c_sync_sub(1, (int) nwt);
-        // ---- B1. deferred seed_prob of children whose parent was already seed_len long:
-        //      C(e-22) is the C of the ancestor 22 generations back (21 parent hops from the parent)
-        {
+        // ---- B1 + B2a, concurrently.  Worker warp 0: exclusive scan of the chunk counts (restores the
+        //      global emission order and gives the buffer cap, reference src/mapper.cpp:480-482,507-509,
+        //      521-523: extension stops when max_paths children exist).  The other worker warps:
+        //      deferred seed_prob of children whose parent was already seed_len long -- C(e-22) is the C
+        //      of the ancestor 22 generations back (21 parent hops from the parent), a serial chain of
+        //      dependent loads that now overlaps the (equally serial) scan.
+        if (ww == 0) {
+            u32 carry = 0;
+            for (u32 i0 = 0; i0 < nch_prev; i0 += 32) {
+                u32 v = i0 + (u32) lane < nch_prev ? sh->bcnt[i0 + lane] : 0u, t;
+                u32 ex = w_exscan(v, &t);
+                if (i0 + (u32) lane < nch_prev) sh->bcnt[i0 + lane] = carry + ex;
+                carry += t;
+            }
+            if (lane == 0) sh->bc[2] = carry;
+        }
+        if (ww != 0 || nwk == 1) {
+            const u32 bt = nwk == 1 ? wt : wt - 32u, nbt = nwk == 1 ? nwt : nwt - 32u;
             const u32 nwl = *(volatile u32 *) &sh->wl_cnt;
-            for (u32 i = wt; i < nwl; i += nwt) {
+            for (u32 i = bt; i < nwl; i += nbt) {
                 uint4 w = W.wlist[i];
                 u32 idx = w.y;
                 for (u32 j = 1; j <= 21; j++)
@@ -1045,20 +1118,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         if (wt == 0) sh->wl_cnt = 0;
         PT_MARK(1)
 
-        // ---- B2. restore the emission order: exclusive scan of the chunk counts, the buffer cap
-        //      (reference src/mapper.cpp:480-482,507-509,521-523: extension stops when max_paths
-        //      children exist), ended-path seed rows, and compaction of the sort keys
-        if (ww == 0) {
-            u32 carry = 0;
-            for (u32 i0 = 0; i0 < nch_prev; i0 += 32) {
-                u32 v = i0 + (u32) lane < nch_prev ? sh->bcnt[i0 + lane] : 0u, t;
-                u32 ex = w_exscan(v, &t);
-                if (i0 + (u32) lane < nch_prev) sh->bcnt[i0 + lane] = carry + ex;
-                carry += t;
-            }
-            if (lane == 0) sh->bc[2] = carry;
-        }
-        c_sync_sub(1, (int) nwt);
+        // ---- B2. ended-path seed rows and compaction of the sort keys into emission order
         const u32 nc_total = nch_prev ? sh->bc[2] : 0u;
         const u32 nc = nc_total < maxp ? nc_total : maxp;
         const u32 nch = (nc + 31u) >> 5;

@@ -102,6 +102,13 @@ UNC_DEV void t_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
 }
+// per-thread asynchronous 16-byte copies global -> shared (cp.async, LDGSTS): no registers held
+UNC_DEV void a_copy16(void *dst, const void *src) {
+    unsigned d = (unsigned) __cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+UNC_DEV void a_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+UNC_DEV void a_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 UNC_DEV void t_bar_wait(uint64_t *bar, uint32_t parity) {
     unsigned b = (unsigned) __cvta_generic_to_shared(bar);
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"

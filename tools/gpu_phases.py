@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np
 import uncalled_b200._native as N
-N.LIB_PATH = os.path.join(ROOT, "uncalled_b200", "libunc_b200_pt.so")
+N.LIB_PATH = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "uncalled_b200", "libunc_b200_pt.so")
 import uncalled_b200 as U
 import synth, synthdata
 name = sys.argv[1] if len(sys.argv) > 1 else "g4m7"

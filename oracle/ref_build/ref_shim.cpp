@@ -181,6 +181,56 @@ int ref_map_batch_mt(const float *samples, const uint64_t *offsets, const uint32
     return 0;
 }
 
+// ---- streaming path (reference src/mapper.cpp:281-431, realtime_pool.cpp:108-139,349-356) -------------
+// One read fed chunk by chunk through the reference's own Mapper::new_read(Chunk&) /
+// process_chunk / map_chunk / add_chunk, in the order RealtimePool's worker loop and
+// try_add_chunk impose: a chunk is converted to events and pushed into the streaming normaliser
+// (process_chunk), mapped in batches of evt_batch_size events (map_chunk), and the next chunk is
+// accepted only once the previous one is fully mapped (chunk_mapped()).  Wall-clock limits
+// (evt_timeout, chunk_timeout) are disabled so that the result is a function of the input only.
+// Chunks are cut by the reference's own ReadBuffer::get_chunks (full chunks only).
+int ref_stream_read(const float *sig, uint32_t n, float chunk_time, uint32_t max_chunks, ref_paf_rec *out,
+                    uint32_t *n_chunks_used, int32_t *ended) {
+    Mapper::PRMS.evt_timeout = 1e30f;
+    Mapper::PRMS.chunk_timeout = 1e30f;
+    float old_ct = ReadBuffer::PRMS.chunk_time;
+    u32 old_mc = ReadBuffer::PRMS.max_chunks;
+    ReadBuffer::PRMS.chunk_time = chunk_time;
+    ReadBuffer::PRMS.max_chunks = max_chunks;
+    ReadBuffer full;
+    full.id_ = "r"; full.channel_idx_ = 0; full.number_ = 1; full.start_sample_ = 0;
+    full.full_signal_.assign(sig, sig + n);
+    std::vector<Chunk> chunks;
+    full.get_chunks(chunks, true, 0);
+    Mapper m;
+    uint32_t used = 0;
+    memset(out, 0, sizeof(*out));
+    out->rid = -1;
+    if (chunks.empty()) {
+        ReadBuffer::PRMS.chunk_time = old_ct; ReadBuffer::PRMS.max_chunks = old_mc;
+        if (n_chunks_used) *n_chunks_used = 0;
+        if (ended) *ended = 0;
+        return 0;
+    }
+    m.new_read(chunks[0]);
+    used = 1;
+    size_t next = 1;
+    for (;;) {
+        m.process_chunk();
+        if (m.map_chunk()) break;
+        if (m.chunk_mapped()) {
+            if (next < chunks.size()) { if (m.add_chunk(chunks[next])) { next++; used++; } }
+            else m.request_reset();       // try_add_chunk with an empty chunk: no more signal for this read
+        }
+    }
+    Paf p = m.get_read().loc_;
+    fill_rec(m, p, (uint32_t) m.evdt_.total_events_, out);
+    if (n_chunks_used) *n_chunks_used = used;
+    if (ended) *ended = p.ended_ ? 1 : 0;
+    ReadBuffer::PRMS.chunk_time = old_ct; ReadBuffer::PRMS.max_chunks = old_mc;
+    return 0;
+}
+
 // bwa index build exactly as `uncalled index` performs it (bwa_idx_build).
 int ref_index_build(const char *fasta, const char *prefix) {
     BwaIndex<KLEN>::create(fasta, prefix);

@@ -836,13 +836,17 @@ static void set_ref_loc(mapper_t *mp, const cluster_t *sc, float mean_event_len)
 }
 
 /* reference src/mapper.cpp:433-663 (map_next).  Returns 1 when the read is finished. */
+static int map_next_event(mapper_t *mp, float event, float mean_event_len);
 static int map_next(mapper_t *mp, const float *events, u32 n_events, float mean_event_len) {
+    /* norm_.empty() after n_events pops (reference src/normalizer.cpp:120-129) */
+    if (mp->event_i >= n_events || mp->event_i >= mp->prm->max_events) return 1;
+    return map_next_event(mp, events[mp->event_i], mean_event_len);
+}
+
+/* the body of map_next from `float event = norm_.pop()` on (reference src/mapper.cpp:440-663) */
+static int map_next_event(mapper_t *mp, float event, float mean_event_len) {
     const orc_index *x = mp->idx;
     const orc_params *prm = mp->prm;
-    /* norm_.empty() after n_events pops (reference src/normalizer.cpp:120-129) */
-    if (mp->event_i >= n_events || mp->event_i >= prm->max_events) return 1;
-
-    float event = events[mp->event_i];
     for (u32 k = 0; k < ORC_NKMER; k++) mp->kmer_probs[k] = orc_match_prob(mp->model, event, (u16) k);
     const float *probs = mp->kmer_probs;
     const float source_prob = x->thresh[0];
@@ -1029,6 +1033,202 @@ int orc_map_read(const orc_index *idx, const orc_model *m, const orc_params *p, 
     mapper_map_read(&mp, raw, n, out, ev, nb);
     free(ev);
     free(nb);
+    mapper_free(&mp);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ streaming path
+ * reference src/mapper.cpp:281-431 (add_chunk / process_chunk / map_chunk), src/normalizer.cpp:46-75,
+ * 114-152 (streaming Normalizer), src/event_profiler.hpp:46-104, src/realtime_pool.cpp:108-139,349-356
+ * (the order in which a worker thread and try_add_chunk drive one channel), src/read_buffer.cpp:249-296. */
+
+typedef struct {            /* Normalizer as a ring (reference src/normalizer.hpp:72-79) */
+    float *signal;
+    u32 len, n, rd, wr;
+    double mean, varsum;
+    int is_full, is_empty;
+    float tgt_mean, tgt_stdv;
+} snorm_t;
+
+static void snorm_init(snorm_t *z, u32 len, float tgt_mean, float tgt_stdv) {
+    memset(z, 0, sizeof(*z));
+    z->signal = (float *) calloc(len, sizeof(float));
+    z->len = len; z->is_empty = 1; z->tgt_mean = tgt_mean; z->tgt_stdv = tgt_stdv;
+}
+/* Normalizer::reset (:77-88) */
+static void snorm_reset(snorm_t *z) {
+    z->n = z->rd = z->wr = 0; z->mean = z->varsum = 0; z->is_full = 0; z->is_empty = 1; z->signal[0] = 0;
+}
+/* Normalizer::push (:46-75): Welford while filling, rolling update once the ring has wrapped */
+static int snorm_push(snorm_t *z, float newevt) {
+    if (z->is_full) return 0;
+    double oldevt = z->signal[z->wr];
+    z->signal[z->wr] = newevt;
+    if (z->n == z->len) {
+        double oldmean = z->mean;
+        z->mean += (newevt - oldevt) / z->len;
+        z->varsum += (newevt + oldevt - oldmean - z->mean) * (newevt - oldevt);
+    } else {
+        z->n++;
+        double dt1 = newevt - z->mean;
+        z->mean += dt1 / z->n;
+        double dt2 = newevt - z->mean;
+        z->varsum += dt1 * dt2;
+    }
+    z->wr = (z->wr + 1) % z->len;
+    z->is_empty = 0;
+    z->is_full = z->wr == z->rd;
+    return 1;
+}
+/* Normalizer::at + pop (:114-129): scale/shift from the statistics at pop time */
+static float snorm_pop(snorm_t *z) {
+    float scale = z->tgt_stdv / sqrt(z->varsum / z->n);
+    float shift = z->tgt_mean - scale * z->mean;
+    float e = scale * z->signal[z->rd] + shift;
+    z->rd = (z->rd + 1) % z->len;
+    z->is_empty = z->rd == z->wr;
+    z->is_full = 0;
+    return e;
+}
+/* Normalizer::unread_size (:131-134) -- note n_, not the ring length */
+static u32 snorm_unread(const snorm_t *z) {
+    if (z->rd < z->wr) return z->wr - z->rd;
+    return (z->n - z->rd) + z->wr;
+}
+/* Normalizer::skip_unread (:136-152) */
+static u32 snorm_skip_unread(snorm_t *z, u32 nkeep) {
+    if (nkeep >= snorm_unread(z)) return 0;
+    z->is_full = 0;
+    z->is_empty = nkeep == 0;
+    u32 new_rd;
+    if (nkeep <= z->wr) new_rd = z->wr - nkeep;
+    else new_rd = z->n - (nkeep - z->wr);
+    u32 nskip;
+    if (new_rd > z->rd) nskip = new_rd - z->rd;
+    else nskip = (z->n - z->rd) + new_rd;
+    z->rd = new_rd;
+    return nskip;
+}
+
+#define EVP_WIN 25u         /* EventProfiler::PRMS_DEF (reference src/event_profiler.cpp:4-10) */
+#define EVP_STDV_MIN 5.0f
+typedef struct {            /* EventProfiler (reference src/event_profiler.hpp:14-104) */
+    snorm_t window;
+    float means[EVP_WIN + 1];   /* std::deque<Event> events_: only the means are used downstream */
+    u32 q_head, q_size;
+    float next_mean;
+    int is_full;
+    u32 to_mask;
+} evprof_t;
+
+static void evprof_reset(evprof_t *e) {
+    snorm_reset(&e->window);
+    e->q_head = e->q_size = 0; e->next_mean = 0; e->is_full = 0; e->to_mask = 0;
+}
+/* EventProfiler::add_event (:71-104); returns event_ready() */
+static int evprof_add(evprof_t *e, float mean) {
+    snorm_push(&e->window, mean);
+    e->means[(e->q_head + e->q_size) % (EVP_WIN + 1)] = mean; e->q_size++;
+    if (snorm_unread(&e->window) <= EVP_WIN / 2) return 0;
+    float win_stdv = sqrt(e->window.varsum / e->window.n);      /* Normalizer::get_stdv: double sqrt -> float */
+    if (win_stdv < EVP_STDV_MIN) e->to_mask = EVP_WIN - 1;
+    else if (e->to_mask > 0) e->to_mask--;
+    if (e->window.is_full) {
+        e->next_mean = e->means[e->q_head];
+        e->q_head = (e->q_head + 1) % (EVP_WIN + 1); e->q_size--;
+        snorm_pop(&e->window);
+        e->is_full = 1;
+    }
+    return e->is_full && e->to_mask == 0;
+}
+
+/* One read fed chunk by chunk (chunk_len samples per chunk, full chunks only as
+ * ReadBuffer::get_chunks cuts them, at most max_chunks), with the wall-clock limits disabled:
+ * process_chunk -> map_chunk (evt_batch_size = 5 events per call) -> the next chunk only once the
+ * previous one is fully mapped; no more signal -> request_reset -> FAILURE with the ended flag. */
+int orc_stream_map_read(const orc_index *idx, const orc_model *m, const orc_params *p, const float *raw,
+                        uint32_t n, uint32_t chunk_len, uint32_t max_chunks, orc_paf_rec *out,
+                        uint32_t *n_chunks_used, int32_t *ended) {
+    memset(out, 0, sizeof(*out));
+    out->rid = -1;
+    if (n_chunks_used) *n_chunks_used = 0;
+    if (ended) *ended = 0;
+    u32 n_chunks = chunk_len ? n / chunk_len : 0;
+    if (n_chunks > max_chunks) n_chunks = max_chunks;
+    if (n_chunks == 0) return 0;
+
+    mapper_t mp;
+    mapper_init(&mp, idx, m, p);
+    mp.rec = out;
+    trk_reset(&mp.trk);
+    fm_counters cnt = {0, 0, 0};
+    g_cnt = &cnt;
+    snorm_t norm;
+    snorm_init(&norm, 6000, m->model_mean, m->model_stdv);     /* Normalizer::PRMS_DEF.len, Mapper::Mapper set_target */
+    evprof_t prof;
+    snorm_init(&prof.window, EVP_WIN, 0, 0);
+    evprof_reset(&prof);
+    evdt_t ed;
+    evdt_reset(&ed, p);
+    const float bp_per_samp = p->bp_per_sec / p->sample_rate;
+    const u32 evt_batch = 5;                                    /* Mapper::PRMS.evt_batch_size */
+
+    u32 chunk_count = 1, next_chunk = 1, cur = 0;
+    u64 raw_len = chunk_len;
+    int chunk_processed = 0, reset_req = 0, is_ended = 0, done = 0;
+    while (!done) {
+        /* ---- process_chunk (:301-363) */
+        if (!chunk_processed && !reset_req) {
+            u32 nevents = 0;
+            const float *c = raw + (size_t) cur * chunk_len;
+            for (u32 i = 0; i < chunk_len; i++) {
+                if (!evdt_add_sample(&ed, c[i])) continue;
+                if (!evprof_add(&prof, ed.ev_mean)) continue;
+                float evt_mean = prof.next_mean;
+                if (!snorm_push(&norm, evt_mean)) {
+                    u32 nskip = snorm_skip_unread(&norm, nevents);
+                    mp.event_i += nskip; mp.prev_size = 0;        /* skip_events */
+                    if (!snorm_push(&norm, evt_mean)) goto chunk_done;   /* returns with the chunk unprocessed */
+                }
+                nevents++;
+            }
+            chunk_processed = 1;
+        }
+    chunk_done:
+        /* ---- map_chunk (:381-431) */
+        if (reset_req || mp.event_i >= p->max_events) {
+            is_ended = 1; done = 1;                                /* set_failed + set_ended */
+        } else if (norm.is_empty && chunk_processed && chunk_count >= max_chunks) {
+            done = 1;                                              /* set_failed */
+        } else if (!norm.is_empty) {
+            u32 nev = mp.event_i + evt_batch > p->max_events ? p->max_events - mp.event_i : evt_batch;
+            for (u32 i = 0; i < nev && !norm.is_empty; i++) {
+                float event = snorm_pop(&norm);
+                float mel = ed.len_sum / ed.total_events;          /* EventDetector::mean_event_len at this point */
+                if (map_next_event(&mp, event, mel)) { snorm_skip_unread(&norm, 0); done = 1; break; }
+            }
+        }
+        if (done) break;
+        /* ---- RealtimePool::try_add_chunk (:108-139) */
+        if (chunk_processed && norm.is_empty) {
+            if (next_chunk < n_chunks) {
+                /* Mapper::add_chunk (:281-299) -> ReadBuffer::add_chunk (:271-284) */
+                if (chunk_count >= max_chunks) { done = 1; }      /* chunks_maxed: set_failed */
+                else { cur = next_chunk++; chunk_count++; raw_len += chunk_len; chunk_processed = 0; }
+            } else reset_req = 1;
+        }
+    }
+    if (!out->mapped) out->rd_len = (u64) (raw_len * bp_per_samp);   /* ReadBuffer::set_raw_len (:263-266) */
+    out->n_events = ed.total_events;
+    out->events_used = mp.event_i;
+    out->n_neighbor_calls = cnt.n_neighbor_calls;
+    out->n_occ_blocks = cnt.n_occ_blocks;
+    out->n_sa_steps = cnt.n_sa_steps;
+    out->n_clusters = mp.trk.n;
+    g_cnt = NULL;
+    if (n_chunks_used) *n_chunks_used = chunk_count;
+    if (ended) *ended = is_ended;
+    free(norm.signal); free(prof.window.signal);
     mapper_free(&mp);
     return 0;
 }

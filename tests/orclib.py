@@ -111,6 +111,9 @@ def orc():
                                      C.POINTER(OrcPaf)]
         lib.orc_map_batch_mt.argtypes = [C.c_void_p, C.POINTER(OrcModel), C.POINTER(OrcParams), f32p, u64p, u32p,
                                          C.c_uint32, C.c_int, C.POINTER(OrcPaf)]
+        lib.orc_stream_map_read.argtypes = [C.c_void_p, C.POINTER(OrcModel), C.POINTER(OrcParams), f32p, C.c_uint32,
+                                            C.c_uint32, C.c_uint32, C.POINTER(OrcPaf), C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_int32)]
         _orc = lib
     return _orc
 
@@ -162,6 +165,14 @@ class Oracle:
         rec = OrcPaf()
         self.lib.orc_map_read(self.idx, C.byref(self.model), C.byref(self.params), fp(raw), raw.size, C.byref(rec))
         return rec
+
+    def stream_read(self, raw, chunk_len, max_chunks=1000000):
+        """The streaming path (Mapper::process_chunk / map_chunk) over one read; returns (rec, chunks used, ended)."""
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        rec, nu, en = OrcPaf(), C.c_uint32(), C.c_int32()
+        self.lib.orc_stream_map_read(self.idx, C.byref(self.model), C.byref(self.params), fp(raw), raw.size,
+                                     int(chunk_len), int(max_chunks), C.byref(rec), C.byref(nu), C.byref(en))
+        return rec, nu.value, en.value
 
     def map_batch(self, samples, offsets, lens, threads=1):
         samples = np.ascontiguousarray(samples, dtype=np.float32)
@@ -216,6 +227,8 @@ def ref():
         lib.ref_normalize.argtypes = [f32p, C.c_uint32, f32p]
         lib.ref_map_read.argtypes = [f32p, C.c_uint32, C.POINTER(RefPaf)]
         lib.ref_map_batch_mt.argtypes = [f32p, u64p, u32p, C.c_uint32, C.c_int, C.POINTER(RefPaf)]
+        lib.ref_stream_read.argtypes = [f32p, C.c_uint32, C.c_float, C.c_uint32, C.POINTER(RefPaf),
+                                        C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
         lib.ref_index_build.argtypes = [C.c_char_p, C.c_char_p]
         _ref = lib
     return _ref

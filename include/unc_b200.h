@@ -173,6 +173,43 @@ int unc_pool_last_timing(const unc_pool *pool, unc_timing *t);
  * re-run rounds, lanes re-run, reads redone by the serial routine (exactness condition failed). */
 int unc_pool_k1_stats(const unc_pool *pool, uint32_t out[4]);
 
+/* ---- streaming path (chunks of many channels, persistent per-channel state on the device) ----------
+ *   unc_stream_create   RealtimePool::RealtimePool(Conf&): one Mapper per channel  src/realtime_pool.cpp:38-60
+ *   unc_stream_step     RealtimePool::add_chunk / try_add_chunk + MapperThread::run ->
+ *                       Mapper::new_read(Chunk&) / add_chunk / process_chunk / map_chunk
+ *                                                      src/realtime_pool.cpp:74-139,316-360, src/mapper.cpp:210-431
+ *   unc_stream_free     RealtimePool::stop_all         src/realtime_pool.cpp:286-297
+ * One step hands each listed channel its next chunk and maps ALL of the chunk's events (the reference maps
+ * them evt_batch_size at a time and accepts the next chunk only when the previous one is fully mapped, so
+ * the results are the same; its wall-clock limits evt_timeout / chunk_timeout do not exist here). */
+typedef struct {
+    uint32_t channel;     /* 0-based channel index */
+    uint32_t new_read;    /* 1: this chunk starts a new read on the channel (Mapper::new_read) */
+    uint64_t offset;      /* in samples from `samples` */
+    uint32_t n_samples;   /* 0 (with new_read == 0): no more signal for the read in progress */
+    uint32_t dtype;       /* UNC_DTYPE_F32 / UNC_DTYPE_I16 */
+    float cal_range, cal_offset, cal_digit;
+} unc_chunk_desc;
+
+#define UNC_STREAM_INACTIVE 0
+#define UNC_STREAM_MAPPING 1
+#define UNC_STREAM_SUCCESS 2   /* rec holds the mapping */
+#define UNC_STREAM_FAILURE 3   /* gave up: max_events / max_chunks / no more signal (ended = 1 like Paf::set_ended) */
+
+typedef struct {
+    int32_t state, ended;
+    uint32_t chunks;      /* chunks of the read consumed so far */
+    uint32_t pad_;
+    unc_paf_rec rec;      /* n_events = events detected so far, events_used = Mapper::event_i_ */
+} unc_stream_result;
+
+typedef struct unc_stream unc_stream;
+int unc_stream_create(const unc_index *idx, const unc_params *prm, uint32_t n_channels, uint32_t max_chunk_len,
+                      uint32_t max_chunks, unc_stream **out);
+int unc_stream_step(unc_stream *st, const unc_chunk_desc *chunks, uint32_t n, const void *samples,
+                    unc_stream_result *out);
+void unc_stream_free(unc_stream *st);
+
 #ifdef __cplusplus
 }
 #endif

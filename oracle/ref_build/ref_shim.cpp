@@ -189,31 +189,20 @@ int ref_map_batch_mt(const float *samples, const uint64_t *offsets, const uint32
 // accepted only once the previous one is fully mapped (chunk_mapped()).  Wall-clock limits
 // (evt_timeout, chunk_timeout) are disabled so that the result is a function of the input only.
 // Chunks are cut by the reference's own ReadBuffer::get_chunks (full chunks only).
-int ref_stream_read(const float *sig, uint32_t n, float chunk_time, uint32_t max_chunks, ref_paf_rec *out,
-                    uint32_t *n_chunks_used, int32_t *ended) {
-    Mapper::PRMS.evt_timeout = 1e30f;
-    Mapper::PRMS.chunk_timeout = 1e30f;
-    float old_ct = ReadBuffer::PRMS.chunk_time;
-    u32 old_mc = ReadBuffer::PRMS.max_chunks;
-    ReadBuffer::PRMS.chunk_time = chunk_time;
-    ReadBuffer::PRMS.max_chunks = max_chunks;
+static void stream_one(Mapper &m, const float *sig, uint32_t n, uint32_t number, ref_paf_rec *out,
+                       uint32_t *n_chunks_used, int32_t *ended) {
     ReadBuffer full;
-    full.id_ = "r"; full.channel_idx_ = 0; full.number_ = 1; full.start_sample_ = 0;
+    full.id_ = "r"; full.channel_idx_ = 0; full.number_ = number; full.start_sample_ = 0;
     full.full_signal_.assign(sig, sig + n);
     std::vector<Chunk> chunks;
     full.get_chunks(chunks, true, 0);
-    Mapper m;
-    uint32_t used = 0;
     memset(out, 0, sizeof(*out));
     out->rid = -1;
-    if (chunks.empty()) {
-        ReadBuffer::PRMS.chunk_time = old_ct; ReadBuffer::PRMS.max_chunks = old_mc;
-        if (n_chunks_used) *n_chunks_used = 0;
-        if (ended) *ended = 0;
-        return 0;
-    }
+    if (n_chunks_used) *n_chunks_used = 0;
+    if (ended) *ended = 0;
+    if (chunks.empty()) return;
     m.new_read(chunks[0]);
-    used = 1;
+    uint32_t used = 1;
     size_t next = 1;
     for (;;) {
         m.process_chunk();
@@ -227,6 +216,37 @@ int ref_stream_read(const float *sig, uint32_t n, float chunk_time, uint32_t max
     fill_rec(m, p, (uint32_t) m.evdt_.total_events_, out);
     if (n_chunks_used) *n_chunks_used = used;
     if (ended) *ended = p.ended_ ? 1 : 0;
+    m.deactivate();                       // RealtimePool::update after collecting the result (:166)
+}
+
+int ref_stream_read(const float *sig, uint32_t n, float chunk_time, uint32_t max_chunks, ref_paf_rec *out,
+                    uint32_t *n_chunks_used, int32_t *ended) {
+    Mapper::PRMS.evt_timeout = 1e30f;
+    Mapper::PRMS.chunk_timeout = 1e30f;
+    float old_ct = ReadBuffer::PRMS.chunk_time;
+    u32 old_mc = ReadBuffer::PRMS.max_chunks;
+    ReadBuffer::PRMS.chunk_time = chunk_time;
+    ReadBuffer::PRMS.max_chunks = max_chunks;
+    Mapper m;
+    stream_one(m, sig, n, 1, out, n_chunks_used, ended);
+    ReadBuffer::PRMS.chunk_time = old_ct; ReadBuffer::PRMS.max_chunks = old_mc;
+    return 0;
+}
+
+// Several reads one after the other through ONE Mapper, as the reads of one channel reach a
+// RealtimePool (the Mapper's streaming normaliser and sources_added_ persist between reads).
+int ref_stream_channel(const float *samples, const uint64_t *offsets, const uint32_t *lens, uint32_t n_reads,
+                       float chunk_time, uint32_t max_chunks, ref_paf_rec *out, uint32_t *n_chunks_used, int32_t *ended) {
+    Mapper::PRMS.evt_timeout = 1e30f;
+    Mapper::PRMS.chunk_timeout = 1e30f;
+    float old_ct = ReadBuffer::PRMS.chunk_time;
+    u32 old_mc = ReadBuffer::PRMS.max_chunks;
+    ReadBuffer::PRMS.chunk_time = chunk_time;
+    ReadBuffer::PRMS.max_chunks = max_chunks;
+    Mapper m;
+    for (uint32_t i = 0; i < n_reads; i++)
+        stream_one(m, samples + offsets[i], lens[i], i + 1, out + i, n_chunks_used ? n_chunks_used + i : nullptr,
+                   ended ? ended + i : nullptr);
     ReadBuffer::PRMS.chunk_time = old_ct; ReadBuffer::PRMS.max_chunks = old_mc;
     return 0;
 }

@@ -1142,34 +1142,57 @@ static int evprof_add(evprof_t *e, float mean) {
     return e->is_full && e->to_mask == 0;
 }
 
+/* One channel of a flow cell: what a RealtimePool keeps per channel between reads -- the Mapper with
+ * its streaming normaliser statistics and sources_added_ flags (reference src/realtime_pool.cpp:38-60,
+ * src/mapper.cpp:66-95); everything else is reset by Mapper::reset() at new_read (:218-246). */
+typedef struct {
+    mapper_t mp;
+    snorm_t norm;
+    evprof_t prof;
+    evdt_t ed;
+} stream_chan_t;
+
+static void chan_init(stream_chan_t *c, const orc_index *idx, const orc_model *m, const orc_params *p) {
+    mapper_init(&c->mp, idx, m, p);
+    snorm_init(&c->norm, 6000, m->model_mean, m->model_stdv);   /* Normalizer::PRMS_DEF.len; Mapper::Mapper set_target */
+    snorm_init(&c->prof.window, EVP_WIN, 0, 0);
+    evprof_reset(&c->prof);
+    evdt_reset(&c->ed, p);
+}
+static void chan_free(stream_chan_t *c) {
+    free(c->norm.signal); free(c->prof.window.signal);
+    mapper_free(&c->mp);
+}
+
 /* One read fed chunk by chunk (chunk_len samples per chunk, full chunks only as
  * ReadBuffer::get_chunks cuts them, at most max_chunks), with the wall-clock limits disabled:
  * process_chunk -> map_chunk (evt_batch_size = 5 events per call) -> the next chunk only once the
  * previous one is fully mapped; no more signal -> request_reset -> FAILURE with the ended flag. */
-int orc_stream_map_read(const orc_index *idx, const orc_model *m, const orc_params *p, const float *raw,
-                        uint32_t n, uint32_t chunk_len, uint32_t max_chunks, orc_paf_rec *out,
-                        uint32_t *n_chunks_used, int32_t *ended) {
+static void chan_map_read(stream_chan_t *c, const float *raw, uint32_t n, uint32_t chunk_len, uint32_t max_chunks,
+                          orc_paf_rec *out, uint32_t *n_chunks_used, int32_t *ended) {
+    const orc_params *p = c->mp.prm;
+    mapper_t *mp = &c->mp;
     memset(out, 0, sizeof(*out));
     out->rid = -1;
     if (n_chunks_used) *n_chunks_used = 0;
     if (ended) *ended = 0;
     u32 n_chunks = chunk_len ? n / chunk_len : 0;
     if (n_chunks > max_chunks) n_chunks = max_chunks;
-    if (n_chunks == 0) return 0;
+    if (n_chunks == 0) return;
 
-    mapper_t mp;
-    mapper_init(&mp, idx, m, p);
-    mp.rec = out;
-    trk_reset(&mp.trk);
+    /* Mapper::new_read(Chunk&) -> reset() (reference src/mapper.cpp:210-246) */
+    mp->rec = out;
+    mp->prev_size = 0;
+    mp->event_i = 0;
+    trk_reset(&mp->trk);
+    snorm_skip_unread(&c->norm, 0);
+    evdt_reset(&c->ed, p);
+    evprof_reset(&c->prof);
     fm_counters cnt = {0, 0, 0};
     g_cnt = &cnt;
-    snorm_t norm;
-    snorm_init(&norm, 6000, m->model_mean, m->model_stdv);     /* Normalizer::PRMS_DEF.len, Mapper::Mapper set_target */
-    evprof_t prof;
-    snorm_init(&prof.window, EVP_WIN, 0, 0);
-    evprof_reset(&prof);
-    evdt_t ed;
-    evdt_reset(&ed, p);
+    snorm_t *norm = &c->norm;
+    evprof_t *prof = &c->prof;
+    evdt_t *ed = &c->ed;
     const float bp_per_samp = p->bp_per_sec / p->sample_rate;
     const u32 evt_batch = 5;                                    /* Mapper::PRMS.evt_batch_size */
 
@@ -1180,15 +1203,15 @@ int orc_stream_map_read(const orc_index *idx, const orc_model *m, const orc_para
         /* ---- process_chunk (:301-363) */
         if (!chunk_processed && !reset_req) {
             u32 nevents = 0;
-            const float *c = raw + (size_t) cur * chunk_len;
+            const float *ck = raw + (size_t) cur * chunk_len;
             for (u32 i = 0; i < chunk_len; i++) {
-                if (!evdt_add_sample(&ed, c[i])) continue;
-                if (!evprof_add(&prof, ed.ev_mean)) continue;
-                float evt_mean = prof.next_mean;
-                if (!snorm_push(&norm, evt_mean)) {
-                    u32 nskip = snorm_skip_unread(&norm, nevents);
-                    mp.event_i += nskip; mp.prev_size = 0;        /* skip_events */
-                    if (!snorm_push(&norm, evt_mean)) goto chunk_done;   /* returns with the chunk unprocessed */
+                if (!evdt_add_sample(ed, ck[i])) continue;
+                if (!evprof_add(prof, ed->ev_mean)) continue;
+                float evt_mean = prof->next_mean;
+                if (!snorm_push(norm, evt_mean)) {
+                    u32 nskip = snorm_skip_unread(norm, nevents);
+                    mp->event_i += nskip; mp->prev_size = 0;      /* skip_events */
+                    if (!snorm_push(norm, evt_mean)) goto chunk_done;   /* returns with the chunk unprocessed */
                 }
                 nevents++;
             }
@@ -1196,21 +1219,21 @@ int orc_stream_map_read(const orc_index *idx, const orc_model *m, const orc_para
         }
     chunk_done:
         /* ---- map_chunk (:381-431) */
-        if (reset_req || mp.event_i >= p->max_events) {
+        if (reset_req || mp->event_i >= p->max_events) {
             is_ended = 1; done = 1;                                /* set_failed + set_ended */
-        } else if (norm.is_empty && chunk_processed && chunk_count >= max_chunks) {
+        } else if (norm->is_empty && chunk_processed && chunk_count >= max_chunks) {
             done = 1;                                              /* set_failed */
-        } else if (!norm.is_empty) {
-            u32 nev = mp.event_i + evt_batch > p->max_events ? p->max_events - mp.event_i : evt_batch;
-            for (u32 i = 0; i < nev && !norm.is_empty; i++) {
-                float event = snorm_pop(&norm);
-                float mel = ed.len_sum / ed.total_events;          /* EventDetector::mean_event_len at this point */
-                if (map_next_event(&mp, event, mel)) { snorm_skip_unread(&norm, 0); done = 1; break; }
+        } else if (!norm->is_empty) {
+            u32 nev = mp->event_i + evt_batch > p->max_events ? p->max_events - mp->event_i : evt_batch;
+            for (u32 i = 0; i < nev && !norm->is_empty; i++) {
+                float event = snorm_pop(norm);
+                float mel = ed->len_sum / ed->total_events;        /* EventDetector::mean_event_len at this point */
+                if (map_next_event(mp, event, mel)) { snorm_skip_unread(norm, 0); done = 1; break; }
             }
         }
         if (done) break;
         /* ---- RealtimePool::try_add_chunk (:108-139) */
-        if (chunk_processed && norm.is_empty) {
+        if (chunk_processed && norm->is_empty) {
             if (next_chunk < n_chunks) {
                 /* Mapper::add_chunk (:281-299) -> ReadBuffer::add_chunk (:271-284) */
                 if (chunk_count >= max_chunks) { done = 1; }      /* chunks_maxed: set_failed */
@@ -1219,17 +1242,37 @@ int orc_stream_map_read(const orc_index *idx, const orc_model *m, const orc_para
         }
     }
     if (!out->mapped) out->rd_len = (u64) (raw_len * bp_per_samp);   /* ReadBuffer::set_raw_len (:263-266) */
-    out->n_events = ed.total_events;
-    out->events_used = mp.event_i;
+    out->n_events = ed->total_events;
+    out->events_used = mp->event_i;
     out->n_neighbor_calls = cnt.n_neighbor_calls;
     out->n_occ_blocks = cnt.n_occ_blocks;
     out->n_sa_steps = cnt.n_sa_steps;
-    out->n_clusters = mp.trk.n;
+    out->n_clusters = mp->trk.n;
     g_cnt = NULL;
     if (n_chunks_used) *n_chunks_used = chunk_count;
     if (ended) *ended = is_ended;
-    free(norm.signal); free(prof.window.signal);
-    mapper_free(&mp);
+}
+
+int orc_stream_map_read(const orc_index *idx, const orc_model *m, const orc_params *p, const float *raw,
+                        uint32_t n, uint32_t chunk_len, uint32_t max_chunks, orc_paf_rec *out,
+                        uint32_t *n_chunks_used, int32_t *ended) {
+    stream_chan_t c;
+    chan_init(&c, idx, m, p);
+    chan_map_read(&c, raw, n, chunk_len, max_chunks, out, n_chunks_used, ended);
+    chan_free(&c);
+    return 0;
+}
+
+/* Several reads one after the other on ONE channel (the channel's Mapper persists, as in RealtimePool). */
+int orc_stream_map_channel(const orc_index *idx, const orc_model *m, const orc_params *p, const float *samples,
+                           const uint64_t *offsets, const uint32_t *lens, uint32_t n_reads, uint32_t chunk_len,
+                           uint32_t max_chunks, orc_paf_rec *out, uint32_t *n_chunks_used, int32_t *ended) {
+    stream_chan_t c;
+    chan_init(&c, idx, m, p);
+    for (uint32_t i = 0; i < n_reads; i++)
+        chan_map_read(&c, samples + offsets[i], lens[i], chunk_len, max_chunks, out + i,
+                      n_chunks_used ? n_chunks_used + i : NULL, ended ? ended + i : NULL);
+    chan_free(&c);
     return 0;
 }
 

@@ -3,6 +3,8 @@
 // it lets the CPU-only test tier compare the warp-cooperative kernel logic with the oracle.
 #include "unc_device.cuh"   // UNC_EMUL is defined on the command line
 #include "unc_k1.cuh"
+#include "unc_stream.cuh"
+#include "unc_stream_logic.hpp"
 #include "../../include/unc_b200.h"
 #include "unc_host_index.hpp"
 #include "unc_host_params.hpp"
@@ -151,6 +153,118 @@ uint64_t emu_sa(void *pidx, uint64_t row) {
     EmuIndex *e = (EmuIndex *) pidx;
     u32 a = 0, b = 0;
     return unc_sa(e->ix, (u32) row, &a, &b);
+}
+
+
+// ---------------------------------------------------------------- streaming path under the emulator
+struct EmuStream {
+    EmuIndex *e;
+    unc_params prm;
+    DevParams dp;
+    u32 n_channels, max_chunk_len, max_chunks, ev_stride, max_blocks;
+    std::vector<HostChan> ch;
+    std::vector<DevChanSig> sig;
+    std::vector<float> norm_sig;
+    std::vector<DevMapState> map;
+    std::vector<uint4> paths, ckey, cks, elist, wlist, clu, dir;
+    std::vector<uint2> hist, rlist;
+    std::vector<u32> order;
+    DevWork W;
+    DevWorkStrides S;
+};
+struct StreamCtaArgs { const DevIndex *ix; const DevParams *p; const DevBatch *B; const DevWork *W; const DevWorkStrides *S; K2Shared *sh; };
+static void stream_cta_entry(void *a) {
+    StreamCtaArgs *w = (StreamCtaArgs *) a;
+    unc_k2_cta_main_stream(*w->ix, *w->p, *w->B, *w->W, *w->S, w->sh);
+}
+
+void *emu_stream_create(void *pidx, const unc_params *prm, uint32_t n_channels, uint32_t max_chunk_len,
+                        uint32_t max_chunks, uint32_t max_blocks) {
+    EmuStream *T = new EmuStream();
+    T->e = (EmuIndex *) pidx; T->prm = *prm; T->dp = unc_make_dev_params(*prm, T->e->h);
+    T->n_channels = n_channels; T->max_chunk_len = max_chunk_len; T->max_chunks = max_chunks;
+    T->ev_stride = (max_chunk_len + 3u) & ~3u; T->max_blocks = max_blocks;
+    T->ch.resize(n_channels);
+    T->sig.resize(n_channels); memset(T->sig.data(), 0, n_channels * sizeof(DevChanSig));
+    T->norm_sig.assign((size_t) n_channels * UNC_NORM_LEN, 0.0f);
+    T->map.resize(n_channels); memset(T->map.data(), 0, n_channels * sizeof(DevMapState));
+    const size_t maxp = prm->max_paths, nchmax = (maxp + 31) / 32, n = n_channels;
+    DevWorkStrides &S = T->S;
+    S.paths = 2 * (nchmax * 160 + maxp) * 2; S.hist = 24 * (nchmax * 160 + maxp); S.ckey = 2 * maxp;
+    S.cks = nchmax * 160; S.elist = nchmax * 32; S.order = 2 * maxp;
+    const u32 rl_cap = 16384;
+    S.rlist = 2 * rl_cap; S.clu = (size_t) max_blocks * 32 * 2; S.dir = (size_t) max_blocks + 1;
+    T->paths.resize(n * S.paths); T->hist.resize(n * S.hist); T->ckey.resize(n * S.ckey); T->cks.resize(n * S.cks);
+    T->wlist.resize(n * S.cks); T->elist.resize(n * S.elist); T->order.resize(n * S.order); T->rlist.resize(n * S.rlist);
+    T->clu.resize(n * S.clu); T->dir.resize(n * S.dir);
+    DevWork &W = T->W;
+    W.paths = T->paths.data(); W.hist = T->hist.data(); W.wlist = T->wlist.data(); W.ckey = T->ckey.data(); W.cks = T->cks.data();
+    W.elist = T->elist.data(); W.order = T->order.data(); W.rlist = T->rlist.data(); W.clu = T->clu.data(); W.dir = T->dir.data();
+    W.max_blocks = max_blocks; W.rl_cap = rl_cap;
+    return T;
+}
+void emu_stream_free(void *p) { delete (EmuStream *) p; }
+
+// Mirrors unc_stream_step (unc_stream_host.inl): same bookkeeping (unc_stream_logic.hpp), the two device
+// routines run on the CPU: unc_stream_chunk per item, then the mapper CTA under the emulator.
+int emu_stream_step(void *pst, const unc_chunk_desc *chunks, uint32_t n, const void *samples, unc_stream_result *out,
+                    int n_warps) {
+    EmuStream *T = (EmuStream *) pst;
+    const float bp_per_samp = T->prm.bp_per_sec / T->prm.sample_rate;
+    std::vector<int> item_of(n, -1);
+    std::vector<DevReadDesc> rd;
+    std::vector<u32> chan, isnew;
+    u64 total_bytes = 0;
+    for (u32 i = 0; i < n; i++) {
+        const unc_chunk_desc &c = chunks[i];
+        if (c.channel >= T->n_channels || c.n_samples > T->max_chunk_len) return UNC_E_ARG;
+        if (!stream_admit(T->ch[c.channel], c, T->max_chunks)) continue;
+        DevReadDesc d;
+        d.offset = c.offset; d.n_samples = c.n_samples; d.dtype = c.dtype;
+        d.cal_range = c.cal_range; d.cal_offset = c.cal_offset; d.cal_digit = c.cal_digit; d.pad = 0;
+        total_bytes = std::max<u64>(total_bytes, (c.offset + c.n_samples) * (c.dtype ? 2 : 4));
+        item_of[i] = (int) rd.size();
+        rd.push_back(d); chan.push_back(c.channel); isnew.push_back(c.new_read ? 1u : 0u);
+    }
+    const u32 m = (u32) rd.size();
+    std::vector<DevRec> recs(m);
+    std::vector<u32> tot(m);
+    if (m) {
+        std::vector<float> events((size_t) m * T->ev_stride + 1), scale(m), shift(m), mel(m);
+        std::vector<u32> n_events(m), flags(m);
+        std::vector<u64> seq_off(T->e->h.offsets.begin(), T->e->h.offsets.end());
+        u32 queue = 0, k1q = 0;
+        DevBatch B;
+        memset(&B, 0, sizeof(B));
+        B.samples = samples; B.samples_bytes = total_bytes; B.reads = rd.data(); B.n_reads = m;
+        B.events = events.data(); B.normed = nullptr; B.ev_stride = T->ev_stride; B.n_events = n_events.data();
+        B.scale = scale.data(); B.shift = shift.data(); B.mean_event_len = mel.data();
+        B.queue = &queue; B.k1_queue = &k1q; B.k1_flags = flags.data(); B.k1_stats = nullptr;
+        B.out = recs.data(); B.dbg = nullptr;
+        B.seq_offsets = seq_off.data(); B.seq_lens = T->e->h.lens.data(); B.n_seqs = (u32) T->e->h.names.size();
+        B.l_pac = (u64) T->e->h.l_pac;
+        B.mstate = T->map.data(); B.chan = chan.data();
+        DevStream S;
+        S.sig = T->sig.data(); S.norm_sig = T->norm_sig.data(); S.map = T->map.data();
+        for (u32 r = 0; r < m; r++) {
+            unc_stream_chunk(B, T->dp, S, r, isnew[r]);
+            tot[r] = T->sig[chan[r]].evdt.total_events;
+        }
+        K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((T->dp.max_paths + 31) / 32) * 24);
+        StreamCtaArgs a = {&T->e->ix, &T->dp, &B, &T->W, &T->S, sh};
+        emu_run_cta(stream_cta_entry, &a, 32 * (n_warps > 0 ? n_warps : 8));
+        free(sh);
+    }
+    for (u32 i = 0; i < n; i++) {
+        HostChan &h = T->ch[chunks[i].channel];
+        if (item_of[i] >= 0) {
+            unc_paf_rec r;
+            memcpy(&r, &recs[item_of[i]], sizeof(r));
+            stream_settle(h, r, tot[item_of[i]], T->prm.max_events, T->max_chunks);
+        }
+        stream_result(h, bp_per_samp, &out[i]);
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -64,7 +64,7 @@ def build():
     out = os.path.join(EMUL_DIR, "libunc_emul.so")
     deps = [src, os.path.join(EMUL_DIR, "warp_emul.hpp")] + \
            [os.path.join(ROOT, "uncalled_b200", "csrc", f) for f in
-            ("unc_device.cuh", "unc_k1.cuh", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp")]
+            ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_logic.hpp", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-DUNC_EMUL", "-DK2_MAXSEG=16u", "-fPIC", "-shared",
@@ -91,6 +91,10 @@ def lib():
         L.emu_sa.argtypes = [C.c_void_p, C.c_uint64]
         L.emu_sa.restype = C.c_uint64
         L.emu_k1_stats.argtypes = [C.c_void_p]
+        L.emu_stream_create.restype = C.c_void_p
+        L.emu_stream_create.argtypes = [C.c_void_p, C.POINTER(UncParams), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.emu_stream_free.argtypes = [C.c_void_p]
+        L.emu_stream_step.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -122,6 +126,34 @@ class Emu:
         if rc != 0:
             raise RuntimeError("emu_map_batch rc=%d" % rc)
         return list(out), [ev[i, :ne[i]].copy() for i in range(n)], [nm[i, :ne[i]].copy() for i in range(n)], mel
+
+
+def stream_reads(step, n_channels, signals, chunk_len, max_chunks=1000000):
+    """The chunk-feeding policy of the product's python layer (uncalled_b200/stream.py feed_reads; pure python)."""
+    from uncalled_b200.stream import feed_reads
+    return feed_reads(step, n_channels, signals, chunk_len, max_chunks)
+
+
+class EmuStream:
+    """The streaming path under the emulator (tests/emul/emul_main.cpp emu_stream_*)."""
+
+    def __init__(self, emu, n_channels, max_chunk_len, max_chunks=1000000, max_blocks=4096, n_warps=8):
+        self.emu, self.n_channels, self.n_warps = emu, n_channels, n_warps
+        self.h = emu.L.emu_stream_create(emu.idx, C.byref(emu.params), n_channels, max_chunk_len, max_chunks, max_blocks)
+        self.max_chunks = max_chunks
+
+    def step(self, descs, n, flat, res):
+        rc = self.emu.L.emu_stream_step(self.h, descs, n, flat.ctypes.data, res, self.n_warps)
+        if rc != 0:
+            raise RuntimeError("emu_stream_step rc=%d" % rc)
+
+    def map_reads(self, signals, chunk_len):
+        return stream_reads(self.step, self.n_channels, signals, chunk_len, self.max_chunks)
+
+    def close(self):
+        if self.h:
+            self.emu.L.emu_stream_free(self.h)
+            self.h = None
 
 
 def k1_stats():

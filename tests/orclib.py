@@ -114,6 +114,9 @@ def orc():
         lib.orc_stream_map_read.argtypes = [C.c_void_p, C.POINTER(OrcModel), C.POINTER(OrcParams), f32p, C.c_uint32,
                                             C.c_uint32, C.c_uint32, C.POINTER(OrcPaf), C.POINTER(C.c_uint32),
                                             C.POINTER(C.c_int32)]
+        lib.orc_stream_map_channel.argtypes = [C.c_void_p, C.POINTER(OrcModel), C.POINTER(OrcParams), f32p, u64p, u32p,
+                                               C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(OrcPaf),
+                                               C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
         _orc = lib
     return _orc
 
@@ -174,6 +177,18 @@ class Oracle:
                                      int(chunk_len), int(max_chunks), C.byref(rec), C.byref(nu), C.byref(en))
         return rec, nu.value, en.value
 
+    def stream_channel(self, signals, chunk_len, max_chunks=1000000):
+        """Reads one after the other on one channel (persistent Mapper); returns [(rec, chunks, ended)]."""
+        flat = np.ascontiguousarray(np.concatenate(signals), dtype=np.float32)
+        lens = np.array([len(s) for s in signals], np.uint32)
+        offs = np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.uint64)]).astype(np.uint64)
+        n = len(signals)
+        out, nu, en = (OrcPaf * n)(), (C.c_uint32 * n)(), (C.c_int32 * n)()
+        self.lib.orc_stream_map_channel(self.idx, C.byref(self.model), C.byref(self.params), fp(flat),
+                                        offs.ctypes.data_as(u64p), lens.ctypes.data_as(u32p), n, int(chunk_len),
+                                        int(max_chunks), out, nu, en)
+        return [(out[i], nu[i], en[i]) for i in range(n)]
+
     def map_batch(self, samples, offsets, lens, threads=1):
         samples = np.ascontiguousarray(samples, dtype=np.float32)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
@@ -227,6 +242,8 @@ def ref():
         lib.ref_normalize.argtypes = [f32p, C.c_uint32, f32p]
         lib.ref_map_read.argtypes = [f32p, C.c_uint32, C.POINTER(RefPaf)]
         lib.ref_map_batch_mt.argtypes = [f32p, u64p, u32p, C.c_uint32, C.c_int, C.POINTER(RefPaf)]
+        lib.ref_stream_channel.argtypes = [f32p, u64p, u32p, C.c_uint32, C.c_float, C.c_uint32, C.POINTER(RefPaf),
+                                           C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
         lib.ref_stream_read.argtypes = [f32p, C.c_uint32, C.c_float, C.c_uint32, C.POINTER(RefPaf),
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
         lib.ref_index_build.argtypes = [C.c_char_p, C.c_char_p]

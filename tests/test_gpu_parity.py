@@ -260,3 +260,59 @@ def test_small_max_paths_overflow_semantics(U):
     def mod(p):
         p.max_paths = 300
     _compare_with_oracle(U, "g200k", 64, 3000, seed=13, params_mod=mod)
+
+
+def _stream_vs_oracle(U, prefix, sigs, n_channels, chunk_len, max_chunks=1000000, params_mod=None):
+    import orclib
+    idx = U.Index(prefix, device=0)
+    p = U.default_params()
+    O = orclib.Oracle(prefix)
+    if params_mod:
+        params_mod(p)
+        params_mod(O.params)
+    sm = U.StreamMapper(idx, n_channels, chunk_len, max_chunks=max_chunks, params=p)
+    res = sm.map_reads(sigs)
+    sm.close()
+    states = []
+    for c in range(n_channels):
+        idxs = list(range(c, len(sigs), n_channels))
+        want = O.stream_channel([sigs[i] for i in idxs], chunk_len, max_chunks)
+        for i, (rec, nu, en) in zip(idxs, want):
+            r = res[i]
+            if nu == 0:
+                assert r is None, i
+                continue
+            assert (U.paf_key(r[3]), r[2], r[1]) == (orclib.paf_tuple(rec), nu, en), i
+            assert (r[3].n_children, r[3].n_sources, r[3].n_seeds) == (rec.n_children, rec.n_sources, rec.n_seeds), i
+            assert r[3].status == 0 and r[0] == (2 if rec.mapped else 3)
+            states.append((r[0], r[1]))
+    return states
+
+
+def test_stream_chunks_match_streaming_oracle(U):
+    """config-5-like at test scale: 450-sample chunks, 8 channels, 3 reads per channel one after the other (the
+    channel's normaliser statistics and sources_added_ persist), against the oracle's streaming restatement."""
+    import synth
+    import synthdata
+    prefix, g = synthdata.get_index("g200k")
+    sig, _ = synth.reads(g, 24, 8000, seed=15, frac_random=0.3)
+    sigs = [sig[i][:8000 - 53 * i] for i in range(24)] + [sig[0][:200]]
+    st = _stream_vs_oracle(U, prefix, sigs, 8, 450)
+    assert (2, 0) in st and (3, 1) in st
+
+
+def test_stream_limits(U):
+    """max_chunks, max_events in the middle of a chunk, a tiny path buffer, one-second chunks."""
+    import synth
+    import synthdata
+    prefix, g = synthdata.get_index("g200k")
+    sig, _ = synth.reads(g, 10, 6000, seed=9, frac_random=0.5)
+    sigs = [sig[i] for i in range(10)]
+    _stream_vs_oracle(U, prefix, sigs, 5, 450, max_chunks=4)
+    _stream_vs_oracle(U, prefix, sigs, 4, 4000)
+
+    def mod(p):
+        p.max_events = 150
+        p.max_paths = 300
+    st = _stream_vs_oracle(U, prefix, sigs, 3, 450, params_mod=mod)
+    assert (3, 1) in st

@@ -2,5 +2,6 @@
 (skovaka/UNCALLED) behind a C-ABI (include/unc_b200.h)."""
 from ._native import UncError, build, default_params  # noqa: F401
 from .mapper import BatchMapper, Index, make_descs, paf_key  # noqa: F401
+from .stream import StreamMapper, feed_reads  # noqa: F401
 
 __version__ = "0.1.0"

@@ -75,7 +75,8 @@ EXPORTS = ["unc_strerror", "unc_last_error", "unc_device_count", "unc_init", "un
            "unc_index_load", "unc_index_get_info", "unc_index_seq", "unc_index_kmer_range",
            "unc_index_thresholds", "unc_index_free", "unc_index_build", "unc_pool_create", "unc_pool_free",
            "unc_map_batch", "unc_map_batch_device", "unc_events_batch", "unc_match_probs", "unc_fm_neighbors",
-           "unc_fm_sa", "unc_pool_last_timing", "unc_pool_k1_stats"]
+           "unc_fm_sa", "unc_pool_last_timing", "unc_pool_k1_stats", "unc_stream_create", "unc_stream_step",
+           "unc_stream_free"]
 
 
 def build(force=False, verbose=False):
@@ -83,7 +84,8 @@ def build(force=False, verbose=False):
     src_dir = os.path.join(PKG_DIR, "csrc")
     srcs = [os.path.join(src_dir, f) for f in ("unc_abi.cu", "unc_index_build.cpp")]
     deps = srcs + [os.path.join(src_dir, f) for f in
-                   ("unc_device.cuh", "unc_k1.cuh", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp")] + \
+                   ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_host.inl", "unc_stream_logic.hpp", "unc_warp.cuh",
+                    "unc_host_index.hpp", "unc_host_params.hpp")] + \
         [os.path.join(ROOT, "include", "unc_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -132,6 +134,10 @@ def lib():
     L.unc_fm_sa.argtypes = [vp, u32, vp, vp]
     L.unc_pool_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.unc_pool_k1_stats.argtypes = [vp, vp]
+    L.unc_stream_create.argtypes = [vp, C.POINTER(Params), u32, u32, u32, C.POINTER(vp)]
+    L.unc_stream_step.argtypes = [vp, vp, u32, vp, vp]
+    L.unc_stream_free.argtypes = [vp]
+    L.unc_stream_free.restype = None
     _lib = L
     return L
 

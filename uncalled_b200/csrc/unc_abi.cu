@@ -12,6 +12,7 @@
 
 #include "unc_device.cuh"
 #include "unc_k1.cuh"
+#include "unc_stream.cuh"
 #include "../../include/unc_b200.h"
 #include "unc_host_index.hpp"
 #include "unc_host_params.hpp"
@@ -665,3 +666,5 @@ int unc_pool_last_timing(const unc_pool *P, unc_timing *t) {
 }
 
 }  // extern "C"
+
+#include "unc_stream_host.inl"

@@ -80,6 +80,9 @@ struct DevBatch {
     u32 *k1_queue;       // atomic read counter of the event-detection kernel
     u32 *k1_flags;       // per read: 1 = redo with the serial routine (exactness condition failed)
     u32 *k1_stats;       // optional (may be null): tiles, FSM re-run rounds, re-run lanes, flagged reads
+    // streaming (k2_map_stream only): item r continues the read of channel chan[r] from mstate[chan[r]]
+    struct DevMapState *mstate;
+    const u32 *chan;
     // K1 outputs
     float *events;       // n_reads x ev_stride valid event means (raw, un-normalised)
     float *normed;       // optional (may be null): normalised means
@@ -410,6 +413,22 @@ UNC_DEV void unc_k1_read(const DevBatch &B, const DevParams &p, u32 r) {
     B.scale[r] = scale;
     B.shift[r] = shift;
 }
+
+// ------------------------------------------------------------------ streaming: persistent mapper state
+// What Mapper keeps between map_chunk calls of one read (reference src/mapper.hpp:205-236): the path
+// buffers, event_i_, the seed tracker -- here the per-channel workspace slot plus these scalars.
+struct DevMapState {
+    u32 prev_size, gen, event_i, started;     // started == 0: new read (Mapper::reset, src/mapper.cpp:218-246)
+    u32 flags[32];                            // sources_added_: persists across the reads of a channel (src/mapper.cpp:88)
+    u32 t_nb, t_n_alloc, t_n_live, t_n_lens, t_top1, t_top2, t_overflow;
+    float t_len_sum;
+    u32 t_max_map[6];
+    u32 pad[2];
+};
+
+struct DevWorkStrides {
+    size_t paths, hist, ckey, cks, elist, order, rlist, clu, dir;
+};
 
 // ------------------------------------------------------------------ K2: seed tracker
 
@@ -800,13 +819,24 @@ UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *
 
 // ---- tracker warp (warp 0): reference src/mapper.cpp:513-519,601 (update_seeds order),
 //      :631-653 (get_final -> set_ref_loc), :708-728, bwa_index.hpp:213-220
+template <bool STREAM>
 UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
-                            K2Shared *sh, u32 r, u32 n_limit) {
+                            K2Shared *sh, u32 r, u32 n_first, u32 n_limit) {
     const int lane = w_lane();
     Tracker trk;
     trk.blocks = W.clu; trk.dir = W.dir; trk.max_blocks = W.max_blocks;
     trk_reset(trk);
-    u32 verdict = 0, i = 0, final_event = n_limit;
+    DevMapState *ms = nullptr;
+    if (STREAM) {
+        ms = B.mstate + B.chan[r];
+        if (ms->started) {                          // continue the read: the cluster store lives in the channel's slot
+            trk.nb = ms->t_nb; trk.n_alloc = ms->t_n_alloc; trk.n_live = ms->t_n_live; trk.n_lens = ms->t_n_lens;
+            trk.top1 = ms->t_top1; trk.top2 = ms->t_top2; trk.overflow = ms->t_overflow; trk.len_sum = ms->t_len_sum;
+            trk.max_map.ren_start = ms->t_max_map[0]; trk.max_map.evt_en = ms->t_max_map[1]; trk.max_map.ref_st = ms->t_max_map[2];
+            trk.max_map.ren_end = ms->t_max_map[3]; trk.max_map.evt_st = ms->t_max_map[4]; trk.max_map.total_len = ms->t_max_map[5];
+        }
+    }
+    u32 verdict = 0, i = n_first, final_event = n_limit;
     u64 n_seeds = 0;
     for (;;) {
         c_sync();                                  // b_i: workers finished event i (or this is the final barrier)
@@ -825,6 +855,14 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
         if (v) { verdict = v; final_event = i; }
         if (lane == 0) *(volatile u32 *) &sh->verdict[i & 1u] = v;
         i++;
+    }
+    if (STREAM && lane == 0) {                      // what the next map_chunk of this read resumes from
+        ms->t_nb = trk.nb; ms->t_n_alloc = trk.n_alloc; ms->t_n_live = trk.n_live; ms->t_n_lens = trk.n_lens;
+        ms->t_top1 = trk.top1; ms->t_top2 = trk.top2; ms->t_overflow = trk.overflow; ms->t_len_sum = trk.len_sum;
+        ms->t_max_map[0] = trk.max_map.ren_start; ms->t_max_map[1] = trk.max_map.evt_en; ms->t_max_map[2] = trk.max_map.ref_st;
+        ms->t_max_map[3] = trk.max_map.ren_end; ms->t_max_map[4] = trk.max_map.evt_st; ms->t_max_map[5] = trk.max_map.total_len;
+        ms->event_i = final_event;
+        ms->started = 1;
     }
     // all workers have passed the final barrier: their counters are in shared memory
     if (lane == 0) {
@@ -891,8 +929,9 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
 
 UNC_DEV u32 k2_pre_pack(u32 epoch, u32 state) { return (epoch << 2) | state; }
 
+template <bool STREAM>
 UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
-                            K2Shared *sh, u32 r, u32 n_limit, u32 *epoch_io) {
+                            K2Shared *sh, u32 r, u32 n_first, u32 n_limit, u32 *epoch_io) {
     const int lane = w_lane();
     const u32 wt = (u32) c_tid() - 32u, nwt = (u32) c_nthreads() - 32u;   // worker thread index / count
     const u32 ww = wt >> 5, nwk = nwt >> 5;                               // worker warp index / count
@@ -907,13 +946,17 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
     u32 pend_children = 0, pend_sources = 0;           // of the event in flight
     u32 my_blocks = 0, my_steps = 0, pend_blocks = 0, pend_steps = 0;
     u32 epoch = *epoch_io;
-    u32 prev_size = 0, gen = 0, event_i = 0;
+    u32 prev_size = 0, gen = 0, event_i = n_first;
+    if (STREAM) {                                      // resume: the previous chunk's last generation is in the slot
+        const DevMapState *ms = B.mstate + B.chan[r];
+        if (ms->started) { prev_size = ms->prev_size; gen = ms->gen; }
+    }
     const u32 npass = (ix.start_bits + K2_RBITS - 1) / K2_RBITS;
     const u32 lt = w_lanemask_lt();
     PT_DECL
 
     for (; event_i < n_limit; event_i++) {
-        const float event = f_add(f_mul(scale, events[event_i]), shift);
+        const float event = f_add(f_mul(scale, events[event_i - n_first]), shift);
         PT_MARK(7)
 
         // ---- A. pore-model probabilities (reference src/mapper.cpp:443-445)
@@ -1462,7 +1505,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         PT_MARK(6)
         nn = sh->bc[1];
         pend_sources = nn - nc;
-        const u32 v = event_i > 0 ? *(volatile u32 *) &sh->verdict[(event_i - 1u) & 1u] : 0u;
+        const u32 v = event_i > n_first ? *(volatile u32 *) &sh->verdict[(event_i - 1u) & 1u] : 0u;
         if (v) break;                                                 // event_i's work is discarded
         n_children += pend_children; n_sources += pend_sources;
         my_blocks += pend_blocks; my_steps += pend_steps;
@@ -1471,6 +1514,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         gen ^= 1u;
     }
     *epoch_io = epoch;
+    if (STREAM && wt == 0) { DevMapState *ms = B.mstate + B.chan[r]; ms->prev_size = prev_size; ms->gen = gen; }
     PT_FLUSH(B, r)
     for (int d = 16; d > 0; d >>= 1) { my_blocks += w_shfl(my_blocks, lane ^ d); my_steps += w_shfl(my_steps, lane ^ d); }
     if (lane == 0) { s_atomic_add(&sh->cnt_blocks, my_blocks); s_atomic_add(&sh->cnt_steps, my_steps); }
@@ -1481,22 +1525,49 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
     c_sync();                                                         // Y: final barrier
 }
 
-// One read mapped by one CTA.  reference src/mapper.cpp:188-200 (map_read).
+// One read mapped by one CTA.  reference src/mapper.cpp:188-200 (map_read); with STREAM, one map_chunk's
+// worth of events of a read in progress (:381-431), resumed from and saved to the channel's DevMapState.
+template <bool STREAM>
 UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
                              K2Shared *sh, u32 r, u32 *epoch_io) {
     const u32 tid = (u32) c_tid();
     const u32 n_ev = B.n_events[r];
-    const u32 n_limit = n_ev < p.max_events ? n_ev : p.max_events;
-    if (tid < 32) sh->flags[tid] = 0;
+    u32 n_first = 0;
+    if (STREAM) {
+        const DevMapState *ms = B.mstate + B.chan[r];
+        if (ms->started) n_first = ms->event_i;
+        if (tid < 32) sh->flags[tid] = ms->flags[tid];
+    } else {
+        if (tid < 32) sh->flags[tid] = 0;
+    }
+    const u32 n_limit = n_first + n_ev < p.max_events ? n_first + n_ev : (n_first < p.max_events ? p.max_events : n_first);
     if (tid == 0) {
         sh->cnt_blocks = 0; sh->cnt_steps = 0; sh->wk_overflow = 0; sh->wl_cnt = 0;
         sh->verdict[0] = sh->verdict[1] = 0; sh->n_rows[0] = sh->n_rows[1] = 0; sh->bc[1] = 0;
     }
     for (u32 b = tid; b < K2_RB * K2_MAXSEG; b += (u32) c_nthreads()) sh->hist_next[b] = 0;
     c_sync();
-    if (tid < 32) unc_k2_tracker(ix, p, B, W, sh, r, n_limit);
-    else unc_k2_workers(ix, p, B, W, sh, r, n_limit, epoch_io);
+    if (tid < 32) unc_k2_tracker<STREAM>(ix, p, B, W, sh, r, n_first, n_limit);
+    else unc_k2_workers<STREAM>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
     c_sync();
+    if (STREAM && tid < 32) B.mstate[B.chan[r]].flags[tid] = sh->flags[tid];
+}
+
+UNC_DEV DevWork unc_work_slot(const DevWork &W0, const DevWorkStrides &S, size_t slot) {
+    DevWork W;
+    W.paths = W0.paths + slot * S.paths;
+    W.hist = W0.hist + slot * S.hist;
+    W.wlist = W0.wlist + slot * S.cks;
+    W.ckey = W0.ckey + slot * S.ckey;
+    W.cks = W0.cks + slot * S.cks;
+    W.elist = W0.elist + slot * S.elist;
+    W.order = W0.order + slot * S.order;
+    W.rlist = W0.rlist + slot * S.rlist;
+    W.clu = W0.clu + slot * S.clu;
+    W.dir = W0.dir + slot * S.dir;
+    W.max_blocks = W0.max_blocks;
+    W.rl_cap = W0.rl_cap;
+    return W;
 }
 
 // Persistent CTA body: stage the tables, then pull reads from the global queue.
@@ -1510,6 +1581,22 @@ UNC_DEV void unc_k2_cta_main(const DevIndex &ix, const DevParams &p, const DevBa
         u32 r = sh->bc[0];
         c_sync();
         if (r >= B.n_reads) break;
-        unc_k2_map_read(ix, p, B, W, sh, r, &epoch);
+        unc_k2_map_read<false>(ix, p, B, W, sh, r, &epoch);
+    }
+}
+
+// Streaming variant: every item continues a read in the workspace slot of its CHANNEL.
+UNC_DEV void unc_k2_cta_main_stream(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W0,
+                                    const DevWorkStrides &S, K2Shared *sh) {
+    unc_k2_cta_setup(ix, p, sh);
+    u32 epoch = 0;
+    for (;;) {
+        if (c_tid() == 0) sh->bc[0] = d_atomic_add(B.queue, 1u);
+        c_sync();
+        u32 r = sh->bc[0];
+        c_sync();
+        if (r >= B.n_reads) break;
+        const DevWork W = unc_work_slot(W0, S, B.chan[r]);
+        unc_k2_map_read<true>(ix, p, B, W, sh, r, &epoch);
     }
 }

@@ -18,16 +18,19 @@ d = U.make_descs([4000] * n_reads)
 for it in range(2):
     out = bm.map(sig.ravel(), d)
     print("iter", it, bm.timing())
-ph = np.zeros((n_reads, 8), np.uint64)
+ph2 = np.zeros((n_reads, 16), np.uint64)
 L = N.lib()
 L.unc_pool_debug_phases.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
-N.check(L.unc_pool_debug_phases(bm.h, n_reads, ph.ctypes.data))
+N.check(L.unc_pool_debug_phases(bm.h, n_reads, ph2.ctypes.data))
 names = ["A probs", "B extend + B1 deferred seed_prob", "B2 scan/ended rows/key compaction", "C radix sort + fix-up", "D dedup/src", "S sa + E", "X barrier(tracker)", "loop head"]
 ev = out["events_used"].astype(np.float64) + 1
-tot = ph.sum(axis=0).astype(np.float64)
-print("total events", ev.sum())
-for i, nm in enumerate(names):
-    print("%-36s %6.1f%%  %8.0f cycles/event" % (nm, 100 * tot[i] / tot.sum(), tot[i] / ev.sum()))
-print("cycles/event total %.0f" % (tot.sum() / ev.sum()))
-nm = out["mapped"] == 0
-print("non-mapping reads: cycles/event %.0f ; mapping: %.0f" % (ph[nm].sum() / ev[nm].sum(), ph[~nm].sum() / ev[~nm].sum()))
+for title, ph in (("worker warp 0, thread 0 (also runs the single-warp sections)", ph2[:, :8]),
+                  ("last worker warp, lane 0 (its barrier waits expose the single-warp sections)", ph2[:, 8:])):
+    tot = ph.sum(axis=0).astype(np.float64)
+    print("--", title)
+    print("total events", ev.sum())
+    for i, nm in enumerate(names):
+        print("%-36s %6.1f%%  %8.0f cycles/event" % (nm, 100 * tot[i] / max(tot.sum(), 1), tot[i] / ev.sum()))
+    print("cycles/event total %.0f" % (tot.sum() / ev.sum()))
+    nm_ = out["mapped"] == 0
+    print("non-mapping reads: cycles/event %.0f ; mapping: %.0f" % (ph[nm_].sum() / ev[nm_].sum(), ph[~nm_].sum() / ev[~nm_].sum()))

@@ -910,9 +910,14 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
 }
 
 #if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
-#define PT_DECL unsigned long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = clock64();
-#define PT_MARK(i) { long long _n = clock64(); pt_acc[i] += (unsigned long long) (_n - pt_t); pt_t = _n; }
-#define PT_FLUSH(B, r) if (wt == 0 && (B).dbg) { for (int _i = 0; _i < 8; _i++) (B).dbg[(size_t) (r) * 8 + _i] = pt_acc[_i]; }
+// cycle counter with a compiler memory barrier, so that loads/stores of a phase are not scheduled across a mark
+UNC_DEV long long pt_clock() { long long v; asm volatile("mov.u64 %0, %%clock64;" : "=l"(v) :: "memory"); return v; }
+#define PT_DECL unsigned long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = pt_clock();
+#define PT_MARK(i) { long long _n = pt_clock(); pt_acc[i] += (unsigned long long) (_n - pt_t); pt_t = _n; }
+// two observers per read: thread 0 of worker warp 0 (which also runs the single-warp sections: chunk scan,
+// ended rows, fresh sources) -> counters 0..7, and lane 0 of the LAST worker warp (never runs them, so its
+// barrier waits expose them) -> counters 8..15
+#define PT_FLUSH(B, r) if ((B).dbg && (wt == 0 || wt == nwt - 32u)) { for (int _i = 0; _i < 8; _i++) (B).dbg[(size_t) (r) * 16 + (wt == 0 ? 0 : 8) + _i] = pt_acc[_i]; }
 #else
 #define PT_DECL
 #define PT_MARK(i)

@@ -81,3 +81,64 @@ def test_map_pool_i16_reads_and_filters(example_prefix, golden_read, tmp_path):
     out = pool.update()
     pool.stop()
     assert len(out) == 1 and out[0].fields()[1:] == GOLD["default"]["fields"][1:]
+
+
+def test_realtime_pool_surface_and_constants():
+    from uncalled_b200.api import Chunk, Conf, RealtimePool
+    assert (RealtimePool.DEPLETE, RealtimePool.ENRICH) == (0, 1) and (RealtimePool.FULL, RealtimePool.EVEN, RealtimePool.ODD) == (0, 1, 2)
+    for name in ("host", "port", "duration"):                 # uncalled/args.py:223-260 reads these docstrings
+        assert getattr(Conf, name).__doc__
+    c = Chunk("r", 3, 7, 100, np.arange(10, dtype=np.float32), 2, 100)   # clipped like Chunk::Chunk (chunk.cpp:74-83)
+    assert (c.channel, c.number, c.size(), c.empty()) == (3, 7, 8, False)
+    assert np.array_equal(c.pop(), np.arange(2, 10, dtype=np.float32)) and c.empty()
+
+
+def test_realtime_pool_chunk_protocol_with_emulated_device():
+    """RealtimePool driven like the reference's simulator: try_add_chunk per channel with the next chunk (an empty
+    one when the read has no more signal), update() for the finished reads -- on the EMULATED device code, against
+    the oracle's streaming restatement (reads following each other on a channel share its Mapper)."""
+    import emulib
+    import orclib
+    import synth
+    import synthdata
+    from uncalled_b200.api import Chunk, Conf, RealtimePool
+    prefix, g = synthdata.get_index("g200k")
+    E, O = emulib.Emu(prefix), orclib.Oracle(prefix)
+    conf = Conf()
+    conf.num_channels, conf.chunk_time = 2, 0.1125
+    backend = emulib.EmuStream(E, 2, 450)
+
+    class _Idx:
+        seqs = [(O.lib.orc_seq_name(O.idx, i).decode(), int(O.lib.orc_seq_len(O.idx, i))) for i in range(O.lib.orc_n_seqs(O.idx))]
+    pool = RealtimePool(conf, backend=backend, index=_Idx)
+    sig, _ = synth.reads(g, 4, 4000, seed=21, frac_random=0.25)
+    reads = {0: [0, 2], 1: [1, 3]}                       # channel -> reads, one after the other
+    pos = {0: [0, 0], 1: [0, 0]}                         # [index into reads[ch], next chunk]
+    results = {}
+    for _ in range(200):
+        for ch in (0, 1):
+            if pos[ch][0] >= len(reads[ch]):
+                continue
+            i, k = reads[ch][pos[ch][0]], pos[ch][1]
+            nfull = len(sig[i]) // 450
+            c = Chunk("read%d" % i, ch + 1, i + 1, k * 450, sig[i], k * 450, 450) if k < nfull else Chunk("read%d" % i, ch + 1, i + 1, 0, [])
+            if pool.try_add_chunk(c) or c.empty():
+                pos[ch][1] += 1
+        for channel, number, paf in pool.update():
+            results[number - 1] = paf
+            ch = channel - 1
+            pos[ch] = [pos[ch][0] + 1, 0]
+        if len(results) == 4:
+            break
+    assert pool.all_finished() and len(results) == 4
+    pool.stop_all()
+    for ch in (0, 1):
+        want = O.stream_channel([sig[i] for i in reads[ch]], 450)
+        for i, (rec, nu, en) in zip(reads[ch], want):
+            p = results[i]
+            assert p.is_mapped() == bool(rec.mapped) and p.is_ended() == bool(en), i
+            assert p.rd_len == rec.rd_len, i
+            if rec.mapped:
+                assert (p.rd_st, p.rd_en, p.rf_st, p.rf_en, p.matches, p.fwd) == \
+                       (rec.rd_st, rec.rd_en, rec.rf_st, rec.rf_en, rec.matches, bool(rec.fwd)), i
+                assert p.fields()[0] == "read%d" % i and p.int_tags[0] == (4, ch + 1)

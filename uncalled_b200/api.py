@@ -47,6 +47,12 @@ class Conf:
         "read_list": ("", "Only map reads listed in this file"),
         "max_reads": (0, "Maximum number of reads to map"),
         "max_buffer": (100, "Maximum number of reads to store in memory"),
+        "realtime_mode": (0, "RealtimePool.DEPLETE or RealtimePool.ENRICH"),
+        "active_chs": (0, "RealtimePool.FULL, EVEN or ODD"),
+        "host": ("127.0.0.1", "MinKNOW host address"),
+        "port": (8000, "MinKNOW port"),
+        "duration": (72.0, "Duration to map real-time run in hours"),
+        "max_active_reads": (512, "Maximum number of reads being mapped at once"),
         "device": (0, "CUDA device of this process (one process per GPU)"),
         "batch_reads": (4096, "Reads per GPU batch"),
     }
@@ -148,6 +154,18 @@ class Paf:
 # export the enum values into class scope like pybind11's export_values() (read_buffer.hpp:104-112)
 for _t in Paf.Tag:
     setattr(Paf, _t.name, _t)
+
+
+def _paf_from_rec(seqs, rec, read_id, channel, start):
+    """Paf as Mapper::set_ref_loc / set_failed leave it (reference src/mapper.cpp:365-372,708-728)."""
+    g = (lambda k: rec[k]) if isinstance(rec, np.void) else (lambda k: getattr(rec, k))
+    p = Paf(read_id, channel, start)
+    p.set_read_len(int(g("rd_len")))
+    if g("mapped"):
+        rid = int(g("rid"))
+        name = seqs[rid][0] if 0 <= rid < len(seqs) else ""
+        p.set_mapped(g("rd_st"), g("rd_en"), name, g("rf_st"), g("rf_en"), g("rf_len"), bool(g("fwd")), int(g("matches")))
+    return p
 
 
 class _Read:
@@ -253,13 +271,7 @@ class MapPool:
             recs = self._mapper.map(flat, d)
             ms = (time.time() - t0) * 1e3 / len(batch)
             for r, rec in zip(batch, recs):
-                p = Paf(r.id, r.channel, r.start)
-                p.set_read_len(int(rec["rd_len"]))
-                if rec["mapped"]:
-                    rid = int(rec["rid"])
-                    name = self.index.seqs[rid][0] if 0 <= rid < len(self.index.seqs) else ""
-                    p.set_mapped(rec["rd_st"], rec["rd_en"], name, rec["rf_st"], rec["rf_en"], rec["rf_len"],
-                                 bool(rec["fwd"]), int(rec["matches"]))
+                p = _paf_from_rec(self.index.seqs, rec, r.id, r.channel, r.start)
                 p.set_float(Paf.Tag.MAP_TIME, ms)
                 out.append(p)
         n = min(len(self._queue), self.conf.batch_reads)
@@ -274,3 +286,162 @@ class MapPool:
         if self._mapper is not None:
             self._mapper.close()
             self._mapper = None
+
+
+class Chunk:
+    """reference src/chunk.hpp:33-81 (the vector<float> constructor form and the accessors pybind exports)."""
+
+    def __init__(self, read_id="", channel=1, number=0, start=0, raw_data=(), raw_st=0, raw_len=None):
+        raw = np.asarray(raw_data, dtype=np.float32)
+        if raw_len is None:
+            raw_len = len(raw) - raw_st
+        if raw_st + raw_len > len(raw):                   # Chunk::Chunk clips to the signal (src/chunk.cpp:74-83)
+            raw_len = len(raw) - raw_st
+        self.id, self.channel, self.number, self.start = read_id, int(channel), int(number), int(start)
+        self._raw = np.ascontiguousarray(raw[raw_st:raw_st + raw_len])
+
+    def size(self):
+        return len(self._raw)
+
+    def empty(self):
+        return len(self._raw) == 0
+
+    def pop(self):
+        r, self._raw = self._raw, np.zeros(0, np.float32)
+        return r
+
+    def swap(self, other):
+        self.__dict__, other.__dict__ = other.__dict__, self.__dict__
+
+    def print(self):
+        for v in self._raw:
+            print(v)
+
+
+class RealtimePool:
+    """reference src/realtime_pool.hpp:33-91: RealtimePool(conf), add_chunk, try_add_chunk, update() ->
+    [(channel, read number, Paf)], all_finished(), stop_all(), and the mode constants the CLI parser needs
+    (uncalled/args.py:160-187).  One persistent device-side mapper state per channel (StreamMapper) replaces
+    the per-channel Mapper objects and the worker threads; update() maps the buffered chunks of all channels
+    in one unc_stream_step call.  `backend`/`index` exist so the CPU tests can drive this class with the
+    emulated device code."""
+
+    DEPLETE, ENRICH = 0, 1                 # RealtimeParams::Mode
+    FULL, EVEN, ODD = 0, 1, 2              # RealtimeParams::ActiveChs
+
+    def __init__(self, conf, backend=None, index=None):
+        from . import stream as S
+        self.conf, self._S = conf, S
+        self.chunk_len = int(np.float32(conf.chunk_time) * np.float32(conf.sample_rate)) & 0xFFFF   # u16 chunk_len()
+        if backend is None:
+            if not conf.bwa_prefix:
+                raise RuntimeError("Conf.bwa_prefix is not set")
+            index = Index(conf.bwa_prefix, preset=conf.idx_preset, device=conf.device, model_table=conf.model_path or None)
+            p = N.default_params()
+            p.max_events, p.max_paths, p.seed_len = conf.max_events, conf.max_paths, conf.seed_len
+            p.bp_per_sec, p.sample_rate = conf.bp_per_sec, conf.sample_rate
+            backend = S.StreamMapper(index, conf.num_channels, self.chunk_len, max_chunks=conf.max_chunks, params=p)
+        self.backend, self.index = backend, index
+        n = conf.num_channels
+        self._pending = [None] * n          # chunk waiting for the next update()
+        self._read = [None] * n             # (id, number, start) of the read in progress
+        self._fresh = [False] * n           # the pending chunk starts a read
+        self._reset = [False] * n           # request_reset: the read in progress gets no more signal
+        self._stopped = False
+
+    def _active(self, ch):
+        return self._read[ch] is not None
+
+    def add_chunk(self, c):
+        """RealtimePool::add_chunk (src/realtime_pool.cpp:74-101)."""
+        ch = c.channel - 1
+        if self._stopped or not (0 <= ch < self.conf.num_channels):
+            return False
+        if self._active(ch) and self._read[ch][1] != c.number:
+            # a different read arrived while the previous one is mapping: it is reset and the chunk is buffered
+            self._reset[ch] = True
+            self._pending[ch], self._fresh[ch] = c, True
+            return True
+        if not self._active(ch):
+            self._pending[ch], self._fresh[ch] = c, True
+            return True
+        if self._pending[ch] is not None:   # Mapper::add_chunk refuses while the previous chunk is unprocessed
+            return False
+        self._pending[ch], self._fresh[ch] = c, False
+        return True
+
+    def try_add_chunk(self, c):
+        """RealtimePool::try_add_chunk (src/realtime_pool.cpp:108-139): an empty chunk means the read has no more signal."""
+        ch = c.channel - 1
+        if self._stopped or not (0 <= ch < self.conf.num_channels):
+            return False
+        if c.empty():
+            if self._active(ch) and self._pending[ch] is None:
+                self._reset[ch] = True
+            return False
+        if not self._active(ch):
+            if self._pending[ch] is not None:
+                return False
+            self._pending[ch], self._fresh[ch] = c, True
+            return True
+        if self._read[ch][1] == c.number and self._pending[ch] is None:
+            self._pending[ch], self._fresh[ch] = c, False
+            return True
+        return False
+
+    def update(self):
+        """Maps every buffered chunk (one step) and returns the reads that finished: [(channel, number, Paf)]."""
+        S = self._S
+        if self._stopped:
+            return []
+        out = []
+        for phase in (0, 1):                # phase 0: resets of reads in progress; phase 1: the buffered chunks
+            descs, parts, chans, off = [], [], [], 0
+            for ch in range(self.conf.num_channels):
+                d = S.ChunkDesc()
+                d.channel, d.dtype = ch, 0
+                d.cal_range, d.cal_offset, d.cal_digit = 1.0, 0.0, 1.0
+                if phase == 0:
+                    if not (self._reset[ch] and self._active(ch)):
+                        continue
+                    d.new_read, d.offset, d.n_samples = 0, 0, 0
+                else:
+                    c = self._pending[ch]
+                    if c is None:
+                        continue
+                    raw = c.pop()
+                    d.new_read, d.offset, d.n_samples = (1 if self._fresh[ch] else 0), off, len(raw)
+                    if self._fresh[ch]:
+                        self._read[ch] = (c.id, c.number, c.start)
+                    parts.append(raw)
+                    off += len(raw)
+                    self._pending[ch] = None
+                descs.append(d)
+                chans.append(ch)
+            if not descs:
+                continue
+            arr = (S.ChunkDesc * len(descs))(*descs)
+            flat = np.concatenate(parts) if parts else np.zeros(1, np.float32)
+            res = (S.StreamResult * len(descs))()
+            self.backend.step(arr, len(descs), flat, res)
+            for ch, r in zip(chans, res):
+                if phase == 0:
+                    self._reset[ch] = False
+                if r.state == S.MAPPING or self._read[ch] is None:
+                    continue
+                rid, number, start = self._read[ch]
+                p = _paf_from_rec(self.index.seqs if self.index is not None else [], r.rec, rid, ch + 1, start)
+                if r.ended:
+                    p._ended = True        # Paf::set_ended
+                out.append((ch + 1, number, p))
+                self._read[ch] = None       # Mapper::deactivate
+        return out
+
+    def all_finished(self):
+        return all(r is None for r in self._read) and all(p is None for p in self._pending)
+
+    def stop_all(self):
+        if not self._stopped:
+            self._stopped = True
+            if hasattr(self.backend, "close"):
+                self.backend.close()

@@ -24,8 +24,9 @@
 // samples stream through; a read that fails it (or has >= 2^24 samples) is flagged and redone
 // by the serial routine unc_k1_read (k1_fallback kernel), so results never depend on it.
 // Divisions by the constant window lengths use the exactly-rounded Markstein sequence
-// (q = a*r; q' = fma(fma(-w, q, a), r, q), r = RN(1/w)); tests/test_k1_arith.py checks it
-// exhaustively (float) and on 10^9 random operands (double) against IEEE division.
+// (q = a*r; q' = fma(fma(-w, q, a), r, q), r = RN(1/w)); tests/arith/k1_arith_check.c
+// (run by tests/test_k1_emul.py) checks it exhaustively over all 2^32 floats and on 6*10^8 random doubles against
+// IEEE division; below 2^-100, where subnormal quotients can tie, the IEEE division is used.
 #pragma once
 #include "unc_device.cuh"
 

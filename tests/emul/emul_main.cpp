@@ -137,7 +137,7 @@ int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads,
     W.paths = paths.data(); W.hist = hist.data(); W.wlist = wlist.data(); W.ckey = ckey.data(); W.cks = cks.data(); W.elist = elist.data(); W.order = order.data(); W.rlist = rlist.data();
     W.clu = clu.data(); W.dir = dir.data();
     W.max_blocks = max_blocks; W.rl_cap = rl_cap;
-    K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((maxp + 31) / 32) * 24);
+    K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((maxp + 31) / 32) * K2_DYN_PER_CHUNK);
     CtaArgs a = {&e->ix, &dp, &B, &W, sh};
     emu_run_cta(cta_entry, &a, 32 * (n_warps > 0 ? n_warps : 8));   // one persistent CTA maps the whole batch
     free(sh);
@@ -250,7 +250,7 @@ int emu_stream_step(void *pst, const unc_chunk_desc *chunks, uint32_t n, const v
             unc_stream_chunk(B, T->dp, S, r, isnew[r]);
             tot[r] = T->sig[chan[r]].evdt.total_events;
         }
-        K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((T->dp.max_paths + 31) / 32) * 24);
+        K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((T->dp.max_paths + 31) / 32) * K2_DYN_PER_CHUNK);
         StreamCtaArgs a = {&T->e->ix, &T->dp, &B, &T->W, &T->S, sh};
         emu_run_cta(stream_cta_entry, &a, 32 * (n_warps > 0 ? n_warps : 8));
         free(sh);

@@ -59,49 +59,54 @@ def make_descs(lens, dtype=0, cal=(1.0, 0.0, 1.0)):
     return d
 
 
-def build():
+def build(extra_flags=(), tag=""):
+    """Compiles the device source for the host.  extra_flags/tag build a variant (e.g. -DK2_LEAN_B) next to the default."""
     src = os.path.join(EMUL_DIR, "emul_main.cpp")
-    out = os.path.join(EMUL_DIR, "libunc_emul.so")
+    out = os.path.join(EMUL_DIR, "libunc_emul%s.so" % tag)
     deps = [src, os.path.join(EMUL_DIR, "warp_emul.hpp")] + \
            [os.path.join(ROOT, "uncalled_b200", "csrc", f) for f in
             ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_logic.hpp", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-DUNC_EMUL", "-DK2_MAXSEG=16u", "-fPIC", "-shared",
-                    "-I" + EMUL_DIR, "-I" + os.path.join(ROOT, "uncalled_b200", "csrc"), "-o", out, src],
+                    "-I" + EMUL_DIR, "-I" + os.path.join(ROOT, "uncalled_b200", "csrc"), "-o", out, src] + list(extra_flags),
                    check=True, capture_output=True)
     return out
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(build())
-        L.emu_index_load.restype = C.c_void_p
-        L.emu_index_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
-        L.emu_index_free.argtypes = [C.c_void_p]
-        L.emu_kmer_range.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-        L.emu_map_batch.argtypes = [C.c_void_p, C.POINTER(UncParams), C.POINTER(UncReadDesc), C.c_uint32, C.c_void_p,
-                                    C.POINTER(UncPaf), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_int, C.c_uint32, C.c_int]
-        L.emu_match_probs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
-        L.emu_sa.argtypes = [C.c_void_p, C.c_uint64]
-        L.emu_sa.restype = C.c_uint64
-        L.emu_k1_stats.argtypes = [C.c_void_p]
-        L.emu_stream_create.restype = C.c_void_p
-        L.emu_stream_create.argtypes = [C.c_void_p, C.POINTER(UncParams), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
-        L.emu_stream_free.argtypes = [C.c_void_p]
-        L.emu_stream_step.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
-        _lib = L
-    return _lib
+def _bind(L):
+    """argtypes of one loaded emulator library"""
+    L.emu_index_load.restype = C.c_void_p
+    L.emu_index_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    L.emu_index_free.argtypes = [C.c_void_p]
+    L.emu_kmer_range.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.emu_map_batch.argtypes = [C.c_void_p, C.POINTER(UncParams), C.POINTER(UncReadDesc), C.c_uint32, C.c_void_p,
+                                C.POINTER(UncPaf), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_int, C.c_uint32, C.c_int]
+    L.emu_match_probs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    L.emu_sa.argtypes = [C.c_void_p, C.c_uint64]
+    L.emu_sa.restype = C.c_uint64
+    L.emu_k1_stats.argtypes = [C.c_void_p]
+    L.emu_stream_create.restype = C.c_void_p
+    L.emu_stream_create.argtypes = [C.c_void_p, C.POINTER(UncParams), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.emu_stream_free.argtypes = [C.c_void_p]
+    L.emu_stream_step.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+    return L
+
+
+def lib(extra_flags=(), tag=""):
+    """The emulator library; (extra_flags, tag) select a compile-time variant of the device source."""
+    if tag not in _libs:
+        _libs[tag] = _bind(C.CDLL(build(extra_flags, tag)))
+    return _libs[tag]
 
 
 class Emu:
-    def __init__(self, prefix, preset="default"):
-        self.L = lib()
+    def __init__(self, prefix, preset="default", extra_flags=(), tag=""):
+        self.L = lib(extra_flags, tag)
         self.idx = self.L.emu_index_load(prefix.encode(), preset.encode(), MODEL_TABLE.encode())
         if not self.idx:
             raise RuntimeError("emu_index_load failed")

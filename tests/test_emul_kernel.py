@@ -65,6 +65,19 @@ def test_full_buffer_semantics(g200k, max_paths):
     _check(E, O, [sig[i] for i in range(4)])
 
 
+def test_register_lean_extension_variant(g200k):
+    """-DK2_LEAN_B (prototype for a higher-occupancy build: children written to fixed per-parent slots the moment
+    their base is resolved, Occ words read on demand) must produce the same paths, seeds and PAF records."""
+    prefix, g = g200k
+    E = emulib.Emu(prefix, extra_flags=("-DK2_LEAN_B",), tag="_lean")
+    O = orclib.Oracle(prefix)
+    sig, _ = synth.reads(g, 4, 3000, seed=3)
+    _check(E, O, [sig[i] for i in range(4)])
+    _check(E, O, [sig[i] for i in range(2)], n_warps=3)
+    E.params.max_paths = O.params.max_paths = 300
+    _check(E, O, [sig[i][:2500] for i in range(3)])
+
+
 def test_i16_calibration_path(g200k):
     prefix, g = g200k
     E, O = emulib.Emu(prefix), orclib.Oracle()

@@ -1,0 +1,23 @@
+#!/bin/bash
+# Builds the candidate configurations of the mapper kernel into uncalled_b200/variants/ for
+# tools/gpu_variants.py (one GPU call times them all on the bench workload and checks that their PAF
+# records are identical).  ptxas figures of round 1 (sm_100a, CUDA 12.9), k2_map:
+#   default                      124 regs, 0 B spilled   -> 2 CTAs x 8 warps / SM  (shipped)
+#   default   @ 3 CTAs (80 regs) 252 B spilled           -> measured 15-20 % slower
+#   K2_LEAN_B @ 3 CTAs (80 regs)   0 B spilled
+#   K2_LEAN_B @ 4 CTAs (64 regs)  32 B spilled           (also 2 CTAs x 16 warps)
+set -e
+cd "$(dirname "$0")/../uncalled_b200"
+F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 -Xcompiler -fPIC --shared -diag-suppress 550"
+mkdir -p variants
+build() { nvcc $F "${@:2}" -o "variants/$1.so" csrc/unc_abi.cu csrc/unc_index_build.cpp; }
+build base &
+build lean_c2 -DK2_LEAN_B -DK2_MIN_CTAS=2 &
+build lean_c3 -DK2_LEAN_B -DK2_MIN_CTAS=3 &
+build lean_c4 -DK2_LEAN_B -DK2_MIN_CTAS=4 &
+wait
+build lean_w16c2 -DK2_LEAN_B -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
+build lean_w12c2 -DK2_LEAN_B -DK2_WARPS=12 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
+build lean_occ_c3 -DK2_LEAN_B -DK2_MIN_CTAS=3 -DK2_SPIN_NS=20 &
+wait
+ls -la variants

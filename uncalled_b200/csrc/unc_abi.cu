@@ -343,7 +343,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     for (int i = 0; i < 6; i++) PT(cudaEventCreate(&P->ev[i]));
     cudaDeviceProp prop;
     PT(cudaGetDeviceProperties(&prop, idx->device));
-    P->smem = sizeof(K2Shared) + 16 + (size_t) ((prm->max_paths + 31) / 32) * 24;
+    P->smem = sizeof(K2Shared) + 16 + (size_t) ((prm->max_paths + 31) / 32) * K2_DYN_PER_CHUNK;
     PT(cudaFuncSetAttribute(k2_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
     int per_sm = 0;
     PT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_map, K2_THREADS, P->smem));

@@ -152,6 +152,21 @@ UNC_DEV u32 unc_occ_in_block(uint4 b0, uint4 b1, uint4 b2, uint4 b3, u32 kk, u32
     return cnt;
 }
 
+// Same count, reading the block's words from memory as they are needed (L1-resident after the first
+// touch) instead of holding the 64-byte block in 16 registers: the register-lean extension loop uses it.
+UNC_DEV u32 unc_occ_at(const uint4 *blk, u32 kk, u32 c) {
+    u32 cnt = d_ldg((const u32 *) blk + 2u * c);            // low word of the u64 cumulative count of base c
+    const u32 q = (kk & 127u) >> 5;                            // index of the 64-bit word holding symbol kk
+    const uint2 *wp = (const uint2 *) (blk + 2);
+    for (u32 i = 0; i <= q; i++) {
+        const uint2 v = d_ldg(wp + i);
+        const u64 w = ((u64) v.x << 32) | v.y;
+        const u64 m = i < q ? ~0ull : ~((1ull << ((~kk & 31u) << 1)) - 1ull);
+        cnt += (u32) d_popcll(unc_match_bits(w, c) & m);
+    }
+    return cnt;
+}
+
 struct OccBlock { uint4 b0, b1, b2, b3; };
 
 UNC_DEV OccBlock unc_load_block(const DevIndex &ix, u32 kk) {
@@ -731,6 +746,11 @@ UNC_DEV bool trk_get_final(const Tracker &t, const DevParams &p) {
 #define K2_MAXSEG 8u       /* max worker warps (sort segments) */
 #endif
 
+#ifdef K2_LEAN_B
+#define K2_DYN_PER_CHUNK 44u   /* pre 8 + agg 8 + bcnt 4 + ecnt 4 + cmb 20 bytes of dynamic shared memory per 32 paths */
+#else
+#define K2_DYN_PER_CHUNK 24u
+#endif
 struct K2Tables {
     uint2 kmer_range[UNC_NKMER];
     float thresh[64];
@@ -748,6 +768,7 @@ struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
     uint2 *agg;            // D1 aggregates of the k-mer run structure
     u64 *pre;              // D2 look-back prefix words: (epoch<<2 | state) << 32 | sources | seeds<<16
     u32 *bcnt, *ecnt;      // children per chunk (then exclusive prefix), ended paths per chunk
+    u32 *cmb;              // K2_LEAN_B: five ballot words per chunk (which fixed child slots are filled)
     u32 bc[8];             // CTA broadcast scalars
     u32 scan_tmp[32];
     u32 n_rows[2];         // worker -> tracker: seed rows of event e in rlist[e & 1]
@@ -806,7 +827,8 @@ UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *
         sh->pre = (u64 *) base; base += (size_t) n_slots * 8;
         sh->agg = (uint2 *) base; base += (size_t) n_slots * 8;
         sh->bcnt = (u32 *) base; base += (size_t) n_slots * 4;
-        sh->ecnt = (u32 *) base;
+        sh->ecnt = (u32 *) base; base += (size_t) n_slots * 4;
+        sh->cmb = (u32 *) base;                        // n_slots * 20 bytes (used by the K2_LEAN_B build only)
     }
     c_sync();
     for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) {
@@ -980,6 +1002,120 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         // ---- B. extend every previous path (reference src/mapper.cpp:455-524): chunk c of 32
         //      parents writes its children, in emission order, to records/keys [c*160, c*160+count)
         const u32 nch_prev = (prev_size + 31u) >> 5;
+#ifdef K2_LEAN_B
+        // Register-lean extension (prototype): every child is written the moment its base is resolved, to the
+        // FIXED slot c*160 + lane*5 + j (j = 0 stay, 1..4 moves), so no candidate arrays and no in-loop scan are
+        // live; which slots are filled is recorded as five ballot words per chunk (sh->cmb), from which the
+        // compaction and the ended-row pass derive the emission ranks.  Only the Occ block of row start-1 is held;
+        // the rare range that crosses an Occ block boundary fetches the second block per base.
+        {
+            u32 oi_n = UNC_INVALID; uint4 q0_n = make_uint4(0, 0, 0, 0);
+            if (ww < nch_prev) {
+                u32 pi = ww * 32 + (u32) lane;
+                if (pi < prev_size) oi_n = oprev[pi];
+                if (!(oi_n & UNC_INVALID)) q0_n = prev[(size_t) oi_n * 2];
+            }
+            for (u32 c = ww; c < nch_prev; c += nwk) {
+                const u32 oi = oi_n;
+                const uint4 q0 = q0_n;
+                const bool valid = !(oi & UNC_INVALID);
+                if (c + nwk < nch_prev) {
+                    u32 pi = (c + nwk) * 32 + (u32) lane;
+                    oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
+                    if (!(oi_n & UNC_INVALID)) q0_n = prev[(size_t) oi_n * 2];
+                }
+                const u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
+                const u32 moves = q0.w & UNC_PATH_MASK, sa_checked = q0.w >> 31;
+                u32 cmask = 0;
+                float parent_sp = 0.0f;
+                if (valid) {
+                    const uint4 q1 = prev[(size_t) oi * 2 + 1];          // same 32-byte record as q0
+                    parent_sp = u2f(q1.x);
+                    const float prevC = u2f(q1.y);
+                    const float thr = tb->thresh[32 + d_clz(en - st + 1u)];
+                    const u32 cbase = c * K2_CH_SLOTS + (u32) lane * 5u;
+                    const u32 nlen = plen + (plen < UNC_SEED_LEN ? 1u : 0u);
+                    // Occ block of row start-1: read word by word when a base wants it (unc_occ_at)
+                    bool have_bk = false;
+                    const u32 k0 = st - 1u, l0 = en;
+                    const u32 kk = k0 - (k0 >= ix.primary), ll = l0 - (l0 >= ix.primary);
+                    const bool l_is_end = (l0 == ix.seq_len);
+                    for (u32 j = 0; j < 5; j++) {
+                        const u32 ckm = j == 0 ? kmer : ((((kmer << 2) & UNC_KMASK)) | (j - 1u));
+                        const float pb = sh->probs[ckm];
+                        u32 cst = st, cen = en;
+                        if (j == 0) {
+                            if (!(stays < p.max_consec_stay && pb >= thr)) continue;
+                        } else {
+                            if (pb < thr) continue;                       // `if (prob < thresh) continue;`
+                            const u32 bs = j - 1u;
+                            if (!have_bk) { have_bk = true; pend_blocks++; }
+                            const uint4 *blk = ix.bwt + ((size_t) (kk >> 7) << 2);
+                            const u32 ok = unc_occ_at(blk, kk, bs);
+                            u32 ol;
+                            if (l_is_end) ol = unc_L2(ix, bs + 1) - unc_L2(ix, bs);
+                            else {
+                                if ((ll >> 7) != (kk >> 7) && !((cmask >> 5) & 1u)) { pend_blocks++; cmask |= 1u << 5; }   // second block, counted once
+                                ol = unc_occ_at(ix.bwt + ((size_t) (ll >> 7) << 2), ll, bs);
+                            }
+                            cst = unc_L2(ix, bs) + ok + 1u;
+                            cen = unc_L2(ix, bs) + ol;
+                            if (cst > cen) continue;
+                        }
+                        const u32 move = j > 0 ? 1u : 0u;
+                        const u32 ci = cbase + j;
+                        u32 nmoves = ((moves << 1) | move) & UNC_PATH_MASK;
+                        const u32 nstays = move ? 0u : stays + 1u;
+                        const float newC = f_add(prevC, pb);
+                        float sp = 0.0f;
+                        bool seedable = false;
+                        if (plen == UNC_SEED_LEN) {
+                            nmoves |= UNC_PATH_TAIL;
+                            W.wlist[s_atomic_add(&sh->wl_cnt, 1u)] = make_uint4(ci, oi, f2u(newC), nmoves);
+                        } else {
+                            sp = f_div(newC, (float) nlen);
+                            const u32 cmc = (u32) d_popc(nmoves);
+                            seedable = nlen == UNC_SEED_LEN && sp >= p.min_seed_prob && cst == cen && (nmoves & 1u) &&
+                                       (float) ((nlen - cmc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f);
+                        }
+                        const u32 spb = f2u(sp);
+                        next[(size_t) ci * 2] = make_uint4(cst, cen, ckm | (nlen << 16) | (nstays << 24), nmoves | (sa_checked << 31));
+                        next[(size_t) ci * 2 + 1] = make_uint4(spb, f2u(newC), 0u, 0u);
+                        hist_e[ci] = make_uint2(f2u(newC), oi);
+                        cks[ci] = make_uint4(cst, cen, spb, ckm | (seedable ? 1u << 10 : 0u) | ((u32) d_popc(nmoves) << 11) | (ci << 16));
+                        cmask |= 1u << j;
+                    }
+                    cmask &= 31u;
+                }
+                // which of the chunk's 160 fixed slots are filled: one ballot word per child index
+                u32 total = 0, w[5];
+#pragma unroll
+                for (u32 j = 0; j < 5; j++) { w[j] = w_ballot((cmask >> j) & 1u); total += (u32) d_popc(w[j]); }
+                // a childless, not yet SA-checked path may end here with seeds
+                // (reference src/mapper.cpp:513-519 -> update_seeds(path, true), is_seed_valid :842-863)
+                bool ended = false;
+                const u32 mc = (u32) d_popc(moves);
+                if (valid && cmask == 0 && !sa_checked) {
+                    const u32 len = en - st + 1u;
+                    ended = plen == UNC_SEED_LEN && parent_sp >= p.min_seed_prob &&
+                            ((len == 1 && (moves & 1u) && (float) ((plen - mc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f)) ||
+                             (len <= p.max_rep_copy && mc >= p.min_rep_len));
+                }
+                const u32 m_ended = w_ballot(ended);
+                if (ended) {   // children of the earlier lanes of the chunk = the rank the dense layout would have given
+                    u32 off = 0;
+#pragma unroll
+                    for (u32 j = 0; j < 5; j++) off += (u32) d_popc(w[j] & lt);
+                    W.elist[(size_t) c * 32 + (u32) d_popc(m_ended & lt)] = make_uint4(st, en, mc, off);
+                }
+                if (lane == 0) {
+                    sh->bcnt[c] = total; sh->ecnt[c] = (u32) d_popc(m_ended);
+#pragma unroll
+                    for (u32 j = 0; j < 5; j++) sh->cmb[c * 5u + j] = w[j];
+                }
+            }
+        }
+#else
         {
 #ifdef K2_OCC_STAGE
             // three-stage software pipeline per warp: (order entry, record head) two chunks ahead in
@@ -1125,6 +1261,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 }
             }
         }
+#endif
         c_sync_sub(1, (int) nwt);
         // ---- B1 + B2a, concurrently.  Worker warp 0: exclusive scan of the chunk counts (restores the
         //      global emission order and gives the buffer cap, reference src/mapper.cpp:480-482,507-509,
@@ -1200,6 +1337,33 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             // compact the chunk-local keys into emission order: each warp copies the chunks it
             // extended (their keys are still in its L1) to [bcnt[c], bcnt[c+1]) -- coalesced on both
             // sides -- and counts the first radix digit for the destination's sort segment
+#ifdef K2_LEAN_B
+            // fixed-slot layout: lane L's children sit at c*160 + L*5 + j; their emission ranks come from the
+            // chunk's five ballot words (lane-major, then j -- the order the dense layout had)
+            for (u32 c = ww; c < nch_prev; c += nwk) {
+                const u32 base = sh->bcnt[c];
+                if (base >= nc) break;                              // later chunks lie beyond the max_paths cut
+                u32 rank = 0, mine = 0;
+#pragma unroll
+                for (u32 j = 0; j < 5; j++) {
+                    const u32 wj = sh->cmb[c * 5u + j];
+                    rank += (u32) d_popc(wj & lt);
+                    mine |= ((wj >> lane) & 1u) << j;
+                }
+                u32 seg = base / seg_len, bound = (seg + 1u) * seg_len;
+                for (u32 j = 0; j < 5; j++) {
+                    if (!((mine >> j) & 1u)) continue;
+                    const u32 di = base + rank++;
+                    if (di < nc) {
+                        uint4 key = cks[(size_t) c * K2_CH_SLOTS + (u32) lane * 5u + j];
+                        ckA[di] = key;
+                        while (di >= bound) { seg++; bound += seg_len; }
+                        s_atomic_add(&sh->hist_next[(key.x & (K2_RB - 1u)) * K2_MAXSEG + seg], 1u);
+                    }
+                }
+            }
+        }
+#else
             for (u32 c = ww; c < nch_prev; c += nwk) {
                 const u32 base = sh->bcnt[c];
                 if (base >= nc) break;                              // later chunks lie beyond the max_paths cut
@@ -1216,6 +1380,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 }
             }
         }
+#endif
         c_sync_sub(1, (int) nwt);
         u32 n_rows = sh->bc[3];
         if (n_rows > W.rl_cap) n_rows = W.rl_cap;

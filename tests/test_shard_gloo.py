@@ -47,6 +47,11 @@ def test_two_rank_sharding():
     assert [shard.shard_bounds(11, 2, r) for r in range(2)] == [(0, 6), (6, 11)]
     assert [shard.shard_bounds(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert shard.shard_bounds(0, 3, 1) == (0, 0)
+    # streaming: channel c lives on rank c mod world; every channel has exactly one owner and a dense local index
+    owners = [shard.channel_owner(c, 8) for c in range(512)]
+    assert owners[:10] == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1] and all(owners.count(r) == 64 for r in range(8))
+    chans, local = shard.local_channels(512, 8, 3)
+    assert chans[:3] == [3, 11, 19] and local[19] == 2 and len(chans) == 64
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

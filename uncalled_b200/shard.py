@@ -12,6 +12,18 @@ def shard_bounds(n_reads, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def channel_owner(channel, world):
+    """Streaming path: channel `c` (0-based) lives on rank c mod world -- its persistent device state (detector,
+    normaliser, path buffers, seed clusters) never moves, so chunks need no cross-rank exchange either."""
+    return int(channel) % int(world)
+
+
+def local_channels(n_channels, world, rank):
+    """The channels a rank owns, and their local (dense) indices on that rank's StreamMapper."""
+    chans = list(range(int(rank), int(n_channels), int(world)))
+    return chans, {c: i for i, c in enumerate(chans)}
+
+
 def max_over_ranks(value, dist=None, device=None):
     """Max of a python float over all ranks (identity when torch.distributed is not initialised)."""
     if dist is None or not dist.is_initialized():

@@ -65,11 +65,13 @@ def test_full_buffer_semantics(g200k, max_paths):
     _check(E, O, [sig[i] for i in range(4)])
 
 
-def test_register_lean_extension_variant(g200k):
-    """-DK2_LEAN_B (prototype for a higher-occupancy build: children written to fixed per-parent slots the moment
-    their base is resolved, Occ words read on demand) must produce the same paths, seeds and PAF records."""
+@pytest.mark.parametrize("flags,tag", [(("-DK2_LEAN_B",), "_lean"), (("-DK2_LEAN_B", "-DK2_PAR_E"), "_lean_pare")])
+def test_prototype_variants_keep_parity(g200k, flags, tag):
+    """Compile-time prototypes for a higher-occupancy build must produce the same paths, seeds and PAF records:
+    -DK2_LEAN_B (children written to fixed per-parent slots the moment their base is resolved, Occ words read on
+    demand) and -DK2_PAR_E (the fresh-source walk spread over all worker warps with the serial walk's buffer cut)."""
     prefix, g = g200k
-    E = emulib.Emu(prefix, extra_flags=("-DK2_LEAN_B",), tag="_lean")
+    E = emulib.Emu(prefix, extra_flags=flags, tag=tag)
     O = orclib.Oracle(prefix)
     sig, _ = synth.reads(g, 4, 3000, seed=3)
     _check(E, O, [sig[i] for i in range(4)])

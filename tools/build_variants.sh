@@ -18,6 +18,7 @@ build lean_c4 -DK2_LEAN_B -DK2_MIN_CTAS=4 &
 wait
 build lean_w16c2 -DK2_LEAN_B -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
 build lean_w12c2 -DK2_LEAN_B -DK2_WARPS=12 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
-build lean_occ_c3 -DK2_LEAN_B -DK2_MIN_CTAS=3 -DK2_SPIN_NS=20 &
+build lean_pare_c3 -DK2_LEAN_B -DK2_PAR_E -DK2_MIN_CTAS=3 &
+build lean_pare_w16c2 -DK2_LEAN_B -DK2_PAR_E -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
 wait
 ls -la variants

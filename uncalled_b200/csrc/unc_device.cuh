@@ -1638,6 +1638,51 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             e.x = ix.seq_len - unc_sa_lookup(ix, e.x, &pend_steps, &pend_blocks);
             rlist[i] = e;
         }
+#ifdef K2_PAR_E
+        // ---- E. fresh sources (reference src/mapper.cpp:605-624), all worker warps (prototype).  The serial
+        //      walk over the 1024 k-mers stops when the buffer fills; here word j (32 k-mers) is owned by warp
+        //      j % nwk: E1 publishes each word's candidate mask, a prefix over the 32 counts gives every word the
+        //      buffer fill level the serial walk would have had when it reached it, E2 applies the same cut.
+        for (u32 j = ww; j < 32; j += nwk) {
+            const u32 k = j * 32 + (u32) lane;
+            const uint2 kr = tb->kmer_range[k];
+            const bool add = !((sh->flags[j] >> lane) & 1u) && sh->probs[k] >= source_prob && kr.x <= kr.y;
+            const u32 m_add = w_ballot(add);
+            if (lane == 0) sh->scan_tmp[j] = m_add;
+        }
+        c_sync_sub(1, (int) nwt);
+        {
+            const u32 my_cnt = (u32) d_popc(sh->scan_tmp[lane]);
+            u32 tot_add;
+            const u32 my_pre = w_exscan(my_cnt, &tot_add);
+            const u32 nn0 = nn;
+            for (u32 j = ww; j < 32; j += nwk) {
+                const u32 before = nn0 + w_shfl(my_pre, (int) j);   // fill level when the serial walk reaches word j
+                if (before >= maxp) continue;                         // never visited: its flags stay as they are
+                const u32 k = j * 32 + (u32) lane;
+                const u32 fw = sh->flags[j];
+                u32 m_add = sh->scan_tmp[j];
+                const u32 room = maxp - before;
+                u32 visited = 0xFFFFFFFFu;
+                if ((u32) d_popc(m_add) >= room) {
+                    u32 mm = m_add;
+                    for (u32 q = 1; q < room; q++) mm &= mm - 1;
+                    int last = d_ffs(mm) - 1;
+                    visited = last == 31 ? 0xFFFFFFFFu : ((2u << last) - 1u);
+                    m_add &= visited;
+                }
+                const u32 rank = (u32) d_popc(m_add & lt);
+                if ((m_add >> lane) & 1u) {
+                    const uint2 kr = tb->kmer_range[k];
+                    write_source(next, hist_e, S0 + before + rank, kr.x, kr.y, k, sh->probs[k]);
+                    onext[before + rank] = S0 + before + rank;
+                }
+                if (lane == 0) sh->flags[j] = fw & ~visited;
+            }
+            nn = nn0 + tot_add < maxp ? nn0 + tot_add : maxp;
+            if (ww == 0 && lane == 0) { sh->bc[1] = nn; *(volatile u32 *) &sh->n_rows[event_i & 1u] = n_rows; }
+        }
+#else
         if (ww == 0) {
             // ---- E. fresh sources for every sufficiently probable k-mer without one
             //         (reference src/mapper.cpp:605-624)
@@ -1669,6 +1714,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             }
             if (lane == 0) { sh->bc[1] = nn; *(volatile u32 *) &sh->n_rows[event_i & 1u] = n_rows; }
         }
+#endif
         PT_MARK(5)
         // ---- hand the event's seeds to the tracker; learn the outcome of the previous event
         c_sync();                                                     // X_e

@@ -21,4 +21,9 @@ build lean_w12c2 -DK2_LEAN_B -DK2_WARPS=12 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
 build lean_pare_c3 -DK2_LEAN_B -DK2_PAR_E -DK2_MIN_CTAS=3 &
 build lean_pare_w16c2 -DK2_LEAN_B -DK2_PAR_E -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
 wait
-ls -la variants
+# phase-timing builds (tools/gpu_phases.py <genome> <reads> <lib>)
+mkdir -p variants_pt
+nvcc $F -DUNC_PHASE_TIMING -DK2_LEAN_B -DK2_PAR_E -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 -o variants_pt/lean_pare_w16c2.so csrc/unc_abi.cu csrc/unc_index_build.cpp &
+nvcc $F -DUNC_PHASE_TIMING -DK2_LEAN_B -DK2_MIN_CTAS=3 -o variants_pt/lean_c3.so csrc/unc_abi.cu csrc/unc_index_build.cpp &
+wait
+ls -la variants variants_pt

@@ -25,6 +25,22 @@ def test_struct_layouts_match_header():
     assert C.sizeof(N.ReadDesc) == 32 and C.sizeof(N.PafRec) == 120 and C.sizeof(N.Params) == 80
 
 
+def test_header_is_plain_c_and_stream_structs_match(tmp_path):
+    """include/unc_b200.h must be usable from C (it is the drop-in boundary), and the ctypes mirrors of the
+    streaming structs must have the layout the header declares."""
+    import subprocess
+    from uncalled_b200 import stream as S
+    src = tmp_path / "hdr.c"
+    src.write_text('#include <stdio.h>\n#include "unc_b200.h"\nint main(void) { printf("%zu %zu %zu\\n", '
+                   'sizeof(unc_chunk_desc), sizeof(unc_stream_result), sizeof(unc_timing)); return 0; }\n')
+    exe = tmp_path / "hdr"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-o", str(exe), str(src)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    from uncalled_b200 import _native as N
+    assert sizes == [C.sizeof(S.ChunkDesc), C.sizeof(S.StreamResult), C.sizeof(N.Timing)]
+
+
 def test_defaults_mirror_reference_params():
     from uncalled_b200 import _native as N
     p = N.default_params()

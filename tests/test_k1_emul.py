@@ -90,3 +90,22 @@ def test_inexact_sums_fall_back_to_the_serial_routine(emu):
     c = np.full(3000, 87.25, np.float32); c[1500:] = 90.5
     st = _check(emu, [s, z, c, t, sig[1]])
     assert st[3] == 2
+
+
+def test_non_finite_samples_take_the_serial_path(emu):
+    """NaN / Inf samples (a corrupt read) must neither hang nor diverge: the exactness check sends the read to the
+    serial routine, whose arithmetic is the reference's."""
+    import orclib
+    import synth
+    import synthdata
+    prefix, g = synthdata.get_index("g200k")
+    sig, _ = synth.reads(g, 2, 3000, seed=8)
+    a = sig[0].copy(); a[700] = np.nan
+    b = sig[1].copy(); b[100] = np.inf; b[2000] = -np.inf
+    recs, ev, nm, mel = emu.map_batch([a, b], run_k2=False)
+    import emulib
+    assert emulib.k1_stats()[3] == 2
+    O = orclib.Oracle()
+    for i, s in enumerate((a, b)):
+        m, _, _, omel = O.detect(s)
+        assert len(m) == len(ev[i]) and np.array_equal(m, ev[i], equal_nan=True), i

@@ -73,9 +73,9 @@ def test_prototype_variants_keep_parity(g200k, flags, tag):
     prefix, g = g200k
     E = emulib.Emu(prefix, extra_flags=flags, tag=tag)
     O = orclib.Oracle(prefix)
-    sig, _ = synth.reads(g, 4, 3000, seed=3)
-    _check(E, O, [sig[i] for i in range(4)])
-    _check(E, O, [sig[i] for i in range(2)], n_warps=3)
+    sig, _ = synth.reads(g, 3, 3000, seed=3)
+    _check(E, O, [sig[i] for i in range(2)])
+    _check(E, O, [sig[2]], n_warps=3)
     E.params.max_paths = O.params.max_paths = 300
     _check(E, O, [sig[i][:2500] for i in range(3)])
 

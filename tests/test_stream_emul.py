@@ -42,9 +42,9 @@ def test_reads_following_each_other_on_shared_channels(g200k):
     and sources_added_ carry over from a channel's previous read."""
     prefix, g = g200k
     E, O = emulib.Emu(prefix), orclib.Oracle(prefix)
-    sig, _ = synth.reads(g, 6, 6000, seed=5, frac_random=0.3)
-    sigs = [sig[i][:6000 - 37 * i] for i in range(6)] + [sig[0][:300]]      # the last one is shorter than a chunk
-    st = _check(E, O, sigs, 3, 450)
+    sig, _ = synth.reads(g, 4, 5000, seed=5, frac_random=0.3)
+    sigs = [sig[i][:5000 - 37 * i] for i in range(4)] + [sig[0][:300]]      # the last one is shorter than a chunk
+    st = _check(E, O, sigs, 2, 450)
     assert (2, 0) in st
 
 

@@ -129,6 +129,35 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def stream_job(sm, sigs, steps, warmup, barrier, on_timed_start=None):
+    """W untimed + K timed passes of all reads through a stream mapper (anything with .step and .map_reads);
+    returns (total ms of the K passes, per-pass counters of the C-ABI steps, the last pass's results)."""
+    counters = {"steps": 0, "chunks": 0, "bytes": 0}
+    inner = sm.step
+
+    def counting_step(descs, n, flat, res):
+        counters["steps"] += 1
+        counters["chunks"] += sum(1 for i in range(n) if descs[i].n_samples)
+        counters["bytes"] += int(flat.nbytes)
+        inner(descs, n, flat, res)
+    sm.step = counting_step
+    for _ in range(warmup):
+        sm.map_reads(sigs)
+    for k in counters:
+        counters[k] = 0
+    if on_timed_start:
+        on_timed_start()
+    barrier()
+    t0 = time.perf_counter()
+    res = None
+    for _ in range(steps):
+        res = sm.map_reads(sigs)
+    barrier()
+    ms = (time.perf_counter() - t0) * 1e3
+    sm.step = inner
+    return ms, counters, res
+
+
 def run_stream_workload(args, rank, local_rank, world):
     """configs[4]-like: chunk streaming (450-sample chunks = chunk_time 0.1125 s) over 512 channels with persistent
     per-channel device state (unc_stream_step), reads following each other on every channel.  A step = all reads
@@ -146,34 +175,13 @@ def run_stream_workload(args, rank, local_rank, world):
     sigs = [sig[i] for i in range(n_reads)]
     idx = U.Index(prefix, device=local_rank)
     sm = U.StreamMapper(idx, n_channels, chunk_len)
-    counters = {"steps": 0, "chunks": 0, "bytes": 0}
-    inner = sm.step
-
-    def counting_step(descs, n, flat, res):
-        counters["steps"] += 1
-        counters["chunks"] += sum(1 for i in range(n) if descs[i].n_samples)
-        counters["bytes"] += int(flat.nbytes)
-        inner(descs, n, flat, res)
-    sm.step = counting_step
+    sampler = ClockSampler(local_rank)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        sm.map_reads(sigs)
-    for k in counters:
-        counters[k] = 0
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    res = None
-    for _ in range(args.steps):
-        res = sm.map_reads(sigs)
-    barrier()
-    ms = (time.perf_counter() - t0) * 1e3
+    ms, counters, res = stream_job(sm, sigs, args.steps, args.warmup, barrier, sampler.start if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     v = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:

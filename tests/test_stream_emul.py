@@ -66,3 +66,29 @@ def test_max_events_and_small_path_buffer(g200k):
     sig, _ = synth.reads(g, 6, 5000, seed=9, frac_random=0.5)
     st = _check(E, O, [sig[i] for i in range(6)], 2, 450, n_warps=5)
     assert (3, 1) in st and (2, 0) in st
+
+
+def test_bench_stream_job_logic(g200k):
+    """bench.py --workload stream: the pass/count/timing loop (stream_job), driven with the emulated device."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    prefix, g = g200k
+    E = emulib.Emu(prefix)
+    sig, _ = synth.reads(g, 2, 1500, seed=5)
+
+    class SM:
+        def __init__(self):
+            self.es = emulib.EmuStream(E, 2, 450)
+            self.step = self.es.step
+
+        def map_reads(self, sigs):
+            from uncalled_b200.stream import feed_reads
+            return feed_reads(self.step, 2, sigs, 450)
+    sm = SM()
+    calls = []
+    ms, counters, res = bench.stream_job(sm, [sig[0], sig[1]], 1, 1, lambda: calls.append("b"), lambda: calls.append("s"))
+    assert calls == ["s", "b", "b"] and ms > 0
+    assert 2 <= counters["chunks"] <= 6 and counters["steps"] >= 2 and counters["bytes"] >= counters["chunks"] * 450 * 4
+    assert len(res) == 2 and all(r is not None and r[0] in (2, 3) for r in res)

@@ -43,6 +43,7 @@
 #define private public
 #include "mapper.hpp"
 #undef private
+#include "self_align_ref.hpp"
 
 extern "C" {
 
@@ -249,6 +250,26 @@ int ref_stream_channel(const float *samples, const uint64_t *offsets, const uint
                    ended ? ended + i : nullptr);
     ReadBuffer::PRMS.chunk_time = old_ct; ReadBuffer::PRMS.max_chunks = old_mc;
     return 0;
+}
+
+// self_align (reference src/self_align_ref.cpp:34-91) as `uncalled index` calls it: FM range lengths along
+// the reference from deterministically sampled start positions.  Returns the number of paths; a second call
+// with buffers copies them out (CSR: offsets[n+1], values[offsets[n]]).
+static std::vector<std::vector<u64>> g_self_align;
+uint64_t ref_self_align(const char *bwa_prefix, uint32_t sample_dist, uint64_t *n_values) {
+    g_self_align = self_align(bwa_prefix, sample_dist);
+    uint64_t tot = 0;
+    for (auto &v : g_self_align) tot += v.size();
+    if (n_values) *n_values = tot;
+    return g_self_align.size();
+}
+void ref_self_align_copy(uint64_t *offsets, uint64_t *values) {
+    uint64_t o = 0;
+    for (size_t i = 0; i < g_self_align.size(); i++) {
+        offsets[i] = o;
+        for (u64 x : g_self_align[i]) values[o++] = x;
+    }
+    offsets[g_self_align.size()] = o;
 }
 
 // bwa index build exactly as `uncalled index` performs it (bwa_idx_build).

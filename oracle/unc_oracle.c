@@ -474,6 +474,7 @@ int orc_index_load(const char *prefix, const char *preset, orc_index **out) {
         x->kmer_en[k] = en;
     }
 
+    if (preset && !strcmp(preset, "-")) { *out = x; return 0; }   /* index time: no .uncl yet (self_align) */
     snprintf(fn, sizeof fn, "%s.uncl", prefix);
     fp = fopen(fn, "r");
     if (!fp) { orc_index_free(x); return -6; }
@@ -498,6 +499,48 @@ int orc_index_load(const char *prefix, const char *preset, orc_index **out) {
     free(line);
     fclose(fp);
     *out = x;
+    return 0;
+}
+
+/* self_align (reference src/self_align_ref.cpp:34-91): for every sampled start position i of every
+ * sequence (glibc rand() % sample_dist == 0 after srand(0), one draw per position), the FM range lengths of
+ * the backward search that walks FORWARD along the reference with complemented bases, from
+ * get_base_range (whose start is L2[b], not L2[b]+1, src/bwa_index.hpp:172-174) until the range is unique.
+ * Bases come from the .pac file (src/bwa_index.hpp:141-147,257-259).  Two calls: values == NULL counts. */
+int orc_self_align(const orc_index *x, const char *prefix, uint32_t sample_dist, uint64_t *n_paths, uint64_t *n_values,
+                   uint64_t *offsets, uint64_t *values) {
+    char fn[4096];
+    snprintf(fn, sizeof fn, "%s.pac", prefix);
+    size_t sz = 0;
+    u8 *pac = (u8 *) read_file(fn, &sz);
+    if (!pac) return -1;
+    srand(0);
+    u64 st = 0, np = 0, nv = 0;
+    for (int s = 0; s < x->n_seqs; s++) {
+        const u64 len = (u64) x->lens[s];
+        for (u64 i = 0; i < len; i++) {
+            if (rand() % sample_dist != 0) continue;
+            if (offsets) offsets[np] = nv;
+            np++;
+            u8 b = (u8) (3 - ((pac[(st + i) >> 2] >> (((3 ^ (st + i)) & 3) << 1)) & 3));
+            u64 rs = x->L2[b], re = x->L2[b + 1];
+            u64 j = i + 1;
+            for (; j < len && re - rs + 1 > 1; j++) {
+                if (values) values[nv] = re - rs + 1;
+                nv++;
+                b = (u8) (3 - ((pac[(st + j) >> 2] >> (((3 ^ (st + j)) & 3) << 1)) & 3));
+                u64 ns, ne;
+                orc_get_neighbor(x, rs, re, b, &ns, &ne);
+                rs = ns; re = ne;
+            }
+            if (re - rs + 1 > 0) { if (values) values[nv] = re - rs + 1; nv++; }
+        }
+        st += len;
+    }
+    if (offsets) offsets[np] = nv;
+    free(pac);
+    if (n_paths) *n_paths = np;
+    if (n_values) *n_values = nv;
     return 0;
 }
 

@@ -247,8 +247,38 @@ def ref():
         lib.ref_stream_read.argtypes = [f32p, C.c_uint32, C.c_float, C.c_uint32, C.POINTER(RefPaf),
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
         lib.ref_index_build.argtypes = [C.c_char_p, C.c_char_p]
+        lib.ref_self_align.argtypes = [C.c_char_p, C.c_uint32, u64p]
+        lib.ref_self_align.restype = C.c_uint64
+        lib.ref_self_align_copy.argtypes = [C.c_void_p, C.c_void_p]
         _ref = lib
     return _ref
+
+
+def self_align(prefix, sample_dist):
+    """The oracle's self_align as CSR (offsets[n+1], values): FM range lengths of the sampled paths."""
+    lib = orc()
+    lib.orc_self_align.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, u64p, u64p, C.c_void_p, C.c_void_p]
+    idx = C.c_void_p()
+    if lib.orc_index_load(prefix.encode(), b"-", C.byref(idx)) != 0:
+        raise RuntimeError("oracle index load failed: " + prefix)
+    try:
+        a, b = C.c_uint64(), C.c_uint64()
+        lib.orc_self_align(idx, prefix.encode(), sample_dist, C.byref(a), C.byref(b), None, None)
+        off, val = np.zeros(a.value + 1, np.uint64), np.zeros(max(b.value, 1), np.uint64)
+        lib.orc_self_align(idx, prefix.encode(), sample_dist, C.byref(a), C.byref(b), off.ctypes.data, val.ctypes.data)
+        return off, val[:b.value]
+    finally:
+        lib.orc_index_free(idx)
+
+
+def ref_self_align(prefix, sample_dist):
+    """oracle/_ref: the reference's own self_align (src/self_align_ref.cpp), same CSR form."""
+    R = ref()
+    nv = C.c_uint64()
+    n = R.ref_self_align(prefix.encode(), sample_dist, C.byref(nv))
+    off, val = np.zeros(n + 1, np.uint64), np.zeros(max(nv.value, 1), np.uint64)
+    R.ref_self_align_copy(off.ctypes.data, val.ctypes.data)
+    return off, val[:nv.value]
 
 
 def materialise_example_index(dst_dir):

@@ -210,6 +210,19 @@ int unc_stream_step(unc_stream *st, const unc_chunk_desc *chunks, uint32_t n, co
                     unc_stream_result *out);
 void unc_stream_free(unc_stream *st);
 
+/* ---- `uncalled index` after the BWA build ----------------------------------------------------------
+ *   unc_self_align      self_align(bwa_prefix, sample_dist) -> vector<vector<u64>>
+ *                                                      src/self_align_ref.cpp:34-91 (Python: src/pybinder.cpp:59,
+ *                                                      called by IndexParameterizer, uncalled/index.py:82)
+ * For every sampled reference position (glibc srand(0); rand() % sample_dist == 0, one draw per position) the
+ * FM range lengths of the search that follows the reference until the range is unique.  Loads <prefix>.bwt /
+ * .sa / .ann / .pac itself (no .uncl exists yet).  Result in CSR form: path i = (*values)[(*offsets)[i] ..
+ * (*offsets)[i+1]), (*offsets) has *n_paths + 1 entries.  Both arrays are allocated by the library; release
+ * each with unc_free. */
+int unc_self_align(const char *bwa_prefix, uint32_t sample_dist, uint64_t *n_paths, uint64_t **offsets,
+                   uint64_t **values);
+void unc_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,8 @@
 #include "unc_k1.cuh"
 #include "unc_stream.cuh"
 #include "unc_stream_logic.hpp"
+#include "unc_selfalign.cuh"
+#include "unc_selfalign_host.hpp"
 #include "../../include/unc_b200.h"
 #include "unc_host_index.hpp"
 #include "unc_host_params.hpp"
@@ -266,5 +268,41 @@ int emu_stream_step(void *pst, const unc_chunk_desc *chunks, uint32_t n, const v
     }
     return 0;
 }
+
+// ---- self_align: the device functions of unc_selfalign.cuh, one "thread" after the other, around the same
+// host steps as unc_self_align (uncalled_b200/csrc/unc_selfalign_host.inl)
+int emu_glibc_rand(unsigned seed, uint32_t n, int32_t *out) {
+    GlibcRand g(seed);
+    for (uint32_t i = 0; i < n; i++) out[i] = g.next();
+    return 0;
+}
+
+int emu_self_align(const char *prefix, uint32_t sample_dist, uint64_t *n_paths, uint64_t **offsets, uint64_t **values) {
+    HostIndex h;
+    std::vector<char> pac;
+    if (!hix_load_fm(h, prefix) || !hix_read_file(std::string(prefix) + ".pac", pac)) return -1;
+    pac.resize(pac.size() + 16, 0);
+    std::vector<u32> pos, lim;
+    unc_selfalign_sample(h.lens, sample_dist, pos, lim);
+    const size_t n = pos.size();
+    DevIndex ix{};
+    ix.bwt = (const uint4 *) h.bwt.data();
+    ix.primary = (u32) h.primary; ix.seq_len = (u32) h.seq_len;
+    for (int i = 0; i < 5; i++) ix.L2[i] = (u32) h.L2[i];
+    std::vector<u32> count(n), stage((size_t) UNC_SA_STAGE * n);
+    DevSelfAlign A{};
+    A.pac = (const u8 *) pac.data(); A.pos = pos.data(); A.lim = lim.data(); A.n = (u32) n;
+    A.count = count.data(); A.stage = stage.data();
+    for (size_t i = 0; i < n; i++) unc_selfalign_count(ix, A, (u32) i);
+    uint64_t *off = (uint64_t *) malloc((n + 1) * 8);
+    off[0] = 0;
+    for (size_t i = 0; i < n; i++) off[i + 1] = off[i] + count[i];
+    uint64_t *val = (uint64_t *) malloc((off[n] ? off[n] : 1) * 8);
+    A.offsets = off; A.values = val;
+    for (size_t i = 0; i < n; i++) unc_selfalign_write(ix, A, (u32) i);
+    *n_paths = n; *offsets = off; *values = val;
+    return 0;
+}
+void emu_free(void *p) { free(p); }
 
 }  // extern "C"

@@ -65,7 +65,8 @@ def build(extra_flags=(), tag=""):
     out = os.path.join(EMUL_DIR, "libunc_emul%s.so" % tag)
     deps = [src, os.path.join(EMUL_DIR, "warp_emul.hpp")] + \
            [os.path.join(ROOT, "uncalled_b200", "csrc", f) for f in
-            ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_logic.hpp", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp")]
+            ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_logic.hpp", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp",
+             "unc_selfalign.cuh", "unc_selfalign_host.hpp")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-ffp-contract=off", "-DUNC_EMUL", "-DK2_MAXSEG=16u", "-fPIC", "-shared",
@@ -87,6 +88,10 @@ def _bind(L):
                                 C.POINTER(UncPaf), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_uint32, C.c_int]
     L.emu_match_probs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    L.emu_self_align.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.emu_glibc_rand.argtypes = [C.c_uint, C.c_uint32, C.c_void_p]
+    L.emu_free.argtypes = [C.c_void_p]
+    L.emu_free.restype = None
     L.emu_sa.argtypes = [C.c_void_p, C.c_uint64]
     L.emu_sa.restype = C.c_uint64
     L.emu_k1_stats.argtypes = [C.c_void_p]
@@ -176,3 +181,23 @@ def paf_tuple(r):
     if not r.mapped:
         return (0, int(r.rd_len), int(r.n_events), int(r.events_used))
     return tuple(int(getattr(r, k)) for k in PAF_KEYS)
+
+
+def self_align(prefix, sample_dist):
+    """unc_selfalign.cuh on the CPU: (offsets, values) as numpy arrays."""
+    import numpy as np
+    L = lib()
+    n, po, pv = C.c_uint64(), C.c_void_p(), C.c_void_p()
+    if L.emu_self_align(prefix.encode(), sample_dist, C.byref(n), C.byref(po), C.byref(pv)) != 0:
+        raise RuntimeError("emu_self_align failed")
+    off = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), (n.value + 1,)).copy()
+    val = np.ctypeslib.as_array(C.cast(pv, C.POINTER(C.c_uint64)), (max(int(off[-1]), 1),)).copy()[:int(off[-1])]
+    L.emu_free(po); L.emu_free(pv)
+    return off, val
+
+
+def glibc_rand(seed, n):
+    import numpy as np
+    out = np.zeros(n, np.int32)
+    lib().emu_glibc_rand(seed, n, out.ctypes.data)
+    return out

@@ -3,5 +3,6 @@
 from ._native import UncError, build, default_params  # noqa: F401
 from .mapper import BatchMapper, Index, make_descs, paf_key  # noqa: F401
 from .stream import StreamMapper, feed_reads  # noqa: F401
+from .index import BwaIndex, index_cmd, self_align  # noqa: F401
 
 __version__ = "0.1.0"

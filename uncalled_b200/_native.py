@@ -76,7 +76,7 @@ EXPORTS = ["unc_strerror", "unc_last_error", "unc_device_count", "unc_init", "un
            "unc_index_thresholds", "unc_index_free", "unc_index_build", "unc_pool_create", "unc_pool_free",
            "unc_map_batch", "unc_map_batch_device", "unc_events_batch", "unc_match_probs", "unc_fm_neighbors",
            "unc_fm_sa", "unc_pool_last_timing", "unc_pool_k1_stats", "unc_stream_create", "unc_stream_step",
-           "unc_stream_free"]
+           "unc_stream_free", "unc_self_align", "unc_free"]
 
 
 def build(force=False, verbose=False):
@@ -85,6 +85,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(src_dir, f) for f in ("unc_abi.cu", "unc_index_build.cpp")]
     deps = srcs + [os.path.join(src_dir, f) for f in
                    ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_host.inl", "unc_stream_logic.hpp", "unc_warp.cuh",
+                    "unc_selfalign.cuh", "unc_selfalign_host.hpp", "unc_selfalign_host.inl",
                     "unc_host_index.hpp", "unc_host_params.hpp")] + \
         [os.path.join(ROOT, "include", "unc_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
@@ -138,6 +139,9 @@ def lib():
     L.unc_stream_step.argtypes = [vp, vp, u32, vp, vp]
     L.unc_stream_free.argtypes = [vp]
     L.unc_stream_free.restype = None
+    L.unc_self_align.argtypes = [C.c_char_p, u32, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp)]
+    L.unc_free.argtypes = [vp]
+    L.unc_free.restype = None
     _lib = L
     return L
 

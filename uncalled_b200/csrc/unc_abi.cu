@@ -668,3 +668,4 @@ int unc_pool_last_timing(const unc_pool *P, unc_timing *t) {
 }  // extern "C"
 
 #include "unc_stream_host.inl"
+#include "unc_selfalign_host.inl"

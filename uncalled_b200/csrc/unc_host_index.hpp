@@ -72,7 +72,8 @@ static inline bool hix_load_model(HostIndex &h, const std::string &table_path) {
     return true;
 }
 
-static inline bool hix_load(HostIndex &h, const std::string &prefix, const std::string &preset) {
+// The FM index proper (.bwt, .sa, .ann) -- all `uncalled index` has before the thresholds exist
+static inline bool hix_load_fm(HostIndex &h, const std::string &prefix) {
     std::vector<char> b;
     if (!hix_read_file(prefix + ".bwt", b) || b.size() < 40) { h.error = "cannot read " + prefix + ".bwt"; return false; }
     memcpy(&h.primary, b.data(), 8);
@@ -121,11 +122,15 @@ static inline bool hix_load(HostIndex &h, const std::string &prefix, const std::
         h.lens.push_back((uint32_t) len);
     }
     fclose(fp);
+    return true;
+}
 
+static inline bool hix_load(HostIndex &h, const std::string &prefix, const std::string &preset) {
+    if (!hix_load_fm(h, prefix)) return false;
     // .uncl: "<preset>\t<thr for range len 1>,<2-3>,<4-7>,...\t<prob>\t<speed>"
     // (reference src/mapper.cpp:123-157); atof semantics incl. "nan"
     for (int i = 0; i < 64; i++) h.thresh[i] = 0.f;
-    fp = fopen((prefix + ".uncl").c_str(), "r");
+    FILE *fp = fopen((prefix + ".uncl").c_str(), "r");
     if (!fp) { h.error = "cannot read " + prefix + ".uncl"; return false; }
     char *line = NULL;
     size_t cap = 0;

@@ -223,6 +223,38 @@ int unc_self_align(const char *bwa_prefix, uint32_t sample_dist, uint64_t *n_pat
                    uint64_t **values);
 void unc_free(void *p);
 
+/* ---- fast5 input (host; no libhdf5 needed) -------------------------------------------------------------
+ *   unc_fast5_open      Fast5Reader::open_next: format detection and the list of reads
+ *                                                      src/fast5_reader.cpp:134-177
+ *   unc_fast5_info      ReadBuffer(hdf5_tools::File&, raw_path, ch_path): attributes as the reference parses
+ *                       them (text -> atoi / atof)      src/read_buffer.cpp:198-225,
+ *                                                      submods/fast5/include/fast5/hdf5_tools.hpp:1013-1141
+ *   unc_fast5_load      the same constructor's `file.read(raw_path + "/Signal", int_data)` + truncation to
+ *                       max_chunks * chunk_len samples  src/read_buffer.cpp:227-236
+ *                       for a range of reads, decoded by several host threads into one staging buffer
+ * The signal stays int16: unc_map_batch calibrates it on the device (unc_read_desc dtype 1) exactly as
+ * src/read_buffer.cpp:239-242 does (u16 reinterpretation included). */
+typedef struct {
+    const char *read_id;        /* attribute read_id; valid until the next info/load call or close */
+    int32_t number;             /* atoi(read_number) */
+    int32_t start_sample;       /* atoi(start_time): 32 bit, like the reference */
+    int32_t channel;            /* atoi(channel_number) -- what Paf prints as ch:i: */
+    float cal_digitisation, cal_range, cal_offset;
+    uint64_t n_samples;         /* after truncation, for unc_fast5_load */
+    uint64_t sample_offset;     /* unc_fast5_load: where this read's samples start in dst */
+} unc_fast5_read;
+
+typedef struct unc_fast5 unc_fast5;
+int unc_fast5_open(const char *path, unc_fast5 **out);
+int unc_fast5_count(const unc_fast5 *f, uint32_t *n_reads, int *single_read_format);
+int unc_fast5_info(unc_fast5 *f, uint32_t i, unc_fast5_read *info);
+/* max_samples_per_read 0 = whole signals; threads 0 = all hardware threads.  UNC_E_TOO_LARGE when the signals
+ * need more than `capacity` samples. */
+int unc_fast5_load(unc_fast5 *f, uint32_t first, uint32_t n, uint64_t max_samples_per_read, int16_t *dst,
+                   uint64_t capacity, unc_fast5_read *info, int threads);
+void unc_fast5_close(unc_fast5 *f);
+const char *unc_fast5_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

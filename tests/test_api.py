@@ -142,3 +142,84 @@ def test_realtime_pool_chunk_protocol_with_emulated_device():
                 assert (p.rd_st, p.rd_en, p.rf_st, p.rf_en, p.matches, p.fwd) == \
                        (rec.rd_st, rec.rd_en, rec.rf_st, rec.rf_en, rec.matches, bool(rec.fwd)), i
                 assert p.fields()[0] == "read%d" % i and p.int_tags[0] == (4, ch + 1)
+
+
+@pytest.mark.gpu
+def test_uncalled_map_on_the_example_fast5(example_prefix, tmp_path):
+    """config 1 end to end from the FILE: `uncalled map -t 1 <index> <fast5>`, `-c 1` and `-e 100` (SURVEY 8c golden
+    lines), the fast5 decoded by the library's own reader, calibrated on the GPU; and a fast5 list + read filter."""
+    from uncalled_b200.api import Conf, MapPool
+    f5 = os.path.join(ROOT, "tests", "golden", "fast5", "example_single.fast5")
+    for key, mod in (("default", {}), ("max_chunks_1", {"max_chunks": 1}), ("max_events_100", {"max_events": 100})):
+        conf = Conf()
+        conf.bwa_prefix = example_prefix
+        for k, v in mod.items():
+            setattr(conf, k, v)
+        pool = MapPool(conf)
+        pool.add_fast5(f5)
+        assert pool.running()
+        lines = []
+        while pool.running():
+            lines += [p.line() for p in pool.update()]
+        pool.stop()
+        assert len(lines) == 1 and lines[0].rsplit("\t", 1)[0] == GOLD[key]["line"], (key, lines)
+    # fast5_list + read_list + max_reads over multi-read files (none of these reads map to the example reference)
+    fl, rl = tmp_path / "files.txt", tmp_path / "reads.txt"
+    multi = os.path.join(ROOT, "tests", "golden", "fast5", "multi_gzip.fast5")
+    fl.write_text(multi + "\n" + f5 + "\n")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fast5", "golden.json")))
+    ids = sorted(set(r["id"] for r in gold if r["file"] == "multi_gzip.fast5"))
+    rl.write_text("\n".join(ids[:5] + ["f41a60f7-de4a-4b17-9f54-387e52d60b65"]) + "\n")
+    conf = Conf()
+    conf.bwa_prefix, conf.fast5_list, conf.read_list, conf.batch_reads = example_prefix, str(fl), str(rl), 4
+    pool = MapPool(conf)
+    out = []
+    while pool.running():
+        out += pool.update()
+    pool.stop()
+    assert sorted(p.fields()[0] for p in out) == sorted(ids[:5] + ["f41a60f7-de4a-4b17-9f54-387e52d60b65"])
+    assert [p.is_mapped() for p in out if p.fields()[0].startswith("f41a60f7")] == [True]
+
+
+def test_cli_parser_and_fast5_discovery(tmp_path, capsys):
+    """`uncalled map` / `uncalled index` option names and defaults (uncalled/args.py:87-161,218-286) and the fast5
+    path expansion of scripts/uncalled:80-118."""
+    from uncalled_b200 import cli
+    f5dir = os.path.join(ROOT, "tests", "golden", "fast5")
+    _, conf, args = cli.load_conf(["map", "-t", "3", "-c", "1", "-e", "100", "-n", "7", "-l", "reads.txt", "-p", "fast",
+                                   "idx/ecoli", f5dir, "-r"])
+    assert (conf.bwa_prefix, conf.threads, conf.max_chunks, conf.max_events, conf.max_reads, conf.read_list, conf.idx_preset) == \
+        ("idx/ecoli", 3, 1, 100, 7, "reads.txt", "fast")
+    assert args.recursive and conf.chunk_time == 1.0
+    found = sorted(os.path.basename(p) for p in cli.load_fast5s([f5dir], False) if p)
+    assert found == sorted(f for f in os.listdir(f5dir) if f.endswith(".fast5")) and len(found) == 8
+    lst = tmp_path / "list.txt"
+    lst.write_text(os.path.join(f5dir, "multi_gzip.fast5") + "\n#comment.fast5\nnot_a_fast5.txt\n" + str(tmp_path / "gone.fast5") + "\n")
+    assert [os.path.basename(p) for p in cli.load_fast5s([str(lst)], False) if p] == ["multi_gzip.fast5"]
+    assert "is not a fast5 file" in capsys.readouterr().err
+    _, _, a = cli.load_conf(["index", "ref.fa", "-o", "out/ref", "--probs", "0.5,0.2", "-s", "50", "-1", "0.55"])
+    assert (a.fasta_filename, a.bwa_prefix, a.probs, a.speeds, a.max_sample_dist, a.matchpr1, a.matchpr2, a.min_samples) == \
+        ("ref.fa", "out/ref", "0.5,0.2", None, 50, 0.55, 0.9838, 50000)
+    with pytest.raises(SystemExit):
+        list(cli.load_fast5s([str(tmp_path / "absent_dir")], False))
+
+
+@pytest.mark.gpu
+def test_cli_index_then_map_end_to_end(tmp_path, capsys):
+    """`uncalled index example_ref.fa` from the FASTA alone, then `uncalled map` of the example fast5 against it: the
+    reference's golden PAF line (a rebuilt index is byte-identical to the shipped one)."""
+    import orclib
+    from uncalled_b200 import cli
+    os.makedirs(tmp_path / "src")
+    src = orclib.materialise_example_index(str(tmp_path / "src"))
+    fa = str(tmp_path / "example_ref.fa")
+    open(fa, "wb").write(open(src + ".fa", "rb").read())
+    assert cli.main(["index", fa]) == 0
+    for ext in (".bwt", ".sa", ".ann", ".amb", ".pac", ".uncl"):
+        assert open(fa + ext, "rb").read() == open(src + ext, "rb").read(), ext
+    capsys.readouterr()
+    assert cli.main(["map", fa, os.path.join(ROOT, "tests", "golden", "fast5", "example_single.fast5")]) == 0
+    cap = capsys.readouterr()
+    lines = cap.out.strip().split("\n")
+    assert len(lines) == 1 and lines[0].rsplit("\t", 1)[0] == GOLD["default"]["line"].replace("\n", "")
+    assert cap.err.count("Mapping\n") == 1 and cap.err.count("Finishing\n") == 1

@@ -71,18 +71,26 @@ class IndexInfo(C.Structure):
                 ("device_bytes", C.c_uint64), ("n_kmer_groups", C.c_uint32)]
 
 
+class Fast5Read(C.Structure):
+    """unc_fast5_read (include/unc_b200.h)"""
+    _fields_ = [("read_id", C.c_char_p), ("number", C.c_int32), ("start_sample", C.c_int32), ("channel", C.c_int32),
+                ("cal_digitisation", C.c_float), ("cal_range", C.c_float), ("cal_offset", C.c_float),
+                ("n_samples", C.c_uint64), ("sample_offset", C.c_uint64)]
+
+
 EXPORTS = ["unc_strerror", "unc_last_error", "unc_device_count", "unc_init", "unc_params_default",
            "unc_index_load", "unc_index_get_info", "unc_index_seq", "unc_index_kmer_range",
            "unc_index_thresholds", "unc_index_free", "unc_index_build", "unc_pool_create", "unc_pool_free",
            "unc_map_batch", "unc_map_batch_device", "unc_events_batch", "unc_match_probs", "unc_fm_neighbors",
            "unc_fm_sa", "unc_pool_last_timing", "unc_pool_k1_stats", "unc_stream_create", "unc_stream_step",
-           "unc_stream_free", "unc_self_align", "unc_free"]
+           "unc_stream_free", "unc_self_align", "unc_free", "unc_fast5_open", "unc_fast5_count", "unc_fast5_info",
+           "unc_fast5_load", "unc_fast5_close", "unc_fast5_last_error"]
 
 
 def build(force=False, verbose=False):
     """Compile uncalled_b200/libunc_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     src_dir = os.path.join(PKG_DIR, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("unc_abi.cu", "unc_index_build.cpp")]
+    srcs = [os.path.join(src_dir, f) for f in ("unc_abi.cu", "unc_index_build.cpp", "unc_fast5.cpp")]
     deps = srcs + [os.path.join(src_dir, f) for f in
                    ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_host.inl", "unc_stream_logic.hpp", "unc_warp.cuh",
                     "unc_selfalign.cuh", "unc_selfalign_host.hpp", "unc_selfalign_host.inl",
@@ -90,7 +98,7 @@ def build(force=False, verbose=False):
         [os.path.join(ROOT, "include", "unc_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs + ["-lz"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise UncError("nvcc failed:\n" + r.stdout + r.stderr)
@@ -142,6 +150,13 @@ def lib():
     L.unc_self_align.argtypes = [C.c_char_p, u32, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp)]
     L.unc_free.argtypes = [vp]
     L.unc_free.restype = None
+    L.unc_fast5_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.unc_fast5_count.argtypes = [vp, C.POINTER(u32), C.POINTER(C.c_int)]
+    L.unc_fast5_info.argtypes = [vp, u32, C.POINTER(Fast5Read)]
+    L.unc_fast5_load.argtypes = [vp, u32, u32, C.c_uint64, vp, C.c_uint64, C.POINTER(Fast5Read), C.c_int]
+    L.unc_fast5_close.argtypes = [vp]
+    L.unc_fast5_close.restype = None
+    L.unc_fast5_last_error.restype = C.c_char_p
     _lib = L
     return L
 

@@ -9,11 +9,11 @@ constructing a MapPool without a usable CUDA device raises UncError.
 Differences a caller can observe (documented, not hidden):
   * `MapPool(conf)` maps batches on the GPU instead of one read per CPU thread; `conf.threads`
     is accepted and ignored by the mapper (reference src/map_pool.cpp:31).
-  * fast5 input needs an HDF5 reader.  The reference vendors libhdf5; this image has no
-    HDF5 binding, so `add_fast5()` works only when `h5py` is importable and otherwise raises
-    RuntimeError (like the reference does for an unreadable file, src/fast5_reader.cpp).  Reads
-    can always be queued as arrays with `add_read()`, which is what `Fast5Reader` hands to
-    `MapPool::update` after decoding (reference src/read_buffer.cpp:160-246).
+  * fast5 files are read by the library's own HDF5 subset reader (uncalled_b200/csrc/unc_fast5.cpp; the
+    reference vendors libhdf5).  VBZ-compressed files are rejected with a clear error (the reference's
+    vendored libhdf5 cannot read them either without an external plugin).  Reads can also be queued as
+    arrays with `add_read()`, which is what `Fast5Reader` hands to `MapPool::update` after decoding
+    (reference src/read_buffer.cpp:160-246).
 """
 import enum
 import sys
@@ -31,7 +31,7 @@ class Conf:
 
     _FIELDS = {
         # name: (default, doc)           defaults: src/mapper.cpp:29-52, read_buffer.cpp:26-32, fast5_reader.cpp:26-31
-        "threads": (1, "Number of threads (accepted; the GPU mapper does not use CPU mapping threads)"),
+        "threads": (1, "Number of threads (the GPU mapper has no CPU mapping threads; used as fast5 decoding threads)"),
         "bwa_prefix": ("", "BWA prefix to map to"),
         "idx_preset": ("default", "Mapping mode preset line of the .uncl file"),
         "model_path": ("", "k-mer model file (empty: built-in r9.4 5-mer template model)"),
@@ -191,6 +191,9 @@ class MapPool:
         self.params = p
         self._queue, self._mapper, self._cap = [], None, (0, 0)
         self._n_added, self._stopped = 0, False
+        self._files, self._open, self._next = [], None, 0
+        if conf.fast5_list:                                   # Fast5Reader::load_fast5_list (src/fast5_reader.cpp:77-92)
+            self._files = [l.rstrip("\n") for l in open(conf.fast5_list) if l.strip()]
         self._read_filter = None
         if conf.read_list:
             self._read_filter = set(l.strip() for l in open(conf.read_list) if l.strip())
@@ -222,33 +225,38 @@ class MapPool:
         return True
 
     def add_fast5(self, fast5_name):
-        try:
-            import h5py
-        except ImportError:
-            raise RuntimeError("add_fast5('%s'): no HDF5 reader in this environment (h5py); queue decoded reads "
-                               "with MapPool.add_read()" % fast5_name)
-        with h5py.File(fast5_name, "r") as f:             # layouts: reference src/fast5_reader.cpp:134-210
-            def one(raw_grp, ch_grp):
-                a, c = raw_grp.attrs, ch_grp.attrs
-                rid = a["read_id"]
-                rid = rid.decode() if isinstance(rid, bytes) else str(rid)
-                # attributes pass through 6-significant-digit text in the reference (hdf5_tools.hpp:1124-1141)
-                cal = tuple(float(np.float32(float("%g" % float(c[k])))) for k in ("range", "offset", "digitisation"))
-                self.add_read(rid, raw_grp["Signal"][()].astype(np.int16), int(c["channel_number"]),
-                              int(a["read_number"]), int(a["start_time"]), calibration=cal)
-            if "Raw" in f:                                # single-read file
-                for name in f["Raw/Reads"]:
-                    one(f["Raw/Reads"][name], f["UniqueGlobalKey/channel_id"])
-            else:
-                for name in f:
-                    if name.startswith("read_"):
-                        one(f[name]["Raw"], f[name]["channel_id"])
+        """Fast5Reader::add_fast5 (src/fast5_reader.cpp:73-75): the file is queued and read when update() needs
+        reads.  A file that cannot be read raises RuntimeError from update(), as the reference's reader throws
+        from its fill_buffer()."""
+        self._files.append(fast5_name)
+
+    def _fill_from_fast5(self):
+        """Fast5Reader::fill_buffer (src/fast5_reader.cpp:179-229): top the queue up from the pending files."""
+        from .fast5 import Fast5File
+        want = self.conf.batch_reads
+        while len(self._queue) < want and (self._open is not None or self._files):
+            if self.conf.max_reads and self._n_added >= self.conf.max_reads:
+                self._files, self._open = [], None
+                return
+            if self._open is None:
+                self._open, self._next = Fast5File(self._files.pop(0)), 0
+            f = self._open
+            n = min(want - len(self._queue), f.n_reads - self._next)
+            for r in f.load(self._next, n, max_samples_per_read=self._max_len(), threads=self.conf.threads):
+                self.add_read(r.read_id, r.signal, r.channel, r.number, r.start_sample, calibration=r.calibration)
+            self._next += n
+            if self._next >= f.n_reads:
+                f.close()
+                self._open = None
 
     # -- output --------------------------------------------------------------------------
     def update(self):
         """Maps up to conf.batch_reads queued reads on the GPU and returns their Paf records
         (the reference returns whatever its threads finished since the last call, src/map_pool.cpp:45-69)."""
-        if self._stopped or not self._queue:
+        if self._stopped:
+            return []
+        self._fill_from_fast5()
+        if not self._queue:
             return []
         out = []
         for dtype in (0, 1):
@@ -279,7 +287,7 @@ class MapPool:
         return out
 
     def running(self):
-        return not self._stopped and len(self._queue) > 0
+        return not self._stopped and (len(self._queue) > 0 or self._open is not None or len(self._files) > 0)
 
     def stop(self):
         self._stopped = True

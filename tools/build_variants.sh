@@ -10,7 +10,8 @@ set -e
 cd "$(dirname "$0")/../uncalled_b200"
 F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 -Xcompiler -fPIC --shared -diag-suppress 550"
 mkdir -p variants
-build() { nvcc $F "${@:2}" -o "variants/$1.so" csrc/unc_abi.cu csrc/unc_index_build.cpp; }
+SRC="csrc/unc_abi.cu csrc/unc_index_build.cpp csrc/unc_fast5.cpp -lz"
+build() { nvcc $F "${@:2}" -o "variants/$1.so" $SRC; }
 build base &
 build lean_c2 -DK2_LEAN_B -DK2_MIN_CTAS=2 &
 build lean_c3 -DK2_LEAN_B -DK2_MIN_CTAS=3 &
@@ -23,7 +24,8 @@ build lean_pare_w16c2 -DK2_LEAN_B -DK2_PAR_E -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_
 wait
 # phase-timing builds (tools/gpu_phases.py <genome> <reads> <lib>)
 mkdir -p variants_pt
-nvcc $F -DUNC_PHASE_TIMING -DK2_LEAN_B -DK2_PAR_E -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 -o variants_pt/lean_pare_w16c2.so csrc/unc_abi.cu csrc/unc_index_build.cpp &
-nvcc $F -DUNC_PHASE_TIMING -DK2_LEAN_B -DK2_MIN_CTAS=3 -o variants_pt/lean_c3.so csrc/unc_abi.cu csrc/unc_index_build.cpp &
+nvcc $F -DUNC_PHASE_TIMING -o libunc_b200_pt.so $SRC &      # the shipped configuration with phase marks
+nvcc $F -DUNC_PHASE_TIMING -DK2_LEAN_B -DK2_PAR_E -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 -o variants_pt/lean_pare_w16c2.so $SRC &
+nvcc $F -DUNC_PHASE_TIMING -DK2_LEAN_B -DK2_MIN_CTAS=3 -o variants_pt/lean_c3.so $SRC &
 wait
 ls -la variants variants_pt

@@ -65,11 +65,13 @@ def test_full_buffer_semantics(g200k, max_paths):
     _check(E, O, [sig[i] for i in range(4)])
 
 
-@pytest.mark.parametrize("flags,tag", [(("-DK2_LEAN_B",), "_lean"), (("-DK2_LEAN_B", "-DK2_PAR_E"), "_lean_pare")])
+@pytest.mark.parametrize("flags,tag", [(("-DK2_LEAN_B",), "_lean"), (("-DK2_LEAN_B", "-DK2_PAR_E"), "_lean_pare"),
+                                      (("-DK2_SCAN2",), "_scan2")])
 def test_prototype_variants_keep_parity(g200k, flags, tag):
     """Compile-time prototypes for a higher-occupancy build must produce the same paths, seeds and PAF records:
     -DK2_LEAN_B (children written to fixed per-parent slots the moment their base is resolved, Occ words read on
-    demand) and -DK2_PAR_E (the fresh-source walk spread over all worker warps with the serial walk's buffer cut)."""
+    demand), -DK2_PAR_E (the fresh-source walk spread over all worker warps with the serial walk's buffer cut) and
+    -DK2_SCAN2 (radix-pass counter scan with one barrier less)."""
     prefix, g = g200k
     E = emulib.Emu(prefix, extra_flags=flags, tag=tag)
     O = orclib.Oracle(prefix)

@@ -22,6 +22,9 @@ build lean_w12c2 -DK2_LEAN_B -DK2_WARPS=12 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
 build lean_pare_c3 -DK2_LEAN_B -DK2_PAR_E -DK2_MIN_CTAS=3 &
 build lean_pare_w16c2 -DK2_LEAN_B -DK2_PAR_E -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
 wait
+build scan2 -DK2_SCAN2 &
+build lean_pare_scan2_c3 -DK2_LEAN_B -DK2_PAR_E -DK2_SCAN2 -DK2_MIN_CTAS=3 &
+wait
 # phase-timing builds (tools/gpu_phases.py <genome> <reads> <lib>)
 mkdir -p variants_pt
 nvcc $F -DUNC_PHASE_TIMING -o libunc_b200_pt.so $SRC &      # the shipped configuration with phase marks

@@ -790,6 +790,15 @@ UNC_DEV void k2_wk_exscan_bins(K2Shared *sh, u32 *src, u32 *dst, u32 wt, u32 nwt
     u32 wtot, woff = w_exscan(sum, &wtot);
     if (w_lane() == 31) sh->scan_tmp[wt >> 5] = wtot;
     c_sync_sub(1, (int) nwt);
+#ifdef K2_SCAN2
+    // prototype: every warp scans the (at most 31) warp totals itself -- one barrier less per radix pass
+    u32 run;
+    {
+        u32 v = (u32) w_lane() < (nwt >> 5) ? sh->scan_tmp[w_lane()] : 0, t;
+        u32 e = w_exscan(v, &t);
+        run = w_shfl(e, (int) (wt >> 5)) + woff;
+    }
+#else
     if (wt < 32) {
         u32 v = wt < (nwt >> 5) ? sh->scan_tmp[wt] : 0, t;
         u32 e = w_exscan(v, &t);
@@ -797,6 +806,7 @@ UNC_DEV void k2_wk_exscan_bins(K2Shared *sh, u32 *src, u32 *dst, u32 wt, u32 nwt
     }
     c_sync_sub(1, (int) nwt);
     u32 run = sh->scan_tmp[wt >> 5] + woff;
+#endif
     for (u32 j = lo; j < hi; j++) {
         u32 cnt = src[j];
         dst[j] = run;

@@ -30,6 +30,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -669,31 +670,35 @@ int unc_fast5_load(unc_fast5 *h, uint32_t first, uint32_t n, uint64_t max_sample
         return UNC_E_ARG;
     }
     try {
-        uint64_t total = 0;
-        for (uint32_t i = 0; i < n; i++) {
-            fill_info(h, first + i, &info[i]);
-            if (max_samples_per_read && info[i].n_samples > max_samples_per_read) info[i].n_samples = max_samples_per_read;
-            info[i].sample_offset = total;
-            total += info[i].n_samples;
-        }
-        if (total > capacity) { g_f5_err = "staging buffer too small"; return UNC_E_TOO_LARGE; }
         unsigned nt = threads > 0 ? (unsigned) threads : std::max(1u, std::thread::hardware_concurrency());
         nt = std::min<unsigned>(nt, std::max<uint32_t>(n, 1u));
-        std::atomic<uint32_t> next(0);
         std::vector<std::string> errs(nt);
-        auto work = [&](unsigned t) {
-            try {
-                for (uint32_t i; (i = next.fetch_add(1)) < n;) {
-                    Dataset D = h->f.dataset(h->reads[first + i].sig_addr);
-                    h->f.read_i16(D, dst + info[i].sample_offset, info[i].n_samples);
-                }
-            } catch (const std::exception &e) { errs[t] = e.what(); }
+        // two parallel phases over the reads, handed out by an atomic counter: (1) attributes + signal length,
+        // (2) after the prefix sum of the lengths, the signals themselves
+        auto run = [&](const std::function<void(uint32_t)> &fn) {
+            std::atomic<uint32_t> next(0);
+            auto work = [&](unsigned t) {
+                uint32_t i = 0;
+                try { while ((i = next.fetch_add(1)) < n) fn(i); }
+                catch (const std::exception &e) { errs[t] = h->reads[first + i].raw_path + ": " + e.what(); }
+            };
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < nt; t++) pool.emplace_back(work, t);
+            work(0);
+            for (auto &t : pool) t.join();
+            for (auto &e : errs) if (!e.empty()) throw H5Error(e);
         };
-        std::vector<std::thread> pool;
-        for (unsigned t = 1; t < nt; t++) pool.emplace_back(work, t);
-        work(0);
-        for (auto &t : pool) t.join();
-        for (auto &e : errs) if (!e.empty()) { g_f5_err = e; return UNC_E_IO; }
+        run([&](uint32_t i) {
+            fill_info(h, first + i, &info[i]);
+            if (max_samples_per_read && info[i].n_samples > max_samples_per_read) info[i].n_samples = max_samples_per_read;
+        });
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; i++) { info[i].sample_offset = total; total += info[i].n_samples; }
+        if (total > capacity) { g_f5_err = "staging buffer too small"; return UNC_E_TOO_LARGE; }
+        run([&](uint32_t i) {
+            Dataset D = h->f.dataset(h->reads[first + i].sig_addr);
+            h->f.read_i16(D, dst + info[i].sample_offset, info[i].n_samples);
+        });
     } catch (const std::exception &e) {
         g_f5_err = e.what();
         return UNC_E_IO;

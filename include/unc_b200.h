@@ -121,6 +121,10 @@ int unc_device_count(void);
 /* Select the CUDA device used by subsequent unc_index_load / unc_pool_create calls of
  * this process (one process per GPU). */
 int unc_init(int device);
+/* End of use in this process: waits for the selected device to go idle and forgets the device selection and
+ * error text.  Objects the caller still holds (indexes, pools, streams) stay valid until freed; the CUDA context
+ * is NOT reset, because the host application (e.g. PyTorch in bench.py) may share it. */
+int unc_shutdown(void);
 
 int unc_params_default(unc_params *p);
 

@@ -78,7 +78,7 @@ class Fast5Read(C.Structure):
                 ("n_samples", C.c_uint64), ("sample_offset", C.c_uint64)]
 
 
-EXPORTS = ["unc_strerror", "unc_last_error", "unc_device_count", "unc_init", "unc_params_default",
+EXPORTS = ["unc_strerror", "unc_last_error", "unc_device_count", "unc_init", "unc_shutdown", "unc_params_default",
            "unc_index_load", "unc_index_get_info", "unc_index_seq", "unc_index_kmer_range",
            "unc_index_thresholds", "unc_index_free", "unc_index_build", "unc_pool_create", "unc_pool_free",
            "unc_map_batch", "unc_map_batch_device", "unc_events_batch", "unc_match_probs", "unc_fm_neighbors",

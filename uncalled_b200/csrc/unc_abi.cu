@@ -203,6 +203,17 @@ int unc_init(int device) {
     return UNC_OK;
 }
 
+int unc_shutdown(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) == cudaSuccess && g_device < n && cudaSetDevice(g_device) == cudaSuccess) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return fail(UNC_E_CUDA, std::string("cudaDeviceSynchronize: ") + cudaGetErrorString(e));
+    }
+    g_device = 0;
+    g_err.clear();
+    return UNC_OK;
+}
+
 int unc_params_default(unc_params *p) {
     if (!p) return fail(UNC_E_ARG, "null params");
     unc_fill_default_params(p);

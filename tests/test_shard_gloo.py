@@ -64,3 +64,11 @@ def test_two_rank_sharding():
         assert p.exitcode == 0
     assert t == 2.0                                   # max over ranks
     assert [r[-1] for r in allrecs] == list(range(11))  # rank-ordered gather keeps read order
+
+
+def test_fast5_files_are_dealt_round_robin():
+    from uncalled_b200.shard import local_files
+    files = ["f%d.fast5" % i for i in range(11)]
+    parts = [local_files(files, 4, r) for r in range(4)]
+    assert sorted(sum(parts, [])) == sorted(files) and [len(p) for p in parts] == [3, 3, 3, 2]
+    assert parts[1] == ["f1.fast5", "f5.fast5", "f9.fast5"] and local_files(files, 1, 0) == files

@@ -1,7 +1,8 @@
 """`uncalled index` and `uncalled map` (reference scripts/uncalled:38-78,127-167 with the options of
 uncalled/args.py:87-161,218-286) on this package: same sub-commands, option names, defaults, stderr progress
 lines and PAF output.  `python -m uncalled_b200 map <prefix> <fast5s...>`.  `--device` picks the GPU of this
-process (one process per GPU; shard the fast5 list across processes for more)."""
+process; under `torchrun --nproc-per-node N -m uncalled_b200 map ...` every rank maps its share of the fast5 files on
+its own GPU (reads are independent: no collective)."""
 import argparse
 import os
 import sys
@@ -104,11 +105,16 @@ def map_cmd(conf, args, out=None):
     assert_exists(conf.bwa_prefix + ".uncl")
     if len(conf.read_list) > 0:
         assert_exists(conf.read_list)
+    # one process per GPU (torchrun / mpirun): rank r maps the files i with i mod WORLD_SIZE == r on GPU LOCAL_RANK
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:
+        conf.device = int(os.environ.get("LOCAL_RANK", rank))
     mapper = MapPool(conf)
     sys.stderr.write("Loading fast5s\n")
-    for fast5 in load_fast5s(args.fast5s, args.recursive):
-        if fast5 is not None:
-            mapper.add_fast5(fast5)
+    from .shard import local_files
+    files = [f for f in load_fast5s(args.fast5s, args.recursive) if f is not None]
+    for fast5 in local_files(files, world, rank):
+        mapper.add_fast5(fast5)
     sys.stderr.write("Mapping\n")
     sys.stderr.flush()
     try:

@@ -12,6 +12,12 @@ def shard_bounds(n_reads, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def local_files(files, world, rank):
+    """fast5 files of a rank when `uncalled map` runs as one process per GPU: file i goes to rank i mod world
+    (files are the natural unit: each is opened and decoded by exactly one process)."""
+    return [f for i, f in enumerate(files) if i % int(world) == int(rank)]
+
+
 def channel_owner(channel, world):
     """Streaming path: channel `c` (0-based) lives on rank c mod world -- its persistent device state (detector,
     normaliser, path buffers, seed clusters) never moves, so chunks need no cross-rank exchange either."""

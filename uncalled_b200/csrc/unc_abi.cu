@@ -29,7 +29,11 @@ static_assert(sizeof(DevReadDesc) == 32, "DevReadDesc layout");
 #define K2_MIN_CTAS 2
 #endif
 #define K2_THREADS (K2_WARPS * 32)
+#ifdef K2_TRK_INLINE
+static_assert(K2_WARPS >= 1 && K2_WARPS <= K2_MAXSEG, "worker warps (all of them) must fit the sort segments");
+#else
 static_assert(K2_WARPS >= 2 && K2_WARPS - 1 <= K2_MAXSEG, "worker warps must fit the sort segments");
+#endif
 
 __global__ void k_kmer_ranges(DevIndex ix, uint2 *out) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;

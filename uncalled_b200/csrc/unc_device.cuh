@@ -721,6 +721,53 @@ UNC_DEV bool trk_get_final(const Tracker &t, const DevParams &p) {
            (p.min_top_conf > 0 && f_div(sl, second_len) >= p.min_top_conf);
 }
 
+#if defined(K2_TRK_INLINE) && defined(K2_OCC_STAGE)
+#error "K2_TRK_INLINE hands phase-B chunks out dynamically; the K2_OCC_STAGE pipeline assumes the static assignment"
+#endif
+#ifdef K2_TRK_INLINE
+// Prototype: no dedicated tracker warp.  All warps of the CTA are workers; worker warp 0 runs the seed clustering
+// of event e-1 as one out-of-line call at the start of event e, while the other warps already extend paths (phase B
+// hands out its chunks dynamically, so they absorb warp 0's late arrival).  Between calls the tracker's scalars
+// live in shared memory: [0..18] = Tracker fields, [19,20] = seeds so far, [21] = verdict, [22] = final event.
+UNC_DEV void trk_state_save(u32 *w, const Tracker &t) {
+    w[0] = t.nb; w[1] = t.n_alloc; w[2] = t.n_live; w[3] = t.n_lens; w[4] = t.top1; w[5] = t.top2;
+    w[6] = f2u(t.len_sum); w[7] = t.overflow;
+    w[8] = t.max_map.ren_start; w[9] = t.max_map.evt_en; w[10] = t.max_map.ref_st; w[11] = t.max_map.ren_end;
+    w[12] = t.max_map.evt_st; w[13] = t.max_map.total_len;
+}
+UNC_DEV void trk_state_load(const u32 *w, Tracker &t) {
+    t.nb = w[0]; t.n_alloc = w[1]; t.n_live = w[2]; t.n_lens = w[3]; t.top1 = w[4]; t.top2 = w[5];
+    t.len_sum = u2f(w[6]); t.overflow = w[7];
+    t.max_map.ren_start = w[8]; t.max_map.evt_en = w[9]; t.max_map.ref_st = w[10]; t.max_map.ren_end = w[11];
+    t.max_map.evt_st = w[12]; t.max_map.total_len = w[13];
+}
+// One event's seeds (ended paths of event evt-1 first, then the children's of evt) through SeedTracker::add_seed,
+// then get_final: what one iteration of the tracker warp's loop does.  Executed by one whole warp; returns the
+// verdict (0 go on, 1 mapped, 2 overflow).  Out of line, so that its registers do not add to the worker loops'.
+UNC_DEV_NOINLINE u32 unc_k2_track_event(uint4 *clu, uint4 *dir, u32 max_blocks, u32 min_map_len, float min_mean_conf,
+                                        float min_top_conf, const uint2 *rl, u32 n, u32 evt, u32 wk_overflow, u32 *state) {
+    Tracker trk;
+    trk.blocks = clu; trk.dir = dir; trk.max_blocks = max_blocks;
+    trk_state_load(state, trk);
+    DevParams pp;
+    pp.min_map_len = min_map_len; pp.min_mean_conf = min_mean_conf; pp.min_top_conf = min_top_conf;
+    for (u32 j = 0; j < n; j++) {
+        uint2 e = rl[j];
+        trk_add_seed(trk, pp, e.x, e.y & 0xFFu, (e.y & 0x100u) ? evt - 1u : evt);
+    }
+    const u32 v = (trk.overflow || wk_overflow) ? 2u : (trk_get_final(trk, pp) ? 1u : 0u);
+    w_sync();
+    if (w_lane() == 0) {
+        trk_state_save(state, trk);
+        const u64 ns = (((u64) state[20] << 32) | state[19]) + n;
+        state[19] = (u32) ns; state[20] = (u32) (ns >> 32);
+        if (v) { state[21] = v; state[22] = evt; }
+    }
+    w_sync();
+    return v;
+}
+#endif
+
 // ------------------------------------------------------------------ K2: mapper (one CTA per read)
 //
 // Warp 0 of the CTA is the TRACKER: it owns the seed-cluster set (sequential by nature) and
@@ -777,6 +824,9 @@ struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
     u32 wl_cnt;            // deferred window look-ups of the event in flight
     u32 cnt_blocks, cnt_steps;
     u32 tot_children[2], tot_sources[2];   // u64 as two words, written by a worker at the end
+#ifdef K2_TRK_INLINE
+    u32 trk_state[24];     // the seed tracker's scalars between its per-event calls (see unc_k2_track_event)
+#endif
 };
 
 // exclusive scan over the K2_RB*K2_MAXSEG sort counters by the worker threads:
@@ -849,6 +899,52 @@ UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *
     c_sync();
 }
 
+// The read's result record (one lane): reference src/mapper.cpp:631-653 (get_final -> set_ref_loc), :708-728,
+// bwa_index.hpp:213-220
+UNC_DEV void unc_k2_write_record(const DevIndex &ix, const DevParams &p, const DevBatch &B, K2Shared *sh, u32 r,
+                                 const Tracker &trk, u32 verdict, u32 final_event, u64 n_seeds) {
+    const float mel = B.mean_event_len[r];
+    const float bp_per_samp = f_div(p.bp_per_sec, p.sample_rate);
+    DevRec o;
+    o.mapped = 0; o.fwd = 0; o.rid = -1; o.status = verdict == 2u ? -7 : 0;
+    o.n_events = B.n_events[r]; o.events_used = final_event; o.matches = 0; o.n_clusters = trk.n_live;
+    o.rd_len = f_to_u64(f_mul((float) (u64) B.reads[r].n_samples, bp_per_samp));
+    o.rd_st = o.rd_en = o.rf_st = o.rf_en = o.rf_len = 0;
+    if (verdict == 1u) {
+        const Clu &sc = trk.max_map;
+        bool fwd = sc.ref_st < ix.seq_len / 2u;
+        u64 sa_st = fwd ? (u64) sc.ref_st : (u64) ix.seq_len - ((u64) sc.ren_end + 4u);
+        o.rd_st = unc_event_to_bp(sc.evt_st - UNC_SEED_LEN, false, mel, bp_per_samp);
+        o.rd_en = unc_event_to_bp(sc.evt_en, true, mel, bp_per_samp);
+        o.rd_len = unc_event_to_bp(final_event, true, mel, bp_per_samp);
+        // bns_pos2rid (reference submods/bwa/bntseq.c:354-368)
+        int rid = -1;
+        if ((long long) sa_st < (long long) B.l_pac) {
+            int left = 0, mid = 0, right = (int) B.n_seqs;
+            while (left < right) {
+                mid = (left + right) >> 1;
+                if (sa_st >= B.seq_offsets[mid]) {
+                    if (mid == (int) B.n_seqs - 1) break;
+                    if (sa_st < B.seq_offsets[mid + 1]) break;
+                    left = mid + 1;
+                } else right = mid;
+            }
+            rid = mid;
+        }
+        u64 rf_st = 0, rf_len = 0;
+        if (rid >= 0) { rf_st = sa_st - B.seq_offsets[rid]; rf_len = B.seq_lens[rid]; }
+        o.mapped = 1; o.fwd = fwd ? 1 : 0; o.rid = rid;
+        o.rf_st = rf_st; o.rf_len = rf_len;
+        o.rf_en = rf_st + ((u64) sc.ren_end - (u64) sc.ref_st + 5u);
+        o.matches = (sc.total_len + 4u) & 0xFFFFu;
+    }
+    o.n_children = ((u64) sh->tot_children[1] << 32) | sh->tot_children[0];
+    o.n_sources = ((u64) sh->tot_sources[1] << 32) | sh->tot_sources[0];
+    o.n_seeds = n_seeds;
+    o.n_occ_blocks = sh->cnt_blocks; o.n_sa_steps = sh->cnt_steps;
+    B.out[r] = o;
+}
+
 // ---- tracker warp (warp 0): reference src/mapper.cpp:513-519,601 (update_seeds order),
 //      :631-653 (get_final -> set_ref_loc), :708-728, bwa_index.hpp:213-220
 template <bool STREAM>
@@ -897,48 +993,7 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
         ms->started = 1;
     }
     // all workers have passed the final barrier: their counters are in shared memory
-    if (lane == 0) {
-        const float mel = B.mean_event_len[r];
-        const float bp_per_samp = f_div(p.bp_per_sec, p.sample_rate);
-        DevRec o;
-        o.mapped = 0; o.fwd = 0; o.rid = -1; o.status = verdict == 2u ? -7 : 0;
-        o.n_events = B.n_events[r]; o.events_used = final_event; o.matches = 0; o.n_clusters = trk.n_live;
-        o.rd_len = f_to_u64(f_mul((float) (u64) B.reads[r].n_samples, bp_per_samp));
-        o.rd_st = o.rd_en = o.rf_st = o.rf_en = o.rf_len = 0;
-        if (verdict == 1u) {
-            const Clu &sc = trk.max_map;
-            bool fwd = sc.ref_st < ix.seq_len / 2u;
-            u64 sa_st = fwd ? (u64) sc.ref_st : (u64) ix.seq_len - ((u64) sc.ren_end + 4u);
-            o.rd_st = unc_event_to_bp(sc.evt_st - UNC_SEED_LEN, false, mel, bp_per_samp);
-            o.rd_en = unc_event_to_bp(sc.evt_en, true, mel, bp_per_samp);
-            o.rd_len = unc_event_to_bp(final_event, true, mel, bp_per_samp);
-            // bns_pos2rid (reference submods/bwa/bntseq.c:354-368)
-            int rid = -1;
-            if ((long long) sa_st < (long long) B.l_pac) {
-                int left = 0, mid = 0, right = (int) B.n_seqs;
-                while (left < right) {
-                    mid = (left + right) >> 1;
-                    if (sa_st >= B.seq_offsets[mid]) {
-                        if (mid == (int) B.n_seqs - 1) break;
-                        if (sa_st < B.seq_offsets[mid + 1]) break;
-                        left = mid + 1;
-                    } else right = mid;
-                }
-                rid = mid;
-            }
-            u64 rf_st = 0, rf_len = 0;
-            if (rid >= 0) { rf_st = sa_st - B.seq_offsets[rid]; rf_len = B.seq_lens[rid]; }
-            o.mapped = 1; o.fwd = fwd ? 1 : 0; o.rid = rid;
-            o.rf_st = rf_st; o.rf_len = rf_len;
-            o.rf_en = rf_st + ((u64) sc.ren_end - (u64) sc.ref_st + 5u);
-            o.matches = (sc.total_len + 4u) & 0xFFFFu;
-        }
-        o.n_children = ((u64) sh->tot_children[1] << 32) | sh->tot_children[0];
-        o.n_sources = ((u64) sh->tot_sources[1] << 32) | sh->tot_sources[0];
-        o.n_seeds = n_seeds;
-        o.n_occ_blocks = sh->cnt_blocks; o.n_sa_steps = sh->cnt_steps;
-        B.out[r] = o;
-    }
+    if (lane == 0) unc_k2_write_record(ix, p, B, sh, r, trk, verdict, final_event, n_seeds);
 }
 
 #if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
@@ -966,11 +1021,24 @@ UNC_DEV long long pt_clock() { long long v; asm volatile("mov.u64 %0, %%clock64;
 
 UNC_DEV u32 k2_pre_pack(u32 epoch, u32 state) { return (epoch << 2) | state; }
 
+#ifdef K2_TRK_INLINE
+// next chunk of 32 parents for this warp (phase B): a shared counter, so that a warp that arrives late takes less
+UNC_DEV u32 k2_grab_chunk(K2Shared *sh) {
+    u32 c = 0;
+    if (w_lane() == 0) c = s_atomic_add(&sh->bc[4], 1u);
+    return w_shfl(c, 0);
+}
+#endif
+
 template <bool STREAM>
 UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
                             K2Shared *sh, u32 r, u32 n_first, u32 n_limit, u32 *epoch_io) {
     const int lane = w_lane();
+#ifdef K2_TRK_INLINE
+    const u32 wt = (u32) c_tid(), nwt = (u32) c_nthreads();               // every warp is a worker
+#else
     const u32 wt = (u32) c_tid() - 32u, nwt = (u32) c_nthreads() - 32u;   // worker thread index / count
+#endif
     const u32 ww = wt >> 5, nwk = nwt >> 5;                               // worker warp index / count
     const K2Tables *tb = &sh->tb;
     const u32 maxp = p.max_paths;
@@ -1008,6 +1076,15 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         u32 *onext = W.order + (size_t) (gen ^ 1u) * maxp;
         uint4 *ckA = W.ckey, *ckB = W.ckey + maxp, *cks = W.cks;
         uint2 *rlist = W.rlist + (size_t) (event_i & 1u) * W.rl_cap;
+#ifdef K2_TRK_INLINE
+        if (ww == 0 && event_i > n_first) {             // seed clustering of the previous event, while the others extend
+            const u32 pe = event_i - 1u;
+            const u32 tv = unc_k2_track_event(W.clu, W.dir, W.max_blocks, p.min_map_len, p.min_mean_conf, p.min_top_conf,
+                                              W.rlist + (size_t) (pe & 1u) * W.rl_cap, *(volatile u32 *) &sh->n_rows[pe & 1u],
+                                              pe, *(volatile u32 *) &sh->wk_overflow, sh->trk_state);
+            if (lane == 0) *(volatile u32 *) &sh->verdict[pe & 1u] = tv;
+        }
+#endif
 
         // ---- B. extend every previous path (reference src/mapper.cpp:455-524): chunk c of 32
         //      parents writes its children, in emission order, to records/keys [c*160, c*160+count)
@@ -1020,17 +1097,28 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         // the rare range that crosses an Occ block boundary fetches the second block per base.
         {
             u32 oi_n = UNC_INVALID; uint4 q0_n = make_uint4(0, 0, 0, 0);
-            if (ww < nch_prev) {
-                u32 pi = ww * 32 + (u32) lane;
+#ifdef K2_TRK_INLINE
+            const u32 c_first = k2_grab_chunk(sh);      // chunks are handed out dynamically (sh->bc[4])
+#else
+            const u32 c_first = ww;
+#endif
+            if (c_first < nch_prev) {
+                u32 pi = c_first * 32 + (u32) lane;
                 if (pi < prev_size) oi_n = oprev[pi];
                 if (!(oi_n & UNC_INVALID)) q0_n = prev[(size_t) oi_n * 2];
             }
-            for (u32 c = ww; c < nch_prev; c += nwk) {
+#ifdef K2_TRK_INLINE
+            for (u32 c = c_first, cn; c < nch_prev; c = cn) {
+                cn = k2_grab_chunk(sh);
+#else
+            for (u32 c = c_first; c < nch_prev; c += nwk) {
+                const u32 cn = c + nwk;
+#endif
                 const u32 oi = oi_n;
                 const uint4 q0 = q0_n;
                 const bool valid = !(oi & UNC_INVALID);
-                if (c + nwk < nch_prev) {
-                    u32 pi = (c + nwk) * 32 + (u32) lane;
+                if (cn < nch_prev) {
+                    u32 pi = cn * 32 + (u32) lane;
                     oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
                     if (!(oi_n & UNC_INVALID)) q0_n = prev[(size_t) oi_n * 2];
                 }
@@ -1177,17 +1265,28 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
 #else
             // software prefetch of the next chunk's order entry + record head
             u32 oi_n = UNC_INVALID; uint4 q0_n = make_uint4(0, 0, 0, 0), q1_n = make_uint4(0, 0, 0, 0);
-            if (ww < nch_prev) {
-                u32 pi = ww * 32 + (u32) lane;
+#ifdef K2_TRK_INLINE
+            const u32 c_first = k2_grab_chunk(sh);      // chunks are handed out dynamically (sh->bc[4])
+#else
+            const u32 c_first = ww;
+#endif
+            if (c_first < nch_prev) {
+                u32 pi = c_first * 32 + (u32) lane;
                 if (pi < prev_size) oi_n = oprev[pi];
                 if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = pr[1]; }
             }
-            for (u32 c = ww; c < nch_prev; c += nwk) {
+#ifdef K2_TRK_INLINE
+            for (u32 c = c_first, cn; c < nch_prev; c = cn) {
+                cn = k2_grab_chunk(sh);
+#else
+            for (u32 c = c_first; c < nch_prev; c += nwk) {
+                const u32 cn = c + nwk;
+#endif
                 const u32 oi = oi_n;
                 const uint4 q0 = q0_n, q1 = q1_n;
                 const bool valid = !(oi & UNC_INVALID);
-                if (c + nwk < nch_prev) {
-                    u32 pi = (c + nwk) * 32 + (u32) lane;
+                if (cn < nch_prev) {
+                    u32 pi = cn * 32 + (u32) lane;
                     oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
                     if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = pr[1]; }
                 }
@@ -1311,6 +1410,9 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         }
         c_sync_sub(1, (int) nwt);
         if (wt == 0) sh->wl_cnt = 0;
+#ifdef K2_TRK_INLINE
+        if (wt == 0) sh->bc[4] = 0;
+#endif
         PT_MARK(1)
 
         // ---- B2. ended-path seed rows and compaction of the sort keys into emission order
@@ -1739,6 +1841,15 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         prev_size = nn;
         gen ^= 1u;
     }
+#ifdef K2_TRK_INLINE
+    // the last event's seeds (the tracker warp took them while the workers waited at the final barrier)
+    if (ww == 0 && event_i == n_limit && n_limit > n_first) {
+        const u32 pe = n_limit - 1u;
+        unc_k2_track_event(W.clu, W.dir, W.max_blocks, p.min_map_len, p.min_mean_conf, p.min_top_conf,
+                           W.rlist + (size_t) (pe & 1u) * W.rl_cap, *(volatile u32 *) &sh->n_rows[pe & 1u], pe,
+                           *(volatile u32 *) &sh->wk_overflow, sh->trk_state);
+    }
+#endif
     *epoch_io = epoch;
     if (STREAM && wt == 0) { DevMapState *ms = B.mstate + B.chan[r]; ms->prev_size = prev_size; ms->gen = gen; }
     PT_FLUSH(B, r)
@@ -1770,11 +1881,49 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
     if (tid == 0) {
         sh->cnt_blocks = 0; sh->cnt_steps = 0; sh->wk_overflow = 0; sh->wl_cnt = 0;
         sh->verdict[0] = sh->verdict[1] = 0; sh->n_rows[0] = sh->n_rows[1] = 0; sh->bc[1] = 0;
+#ifdef K2_TRK_INLINE
+        sh->bc[4] = 0;
+        Tracker t0;
+        t0.blocks = W.clu; t0.dir = W.dir; t0.max_blocks = W.max_blocks;
+        trk_reset(t0);
+        if (STREAM) {
+            const DevMapState *ms = B.mstate + B.chan[r];
+            if (ms->started) {
+                t0.nb = ms->t_nb; t0.n_alloc = ms->t_n_alloc; t0.n_live = ms->t_n_live; t0.n_lens = ms->t_n_lens;
+                t0.top1 = ms->t_top1; t0.top2 = ms->t_top2; t0.overflow = ms->t_overflow; t0.len_sum = ms->t_len_sum;
+                t0.max_map.ren_start = ms->t_max_map[0]; t0.max_map.evt_en = ms->t_max_map[1]; t0.max_map.ref_st = ms->t_max_map[2];
+                t0.max_map.ren_end = ms->t_max_map[3]; t0.max_map.evt_st = ms->t_max_map[4]; t0.max_map.total_len = ms->t_max_map[5];
+            }
+        }
+        trk_state_save(sh->trk_state, t0);
+        sh->trk_state[19] = sh->trk_state[20] = 0; sh->trk_state[21] = 0; sh->trk_state[22] = n_limit;
+#endif
     }
     for (u32 b = tid; b < K2_RB * K2_MAXSEG; b += (u32) c_nthreads()) sh->hist_next[b] = 0;
     c_sync();
+#ifdef K2_TRK_INLINE
+    unc_k2_workers<STREAM>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
+    c_sync();
+    if (tid == 0) {
+        Tracker t1;
+        t1.blocks = W.clu; t1.dir = W.dir; t1.max_blocks = W.max_blocks;
+        trk_state_load(sh->trk_state, t1);
+        const u32 verdict = sh->trk_state[21], final_event = sh->trk_state[22];
+        if (STREAM) {
+            DevMapState *ms = B.mstate + B.chan[r];
+            ms->t_nb = t1.nb; ms->t_n_alloc = t1.n_alloc; ms->t_n_live = t1.n_live; ms->t_n_lens = t1.n_lens;
+            ms->t_top1 = t1.top1; ms->t_top2 = t1.top2; ms->t_overflow = t1.overflow; ms->t_len_sum = t1.len_sum;
+            ms->t_max_map[0] = t1.max_map.ren_start; ms->t_max_map[1] = t1.max_map.evt_en; ms->t_max_map[2] = t1.max_map.ref_st;
+            ms->t_max_map[3] = t1.max_map.ren_end; ms->t_max_map[4] = t1.max_map.evt_st; ms->t_max_map[5] = t1.max_map.total_len;
+            ms->event_i = final_event;
+            ms->started = 1;
+        }
+        unc_k2_write_record(ix, p, B, sh, r, t1, verdict, final_event, ((u64) sh->trk_state[20] << 32) | sh->trk_state[19]);
+    }
+#else
     if (tid < 32) unc_k2_tracker<STREAM>(ix, p, B, W, sh, r, n_first, n_limit);
     else unc_k2_workers<STREAM>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
+#endif
     c_sync();
     if (STREAM && tid < 32) B.mstate[B.chan[r]].flags[tid] = sh->flags[tid];
 }

@@ -18,14 +18,15 @@ d = U.make_descs([4000] * n_reads)
 for it in range(2):
     out = bm.map(sig.ravel(), d)
     print("iter", it, bm.timing())
-ph2 = np.zeros((n_reads, 16), np.uint64)
+ph2 = np.zeros((n_reads, 32), np.uint64)
 L = N.lib()
 L.unc_pool_debug_phases.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
 N.check(L.unc_pool_debug_phases(bm.h, n_reads, ph2.ctypes.data))
-names = ["A probs", "B extend + B1 deferred seed_prob", "B2 scan/ended rows/key compaction", "C radix sort + fix-up", "D dedup/src", "S sa + E", "X barrier(tracker)", "loop head"]
+names = ["A probs", "B extend + B1 deferred seed_prob", "B2 scan/ended rows/key compaction", "C radix sort + fix-up", "D dedup/src", "S sa + E",
+         "X barrier(tracker)", "head: event load + scaling", "head: verdict + bookkeeping", "head: loop back-edge"]
 ev = out["events_used"].astype(np.float64) + 1
-for title, ph in (("worker warp 0, thread 0 (also runs the single-warp sections)", ph2[:, :8]),
-                  ("last worker warp, lane 0 (its barrier waits expose the single-warp sections)", ph2[:, 8:])):
+for title, ph in (("worker warp 0, thread 0 (also runs the single-warp sections)", ph2[:, :10]),
+                  ("last worker warp, lane 0 (its barrier waits expose the single-warp sections)", ph2[:, 16:26])):
     tot = ph.sum(axis=0).astype(np.float64)
     print("--", title)
     print("total events", ev.sum())

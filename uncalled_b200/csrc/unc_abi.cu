@@ -430,8 +430,8 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     PT(cudaMalloc(&P->d_k1_flags, (size_t) max_reads * 4));
     PT(cudaMalloc(&P->d_out, (size_t) max_reads * sizeof(DevRec)));
 #ifdef UNC_PHASE_TIMING
-    PT(cudaMalloc(&P->d_dbg, (size_t) max_reads * 128));
-    PT(cudaMemset(P->d_dbg, 0, (size_t) max_reads * 128));
+    PT(cudaMalloc(&P->d_dbg, (size_t) max_reads * 256));
+    PT(cudaMemset(P->d_dbg, 0, (size_t) max_reads * 256));
 #endif
     PT(cudaMallocHost(&P->h_out, (size_t) max_reads * sizeof(unc_paf_rec)));
 #undef PT
@@ -664,7 +664,7 @@ int unc_fm_sa(const unc_index *x, uint32_t n, const uint64_t *rows, uint64_t *ou
 // debug builds (-DUNC_PHASE_TIMING): per-read cycle counters of the mapper's phases
 int unc_pool_debug_phases(const unc_pool *P, uint32_t n, unsigned long long *out) {
     if (!P || !out || !P->d_dbg) return fail(UNC_E_ARG, "phase timing not compiled in");
-    CUDA_TRY(cudaMemcpy(out, P->d_dbg, (size_t) n * 128, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out, P->d_dbg, (size_t) n * 256, cudaMemcpyDeviceToHost));
     return UNC_OK;
 }
 

@@ -999,12 +999,13 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
 #if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
 // cycle counter with a compiler memory barrier, so that loads/stores of a phase are not scheduled across a mark
 UNC_DEV long long pt_clock() { long long v; asm volatile("mov.u64 %0, %%clock64;" : "=l"(v) :: "memory"); return v; }
-#define PT_DECL unsigned long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = pt_clock();
+#define PT_DECL unsigned long long pt_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = pt_clock();
 #define PT_MARK(i) { long long _n = pt_clock(); pt_acc[i] += (unsigned long long) (_n - pt_t); pt_t = _n; }
 // two observers per read: thread 0 of worker warp 0 (which also runs the single-warp sections: chunk scan,
 // ended rows, fresh sources) -> counters 0..7, and lane 0 of the LAST worker warp (never runs them, so its
-// barrier waits expose them) -> counters 8..15
-#define PT_FLUSH(B, r) if ((B).dbg && (wt == 0 || wt == nwt - 32u)) { for (int _i = 0; _i < 8; _i++) (B).dbg[(size_t) (r) * 16 + (wt == 0 ? 0 : 8) + _i] = pt_acc[_i]; }
+// barrier waits expose them) -> counters 16..31.  Marks 0..6 = phases A..X, 8 = verdict + bookkeeping after the event
+// barrier, 9 = loop back-edge, 7 = the event's load and scaling (8 + 9 + 7 = the former "loop head")
+#define PT_FLUSH(B, r) if ((B).dbg && (wt == 0 || wt == nwt - 32u)) { for (int _i = 0; _i < 16; _i++) (B).dbg[(size_t) (r) * 32 + (wt == 0 ? 0 : 16) + _i] = pt_acc[_i]; }
 #else
 #define PT_DECL
 #define PT_MARK(i)
@@ -1061,6 +1062,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
     PT_DECL
 
     for (; event_i < n_limit; event_i++) {
+        PT_MARK(9)
         const float event = f_add(f_mul(scale, events[event_i - n_first]), shift);
         PT_MARK(7)
 
@@ -1840,6 +1842,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         pend_children = pend_sources = pend_blocks = pend_steps = 0;
         prev_size = nn;
         gen ^= 1u;
+        PT_MARK(8)
     }
 #ifdef K2_TRK_INLINE
     // the last event's seeds (the tracker warp took them while the workers waited at the final barrier)

@@ -67,14 +67,17 @@ def test_full_buffer_semantics(g200k, max_paths):
 
 @pytest.mark.parametrize("flags,tag", [(("-DK2_LEAN_B",), "_lean"), (("-DK2_LEAN_B", "-DK2_PAR_E"), "_lean_pare"),
                                       (("-DK2_SCAN2",), "_scan2"), (("-DK2_TRK_INLINE",), "_trk"),
-                                      (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2"), "_trk_lean_pare_scan2")])
+                                      (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2"), "_trk_lean_pare_scan2"),
+                                      (("-DK2_PF2",), "_pf2"),
+                                      (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2", "-DK2_PF2"), "_all")])
 def test_prototype_variants_keep_parity(g200k, flags, tag):
     """Compile-time prototypes for a higher-occupancy build must produce the same paths, seeds and PAF records:
     -DK2_LEAN_B (children written to fixed per-parent slots the moment their base is resolved, Occ words read on
     demand), -DK2_PAR_E (the fresh-source walk spread over all worker warps with the serial walk's buffer cut) and
     -DK2_SCAN2 (radix-pass counter scan with one barrier less), -DK2_TRK_INLINE (no dedicated tracker warp: every warp
     works, worker warp 0 clusters the previous event's seeds in one out-of-line call while the others already extend
-    paths from a dynamic chunk counter)."""
+    paths from a dynamic chunk counter), -DK2_PF2 (order entries fetched two chunks ahead of the extension, compaction keys
+    one chunk ahead)."""
     prefix, g = g200k
     E = emulib.Emu(prefix, extra_flags=flags, tag=tag)
     O = orclib.Oracle(prefix)

@@ -786,6 +786,10 @@ UNC_DEV_NOINLINE u32 unc_k2_track_event(uint4 *clu, uint4 *dir, u32 max_blocks, 
 // (C, parent idx); only ~2 % of children have a full-length parent, and those look-ups are
 // deferred to a separate pass so the extension loop never waits on the 22-hop walk.
 // Sort key (ckey) = (fm_start, fm_end, seed_prob bits, kmer | seedable<<10 | move_count<<11 | emission idx<<16)
+#ifdef K2_PF2      /* deeper software prefetch: phase B (order entry two chunks ahead) and key compaction */
+#define K2_PF2_B
+#define K2_PF2_C
+#endif
 #define K2_MAXCH 1024u     /* chunks of 32 paths (max_paths <= 32767) */
 #define K2_RBITS 8u        /* radix digit width of the child sort */
 #define K2_RB 256u
@@ -1030,6 +1034,11 @@ UNC_DEV u32 k2_grab_chunk(K2Shared *sh) {
     return w_shfl(c, 0);
 }
 #endif
+#ifdef K2_TRK_INLINE
+#define K2_NEXT_CHUNK(c) k2_grab_chunk(sh)
+#else
+#define K2_NEXT_CHUNK(c) ((c) + nwk)
+#endif
 
 template <bool STREAM>
 UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
@@ -1109,6 +1118,20 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 if (pi < prev_size) oi_n = oprev[pi];
                 if (!(oi_n & UNC_INVALID)) q0_n = prev[(size_t) oi_n * 2];
             }
+#ifdef K2_PF2_B
+            u32 oi_nn = UNC_INVALID;                    // order entries two chunks ahead, record heads one (see below)
+            const u32 c_second = K2_NEXT_CHUNK(c_first);
+            if (c_second < nch_prev) { u32 pi = c_second * 32 + (u32) lane; if (pi < prev_size) oi_nn = oprev[pi]; }
+            for (u32 c = c_first, cn = c_second, cnn = 0; c < nch_prev; c = cn, cn = cnn) {
+                cnn = K2_NEXT_CHUNK(cn);
+                const u32 oi = oi_n;
+                const uint4 q0 = q0_n;
+                const bool valid = !(oi & UNC_INVALID);
+                oi_n = oi_nn;
+                if (cn < nch_prev && !(oi_n & UNC_INVALID)) q0_n = prev[(size_t) oi_n * 2];
+                oi_nn = UNC_INVALID;
+                if (cnn < nch_prev) { u32 pi = cnn * 32 + (u32) lane; if (pi < prev_size) oi_nn = oprev[pi]; }
+#else
 #ifdef K2_TRK_INLINE
             for (u32 c = c_first, cn; c < nch_prev; c = cn) {
                 cn = k2_grab_chunk(sh);
@@ -1124,6 +1147,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                     oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
                     if (!(oi_n & UNC_INVALID)) q0_n = prev[(size_t) oi_n * 2];
                 }
+#endif
                 const u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
                 const u32 moves = q0.w & UNC_PATH_MASK, sa_checked = q0.w >> 31;
                 u32 cmask = 0;
@@ -1277,6 +1301,22 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 if (pi < prev_size) oi_n = oprev[pi];
                 if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = pr[1]; }
             }
+#ifdef K2_PF2_B
+            // prototype: the record's address depends on the order entry (two dependent loads), so the order entry is
+            // fetched TWO chunks ahead and the record one chunk ahead
+            u32 oi_nn = UNC_INVALID;
+            const u32 c_second = K2_NEXT_CHUNK(c_first);
+            if (c_second < nch_prev) { u32 pi = c_second * 32 + (u32) lane; if (pi < prev_size) oi_nn = oprev[pi]; }
+            for (u32 c = c_first, cn = c_second, cnn = 0; c < nch_prev; c = cn, cn = cnn) {
+                cnn = K2_NEXT_CHUNK(cn);
+                const u32 oi = oi_n;
+                const uint4 q0 = q0_n, q1 = q1_n;
+                const bool valid = !(oi & UNC_INVALID);
+                oi_n = oi_nn;
+                if (cn < nch_prev && !(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = pr[1]; }
+                oi_nn = UNC_INVALID;
+                if (cnn < nch_prev) { u32 pi = cnn * 32 + (u32) lane; if (pi < prev_size) oi_nn = oprev[pi]; }
+#else
 #ifdef K2_TRK_INLINE
             for (u32 c = c_first, cn; c < nch_prev; c = cn) {
                 cn = k2_grab_chunk(sh);
@@ -1292,6 +1332,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                     oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
                     if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = pr[1]; }
                 }
+#endif
 #endif
                 u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
                 u32 moves = q0.w & UNC_PATH_MASK, sa_checked = q0.w >> 31;
@@ -1478,6 +1519,36 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             }
         }
 #else
+#ifdef K2_PF2_C
+            // prototype: the first 32 keys of the warp's next chunk are requested before the current chunk's are
+            // stored and counted (a chunk rarely holds more than 32 children)
+            uint4 kpre = make_uint4(0, 0, 0, 0);
+            if (ww < nch_prev) {
+                const u32 b0 = sh->bcnt[ww], e0 = ww + 1 < nch_prev ? sh->bcnt[ww + 1] : nc_total;
+                if (b0 + (u32) lane < e0 && b0 + (u32) lane < nc) kpre = cks[(size_t) ww * K2_CH_SLOTS + (u32) lane];
+            }
+            for (u32 c = ww; c < nch_prev; c += nwk) {
+                const u32 base = sh->bcnt[c];
+                if (base >= nc) break;                              // later chunks lie beyond the max_paths cut
+                const u32 end = c + 1 < nch_prev ? sh->bcnt[c + 1] : nc_total;
+                u32 seg = base / seg_len, bound = (seg + 1u) * seg_len;
+                const uint4 kcur = kpre;
+                if (c + nwk < nch_prev) {
+                    const u32 bn = sh->bcnt[c + nwk], en = c + nwk + 1 < nch_prev ? sh->bcnt[c + nwk + 1] : nc_total;
+                    if (bn + (u32) lane < en && bn + (u32) lane < nc) kpre = cks[(size_t) (c + nwk) * K2_CH_SLOTS + (u32) lane];
+                }
+                for (u32 i = (u32) lane; base + i < end; i += 32) {
+                    const u32 di = base + i;
+                    if (di < nc) {
+                        uint4 key = i < 32 ? kcur : cks[(size_t) c * K2_CH_SLOTS + i];
+                        ckA[di] = key;
+                        while (di >= bound) { seg++; bound += seg_len; }
+                        s_atomic_add(&sh->hist_next[(key.x & (K2_RB - 1u)) * K2_MAXSEG + seg], 1u);
+                    }
+                }
+            }
+        }
+#else
             for (u32 c = ww; c < nch_prev; c += nwk) {
                 const u32 base = sh->bcnt[c];
                 if (base >= nc) break;                              // later chunks lie beyond the max_paths cut
@@ -1494,6 +1565,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 }
             }
         }
+#endif
 #endif
         c_sync_sub(1, (int) nwt);
         u32 n_rows = sh->bc[3];

@@ -65,10 +65,8 @@ def test_full_buffer_semantics(g200k, max_paths):
     _check(E, O, [sig[i] for i in range(4)])
 
 
-@pytest.mark.parametrize("flags,tag", [(("-DK2_LEAN_B",), "_lean"), (("-DK2_LEAN_B", "-DK2_PAR_E"), "_lean_pare"),
-                                      (("-DK2_SCAN2",), "_scan2"), (("-DK2_TRK_INLINE",), "_trk"),
-                                      (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2"), "_trk_lean_pare_scan2"),
-                                      (("-DK2_PF2",), "_pf2"),
+@pytest.mark.parametrize("flags,tag", [(("-DK2_LEAN_B", "-DK2_PAR_E"), "_lean_pare"), (("-DK2_TRK_INLINE",), "_trk"),
+                                      (("-DK2_SCAN2", "-DK2_PF2"), "_scan2_pf2"),
                                       (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2", "-DK2_PF2"), "_all")])
 def test_prototype_variants_keep_parity(g200k, flags, tag):
     """Compile-time prototypes for a higher-occupancy build must produce the same paths, seeds and PAF records:

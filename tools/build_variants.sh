@@ -28,6 +28,7 @@ build scan2 -DK2_SCAN2 &
 build trk -DK2_TRK_INLINE &
 build trk_scan2 -DK2_TRK_INLINE -DK2_SCAN2 &
 build pf2 -DK2_PF2 &
+build bmatch -DK2_BMATCH &
 build trk_pf2 -DK2_TRK_INLINE -DK2_PF2 &
 build lean_pare_scan2_c3 -DK2_LEAN_B -DK2_PAR_E -DK2_SCAN2 -DK2_MIN_CTAS=3 &
 wait

@@ -1596,7 +1596,18 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                     kn = kn2;
                     if (c + 2 < c_hi && g + 64 < nc) kn2 = src[g + 64];
                     u32 dg = a ? ((k.x >> sb) & (K2_RB - 1u)) : K2_RB + (u32) lane;  // inactive lanes: unique digit
+#ifdef K2_BMATCH
+                    // prototype: lanes with the same 8-bit digit from eight ballots instead of match.any
+                    u32 peers = w_ballot(a);
+#pragma unroll
+                    for (u32 b = 0; b < K2_RBITS; b++) {
+                        const u32 bal = w_ballot((dg >> b) & 1u);
+                        peers &= ((dg >> b) & 1u) ? bal : ~bal;
+                    }
+                    if (!a) peers = 1u << lane;
+#else
                     u32 peers = w_match(dg);
+#endif
                     u32 rank = (u32) d_popc(peers & lt);
                     int leader = d_ffs(peers) - 1;
                     u32 bpos = 0;

@@ -11,7 +11,12 @@ def one(lib, n_reads):
     import uncalled_b200 as U
     import synth, synthdata
     prefix, g = synthdata.get_index("g4m7")
-    sig, _ = synth.reads(g, n_reads, 4000, seed=7)
+    cache = "/tmp/unc_variants_sig_%d.npy" % n_reads          # the same signals for every variant: generate once per box
+    if os.path.exists(cache):
+        sig = np.load(cache)
+    else:
+        sig, _ = synth.reads(g, n_reads, 4000, seed=7)
+        np.save(cache, sig)
     idx = U.Index(prefix, device=0)
     bm = U.BatchMapper(idx, max_reads=n_reads, max_samples=n_reads * 4000)
     d = U.make_descs([4000] * n_reads)
@@ -38,5 +43,8 @@ if __name__ == "__main__":
                 for kv in f[:-3].split("__")[1:]:
                     k, v = kv.split("=")
                     env[k] = v
-                r = subprocess.run([sys.executable, __file__, "--one", os.path.join(vdir, f), str(n)], capture_output=True, text=True, timeout=600, env=env)
-                print(r.stdout.strip() or ("FAILED %s: %s" % (f, r.stderr[-400:])), flush=True)
+                try:
+                    r = subprocess.run([sys.executable, __file__, "--one", os.path.join(vdir, f), str(n)], capture_output=True, text=True, timeout=300, env=env)
+                    print(r.stdout.strip() or ("FAILED %s: %s" % (f, r.stderr[-400:])), flush=True)
+                except subprocess.TimeoutExpired:
+                    print("TIMEOUT %s" % f, flush=True)

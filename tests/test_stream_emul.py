@@ -57,11 +57,13 @@ def test_max_chunks_and_one_second_chunks(g200k):
     _check(E, O, [sig[i][:4500] for i in range(2)], 2, 4000, n_warps=2)   # chunk_time 1.0 s, a 2-warp CTA
 
 
-def test_tracker_inline_variant_streams_identically(g200k):
+@pytest.mark.parametrize("flags,tag", [(("-DK2_TRK_INLINE",), "_trk"),
+                                      (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2", "-DK2_PF2"), "_all")])
+def test_tracker_inline_variant_streams_identically(g200k, flags, tag):
     """-DK2_TRK_INLINE keeps the seed tracker's state in shared memory between events and in the channel's
-    DevMapState between chunks: same results chunk by chunk."""
+    DevMapState between chunks: same results chunk by chunk (alone and with the other prototypes)."""
     prefix, g = g200k
-    E = emulib.Emu(prefix, extra_flags=("-DK2_TRK_INLINE",), tag="_trk")
+    E = emulib.Emu(prefix, extra_flags=flags, tag=tag)
     O = orclib.Oracle(prefix)
     sig, _ = synth.reads(g, 4, 5000, seed=5, frac_random=0.3)
     st = _check(E, O, [sig[i][:5000 - 37 * i] for i in range(4)], 2, 450)

@@ -67,7 +67,8 @@ def test_full_buffer_semantics(g200k, max_paths):
 
 @pytest.mark.parametrize("flags,tag", [(("-DK2_LEAN_B", "-DK2_PAR_E"), "_lean_pare"), (("-DK2_TRK_INLINE",), "_trk"),
                                       (("-DK2_SCAN2", "-DK2_PF2", "-DK2_BMATCH"), "_scan2_pf2_bmatch"),
-                                      (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2", "-DK2_PF2"), "_all")])
+                                      (("-DK2_DFUSE",), "_dfuse"),
+                                      (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2", "-DK2_PF2", "-DK2_DFUSE"), "_all")])
 def test_prototype_variants_keep_parity(g200k, flags, tag):
     """Compile-time prototypes for a higher-occupancy build must produce the same paths, seeds and PAF records:
     -DK2_LEAN_B (children written to fixed per-parent slots the moment their base is resolved, Occ words read on
@@ -75,7 +76,8 @@ def test_prototype_variants_keep_parity(g200k, flags, tag):
     -DK2_SCAN2 (radix-pass counter scan with one barrier less), -DK2_TRK_INLINE (no dedicated tracker warp: every warp
     works, worker warp 0 clusters the previous event's seeds in one out-of-line call while the others already extend
     paths from a dynamic chunk counter), -DK2_PF2 (order entries fetched two chunks ahead of the extension, compaction keys
-    one chunk ahead), -DK2_BMATCH (equal-digit lanes of the radix scatter from eight ballots instead of match.any)."""
+    one chunk ahead), -DK2_BMATCH (equal-digit lanes of the radix scatter from eight ballots instead of match.any), -DK2_DFUSE (the k-mer-run
+    aggregates of the dedup phase published inside its main pass: one pass over the keys and one barrier less)."""
     prefix, g = g200k
     E = emulib.Emu(prefix, extra_flags=flags, tag=tag)
     O = orclib.Oracle(prefix)

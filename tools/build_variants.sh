@@ -29,6 +29,7 @@ build trk -DK2_TRK_INLINE &
 build trk_scan2 -DK2_TRK_INLINE -DK2_SCAN2 &
 build pf2 -DK2_PF2 &
 build bmatch -DK2_BMATCH &
+build dfuse -DK2_DFUSE &
 build trk_pf2 -DK2_TRK_INLINE -DK2_PF2 &
 build lean_pare_scan2_c3 -DK2_LEAN_B -DK2_PAR_E -DK2_SCAN2 -DK2_MIN_CTAS=3 &
 wait
@@ -40,6 +41,8 @@ build trk_all_c4 $ALL -DK2_MIN_CTAS=4 &
 build trk_all_w16c2 $ALL -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
 wait
 build trk_all_pf2_c3 $ALL -DK2_PF2 -DK2_MIN_CTAS=3 &
+build trk_all_pf2_dfuse_c3 $ALL -DK2_PF2 -DK2_DFUSE -DK2_MIN_CTAS=3 &
+build trk_all_pf2_dfuse_bmatch_c3 $ALL -DK2_PF2 -DK2_DFUSE -DK2_BMATCH -DK2_MIN_CTAS=3 &
 build trk_all_pf2_w16c2 $ALL -DK2_PF2 -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
 wait
 # phase-timing builds (tools/gpu_phases.py <genome> <reads> <lib>)

@@ -797,10 +797,15 @@ UNC_DEV_NOINLINE u32 unc_k2_track_event(uint4 *clu, uint4 *dir, u32 max_blocks, 
 #define K2_MAXSEG 8u       /* max worker warps (sort segments) */
 #endif
 
-#ifdef K2_LEAN_B
-#define K2_DYN_PER_CHUNK 44u   /* pre 8 + agg 8 + bcnt 4 + ecnt 4 + cmb 20 bytes of dynamic shared memory per 32 paths */
+#ifdef K2_DFUSE
+#define K2_DYN_FUSE 16u        /* agg2: two tagged 64-bit words per chunk */
 #else
-#define K2_DYN_PER_CHUNK 24u
+#define K2_DYN_FUSE 0u
+#endif
+#ifdef K2_LEAN_B
+#define K2_DYN_PER_CHUNK (44u + K2_DYN_FUSE)   /* pre 8 + agg 8 + bcnt 4 + ecnt 4 + cmb 20 bytes of dynamic shared memory per 32 paths */
+#else
+#define K2_DYN_PER_CHUNK (24u + K2_DYN_FUSE)
 #endif
 struct K2Tables {
     uint2 kmer_range[UNC_NKMER];
@@ -820,6 +825,9 @@ struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
     u64 *pre;              // D2 look-back prefix words: (epoch<<2 | state) << 32 | sources | seeds<<16
     u32 *bcnt, *ecnt;      // children per chunk (then exclusive prefix), ended paths per chunk
     u32 *cmb;              // K2_LEAN_B: five ballot words per chunk (which fixed child slots are filled)
+#ifdef K2_DFUSE
+    u64 *agg2;             // the D1 aggregates as two epoch-tagged words per chunk, published inside D2
+#endif
     u32 bc[8];             // CTA broadcast scalars
     u32 scan_tmp[32];
     u32 n_rows[2];         // worker -> tracker: seed rows of event e in rlist[e & 1]
@@ -893,6 +901,13 @@ UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *
         sh->bcnt = (u32 *) base; base += (size_t) n_slots * 4;
         sh->ecnt = (u32 *) base; base += (size_t) n_slots * 4;
         sh->cmb = (u32 *) base;                        // n_slots * 20 bytes (used by the K2_LEAN_B build only)
+#ifdef K2_DFUSE
+#ifdef K2_LEAN_B
+        base += (size_t) n_slots * 20;
+#endif
+        base = (char *) ((((size_t) base) + 7) & ~(size_t) 7);
+        sh->agg2 = (u64 *) base;                       // n_slots * 16 bytes
+#endif
     }
     c_sync();
     for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) {
@@ -900,6 +915,9 @@ UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *
     }
     for (u32 k = (u32) c_tid(); k < 64; k += (u32) c_nthreads()) sh->tb.thresh[k] = ix.thresh[k];
     for (u32 c = (u32) c_tid(); c < n_slots; c += (u32) c_nthreads()) sh->pre[c] = 0;
+#ifdef K2_DFUSE
+    for (u32 c = (u32) c_tid(); c < 2u * n_slots; c += (u32) c_nthreads()) sh->agg2[c] = 0;   // tag 0 = never published (epochs start at 1)
+#endif
     c_sync();
 }
 
@@ -1025,6 +1043,20 @@ UNC_DEV long long pt_clock() { long long v; asm volatile("mov.u64 %0, %%clock64;
 #define K2_CH_SLOTS 160u    /* 32 parents x at most 5 children */
 
 UNC_DEV u32 k2_pre_pack(u32 epoch, u32 state) { return (epoch << 2) | state; }
+
+#ifdef K2_DFUSE
+// aggregate of chunk pc once its warp has published it for this epoch: (max fm_end of the trailing run, packed k-mers)
+UNC_DEV uint2 k2_agg_wait(K2Shared *sh, u32 pc, u32 epoch) {
+    u64 w0, w1;
+    for (;;) {
+        w0 = s_load_u64(&sh->agg2[2u * pc]);
+        w1 = s_load_u64(&sh->agg2[2u * pc + 1u]);
+        if ((u32) (w0 >> 32) == epoch && (u32) (w1 >> 32) == epoch) break;
+        w_spin();
+    }
+    return make_uint2((u32) w0, (u32) w1);
+}
+#endif
 
 #ifdef K2_TRK_INLINE
 // next chunk of 32 parents for this warp (phase B): a shared counter, so that a warp that arrives late takes less
@@ -1679,6 +1711,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             // ---- D. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603).
             // D1: per-chunk aggregate of the k-mer run structure: (max fm_end of the trailing run,
             //     first k-mer | last k-mer << 11 | whole-chunk-is-one-run << 22)
+#ifndef K2_DFUSE
             uint4 d1n = make_uint4(0, 0, 0, 0);
             if (ww < nch && ww * 32 + (u32) lane < nc) d1n = sk[ww * 32 + (u32) lane];
             for (u32 c = ww; c < nch; c += nwk) {
@@ -1701,6 +1734,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 if (lane == 0) sh->agg[c] = make_uint2(ml, kf | (kl << 11) | (single ? 1u << 22 : 0u));
             }
             c_sync_sub(1, (int) nwt);
+#endif
             // D2: everything else; source / seed positions from a decoupled look-back prefix sum
             epoch++;
             uint4 d2c = make_uint4(0, 0, 0, 0), d2n = make_uint4(0, 0, 0, 0);
@@ -1738,16 +1772,34 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                 }
                 u32 first_head = (m_lhead & ~1u) ? (u32) d_ffs(m_lhead & ~1u) - 1u : 32u;
                 bool in_lead = a && (u32) lane < first_head;
+#ifdef K2_DFUSE
+                {   // prototype: this chunk's run aggregate (what the separate D1 pass computed) from the scan just done,
+                    // published -- tagged with the epoch -- for the chunks after it; no D1 pass, no barrier
+                    const u32 m_act = w_ballot(a);
+                    const int lastl = 31 - d_clz(m_act);
+                    const u32 kl = w_shfl(kmer, lastl), ml = w_shfl(mx, lastl), kf = w_shfl(kmer, 0);
+                    const bool single = (m_lhead & m_act & ~1u) == 0;
+                    if (lane == 0) {
+                        s_store_u64(&sh->agg2[2u * c], ((u64) epoch << 32) | ml);
+                        s_store_u64(&sh->agg2[2u * c + 1u], ((u64) epoch << 32) | (kf | (kl << 11) | (single ? 1u << 22 : 0u)));
+                    }
+                }
+#endif
                 // carry of the leading run: does it continue the previous chunk's trailing run, and
                 // what is the max fm_end over that run's earlier elements?
                 u32 cont = 0, cmax = 0;
+#ifdef K2_DFUSE
+#define K2_AGG(i) k2_agg_wait(sh, (i), epoch)
+#else
+#define K2_AGG(i) sh->agg[(i)]
+#endif
                 if (lane == 0 && c > 0) {
-                    uint2 ag = sh->agg[c - 1];
+                    uint2 ag = K2_AGG(c - 1);
                     if (((ag.y >> 11) & 0x7FFu) == kmer) {
                         cont = 1; cmax = ag.x;
                         u32 pc = c - 1;
                         while (pc > 0 && ((ag.y >> 22) & 1u)) {            // that chunk was a single run: look further back
-                            uint2 pg = sh->agg[pc - 1];
+                            uint2 pg = K2_AGG(pc - 1);
                             if (((pg.y >> 11) & 0x7FFu) != (ag.y & 0x7FFu)) break;
                             cmax = pg.x > cmax ? pg.x : cmax;
                             ag = pg; pc--;

@@ -223,3 +223,89 @@ def test_cli_index_then_map_end_to_end(tmp_path, capsys):
     lines = cap.out.strip().split("\n")
     assert len(lines) == 1 and lines[0].rsplit("\t", 1)[0] == GOLD["default"]["line"].replace("\n", "")
     assert cap.err.count("Mapping\n") == 1 and cap.err.count("Finishing\n") == 1
+
+
+class _EmuBackend:
+    """The emulated device code standing in for the GPU BatchMapper (test vehicle): maps each read with the same
+    device source compiled for the CPU (tests/emulib.py)."""
+
+    def __init__(self, E):
+        self.E, self.calls = E, []
+
+    def map(self, flat, descs):
+        self.calls.append(len(descs))
+        out = []
+        for d in descs:
+            s = flat[int(d["offset"]):int(d["offset"]) + int(d["n_samples"])]
+            cal = (float(d["cal_range"]), float(d["cal_offset"]), float(d["cal_digit"]))
+            out.append(self.E.map_batch([s], dtype=int(d["dtype"]), cal=cal)[0][0])
+        return out
+
+
+def test_uncalled_map_from_fast5_files_on_the_emulated_device(tmp_path):
+    """`uncalled map` end to end WITHOUT a GPU: fast5 files -> the library's reader -> MapPool (queueing, read
+    filter, max_reads, max_chunks truncation, decode prefetch) -> the device source under the CPU emulator -> PAF.
+    The example fast5 must give the reference's golden lines for `-c 1` and `-e 100`."""
+    import emulib
+    import orclib
+    from uncalled_b200.api import Conf, MapPool
+    prefix = orclib.materialise_example_index(str(tmp_path))
+    O = orclib.Oracle(prefix)
+
+    class _Idx:
+        seqs = [(O.lib.orc_seq_name(O.idx, i).decode(), int(O.lib.orc_seq_len(O.idx, i))) for i in range(O.lib.orc_n_seqs(O.idx))]
+    f5dir = os.path.join(ROOT, "tests", "golden", "fast5")
+    ex, multi = os.path.join(f5dir, "example_single.fast5"), os.path.join(f5dir, "multi_many_reads.fast5")
+    for key, mod in (("max_chunks_1", {"max_chunks": 1}), ("max_events_100", {"max_events": 100})):
+        E = emulib.Emu(prefix)
+        conf = Conf()
+        for k, v in mod.items():
+            setattr(conf, k, v)
+            if hasattr(E.params, k):
+                setattr(E.params, k, v)
+        pool = MapPool(conf, backend=_EmuBackend(E), index=_Idx)
+        pool.add_fast5(ex)
+        assert pool.running()
+        lines = []
+        while pool.running():
+            lines += [p.line() for p in pool.update()]
+        pool.stop()
+        assert len(lines) == 1 and lines[0].rsplit("\t", 1)[0] == GOLD[key]["line"], (key, lines)
+    # batches of 16 reads over two files (70 tiny reads + the example), decode of batch k+1 overlapping batch k;
+    # a read list and max_reads applied the way Fast5Reader does
+    gold = json.load(open(os.path.join(f5dir, "golden.json")))
+    ids = sorted(set(r["id"] for r in gold if r["file"] == "multi_many_reads.fast5"))
+    E = emulib.Emu(prefix)
+    conf = Conf()
+    conf.batch_reads, conf.max_chunks, conf.threads = 16, 1, 2
+    be = _EmuBackend(E)
+    pool = MapPool(conf, backend=be, index=_Idx)
+    pool.add_fast5(multi)
+    pool.add_fast5(ex)
+    out = []
+    while pool.running():
+        out += pool.update()
+    pool.stop()
+    assert sorted(p.fields()[0] for p in out) == sorted(ids + ["f41a60f7-de4a-4b17-9f54-387e52d60b65"])
+    assert be.calls == [16, 16, 16, 16, 7] and not pool.running()
+    assert [p.line().rsplit("\t", 1)[0] for p in out if p.is_mapped()] == [GOLD["max_chunks_1"]["line"]]
+    rl = tmp_path / "reads.txt"
+    rl.write_text("\n".join(ids[10:40]) + "\n")
+    conf = Conf()
+    conf.batch_reads, conf.read_list, conf.max_reads = 8, str(rl), 12
+    be = _EmuBackend(E)
+    pool = MapPool(conf, backend=be, index=_Idx)
+    pool.add_fast5(multi)
+    out = []
+    while pool.running():
+        out += pool.update()
+    pool.stop()
+    assert len(out) == 12 and set(p.fields()[0] for p in out) <= set(ids[10:40]) and sum(be.calls) == 12
+    # an unreadable file surfaces as an error from update(), like the reference's reader throwing in fill_buffer
+    bad = tmp_path / "bad.fast5"
+    bad.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 100)
+    pool = MapPool(Conf(), backend=_EmuBackend(E), index=_Idx)
+    pool.add_fast5(str(bad))
+    with pytest.raises(RuntimeError):
+        pool.update()
+    pool.stop()

@@ -179,12 +179,17 @@ class _Read:
 class MapPool:
     """reference src/map_pool.hpp:33-53: MapPool(conf), add_fast5, update() -> [Paf], running(), stop()."""
 
-    def __init__(self, conf):
+    def __init__(self, conf, backend=None, index=None):
+        """`backend` (tests): an object with map(samples, descs) -> records standing in for the GPU BatchMapper,
+        with `index.seqs` = [(name, length)]; by default the index is loaded onto conf.device."""
         self.conf = conf
-        if not conf.bwa_prefix:
-            raise RuntimeError("Conf.bwa_prefix is not set")
-        self.index = Index(conf.bwa_prefix, preset=conf.idx_preset, device=conf.device,
-                           model_table=conf.model_path or None)
+        self._backend = backend
+        if backend is None:
+            if not conf.bwa_prefix:
+                raise RuntimeError("Conf.bwa_prefix is not set")
+            index = Index(conf.bwa_prefix, preset=conf.idx_preset, device=conf.device,
+                          model_table=conf.model_path or None)
+        self.index = index
         p = N.default_params()
         p.max_events, p.max_paths, p.seed_len = conf.max_events, conf.max_paths, conf.seed_len
         p.bp_per_sec, p.sample_rate = conf.bp_per_sec, conf.sample_rate
@@ -192,6 +197,7 @@ class MapPool:
         self._queue, self._mapper, self._cap = [], None, (0, 0)
         self._n_added, self._stopped = 0, False
         self._files, self._open, self._next = [], None, 0
+        self._future, self._executor = None, None          # fast5 decoding of the NEXT batch overlaps the mapping
         if conf.fast5_list:                                   # Fast5Reader::load_fast5_list (src/fast5_reader.cpp:77-92)
             self._files = [l.rstrip("\n") for l in open(conf.fast5_list) if l.strip()]
         self._read_filter = None
@@ -230,24 +236,46 @@ class MapPool:
         from its fill_buffer()."""
         self._files.append(fast5_name)
 
-    def _fill_from_fast5(self):
-        """Fast5Reader::fill_buffer (src/fast5_reader.cpp:179-229): top the queue up from the pending files."""
+    def _decode_next(self, want):
+        """Fast5Reader::fill_buffer (src/fast5_reader.cpp:179-229): decode up to `want` reads from the pending
+        files (conf.threads host threads inside unc_fast5_load).  Runs on the prefetch thread while the GPU maps."""
         from .fast5 import Fast5File
-        want = self.conf.batch_reads
-        while len(self._queue) < want and (self._open is not None or self._files):
-            if self.conf.max_reads and self._n_added >= self.conf.max_reads:
-                self._files, self._open = [], None
-                return
+        out = []
+        while len(out) < want and (self._open is not None or self._files):
             if self._open is None:
                 self._open, self._next = Fast5File(self._files.pop(0)), 0
             f = self._open
-            n = min(want - len(self._queue), f.n_reads - self._next)
-            for r in f.load(self._next, n, max_samples_per_read=self._max_len(), threads=self.conf.threads):
-                self.add_read(r.read_id, r.signal, r.channel, r.number, r.start_sample, calibration=r.calibration)
+            n = min(want - len(out), f.n_reads - self._next)
+            out += f.load(self._next, n, max_samples_per_read=self._max_len(), threads=self.conf.threads)
             self._next += n
             if self._next >= f.n_reads:
                 f.close()
                 self._open = None
+        return out
+
+    def _files_pending(self):
+        if self.conf.max_reads and self._n_added >= self.conf.max_reads:      # Fast5Reader::all_buffered
+            if self._open is not None:
+                self._open.close()
+            self._files, self._open = [], None
+        return self._open is not None or len(self._files) > 0
+
+    def _queue_decoded(self, reads):
+        for r in reads:
+            self.add_read(r.read_id, r.signal, r.channel, r.number, r.start_sample, calibration=r.calibration)
+
+    def _fill_from_fast5(self):
+        want = self.conf.batch_reads
+        if self._future is not None:                     # decoded while the previous batch was on the GPU
+            fut, self._future = self._future, None
+            self._queue_decoded(fut.result())
+        while len(self._queue) < want and self._files_pending():
+            self._queue_decoded(self._decode_next(want - len(self._queue)))
+        if self._files_pending():                        # start on the next batch before this one is mapped
+            if self._executor is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._executor = ThreadPoolExecutor(max_workers=1)
+            self._future = self._executor.submit(self._decode_next, want)
 
     # -- output --------------------------------------------------------------------------
     def update(self):
@@ -266,7 +294,9 @@ class MapPool:
             # one calibration per i16 batch call would over-constrain callers: descriptors carry it per read
             lens = [len(r.signal) for r in batch]
             total = int(sum(lens))
-            if self._mapper is None or len(batch) > self._cap[0] or total > self._cap[1]:
+            if self._backend is not None:
+                self._mapper = self._backend
+            elif self._mapper is None or len(batch) > self._cap[0] or total > self._cap[1]:
                 self._cap = (max(len(batch), self._cap[0], 64), max(total, self._cap[1], 1 << 20))
                 if self._mapper is not None:
                     self._mapper.close()
@@ -287,13 +317,26 @@ class MapPool:
         return out
 
     def running(self):
-        return not self._stopped and (len(self._queue) > 0 or self._open is not None or len(self._files) > 0)
+        return not self._stopped and (len(self._queue) > 0 or self._future is not None or self._open is not None or
+                                      len(self._files) > 0)
 
     def stop(self):
         self._stopped = True
-        if self._mapper is not None:
+        if self._future is not None:
+            try:
+                self._future.result()
+            except Exception:
+                pass
+            self._future = None
+        if self._executor is not None:
+            self._executor.shutdown(wait=True)
+            self._executor = None
+        if self._open is not None:
+            self._open.close()
+            self._open = None
+        if self._mapper is not None and self._backend is None:
             self._mapper.close()
-            self._mapper = None
+        self._mapper = None
 
 
 class Chunk:

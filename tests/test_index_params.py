@@ -120,3 +120,26 @@ def test_unparsable_targets_are_skipped_like_the_cli():
     off, val = paths_of("example", 1)
     assert IP.uncl_text(off, val, probs="x,0.5", speeds=["-"]).splitlines()[1].startswith("prob_0.5\t")
     assert len(IP.uncl_text(off, val, probs="x", speeds="y").splitlines()) == 1
+
+
+def test_index_cmd_end_to_end_with_the_emulated_device(tmp_path):
+    """`uncalled index` from a FASTA alone: the product's FM-index builder, the device self-alignment source under
+    the CPU emulator (injected in place of the GPU call) and the parameter search reproduce the index files AND the
+    .uncl file that the reference ships for its example, and a multi-preset file of the reference's parameterizer."""
+    import emulib
+    import orclib
+    from uncalled_b200 import index as UI
+    os.makedirs(tmp_path / "src")
+    src = orclib.materialise_example_index(str(tmp_path / "src"))
+    fa = str(tmp_path / "example_ref.fa")
+    open(fa, "wb").write(open(src + ".fa", "rb").read())
+    row = PRESETS[0]
+    assert row["index"] == "example" and not row["opts"]
+    UI.index_cmd(fa, probs=row["probs"], speeds=row["speeds"], self_align_fn=emulib.self_align)
+    for ext in (".bwt", ".sa", ".ann", ".amb", ".pac"):
+        assert open(fa + ext, "rb").read() == open(src + ext, "rb").read(), ext
+    assert open(fa + ".uncl").read() == row["uncl"]
+    assert row["uncl"].splitlines()[0] + "\n" == open(src + ".uncl").read()          # its first line is the shipped file
+    os.remove(fa + ".uncl")
+    UI.index_cmd(fa, self_align_fn=emulib.self_align)                                 # BWA files are reused now
+    assert open(fa + ".uncl").read() == open(src + ".uncl").read()

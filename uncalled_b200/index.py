@@ -45,18 +45,19 @@ def self_align(bwa_prefix, sample_dist):
     return [v[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
 
 
-def write_uncl(bwa_prefix, probs=None, speeds=None, **opts):
-    """IndexParameterizer(args) + add_preset(...) + write() (scripts/uncalled:57-76): writes <prefix>.uncl."""
+def write_uncl(bwa_prefix, probs=None, speeds=None, self_align_fn=None, **opts):
+    """IndexParameterizer(args) + add_preset(...) + write() (scripts/uncalled:57-76): writes <prefix>.uncl.
+    `self_align_fn(prefix, sample_dist) -> (offsets, values)` replaces the GPU call in CPU-only tests."""
     o = dict(IP.DEFAULTS, **opts)
     sd = IP.sample_distance(IP.reference_length(bwa_prefix), o["max_sample_dist"], o["min_samples"], o["max_samples"])
-    off, val = self_align_csr(bwa_prefix, sd)
+    off, val = (self_align_fn or self_align_csr)(bwa_prefix, sd)
     text = IP.uncl_text(off, val, probs=probs, speeds=speeds, **opts)
     with open(bwa_prefix + UNCL_SUFF, "w") as f:
         f.write(text)
     return text
 
 
-def index_cmd(fasta_filename, bwa_prefix=None, probs=None, speeds=None, **opts):
+def index_cmd(fasta_filename, bwa_prefix=None, probs=None, speeds=None, self_align_fn=None, **opts):
     """`uncalled index [-o PREFIX] [--probs a,b] [--speeds c,d] FASTA` (scripts/uncalled:38-78): reuses an existing
     BWA index, builds it otherwise; then the parameter search.  `opts`: the remaining `uncalled index` options
     (max_sample_dist, min_samples, max_samples, kmer_len, matchpr1, matchpr2, pathlen_percentile, max_replen)."""
@@ -68,6 +69,6 @@ def index_cmd(fasta_filename, bwa_prefix=None, probs=None, speeds=None, **opts):
     else:
         BwaIndex.create(fasta_filename, bwa_prefix)
     sys.stderr.write("Initializing parameter search\n")
-    write_uncl(bwa_prefix, probs=probs, speeds=speeds, **opts)
+    write_uncl(bwa_prefix, probs=probs, speeds=speeds, self_align_fn=self_align_fn, **opts)
     sys.stderr.write("Done\n")
     return bwa_prefix

@@ -158,6 +158,17 @@ int unc_map_batch(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads, 
 int unc_map_batch_device(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads,
                          const void *d_samples, unc_paf_rec *out);
 
+/* The same work as two calls, so that batches on DIFFERENT pools overlap: submit queues the copies and both
+ * kernels on the pool's stream and returns; wait blocks until they are done and hands the records over.  Reads
+ * differ widely in cost (one that never maps takes ~6x one that does), so the last reads of a batch leave CTAs
+ * idle; with two pools used alternately the next batch's CTAs fill the SMs the previous batch's tail frees -- what
+ * the reference's thread pool gets by handing every idle thread the next read (src/map_pool.cpp:45-69).
+ * `samples` (and, for host samples, the buffer they live in) must stay untouched until the matching wait; a pool
+ * holds at most one submitted batch. */
+int unc_map_batch_submit(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads, const void *samples,
+                         int samples_on_device);
+int unc_map_batch_wait(unc_pool *pool, unc_paf_rec *out);
+
 /* Event detection + normalisation alone.  events/normed hold `stride` floats per read
  * (stride >= the longest read's n_samples); n_events, mean_event_len one entry per read. */
 int unc_events_batch(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads, const void *samples,

@@ -363,3 +363,30 @@ def test_index_cmd_reproduces_reference_uncl_files(U, tmp_path):
     assert open(ex + ".uncl").read() == shipped
     presets = json.load(open(os.path.join(ROOT, "tests", "golden", "uncl_presets.json")))[0]
     assert UI.write_uncl(ex, probs=presets["probs"], speeds=presets["speeds"]) == presets["uncl"]
+
+
+def test_submit_wait_on_two_pools_matches_the_synchronous_call(U):
+    """unc_map_batch_submit / _wait: batches in flight on two pools at once give the records of unc_map_batch."""
+    import synth
+    import synthdata
+    prefix, g = synthdata.get_index("g200k")
+    idx = U.Index(prefix, device=0)
+    sig, _ = synth.reads(g, 96, 3000, seed=13, frac_random=0.3)
+    halves = [np.ascontiguousarray(sig[:48].reshape(-1)), np.ascontiguousarray(sig[48:].reshape(-1))]
+    d = U.make_descs([3000] * 48)
+    pools = [U.BatchMapper(idx, max_reads=48, max_samples=48 * 3000) for _ in range(2)]
+    want = [pools[0].map(halves[0], d).copy(), pools[0].map(halves[1], d).copy()]
+    for rep in range(3):
+        pools[0].submit(halves[0], d)
+        pools[1].submit(halves[1], d)
+        with pytest.raises(U.UncError):
+            pools[0].submit(halves[1], d)                      # a pool holds one batch at a time
+        got1 = pools[1].wait()
+        got0 = pools[0].wait()
+        assert np.array_equal(got0, want[0]) and np.array_equal(got1, want[1]), rep
+    with pytest.raises(U.UncError):
+        pools[0].wait()                                            # nothing submitted
+    with pytest.raises(U.UncError):
+        U._native.check(pools[0].L.unc_map_batch_wait(pools[0].h, want[0].ctypes.data))   # the C entry point says so too
+    for p in pools:
+        p.close()

@@ -13,3 +13,6 @@ for v in uncalled_b200/variants_pt/*.so; do
   timeout 200 python tools/gpu_phases.py g4m7 2368 "$v" > "gpurun_out/phases_$(basename "$v" .so).txt" 2>&1; tail -24 "gpurun_out/phases_$(basename "$v" .so).txt"
 done
 timeout 600 python bench.py --workload stream --steps 2 --warmup 1 > gpurun_out/bench_stream.json 2> gpurun_out/bench_stream.err; echo "stream bench rc=$?"; cut -c1-600 gpurun_out/bench_stream.json; tail -3 gpurun_out/bench_stream.err
+# batch tail: two pools used alternately (expected from a list-scheduling simulation of the oracle's per-read costs:
+# makespan / ideal = 1.07 at 2 CTAs/SM, 1.11 at 3, 1.15 at 4 for 10 000-read batches)
+timeout 600 python bench.py --overlap --no-cpu-baseline --steps 4 --warmup 3 > gpurun_out/bench_overlap.json 2> gpurun_out/bench_overlap.err; echo "overlap bench rc=$?"; cut -c1-900 gpurun_out/bench_overlap.json

@@ -171,6 +171,8 @@ struct unc_pool {
     uint32_t n_slots = 0, grid = 0;
     size_t smem = 0;
     unc_timing last;
+    uint32_t pending_n = 0;      // reads of a submitted, not yet collected batch (unc_map_batch_submit / _wait)
+    uint64_t pending_h2d = 0;
 };
 
 extern "C" {
@@ -518,9 +520,10 @@ static void launch_k1(unc_pool *P, const DevBatch &B, uint32_t n, cudaStream_t s
     k1_norm<<<(n + 127) / 128, 128, 0, s>>>(B, P->dp);
 }
 
-static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, bool on_device,
-                     unc_paf_rec *out) {
-    if (!P || !reads || !samples || !out) return fail(UNC_E_ARG, "null argument");
+// first half of a batch: everything is put on the pool's stream (copies in, both kernels, copy out), nothing waits
+static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, bool on_device) {
+    if (!P || !reads || !samples) return fail(UNC_E_ARG, "null argument");
+    if (P->pending_n) return fail(UNC_E_ARG, "the pool still holds a submitted batch: call unc_map_batch_wait first");
     CUDA_TRY(cudaSetDevice(P->idx->device));
     uint64_t span = 0;
     uint32_t mx = 0;
@@ -550,7 +553,20 @@ static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     CUDA_TRY(cudaEventRecord(P->ev[3], s));
     CUDA_TRY(cudaMemcpyAsync(P->h_out, P->d_out, (size_t) n * sizeof(DevRec), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(P->ev[4], s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    P->pending_n = n;
+    P->pending_h2d = h2d;
+    return UNC_OK;
+}
+
+// second half: wait for the stream, hand the records over, read the event timings
+static int batch_finish(unc_pool *P, unc_paf_rec *out) {
+    if (!P || !out) return fail(UNC_E_ARG, "null argument");
+    if (!P->pending_n) return fail(UNC_E_ARG, "no submitted batch to wait for");
+    const uint32_t n = P->pending_n;
+    const uint64_t h2d = P->pending_h2d;
+    P->pending_n = 0;
+    CUDA_TRY(cudaSetDevice(P->idx->device));
+    CUDA_TRY(cudaStreamSynchronize(P->stream));
     memcpy(out, P->h_out, (size_t) n * sizeof(unc_paf_rec));
     unc_timing &t = P->last;
     cudaEventElapsedTime(&t.h2d_ms, P->ev[0], P->ev[1]);
@@ -568,8 +584,24 @@ static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const 
     return UNC_OK;
 }
 
+static int run_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, bool on_device,
+                     unc_paf_rec *out) {
+    if (!out) return fail(UNC_E_ARG, "null argument");
+    int rc = batch_enqueue(P, reads, n, samples, on_device);
+    if (rc) return rc;
+    return batch_finish(P, out);
+}
+
 int unc_map_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, unc_paf_rec *out) {
     return run_batch(P, reads, n, samples, false, out);
+}
+
+int unc_map_batch_submit(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, int samples_on_device) {
+    return batch_enqueue(P, reads, n, samples, samples_on_device != 0);
+}
+
+int unc_map_batch_wait(unc_pool *P, unc_paf_rec *out) {
+    return batch_finish(P, out);
 }
 
 int unc_map_batch_device(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *d_samples, unc_paf_rec *out) {

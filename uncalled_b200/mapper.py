@@ -119,6 +119,30 @@ class BatchMapper:
             N.check(rc)
         return out
 
+    def submit(self, samples, descs, on_device=False):
+        """First half of map()/map_device(): queue the batch on this pool's stream and return.  `samples`: host numpy
+        array, or an integer device pointer with on_device=True; keep it (and `descs`) alive until wait()."""
+        if on_device:
+            ptr = C.c_void_p(int(samples))
+        else:
+            samples = np.ascontiguousarray(samples)
+            ptr = C.c_void_p(samples.ctypes.data)
+        self._pending = (samples, descs)
+        N.check(self.L.unc_map_batch_submit(self.h, descs.ctypes.data, len(descs), ptr, 1 if on_device else 0))
+
+    def wait(self):
+        """Second half: block until the submitted batch is done; returns its records."""
+        if getattr(self, "_pending", None) is None:
+            raise N.UncError("no submitted batch to wait for")
+        _, descs = self._pending
+        out = np.zeros(len(descs), dtype=N.PAF_DTYPE)
+        rc = self.L.unc_map_batch_wait(self.h, out.ctypes.data)
+        self._pending = None
+        self._last_rc = rc
+        if rc != 0 and rc != -7:
+            N.check(rc)
+        return out
+
     def events(self, samples, descs):
         samples = np.ascontiguousarray(samples)
         n = len(descs)

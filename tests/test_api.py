@@ -242,6 +242,21 @@ class _EmuBackend:
         return out
 
 
+class _EmuBackendTwoCall(_EmuBackend):
+    """The same with the submit()/wait() form of the GPU mapper, so that MapPool pipelines its batches."""
+
+    def __init__(self, E):
+        _EmuBackend.__init__(self, E)
+        self.fifo, self.max_in_flight = [], 0
+
+    def submit(self, flat, descs):
+        self.fifo.append(self.map(flat, descs))
+        self.max_in_flight = max(self.max_in_flight, len(self.fifo))
+
+    def wait(self):
+        return self.fifo.pop(0)
+
+
 def test_uncalled_map_from_fast5_files_on_the_emulated_device(tmp_path):
     """`uncalled map` end to end WITHOUT a GPU: fast5 files -> the library's reader -> MapPool (queueing, read
     filter, max_reads, max_chunks truncation, decode prefetch) -> the device source under the CPU emulator -> PAF.
@@ -278,17 +293,21 @@ def test_uncalled_map_from_fast5_files_on_the_emulated_device(tmp_path):
     E = emulib.Emu(prefix)
     conf = Conf()
     conf.batch_reads, conf.max_chunks, conf.threads = 16, 1, 2
-    be = _EmuBackend(E)
-    pool = MapPool(conf, backend=be, index=_Idx)
-    pool.add_fast5(multi)
-    pool.add_fast5(ex)
-    out = []
-    while pool.running():
-        out += pool.update()
-    pool.stop()
-    assert sorted(p.fields()[0] for p in out) == sorted(ids + ["f41a60f7-de4a-4b17-9f54-387e52d60b65"])
-    assert be.calls == [16, 16, 16, 16, 7] and not pool.running()
-    assert [p.line().rsplit("\t", 1)[0] for p in out if p.is_mapped()] == [GOLD["max_chunks_1"]["line"]]
+    for be in (_EmuBackend(E), _EmuBackendTwoCall(E)):
+        pool = MapPool(conf, backend=be, index=_Idx)
+        pool.add_fast5(multi)
+        pool.add_fast5(ex)
+        out, per_call = [], []
+        while pool.running():
+            got = pool.update()
+            per_call.append(len(got))
+            out += got
+        pool.stop()
+        assert sorted(p.fields()[0] for p in out) == sorted(ids + ["f41a60f7-de4a-4b17-9f54-387e52d60b65"])
+        assert be.calls == [16, 16, 16, 16, 7] and not pool.running()
+        assert [p.line().rsplit("\t", 1)[0] for p in out if p.is_mapped()] == [GOLD["max_chunks_1"]["line"]]
+        if isinstance(be, _EmuBackendTwoCall):      # batch k+1 was submitted before batch k was collected
+            assert be.max_in_flight == 2 and per_call == [0, 16, 16, 16, 16 + 7] and not be.fifo
     rl = tmp_path / "reads.txt"
     rl.write_text("\n".join(ids[10:40]) + "\n")
     conf = Conf()

@@ -194,7 +194,8 @@ class MapPool:
         p.max_events, p.max_paths, p.seed_len = conf.max_events, conf.max_paths, conf.seed_len
         p.bp_per_sec, p.sample_rate = conf.bp_per_sec, conf.sample_rate
         self.params = p
-        self._queue, self._mapper, self._cap = [], None, (0, 0)
+        self._queue = []
+        self._mappers, self._caps, self._inflight = [None, None], [(0, 0), (0, 0)], None   # two pools: batches overlap
         self._n_added, self._stopped = 0, False
         self._files, self._open, self._next = [], None, 0
         self._future, self._executor = None, None          # fast5 decoding of the NEXT batch overlaps the mapping
@@ -278,50 +279,92 @@ class MapPool:
             self._future = self._executor.submit(self._decode_next, want)
 
     # -- output --------------------------------------------------------------------------
+    def _take_batch(self):
+        """The leading reads of one sample type, at most conf.batch_reads (a device batch has one sample type)."""
+        if not self._queue:
+            return None
+        dtype, n = self._queue[0].dtype, 0
+        while n < len(self._queue) and n < self.conf.batch_reads and self._queue[n].dtype == dtype:
+            n += 1
+        batch = self._queue[:n]
+        del self._queue[:n]
+        return batch
+
+    def _mapper_for(self, slot, n_reads, total):
+        if self._backend is not None:
+            return self._backend
+        m, cap = self._mappers[slot], self._caps[slot]
+        if m is None or n_reads > cap[0] or total > cap[1]:
+            cap = (max(n_reads, cap[0], 64), max(total, cap[1], 1 << 20))
+            if m is not None:
+                m.close()
+            m = BatchMapper(self.index, params=self.params, max_reads=cap[0], max_samples=cap[1])
+            self._mappers[slot], self._caps[slot] = m, cap
+        return m
+
+    def _launch(self, batch):
+        """Put a batch on the GPU (unc_map_batch_submit on the pool that is not in flight) and return at once."""
+        lens = [len(r.signal) for r in batch]
+        total = int(sum(lens))
+        dtype = batch[0].dtype
+        d = make_descs(lens, dtype=dtype)
+        for i, r in enumerate(batch):              # descriptors carry the calibration per read
+            d["cal_range"][i], d["cal_offset"][i], d["cal_digit"][i] = r.cal
+        flat = np.concatenate([r.signal for r in batch]) if total else np.zeros(1, np.float32 if dtype == 0 else np.int16)
+        slot = 1 - self._inflight["slot"] if self._inflight is not None else 0
+        m = self._mapper_for(slot, len(batch), total)
+        job = {"slot": slot, "batch": batch, "flat": flat, "descs": d, "t0": time.time(), "mapper": m, "recs": None}
+        if hasattr(m, "submit"):
+            m.submit(flat, d)
+        else:                                      # a test backend without the two-call form
+            job["recs"] = m.map(flat, d)
+        return job
+
+    def _collect(self, job):
+        recs = job["recs"] if job["recs"] is not None else job["mapper"].wait()
+        batch = job["batch"]
+        ms = (time.time() - job["t0"]) * 1e3 / len(batch)
+        out = []
+        for r, rec in zip(batch, recs):
+            p = _paf_from_rec(self.index.seqs, rec, r.id, r.channel, r.start)
+            p.set_float(Paf.Tag.MAP_TIME, ms)
+            out.append(p)
+        return out
+
     def update(self):
-        """Maps up to conf.batch_reads queued reads on the GPU and returns their Paf records
-        (the reference returns whatever its threads finished since the last call, src/map_pool.cpp:45-69)."""
+        """Returns the Paf records that are ready (the reference returns whatever its threads finished since the
+        last call, src/map_pool.cpp:45-69).  Batches of conf.batch_reads reads are mapped on the GPU; when more input
+        is waiting, the next batch is submitted (on a second pool) BEFORE the call waits for the one in flight, so that
+        its CTAs fill the SMs which the tail of the previous batch leaves idle, and fast5 decoding runs alongside."""
         if self._stopped:
             return []
         self._fill_from_fast5()
-        if not self._queue:
-            return []
+        nxt = self._take_batch()
+        job = self._launch(nxt) if nxt else None
         out = []
-        for dtype in (0, 1):
-            batch = [r for r in self._queue[:self.conf.batch_reads] if r.dtype == dtype]
-            if not batch:
-                continue
-            # one calibration per i16 batch call would over-constrain callers: descriptors carry it per read
-            lens = [len(r.signal) for r in batch]
-            total = int(sum(lens))
-            if self._backend is not None:
-                self._mapper = self._backend
-            elif self._mapper is None or len(batch) > self._cap[0] or total > self._cap[1]:
-                self._cap = (max(len(batch), self._cap[0], 64), max(total, self._cap[1], 1 << 20))
-                if self._mapper is not None:
-                    self._mapper.close()
-                self._mapper = BatchMapper(self.index, params=self.params, max_reads=self._cap[0], max_samples=self._cap[1])
-            d = make_descs(lens, dtype=dtype)
-            for i, r in enumerate(batch):
-                d["cal_range"][i], d["cal_offset"][i], d["cal_digit"][i] = r.cal
-            flat = np.concatenate([r.signal for r in batch]) if total else np.zeros(1, np.float32 if dtype == 0 else np.int16)
-            t0 = time.time()
-            recs = self._mapper.map(flat, d)
-            ms = (time.time() - t0) * 1e3 / len(batch)
-            for r, rec in zip(batch, recs):
-                p = _paf_from_rec(self.index.seqs, rec, r.id, r.channel, r.start)
-                p.set_float(Paf.Tag.MAP_TIME, ms)
-                out.append(p)
-        n = min(len(self._queue), self.conf.batch_reads)
-        del self._queue[:n]
+        if self._inflight is not None:
+            out = self._collect(self._inflight)
+            self._inflight = None
+        if job is not None:
+            more = bool(self._queue) or self._future is not None or self._open is not None or bool(self._files)
+            if more:
+                self._inflight = job               # collected by the next call, after that call's submit
+            else:
+                out += self._collect(job)
         return out
 
     def running(self):
-        return not self._stopped and (len(self._queue) > 0 or self._future is not None or self._open is not None or
-                                      len(self._files) > 0)
+        return not self._stopped and (len(self._queue) > 0 or self._inflight is not None or self._future is not None or
+                                      self._open is not None or len(self._files) > 0)
 
     def stop(self):
         self._stopped = True
+        if self._inflight is not None:
+            try:
+                self._collect(self._inflight)
+            except Exception:
+                pass
+            self._inflight = None
         if self._future is not None:
             try:
                 self._future.result()
@@ -334,9 +377,10 @@ class MapPool:
         if self._open is not None:
             self._open.close()
             self._open = None
-        if self._mapper is not None and self._backend is None:
-            self._mapper.close()
-        self._mapper = None
+        for i, m in enumerate(self._mappers):
+            if m is not None:
+                m.close()
+            self._mappers[i] = None
 
 
 class Chunk:

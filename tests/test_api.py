@@ -39,50 +39,6 @@ def test_conf_has_real_properties_with_docs():
     assert c.max_events == 100 and c.chunk_time == 1.0 and c.idx_preset == "default"
 
 
-@pytest.mark.gpu
-def test_map_pool_prints_the_reference_paf_lines(example_prefix, golden_read):
-    """`uncalled map`, `-c 1` and `-e 100` on the example read (config 1), line for line up to the mt tag."""
-    from uncalled_b200.api import Conf, MapPool
-    raw = golden_read["raw"]
-    rid, ch, st = str(golden_read["read_id"]), int(golden_read["channel"]), int(golden_read["start"])
-    for key, mod in (("default", {}), ("max_chunks_1", {"max_chunks": 1}), ("max_events_100", {"max_events": 100})):
-        conf = Conf()
-        conf.bwa_prefix = example_prefix
-        for k, v in mod.items():
-            setattr(conf, k, v)
-        pool = MapPool(conf)
-        assert not pool.running()
-        pool.add_read(rid, raw, channel=ch, number=0, start_sample=st)
-        lines = []
-        while pool.running():
-            lines += [p.line() for p in pool.update()]
-        pool.stop()
-        assert len(lines) == 1
-        body, mt = lines[0].rsplit("\t", 1)
-        assert body == GOLD[key]["line"] and mt.startswith("mt:f:"), (key, lines[0])
-
-
-@pytest.mark.gpu
-def test_map_pool_i16_reads_and_filters(example_prefix, golden_read, tmp_path):
-    from uncalled_b200.api import Conf, MapPool
-    raw = golden_read["raw"]
-    cal = (1534.14, 10.0, 8192.0)       # the example read's calibration attributes (SURVEY 8c)
-    dac = np.round(raw.astype(np.float64) * cal[2] / cal[0] - cal[1]).astype(np.int64)
-    dac16 = dac.astype(np.uint16).astype(np.int16)       # the >32767 spike wraps like the fast5 payload does
-    pa = (np.float32(cal[0]) * (dac16.astype(np.uint16).astype(np.float32) + np.float32(cal[1]))) / np.float32(cal[2])
-    assert np.array_equal(pa.astype(np.float32), raw)
-    rl = tmp_path / "reads.txt"
-    rl.write_text("keep_me\n")
-    conf = Conf()
-    conf.bwa_prefix, conf.read_list = example_prefix, str(rl)
-    pool = MapPool(conf)
-    assert pool.add_read("keep_me", dac16, channel=486, start_sample=257117, calibration=cal)
-    assert not pool.add_read("drop_me", dac16, calibration=cal)
-    out = pool.update()
-    pool.stop()
-    assert len(out) == 1 and out[0].fields()[1:] == GOLD["default"]["fields"][1:]
-
-
 def test_realtime_pool_surface_and_constants():
     from uncalled_b200.api import Chunk, Conf, RealtimePool
     assert (RealtimePool.DEPLETE, RealtimePool.ENRICH) == (0, 1) and (RealtimePool.FULL, RealtimePool.EVEN, RealtimePool.ODD) == (0, 1, 2)
@@ -144,43 +100,6 @@ def test_realtime_pool_chunk_protocol_with_emulated_device():
                 assert p.fields()[0] == "read%d" % i and p.int_tags[0] == (4, ch + 1)
 
 
-@pytest.mark.gpu
-def test_uncalled_map_on_the_example_fast5(example_prefix, tmp_path):
-    """config 1 end to end from the FILE: `uncalled map -t 1 <index> <fast5>`, `-c 1` and `-e 100` (SURVEY 8c golden
-    lines), the fast5 decoded by the library's own reader, calibrated on the GPU; and a fast5 list + read filter."""
-    from uncalled_b200.api import Conf, MapPool
-    f5 = os.path.join(ROOT, "tests", "golden", "fast5", "example_single.fast5")
-    for key, mod in (("default", {}), ("max_chunks_1", {"max_chunks": 1}), ("max_events_100", {"max_events": 100})):
-        conf = Conf()
-        conf.bwa_prefix = example_prefix
-        for k, v in mod.items():
-            setattr(conf, k, v)
-        pool = MapPool(conf)
-        pool.add_fast5(f5)
-        assert pool.running()
-        lines = []
-        while pool.running():
-            lines += [p.line() for p in pool.update()]
-        pool.stop()
-        assert len(lines) == 1 and lines[0].rsplit("\t", 1)[0] == GOLD[key]["line"], (key, lines)
-    # fast5_list + read_list + max_reads over multi-read files (none of these reads map to the example reference)
-    fl, rl = tmp_path / "files.txt", tmp_path / "reads.txt"
-    multi = os.path.join(ROOT, "tests", "golden", "fast5", "multi_gzip.fast5")
-    fl.write_text(multi + "\n" + f5 + "\n")
-    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fast5", "golden.json")))
-    ids = sorted(set(r["id"] for r in gold if r["file"] == "multi_gzip.fast5"))
-    rl.write_text("\n".join(ids[:5] + ["f41a60f7-de4a-4b17-9f54-387e52d60b65"]) + "\n")
-    conf = Conf()
-    conf.bwa_prefix, conf.fast5_list, conf.read_list, conf.batch_reads = example_prefix, str(fl), str(rl), 4
-    pool = MapPool(conf)
-    out = []
-    while pool.running():
-        out += pool.update()
-    pool.stop()
-    assert sorted(p.fields()[0] for p in out) == sorted(ids[:5] + ["f41a60f7-de4a-4b17-9f54-387e52d60b65"])
-    assert [p.is_mapped() for p in out if p.fields()[0].startswith("f41a60f7")] == [True]
-
-
 def test_cli_parser_and_fast5_discovery(tmp_path, capsys):
     """`uncalled map` / `uncalled index` option names and defaults (uncalled/args.py:87-161,218-286) and the fast5
     path expansion of scripts/uncalled:80-118."""
@@ -202,27 +121,6 @@ def test_cli_parser_and_fast5_discovery(tmp_path, capsys):
         ("ref.fa", "out/ref", "0.5,0.2", None, 50, 0.55, 0.9838, 50000)
     with pytest.raises(SystemExit):
         list(cli.load_fast5s([str(tmp_path / "absent_dir")], False))
-
-
-@pytest.mark.gpu
-def test_cli_index_then_map_end_to_end(tmp_path, capsys):
-    """`uncalled index example_ref.fa` from the FASTA alone, then `uncalled map` of the example fast5 against it: the
-    reference's golden PAF line (a rebuilt index is byte-identical to the shipped one)."""
-    import orclib
-    from uncalled_b200 import cli
-    os.makedirs(tmp_path / "src")
-    src = orclib.materialise_example_index(str(tmp_path / "src"))
-    fa = str(tmp_path / "example_ref.fa")
-    open(fa, "wb").write(open(src + ".fa", "rb").read())
-    assert cli.main(["index", fa]) == 0
-    for ext in (".bwt", ".sa", ".ann", ".amb", ".pac", ".uncl"):
-        assert open(fa + ext, "rb").read() == open(src + ext, "rb").read(), ext
-    capsys.readouterr()
-    assert cli.main(["map", fa, os.path.join(ROOT, "tests", "golden", "fast5", "example_single.fast5")]) == 0
-    cap = capsys.readouterr()
-    lines = cap.out.strip().split("\n")
-    assert len(lines) == 1 and lines[0].rsplit("\t", 1)[0] == GOLD["default"]["line"].replace("\n", "")
-    assert cap.err.count("Mapping\n") == 1 and cap.err.count("Finishing\n") == 1
 
 
 class _EmuBackend:

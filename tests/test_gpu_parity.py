@@ -316,77 +316,3 @@ def test_stream_limits(U):
         p.max_paths = 300
     st = _stream_vs_oracle(U, prefix, sigs, 3, 450, params_mod=mod)
     assert (3, 1) in st
-
-
-def test_self_align_matches_oracle_and_reference_digest(U, example_prefix, tmp_path):
-    """`uncalled index`: unc_self_align against the oracle, the reference's digests and, end to end, the
-    reference-made .uncl files."""
-    import hashlib
-    import orclib
-    import synthdata
-    from uncalled_b200 import index as UI, index_params as IP
-    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "self_align_golden.json")))
-    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, "<u8").tobytes()).hexdigest()   # noqa: E731
-    for row in gold:
-        prefix = example_prefix if row["index"] == "example" else synthdata.get_index(row["index"])[0]
-        off, val = UI.self_align_csr(prefix, row["sample_dist"])
-        assert (len(off) - 1, len(val)) == (row["n_paths"], row["n_values"])
-        assert sha(off) == row["offsets_sha256"] and sha(val) == row["values_sha256"], row["index"]
-    for name, sd in (("g4m7", 94), ("g200k", 1)):
-        prefix = synthdata.get_index(name)[0]
-        a, b = UI.self_align_csr(prefix, sd), orclib.self_align(prefix, sd)
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), name
-    # repeats, tiny and ambiguous sequences: paths beyond the staging depth are re-walked in pass 2
-    import test_selfalign_emul as tse
-    prefix = tse.repeat_index(str(tmp_path))
-    for sd in (1, 3):
-        a, b = UI.self_align_csr(prefix, sd), orclib.self_align(prefix, sd)
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), sd
-    assert UI.self_align(prefix, 3) == [[int(v) for v in b[1][int(b[0][i]):int(b[0][i + 1])]] for i in range(len(b[0]) - 1)]
-
-
-def test_index_cmd_reproduces_reference_uncl_files(U, tmp_path):
-    """FASTA -> .bwt/.sa/... -> self_align on the GPU -> .uncl, against what the real `uncalled index` wrote."""
-    import shutil
-    import synth
-    import orclib
-    from uncalled_b200 import index as UI
-    synth_uncl = json.load(open(os.path.join(ROOT, "tests", "golden", "synth_uncl.json")))
-    fa = str(tmp_path / "g.fa")
-    synth.write_fasta(fa, synth.genome(synth_uncl["g200k"]["size"], synth_uncl["g200k"]["seed"]))
-    prefix = UI.index_cmd(fa, str(tmp_path / "g200k"))
-    assert open(prefix + ".uncl").read() == synth_uncl["g200k"]["uncl"]
-    ex = orclib.materialise_example_index(str(tmp_path))
-    shipped = open(ex + ".uncl").read()
-    os.remove(ex + ".uncl")
-    UI.index_cmd(ex + ".fa", ex)                                   # reuses the shipped BWA files
-    assert open(ex + ".uncl").read() == shipped
-    presets = json.load(open(os.path.join(ROOT, "tests", "golden", "uncl_presets.json")))[0]
-    assert UI.write_uncl(ex, probs=presets["probs"], speeds=presets["speeds"]) == presets["uncl"]
-
-
-def test_submit_wait_on_two_pools_matches_the_synchronous_call(U):
-    """unc_map_batch_submit / _wait: batches in flight on two pools at once give the records of unc_map_batch."""
-    import synth
-    import synthdata
-    prefix, g = synthdata.get_index("g200k")
-    idx = U.Index(prefix, device=0)
-    sig, _ = synth.reads(g, 96, 3000, seed=13, frac_random=0.3)
-    halves = [np.ascontiguousarray(sig[:48].reshape(-1)), np.ascontiguousarray(sig[48:].reshape(-1))]
-    d = U.make_descs([3000] * 48)
-    pools = [U.BatchMapper(idx, max_reads=48, max_samples=48 * 3000) for _ in range(2)]
-    want = [pools[0].map(halves[0], d).copy(), pools[0].map(halves[1], d).copy()]
-    for rep in range(3):
-        pools[0].submit(halves[0], d)
-        pools[1].submit(halves[1], d)
-        with pytest.raises(U.UncError):
-            pools[0].submit(halves[1], d)                      # a pool holds one batch at a time
-        got1 = pools[1].wait()
-        got0 = pools[0].wait()
-        assert np.array_equal(got0, want[0]) and np.array_equal(got1, want[1]), rep
-    with pytest.raises(U.UncError):
-        pools[0].wait()                                            # nothing submitted
-    with pytest.raises(U.UncError):
-        U._native.check(pools[0].L.unc_map_batch_wait(pools[0].h, want[0].ctypes.data))   # the C entry point says so too
-    for p in pools:
-        p.close()

@@ -1,0 +1,191 @@
+"""GPU tests that sort LAST on purpose: the Python surface (MapPool, CLI) and the paths added after this round's GPU
+minutes were spent (fast5 -> map end to end, `uncalled index` on the GPU, submit/wait on two pools).  `pytest -x` reaches
+them only after the parity suite of tests/test_gpu_parity.py has run."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "example_paf.json")))
+
+
+@pytest.fixture(scope="module")
+def U():
+    import uncalled_b200
+    uncalled_b200._native.lib()
+    return uncalled_b200
+
+
+def test_submit_wait_on_two_pools_matches_the_synchronous_call(U):
+    """unc_map_batch_submit / _wait: batches in flight on two pools at once give the records of unc_map_batch."""
+    import synth
+    import synthdata
+    prefix, g = synthdata.get_index("g200k")
+    idx = U.Index(prefix, device=0)
+    sig, _ = synth.reads(g, 96, 3000, seed=13, frac_random=0.3)
+    halves = [np.ascontiguousarray(sig[:48].reshape(-1)), np.ascontiguousarray(sig[48:].reshape(-1))]
+    d = U.make_descs([3000] * 48)
+    pools = [U.BatchMapper(idx, max_reads=48, max_samples=48 * 3000) for _ in range(2)]
+    want = [pools[0].map(halves[0], d).copy(), pools[0].map(halves[1], d).copy()]
+    for rep in range(3):
+        pools[0].submit(halves[0], d)
+        pools[1].submit(halves[1], d)
+        with pytest.raises(U.UncError):
+            pools[0].submit(halves[1], d)                      # a pool holds one batch at a time
+        got1 = pools[1].wait()
+        got0 = pools[0].wait()
+        assert np.array_equal(got0, want[0]) and np.array_equal(got1, want[1]), rep
+    with pytest.raises(U.UncError):
+        pools[0].wait()                                            # nothing submitted
+    with pytest.raises(U.UncError):
+        U._native.check(pools[0].L.unc_map_batch_wait(pools[0].h, want[0].ctypes.data))   # the C entry point says so too
+    for p in pools:
+        p.close()
+
+
+def test_self_align_matches_oracle_and_reference_digest(U, example_prefix, tmp_path):
+    """`uncalled index`: unc_self_align against the oracle, the reference's digests and, end to end, the
+    reference-made .uncl files."""
+    import hashlib
+    import orclib
+    import synthdata
+    from uncalled_b200 import index as UI, index_params as IP
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "self_align_golden.json")))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, "<u8").tobytes()).hexdigest()   # noqa: E731
+    for row in gold:
+        prefix = example_prefix if row["index"] == "example" else synthdata.get_index(row["index"])[0]
+        off, val = UI.self_align_csr(prefix, row["sample_dist"])
+        assert (len(off) - 1, len(val)) == (row["n_paths"], row["n_values"])
+        assert sha(off) == row["offsets_sha256"] and sha(val) == row["values_sha256"], row["index"]
+    for name, sd in (("g4m7", 94), ("g200k", 1)):
+        prefix = synthdata.get_index(name)[0]
+        a, b = UI.self_align_csr(prefix, sd), orclib.self_align(prefix, sd)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), name
+    # repeats, tiny and ambiguous sequences: paths beyond the staging depth are re-walked in pass 2
+    import test_selfalign_emul as tse
+    prefix = tse.repeat_index(str(tmp_path))
+    for sd in (1, 3):
+        a, b = UI.self_align_csr(prefix, sd), orclib.self_align(prefix, sd)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), sd
+    assert UI.self_align(prefix, 3) == [[int(v) for v in b[1][int(b[0][i]):int(b[0][i + 1])]] for i in range(len(b[0]) - 1)]
+
+
+def test_index_cmd_reproduces_reference_uncl_files(U, tmp_path):
+    """FASTA -> .bwt/.sa/... -> self_align on the GPU -> .uncl, against what the real `uncalled index` wrote."""
+    import shutil
+    import synth
+    import orclib
+    from uncalled_b200 import index as UI
+    synth_uncl = json.load(open(os.path.join(ROOT, "tests", "golden", "synth_uncl.json")))
+    fa = str(tmp_path / "g.fa")
+    synth.write_fasta(fa, synth.genome(synth_uncl["g200k"]["size"], synth_uncl["g200k"]["seed"]))
+    prefix = UI.index_cmd(fa, str(tmp_path / "g200k"))
+    assert open(prefix + ".uncl").read() == synth_uncl["g200k"]["uncl"]
+    ex = orclib.materialise_example_index(str(tmp_path))
+    shipped = open(ex + ".uncl").read()
+    os.remove(ex + ".uncl")
+    UI.index_cmd(ex + ".fa", ex)                                   # reuses the shipped BWA files
+    assert open(ex + ".uncl").read() == shipped
+    presets = json.load(open(os.path.join(ROOT, "tests", "golden", "uncl_presets.json")))[0]
+    assert UI.write_uncl(ex, probs=presets["probs"], speeds=presets["speeds"]) == presets["uncl"]
+
+
+def test_map_pool_prints_the_reference_paf_lines(example_prefix, golden_read):
+    """`uncalled map`, `-c 1` and `-e 100` on the example read (config 1), line for line up to the mt tag."""
+    from uncalled_b200.api import Conf, MapPool
+    raw = golden_read["raw"]
+    rid, ch, st = str(golden_read["read_id"]), int(golden_read["channel"]), int(golden_read["start"])
+    for key, mod in (("default", {}), ("max_chunks_1", {"max_chunks": 1}), ("max_events_100", {"max_events": 100})):
+        conf = Conf()
+        conf.bwa_prefix = example_prefix
+        for k, v in mod.items():
+            setattr(conf, k, v)
+        pool = MapPool(conf)
+        assert not pool.running()
+        pool.add_read(rid, raw, channel=ch, number=0, start_sample=st)
+        lines = []
+        while pool.running():
+            lines += [p.line() for p in pool.update()]
+        pool.stop()
+        assert len(lines) == 1
+        body, mt = lines[0].rsplit("\t", 1)
+        assert body == GOLD[key]["line"] and mt.startswith("mt:f:"), (key, lines[0])
+
+
+def test_map_pool_i16_reads_and_filters(example_prefix, golden_read, tmp_path):
+    from uncalled_b200.api import Conf, MapPool
+    raw = golden_read["raw"]
+    cal = (1534.14, 10.0, 8192.0)       # the example read's calibration attributes
+    dac = np.round(raw.astype(np.float64) * cal[2] / cal[0] - cal[1]).astype(np.int64)
+    dac16 = dac.astype(np.uint16).astype(np.int16)       # the >32767 spike wraps like the fast5 payload does
+    pa = (np.float32(cal[0]) * (dac16.astype(np.uint16).astype(np.float32) + np.float32(cal[1]))) / np.float32(cal[2])
+    assert np.array_equal(pa.astype(np.float32), raw)
+    rl = tmp_path / "reads.txt"
+    rl.write_text("keep_me\n")
+    conf = Conf()
+    conf.bwa_prefix, conf.read_list = example_prefix, str(rl)
+    pool = MapPool(conf)
+    assert pool.add_read("keep_me", dac16, channel=486, start_sample=257117, calibration=cal)
+    assert not pool.add_read("drop_me", dac16, calibration=cal)
+    out = pool.update()
+    pool.stop()
+    assert len(out) == 1 and out[0].fields()[1:] == GOLD["default"]["fields"][1:]
+
+
+def test_uncalled_map_on_the_example_fast5(example_prefix, tmp_path):
+    """config 1 end to end from the FILE: `uncalled map -t 1 <index> <fast5>`, `-c 1` and `-e 100` (SURVEY 8c golden
+    lines), the fast5 decoded by the library's own reader, calibrated on the GPU; and a fast5 list + read filter."""
+    from uncalled_b200.api import Conf, MapPool
+    f5 = os.path.join(ROOT, "tests", "golden", "fast5", "example_single.fast5")
+    for key, mod in (("default", {}), ("max_chunks_1", {"max_chunks": 1}), ("max_events_100", {"max_events": 100})):
+        conf = Conf()
+        conf.bwa_prefix = example_prefix
+        for k, v in mod.items():
+            setattr(conf, k, v)
+        pool = MapPool(conf)
+        pool.add_fast5(f5)
+        assert pool.running()
+        lines = []
+        while pool.running():
+            lines += [p.line() for p in pool.update()]
+        pool.stop()
+        assert len(lines) == 1 and lines[0].rsplit("\t", 1)[0] == GOLD[key]["line"], (key, lines)
+    # fast5_list + read_list + max_reads over multi-read files (none of these reads map to the example reference)
+    fl, rl = tmp_path / "files.txt", tmp_path / "reads.txt"
+    multi = os.path.join(ROOT, "tests", "golden", "fast5", "multi_gzip.fast5")
+    fl.write_text(multi + "\n" + f5 + "\n")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fast5", "golden.json")))
+    ids = sorted(set(r["id"] for r in gold if r["file"] == "multi_gzip.fast5"))
+    rl.write_text("\n".join(ids[:5] + ["f41a60f7-de4a-4b17-9f54-387e52d60b65"]) + "\n")
+    conf = Conf()
+    conf.bwa_prefix, conf.fast5_list, conf.read_list, conf.batch_reads = example_prefix, str(fl), str(rl), 4
+    pool = MapPool(conf)
+    out = []
+    while pool.running():
+        out += pool.update()
+    pool.stop()
+    assert sorted(p.fields()[0] for p in out) == sorted(ids[:5] + ["f41a60f7-de4a-4b17-9f54-387e52d60b65"])
+    assert [p.is_mapped() for p in out if p.fields()[0].startswith("f41a60f7")] == [True]
+
+
+def test_cli_index_then_map_end_to_end(tmp_path, capsys):
+    """`uncalled index example_ref.fa` from the FASTA alone, then `uncalled map` of the example fast5 against it: the
+    reference's golden PAF line (a rebuilt index is byte-identical to the shipped one)."""
+    import orclib
+    from uncalled_b200 import cli
+    os.makedirs(tmp_path / "src")
+    src = orclib.materialise_example_index(str(tmp_path / "src"))
+    fa = str(tmp_path / "example_ref.fa")
+    open(fa, "wb").write(open(src + ".fa", "rb").read())
+    assert cli.main(["index", fa]) == 0
+    for ext in (".bwt", ".sa", ".ann", ".amb", ".pac", ".uncl"):
+        assert open(fa + ext, "rb").read() == open(src + ext, "rb").read(), ext
+    capsys.readouterr()
+    assert cli.main(["map", fa, os.path.join(ROOT, "tests", "golden", "fast5", "example_single.fast5")]) == 0
+    cap = capsys.readouterr()
+    lines = cap.out.strip().split("\n")
+    assert len(lines) == 1 and lines[0].rsplit("\t", 1)[0] == GOLD["default"]["line"].replace("\n", "")
+    assert cap.err.count("Mapping\n") == 1 and cap.err.count("Finishing\n") == 1

@@ -168,6 +168,11 @@ int unc_map_batch_device(unc_pool *pool, const unc_read_desc *reads, uint32_t n_
 int unc_map_batch_submit(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads, const void *samples,
                          int samples_on_device);
 int unc_map_batch_wait(unc_pool *pool, unc_paf_rec *out);
+/* Device-side timing of work spread over several pools: record marks event `slot` (0 or 1) at the current end of
+ * the pool's stream; elapsed waits for both events and returns the milliseconds from the first to the second (they
+ * may belong to different pools of the same device). */
+int unc_pool_record(unc_pool *pool, int slot);
+int unc_pool_elapsed(unc_pool *from, int from_slot, unc_pool *to, int to_slot, float *ms);
 
 /* Event detection + normalisation alone.  events/normed hold `stride` floats per read
  * (stride >= the longest read's n_samples); n_events, mean_event_len one entry per read. */

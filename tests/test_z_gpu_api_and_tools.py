@@ -38,6 +38,14 @@ def test_submit_wait_on_two_pools_matches_the_synchronous_call(U):
         got1 = pools[1].wait()
         got0 = pools[0].wait()
         assert np.array_equal(got0, want[0]) and np.array_equal(got1, want[1]), rep
+    pools[0].record(0)                                             # device-side timing across the two pools
+    pools[0].submit(halves[0], d)
+    pools[1].submit(halves[1], d)
+    pools[0].record(1)
+    pools[1].record(1)
+    assert np.array_equal(pools[0].wait(), want[0]) and np.array_equal(pools[1].wait(), want[1])
+    span = max(pools[0].elapsed_ms(0, pools[0], 1), pools[0].elapsed_ms(0, pools[1], 1))
+    assert 0.0 < span < 60000.0
     with pytest.raises(U.UncError):
         pools[0].wait()                                            # nothing submitted
     with pytest.raises(U.UncError):

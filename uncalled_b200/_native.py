@@ -81,7 +81,7 @@ class Fast5Read(C.Structure):
 EXPORTS = ["unc_strerror", "unc_last_error", "unc_device_count", "unc_init", "unc_shutdown", "unc_params_default",
            "unc_index_load", "unc_index_get_info", "unc_index_seq", "unc_index_kmer_range",
            "unc_index_thresholds", "unc_index_free", "unc_index_build", "unc_pool_create", "unc_pool_free",
-           "unc_map_batch", "unc_map_batch_device", "unc_map_batch_submit", "unc_map_batch_wait", "unc_events_batch", "unc_match_probs", "unc_fm_neighbors",
+           "unc_map_batch", "unc_map_batch_device", "unc_map_batch_submit", "unc_map_batch_wait", "unc_pool_record", "unc_pool_elapsed", "unc_events_batch", "unc_match_probs", "unc_fm_neighbors",
            "unc_fm_sa", "unc_pool_last_timing", "unc_pool_k1_stats", "unc_stream_create", "unc_stream_step",
            "unc_stream_free", "unc_self_align", "unc_free", "unc_fast5_open", "unc_fast5_count", "unc_fast5_info",
            "unc_fast5_load", "unc_fast5_close", "unc_fast5_last_error"]
@@ -139,6 +139,8 @@ def lib():
     L.unc_map_batch_device.argtypes = [vp, vp, u32, vp, vp]
     L.unc_map_batch_submit.argtypes = [vp, vp, u32, vp, C.c_int]
     L.unc_map_batch_wait.argtypes = [vp, vp]
+    L.unc_pool_record.argtypes = [vp, C.c_int]
+    L.unc_pool_elapsed.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_float)]
     L.unc_events_batch.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp, vp]
     L.unc_match_probs.argtypes = [vp, C.c_float, vp]
     L.unc_fm_neighbors.argtypes = [vp, u32, vp, vp, vp, vp, vp]

@@ -171,6 +171,7 @@ struct unc_pool {
     uint32_t n_slots = 0, grid = 0;
     size_t smem = 0;
     unc_timing last;
+    cudaEvent_t ev_user[2] = {nullptr, nullptr};   // unc_pool_record / unc_pool_elapsed
     uint32_t pending_n = 0;      // reads of a submitted, not yet collected batch (unc_map_batch_submit / _wait)
     uint64_t pending_h2d = 0;
 };
@@ -449,6 +450,7 @@ void unc_pool_free(unc_pool *P) {
     cudaFree(P->d_events); cudaFree(P->d_normed);
     cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue); cudaFree(P->d_k1_flags);
     cudaFree(P->d_out); cudaFreeHost(P->h_out); cudaFree(P->d_dbg);
+    for (int i = 0; i < 2; i++) if (P->ev_user[i]) cudaEventDestroy(P->ev_user[i]);
     for (int i = 0; i < 6; i++) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
     if (P->stream) cudaStreamDestroy(P->stream);
     delete P;
@@ -602,6 +604,25 @@ int unc_map_batch_submit(unc_pool *P, const unc_read_desc *reads, uint32_t n, co
 
 int unc_map_batch_wait(unc_pool *P, unc_paf_rec *out) {
     return batch_finish(P, out);
+}
+
+int unc_pool_record(unc_pool *P, int slot) {
+    if (!P || slot < 0 || slot > 1) return fail(UNC_E_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(P->idx->device));
+    if (!P->ev_user[slot]) CUDA_TRY(cudaEventCreate(&P->ev_user[slot]));
+    CUDA_TRY(cudaEventRecord(P->ev_user[slot], P->stream));
+    return UNC_OK;
+}
+
+int unc_pool_elapsed(unc_pool *from, int from_slot, unc_pool *to, int to_slot, float *ms) {
+    if (!from || !to || !ms || from_slot < 0 || from_slot > 1 || to_slot < 0 || to_slot > 1 || !from->ev_user[from_slot] ||
+        !to->ev_user[to_slot])
+        return fail(UNC_E_ARG, "bad argument or event never recorded");
+    CUDA_TRY(cudaSetDevice(to->idx->device));
+    CUDA_TRY(cudaEventSynchronize(from->ev_user[from_slot]));
+    CUDA_TRY(cudaEventSynchronize(to->ev_user[to_slot]));
+    CUDA_TRY(cudaEventElapsedTime(ms, from->ev_user[from_slot], to->ev_user[to_slot]));
+    return UNC_OK;
 }
 
 int unc_map_batch_device(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *d_samples, unc_paf_rec *out) {

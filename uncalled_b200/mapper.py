@@ -143,6 +143,16 @@ class BatchMapper:
             N.check(rc)
         return out
 
+    def record(self, slot):
+        """Mark event `slot` (0/1) at the current end of this pool's stream (device-side timing across pools)."""
+        N.check(self.L.unc_pool_record(self.h, int(slot)))
+
+    def elapsed_ms(self, slot, other, other_slot):
+        """Milliseconds from this pool's event `slot` to `other`'s event `other_slot` (waits for both)."""
+        ms = C.c_float()
+        N.check(self.L.unc_pool_elapsed(self.h, int(slot), other.h, int(other_slot), C.byref(ms)))
+        return float(ms.value)
+
     def events(self, samples, descs):
         samples = np.ascontiguousarray(samples)
         n = len(descs)

@@ -303,7 +303,10 @@ class MapPool:
         return m
 
     def _launch(self, batch):
-        """Put a batch on the GPU (unc_map_batch_submit on the pool that is not in flight) and return at once."""
+        """Put a batch on the GPU (unc_map_batch_submit on the pool that is not in flight) and return at once.
+        The CTAs take reads from the batch in order, so the longest signals go first: the batch then ends on short
+        reads instead of leaving most SMs idle behind one long read (results are matched by read, not by position)."""
+        batch.sort(key=lambda r: -len(r.signal))
         lens = [len(r.signal) for r in batch]
         total = int(sum(lens))
         dtype = batch[0].dtype

@@ -197,3 +197,20 @@ def test_cli_index_then_map_end_to_end(tmp_path, capsys):
     lines = cap.out.strip().split("\n")
     assert len(lines) == 1 and lines[0].rsplit("\t", 1)[0] == GOLD["default"]["line"].replace("\n", "")
     assert cap.err.count("Mapping\n") == 1 and cap.err.count("Finishing\n") == 1
+
+
+def test_multi_contig_index_built_and_mapped_on_the_gpu(U, tmp_path):
+    """Three contigs with N runs: `uncalled index` entirely on this library (GPU self-alignments), then reads of every
+    contig through unc_map_batch against the oracle -- rid / offsets come from bns_pos2rid on the device."""
+    import orclib
+    import test_multi_contig as M
+    prefix, gens = M.build_multi_contig_index(str(tmp_path), None)           # None: unc_self_align on the GPU
+    sigs = M.contig_reads(gens)
+    idx = U.Index(prefix, device=0)
+    bm = U.BatchMapper(idx, max_reads=len(sigs), max_samples=sum(len(s) for s in sigs))
+    out = bm.map(np.concatenate(sigs), U.make_descs([len(s) for s in sigs]))
+    O = orclib.Oracle(prefix)
+    for i, s in enumerate(sigs):
+        assert orclib.paf_tuple(O.map_read(s)) == U.paf_key(out[i]), i
+    assert len(set(int(r["rid"]) for r in out if r["mapped"])) == 3
+    bm.close()

@@ -1035,6 +1035,7 @@ static void mapper_free(mapper_t *mp) {
 }
 
 /* reference src/mapper.cpp:188-200 (map_read), :216-246 (reset), read_buffer.cpp:263-266 */
+static __thread int g_carry_flags = 0;   /* orc_map_reads_one_mapper: keep sources_added_ from the previous read (see there) */
 static void mapper_map_read(mapper_t *mp, const float *raw, u32 n, orc_paf_rec *out, float *ev_buf,
                             float *norm_buf) {
     struct timespec t0, t1;
@@ -1045,7 +1046,7 @@ static void mapper_map_read(mapper_t *mp, const float *raw, u32 n, orc_paf_rec *
     mp->prev_size = 0;
     mp->event_i = 0;
     trk_reset(&mp->trk);
-    memset(mp->sources_added, 0, sizeof(mp->sources_added)); /* fresh Mapper per read */
+    if (!g_carry_flags) memset(mp->sources_added, 0, sizeof(mp->sources_added)); /* fresh Mapper per read */
     fm_counters cnt = {0, 0, 0};
     g_cnt = &cnt;
 
@@ -1074,6 +1075,26 @@ int orc_map_read(const orc_index *idx, const orc_model *m, const orc_params *p, 
     mapper_init(&mp, idx, m, p);
     float *ev = (float *) malloc(((size_t) n + 1) * 4), *nb = (float *) malloc(((size_t) n + 1) * 4);
     mapper_map_read(&mp, raw, n, out, ev, nb);
+    free(ev);
+    free(nb);
+    mapper_free(&mp);
+    return 0;
+}
+
+/* ONE long-lived Mapper mapping the reads in the given order, as a MapPool thread does (reference
+ * src/map_pool.cpp:104-158): Mapper::reset() (src/mapper.cpp:216-246) clears everything except the
+ * sources_added_ flags (:88), so a read starts with whatever its predecessor left set.  This is what
+ * `uncalled map -t 1` computes for a multi-read input; single-threaded on purpose (the order is the point). */
+int orc_map_reads_one_mapper(const orc_index *idx, const orc_model *m, const orc_params *p, const float *samples,
+                             const uint64_t *offsets, const uint32_t *lens, uint32_t n_reads, orc_paf_rec *out) {
+    mapper_t mp;
+    mapper_init(&mp, idx, m, p);
+    u32 mx = 0;
+    for (u32 i = 0; i < n_reads; i++) if (lens[i] > mx) mx = lens[i];
+    float *ev = (float *) malloc(((size_t) mx + 1) * 4), *nb = (float *) malloc(((size_t) mx + 1) * 4);
+    g_carry_flags = 1;
+    for (u32 i = 0; i < n_reads; i++) mapper_map_read(&mp, samples + offsets[i], lens[i], &out[i], ev, nb);
+    g_carry_flags = 0;
     free(ev);
     free(nb);
     mapper_free(&mp);

@@ -198,6 +198,19 @@ class Oracle:
                                   offsets.ctypes.data_as(u64p), lens.ctypes.data_as(u32p), len(lens), threads, out)
         return list(out)
 
+    def map_reads_one_mapper(self, samples, offsets, lens):
+        """One long-lived Mapper over the reads in order (`uncalled map -t 1`): sources_added_ carried between reads."""
+        n = len(lens)
+        out = (OrcPaf * n)()
+        self.lib.orc_map_reads_one_mapper.argtypes = [C.c_void_p, C.POINTER(OrcModel), C.POINTER(OrcParams), f32p, u64p, u32p,
+                                                      C.c_uint32, C.POINTER(OrcPaf)]
+        samples = np.ascontiguousarray(samples, np.float32)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        lens = np.ascontiguousarray(lens, np.uint32)
+        self.lib.orc_map_reads_one_mapper(self.idx, C.byref(self.model), C.byref(self.params), fp(samples),
+                                          offsets.ctypes.data_as(u64p), lens.ctypes.data_as(u32p), n, out)
+        return list(out)
+
     def kmer_ranges(self):
         st = np.zeros(1024, np.uint64)
         en = np.zeros(1024, np.uint64)
@@ -215,11 +228,12 @@ def ref_available():
     return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libuncalled_ref.so"))
 
 
-def ref():
-    """oracle/_ref: the reference's own code.  One index per process (static state)."""
+def ref(stable_sort=False):
+    """oracle/_ref: the reference's own code.  One index per process (static state), and one of the two builds per
+    process: stable_sort=True loads the build whose child sort is stable (oracle/ref_build/stubs_stable/pdqsort.h)."""
     global _ref
     if _ref is None:
-        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libuncalled_ref.so"))
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libuncalled_ref_stable.so" if stable_sort else "libuncalled_ref.so"))
         lib.ref_load.argtypes = [C.c_char_p, C.c_char_p]
         lib.ref_set_max_events.argtypes = [C.c_uint32]
         lib.ref_fmi_size.restype = C.c_uint64

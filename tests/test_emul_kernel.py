@@ -67,7 +67,6 @@ def test_full_buffer_semantics(g200k, max_paths):
 
 @pytest.mark.parametrize("flags,tag", [(("-DK2_LEAN_B", "-DK2_PAR_E"), "_lean_pare"), (("-DK2_TRK_INLINE",), "_trk"),
                                       (("-DK2_SCAN2", "-DK2_PF2", "-DK2_BMATCH"), "_scan2_pf2_bmatch"),
-                                      (("-DK2_DFUSE",), "_dfuse"),
                                       (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2", "-DK2_PF2", "-DK2_DFUSE"), "_all")])
 def test_prototype_variants_keep_parity(g200k, flags, tag):
     """Compile-time prototypes for a higher-occupancy build must produce the same paths, seeds and PAF records:

@@ -57,8 +57,7 @@ def test_max_chunks_and_one_second_chunks(g200k):
     _check(E, O, [sig[i][:4500] for i in range(2)], 2, 4000, n_warps=2)   # chunk_time 1.0 s, a 2-warp CTA
 
 
-@pytest.mark.parametrize("flags,tag", [(("-DK2_TRK_INLINE",), "_trk"),
-                                      (("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2", "-DK2_PF2", "-DK2_DFUSE"), "_all")])
+@pytest.mark.parametrize("flags,tag", [(("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2", "-DK2_PF2", "-DK2_DFUSE"), "_all")])
 def test_tracker_inline_variant_streams_identically(g200k, flags, tag):
     """-DK2_TRK_INLINE keeps the seed tracker's state in shared memory between events and in the channel's
     DevMapState between chunks: same results chunk by chunk (alone and with the other prototypes)."""

@@ -841,6 +841,188 @@ static int path_cmp(const void *a, const void *b) {
     return p->emit_idx < q->emit_idx ? -1 : (p->emit_idx > q->emit_idx);
 }
 
+/* ---- the reference's child sort, restated: pdqsort (reference submods/pdqsort/pdqsort.h, Orson Peters' pattern-defeating
+ * quicksort, non-branchless variant because PathBuffer is not arithmetic: pdqsort.h:507-526) under operator< of
+ * src/mapper.cpp:866-871.  It is UNSTABLE: children that compare equal end up in an order that depends on the whole
+ * array's input order.  orc_set_child_sort(1) selects it, so that the oracle reproduces the unmodified reference even there;
+ * the default (0) is the stable order the CUDA path uses.  Elements are moved as whole structs, as
+ * the reference's memcpy copy constructor does (src/mapper.cpp:742-744). */
+static int g_child_sort_pdq = 0;          /* process-wide: the batch entry points map on worker threads */
+static unsigned long g_pdq_heapsorts = 0;
+void orc_set_child_sort(int pdqsort_mode) { g_child_sort_pdq = pdqsort_mode; }
+unsigned long orc_pdq_heapsort_fallbacks(void) { return g_pdq_heapsorts; }
+
+static inline int p_less(const path_t *a, const path_t *b) {
+    if (a->fm_start != b->fm_start) return a->fm_start < b->fm_start;
+    if (a->fm_end != b->fm_end) return a->fm_end < b->fm_end;
+    return a->seed_prob < b->seed_prob;
+}
+static inline void p_swap(path_t *a, path_t *b) { path_t t = *a; *a = *b; *b = t; }
+static inline void p_sort2(path_t *a, path_t *b) { if (p_less(b, a)) p_swap(a, b); }
+static inline void p_sort3(path_t *a, path_t *b, path_t *c) { p_sort2(a, b); p_sort2(b, c); p_sort2(a, b); }
+
+/* pdqsort.h:76-97 (guarded) and :99-121 (unguarded: *(begin-1) is known to be <= everything in the range) */
+static void pdq_insertion(path_t *begin, path_t *end, int guarded) {
+    if (begin == end) return;
+    for (path_t *cur = begin + 1; cur != end; ++cur) {
+        path_t *sift = cur, *sift_1 = cur - 1;
+        if (p_less(sift, sift_1)) {
+            path_t tmp = *sift;
+            do { *sift-- = *sift_1; } while ((!guarded || sift != begin) && p_less(&tmp, --sift_1));
+            *sift = tmp;
+        }
+    }
+}
+/* pdqsort.h:123-148: gives up (returns 0) once more than 8 element moves were needed */
+static int pdq_partial_insertion(path_t *begin, path_t *end) {
+    if (begin == end) return 1;
+    long limit = 0;
+    for (path_t *cur = begin + 1; cur != end; ++cur) {
+        if (limit > 8) return 0;
+        path_t *sift = cur, *sift_1 = cur - 1;
+        if (p_less(sift, sift_1)) {
+            path_t tmp = *sift;
+            do { *sift-- = *sift_1; } while (sift != begin && p_less(&tmp, --sift_1));
+            *sift = tmp;
+            limit += cur - sift;
+        }
+    }
+    return 1;
+}
+/* pdqsort.h:340-381: elements equal to the pivot go right; *already = the range was partitioned on entry */
+static path_t *pdq_partition_right(path_t *begin, path_t *end, int *already) {
+    path_t pivot = *begin;
+    path_t *first = begin, *last = end;
+    while (p_less(++first, &pivot)) {}
+    if (first - 1 == begin) { while (first < last && !p_less(--last, &pivot)) {} }
+    else { while (!p_less(--last, &pivot)) {} }
+    *already = first >= last;
+    while (first < last) {
+        p_swap(first, last);
+        while (p_less(++first, &pivot)) {}
+        while (!p_less(--last, &pivot)) {}
+    }
+    path_t *pivot_pos = first - 1;
+    *begin = *pivot_pos;
+    *pivot_pos = pivot;
+    return pivot_pos;
+}
+/* pdqsort.h:384-408: elements equal to the pivot go left */
+static path_t *pdq_partition_left(path_t *begin, path_t *end) {
+    path_t pivot = *begin;
+    path_t *first = begin, *last = end;
+    while (p_less(&pivot, --last)) {}
+    if (last + 1 == end) { while (first < last && !p_less(&pivot, ++first)) {} }
+    else { while (!p_less(&pivot, ++first)) {} }
+    while (first < last) {
+        p_swap(first, last);
+        while (p_less(&pivot, --last)) {}
+        while (!p_less(&pivot, ++first)) {}
+    }
+    path_t *pivot_pos = last;
+    *begin = *pivot_pos;
+    *pivot_pos = pivot;
+    return pivot_pos;
+}
+/* libstdc++'s std::make_heap + std::sort_heap (bits/stl_heap.h: __adjust_heap / __push_heap), pdqsort's fallback after
+ * log2(n) highly unbalanced partitions (pdqsort.h:464-468) */
+static void heap_adjust(path_t *first, long hole, long len, path_t value) {
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (p_less(first + child, first + (child - 1))) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    long parent = (hole - 1) / 2;
+    while (hole > top && p_less(first + parent, &value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+static void pdq_heapsort(path_t *first, path_t *last) {
+    long len = last - first;
+    g_pdq_heapsorts++;
+    if (len < 2) return;
+    for (long parent = (len - 2) / 2;; parent--) {
+        heap_adjust(first, parent, len, first[parent]);
+        if (parent == 0) break;
+    }
+    while (last - first > 1) {
+        --last;
+        path_t value = *last;
+        *last = *first;
+        heap_adjust(first, 0, last - first, value);
+    }
+}
+/* pdqsort.h:411-504 */
+static void pdq_loop(path_t *begin, path_t *end, int bad_allowed, int leftmost) {
+    for (;;) {
+        long size = end - begin;
+        if (size < 24) { pdq_insertion(begin, end, leftmost); return; }
+        long s2 = size / 2;
+        if (size > 128) {
+            p_sort3(begin, begin + s2, end - 1);
+            p_sort3(begin + 1, begin + (s2 - 1), end - 2);
+            p_sort3(begin + 2, begin + (s2 + 1), end - 3);
+            p_sort3(begin + (s2 - 1), begin + s2, begin + (s2 + 1));
+            p_swap(begin, begin + s2);
+        } else {
+            p_sort3(begin + s2, begin, end - 1);
+        }
+        if (!leftmost && !p_less(begin - 1, begin)) {
+            begin = pdq_partition_left(begin, end) + 1;
+            continue;
+        }
+        int already;
+        path_t *pivot_pos = pdq_partition_right(begin, end, &already);
+        long l_size = pivot_pos - begin, r_size = end - (pivot_pos + 1);
+        int highly_unbalanced = l_size < size / 8 || r_size < size / 8;
+        if (highly_unbalanced) {
+            if (--bad_allowed == 0) { pdq_heapsort(begin, end); return; }
+            if (l_size >= 24) {
+                p_swap(begin, begin + l_size / 4);
+                p_swap(pivot_pos - 1, pivot_pos - l_size / 4);
+                if (l_size > 128) {
+                    p_swap(begin + 1, begin + (l_size / 4 + 1));
+                    p_swap(begin + 2, begin + (l_size / 4 + 2));
+                    p_swap(pivot_pos - 2, pivot_pos - (l_size / 4 + 1));
+                    p_swap(pivot_pos - 3, pivot_pos - (l_size / 4 + 2));
+                }
+            }
+            if (r_size >= 24) {
+                p_swap(pivot_pos + 1, pivot_pos + (1 + r_size / 4));
+                p_swap(end - 1, end - r_size / 4);
+                if (r_size > 128) {
+                    p_swap(pivot_pos + 2, pivot_pos + (2 + r_size / 4));
+                    p_swap(pivot_pos + 3, pivot_pos + (3 + r_size / 4));
+                    p_swap(end - 2, end - (1 + r_size / 4));
+                    p_swap(end - 3, end - (2 + r_size / 4));
+                }
+            }
+        } else if (already && pdq_partial_insertion(begin, pivot_pos) && pdq_partial_insertion(pivot_pos + 1, end)) {
+            return;
+        }
+        pdq_loop(begin, pivot_pos, bad_allowed, leftmost);
+        begin = pivot_pos + 1;
+        leftmost = 0;
+    }
+}
+static void pdq_sort(path_t *begin, path_t *end) {
+    if (begin == end) return;
+    int lg = 0;
+    for (long n = end - begin; n >>= 1;) ++lg;
+    pdq_loop(begin, end, lg, 1);
+}
+
 static inline float prob_thresh(const orc_index *x, u64 fmlen) { return x->thresh[__builtin_clzll(fmlen)]; }
 
 /* reference src/mapper.cpp:703-706 (event_to_bp) */
@@ -930,7 +1112,8 @@ static int map_next_event(mapper_t *mp, float event, float mean_event_len) {
 
     if (nn != 0) {
         u32 next_size = nn;
-        qsort(mp->next, next_size, sizeof(path_t), path_cmp);
+        if (g_child_sort_pdq) pdq_sort(mp->next, mp->next + next_size);
+        else qsort(mp->next, next_size, sizeof(path_t), path_cmp);
 
         u16 source_kmer, prev_kmer = ORC_NKMER;
         u64 unchecked_st = 1, unchecked_en = 0, src_st, src_en;

@@ -140,6 +140,17 @@ for i in range(30, 40):
     if a != b:
         d.append((i, a[5], a[10], b[5], b[10]))
 print("TIE-DIFF", d)
+# ... and with the reference's pdqsort restated in the oracle (orc_set_child_sort(1)) nothing differs any more, here and on
+# reads of a second set that the stable order maps differently
+O.lib.orc_set_child_sort(1)
+b, _ = synth.reads(g, 2400, 4000, seed=123, frac_random=0.15)
+for s in [sig[i] for i in range(30, 40)] + [b[i] for i in (64, 137, 1395, 1598, 1971)]:
+    s = np.ascontiguousarray(s, np.float32)
+    out = orclib.RefPaf()
+    R.ref_map_read(orclib.fp(s), len(s), C.byref(out))
+    assert orclib.paf_tuple(out) == orclib.paf_tuple(O.map_read(s))
+O.lib.orc_set_child_sort(0)
+print("PDQ-OK")
 """
 
 
@@ -149,7 +160,8 @@ def test_the_two_documented_divergences_and_nothing_else():
     fresh flags (the product's batch semantics) changes read 589 of the 600-read set and no other read near it.
     (2) Tie order: the reference sorts children with pdqsort (unstable); of reads 30..39 mapped by FRESH Mappers on both
     sides, read 36 ends one seed longer in the reference (matches 55 / rf_en 1749657 against 54 / 1749656) and the other
-    nine are identical."""
+    nine are identical; with pdqsort itself restated in the oracle (orc_set_child_sort(1)) all of them, and five reads of a
+    second set that the stable order maps differently, are identical to the unmodified reference."""
     import subprocess
     import orclib
     if not orclib.ref_available():
@@ -158,6 +170,7 @@ def test_the_two_documented_divergences_and_nothing_else():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     assert "CARRY-DIFF [589]" in r.stdout and "TIE-DIFF [(36, 55, 1749657, 54, 1749656)]" in r.stdout, r.stdout
+    assert "PDQ-OK" in r.stdout
 
 
 STABLE = r"""

@@ -2,6 +2,7 @@
 """Reproduces the numbers of DESIGN.md section 2 (needs oracle/_ref, i.e. /root/reference at build time; minutes of CPU):
     python tools/measure_divergences.py pdqsort [n]   reference as is        vs the oracle, fresh Mapper per read
     python tools/measure_divergences.py stable  [n]   reference, stable sort vs the oracle, fresh Mapper per read
+    python tools/measure_divergences.py pdq-oracle [n] reference as is     vs the oracle with pdqsort restated (orc_set_child_sort(1))
     python tools/measure_divergences.py carry   [n]   reference, ONE long-lived Mapper vs the oracle's fresh / carried modes
 One build of the reference per process (it keeps its index in process-global statics)."""
 import ctypes as C
@@ -23,6 +24,8 @@ prefix, g = synthdata.get_index("g4m7")
 R = orclib.ref(stable_sort=(mode == "stable"))
 assert R.ref_load(prefix.encode(), b"default") == 0
 O = orclib.Oracle(prefix)
+if mode == "pdq-oracle":
+    O.lib.orc_set_child_sort(1)
 sig, _ = synth.reads(g, n, 4000, seed=7 if mode == "carry" else 123, frac_random=0.15)
 flat = np.ascontiguousarray(sig.reshape(-1))
 offs, lens = (np.arange(n) * 4000).astype(np.uint64), np.full(n, 4000, np.uint32)

@@ -1023,6 +1023,37 @@ static void pdq_sort(path_t *begin, path_t *end) {
     pdq_loop(begin, end, lg, 1);
 }
 
+/* Diagnostics (orc_set_child_sort(2) = pdqsort + statistics): per event, does the survivor of any run of equal ranges --
+ * the LAST of the run, reference src/mapper.cpp:569-572 -- differ between pdqsort's order and the stable order in a field
+ * that outlives the event?  [0] events with children, [1] events where a survivor differs, [2] children, [3] children in
+ * runs whose survivor differs. */
+static unsigned long g_tie_stats[4];
+void orc_tie_stats(unsigned long out[4]) { memcpy(out, g_tie_stats, sizeof(g_tie_stats)); }
+static void tie_stats(const path_t *next, u32 n) {
+    path_t *a = (path_t *) malloc((size_t) n * sizeof(path_t)), *b = (path_t *) malloc((size_t) n * sizeof(path_t));
+    memcpy(a, next, (size_t) n * sizeof(path_t));
+    memcpy(b, next, (size_t) n * sizeof(path_t));
+    pdq_sort(a, a + n);
+    qsort(b, n, sizeof(path_t), path_cmp);
+    unsigned long bad_runs = 0, bad_children = 0;
+    for (u32 i = 0; i < n;) {
+        u32 j = i;
+        while (j + 1 < n && a[j + 1].fm_start == a[i].fm_start && a[j + 1].fm_end == a[i].fm_end) j++;
+        const path_t *x = &a[j], *y = &b[j];             /* the survivors (both arrays hold the same multiset of keys) */
+        int same = x->event_moves == y->event_moves && x->length == y->length && x->consec_stays == y->consec_stays &&
+                   x->sa_checked == y->sa_checked && x->kmer == y->kmer &&
+                   !memcmp(x->prob_sums, y->prob_sums, sizeof(x->prob_sums));
+        if (!same) { bad_runs++; bad_children += j - i + 1; }
+        i = j + 1;
+    }
+    __sync_fetch_and_add(&g_tie_stats[0], 1);
+    __sync_fetch_and_add(&g_tie_stats[1], bad_runs ? 1 : 0);
+    __sync_fetch_and_add(&g_tie_stats[2], n);
+    __sync_fetch_and_add(&g_tie_stats[3], bad_children);
+    free(a);
+    free(b);
+}
+
 static inline float prob_thresh(const orc_index *x, u64 fmlen) { return x->thresh[__builtin_clzll(fmlen)]; }
 
 /* reference src/mapper.cpp:703-706 (event_to_bp) */
@@ -1112,8 +1143,12 @@ static int map_next_event(mapper_t *mp, float event, float mean_event_len) {
 
     if (nn != 0) {
         u32 next_size = nn;
-        if (g_child_sort_pdq) pdq_sort(mp->next, mp->next + next_size);
-        else qsort(mp->next, next_size, sizeof(path_t), path_cmp);
+        if (g_child_sort_pdq) {
+            if (g_child_sort_pdq == 2) tie_stats(mp->next, next_size);   /* diagnostics: how often does the order of ties matter? */
+            pdq_sort(mp->next, mp->next + next_size);
+        } else {
+            qsort(mp->next, next_size, sizeof(path_t), path_cmp);
+        }
 
         u16 source_kmer, prev_kmer = ORC_NKMER;
         u64 unchecked_st = 1, unchecked_en = 0, src_st, src_en;

@@ -316,3 +316,24 @@ def test_stream_limits(U):
         p.max_paths = 300
     st = _stream_vs_oracle(U, prefix, sigs, 3, 450, params_mod=mod)
     assert (3, 1) in st
+
+
+def test_map_matches_records_computed_by_the_reference_itself(U):
+    """No oracle in between: tests/golden/synth_paf_golden.json holds what the reference's own code computes for 320 seeded
+    reads (tools/make_synth_paf_golden.py) -- with its child sort made stable, which is the order this path defines for
+    equal children, and as it is (pdqsort): identical to the former on every read, to the latter on all but the two reads
+    the fixture lists (tie order)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synth_paf_golden as M
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "synth_paf_golden.json")))
+    for name, n, ns, seed, frac in M.SETS:
+        prefix, sig = M.signals(name, n, ns, seed, frac)
+        idx = U.Index(prefix, device=0)
+        bm = U.BatchMapper(idx, max_reads=n, max_samples=n * ns)
+        out = bm.map(np.ascontiguousarray(sig.reshape(-1)), U.make_descs([ns] * n))
+        got = [[int(v) for v in U.paf_key(r)] for r in out]
+        assert got == gold["reference_stable_sort"][name], name
+        assert [i for i in range(n) if got[i] != gold["reference"][name][i]] == gold["differ"][name]
+        bm.close()
+

@@ -206,3 +206,25 @@ def test_reference_with_a_stable_child_sort_agrees_on_every_read():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "STABLE-OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
+
+
+def test_oracle_matches_reference_made_paf_golden_in_both_sort_modes():
+    """tests/golden/synth_paf_golden.json (tools/make_synth_paf_golden.py): records computed by the reference's own code for
+    320 seeded reads -- as it is, and with its child sort made stable.  Oracle mode 1 (pdqsort restated) must give the
+    former, mode 0 (stable) the latter; the two differ on two reads of the 4.7 Mb set."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synth_paf_golden as M
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "synth_paf_golden.json")))
+    assert gold["differ"] == {"g200k": [], "g4m7": [64, 137]}
+    for name, n, ns, seed, frac in M.SETS:
+        prefix, sig = M.signals(name, n, ns, seed, frac)
+        O = orclib.Oracle(prefix)
+        flat = np.ascontiguousarray(sig.reshape(-1))
+        offs, lens = (np.arange(n) * ns).astype(np.uint64), np.full(n, ns, np.uint32)
+        try:
+            for mode, key in ((0, "reference_stable_sort"), (1, "reference")):
+                O.lib.orc_set_child_sort(mode)
+                got = [[int(v) for v in orclib.paf_tuple(r)] for r in O.map_batch(flat, offs, lens, threads=8)]
+                assert got == gold[key][name], (name, key)
+        finally:
+            O.lib.orc_set_child_sort(0)

@@ -158,6 +158,19 @@ int unc_map_batch(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads, 
 int unc_map_batch_device(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads,
                          const void *d_samples, unc_paf_rec *out);
 
+/* The batch mapped as ONE long-lived Mapper maps its reads one after the other -- what `uncalled map -t 1` prints
+ * for a multi-read input.  Replaces a MapPool thread's loop over its reads (reference src/map_pool.cpp:104-158):
+ * Mapper::reset (src/mapper.cpp:216-246) keeps the sources_added_ flags (:88), so a read starts with the flags its
+ * predecessor left set.  unc_map_batch gives every read a clear set (the reference's result for a read that is
+ * first on its thread); this call resolves the chain instead: all reads are mapped in one launch, then only those
+ * whose predecessor ended with other flags than they were mapped from are mapped again, until nothing changes
+ * (uncalled_b200/csrc/unc_ordered_logic.hpp).  carry[32] (k-mer k = bit k&31 of word k>>5): in, the flags before
+ * reads[0] (all zero for a new Mapper); out, the flags after the last read -- pass it on to the next batch.
+ * n_remapped / n_rounds (optional): reads mapped a second time, extra launches. */
+int unc_map_batch_ordered(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads, const void *samples,
+                          int samples_on_device, uint32_t carry[32], unc_paf_rec *out, uint32_t *n_remapped,
+                          uint32_t *n_rounds);
+
 /* The same work as two calls, so that batches on DIFFERENT pools overlap: submit queues the copies and both
  * kernels on the pool's stream and returns; wait blocks until they are done and hands the records over.  Reads
  * differ widely in cost (one that never maps takes ~6x one that does), so the last reads of a batch leave CTAs

@@ -1319,6 +1319,29 @@ int orc_map_reads_one_mapper(const orc_index *idx, const orc_model *m, const orc
     return 0;
 }
 
+/* One read mapped by a Mapper whose sources_added_ flags (reference src/mapper.cpp:88) start as flags_in
+ * (bit k&31 of word k>>5 = k-mer k; NULL = all clear) and are returned as they stand when map_read returns
+ * (flags_out, may be NULL).  orc_map_reads_one_mapper is this call chained over the reads; the CUDA path's
+ * ordered mode (unc_map_batch_ordered) is checked against both. */
+int orc_map_read_flags(const orc_index *idx, const orc_model *m, const orc_params *p, const float *raw, uint32_t n,
+                       const uint32_t *flags_in, uint32_t *flags_out, orc_paf_rec *out) {
+    mapper_t mp;
+    mapper_init(&mp, idx, m, p);
+    float *ev = (float *) malloc(((size_t) n + 1) * 4), *nb = (float *) malloc(((size_t) n + 1) * 4);
+    for (u32 k = 0; k < ORC_NKMER; k++) mp.sources_added[k] = flags_in ? (u8) ((flags_in[k >> 5] >> (k & 31u)) & 1u) : 0;
+    g_carry_flags = 1;
+    mapper_map_read(&mp, raw, n, out, ev, nb);
+    g_carry_flags = 0;
+    if (flags_out) {
+        memset(flags_out, 0, (ORC_NKMER / 32) * 4);
+        for (u32 k = 0; k < ORC_NKMER; k++) if (mp.sources_added[k]) flags_out[k >> 5] |= 1u << (k & 31u);
+    }
+    free(ev);
+    free(nb);
+    mapper_free(&mp);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ streaming path
  * reference src/mapper.cpp:281-431 (add_chunk / process_chunk / map_chunk), src/normalizer.cpp:46-75,
  * 114-152 (streaming Normalizer), src/event_profiler.hpp:46-104, src/realtime_pool.cpp:108-139,349-356

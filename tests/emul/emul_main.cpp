@@ -5,6 +5,7 @@
 #include "unc_k1.cuh"
 #include "unc_stream.cuh"
 #include "unc_stream_logic.hpp"
+#include "unc_ordered_logic.hpp"
 #include "unc_selfalign.cuh"
 #include "unc_selfalign_host.hpp"
 #include "../../include/unc_b200.h"
@@ -69,9 +70,10 @@ static void cta_entry(void *a) {
 }
 
 // events (optional, n_reads x stride) / normed (optional) are filled like unc_events_batch.
-int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads, uint32_t n_reads,
+static int emu_map_batch_impl(void *pidx, const unc_params *prm, const unc_read_desc *reads, uint32_t n_reads,
                   const void *samples, unc_paf_rec *out, uint32_t stride, float *events_out, float *normed_out,
-                  uint32_t *n_events_out, float *mel_out, int run_k2, uint32_t max_blocks, int n_warps) {
+                  uint32_t *n_events_out, float *mel_out, int run_k2, uint32_t max_blocks, int n_warps,
+                  const uint32_t *flags_in, uint32_t *flags_out) {
     EmuIndex *e = (EmuIndex *) pidx;
     std::string err;
     if (unc_check_params(*prm, err)) { fprintf(stderr, "%s\n", err.c_str()); return UNC_E_ARG; }
@@ -97,6 +99,7 @@ int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads,
     B.queue = &queue; B.out = (DevRec *) out; B.dbg = nullptr;
     B.seq_offsets = seq_off.data(); B.seq_lens = e->h.lens.data(); B.n_seqs = (u32) e->h.names.size();
     B.l_pac = (u64) e->h.l_pac;
+    B.flags_in = flags_in; B.flags_out = flags_out;
     u64 total_bytes = 0;
     for (u32 i = 0; i < n_reads; i++) {
         u64 e = (reads[i].offset + reads[i].n_samples) * (reads[i].dtype ? 2 : 4);
@@ -144,6 +147,30 @@ int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads,
     emu_run_cta(cta_entry, &a, 32 * (n_warps > 0 ? n_warps : 8));   // one persistent CTA maps the whole batch
     free(sh);
     return 0;
+}
+
+int emu_map_batch(void *pidx, const unc_params *prm, const unc_read_desc *reads, uint32_t n_reads,
+                  const void *samples, unc_paf_rec *out, uint32_t stride, float *events_out, float *normed_out,
+                  uint32_t *n_events_out, float *mel_out, int run_k2, uint32_t max_blocks, int n_warps) {
+    return emu_map_batch_impl(pidx, prm, reads, n_reads, samples, out, stride, events_out, normed_out, n_events_out, mel_out,
+                              run_k2, max_blocks, n_warps, nullptr, nullptr);
+}
+
+// unc_map_batch_ordered with the emulated kernels behind the product's own host logic (unc_ordered_logic.hpp)
+int emu_map_batch_ordered(void *pidx, const unc_params *prm, const unc_read_desc *reads, uint32_t n_reads,
+                          const void *samples, uint32_t *carry, unc_paf_rec *out, uint32_t *n_remapped, uint32_t *n_rounds,
+                          uint32_t max_blocks, int n_warps) {
+    std::vector<unc_read_desc> sub;
+    auto map_subset = [&](const uint32_t *ids, uint32_t m, const uint32_t *fi, uint32_t *fo, unc_paf_rec *recs) -> int {
+        sub.resize(m);
+        for (uint32_t j = 0; j < m; j++) sub[j] = reads[ids[j]];
+        int rc = emu_map_batch_impl(pidx, prm, sub.data(), m, samples, recs, 0, nullptr, nullptr, nullptr, nullptr, 1, max_blocks,
+                                    n_warps, fi, fo);
+        if (rc) return rc;
+        for (uint32_t j = 0; j < m; j++) if (recs[j].status != 0) return UNC_E_OVERFLOW;
+        return UNC_OK;
+    };
+    return unc_ordered_map(n_reads, carry, out, n_remapped, n_rounds, map_subset);
 }
 
 void emu_match_probs(void *pidx, float event, float *out) {

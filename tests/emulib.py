@@ -65,7 +65,7 @@ def build(extra_flags=(), tag=""):
     out = os.path.join(EMUL_DIR, "libunc_emul%s.so" % tag)
     deps = [src, os.path.join(EMUL_DIR, "warp_emul.hpp")] + \
            [os.path.join(ROOT, "uncalled_b200", "csrc", f) for f in
-            ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_logic.hpp", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp",
+            ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_logic.hpp", "unc_ordered_logic.hpp", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp",
              "unc_selfalign.cuh", "unc_selfalign_host.hpp")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
@@ -87,6 +87,9 @@ def _bind(L):
     L.emu_map_batch.argtypes = [C.c_void_p, C.POINTER(UncParams), C.POINTER(UncReadDesc), C.c_uint32, C.c_void_p,
                                 C.POINTER(UncPaf), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_uint32, C.c_int]
+    L.emu_map_batch_ordered.argtypes = [C.c_void_p, C.POINTER(UncParams), C.POINTER(UncReadDesc), C.c_uint32, C.c_void_p,
+                                        C.c_void_p, C.POINTER(UncPaf), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                        C.c_uint32, C.c_int]
     L.emu_match_probs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
     L.emu_self_align.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.emu_glibc_rand.argtypes = [C.c_uint, C.c_uint32, C.c_void_p]
@@ -136,6 +139,22 @@ class Emu:
         if rc != 0:
             raise RuntimeError("emu_map_batch rc=%d" % rc)
         return list(out), [ev[i, :ne[i]].copy() for i in range(n)], [nm[i, :ne[i]].copy() for i in range(n)], mel
+
+
+    def map_ordered(self, signals, carry=None, max_blocks=4096, n_warps=8):
+        """unc_map_batch_ordered under the emulator: (recs, carry after, reads mapped again, extra rounds)."""
+        lens = [len(s) for s in signals]
+        flat = np.ascontiguousarray(np.concatenate(signals).astype(np.float32))
+        n = len(lens)
+        d = make_descs(lens)
+        out = (UncPaf * n)()
+        carry = np.zeros(32, np.uint32) if carry is None else np.array(carry, dtype=np.uint32, copy=True)
+        nre, nro = C.c_uint32(), C.c_uint32()
+        rc = self.L.emu_map_batch_ordered(self.idx, C.byref(self.params), d, n, flat.ctypes.data, carry.ctypes.data, out,
+                                          C.byref(nre), C.byref(nro), max_blocks, n_warps)
+        if rc != 0:
+            raise RuntimeError("emu_map_batch_ordered rc=%d" % rc)
+        return list(out), carry, nre.value, nro.value
 
 
 def stream_reads(step, n_channels, signals, chunk_len, max_chunks=1000000):

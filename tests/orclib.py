@@ -211,6 +211,18 @@ class Oracle:
                                           offsets.ctypes.data_as(u64p), lens.ctypes.data_as(u32p), n, out)
         return list(out)
 
+    def map_read_flags(self, raw, flags_in=None):
+        """One read with explicit sources_added_ flags (32 words) before; returns (rec, flags after)."""
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        rec = OrcPaf()
+        fi = None if flags_in is None else np.ascontiguousarray(flags_in, np.uint32)
+        fo = np.zeros(32, np.uint32)
+        self.lib.orc_map_read_flags.argtypes = [C.c_void_p, C.POINTER(OrcModel), C.POINTER(OrcParams), f32p, C.c_uint32,
+                                                C.c_void_p, C.c_void_p, C.POINTER(OrcPaf)]
+        self.lib.orc_map_read_flags(self.idx, C.byref(self.model), C.byref(self.params), fp(raw), raw.size,
+                                    None if fi is None else fi.ctypes.data, fo.ctypes.data, C.byref(rec))
+        return rec, fo
+
     def kmer_ranges(self):
         st = np.zeros(1024, np.uint64)
         en = np.zeros(1024, np.uint64)

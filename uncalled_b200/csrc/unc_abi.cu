@@ -16,6 +16,7 @@
 #include "../../include/unc_b200.h"
 #include "unc_host_index.hpp"
 #include "unc_host_params.hpp"
+#include "unc_ordered_logic.hpp"
 
 static_assert(sizeof(DevRec) == sizeof(unc_paf_rec), "DevRec must mirror unc_paf_rec");
 static_assert(sizeof(DevReadDesc) == 32, "DevReadDesc layout");
@@ -174,6 +175,8 @@ struct unc_pool {
     cudaEvent_t ev_user[2] = {nullptr, nullptr};   // unc_pool_record / unc_pool_elapsed
     uint32_t pending_n = 0;      // reads of a submitted, not yet collected batch (unc_map_batch_submit / _wait)
     uint64_t pending_h2d = 0;
+    // ordered mode (unc_map_batch_ordered): per-read sources_added_ words in / out, allocated on first use
+    u32 *d_flags_in = nullptr, *d_flags_out = nullptr;
 };
 
 extern "C" {
@@ -450,6 +453,7 @@ void unc_pool_free(unc_pool *P) {
     cudaFree(P->d_events); cudaFree(P->d_normed);
     cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue); cudaFree(P->d_k1_flags);
     cudaFree(P->d_out); cudaFreeHost(P->h_out); cudaFree(P->d_dbg);
+    cudaFree(P->d_flags_in); cudaFree(P->d_flags_out);
     for (int i = 0; i < 2; i++) if (P->ev_user[i]) cudaEventDestroy(P->ev_user[i]);
     for (int i = 0; i < 6; i++) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
     if (P->stream) cudaStreamDestroy(P->stream);
@@ -523,7 +527,9 @@ static void launch_k1(unc_pool *P, const DevBatch &B, uint32_t n, cudaStream_t s
 }
 
 // first half of a batch: everything is put on the pool's stream (copies in, both kernels, copy out), nothing waits
-static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, bool on_device) {
+// h_flags_in (ordered mode only): n x 32 sources_added_ words the reads start from; their final words go to d_flags_out.
+static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, bool on_device,
+                         const uint32_t *h_flags_in = nullptr) {
     if (!P || !reads || !samples) return fail(UNC_E_ARG, "null argument");
     if (P->pending_n) return fail(UNC_E_ARG, "the pool still holds a submitted batch: call unc_map_batch_wait first");
     CUDA_TRY(cudaSetDevice(P->idx->device));
@@ -545,6 +551,16 @@ static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, co
     CUDA_TRY(cudaEventRecord(P->ev[1], s));
     // the pool's own staging buffer is padded, so whole 16-byte bulk copies may run past `span`
     DevBatch B = make_batch(P, d_samples, on_device ? span : ((span + 15) & ~(uint64_t) 15), n, false);
+    if (h_flags_in) {
+        if (!P->d_flags_in) {
+            CUDA_TRY(cudaMalloc(&P->d_flags_in, (size_t) P->max_reads * 128));
+            CUDA_TRY(cudaMalloc(&P->d_flags_out, (size_t) P->max_reads * 128));
+        }
+        CUDA_TRY(cudaMemcpyAsync(P->d_flags_in, h_flags_in, (size_t) n * 128, cudaMemcpyHostToDevice, s));
+        B.flags_in = P->d_flags_in;
+        B.flags_out = P->d_flags_out;
+        h2d += (uint64_t) n * 128;
+    }
     launch_k1(P, B, n, s);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[2], s));
@@ -627,6 +643,37 @@ int unc_pool_elapsed(unc_pool *from, int from_slot, unc_pool *to, int to_slot, f
 
 int unc_map_batch_device(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *d_samples, unc_paf_rec *out) {
     return run_batch(P, reads, n, d_samples, true, out);
+}
+
+int unc_map_batch_ordered(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, int samples_on_device,
+                          uint32_t carry[32], unc_paf_rec *out, uint32_t *n_remapped, uint32_t *n_rounds) {
+    if (!P || !reads || !samples || !carry || !out) return fail(UNC_E_ARG, "null argument");
+    if (n == 0 || n > P->max_reads) return fail(UNC_E_ARG, "n_reads outside 1..max_reads");
+    bool first = true;
+    unc_timing sum;
+    memset(&sum, 0, sizeof(sum));
+    std::vector<unc_read_desc> sub;
+    auto map_subset = [&](const uint32_t *ids, uint32_t m, const uint32_t *fi, uint32_t *fo, unc_paf_rec *recs) -> int {
+        sub.resize(m);
+        for (uint32_t j = 0; j < m; j++) sub[j] = reads[ids[j]];
+        // after round 0 the samples are on the device (the pool's staging buffer, or where the caller put them)
+        const void *src = first ? samples : (samples_on_device ? samples : (const void *) P->d_samples);
+        int rc = batch_enqueue(P, sub.data(), m, src, first ? samples_on_device != 0 : true, fi);
+        first = false;
+        if (rc) return rc;
+        rc = batch_finish(P, recs);
+        if (rc != UNC_OK && rc != UNC_E_OVERFLOW) return rc;
+        CUDA_TRY(cudaMemcpy(fo, P->d_flags_out, (size_t) m * 128, cudaMemcpyDeviceToHost));
+        const unc_timing &t = P->last;
+        sum.h2d_ms += t.h2d_ms; sum.k1_ms += t.k1_ms; sum.k1_events_ms += t.k1_events_ms; sum.k2_ms += t.k2_ms;
+        sum.d2h_ms += t.d2h_ms; sum.total_ms += t.total_ms; sum.kernel_launches += t.kernel_launches;
+        sum.h2d_bytes += t.h2d_bytes; sum.d2h_bytes += t.d2h_bytes + (uint64_t) m * 128;
+        return rc;
+    };
+    int rc = unc_ordered_map(n, carry, out, n_remapped, n_rounds, map_subset);
+    P->last = sum;
+    if (rc == UNC_E_OVERFLOW) return fail(rc, "a read overflowed its seed-cluster workspace (see unc_paf_rec.status)");
+    return rc;
 }
 
 int unc_events_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, uint32_t stride,

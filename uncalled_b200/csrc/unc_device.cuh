@@ -97,6 +97,10 @@ struct DevBatch {
     const u32 *seq_lens;
     u32 n_seqs;
     u64 l_pac;
+    // ordered mode (unc_map_batch_ordered; both optional): read r starts with the sources_added_ words
+    // flags_in[32r..32r+32) instead of a clear set and leaves its final ones in flags_out[32r..32r+32)
+    const u32 *flags_in = nullptr;
+    u32 *flags_out = nullptr;
 };
 
 struct DevWork {   // per-slot (per-CTA) workspaces; slot s uses [s*stride, (s+1)*stride)
@@ -815,6 +819,7 @@ struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
     K2Tables tb;
     float probs[UNC_NKMER];
     u32 flags[32];         // sources_added_ bits (reference src/mapper.cpp:88), kmer k -> word k>>5
+    u32 flags_prev[32];    // the flags as the previous event left them (restored when the event in flight is discarded)
 #ifdef K2_OCC_STAGE
     uint4 occ_stage[K2_MAXSEG * 32 * 5];   // per worker warp: 32 lanes x (64-byte Occ block + 16 B pad: conflict-free LDS.128)
 #endif
@@ -1108,6 +1113,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         PT_MARK(7)
 
         // ---- A. pore-model probabilities (reference src/mapper.cpp:443-445)
+        if (wt < 32u) sh->flags_prev[wt] = sh->flags[wt];               // what the read ends with if this event is discarded
         for (u32 k = wt; k < UNC_NKMER; k += nwt)
             sh->probs[k] = unc_match_prob(event, d_ldg(ix.lv_mean + k), d_ldg(ix.lv_var2 + k), d_ldg(ix.lognorm + k));
         c_sync_sub(1, (int) nwt);
@@ -1971,7 +1977,10 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         nn = sh->bc[1];
         pend_sources = nn - nc;
         const u32 v = event_i > n_first ? *(volatile u32 *) &sh->verdict[(event_i - 1u) & 1u] : 0u;
-        if (v) break;                                                 // event_i's work is discarded
+        if (v) {                                                      // event_i's work is discarded: the Mapper returned
+            if (wt < 32u) sh->flags[wt] = sh->flags_prev[wt];         // after event_i - 1 (reference src/mapper.cpp:633-651)
+            break;
+        }
         n_children += pend_children; n_sources += pend_sources;
         my_blocks += pend_blocks; my_steps += pend_steps;
         pend_children = pend_sources = pend_blocks = pend_steps = 0;
@@ -2013,7 +2022,7 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
         if (ms->started) n_first = ms->event_i;
         if (tid < 32) sh->flags[tid] = ms->flags[tid];
     } else {
-        if (tid < 32) sh->flags[tid] = 0;
+        if (tid < 32) sh->flags[tid] = B.flags_in ? B.flags_in[(size_t) r * 32 + tid] : 0u;
     }
     const u32 n_limit = n_first + n_ev < p.max_events ? n_first + n_ev : (n_first < p.max_events ? p.max_events : n_first);
     if (tid == 0) {
@@ -2064,6 +2073,7 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
 #endif
     c_sync();
     if (STREAM && tid < 32) B.mstate[B.chan[r]].flags[tid] = sh->flags[tid];
+    if (!STREAM && B.flags_out && tid < 32) B.flags_out[(size_t) r * 32 + tid] = sh->flags[tid];
 }
 
 UNC_DEV DevWork unc_work_slot(const DevWork &W0, const DevWorkStrides &S, size_t slot) {

@@ -52,7 +52,7 @@ class Fast5File:
         self.close()
 
     def close(self):
-        if self._h is not None:
+        if getattr(self, "_h", None) is not None:
             self._L.unc_fast5_close(self._h)
             self._h = None
 

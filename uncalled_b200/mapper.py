@@ -119,6 +119,26 @@ class BatchMapper:
             N.check(rc)
         return out
 
+    def map_ordered(self, samples, descs, carry=None, on_device=False):
+        """The batch as ONE long-lived Mapper maps it, read after read (`uncalled map -t 1`; unc_map_batch_ordered).
+        carry: 32 uint32 sources_added_ words the previous batch ended with (None = a new Mapper); returns
+        (records, carry after the last read, reads mapped again, extra rounds)."""
+        if on_device:
+            ptr = C.c_void_p(int(samples))
+        else:
+            samples = np.ascontiguousarray(samples)
+            ptr = C.c_void_p(samples.ctypes.data)
+        carry = np.zeros(32, np.uint32) if carry is None else np.array(carry, dtype=np.uint32, copy=True)
+        assert carry.shape == (32,)
+        out = np.zeros(len(descs), dtype=N.PAF_DTYPE)
+        nre, nro = C.c_uint32(), C.c_uint32()
+        rc = self.L.unc_map_batch_ordered(self.h, descs.ctypes.data, len(descs), ptr, 1 if on_device else 0,
+                                          carry.ctypes.data, out.ctypes.data, C.byref(nre), C.byref(nro))
+        self._last_rc = rc
+        if rc != 0 and rc != -7:
+            N.check(rc)
+        return out, carry, int(nre.value), int(nro.value)
+
     def submit(self, samples, descs, on_device=False):
         """First half of map()/map_device(): queue the batch on this pool's stream and return.  `samples`: host numpy
         array, or an integer device pointer with on_device=True; keep it (and `descs`) alive until wait()."""

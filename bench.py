@@ -220,6 +220,9 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="additionally time the steps with two pools used alternately (unc_map_batch_submit / _wait): the "
                          "next batch's CTAs fill the SMs that the previous batch's tail leaves idle; reported under 'overlap'")
+    ap.add_argument("--ordered", action="store_true",
+                    help="additionally time unc_map_batch_ordered (`uncalled map -t 1` semantics: one long-lived Mapper, reads in "
+                         "order, resolved by re-mapping the reads whose predecessor left flags set); reported under 'ordered'")
     ap.add_argument("--workload", default="batch", choices=["batch", "stream"],
                     help="batch: configs[1] (the headline); stream: chunk streaming over 512 channels (configs[4]-like)")
     ap.add_argument("--reads-per-channel", type=int, default=2)
@@ -335,6 +338,20 @@ def main():
                            "the last step's tail is not hidden"}
         bm2.close()
 
+    ordered = None
+    if args.ordered:
+        oh = {}
+
+        def step_ordered():
+            oh["r"] = bm.map_ordered(dev.data_ptr(), descs, on_device=True)
+        timed(step_ordered, 1)
+        od_ms, od_wall, _ = timed(step_ordered, args.steps)
+        recs_o, _, n_re, n_ro = oh["r"]
+        ordered = {"value": world * n_reads / (od_ms / args.steps / 1e3), "unit": "reads/s", "ms_per_step": od_ms / args.steps,
+                   "wall_ms_per_step": od_wall / args.steps, "reads_mapped_again": n_re, "extra_rounds": n_ro,
+                   "records_differing_from_plain_batch": int((recs_o != out_dev).sum()),
+                   "note": "device-resident samples; sum of the CUDA-event times of all rounds, max over ranks"}
+
     ms_per_step = dev_ms / args.steps
     value = world * n_reads / (ms_per_step / 1e3)
     e2e_value = world * n_reads / (e2e_ms / args.steps / 1e3)
@@ -375,6 +392,7 @@ def main():
             "gpu_launches": int(sum(t["kernel_launches"] for t in tms)),
             "wall_ms_per_step": wall_ms / args.steps,
             "overlap": overlap,
+            "ordered": ordered,
             "clocks": clocks,
             "roofline": {"kernel": "k2_map", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,

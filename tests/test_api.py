@@ -226,3 +226,45 @@ def test_uncalled_map_from_fast5_files_on_the_emulated_device(tmp_path):
     with pytest.raises(RuntimeError):
         pool.update()
     pool.stop()
+
+
+def test_ordered_conf_keeps_input_order_and_threads_the_carry():
+    """conf.ordered: batches are not re-sorted, go through map_ordered one after the other, and each batch starts
+    from the flags the previous one ended with (the kernels behind it: tests/test_ordered_emul.py)."""
+    import uncalled_b200._native as N
+    from uncalled_b200.api import Conf, MapPool
+
+    class _Idx:
+        seqs = [("chr", 1000)]
+
+    class _Stub:
+        def __init__(self):
+            self.calls = []
+
+        def map_ordered(self, flat, descs, carry=None, on_device=False):
+            self.calls.append(([int(x) for x in descs["n_samples"]], None if carry is None else carry.copy()))
+            out = np.zeros(len(descs), dtype=N.PAF_DTYPE)
+            nxt = np.full(32, len(self.calls), np.uint32)
+            return out, nxt, 0, 0
+
+        def map(self, flat, descs):
+            raise AssertionError("ordered mode must not use the plain batch call")
+
+    conf = Conf()
+    conf.ordered, conf.batch_reads = 1, 3
+    be = _Stub()
+    pool = MapPool(conf, backend=be, index=_Idx)
+    lens = [50, 400, 30, 200, 10]
+    for i, n in enumerate(lens):
+        pool.add_read("r%d" % i, np.zeros(n, np.float32))
+    out = []
+    while pool.running():
+        out += pool.update()
+    pool.stop()
+    assert [p.fields()[0] for p in out] == ["r%d" % i for i in range(5)]
+    assert [c[0] for c in be.calls] == [[50, 400, 30], [200, 10]]
+    assert be.calls[0][1] is None and np.array_equal(be.calls[1][1], np.full(32, 1, np.uint32))
+    from uncalled_b200 import cli
+    _, c2, _ = cli.load_conf(["map", "--ordered", "idx", "reads.fast5"])
+    _, c3, _ = cli.load_conf(["map", "idx", "reads.fast5"])
+    assert c2.ordered == 1 and c3.ordered == 0

@@ -214,3 +214,51 @@ def test_multi_contig_index_built_and_mapped_on_the_gpu(U, tmp_path):
         assert orclib.paf_tuple(O.map_read(s)) == U.paf_key(out[i]), i
     assert len(set(int(r["rid"]) for r in out if r["mapped"])) == 3
     bm.close()
+
+
+def test_ordered_mode_equals_one_long_lived_mapper(U):
+    """unc_map_batch_ordered (`uncalled map -t 1`): the whole batch in one launch plus re-mapping of the reads whose
+    predecessor left flags set == the oracle's ONE Mapper mapping the reads one after the other (pinned to the
+    reference's own long-lived Mapper by tests/test_oracle_pinned.py).  A small path buffer makes most reads depend
+    on their predecessor; the 4.7 Mb case is the bench workload's shape."""
+    import orclib
+    import synth
+    import synthdata
+    cnt = ("n_children", "n_sources", "n_seeds", "n_clusters")
+    for name, max_paths, n, L, seed, fr in (("g200k", 300, 96, 2000, 21, 0.4), ("g4m7", 10000, 64, 4000, 7, 0.15)):
+        prefix, g = synthdata.get_index(name)
+        idx, O = U.Index(prefix, device=0), orclib.Oracle(prefix)
+        p = U._native.default_params()
+        p.max_paths = O.params.max_paths = max_paths
+        sig, _ = synth.reads(g, n, L, seed=seed, frac_random=fr)
+        flat = np.ascontiguousarray(sig.reshape(-1), np.float32)
+        lens = np.full(n, L, np.uint32)
+        offs = (np.arange(n, dtype=np.uint64) * L).astype(np.uint64)
+        want = O.map_reads_one_mapper(flat, offs, lens)
+        d = U.make_descs([L] * n)
+        bm = U.BatchMapper(idx, params=p, max_reads=n, max_samples=n * L)
+        recs, carry, n_remapped, n_rounds = bm.map_ordered(flat, d)
+        for i in range(n):
+            assert U.paf_key(recs[i]) == orclib.paf_tuple(want[i]), (name, i)
+            assert tuple(int(recs[i][k]) for k in cnt) == tuple(int(getattr(want[i], k)) for k in cnt), (name, i)
+        assert n_remapped >= 1 and 1 <= n_rounds <= n, (name, n_remapped, n_rounds)
+        t = bm.timing()
+        assert t["kernel_launches"] == 4 * (1 + n_rounds) and t["k2_ms"] > 0
+        # the flags after the last read, and two batches linked by them
+        prev = np.zeros(32, np.uint32)
+        for i in range(n):
+            _, prev = O.map_read_flags(sig[i], prev)
+        assert np.array_equal(carry, prev), name
+        k = n // 3
+        a, c1, _, _ = bm.map_ordered(flat[:k * L], d[:k])
+        b, c2, _, _ = bm.map_ordered(flat[k * L:], U.make_descs([L] * (n - k)), carry=c1)
+        assert np.array_equal(np.concatenate([a, b]), recs) and np.array_equal(c2, carry), name
+        # plain batch mapping is unaffected: every read from a new Mapper
+        plain = bm.map(flat, d)
+        fresh = O.map_batch(flat, offs, lens, threads=8)
+        assert [U.paf_key(r) for r in plain] == [orclib.paf_tuple(r) for r in fresh], name
+        if name == "g200k":
+            assert any(U.paf_key(plain[i]) != U.paf_key(recs[i]) or int(plain[i]["n_sources"]) != int(recs[i]["n_sources"])
+                       for i in range(n))
+        bm.close()
+        idx.close()

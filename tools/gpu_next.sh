@@ -16,3 +16,5 @@ timeout 600 python bench.py --workload stream --steps 2 --warmup 1 > gpurun_out/
 # batch tail: two pools used alternately (expected from a list-scheduling simulation of the oracle's per-read costs:
 # makespan / ideal = 1.07 at 2 CTAs/SM, 1.11 at 3, 1.15 at 4 for 10 000-read batches)
 timeout 600 python bench.py --overlap --no-cpu-baseline --steps 4 --warmup 3 > gpurun_out/bench_overlap.json 2> gpurun_out/bench_overlap.err; echo "overlap bench rc=$?"; cut -c1-900 gpurun_out/bench_overlap.json
+# ordered mode (`uncalled map -t 1` semantics, unc_map_batch_ordered): cost of the re-mapping rounds on the bench workload
+timeout 600 python bench.py --ordered --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/bench_ordered.json 2> gpurun_out/bench_ordered.err; echo "ordered bench rc=$?"; python -c "import json;print(json.load(open('gpurun_out/bench_ordered.json'))['ordered'])"

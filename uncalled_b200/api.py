@@ -9,6 +9,8 @@ constructing a MapPool without a usable CUDA device raises UncError.
 Differences a caller can observe (documented, not hidden):
   * `MapPool(conf)` maps batches on the GPU instead of one read per CPU thread; `conf.threads`
     is accepted and ignored by the mapper (reference src/map_pool.cpp:31).
+    `conf.ordered = 1` (CLI `--ordered`) reproduces what the reference prints with ONE thread for a multi-read
+    input: reads mapped in input order by one long-lived Mapper (divergence 2).
   * fast5 files are read by the library's own HDF5 subset reader (uncalled_b200/csrc/unc_fast5.cpp; the
     reference vendors libhdf5).  VBZ-compressed files are rejected with a clear error (the reference's
     vendored libhdf5 cannot read them either without an external plugin).  Reads can also be queued as
@@ -55,6 +57,9 @@ class Conf:
         "max_active_reads": (512, "Maximum number of reads being mapped at once"),
         "device": (0, "CUDA device of this process (one process per GPU)"),
         "batch_reads": (4096, "Reads per GPU batch"),
+        "ordered": (0, "1: map the reads in input order as ONE long-lived Mapper does, i.e. exactly what the reference "
+                       "prints with `-t 1` (a read inherits the source flags its predecessor left set); "
+                       "0: every read is mapped by a new Mapper (batch order free, fastest)"),
     }
 
     def __init__(self):
@@ -197,6 +202,7 @@ class MapPool:
         self._queue = []
         self._mappers, self._caps, self._inflight = [None, None], [(0, 0), (0, 0)], None   # two pools: batches overlap
         self._n_added, self._stopped = 0, False
+        self._carry = None                                    # conf.ordered: sources_added_ words after the last read mapped
         self._files, self._open, self._next = [], None, 0
         self._future, self._executor = None, None          # fast5 decoding of the NEXT batch overlaps the mapping
         if conf.fast5_list:                                   # Fast5Reader::load_fast5_list (src/fast5_reader.cpp:77-92)
@@ -306,7 +312,9 @@ class MapPool:
         """Put a batch on the GPU (unc_map_batch_submit on the pool that is not in flight) and return at once.
         The CTAs take reads from the batch in order, so the longest signals go first: the batch then ends on short
         reads instead of leaving most SMs idle behind one long read (results are matched by read, not by position)."""
-        batch.sort(key=lambda r: -len(r.signal))
+        ordered = bool(self.conf.ordered)
+        if not ordered:
+            batch.sort(key=lambda r: -len(r.signal))
         lens = [len(r.signal) for r in batch]
         total = int(sum(lens))
         dtype = batch[0].dtype
@@ -317,7 +325,11 @@ class MapPool:
         slot = 1 - self._inflight["slot"] if self._inflight is not None else 0
         m = self._mapper_for(slot, len(batch), total)
         job = {"slot": slot, "batch": batch, "flat": flat, "descs": d, "t0": time.time(), "mapper": m, "recs": None}
-        if hasattr(m, "submit"):
+        if ordered:
+            # one Mapper, read after read (reference src/map_pool.cpp:104-158 with one thread): the chain through the
+            # flags is resolved inside unc_map_batch_ordered; batches follow each other, linked by the carry
+            job["recs"], self._carry, _, _ = m.map_ordered(flat, d, carry=self._carry)
+        elif hasattr(m, "submit"):
             m.submit(flat, d)
         else:                                      # a test backend without the two-call form
             job["recs"] = m.map(flat, d)

@@ -49,6 +49,7 @@ def get_parser(conf):
     p.add_argument("--chunk-time", type=float, default=1, required=False, help="Length of chunks in seconds")
     p.add_argument("--device", type=int, default=conf.device, help="CUDA device")
     p.add_argument("--batch-reads", type=int, default=conf.batch_reads, help="Reads per GPU batch")
+    p.add_argument("--ordered", action="store_const", const=1, default=conf.ordered, help=type(conf).ordered.__doc__)
     return parser
 
 

@@ -73,7 +73,7 @@ static void cta_entry(void *a) {
 static int emu_map_batch_impl(void *pidx, const unc_params *prm, const unc_read_desc *reads, uint32_t n_reads,
                   const void *samples, unc_paf_rec *out, uint32_t stride, float *events_out, float *normed_out,
                   uint32_t *n_events_out, float *mel_out, int run_k2, uint32_t max_blocks, int n_warps,
-                  const uint32_t *flags_in, uint32_t *flags_out) {
+                  const uint32_t *flags_in, uint32_t *flags_out, uint32_t *cand_out = nullptr) {
     EmuIndex *e = (EmuIndex *) pidx;
     std::string err;
     if (unc_check_params(*prm, err)) { fprintf(stderr, "%s\n", err.c_str()); return UNC_E_ARG; }
@@ -128,6 +128,12 @@ static int emu_map_batch_impl(void *pidx, const unc_params *prm, const unc_read_
     if (normed_out) memcpy(normed_out, normed.data(), (size_t) n_reads * stride * 4);
     if (n_events_out) memcpy(n_events_out, n_events.data(), n_reads * 4);
     if (mel_out) memcpy(mel_out, mel.data(), n_reads * 4);
+    if (cand_out) {                                  // k_event0_cands of unc_abi.cu
+        memset(cand_out, 0, (size_t) n_reads * 128);
+        for (u32 r = 0; r < n_reads; r++)
+            for (u32 k = 0; k < UNC_NKMER; k++)
+                if (unc_event0_cand(e->ix, dp, B, r, k)) cand_out[(size_t) r * 32 + (k >> 5)] |= 1u << (k & 31u);
+    }
     if (!run_k2) return 0;
 
     u32 maxp = dp.max_paths;
@@ -161,16 +167,16 @@ int emu_map_batch_ordered(void *pidx, const unc_params *prm, const unc_read_desc
                           const void *samples, uint32_t *carry, unc_paf_rec *out, uint32_t *n_remapped, uint32_t *n_rounds,
                           uint32_t max_blocks, int n_warps) {
     std::vector<unc_read_desc> sub;
-    auto map_subset = [&](const uint32_t *ids, uint32_t m, const uint32_t *fi, uint32_t *fo, unc_paf_rec *recs) -> int {
+    auto map_subset = [&](const uint32_t *ids, uint32_t m, const uint32_t *fi, uint32_t *fo, unc_paf_rec *recs, uint32_t *cand) -> int {
         sub.resize(m);
         for (uint32_t j = 0; j < m; j++) sub[j] = reads[ids[j]];
         int rc = emu_map_batch_impl(pidx, prm, sub.data(), m, samples, recs, 0, nullptr, nullptr, nullptr, nullptr, 1, max_blocks,
-                                    n_warps, fi, fo);
+                                    n_warps, fi, fo, cand);
         if (rc) return rc;
         for (uint32_t j = 0; j < m; j++) if (recs[j].status != 0) return UNC_E_OVERFLOW;
         return UNC_OK;
     };
-    return unc_ordered_map(n_reads, carry, out, n_remapped, n_rounds, map_subset);
+    return unc_ordered_map(n_reads, prm->max_paths, carry, out, n_remapped, n_rounds, map_subset);
 }
 
 void emu_match_probs(void *pidx, float event, float *out) {

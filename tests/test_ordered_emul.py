@@ -76,3 +76,23 @@ def test_carry_links_consecutive_batches(setup):
     for s in sigs:
         _, prev = O.map_read_flags(s, prev)
     assert np.array_equal(carry2, prev)
+
+
+def test_first_event_fills_the_buffer(setup):
+    """max_paths below the number of first-event candidates: the fresh-source walk stops early, flags behind the cut
+    survive the first event, and the candidate-mask shortcut must not be taken."""
+    E, O, sigs = setup
+    sigs = [s[:1200] for s in sigs[:4]]
+    old = E.params.max_paths
+    E.params.max_paths = O.params.max_paths = 40
+    try:
+        want = _chain(O, sigs)
+        recs, carry, n_remapped, _ = E.map_ordered(sigs)
+        for i in range(len(sigs)):
+            assert (emulib.paf_tuple(recs[i]), _counts(recs[i])) == (orclib.paf_tuple(want[i]), _counts(want[i])), i
+        prev = np.zeros(32, np.uint32)
+        for s in sigs:
+            _, prev = O.map_read_flags(s, prev)
+        assert np.array_equal(carry, prev) and prev.any() and n_remapped >= 1
+    finally:
+        E.params.max_paths = O.params.max_paths = old

@@ -95,6 +95,14 @@ k2_map(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, si
     unc_k2_cta_main(ix, p, B, W, sh);
 }
 
+// ordered mode: per read the 1024-bit mask of the k-mers that pass the first event's fresh-source tests
+// (block = read, thread = k-mer; word k>>5, bit k&31 = the ballot of warp k>>5)
+__global__ void __launch_bounds__(UNC_NKMER) k_event0_cands(DevIndex ix, DevParams p, DevBatch B, u32 *cand) {
+    const u32 r = blockIdx.x, k = threadIdx.x;
+    const u32 m = __ballot_sync(0xFFFFFFFFu, unc_event0_cand(ix, p, B, r, k));
+    if ((k & 31u) == 0) cand[(size_t) r * 32 + (k >> 5)] = m;
+}
+
 __global__ void k_match_probs(DevIndex ix, float event, float *out) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < UNC_NKMER) out[k] = unc_match_prob(event, ix.lv_mean[k], ix.lv_var2[k], ix.lognorm[k]);
@@ -176,7 +184,8 @@ struct unc_pool {
     uint32_t pending_n = 0;      // reads of a submitted, not yet collected batch (unc_map_batch_submit / _wait)
     uint64_t pending_h2d = 0;
     // ordered mode (unc_map_batch_ordered): per-read sources_added_ words in / out, allocated on first use
-    u32 *d_flags_in = nullptr, *d_flags_out = nullptr;
+    u32 *d_flags_in = nullptr, *d_flags_out = nullptr, *d_cand = nullptr;
+    bool want_cand = false;      // the next batch_enqueue also launches k_event0_cands
 };
 
 extern "C" {
@@ -453,7 +462,7 @@ void unc_pool_free(unc_pool *P) {
     cudaFree(P->d_events); cudaFree(P->d_normed);
     cudaFree(P->d_scale); cudaFree(P->d_shift); cudaFree(P->d_mel); cudaFree(P->d_n_events); cudaFree(P->d_queue); cudaFree(P->d_k1_flags);
     cudaFree(P->d_out); cudaFreeHost(P->h_out); cudaFree(P->d_dbg);
-    cudaFree(P->d_flags_in); cudaFree(P->d_flags_out);
+    cudaFree(P->d_flags_in); cudaFree(P->d_flags_out); cudaFree(P->d_cand);
     for (int i = 0; i < 2; i++) if (P->ev_user[i]) cudaEventDestroy(P->ev_user[i]);
     for (int i = 0; i < 6; i++) if (P->ev[i]) cudaEventDestroy(P->ev[i]);
     if (P->stream) cudaStreamDestroy(P->stream);
@@ -555,6 +564,7 @@ static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, co
         if (!P->d_flags_in) {
             CUDA_TRY(cudaMalloc(&P->d_flags_in, (size_t) P->max_reads * 128));
             CUDA_TRY(cudaMalloc(&P->d_flags_out, (size_t) P->max_reads * 128));
+            CUDA_TRY(cudaMalloc(&P->d_cand, (size_t) P->max_reads * 128));
         }
         CUDA_TRY(cudaMemcpyAsync(P->d_flags_in, h_flags_in, (size_t) n * 128, cudaMemcpyHostToDevice, s));
         B.flags_in = P->d_flags_in;
@@ -562,6 +572,7 @@ static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, co
         h2d += (uint64_t) n * 128;
     }
     launch_k1(P, B, n, s);
+    if (h_flags_in && P->want_cand) k_event0_cands<<<n, UNC_NKMER, 0, s>>>(P->idx->ix, P->dp, B, P->d_cand);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[2], s));
     uint32_t grid = std::min<uint32_t>(P->grid, n);
@@ -653,24 +664,27 @@ int unc_map_batch_ordered(unc_pool *P, const unc_read_desc *reads, uint32_t n, c
     unc_timing sum;
     memset(&sum, 0, sizeof(sum));
     std::vector<unc_read_desc> sub;
-    auto map_subset = [&](const uint32_t *ids, uint32_t m, const uint32_t *fi, uint32_t *fo, unc_paf_rec *recs) -> int {
+    auto map_subset = [&](const uint32_t *ids, uint32_t m, const uint32_t *fi, uint32_t *fo, unc_paf_rec *recs, uint32_t *cand) -> int {
         sub.resize(m);
         for (uint32_t j = 0; j < m; j++) sub[j] = reads[ids[j]];
         // after round 0 the samples are on the device (the pool's staging buffer, or where the caller put them)
         const void *src = first ? samples : (samples_on_device ? samples : (const void *) P->d_samples);
+        P->want_cand = cand != nullptr;
         int rc = batch_enqueue(P, sub.data(), m, src, first ? samples_on_device != 0 : true, fi);
+        P->want_cand = false;
         first = false;
         if (rc) return rc;
         rc = batch_finish(P, recs);
         if (rc != UNC_OK && rc != UNC_E_OVERFLOW) return rc;
         CUDA_TRY(cudaMemcpy(fo, P->d_flags_out, (size_t) m * 128, cudaMemcpyDeviceToHost));
+        if (cand) CUDA_TRY(cudaMemcpy(cand, P->d_cand, (size_t) m * 128, cudaMemcpyDeviceToHost));
         const unc_timing &t = P->last;
         sum.h2d_ms += t.h2d_ms; sum.k1_ms += t.k1_ms; sum.k1_events_ms += t.k1_events_ms; sum.k2_ms += t.k2_ms;
-        sum.d2h_ms += t.d2h_ms; sum.total_ms += t.total_ms; sum.kernel_launches += t.kernel_launches;
-        sum.h2d_bytes += t.h2d_bytes; sum.d2h_bytes += t.d2h_bytes + (uint64_t) m * 128;
+        sum.d2h_ms += t.d2h_ms; sum.total_ms += t.total_ms; sum.kernel_launches += t.kernel_launches + (cand ? 1u : 0u);
+        sum.h2d_bytes += t.h2d_bytes; sum.d2h_bytes += t.d2h_bytes + (uint64_t) m * (cand ? 256 : 128);
         return rc;
     };
-    int rc = unc_ordered_map(n, carry, out, n_remapped, n_rounds, map_subset);
+    int rc = unc_ordered_map(n, P->prm.max_paths, carry, out, n_remapped, n_rounds, map_subset);
     P->last = sum;
     if (rc == UNC_E_OVERFLOW) return fail(rc, "a read overflowed its seed-cluster workspace (see unc_paf_rec.status)");
     return rc;

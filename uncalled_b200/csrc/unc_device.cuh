@@ -2076,6 +2076,18 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
     if (!STREAM && B.flags_out && tid < 32) B.flags_out[(size_t) r * 32 + tid] = sh->flags[tid];
 }
 
+// Ordered mode (unc_ordered_logic.hpp): would k-mer k get a fresh source at read r's FIRST event if its
+// sources_added_ flag were clear?  This is phase E's `add` test for event 0 (reference src/mapper.cpp:611-614) on
+// the event value the event loop computes.  A read's first event has no children, so the flags it starts from act
+// only through these k-mers: two initial flag sets that agree on them give the same mapping.
+UNC_DEV bool unc_event0_cand(const DevIndex &ix, const DevParams &p, const DevBatch &B, u32 r, u32 k) {
+    if (B.n_events[r] == 0 || p.max_events == 0) return false;
+    const float event = f_add(f_mul(B.scale[r], B.events[(size_t) r * B.ev_stride]), B.shift[r]);
+    const uint2 kr = ix.kmer_range[k];
+    return unc_match_prob(event, d_ldg(ix.lv_mean + k), d_ldg(ix.lv_var2 + k), d_ldg(ix.lognorm + k)) >= ix.thresh[0] &&
+           kr.x <= kr.y;
+}
+
 UNC_DEV DevWork unc_work_slot(const DevWork &W0, const DevWorkStrides &S, size_t slot) {
     DevWork W;
     W.paths = W0.paths + slot * S.paths;

@@ -8,8 +8,15 @@
 //             mapped again from exactly those flags.
 // Read 0 is right after round 0, and once read i-1 is right read i is mapped from the right flags in the next
 // round, so the first inconsistent index moves forward every round and the loop ends with every read mapped from
-// its predecessor's true final flags.  In practice (4.7 Mb index, 4000-sample reads) 4 % of the reads end with a
-// flag set and chains are one or two reads long: round 1 re-maps those 4 %, round 2 a handful, round 3 none.
+// flags equivalent to its predecessor's true final ones.
+// Which reads have to be mapped again: a read's first event has no children, so its initial flags act only in that
+// event's fresh-source walk (reference src/mapper.cpp:605-624), which skips flagged k-mers and clears every flag it
+// visits.  With cand = the k-mers that pass the walk's other tests (round 0 also returns this 1024-bit mask per read,
+// unc_event0_cand) and fewer candidates than max_paths (the walk then visits all k-mers), two initial flag sets
+// that agree on cand give the same sources, the same cleared flags and hence the same mapping and final flags.  So a
+// read is re-mapped only if its predecessor's final flags differ from the ones it was mapped from ON A CANDIDATE (or
+// the walk could stop early: cand >= max_paths).  In practice (4.7 Mb index, 4000-sample reads) 4 % of the reads end
+// with a flag set, and a fraction of a percent of the reads see one of those flags on a candidate.
 // A read without events never touches the flags (Mapper::map_read does not enter map_next): it passes its
 // predecessor's flags on and is never re-mapped.
 //
@@ -22,18 +29,19 @@
 
 #include "../../include/unc_b200.h"
 
-// map_subset(ids, n_ids, flags_in /* n_ids x 32 */, flags_out /* n_ids x 32 */, recs /* n_ids */) -> UNC_OK or an error.
+// map_subset(ids, n_ids, flags_in /* n_ids x 32 */, flags_out /* n_ids x 32 */, recs /* n_ids */,
+//            cand /* n_ids x 32, or NULL when not wanted */) -> UNC_OK or an error.
 // A read's record status != 0 (workspace overflow) is reported by the caller; its flags are still passed on.
 template <class MapSubset>
-int unc_ordered_map(uint32_t n, uint32_t carry[32], unc_paf_rec *out, uint32_t *n_remapped, uint32_t *n_rounds,
-                    MapSubset map_subset) {
+int unc_ordered_map(uint32_t n, uint32_t max_paths, uint32_t carry[32], unc_paf_rec *out, uint32_t *n_remapped,
+                    uint32_t *n_rounds, MapSubset map_subset) {
     if (n_remapped) *n_remapped = 0;
     if (n_rounds) *n_rounds = 0;
     if (n == 0) return UNC_OK;
-    std::vector<uint32_t> fin((size_t) n * 32, 0u), fout((size_t) n * 32, 0u), ids(n);
+    std::vector<uint32_t> fin((size_t) n * 32, 0u), fout((size_t) n * 32, 0u), cand((size_t) n * 32, 0u), ids(n);
     memcpy(fin.data(), carry, 128);
     for (uint32_t i = 0; i < n; i++) ids[i] = i;
-    int rc = map_subset(ids.data(), n, fin.data(), fout.data(), out);
+    int rc = map_subset(ids.data(), n, fin.data(), fout.data(), out, cand.data());
     if (rc != UNC_OK && rc != UNC_E_OVERFLOW) return rc;
     int worst = rc;
     std::vector<uint32_t> sub_in, sub_out;
@@ -50,17 +58,23 @@ int unc_ordered_map(uint32_t n, uint32_t carry[32], unc_paf_rec *out, uint32_t *
                 continue;
             }
             if (i == 0) continue;
-            const uint32_t *want = &fout[(size_t) (i - 1) * 32];
-            if (memcmp(&fin[(size_t) i * 32], want, 128) != 0) {
+            const uint32_t *want = &fout[(size_t) (i - 1) * 32], *cd = &cand[(size_t) i * 32];
+            uint32_t *have = &fin[(size_t) i * 32];
+            if (memcmp(have, want, 128) == 0) continue;
+            uint32_t on_cand = 0, n_cand = 0;
+            for (int w = 0; w < 32; w++) { on_cand |= (have[w] ^ want[w]) & cd[w]; n_cand += (uint32_t) __builtin_popcount(cd[w]); }
+            if (on_cand || n_cand >= max_paths) {
                 ids.push_back(i);
                 sub_in.insert(sub_in.end(), want, want + 32);
+            } else {
+                memcpy(have, want, 128);                    // same mapping, same final flags: nothing to redo
             }
         }
         if (ids.empty()) break;
         const uint32_t m = (uint32_t) ids.size();
         sub_out.assign((size_t) m * 32, 0u);
         sub_recs.resize(m);
-        rc = map_subset(ids.data(), m, sub_in.data(), sub_out.data(), sub_recs.data());
+        rc = map_subset(ids.data(), m, sub_in.data(), sub_out.data(), sub_recs.data(), (uint32_t *) nullptr);
         if (rc != UNC_OK && rc != UNC_E_OVERFLOW) return rc;
         if (rc) worst = rc;
         for (uint32_t j = 0; j < m; j++) {

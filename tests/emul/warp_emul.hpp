@@ -11,7 +11,25 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__x86_64__)
+// Fiber switch: callee-saved registers + stack pointer only.  glibc's swapcontext also saves/restores the signal
+// mask with a system call per switch, which dominated the emulator's run time (the fibers switch at every collective).
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(".text\n"
+    ".hidden emu_switch\n"
+    ".globl emu_switch\n"
+    ".type emu_switch,@function\n"
+    "emu_switch:\n"
+    "    pushq %rbp\n    pushq %rbx\n    pushq %r12\n    pushq %r13\n    pushq %r14\n    pushq %r15\n"
+    "    movq %rsp, (%rdi)\n"
+    "    movq %rsi, %rsp\n"
+    "    popq %r15\n    popq %r14\n    popq %r13\n    popq %r12\n    popq %rbx\n    popq %rbp\n"
+    "    ret\n"
+    ".size emu_switch,.-emu_switch\n");
+#define EMU_FAST_SWITCH 1
+#else
 #include <ucontext.h>
+#endif
 
 #define UNC_DEV static inline
 #define UNC_DEV_NOINLINE static
@@ -29,7 +47,11 @@ struct WarpRv {      // per-warp rendezvous state
     uint64_t gen;
 };
 struct WarpEmu {     // one CTA: n_threads fibers, 32 per warp
+#ifdef EMU_FAST_SWITCH
+    void *ctx[EMU_MAX_THREADS], *main_ctx;      // saved stack pointers
+#else
     ucontext_t ctx[EMU_MAX_THREADS], main_ctx;
+#endif
     char *stacks[EMU_MAX_THREADS];
     int n_threads;
     int cur;
@@ -46,6 +68,14 @@ struct WarpEmu {     // one CTA: n_threads fibers, 32 per warp
 };
 extern thread_local WarpEmu *g_warp;
 
+#ifdef EMU_FAST_SWITCH
+static inline void emu_swap(WarpEmu *w, int from, int to) { emu_switch(&w->ctx[from], w->ctx[to]); }
+static inline void emu_swap_to_main(WarpEmu *w, int from) { emu_switch(&w->ctx[from], w->main_ctx); }
+#else
+static inline void emu_swap(WarpEmu *w, int from, int to) { swapcontext(&w->ctx[from], &w->ctx[to]); }
+static inline void emu_swap_to_main(WarpEmu *w, int from) { swapcontext(&w->ctx[from], &w->main_ctx); }
+#endif
+
 static inline void emu_yield() {
     WarpEmu *w = g_warp;
     int from = w->cur, nxt = from;
@@ -55,7 +85,7 @@ static inline void emu_yield() {
     }
     if (nxt == from) return;
     w->cur = nxt;
-    swapcontext(&w->ctx[from], &w->ctx[nxt]);
+    emu_swap(w, from, nxt);
 }
 
 // all-lane exchange within the calling fiber's warp: every lane posts v, then may read any
@@ -205,14 +235,15 @@ static void emu_trampoline() {
     w->n_done++;
     w->warp_done[me >> 5]++;
     if (w->n_done == w->n_threads) {
-        swapcontext(&w->ctx[me], &w->main_ctx);
+        emu_swap_to_main(w, me);
     } else {
         // a thread left early: the others must not touch a collective any more (checked there)
         int nxt = me;
         for (int i = 0; i < w->n_threads; i++) { nxt = nxt + 1 == w->n_threads ? 0 : nxt + 1; if (!w->done[nxt]) break; }
         w->cur = nxt;
-        swapcontext(&w->ctx[me], &w->ctx[nxt]);
+        emu_swap(w, me, nxt);
     }
+    abort();      // a finished fiber is never resumed
 }
 
 // run fn(arg) on a CTA of n_threads (multiple of 32) fibers
@@ -226,14 +257,29 @@ static inline void emu_run_cta(void (*fn)(void *), void *arg, int n_threads) {
     const size_t STK = 1 << 19;
     for (int i = 0; i < n_threads; i++) {
         w->stacks[i] = (char *) malloc(STK);
+#ifdef EMU_FAST_SWITCH
+        // first switch into the fiber: six zeroed callee-saved registers are popped, then `ret` enters the trampoline
+        // with the stack as after a call (rsp = 16n + 8); the slot above is a null return address (never used)
+        uintptr_t top = ((uintptr_t) w->stacks[i] + STK) & ~(uintptr_t) 15;
+        void **sp = (void **) top;
+        *--sp = nullptr;
+        *--sp = (void *) emu_trampoline;
+        for (int k = 0; k < 6; k++) *--sp = nullptr;
+        w->ctx[i] = (void *) sp;
+#else
         getcontext(&w->ctx[i]);
         w->ctx[i].uc_stack.ss_sp = w->stacks[i];
         w->ctx[i].uc_stack.ss_size = STK;
         w->ctx[i].uc_link = &w->main_ctx;
         makecontext(&w->ctx[i], (void (*)()) emu_trampoline, 0);
+#endif
     }
     w->cur = 0;
+#ifdef EMU_FAST_SWITCH
+    emu_switch(&w->main_ctx, w->ctx[0]);
+#else
     swapcontext(&w->main_ctx, &w->ctx[0]);
+#endif
     for (int i = 0; i < n_threads; i++) free(w->stacks[i]);
     g_warp = saved;
     free(w);

@@ -100,3 +100,14 @@ def test_i16_calibration_path(g200k):
     recs, ev, nm, mel = E.map_batch([i16], run_k2=False, dtype=1, cal=cal)
     m, s, l, omel = O.detect(pa.astype(np.float32))
     assert np.array_equal(ev[0], m) and mel[0] == omel
+
+
+def test_bench_scale_reads_on_the_4m7_index():
+    """The shipped kernel at the bench workload's scale (4.7 Mb index, max_paths 10 000, 4000-sample reads): one read that
+    maps and one that never does and extends ~4 M children through every phase at the buffer cap (3 radix passes,
+    deferred window walks, full-buffer cuts)."""
+    prefix, g = synthdata.get_index("g4m7")
+    E, O = emulib.Emu(prefix), orclib.Oracle(prefix)
+    sig, _ = synth.reads(g, 120, 4000, seed=7, frac_random=0.15)
+    recs, _, _, _ = _check(E, O, [sig[100], sig[99]])
+    assert recs[0].mapped and not recs[1].mapped and recs[1].n_children > 3000000

@@ -158,6 +158,15 @@ int unc_map_batch(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads, 
 int unc_map_batch_device(unc_pool *pool, const unc_read_desc *reads, uint32_t n_reads,
                          const void *d_samples, unc_paf_rec *out);
 
+/* Order of children that compare equal in the per-event child sort (reference src/mapper.cpp:531, pdqsort under
+ * operator< :866-871; only the LAST child of a run of equal FM ranges survives, :569-572).  mode 0 (default): emission
+ * order -- a stable parallel sort; what the reference computes with its sort made stable, and what it computes itself on
+ * 99.7 % of reads.  mode 1: the reference's own pdqsort reproduced step by step (one thread per CTA sorts the event's
+ * keys serially, kernel k2_map_exact), so that equal children land exactly where the reference's land: results are then
+ * those of the unmodified reference on every read, several times slower on reads that run at the max_paths cap.
+ * Applies to the batch calls of this pool (not to the streaming path). */
+int unc_pool_set_tie_order(unc_pool *pool, int mode);
+
 /* The batch mapped as ONE long-lived Mapper maps its reads one after the other -- what `uncalled map -t 1` prints
  * for a multi-read input.  Replaces a MapPool thread's loop over its reads (reference src/map_pool.cpp:104-158):
  * Mapper::reset (src/mapper.cpp:216-246) keeps the sources_added_ flags (:88), so a read starts with the flags its

@@ -64,9 +64,12 @@ static void k1_entry(void *a) {
 static uint32_t g_k1_stats[4];
 extern "C" void emu_k1_stats(uint32_t *out) { memcpy(out, g_k1_stats, sizeof(g_k1_stats)); }
 
+static int g_tie_order = 0;       // emu_set_tie_order: 1 = the exact-ties kernel (k2_map_exact of unc_abi.cu)
+extern "C" void emu_set_tie_order(int mode) { g_tie_order = mode; }
 static void cta_entry(void *a) {
     CtaArgs *w = (CtaArgs *) a;
-    unc_k2_cta_main(*w->ix, *w->p, *w->B, *w->W, w->sh);
+    if (g_tie_order) unc_k2_cta_main<true>(*w->ix, *w->p, *w->B, *w->W, w->sh);
+    else unc_k2_cta_main<false>(*w->ix, *w->p, *w->B, *w->W, w->sh);
 }
 
 // events (optional, n_reads x stride) / normed (optional) are filled like unc_events_batch.

@@ -65,7 +65,7 @@ def build(extra_flags=(), tag=""):
     out = os.path.join(EMUL_DIR, "libunc_emul%s.so" % tag)
     deps = [src, os.path.join(EMUL_DIR, "warp_emul.hpp")] + \
            [os.path.join(ROOT, "uncalled_b200", "csrc", f) for f in
-            ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_logic.hpp", "unc_ordered_logic.hpp", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp",
+            ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_logic.hpp", "unc_ordered_logic.hpp", "unc_pdqsort.cuh", "unc_warp.cuh", "unc_host_index.hpp", "unc_host_params.hpp",
              "unc_selfalign.cuh", "unc_selfalign_host.hpp")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
@@ -90,6 +90,7 @@ def _bind(L):
     L.emu_map_batch_ordered.argtypes = [C.c_void_p, C.POINTER(UncParams), C.POINTER(UncReadDesc), C.c_uint32, C.c_void_p,
                                         C.c_void_p, C.POINTER(UncPaf), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                         C.c_uint32, C.c_int]
+    L.emu_set_tie_order.argtypes = [C.c_int]
     L.emu_match_probs.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
     L.emu_self_align.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.emu_glibc_rand.argtypes = [C.c_uint, C.c_uint32, C.c_void_p]
@@ -140,6 +141,10 @@ class Emu:
             raise RuntimeError("emu_map_batch rc=%d" % rc)
         return list(out), [ev[i, :ne[i]].copy() for i in range(n)], [nm[i, :ne[i]].copy() for i in range(n)], mel
 
+
+    def set_tie_order(self, mode):
+        """1: the exact-ties kernel (the reference's pdqsort reproduced), 0: the default kernel."""
+        self.L.emu_set_tie_order(int(mode))
 
     def map_ordered(self, signals, carry=None, max_blocks=4096, n_warps=8):
         """unc_map_batch_ordered under the emulator: (recs, carry after, reads mapped again, extra rounds)."""

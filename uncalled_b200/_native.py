@@ -81,7 +81,7 @@ class Fast5Read(C.Structure):
 EXPORTS = ["unc_strerror", "unc_last_error", "unc_device_count", "unc_init", "unc_shutdown", "unc_params_default",
            "unc_index_load", "unc_index_get_info", "unc_index_seq", "unc_index_kmer_range",
            "unc_index_thresholds", "unc_index_free", "unc_index_build", "unc_pool_create", "unc_pool_free",
-           "unc_map_batch", "unc_map_batch_device", "unc_map_batch_ordered", "unc_map_batch_submit", "unc_map_batch_wait", "unc_pool_record", "unc_pool_elapsed", "unc_events_batch", "unc_match_probs", "unc_fm_neighbors",
+           "unc_map_batch", "unc_map_batch_device", "unc_map_batch_ordered", "unc_pool_set_tie_order", "unc_map_batch_submit", "unc_map_batch_wait", "unc_pool_record", "unc_pool_elapsed", "unc_events_batch", "unc_match_probs", "unc_fm_neighbors",
            "unc_fm_sa", "unc_pool_last_timing", "unc_pool_k1_stats", "unc_stream_create", "unc_stream_step",
            "unc_stream_free", "unc_self_align", "unc_free", "unc_fast5_open", "unc_fast5_count", "unc_fast5_info",
            "unc_fast5_load", "unc_fast5_close", "unc_fast5_last_error"]
@@ -92,7 +92,7 @@ def build(force=False, verbose=False):
     src_dir = os.path.join(PKG_DIR, "csrc")
     srcs = [os.path.join(src_dir, f) for f in ("unc_abi.cu", "unc_index_build.cpp", "unc_fast5.cpp")]
     deps = srcs + [os.path.join(src_dir, f) for f in
-                   ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_host.inl", "unc_stream_logic.hpp", "unc_ordered_logic.hpp", "unc_warp.cuh",
+                   ("unc_device.cuh", "unc_k1.cuh", "unc_stream.cuh", "unc_stream_host.inl", "unc_stream_logic.hpp", "unc_ordered_logic.hpp", "unc_pdqsort.cuh", "unc_warp.cuh",
                     "unc_selfalign.cuh", "unc_selfalign_host.hpp", "unc_selfalign_host.inl",
                     "unc_host_index.hpp", "unc_host_params.hpp")] + \
         [os.path.join(ROOT, "include", "unc_b200.h")]
@@ -138,6 +138,7 @@ def lib():
     L.unc_map_batch.argtypes = [vp, vp, u32, vp, vp]
     L.unc_map_batch_device.argtypes = [vp, vp, u32, vp, vp]
     L.unc_map_batch_ordered.argtypes = [vp, vp, u32, vp, C.c_int, vp, vp, C.POINTER(u32), C.POINTER(u32)]
+    L.unc_pool_set_tie_order.argtypes = [vp, C.c_int]
     L.unc_map_batch_submit.argtypes = [vp, vp, u32, vp, C.c_int]
     L.unc_map_batch_wait.argtypes = [vp, vp]
     L.unc_pool_record.argtypes = [vp, C.c_int]

@@ -73,27 +73,32 @@ __global__ void __launch_bounds__(128) k1_norm(DevBatch B, DevParams p) {
 // Persistent CTA-per-read mapper.  Each CTA stages the pore model, the 1024 k-mer FM ranges
 // and the thresholds in shared memory, then pulls reads from a global queue; the K2_WARPS warps
 // of the CTA cooperate on every event of the read (chained scans through shared memory).
-__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
-k2_map(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t hist_stride, size_t ckey_stride, size_t cks_stride,
-       size_t elist_stride, size_t order_stride, size_t rlist_stride, size_t clu_stride, size_t dir_stride) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    K2Shared *sh = (K2Shared *) smem_raw;
-    const size_t slot = blockIdx.x;
-    DevWork W;
-    W.paths = W0.paths + slot * paths_stride;
-    W.hist = W0.hist + slot * hist_stride;
-    W.wlist = W0.wlist + slot * cks_stride;
-    W.ckey = W0.ckey + slot * ckey_stride;
-    W.cks = W0.cks + slot * cks_stride;
-    W.elist = W0.elist + slot * elist_stride;
-    W.order = W0.order + slot * order_stride;
-    W.rlist = W0.rlist + slot * rlist_stride;
-    W.clu = W0.clu + slot * clu_stride;
-    W.dir = W0.dir + slot * dir_stride;
-    W.max_blocks = W0.max_blocks;
-    W.rl_cap = W0.rl_cap;
-    unc_k2_cta_main(ix, p, B, W, sh);
-}
+#define K2_MAP_KERNEL(NAME, EXACT)                                                                                          \
+    __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)                                                             \
+    NAME(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t hist_stride, size_t ckey_stride,     \
+         size_t cks_stride, size_t elist_stride, size_t order_stride, size_t rlist_stride, size_t clu_stride,              \
+         size_t dir_stride) {                                                                                              \
+        extern __shared__ __align__(16) unsigned char smem_raw[];                                                          \
+        K2Shared *sh = (K2Shared *) smem_raw;                                                                              \
+        const size_t slot = blockIdx.x;                                                                                    \
+        DevWork W;                                                                                                         \
+        W.paths = W0.paths + slot * paths_stride;                                                                          \
+        W.hist = W0.hist + slot * hist_stride;                                                                             \
+        W.wlist = W0.wlist + slot * cks_stride;                                                                            \
+        W.ckey = W0.ckey + slot * ckey_stride;                                                                             \
+        W.cks = W0.cks + slot * cks_stride;                                                                                \
+        W.elist = W0.elist + slot * elist_stride;                                                                          \
+        W.order = W0.order + slot * order_stride;                                                                          \
+        W.rlist = W0.rlist + slot * rlist_stride;                                                                          \
+        W.clu = W0.clu + slot * clu_stride;                                                                                \
+        W.dir = W0.dir + slot * dir_stride;                                                                                \
+        W.max_blocks = W0.max_blocks;                                                                                      \
+        W.rl_cap = W0.rl_cap;                                                                                              \
+        unc_k2_cta_main<EXACT>(ix, p, B, W, sh);                                                                           \
+    }
+K2_MAP_KERNEL(k2_map, false)
+// the exact-ties kernel (unc_pool_set_tie_order): the same mapper with the reference's unstable child sort run serially
+K2_MAP_KERNEL(k2_map_exact, true)
 
 // ordered mode: per read the 1024-bit mask of the k-mers that pass the first event's fresh-source tests
 // (block = read, thread = k-mer; word k>>5, bit k&31 = the ballot of warp k>>5)
@@ -184,6 +189,7 @@ struct unc_pool {
     uint32_t pending_n = 0;      // reads of a submitted, not yet collected batch (unc_map_batch_submit / _wait)
     uint64_t pending_h2d = 0;
     // ordered mode (unc_map_batch_ordered): per-read sources_added_ words in / out, allocated on first use
+    int tie_order = 0;           // unc_pool_set_tie_order: 0 = emission order (k2_map), 1 = the reference's pdqsort (k2_map_exact)
     u32 *d_flags_in = nullptr, *d_flags_out = nullptr, *d_cand = nullptr;
     bool want_cand = false;      // the next batch_enqueue also launches k_event0_cands
 };
@@ -576,8 +582,13 @@ static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, co
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[2], s));
     uint32_t grid = std::min<uint32_t>(P->grid, n);
-    k2_map<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->hist_stride, P->ckey_stride, P->cks_stride,
-                                             P->elist_stride, P->order_stride, P->rlist_stride, P->clu_stride, P->dir_stride);
+    if (P->tie_order)
+        k2_map_exact<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->hist_stride, P->ckey_stride,
+                                                       P->cks_stride, P->elist_stride, P->order_stride, P->rlist_stride,
+                                                       P->clu_stride, P->dir_stride);
+    else
+        k2_map<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->hist_stride, P->ckey_stride, P->cks_stride,
+                                                 P->elist_stride, P->order_stride, P->rlist_stride, P->clu_stride, P->dir_stride);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(P->ev[3], s));
     CUDA_TRY(cudaMemcpyAsync(P->h_out, P->d_out, (size_t) n * sizeof(DevRec), cudaMemcpyDeviceToHost, s));
@@ -654,6 +665,19 @@ int unc_pool_elapsed(unc_pool *from, int from_slot, unc_pool *to, int to_slot, f
 
 int unc_map_batch_device(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *d_samples, unc_paf_rec *out) {
     return run_batch(P, reads, n, d_samples, true, out);
+}
+
+int unc_pool_set_tie_order(unc_pool *P, int mode) {
+    if (!P || (mode != 0 && mode != 1)) return fail(UNC_E_ARG, "bad argument");
+    if (P->pending_n) return fail(UNC_E_ARG, "the pool holds a submitted batch");
+    if (mode == 1) {
+        CUDA_TRY(cudaSetDevice(P->idx->device));
+        CUDA_TRY(cudaFuncSetAttribute(k2_map_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
+        // CTAs are independent (each pulls reads from the queue into its own slot), so a lower residency than k2_map's
+        // only means that the last CTAs of the grid start late and find the queue empty
+    }
+    P->tie_order = mode;
+    return UNC_OK;
 }
 
 int unc_map_batch_ordered(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, int samples_on_device,

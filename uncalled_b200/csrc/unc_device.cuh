@@ -846,6 +846,8 @@ struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
 #endif
 };
 
+#include "unc_pdqsort.cuh"
+
 // exclusive scan over the K2_RB*K2_MAXSEG sort counters by the worker threads:
 // dst[i] = sum(src[0..i)); src := 0.   wt = worker thread index, nwt = worker thread count.
 UNC_DEV void k2_wk_exscan_bins(K2Shared *sh, u32 *src, u32 *dst, u32 wt, u32 nwt) {
@@ -1077,7 +1079,7 @@ UNC_DEV u32 k2_grab_chunk(K2Shared *sh) {
 #define K2_NEXT_CHUNK(c) ((c) + nwk)
 #endif
 
-template <bool STREAM>
+template <bool STREAM, bool EXACT>
 UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
                             K2Shared *sh, u32 r, u32 n_first, u32 n_limit, u32 *epoch_io) {
     const int lane = w_lane();
@@ -1621,7 +1623,14 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             //         array in every pass, so the scatter is stable without inter-warp ordering
             uint4 *src = ckA, *dst = ckB;
             const u32 c_lo = ww * seg_ch, c_hi = (c_lo + seg_ch < nch) ? c_lo + seg_ch : nch;
-            for (u32 pass = 0; pass < npass; pass++) {
+            if (EXACT) {
+                // exact-ties kernel: the reference's own (unstable) sort, serially, over the keys in emission order --
+                // equal children then land where the reference's land (unc_pdqsort.cuh).  The first pass's digit counts
+                // are dropped; the chunk-local key buffer, idle until the next event, is the sort's stack.
+                k2_wk_exscan_bins(sh, sh->hist_next, sh->hist_cur, wt, nwt);
+                if (wt == 0 && !unc_pdq_sort(ckA, nc, cks, ((maxp + 31u) >> 5) * K2_CH_SLOTS)) s_atomic_or(&sh->wk_overflow, 1u);
+            }
+            for (u32 pass = 0; !EXACT && pass < npass; pass++) {
                 const u32 sb = pass * K2_RBITS;
                 k2_wk_exscan_bins(sh, sh->hist_next, sh->hist_cur, wt, nwt);
                 uint4 kn = make_uint4(0, 0, 0, 0), kn2 = make_uint4(0, 0, 0, 0);
@@ -1668,7 +1677,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             // runs of equal fm_start: order by (fm_end, seed_prob, emission index).  Run heads are
             // found chunk-wise (one coalesced load per 32 keys, neighbours by shuffle); the rare
             // runs are then insertion-sorted by their head lane.
-            {
+            if (!EXACT) {
                 uint4 kq = make_uint4(0, 0, 0, 0); u32 bx = 0, ax = 0;   // key, fm_start before / after the chunk
                 if (ww < nch) {
                     u32 g0 = ww * 32 + (u32) lane;
@@ -2011,7 +2020,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
 
 // One read mapped by one CTA.  reference src/mapper.cpp:188-200 (map_read); with STREAM, one map_chunk's
 // worth of events of a read in progress (:381-431), resumed from and saved to the channel's DevMapState.
-template <bool STREAM>
+template <bool STREAM, bool EXACT>
 UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
                              K2Shared *sh, u32 r, u32 *epoch_io) {
     const u32 tid = (u32) c_tid();
@@ -2049,7 +2058,7 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
     for (u32 b = tid; b < K2_RB * K2_MAXSEG; b += (u32) c_nthreads()) sh->hist_next[b] = 0;
     c_sync();
 #ifdef K2_TRK_INLINE
-    unc_k2_workers<STREAM>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
+    unc_k2_workers<STREAM, EXACT>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
     c_sync();
     if (tid == 0) {
         Tracker t1;
@@ -2069,7 +2078,7 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
     }
 #else
     if (tid < 32) unc_k2_tracker<STREAM>(ix, p, B, W, sh, r, n_first, n_limit);
-    else unc_k2_workers<STREAM>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
+    else unc_k2_workers<STREAM, EXACT>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
 #endif
     c_sync();
     if (STREAM && tid < 32) B.mstate[B.chan[r]].flags[tid] = sh->flags[tid];
@@ -2107,6 +2116,8 @@ UNC_DEV DevWork unc_work_slot(const DevWork &W0, const DevWorkStrides &S, size_t
 
 // Persistent CTA body: stage the tables, then pull reads from the global queue.
 // Needs at least 2 warps (tracker + >= 1 worker) and at most 1 + K2_MAXSEG.
+// EXACT: the exact-ties kernel (the reference's unstable child sort reproduced, unc_pdqsort.cuh)
+template <bool EXACT = false>
 UNC_DEV void unc_k2_cta_main(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W, K2Shared *sh) {
     unc_k2_cta_setup(ix, p, sh);
     u32 epoch = 0;
@@ -2116,7 +2127,7 @@ UNC_DEV void unc_k2_cta_main(const DevIndex &ix, const DevParams &p, const DevBa
         u32 r = sh->bc[0];
         c_sync();
         if (r >= B.n_reads) break;
-        unc_k2_map_read<false>(ix, p, B, W, sh, r, &epoch);
+        unc_k2_map_read<false, EXACT>(ix, p, B, W, sh, r, &epoch);
     }
 }
 
@@ -2132,6 +2143,6 @@ UNC_DEV void unc_k2_cta_main_stream(const DevIndex &ix, const DevParams &p, cons
         c_sync();
         if (r >= B.n_reads) break;
         const DevWork W = unc_work_slot(W0, S, B.chan[r]);
-        unc_k2_map_read<true>(ix, p, B, W, sh, r, &epoch);
+        unc_k2_map_read<true, false>(ix, p, B, W, sh, r, &epoch);
     }
 }

@@ -119,6 +119,11 @@ class BatchMapper:
             N.check(rc)
         return out
 
+    def set_tie_order(self, mode):
+        """0: equal children keep emission order (default kernel); 1: the reference's unstable pdqsort reproduced
+        (exact-ties kernel; unc_pool_set_tie_order)."""
+        N.check(self.L.unc_pool_set_tie_order(self.h, int(mode)))
+
     def map_ordered(self, samples, descs, carry=None, on_device=False):
         """The batch as ONE long-lived Mapper maps it, read after read (`uncalled map -t 1`; unc_map_batch_ordered).
         carry: 32 uint32 sources_added_ words the previous batch ended with (None = a new Mapper); returns

@@ -223,6 +223,9 @@ def main():
     ap.add_argument("--ordered", action="store_true",
                     help="additionally time unc_map_batch_ordered (`uncalled map -t 1` semantics: one long-lived Mapper, reads in "
                          "order, resolved by re-mapping the reads whose predecessor left flags set); reported under 'ordered'")
+    ap.add_argument("--exact-ties", action="store_true",
+                    help="additionally time the exact-ties kernel (unc_pool_set_tie_order(1): the reference's unstable pdqsort "
+                         "reproduced serially per event); reported under 'exact_ties'")
     ap.add_argument("--workload", default="batch", choices=["batch", "stream"],
                     help="batch: configs[1] (the headline); stream: chunk streaming over 512 channels (configs[4]-like)")
     ap.add_argument("--reads-per-channel", type=int, default=2)
@@ -352,6 +355,19 @@ def main():
                    "records_differing_from_plain_batch": int((recs_o != out_dev).sum()),
                    "note": "device-resident samples; sum of the CUDA-event times of all rounds, max over ranks"}
 
+    exact_ties = None
+    if args.exact_ties:
+        bm.set_tie_order(1)
+        try:
+            timed(step_device, 1)
+            ex_ms, ex_wall, _ = timed(step_device, args.steps)
+            recs_e = out_holder["o"]
+        finally:
+            bm.set_tie_order(0)
+        exact_ties = {"value": world * n_reads / (ex_ms / args.steps / 1e3), "unit": "reads/s", "ms_per_step": ex_ms / args.steps,
+                      "records_differing_from_default_kernel": int((recs_e != out_dev).sum()),
+                      "note": "k2_map_exact, device-resident samples, CUDA events, max over ranks"}
+
     ms_per_step = dev_ms / args.steps
     value = world * n_reads / (ms_per_step / 1e3)
     e2e_value = world * n_reads / (e2e_ms / args.steps / 1e3)
@@ -393,6 +409,7 @@ def main():
             "wall_ms_per_step": wall_ms / args.steps,
             "overlap": overlap,
             "ordered": ordered,
+            "exact_ties": exact_ties,
             "clocks": clocks,
             "roofline": {"kernel": "k2_map", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,

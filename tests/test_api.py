@@ -268,3 +268,5 @@ def test_ordered_conf_keeps_input_order_and_threads_the_carry():
     _, c2, _ = cli.load_conf(["map", "--ordered", "idx", "reads.fast5"])
     _, c3, _ = cli.load_conf(["map", "idx", "reads.fast5"])
     assert c2.ordered == 1 and c3.ordered == 0
+    _, c4, _ = cli.load_conf(["map", "--exact-ties", "--ordered", "idx", "reads.fast5"])
+    assert (c4.exact_ties, c4.ordered, c3.exact_ties) == (1, 1, 0)

@@ -264,3 +264,40 @@ def test_ordered_mode_equals_one_long_lived_mapper(U):
                        for i in range(n))
         bm.close()
         idx.close()
+
+
+def test_exact_ties_kernel_equals_the_unmodified_reference_on_every_golden_read(U):
+    """unc_pool_set_tie_order(1) -> k2_map_exact: the 320 reads of tests/golden/synth_paf_golden.json against the records
+    the UNMODIFIED reference computed for them (its pdqsort as it is), no oracle in between; the default kernel still
+    gives the stable-sort records.  Then both exact modes together against the oracle's one-Mapper chain with pdqsort."""
+    import sys
+    import orclib
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synth_paf_golden as M
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "synth_paf_golden.json")))
+    for name, n, ns, seed, frac in M.SETS:
+        prefix, sig = M.signals(name, n, ns, seed, frac)
+        idx = U.Index(prefix, device=0)
+        bm = U.BatchMapper(idx, max_reads=n, max_samples=n * ns)
+        flat, d = np.ascontiguousarray(sig.reshape(-1)), U.make_descs([ns] * n)
+        bm.set_tie_order(1)
+        exact = bm.map(flat, d)
+        assert int((exact["status"] != 0).sum()) == 0
+        assert [[int(v) for v in U.paf_key(r)] for r in exact] == gold["reference"][name], name
+        bm.set_tie_order(0)
+        plain = bm.map(flat, d)
+        assert [[int(v) for v in U.paf_key(r)] for r in plain] == gold["reference_stable_sort"][name], name
+        if name == "g4m7":        # exact ties + ordered = the unmodified reference with one long-lived Mapper (`-t 1`)
+            k = 40
+            O = orclib.Oracle(prefix)
+            O.lib.orc_set_child_sort(1)
+            try:
+                want = O.map_reads_one_mapper(flat[:k * ns], (np.arange(k, dtype=np.uint64) * ns).astype(np.uint64),
+                                              np.full(k, ns, np.uint32))
+            finally:
+                O.lib.orc_set_child_sort(0)
+            bm.set_tie_order(1)
+            recs, _, _, _ = bm.map_ordered(flat[:k * ns], d[:k])
+            assert [U.paf_key(r) for r in recs] == [orclib.paf_tuple(w) for w in want]
+        bm.close()
+        idx.close()

@@ -18,3 +18,5 @@ timeout 600 python bench.py --workload stream --steps 2 --warmup 1 > gpurun_out/
 timeout 600 python bench.py --overlap --no-cpu-baseline --steps 4 --warmup 3 > gpurun_out/bench_overlap.json 2> gpurun_out/bench_overlap.err; echo "overlap bench rc=$?"; cut -c1-900 gpurun_out/bench_overlap.json
 # ordered mode (`uncalled map -t 1` semantics, unc_map_batch_ordered): cost of the re-mapping rounds on the bench workload
 timeout 600 python bench.py --ordered --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/bench_ordered.json 2> gpurun_out/bench_ordered.err; echo "ordered bench rc=$?"; python -c "import json;print(json.load(open('gpurun_out/bench_ordered.json'))['ordered'])"
+# exact-ties kernel (unc_pool_set_tie_order(1): the reference's pdqsort reproduced): its cost on the bench workload
+timeout 900 python bench.py --exact-ties --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/bench_exact.json 2> gpurun_out/bench_exact.err; echo "exact-ties bench rc=$?"; python -c "import json;print(json.load(open('gpurun_out/bench_exact.json'))['exact_ties'])"

@@ -9,6 +9,8 @@ constructing a MapPool without a usable CUDA device raises UncError.
 Differences a caller can observe (documented, not hidden):
   * `MapPool(conf)` maps batches on the GPU instead of one read per CPU thread; `conf.threads`
     is accepted and ignored by the mapper (reference src/map_pool.cpp:31).
+    `conf.exact_ties = 1` (CLI `--exact-ties`) selects the kernel that reproduces the reference's unstable child sort
+    (divergence 1); with both switches the output is the unmodified reference's `-t 1` output.
     `conf.ordered = 1` (CLI `--ordered`) reproduces what the reference prints with ONE thread for a multi-read
     input: reads mapped in input order by one long-lived Mapper (divergence 2).
   * fast5 files are read by the library's own HDF5 subset reader (uncalled_b200/csrc/unc_fast5.cpp; the
@@ -57,6 +59,8 @@ class Conf:
         "max_active_reads": (512, "Maximum number of reads being mapped at once"),
         "device": (0, "CUDA device of this process (one process per GPU)"),
         "batch_reads": (4096, "Reads per GPU batch"),
+        "exact_ties": (0, "1: children that compare equal in the per-event sort are ordered exactly as the reference's "
+                          "unstable pdqsort orders them (exact-ties kernel, slower); 0: emission order (default)"),
         "ordered": (0, "1: map the reads in input order as ONE long-lived Mapper does, i.e. exactly what the reference "
                        "prints with `-t 1` (a read inherits the source flags its predecessor left set); "
                        "0: every read is mapped by a new Mapper (batch order free, fastest)"),
@@ -305,6 +309,8 @@ class MapPool:
             if m is not None:
                 m.close()
             m = BatchMapper(self.index, params=self.params, max_reads=cap[0], max_samples=cap[1])
+            if self.conf.exact_ties:
+                m.set_tie_order(1)
             self._mappers[slot], self._caps[slot] = m, cap
         return m
 

@@ -50,6 +50,7 @@ def get_parser(conf):
     p.add_argument("--device", type=int, default=conf.device, help="CUDA device")
     p.add_argument("--batch-reads", type=int, default=conf.batch_reads, help="Reads per GPU batch")
     p.add_argument("--ordered", action="store_const", const=1, default=conf.ordered, help=type(conf).ordered.__doc__)
+    p.add_argument("--exact-ties", action="store_const", const=1, default=conf.exact_ties, help=type(conf).exact_ties.__doc__)
     return parser
 
 

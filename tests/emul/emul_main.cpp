@@ -66,6 +66,10 @@ extern "C" void emu_k1_stats(uint32_t *out) { memcpy(out, g_k1_stats, sizeof(g_k
 
 static int g_tie_order = 0;       // emu_set_tie_order: 1 = the exact-ties kernel (k2_map_exact of unc_abi.cu)
 extern "C" void emu_set_tie_order(int mode) { g_tie_order = mode; }
+extern "C" void emu_tie_stats(unsigned long *out, int reset) {
+    out[0] = g_emu_tie_stats[0]; out[1] = g_emu_tie_stats[1];
+    if (reset) g_emu_tie_stats[0] = g_emu_tie_stats[1] = 0;
+}
 static void cta_entry(void *a) {
     CtaArgs *w = (CtaArgs *) a;
     if (g_tie_order) unc_k2_cta_main<true>(*w->ix, *w->p, *w->B, *w->W, w->sh);

@@ -847,6 +847,9 @@ struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
 };
 
 #include "unc_pdqsort.cuh"
+#ifdef UNC_EMUL
+static unsigned long g_emu_tie_stats[2];   // test statistics of the exact-ties path (emulator builds only)
+#endif
 
 // exclusive scan over the K2_RB*K2_MAXSEG sort counters by the worker threads:
 // dst[i] = sum(src[0..i)); src := 0.   wt = worker thread index, nwt = worker thread count.
@@ -1624,13 +1627,12 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             uint4 *src = ckA, *dst = ckB;
             const u32 c_lo = ww * seg_ch, c_hi = (c_lo + seg_ch < nch) ? c_lo + seg_ch : nch;
             if (EXACT) {
-                // exact-ties kernel: the reference's own (unstable) sort, serially, over the keys in emission order --
-                // equal children then land where the reference's land (unc_pdqsort.cuh).  The first pass's digit counts
-                // are dropped; the chunk-local key buffer, idle until the next event, is the sort's stack.
-                k2_wk_exscan_bins(sh, sh->hist_next, sh->hist_cur, wt, nwt);
-                if (wt == 0 && !unc_pdq_sort(ckA, nc, cks, ((maxp + 31u) >> 5) * K2_CH_SLOTS)) s_atomic_or(&sh->wk_overflow, 1u);
+                // exact-ties kernel: keep the keys in emission order (the array the reference sorts) in the chunk-local
+                // key buffer, which is idle until the next event's extension
+                for (u32 i = wt; i < nc; i += nwt) cks[i] = ckA[i];
+                if (wt == 0) sh->bc[5] = 0;
             }
-            for (u32 pass = 0; !EXACT && pass < npass; pass++) {
+            for (u32 pass = 0; pass < npass; pass++) {
                 const u32 sb = pass * K2_RBITS;
                 k2_wk_exscan_bins(sh, sh->hist_next, sh->hist_cur, wt, nwt);
                 uint4 kn = make_uint4(0, 0, 0, 0), kn2 = make_uint4(0, 0, 0, 0);
@@ -1677,7 +1679,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
             // runs of equal fm_start: order by (fm_end, seed_prob, emission index).  Run heads are
             // found chunk-wise (one coalesced load per 32 keys, neighbours by shuffle); the rare
             // runs are then insertion-sorted by their head lane.
-            if (!EXACT) {
+            {
                 uint4 kq = make_uint4(0, 0, 0, 0); u32 bx = 0, ax = 0;   // key, fm_start before / after the chunk
                 if (ww < nch) {
                     u32 g0 = ww * 32 + (u32) lane;
@@ -1719,9 +1721,28 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
                     }
                 }
             }
+            if (EXACT) {
+                // Children that operator< does not separate are now adjacent.  Without any, the sorted order is unique
+                // and this one is the reference's; with one, only running the reference's own unstable sort tells where
+                // equal children end up (unc_pdqsort.cuh): one thread sorts the saved emission-order copy.
+                c_sync_sub(1, (int) nwt);
+                for (u32 i = wt; i + 1u < nc; i += nwt) {
+                    const uint4 k0 = src[i], k1 = src[i + 1u];
+                    if (!pq_less(k0, k1) && !pq_less(k1, k0)) *(volatile u32 *) &sh->bc[5] = 1u;
+                }
+            }
             c_sync_sub(1, (int) nwt);
             PT_MARK(3)
             const uint4 *sk = src;   // sorted keys
+#ifdef UNC_EMUL
+            if (EXACT && wt == 0) { g_emu_tie_stats[0]++; g_emu_tie_stats[1] += sh->bc[5]; }   // events sorted / with a tie
+#endif
+            if (EXACT && *(volatile u32 *) &sh->bc[5]) {
+                const u32 cap = ((maxp + 31u) >> 5) * K2_CH_SLOTS;
+                if (wt == 0 && !unc_pdq_sort(cks, nc, cks + nc, cap - nc)) s_atomic_or(&sh->wk_overflow, 1u);
+                c_sync_sub(1, (int) nwt);
+                sk = cks;
+            }
 
             // ---- D. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603).
             // D1: per-chunk aggregate of the k-mer run structure: (max fm_end of the trailing run,

@@ -164,7 +164,7 @@ int unc_map_batch_device(unc_pool *pool, const unc_read_desc *reads, uint32_t n_
  * 99.7 % of reads.  mode 1: the reference's own pdqsort reproduced step by step (one thread per CTA sorts the event's
  * keys serially, kernel k2_map_exact), so that equal children land exactly where the reference's land: results are then
  * those of the unmodified reference on every read, several times slower on reads that run at the max_paths cap.
- * Applies to the batch calls of this pool (not to the streaming path). */
+ * Applies to the batch calls of this pool; unc_stream_set_tie_order is the streaming path's switch. */
 int unc_pool_set_tie_order(unc_pool *pool, int mode);
 
 /* The batch mapped as ONE long-lived Mapper maps its reads one after the other -- what `uncalled map -t 1` prints
@@ -250,6 +250,9 @@ int unc_stream_create(const unc_index *idx, const unc_params *prm, uint32_t n_ch
                       uint32_t max_chunks, unc_stream **out);
 int unc_stream_step(unc_stream *st, const unc_chunk_desc *chunks, uint32_t n, const void *samples,
                     unc_stream_result *out);
+/* Tie order of the per-event child sort for this stream's steps: see unc_pool_set_tie_order (1 = the reference's pdqsort
+ * reproduced; applies from the next step on, the per-channel state is unaffected). */
+int unc_stream_set_tie_order(unc_stream *st, int mode);
 void unc_stream_free(unc_stream *st);
 
 /* ---- `uncalled index` after the BWA build ----------------------------------------------------------

@@ -217,7 +217,8 @@ struct EmuStream {
 struct StreamCtaArgs { const DevIndex *ix; const DevParams *p; const DevBatch *B; const DevWork *W; const DevWorkStrides *S; K2Shared *sh; };
 static void stream_cta_entry(void *a) {
     StreamCtaArgs *w = (StreamCtaArgs *) a;
-    unc_k2_cta_main_stream(*w->ix, *w->p, *w->B, *w->W, *w->S, w->sh);
+    if (g_tie_order) unc_k2_cta_main_stream<true>(*w->ix, *w->p, *w->B, *w->W, *w->S, w->sh);
+    else unc_k2_cta_main_stream<false>(*w->ix, *w->p, *w->B, *w->W, *w->S, w->sh);
 }
 
 void *emu_stream_create(void *pidx, const unc_params *prm, uint32_t n_channels, uint32_t max_chunk_len,

@@ -112,3 +112,24 @@ def test_both_exact_modes_together_equal_the_unmodified_references_long_lived_ma
         pytest.skip("oracle/_ref not built")
     out = orclib.run_in_subprocess(BOTH_EXACT % (os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")), timeout=900)
     assert "EXACT-DIFF [] REMAPPED 1" in out and "PLAIN-DIFF [36, 589]" in out, out
+
+
+def test_streaming_path_with_exact_ties(setup):
+    """k2_map_stream_exact: chunk-wise mapping with the reference's child sort reproduced, against the streaming oracle in
+    pdqsort mode (the reference's own streaming Mapper also sorts with pdqsort) -- reads following each other on channels."""
+    import synth
+    import synthdata
+    import test_stream_emul as TS
+    prefix, g = synthdata.get_index("g200k")
+    E, O = emulib.Emu(prefix), orclib.Oracle(prefix)
+    sig, _ = synth.reads(g, 4, 5000, seed=5, frac_random=0.3)
+    O.lib.orc_set_child_sort(1)
+    try:
+        E.set_tie_order(1)
+        st = TS._check(E, O, [sig[i][:5000 - 37 * i] for i in range(4)], 2, 450)
+        assert (2, 0) in st
+        E.params.max_paths = O.params.max_paths = 300
+        TS._check(E, O, [sig[i] for i in range(3)], 3, 450, max_chunks=4, n_warps=3)
+    finally:
+        E.set_tie_order(0)
+        O.lib.orc_set_child_sort(0)

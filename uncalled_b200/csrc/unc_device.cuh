@@ -2153,6 +2153,7 @@ UNC_DEV void unc_k2_cta_main(const DevIndex &ix, const DevParams &p, const DevBa
 }
 
 // Streaming variant: every item continues a read in the workspace slot of its CHANNEL.
+template <bool EXACT = false>
 UNC_DEV void unc_k2_cta_main_stream(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W0,
                                     const DevWorkStrides &S, K2Shared *sh) {
     unc_k2_cta_setup(ix, p, sh);
@@ -2164,6 +2165,6 @@ UNC_DEV void unc_k2_cta_main_stream(const DevIndex &ix, const DevParams &p, cons
         c_sync();
         if (r >= B.n_reads) break;
         const DevWork W = unc_work_slot(W0, S, B.chan[r]);
-        unc_k2_map_read<true, false>(ix, p, B, W, sh, r, &epoch);
+        unc_k2_map_read<true, EXACT>(ix, p, B, W, sh, r, &epoch);
     }
 }

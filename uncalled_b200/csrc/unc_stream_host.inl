@@ -17,6 +17,13 @@ k2_map_stream(DevIndex ix, DevParams p, DevBatch B, DevWork W0, DevWorkStrides S
     unc_k2_cta_main_stream(ix, p, B, W0, S, (K2Shared *) smem_raw);
 }
 
+// the exact-ties instantiation (unc_stream_set_tie_order): the reference's unstable child sort reproduced, unc_pdqsort.cuh
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
+k2_map_stream_exact(DevIndex ix, DevParams p, DevBatch B, DevWork W0, DevWorkStrides S) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unc_k2_cta_main_stream<true>(ix, p, B, W0, S, (K2Shared *) smem_raw);
+}
+
 struct unc_stream {
     const unc_index *idx = nullptr;
     unc_params prm;
@@ -30,6 +37,7 @@ struct unc_stream {
     DevWorkStrides strides{};
     size_t smem = 0;
     uint32_t grid = 0;
+    int tie_order = 0;           // unc_stream_set_tie_order
     // per-call buffers (capacity n_channels items)
     void *d_samples = nullptr;
     DevReadDesc *d_reads = nullptr, *h_reads = nullptr;
@@ -54,6 +62,16 @@ void unc_stream_free(unc_stream *T) {
     cudaFree(T->d_out); cudaFreeHost(T->h_out);
     if (T->stream) cudaStreamDestroy(T->stream);
     delete T;
+}
+
+int unc_stream_set_tie_order(unc_stream *T, int mode) {
+    if (!T || (mode != 0 && mode != 1)) return fail(UNC_E_ARG, "bad argument");
+    if (mode == 1) {
+        CUDA_TRY(cudaSetDevice(T->idx->device));
+        CUDA_TRY(cudaFuncSetAttribute(k2_map_stream_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T->smem));
+    }
+    T->tie_order = mode;
+    return UNC_OK;
 }
 
 int unc_stream_create(const unc_index *idx, const unc_params *prm, uint32_t n_channels, uint32_t max_chunk_len,
@@ -185,7 +203,10 @@ int unc_stream_step(unc_stream *T, const unc_chunk_desc *chunks, uint32_t n, con
         B.mstate = T->S.map; B.chan = T->d_chan;
         k_stream_chunks<<<(m + 127) / 128, 128, 0, s>>>(B, T->dp, T->S, T->d_new);
         CUDA_TRY(cudaGetLastError());
-        k2_map_stream<<<std::min<uint32_t>(T->grid, m), K2_THREADS, T->smem, s>>>(T->idx->ix, T->dp, B, T->W, T->strides);
+        if (T->tie_order)
+            k2_map_stream_exact<<<std::min<uint32_t>(T->grid, m), K2_THREADS, T->smem, s>>>(T->idx->ix, T->dp, B, T->W, T->strides);
+        else
+            k2_map_stream<<<std::min<uint32_t>(T->grid, m), K2_THREADS, T->smem, s>>>(T->idx->ix, T->dp, B, T->W, T->strides);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(T->h_out, T->d_out, (size_t) m * sizeof(DevRec), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(T->h_flags, T->d_flags, (size_t) m * 4, cudaMemcpyDeviceToHost, s));

@@ -87,6 +87,10 @@ class StreamMapper:
         N.check(self.L.unc_stream_create(index.h, C.byref(self.params), self.n_channels, self.chunk_len,
                                          self.max_chunks, C.byref(self.h)))
 
+    def set_tie_order(self, mode):
+        """1: the reference's unstable child sort reproduced (exact-ties kernel), 0: emission order (default)."""
+        N.check(self.L.unc_stream_set_tie_order(self.h, int(mode)))
+
     def step(self, descs, n, flat, res):
         flat = np.ascontiguousarray(flat)
         rc = self.L.unc_stream_step(self.h, descs, n, flat.ctypes.data, res)

@@ -262,7 +262,7 @@ def test_small_max_paths_overflow_semantics(U):
     _compare_with_oracle(U, "g200k", 64, 3000, seed=13, params_mod=mod)
 
 
-def _stream_vs_oracle(U, prefix, sigs, n_channels, chunk_len, max_chunks=1000000, params_mod=None):
+def _stream_vs_oracle(U, prefix, sigs, n_channels, chunk_len, max_chunks=1000000, params_mod=None, tie_order=0):
     import orclib
     idx = U.Index(prefix, device=0)
     p = U.default_params()
@@ -271,6 +271,8 @@ def _stream_vs_oracle(U, prefix, sigs, n_channels, chunk_len, max_chunks=1000000
         params_mod(p)
         params_mod(O.params)
     sm = U.StreamMapper(idx, n_channels, chunk_len, max_chunks=max_chunks, params=p)
+    if tie_order:
+        sm.set_tie_order(tie_order)
     res = sm.map_reads(sigs)
     sm.close()
     states = []

@@ -301,3 +301,21 @@ def test_exact_ties_kernel_equals_the_unmodified_reference_on_every_golden_read(
             assert [U.paf_key(r) for r in recs] == [orclib.paf_tuple(w) for w in want]
         bm.close()
         idx.close()
+
+
+def test_stream_with_exact_ties(U):
+    """unc_stream_set_tie_order(1) -> k2_map_stream_exact against the streaming oracle in pdqsort mode."""
+    import orclib
+    import synth
+    import synthdata
+    import test_gpu_parity as TG
+    prefix, g = synthdata.get_index("g200k")
+    sig, _ = synth.reads(g, 12, 6000, seed=15, frac_random=0.3)
+    sigs = [sig[i][:6000 - 53 * i] for i in range(12)]
+    lib = orclib.orc()
+    lib.orc_set_child_sort(1)
+    try:
+        st = TG._stream_vs_oracle(U, prefix, sigs, 4, 450, tie_order=1)
+    finally:
+        lib.orc_set_child_sort(0)
+    assert (2, 0) in st

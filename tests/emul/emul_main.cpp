@@ -72,8 +72,9 @@ extern "C" void emu_tie_stats(unsigned long *out, int reset) {
 }
 static void cta_entry(void *a) {
     CtaArgs *w = (CtaArgs *) a;
-    if (g_tie_order) unc_k2_cta_main<true>(*w->ix, *w->p, *w->B, *w->W, w->sh);
-    else unc_k2_cta_main<false>(*w->ix, *w->p, *w->B, *w->W, w->sh);
+    if (g_tie_order) unc_k2_cta_main<true, true>(*w->ix, *w->p, *w->B, *w->W, w->sh);             // k2_map_exact
+    else if (w->B->flags_in) unc_k2_cta_main<false, true>(*w->ix, *w->p, *w->B, *w->W, w->sh);      // k2_map_ord
+    else unc_k2_cta_main<false, false>(*w->ix, *w->p, *w->B, *w->W, w->sh);                         // k2_map
 }
 
 // events (optional, n_reads x stride) / normed (optional) are filled like unc_events_batch.

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) k1_norm(DevBatch B, DevParams p) {
 // Persistent CTA-per-read mapper.  Each CTA stages the pore model, the 1024 k-mer FM ranges
 // and the thresholds in shared memory, then pulls reads from a global queue; the K2_WARPS warps
 // of the CTA cooperate on every event of the read (chained scans through shared memory).
-#define K2_MAP_KERNEL(NAME, EXACT)                                                                                          \
+#define K2_MAP_KERNEL(NAME, EXACT, FLAGS)                                                                                       \
     __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)                                                             \
     NAME(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t hist_stride, size_t ckey_stride,     \
          size_t cks_stride, size_t elist_stride, size_t order_stride, size_t rlist_stride, size_t clu_stride,              \
@@ -94,11 +94,14 @@ __global__ void __launch_bounds__(128) k1_norm(DevBatch B, DevParams p) {
         W.dir = W0.dir + slot * dir_stride;                                                                                \
         W.max_blocks = W0.max_blocks;                                                                                      \
         W.rl_cap = W0.rl_cap;                                                                                              \
-        unc_k2_cta_main<EXACT>(ix, p, B, W, sh);                                                                           \
+        unc_k2_cta_main<EXACT, FLAGS>(ix, p, B, W, sh);                                                                    \
     }
-K2_MAP_KERNEL(k2_map, false)
+K2_MAP_KERNEL(k2_map, false, false)
+// ordered mode (unc_map_batch_ordered): per-read sources_added_ words in and out (kept out of k2_map, whose code is
+// the build that was measured)
+K2_MAP_KERNEL(k2_map_ord, false, true)
 // the exact-ties kernel (unc_pool_set_tie_order): the same mapper with the reference's unstable child sort run serially
-K2_MAP_KERNEL(k2_map_exact, true)
+K2_MAP_KERNEL(k2_map_exact, true, true)
 
 // ordered mode: per read the 1024-bit mask of the k-mers that pass the first event's fresh-source tests
 // (block = read, thread = k-mer; word k>>5, bit k&31 = the ballot of warp k>>5)
@@ -571,6 +574,7 @@ static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, co
             CUDA_TRY(cudaMalloc(&P->d_flags_in, (size_t) P->max_reads * 128));
             CUDA_TRY(cudaMalloc(&P->d_flags_out, (size_t) P->max_reads * 128));
             CUDA_TRY(cudaMalloc(&P->d_cand, (size_t) P->max_reads * 128));
+            CUDA_TRY(cudaFuncSetAttribute(k2_map_ord, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
         }
         CUDA_TRY(cudaMemcpyAsync(P->d_flags_in, h_flags_in, (size_t) n * 128, cudaMemcpyHostToDevice, s));
         B.flags_in = P->d_flags_in;
@@ -586,6 +590,10 @@ static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, co
         k2_map_exact<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->hist_stride, P->ckey_stride,
                                                        P->cks_stride, P->elist_stride, P->order_stride, P->rlist_stride,
                                                        P->clu_stride, P->dir_stride);
+    else if (h_flags_in)
+        k2_map_ord<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->hist_stride, P->ckey_stride,
+                                                     P->cks_stride, P->elist_stride, P->order_stride, P->rlist_stride,
+                                                     P->clu_stride, P->dir_stride);
     else
         k2_map<<<grid, K2_THREADS, P->smem, s>>>(P->idx->ix, P->dp, B, P->W, P->paths_stride, P->hist_stride, P->ckey_stride, P->cks_stride,
                                                  P->elist_stride, P->order_stride, P->rlist_stride, P->clu_stride, P->dir_stride);

@@ -1082,7 +1082,9 @@ UNC_DEV u32 k2_grab_chunk(K2Shared *sh) {
 #define K2_NEXT_CHUNK(c) ((c) + nwk)
 #endif
 
-template <bool STREAM, bool EXACT>
+// FLAGS: the sources_added_ words are an input / output of the read (ordered mode, streaming): keep what the previous
+// event left, so that an event that is discarded because the read mapped one event earlier leaves no trace in them
+template <bool STREAM, bool EXACT, bool FLAGS>
 UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
                             K2Shared *sh, u32 r, u32 n_first, u32 n_limit, u32 *epoch_io) {
     const int lane = w_lane();
@@ -1118,7 +1120,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         PT_MARK(7)
 
         // ---- A. pore-model probabilities (reference src/mapper.cpp:443-445)
-        if (wt < 32u) sh->flags_prev[wt] = sh->flags[wt];               // what the read ends with if this event is discarded
+        if (FLAGS && wt < 32u) sh->flags_prev[wt] = sh->flags[wt];      // what the read ends with if this event is discarded
         for (u32 k = wt; k < UNC_NKMER; k += nwt)
             sh->probs[k] = unc_match_prob(event, d_ldg(ix.lv_mean + k), d_ldg(ix.lv_var2 + k), d_ldg(ix.lognorm + k));
         c_sync_sub(1, (int) nwt);
@@ -2008,7 +2010,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
         pend_sources = nn - nc;
         const u32 v = event_i > n_first ? *(volatile u32 *) &sh->verdict[(event_i - 1u) & 1u] : 0u;
         if (v) {                                                      // event_i's work is discarded: the Mapper returned
-            if (wt < 32u) sh->flags[wt] = sh->flags_prev[wt];         // after event_i - 1 (reference src/mapper.cpp:633-651)
+            if (FLAGS && wt < 32u) sh->flags[wt] = sh->flags_prev[wt];   // after event_i - 1 (reference src/mapper.cpp:633-651)
             break;
         }
         n_children += pend_children; n_sources += pend_sources;
@@ -2041,7 +2043,7 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
 
 // One read mapped by one CTA.  reference src/mapper.cpp:188-200 (map_read); with STREAM, one map_chunk's
 // worth of events of a read in progress (:381-431), resumed from and saved to the channel's DevMapState.
-template <bool STREAM, bool EXACT>
+template <bool STREAM, bool EXACT, bool FLAGS>
 UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
                              K2Shared *sh, u32 r, u32 *epoch_io) {
     const u32 tid = (u32) c_tid();
@@ -2052,7 +2054,7 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
         if (ms->started) n_first = ms->event_i;
         if (tid < 32) sh->flags[tid] = ms->flags[tid];
     } else {
-        if (tid < 32) sh->flags[tid] = B.flags_in ? B.flags_in[(size_t) r * 32 + tid] : 0u;
+        if (tid < 32) sh->flags[tid] = (FLAGS && B.flags_in) ? B.flags_in[(size_t) r * 32 + tid] : 0u;
     }
     const u32 n_limit = n_first + n_ev < p.max_events ? n_first + n_ev : (n_first < p.max_events ? p.max_events : n_first);
     if (tid == 0) {
@@ -2079,7 +2081,7 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
     for (u32 b = tid; b < K2_RB * K2_MAXSEG; b += (u32) c_nthreads()) sh->hist_next[b] = 0;
     c_sync();
 #ifdef K2_TRK_INLINE
-    unc_k2_workers<STREAM, EXACT>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
+    unc_k2_workers<STREAM, EXACT, FLAGS>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
     c_sync();
     if (tid == 0) {
         Tracker t1;
@@ -2099,11 +2101,11 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
     }
 #else
     if (tid < 32) unc_k2_tracker<STREAM>(ix, p, B, W, sh, r, n_first, n_limit);
-    else unc_k2_workers<STREAM, EXACT>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
+    else unc_k2_workers<STREAM, EXACT, FLAGS>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
 #endif
     c_sync();
     if (STREAM && tid < 32) B.mstate[B.chan[r]].flags[tid] = sh->flags[tid];
-    if (!STREAM && B.flags_out && tid < 32) B.flags_out[(size_t) r * 32 + tid] = sh->flags[tid];
+    if (!STREAM && FLAGS && B.flags_out && tid < 32) B.flags_out[(size_t) r * 32 + tid] = sh->flags[tid];
 }
 
 // Ordered mode (unc_ordered_logic.hpp): would k-mer k get a fresh source at read r's FIRST event if its
@@ -2138,7 +2140,7 @@ UNC_DEV DevWork unc_work_slot(const DevWork &W0, const DevWorkStrides &S, size_t
 // Persistent CTA body: stage the tables, then pull reads from the global queue.
 // Needs at least 2 warps (tracker + >= 1 worker) and at most 1 + K2_MAXSEG.
 // EXACT: the exact-ties kernel (the reference's unstable child sort reproduced, unc_pdqsort.cuh)
-template <bool EXACT = false>
+template <bool EXACT = false, bool FLAGS = false>
 UNC_DEV void unc_k2_cta_main(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W, K2Shared *sh) {
     unc_k2_cta_setup(ix, p, sh);
     u32 epoch = 0;
@@ -2148,7 +2150,7 @@ UNC_DEV void unc_k2_cta_main(const DevIndex &ix, const DevParams &p, const DevBa
         u32 r = sh->bc[0];
         c_sync();
         if (r >= B.n_reads) break;
-        unc_k2_map_read<false, EXACT>(ix, p, B, W, sh, r, &epoch);
+        unc_k2_map_read<false, EXACT, FLAGS>(ix, p, B, W, sh, r, &epoch);
     }
 }
 
@@ -2165,6 +2167,6 @@ UNC_DEV void unc_k2_cta_main_stream(const DevIndex &ix, const DevParams &p, cons
         c_sync();
         if (r >= B.n_reads) break;
         const DevWork W = unc_work_slot(W0, S, B.chan[r]);
-        unc_k2_map_read<true, EXACT>(ix, p, B, W, sh, r, &epoch);
+        unc_k2_map_read<true, EXACT, true>(ix, p, B, W, sh, r, &epoch);
     }
 }

@@ -133,3 +133,33 @@ def test_streaming_path_with_exact_ties(setup):
     finally:
         E.set_tie_order(0)
         O.lib.orc_set_child_sort(0)
+
+
+def test_both_exact_modes_in_the_combined_prototype_build():
+    """The compile-time prototypes of the mapper (no tracker warp, lean extension loop, ...: DESIGN.md section 7) keep the
+    ordered-mode flag handling and the exact-ties sort working -- whichever of them becomes the shipped configuration."""
+    import synth
+    import synthdata
+    flags = ("-DK2_TRK_INLINE", "-DK2_LEAN_B", "-DK2_PAR_E", "-DK2_SCAN2", "-DK2_PF2", "-DK2_DFUSE")
+    prefix, g = synthdata.get_index("g200k")
+    E, O = emulib.Emu(prefix, extra_flags=flags, tag="_all"), orclib.Oracle(prefix)
+    E.params.max_paths = O.params.max_paths = 300
+    sig, _ = synth.reads(g, 40, 2000, seed=21, frac_random=0.4)
+    sigs = [np.ascontiguousarray(sig[i], np.float32) for i in (5, 6, 0, 1)]
+    flat = np.concatenate(sigs)
+    lens = np.full(4, 2000, np.uint32)
+    offs = (np.arange(4, dtype=np.uint64) * 2000).astype(np.uint64)
+    O.lib.orc_set_child_sort(1)
+    try:
+        E.set_tie_order(1)
+        want = O.map_reads_one_mapper(flat, offs, lens)
+        recs, carry, n_re, _ = E.map_ordered(sigs, n_warps=5)
+        for i in range(4):
+            assert (emulib.paf_tuple(recs[i]), _counts(recs[i])) == (orclib.paf_tuple(want[i]), _counts(want[i])), i
+        prev = np.zeros(32, np.uint32)
+        for s in sigs:
+            _, prev = O.map_read_flags(s, prev)
+        assert np.array_equal(carry, prev) and n_re >= 1
+    finally:
+        E.L.emu_set_tie_order(0)
+        O.lib.orc_set_child_sort(0)

@@ -34,6 +34,7 @@
 #include <cmath>
 #include <chrono>
 #include <cassert>
+#include "pdqsort.h"
 #include <climits>
 #include <utility>
 #include <exception>
@@ -270,6 +271,32 @@ void ref_self_align_copy(uint64_t *offsets, uint64_t *values) {
         for (u64 x : g_self_align[i]) values[o++] = x;
     }
     offsets[g_self_align.size()] = o;
+}
+
+// pdqsort itself -- the vendored submods/pdqsort/pdqsort.h, the call of src/mapper.cpp:531 -- over 16-byte sort keys under
+// the comparison of PathBuffer's operator< (src/mapper.cpp:866-871 with Range's, src/range.cpp:112-119).  A user-defined
+// comparison on a non-arithmetic type takes the header's non-branchless code path, as PathBuffer does.  Pins
+// uncalled_b200/csrc/unc_pdqsort.cuh (and the oracle's restatement) to the real header on arbitrary arrays, including the
+// patterns that drive it into its heapsort fallback, which mapping data never does.
+struct RefSortKey { uint32_t start, end; float prob; uint32_t tag; };
+void ref_pdqsort_keys(RefSortKey *k, uint32_t n) {
+    pdqsort(k, k + n, [](const RefSortKey &a, const RefSortKey &b) {
+        const bool range_lt = a.start < b.start || (a.start == b.start && a.end < b.end);
+        const bool range_eq = a.start == b.start && a.end == b.end;
+        return range_lt || (range_eq && a.prob < b.prob);
+    });
+}
+
+// pdqsort's fallback after log2(n) highly unbalanced partitions (pdqsort.h:464-468): libstdc++'s make_heap + sort_heap.
+// Mapping data never gets there, so the restatement of that routine is pinned on its own.
+void ref_heapsort_keys(RefSortKey *k, uint32_t n) {
+    auto lt = [](const RefSortKey &a, const RefSortKey &b) {
+        const bool range_lt = a.start < b.start || (a.start == b.start && a.end < b.end);
+        const bool range_eq = a.start == b.start && a.end == b.end;
+        return range_lt || (range_eq && a.prob < b.prob);
+    };
+    std::make_heap(k, k + n, lt);
+    std::sort_heap(k, k + n, lt);
 }
 
 // bwa index build exactly as `uncalled index` performs it (bwa_idx_build).

@@ -187,6 +187,15 @@ int emu_map_batch_ordered(void *pidx, const unc_params *prm, const unc_read_desc
     return unc_ordered_map(n_reads, prm->max_paths, carry, out, n_remapped, n_rounds, map_subset);
 }
 
+// unc_pdq_sort (unc_pdqsort.cuh) on its own: keys = n x (fm_start, fm_end, seed_prob bits, tag); returns 0 if the
+// scratch stack sufficed
+unsigned long emu_pdq_heapsorts(void) { return g_emu_pdq_heapsorts; }
+void emu_pdq_heapsort(uint4 *keys, uint32_t n) { pq_heapsort(keys, 0, (int) n); }
+int emu_pdq_sort(uint4 *keys, uint32_t n, uint32_t stack_cap) {
+    std::vector<uint4> stack(stack_cap ? stack_cap : 1);
+    return unc_pdq_sort(keys, n, stack.data(), stack_cap) ? 0 : 1;
+}
+
 void emu_match_probs(void *pidx, float event, float *out) {
     EmuIndex *e = (EmuIndex *) pidx;
     for (u32 k = 0; k < 1024; k++) out[k] = unc_match_prob(event, e->h.lv_mean[k], e->h.lv_var2[k], e->h.lognorm[k]);

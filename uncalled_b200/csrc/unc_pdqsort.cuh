@@ -14,6 +14,9 @@
 // stack in global memory (the right part is pushed, the left one continued, so the order of work is the header's).
 #pragma once
 
+#ifdef UNC_EMUL
+static unsigned long g_emu_pdq_heapsorts;
+#endif
 // operator< on sort keys: x = fm_start, y = fm_end, z = seed_prob bits (src/mapper.cpp:866-871, Range::operator<)
 UNC_DEV bool pq_less(const uint4 &a, const uint4 &b) {
     if (a.x != b.x) return a.x < b.x;
@@ -116,6 +119,9 @@ UNC_DEV void pq_heap_adjust(uint4 *a, int f, int hole, int len, const uint4 valu
 }
 // std::make_heap + std::sort_heap: pdqsort's fallback after log2(n) highly unbalanced partitions (pdqsort.h:464-468)
 UNC_DEV void pq_heapsort(uint4 *a, int b, int e) {
+#ifdef UNC_EMUL
+    g_emu_pdq_heapsorts++;       // test statistics (emulator builds only): was the fallback exercised?
+#endif
     const int len = e - b;
     if (len < 2) return;
     for (int parent = (len - 2) / 2;; parent--) {

@@ -191,6 +191,7 @@ int emu_map_batch_ordered(void *pidx, const unc_params *prm, const unc_read_desc
 // scratch stack sufficed
 unsigned long emu_pdq_heapsorts(void) { return g_emu_pdq_heapsorts; }
 void emu_pdq_heapsort(uint4 *keys, uint32_t n) { pq_heapsort(keys, 0, (int) n); }
+int emu_pdq_min_bad(int reset) { int v = g_emu_pdq_min_bad; if (reset) g_emu_pdq_min_bad = 1 << 30; return v; }
 int emu_pdq_sort(uint4 *keys, uint32_t n, uint32_t stack_cap) {
     std::vector<uint4> stack(stack_cap ? stack_cap : 1);
     return unc_pdq_sort(keys, n, stack.data(), stack_cap) ? 0 : 1;

@@ -16,6 +16,7 @@
 
 #ifdef UNC_EMUL
 static unsigned long g_emu_pdq_heapsorts;
+static int g_emu_pdq_min_bad = 1 << 30;       // smallest budget of unbalanced partitions seen (test search objective)
 #endif
 // operator< on sort keys: x = fm_start, y = fm_end, z = seed_prob bits (src/mapper.cpp:866-871, Range::operator<)
 UNC_DEV bool pq_less(const uint4 &a, const uint4 &b) {
@@ -173,6 +174,9 @@ UNC_DEV_NOINLINE bool unc_pdq_sort(uint4 *a, u32 n, uint4 *stack, u32 cap) {
             const int l_size = pivot_pos - begin, r_size = end - (pivot_pos + 1);
             const bool highly_unbalanced = l_size < size / 8 || r_size < size / 8;
             if (highly_unbalanced) {
+#ifdef UNC_EMUL
+                if (bad_allowed - 1 < g_emu_pdq_min_bad) g_emu_pdq_min_bad = bad_allowed - 1;
+#endif
                 if (--bad_allowed == 0) {
                     pq_heapsort(a, begin, end);
                     done = true;

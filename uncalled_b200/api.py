@@ -457,6 +457,8 @@ class RealtimePool:
             p.max_events, p.max_paths, p.seed_len = conf.max_events, conf.max_paths, conf.seed_len
             p.bp_per_sec, p.sample_rate = conf.bp_per_sec, conf.sample_rate
             backend = S.StreamMapper(index, conf.num_channels, self.chunk_len, max_chunks=conf.max_chunks, params=p)
+            if conf.exact_ties:
+                backend.set_tie_order(1)
         self.backend, self.index = backend, index
         n = conf.num_channels
         self._pending = [None] * n          # chunk waiting for the next update()

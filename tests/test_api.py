@@ -140,6 +140,22 @@ class _EmuBackend:
         return out
 
 
+class _EmuBackendOrdered(_EmuBackend):
+    """... with unc_map_batch_ordered's counterpart (the product's ordered-mode host logic over the emulated kernels)."""
+
+    def map_ordered(self, flat, descs, carry=None, on_device=False):
+        self.calls.append(len(descs))
+        assert all(int(d["dtype"]) == int(descs[0]["dtype"]) for d in descs)
+        sigs = []
+        for d in descs:
+            s = flat[int(d["offset"]):int(d["offset"]) + int(d["n_samples"])]
+            if int(d["dtype"]) == 1:        # the emulator entry takes pA: calibrate as src/read_buffer.cpp:239-242
+                rng, off, dig = (np.float32(d[k]) for k in ("cal_range", "cal_offset", "cal_digit"))
+                s = (rng * (s.view(np.uint16).astype(np.float32) + off) / dig).astype(np.float32)
+            sigs.append(np.ascontiguousarray(s, np.float32))
+        return self.E.map_ordered(sigs, carry=carry)
+
+
 class _EmuBackendTwoCall(_EmuBackend):
     """The same with the submit()/wait() form of the GPU mapper, so that MapPool pipelines its batches."""
 
@@ -270,3 +286,38 @@ def test_ordered_conf_keeps_input_order_and_threads_the_carry():
     assert c2.ordered == 1 and c3.ordered == 0
     _, c4, _ = cli.load_conf(["map", "--exact-ties", "--ordered", "idx", "reads.fast5"])
     assert (c4.exact_ties, c4.ordered, c3.exact_ties) == (1, 1, 0)
+
+
+def test_uncalled_map_ordered_from_fast5_files_on_the_emulated_device(tmp_path):
+    """`uncalled map --ordered -c 1` end to end without a GPU: reads come out in file order, batch after batch through the
+    ordered-mode entry point with the flag carry threaded, and the example read gives the reference's golden `-c 1` line
+    (the reference's own `-t 1` run is ordered by construction)."""
+    import emulib
+    import orclib
+    from uncalled_b200.api import Conf, MapPool
+    prefix = orclib.materialise_example_index(str(tmp_path))
+    O = orclib.Oracle(prefix)
+
+    class _Idx:
+        seqs = [(O.lib.orc_seq_name(O.idx, i).decode(), int(O.lib.orc_seq_len(O.idx, i))) for i in range(O.lib.orc_n_seqs(O.idx))]
+    f5dir = os.path.join(ROOT, "tests", "golden", "fast5")
+    ex, multi = os.path.join(f5dir, "example_single.fast5"), os.path.join(f5dir, "multi_many_reads.fast5")
+    gold = json.load(open(os.path.join(f5dir, "golden.json")))
+    file_order = list(dict.fromkeys(r["id"] for r in gold if r["file"] == "multi_many_reads.fast5"))   # two rows per read
+    E = emulib.Emu(prefix)
+    conf = Conf()
+    conf.batch_reads, conf.max_chunks, conf.ordered = 32, 1, 1
+    be = _EmuBackendOrdered(E)
+    pool = MapPool(conf, backend=be, index=_Idx)
+    pool.add_fast5(multi)
+    pool.add_fast5(ex)
+    out = []
+    while pool.running():
+        out += pool.update()
+    pool.stop()
+    ids = [p.fields()[0] for p in out]
+    assert ids[-1] == "f41a60f7-de4a-4b17-9f54-387e52d60b65" and len(ids) == len(file_order) + 1
+    assert sorted(ids[:-1]) == sorted(file_order)
+    assert ids[:-1] == file_order                          # input order, not longest-first
+    assert [p.line().rsplit("\t", 1)[0] for p in out if p.is_mapped()] == [GOLD["max_chunks_1"]["line"]]
+    assert sum(be.calls) == len(ids) and max(be.calls) <= 32

@@ -20,6 +20,10 @@
  *   unc_map_batch       MapPool::update -> MapperThread::run -> Mapper::new_read/map_read
  *                                                      src/map_pool.cpp:45-69,130-158,
  *                                                      src/mapper.cpp:188-207
+ *   unc_map_batch_ordered  one MapperThread's loop with its long-lived Mapper (`-t 1`)
+ *                                                      src/map_pool.cpp:104-158, src/mapper.cpp:88,216-246
+ *   unc_pool_set_tie_order / unc_stream_set_tie_order
+ *                       pdqsort(next_paths_...) as it is  src/mapper.cpp:531,866-871, submods/pdqsort/pdqsort.h
  *   unc_events_batch    EventDetector::get_means + Normalizer::set_signal/pop
  *                                                      src/event_detector.cpp:133-145,
  *                                                      src/normalizer.cpp:31-44,114-129

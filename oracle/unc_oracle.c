@@ -1541,7 +1541,10 @@ static void chan_map_read(stream_chan_t *c, const float *raw, uint32_t n, uint32
         if (chunk_processed && norm->is_empty) {
             if (next_chunk < n_chunks) {
                 /* Mapper::add_chunk (:281-299) -> ReadBuffer::add_chunk (:271-284) */
-                if (chunk_count >= max_chunks) { done = 1; }      /* chunks_maxed: set_failed */
+                if (chunk_count >= max_chunks) {                  /* chunks_maxed: set_failed; the next map_chunk's */
+                    done = 1;                                     /* first test adds set_ended when event_i_ is at max_events */
+                    if (mp->event_i >= p->max_events) is_ended = 1;
+                }
                 else { cur = next_chunk++; chunk_count++; raw_len += chunk_len; chunk_processed = 0; }
             } else reset_req = 1;
         }

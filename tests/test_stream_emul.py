@@ -105,3 +105,18 @@ def test_bench_stream_job_logic(g200k):
     assert calls == ["s", "b", "b"] and ms > 0
     assert 2 <= counters["chunks"] <= 6 and counters["steps"] >= 2 and counters["bytes"] >= counters["chunks"] * 450 * 4
     assert len(res) == 2 and all(r is not None and r[0] in (2, 3) for r in res)
+
+
+@pytest.mark.parametrize("seed,length", [(334826472, 2996), (297309666, 5699)])
+def test_max_events_reached_exactly_at_the_end_of_a_chunk(g200k, seed, length):
+    """event_i_ gets to max_events with the chunk's last event: map_chunk notices only at its next call, and the fully
+    mapped chunk lets try_add_chunk hand over one more chunk first -- it goes through the detector and the normaliser,
+    none of its events is mapped, then the read fails as ended (3 chunks, not 2; found by tools/emul_stream_sweep.py and
+    confirmed with the reference's own Mapper: oracle/_ref gives (0, 151, 255, 150), 3 chunks, ended, for the first)."""
+    prefix, g = g200k
+    E, O = emulib.Emu(prefix), orclib.Oracle(prefix)
+    E.params.max_events = O.params.max_events = 150
+    E.params.max_paths = O.params.max_paths = 77
+    sig, _ = synth.reads(g, 3, length, seed=seed, frac_random=0.35)
+    st = _check(E, O, [sig[i] for i in range(3)], 1, 450)
+    assert (3, 1) in st

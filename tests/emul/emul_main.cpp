@@ -19,6 +19,8 @@ struct EmuIndex {
     DevIndex ix;
     std::vector<uint2> kmer_range;
     std::vector<float> lv_mean, lv_var2, lognorm;
+    std::vector<uint4> occ2;
+    uint16_t krank[1024], rkmer[1024];
 };
 
 extern "C" {
@@ -43,6 +45,14 @@ void *emu_index_load(const char *prefix, const char *preset, const char *model_t
     e->kmer_range.resize(1024);
     for (u32 k = 0; k < 1024; k++) e->kmer_range[k] = unc_kmer_range_compute(ix, k);
     ix.kmer_range = e->kmer_range.data();
+    {   // the GPU-side Occ layout and the k-mer rank tables, as unc_index_load builds them
+        const u32 n_blk = (u32) (h.bwt.size() / 16) * 2u;
+        e->occ2.resize((size_t) n_blk * 2);
+        for (u32 j = 0; j < n_blk; j++) unc_occ2_build_block(ix.bwt, j, e->occ2.data());
+        ix.occ2 = e->occ2.data();
+        hix_kmer_ranks(e->kmer_range.data(), e->krank, e->rkmer);
+        ix.krank = e->krank; ix.rkmer = e->rkmer;
+    }
     return e;
 }
 
@@ -156,7 +166,7 @@ static int emu_map_batch_impl(void *pidx, const unc_params *prm, const unc_read_
     W.paths = paths.data(); W.hist = hist.data(); W.wlist = wlist.data(); W.ckey = ckey.data(); W.cks = cks.data(); W.elist = elist.data(); W.order = order.data(); W.rlist = rlist.data();
     W.clu = clu.data(); W.dir = dir.data();
     W.max_blocks = max_blocks; W.rl_cap = rl_cap;
-    K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((maxp + 31) / 32) * K2_DYN_PER_CHUNK);
+    K2Shared *sh = (K2Shared *) calloc(1, K2_SMEM_BYTES(maxp));
     CtaArgs a = {&e->ix, &dp, &B, &W, sh};
     emu_run_cta(cta_entry, &a, 32 * (n_warps > 0 ? n_warps : 8));   // one persistent CTA maps the whole batch
     free(sh);
@@ -304,7 +314,7 @@ int emu_stream_step(void *pst, const unc_chunk_desc *chunks, uint32_t n, const v
             unc_stream_chunk(B, T->dp, S, r, isnew[r]);
             tot[r] = T->sig[chan[r]].evdt.total_events;
         }
-        K2Shared *sh = (K2Shared *) calloc(1, sizeof(K2Shared) + 16 + (size_t) ((T->dp.max_paths + 31) / 32) * K2_DYN_PER_CHUNK);
+        K2Shared *sh = (K2Shared *) calloc(1, K2_SMEM_BYTES(T->dp.max_paths));
         StreamCtaArgs a = {&T->e->ix, &T->dp, &B, &T->W, &T->S, sh};
         emu_run_cta(stream_cta_entry, &a, 32 * (n_warps > 0 ? n_warps : 8));
         free(sh);

@@ -41,6 +41,12 @@ __global__ void k_kmer_ranges(DevIndex ix, uint2 *out) {
     if (k < UNC_NKMER) out[k] = unc_kmer_range_compute(ix, k);
 }
 
+// the GPU-side Occ layout (unc_k2v2.cuh): one 32-byte block per 64 BWT positions
+__global__ void k_occ2_build(const uint4 *bwt, uint4 *out, u32 n_blk) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_blk) unc_occ2_build_block(bwt, j, out);
+}
+
 // bwt_sa(k) for every row: turns the mapper's <=31-step LF walk per seed into one load.
 __global__ void k_sa_expand(DevIndex ix, u32 *out, u32 n_rows) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,7 +166,7 @@ struct unc_index {
     int device = 0;
     std::vector<uint2> kmer_range;  // host copy
     void *d_bwt = nullptr, *d_sa = nullptr, *d_kr = nullptr, *d_model = nullptr, *d_thresh = nullptr;
-    void *d_seq_off = nullptr, *d_seq_len = nullptr, *d_sa_full = nullptr;
+    void *d_seq_off = nullptr, *d_seq_len = nullptr, *d_sa_full = nullptr, *d_occ2 = nullptr, *d_krank = nullptr;
     size_t device_bytes = 0;
 };
 
@@ -306,6 +312,7 @@ int unc_index_load(const char *bwa_prefix, const char *preset, const char *model
     for (int i = 0; i < 5; i++) ix.L2[i] = (u32) h.L2[i];
     ix.start_bits = 64 - __builtin_clzll(h.seq_len ? h.seq_len : 1);
     ix.sa_full = nullptr;
+    ix.occ2 = nullptr; ix.krank = nullptr; ix.rkmer = nullptr;
     {   // expanded suffix array (4 bytes per FM row); skipped when device memory is short
         size_t free_b = 0, total_b = 0;
         const size_t need = ((size_t) h.seq_len + 1) * 4;
@@ -321,6 +328,21 @@ int unc_index_load(const char *bwa_prefix, const char *preset, const char *model
     x->kmer_range.resize(1024);
     cudaError_t e = cudaMemcpy(x->kmer_range.data(), x->d_kr, 1024 * sizeof(uint2), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { unc_index_free(x); return fail(UNC_E_CUDA, std::string("k_kmer_ranges: ") + cudaGetErrorString(e)); }
+    {   // GPU-side layouts of the mapper's second structure: 32-byte Occ blocks, k-mer rank tables
+        const u32 n_blk = (u32) (h.bwt.size() / 16) * 2u;
+        if (cudaMalloc(&x->d_occ2, (size_t) n_blk * 32 + 64) != cudaSuccess) { unc_index_free(x); return fail(UNC_E_CUDA, "cudaMalloc occ2"); }
+        cudaMemset((char *) x->d_occ2 + (size_t) n_blk * 32, 0, 64);
+        k_occ2_build<<<(n_blk + 255) / 256, 256>>>(ix.bwt, (uint4 *) x->d_occ2, n_blk);
+        uint16_t ranks[2048];
+        hix_kmer_ranks(x->kmer_range.data(), ranks, ranks + 1024);
+        if (cudaMalloc(&x->d_krank, sizeof(ranks)) != cudaSuccess ||
+            cudaMemcpy(x->d_krank, ranks, sizeof(ranks), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaDeviceSynchronize() != cudaSuccess) { unc_index_free(x); return fail(UNC_E_CUDA, "occ2 / k-mer rank tables"); }
+        ix.occ2 = (const uint4 *) x->d_occ2;
+        ix.krank = (const u16 *) x->d_krank;
+        ix.rkmer = ix.krank + 1024;
+        x->device_bytes += (size_t) n_blk * 32 + 64 + sizeof(ranks);
+    }
     *out = x;
     return UNC_OK;
 }
@@ -358,7 +380,7 @@ int unc_index_thresholds(const unc_index *x, float out[64]) {
 void unc_index_free(unc_index *x) {
     if (!x) return;
     cudaFree(x->d_bwt); cudaFree(x->d_sa); cudaFree(x->d_kr); cudaFree(x->d_model); cudaFree(x->d_thresh);
-    cudaFree(x->d_seq_off); cudaFree(x->d_seq_len); cudaFree(x->d_sa_full);
+    cudaFree(x->d_seq_off); cudaFree(x->d_seq_len); cudaFree(x->d_sa_full); cudaFree(x->d_occ2); cudaFree(x->d_krank);
     delete x;
 }
 
@@ -382,7 +404,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     for (int i = 0; i < 6; i++) PT(cudaEventCreate(&P->ev[i]));
     cudaDeviceProp prop;
     PT(cudaGetDeviceProperties(&prop, idx->device));
-    P->smem = sizeof(K2Shared) + 16 + (size_t) ((prm->max_paths + 31) / 32) * K2_DYN_PER_CHUNK;
+    P->smem = K2_SMEM_BYTES(prm->max_paths);
     PT(cudaFuncSetAttribute(k2_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
     int per_sm = 0;
     PT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_map, K2_THREADS, P->smem));

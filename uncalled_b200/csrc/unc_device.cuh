@@ -40,6 +40,10 @@ struct DevIndex {
     u32 primary, seq_len;
     u32 L2[5];
     u32 start_bits;        // bits needed to represent seq_len (radix-sort passes)
+    // GPU-side layouts derived at index load (unc_k2v2.cuh):
+    const uint4 *occ2;     // 32-byte Occ blocks: 4 x u32 counts before the block + 64 two-bit BWT symbols
+    const u16 *krank;      // k-mer -> position of its FM range among the 1024 (ranges are disjoint and ordered)
+    const u16 *rkmer;      // the inverse
 };
 
 // L2[c] through selects: a dynamically indexed member would force the whole kernel-parameter
@@ -795,6 +799,8 @@ UNC_DEV_NOINLINE u32 unc_k2_track_event(uint4 *clu, uint4 *dir, u32 max_blocks, 
 #define K2_PF2_C
 #endif
 #define K2_MAXCH 1024u     /* chunks of 32 paths (max_paths <= 32767) */
+#define K2_CH_SLOTS 160u   /* 32 parents x at most 5 children */
+#define K2_V2_DYN_BYTES (16u + K2_MAXSEG * (K2_CH_SLOTS * 8u + K2_CH_SLOTS))   /* per-warp child staging of unc_k2v2.cuh */
 #define K2_RBITS 8u        /* radix digit width of the child sort */
 #define K2_RB 256u
 #ifndef K2_MAXSEG
@@ -811,11 +817,21 @@ UNC_DEV_NOINLINE u32 unc_k2_track_event(uint4 *clu, uint4 *dir, u32 max_blocks, 
 #else
 #define K2_DYN_PER_CHUNK (24u + K2_DYN_FUSE)
 #endif
+/* dynamic shared memory of a mapper CTA: the struct, the per-chunk arrays, the per-warp child staging */
+#define K2_SMEM_BYTES(maxp) (sizeof(K2Shared) + 16 + (size_t) (((maxp) + 31) / 32) * K2_DYN_PER_CHUNK + 32 + K2_V2_DYN_BYTES)
 struct K2Tables {
     uint2 kmer_range[UNC_NKMER];
     float thresh[64];
 };
-struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
+struct K2V2 {              // second worker structure (unc_k2v2.cuh)
+    u16 krank[UNC_NKMER], rkmer[UNC_NKMER];
+    u32 kcnt[UNC_NKMER];   // per k-mer bucket: children counted during the extension, then the scatter cursor (= bucket end)
+    u32 koff[UNC_NKMER];   // bucket start in the sorted key array
+    u32 kagg[UNC_NKMER];   // (gap sources | child seeds << 16) of the bucket, then their exclusive prefix
+    u32 fresh_mask[32], fresh_before[32];   // fresh-source plan per 32-k-mer word
+    u32 grab[2];           // bucket hand-out counters (sort pass, emit pass)
+};
+struct K2Shared {          // per CTA
     K2Tables tb;
     float probs[UNC_NKMER];
     u32 flags[32];         // sources_added_ bits (reference src/mapper.cpp:88), kmer k -> word k>>5
@@ -830,6 +846,8 @@ struct K2Shared {          // per CTA (~29 KB + 24 B per 32 max_paths)
     u64 *pre;              // D2 look-back prefix words: (epoch<<2 | state) << 32 | sources | seeds<<16
     u32 *bcnt, *ecnt;      // children per chunk (then exclusive prefix), ended paths per chunk
     u32 *cmb;              // K2_LEAN_B: five ballot words per chunk (which fixed child slots are filled)
+    K2V2 v2;
+    unsigned char *v2_stage;   // K2V2_STAGE_BYTES per worker warp (dynamic shared memory)
 #ifdef K2_DFUSE
     u64 *agg2;             // the D1 aggregates as two epoch-tagged words per chunk, published inside D2
 #endif
@@ -918,12 +936,15 @@ UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *
         base = (char *) ((((size_t) base) + 7) & ~(size_t) 7);
         sh->agg2 = (u64 *) base;                       // n_slots * 16 bytes
 #endif
+        sh->v2_stage = (unsigned char *) sh->pre + (size_t) n_slots * K2_DYN_PER_CHUNK + 8;
+        sh->v2_stage = (unsigned char *) ((((size_t) sh->v2_stage) + 15) & ~(size_t) 15);
     }
     c_sync();
     for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) {
         sh->tb.kmer_range[k] = ix.kmer_range[k];
     }
     for (u32 k = (u32) c_tid(); k < 64; k += (u32) c_nthreads()) sh->tb.thresh[k] = ix.thresh[k];
+    for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) { sh->v2.krank[k] = ix.krank[k]; sh->v2.rkmer[k] = ix.rkmer[k]; }
     for (u32 c = (u32) c_tid(); c < n_slots; c += (u32) c_nthreads()) sh->pre[c] = 0;
 #ifdef K2_DFUSE
     for (u32 c = (u32) c_tid(); c < 2u * n_slots; c += (u32) c_nthreads()) sh->agg2[c] = 0;   // tag 0 = never published (epochs start at 1)
@@ -1050,7 +1071,6 @@ UNC_DEV long long pt_clock() { long long v; asm volatile("mov.u64 %0, %%clock64;
 // ("sparse") slots, a small scan + key compaction restores the emission order afterwards; phase D
 // resolves the k-mer-run carry from per-chunk aggregates and the source/seed positions with a
 // decoupled look-back prefix sum.
-#define K2_CH_SLOTS 160u    /* 32 parents x at most 5 children */
 
 UNC_DEV u32 k2_pre_pack(u32 epoch, u32 state) { return (epoch << 2) | state; }
 
@@ -2041,6 +2061,8 @@ UNC_DEV void unc_k2_workers(const DevIndex &ix, const DevParams &p, const DevBat
     c_sync();                                                         // Y: final barrier
 }
 
+#include "unc_k2v2.cuh"
+
 // One read mapped by one CTA.  reference src/mapper.cpp:188-200 (map_read); with STREAM, one map_chunk's
 // worth of events of a read in progress (:381-431), resumed from and saved to the channel's DevMapState.
 template <bool STREAM, bool EXACT, bool FLAGS>
@@ -2101,6 +2123,9 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
     }
 #else
     if (tid < 32) unc_k2_tracker<STREAM>(ix, p, B, W, sh, r, n_first, n_limit);
+#ifndef K2_V1
+    else if (!EXACT) unc_k2_workers_v2<STREAM, FLAGS>(ix, p, B, W, sh, r, n_first, n_limit);
+#endif
     else unc_k2_workers<STREAM, EXACT, FLAGS>(ix, p, B, W, sh, r, n_first, n_limit, epoch_io);
 #endif
     c_sync();

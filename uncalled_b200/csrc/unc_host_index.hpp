@@ -5,6 +5,7 @@
 // File formats: reference submods/bwa/bwt.c:421-462 (.bwt/.sa), submods/bwa/bntseq.c:97-135
 // (.ann), src/mapper.cpp:123-157 (.uncl); pore model: src/pore_model.hpp:48-103.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -154,4 +155,20 @@ static inline bool hix_load(HostIndex &h, const std::string &prefix, const std::
     free(line);
     fclose(fp);
     return true;
+}
+
+// k-mer -> position of its FM range among the 1024 ranges ordered by start (the ranges of distinct k-mers are
+// disjoint, so children sorted by fm_start are grouped by k-mer in this order; unc_k2v2.cuh); ties (absent
+// k-mers have an empty range that starts where a present one does) are broken by the k-mer code.
+template <typename R>
+static inline void hix_kmer_ranks(const R *kmer_range, uint16_t krank[1024], uint16_t rkmer[1024]) {
+    std::vector<uint32_t> ord(1024);
+    for (uint32_t k = 0; k < 1024; k++) ord[k] = k;
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+        if (kmer_range[a].x != kmer_range[b].x) return kmer_range[a].x < kmer_range[b].x;
+        const bool ea = kmer_range[a].x > kmer_range[a].y, eb = kmer_range[b].x > kmer_range[b].y;   // empty ranges first
+        if (ea != eb) return ea;
+        return a < b;
+    });
+    for (uint32_t i = 0; i < 1024; i++) { rkmer[i] = (uint16_t) ord[i]; krank[ord[i]] = (uint16_t) i; }
 }

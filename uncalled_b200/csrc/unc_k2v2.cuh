@@ -1,0 +1,730 @@
+// unc_k2v2.cuh -- the mapper's worker warps, second structure (included by unc_device.cuh).
+//
+// Same results as unc_k2_workers (the first structure, kept for the exact-ties kernel): the reference's
+// map_next (src/mapper.cpp:433-663) minus the seed clustering, which the tracker warp runs.  What changed
+// is how an event's work is laid out on the CTA:
+//
+//   * FM index: a GPU-side Occ layout (DevIndex::occ2: 32-byte blocks = 4 x u32 cumulative counts + 64
+//     two-bit BWT symbols, one sector per row) and ONE popcount sweep that yields Occ(k, c) for all four
+//     bases, so that the warp executes the same instructions whichever bases its lanes want.
+//   * extension: a lane owns a PARENT while thresholds and FM ranges are computed, then a CHILD while the
+//     records are written (the chunk's children are staged in shared memory and re-dealt to the lanes), so
+//     the record-writing code runs once per 32 children instead of five times per 32 parents.
+//   * child sort: children sorted by fm_start are grouped by k-mer, and the k-mers' FM ranges are disjoint
+//     and ordered (DevIndex::krank).  So the children are counted per k-mer during the extension, scattered
+//     into k-mer buckets (one pass), and every bucket is sorted on its own by ONE warp: buckets of <= 32
+//     keys by ranking in registers, larger ones by a warp-private LSD radix sort on the bits the bucket's
+//     span needs.  No CTA-wide radix passes.
+//   * dedup / gap sources / child seeds (src/mapper.cpp:527-603) work on k-mer runs, which are now exactly
+//     the buckets: a warp walks its bucket with the run state in registers; the positions of the sources
+//     and seeds come from one prefix sum over the buckets' counts.  No per-chunk aggregates, no look-back.
+//   * 8 CTA barriers per event instead of ~20.
+#pragma once
+
+#define K2V2_STAGE_BYTES (K2_CH_SLOTS * 8u + K2_CH_SLOTS)   /* per worker warp: (start, end) + (lane | j<<5) of a chunk's children */
+
+// ---- Occ for all four bases at once ------------------------------------------------------------------
+
+// occ2 block j covers BWT positions [64j, 64j+64): counts of A,C,G,T before the block, then the 64 symbols
+// (4 x u32, 16 symbols each, first symbol in the top two bits -- the .bwt file's own packing).
+// Built from the bwa layout (submods/bwa/bwt.c:107-129: 128-position blocks of 4 x u64 counts + 8 x u32).
+UNC_DEV void unc_occ2_build_block(const uint4 *bwt, u32 j, uint4 *out) {
+    const uint4 *p = bwt + ((size_t) (j >> 1) << 2);
+    const uint4 b0 = p[0], b1 = p[1];
+    uint4 cnt = make_uint4(b0.x, b0.z, b1.x, b1.z);        // low words of the u64 counts
+    const uint4 lo = p[2], hi = p[3];
+    if (j & 1u) {
+        const u32 w[4] = {lo.x, lo.y, lo.z, lo.w};
+        for (int i = 0; i < 4; i++) {
+            const u32 h = w[i] >> 1, m = 0x55555555u;
+            const u32 c3 = (u32) d_popc(h & w[i] & m), c2 = (u32) d_popc(h & ~w[i] & m), c1 = (u32) d_popc(~h & w[i] & m);
+            cnt.x += 16u - c1 - c2 - c3; cnt.y += c1; cnt.z += c2; cnt.w += c3;
+        }
+    }
+    out[(size_t) j * 2] = cnt;
+    out[(size_t) j * 2 + 1] = (j & 1u) ? hi : lo;
+}
+
+// Occ(., c) for c = 0..3 at position p (0..63, inclusive) of an occ2 block already in registers
+UNC_DEV void unc_occ2_all(const uint4 cnt, const uint4 sym, u32 p, u32 o[4]) {
+    u32 c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const u32 w = i == 0 ? sym.x : i == 1 ? sym.y : i == 2 ? sym.z : sym.w;
+        int n = (int) p + 1 - 16 * i;                       // symbols of this word at or before p
+        n = n < 0 ? 0 : (n > 16 ? 16 : n);
+        const u32 m = n == 0 ? 0u : (0x55555555u & (0xFFFFFFFFu << (32 - 2 * n)));
+        const u32 h = w >> 1;
+        c3 += (u32) d_popc(h & w & m); c2 += (u32) d_popc(h & ~w & m); c1 += (u32) d_popc(~h & w & m);
+    }
+    o[0] = cnt.x + (p + 1u - c1 - c2 - c3); o[1] = cnt.y + c1; o[2] = cnt.z + c2; o[3] = cnt.w + c3;
+}
+
+// ---- sort keys -----------------------------------------------------------------------------------------
+// key = (fm_start, fm_end, seed_prob bits, seedable | move_count << 1 | record index << 6)
+// order: fm_start, fm_end, seed_prob, record index (= emission order) -- reference src/mapper.cpp:866-871 plus
+// the documented tie-break.  seed_prob is compared through a monotone integer image of the float so that the
+// order is total whatever the bits are (a NaN cannot make two keys claim one rank); -0 counts as +0.
+UNC_DEV u32 k2v2_fkey(u32 bits) {
+    if (bits == 0x80000000u) bits = 0u;
+    return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+}
+UNC_DEV bool k2v2_less(u32 ax, u32 ay, u32 az, u32 aw, u32 bx, u32 by, u32 bz, u32 bw) {
+    if (ax != bx) return ax < bx;
+    if (ay != by) return ay < by;
+    const u32 fa = k2v2_fkey(az), fb = k2v2_fkey(bz);
+    if (fa != fb) return fa < fb;
+    return (aw >> 6) < (bw >> 6);
+}
+
+// One k-mer bucket [o, o+n) of `keys`, n > 32, sorted by ONE warp: LSD radix on (fm_start - lo) over the bits
+// the bucket's span needs, then runs of equal fm_start ordered by (fm_end, seed_prob, record index).
+// `tmp` is the ping-pong partner of `keys` (same index range), `hist` 256 warp-private counters.
+// The sorted keys end in `keys`.
+UNC_DEV void k2v2_sort_big(uint4 *keys, uint4 *tmp, u32 o, u32 n, u32 lo, u32 span_bits, u32 *hist) {
+    const int lane = w_lane();
+    const u32 lt = w_lanemask_lt();
+    const u32 npass = (span_bits + 7u) >> 3;
+    uint4 *src = keys + o, *dst = tmp + o;
+    const u32 nch = (n + 31u) >> 5;
+    for (u32 pass = 0; pass < npass; pass++) {
+        const u32 sb = pass * 8u;
+        for (u32 b = (u32) lane; b < 256u; b += 32u) hist[b] = 0;
+        w_sync();
+        for (u32 c = 0; c < nch; c++) {
+            const u32 g = c * 32u + (u32) lane;
+            if (g < n) s_atomic_add(&hist[((src[g].x - lo) >> sb) & 255u], 1u);
+        }
+        w_sync();
+        {   // exclusive scan of the 256 counters: 8 consecutive bins per lane
+            u32 v[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { v[i] = hist[(u32) lane * 8u + (u32) i]; sum += v[i]; }
+            u32 tot, run = w_exscan(sum, &tot);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { hist[(u32) lane * 8u + (u32) i] = run; run += v[i]; }
+        }
+        w_sync();
+        for (u32 c = 0; c < nch; c++) {
+            const u32 g = c * 32u + (u32) lane;
+            const bool a = g < n;
+            uint4 k = make_uint4(0, 0, 0, 0);
+            if (a) k = src[g];
+            const u32 dg = a ? (((k.x - lo) >> sb) & 255u) : 256u + (u32) lane;   // inactive lanes: unique digit
+            const u32 peers = w_match(dg);
+            const u32 rank = (u32) d_popc(peers & lt);
+            const int leader = d_ffs(peers) - 1;
+            u32 bpos = 0;
+            if (a && lane == leader) { bpos = hist[dg]; hist[dg] = bpos + (u32) d_popc(peers); }
+            w_sync();                              // the next chunk's leaders read these counters
+            bpos = w_shfl(bpos, leader);
+            if (a) dst[bpos + rank] = k;
+        }
+        w_sync();
+        uint4 *t = src; src = dst; dst = t;
+    }
+    if (src != keys + o) {                          // odd number of passes: bring the keys home
+        for (u32 g = (u32) lane; g < n; g += 32u) dst[g] = src[g];
+        w_sync();
+        src = keys + o;
+    }
+    // runs of equal fm_start: insertion sort by the run's head lane (rare and short)
+    for (u32 c = 0; c < nch; c++) {
+        const u32 g = c * 32u + (u32) lane;
+        const bool a = g < n;
+        u32 s = 0, px = 0, nx = 0;
+        if (a) { s = src[g].x; if (g > 0) px = src[g - 1].x; if (g + 1 < n) nx = src[g + 1].x; }
+        const bool head = a && (g == 0 || px != s) && (g + 1 < n && nx == s);
+        if (head) {
+            u32 e = g + 1;
+            while (e < n && src[e].x == s) e++;
+            for (u32 i = g + 1; i < e; i++) {
+                const uint4 key = src[i];
+                u32 j = i;
+                while (j > g) {
+                    const uint4 q = src[j - 1];
+                    if (!k2v2_less(key.x, key.y, key.z, key.w, q.x, q.y, q.z, q.w)) break;
+                    src[j] = q;
+                    j--;
+                }
+                src[j] = key;
+            }
+        }
+        w_sync();
+    }
+}
+
+// What one chunk of <= 32 consecutive sorted keys of ONE k-mer bucket contributes (reference
+// src/mapper.cpp:1153-1194 of the restatement, :527-603 of the reference): lane i holds key g = g0 + i.
+struct K2V2Walk {
+    bool a, dup, begin_v, after_v, seed;
+    u32 as, ae;          // the after-source's range
+    u32 m_b, m_a, m_seed;
+};
+// cur = this lane's key, nxt = the key after it (valid iff has_next), carry_mx = max fm_end over the bucket's
+// earlier chunks (0 for the first).  Returns the chunk's max fm_end (incl. the carry) in *mx_out (uniform).
+UNC_DEV K2V2Walk k2v2_walk_chunk(const uint4 cur, const uint4 nxt, bool a, bool has_next, bool first_chunk, u32 carry_mx,
+                                 bool prob_ok, uint2 kr, u32 *mx_out) {
+    const int lane = w_lane();
+    K2V2Walk r;
+    r.a = a;
+    r.dup = has_next && nxt.x == cur.x && nxt.y == cur.y;
+    u32 mx = a ? cur.y : 0u;                          // inclusive prefix max of fm_end (one run: the bucket)
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 omx = w_shfl_up(mx, d);
+        if (lane >= d) mx = omx > mx ? omx : mx;
+    }
+    if (!first_chunk) mx = mx > carry_mx ? mx : carry_mx;
+    *mx_out = w_shfl(mx, 31);
+    r.begin_v = a && first_chunk && lane == 0 && prob_ok && kr.x <= cur.x - 1u;
+    r.as = mx + 1u;
+    r.ae = has_next ? nxt.x - 1u : kr.y;
+    r.after_v = a && !r.dup && prob_ok && r.as <= r.ae;
+    r.seed = a && !r.dup && (cur.w & 1u);
+    r.m_b = w_ballot(r.begin_v); r.m_a = w_ballot(r.after_v); r.m_seed = w_ballot(r.seed);
+    return r;
+}
+
+// the next group of 32 bucket ranks for this warp (two sweeps of 32 groups: see phase C2)
+UNC_DEV u32 k2v2_grab(u32 *counter) {
+    u32 g = 0;
+    if (w_lane() == 0) g = s_atomic_add(counter, 1u);
+    return w_shfl(g, 0);
+}
+
+template <bool STREAM, bool FLAGS>
+UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
+                               K2Shared *sh, u32 r, u32 n_first, u32 n_limit) {
+    const int lane = w_lane();
+    const u32 wt = (u32) c_tid() - 32u, nwt = (u32) c_nthreads() - 32u;   // worker thread index / count
+    const u32 ww = wt >> 5, nwk = nwt >> 5;                               // worker warp index / count
+    const K2Tables *tb = &sh->tb;
+    K2V2 *v2 = &sh->v2;
+    const u32 maxp = p.max_paths;
+    const u32 S0 = ((maxp + 31u) >> 5) * K2_CH_SLOTS;                     // record index of the first source
+    const size_t gen_recs = (size_t) S0 + maxp;
+    const float scale = B.scale[r], shift = B.shift[r];
+    const float *events = B.events + (size_t) r * B.ev_stride;
+    const float source_prob = tb->thresh[0];
+    u64 n_children = 0, n_sources = 0;                 // committed (events confirmed by the tracker)
+    u32 pend_children = 0, pend_sources = 0;           // of the event in flight
+    u32 my_blocks = 0, my_steps = 0, pend_blocks = 0, pend_steps = 0;
+    u32 prev_size = 0, gen = 0, event_i = n_first;
+    if (STREAM) {                                      // resume: the previous chunk's last generation is in the slot
+        const DevMapState *ms = B.mstate + B.chan[r];
+        if (ms->started) { prev_size = ms->prev_size; gen = ms->gen; }
+    }
+    const u32 lt = w_lanemask_lt();
+    uint2 *stage_r = (uint2 *) (sh->v2_stage + (size_t) ww * K2V2_STAGE_BYTES);
+    u8 *stage_m = (u8 *) (stage_r + K2_CH_SLOTS);
+    u32 *whist = sh->hist_cur + (size_t) ww * 256u;    // warp-private radix counters (big buckets)
+#ifdef UNC_EMUL
+    if (wt == 0 && getenv("UNC_EMU_TRACE_V2")) fprintf(stderr, "k2v2 read %u\n", r);
+#endif
+    PT_DECL
+
+    for (; event_i < n_limit; event_i++) {
+        PT_MARK(9)
+        const float event = f_add(f_mul(scale, events[event_i - n_first]), shift);
+        PT_MARK(7)
+
+        // ---- A. pore-model probabilities (reference src/mapper.cpp:443-445); clear the bucket counters
+        if (FLAGS && wt < 32u) sh->flags_prev[wt] = sh->flags[wt];      // what the read ends with if this event is discarded
+        for (u32 k = wt; k < UNC_NKMER; k += nwt) {
+            sh->probs[k] = unc_match_prob(event, d_ldg(ix.lv_mean + k), d_ldg(ix.lv_var2 + k), d_ldg(ix.lognorm + k));
+            v2->kcnt[k] = 0; v2->kagg[k] = 0;
+        }
+        if (wt == 0) { v2->grab[0] = 0; v2->grab[1] = 0; }
+        c_sync_sub(1, (int) nwt);
+        PT_MARK(0)
+
+        uint4 *prev = W.paths + (size_t) gen * gen_recs * 2, *next = W.paths + (size_t) (gen ^ 1u) * gen_recs * 2;
+        uint2 *hist_e = W.hist + (size_t) (event_i % UNC_NGEN) * gen_recs;
+        const u32 *oprev = W.order + (size_t) gen * maxp;
+        u32 *onext = W.order + (size_t) (gen ^ 1u) * maxp;
+        uint4 *ckA = W.ckey, *ckB = W.ckey + maxp, *cks = W.cks;
+        uint2 *rlist = W.rlist + (size_t) (event_i & 1u) * W.rl_cap;
+
+        // ---- B. extend every previous path (reference src/mapper.cpp:455-524): chunk c of 32 parents writes its
+        //      children, in emission order, to records / keys [c*160, c*160+count)
+        const u32 nch_prev = (prev_size + 31u) >> 5;
+        {
+            u32 oi_n = UNC_INVALID; uint4 q0_n = make_uint4(0, 0, 0, 0); uint2 q1_n = make_uint2(0, 0);   // q1: (seed_prob, C)
+            if (ww < nch_prev) {
+                const u32 pi = ww * 32u + (u32) lane;
+                if (pi < prev_size) oi_n = oprev[pi];
+                if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = *(const uint2 *) (pr + 1); }
+            }
+            for (u32 c = ww; c < nch_prev; c += nwk) {
+                const u32 oi = oi_n;
+                const uint4 q0 = q0_n; const uint2 q1 = q1_n;
+                const bool valid = !(oi & UNC_INVALID);
+                if (c + nwk < nch_prev) {                       // software prefetch of the next chunk's order entry + record
+                    const u32 pi = (c + nwk) * 32u + (u32) lane;
+                    oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
+                    if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = *(const uint2 *) (pr + 1); }
+                }
+                // -- parent per lane: thresholds, wanted bases, FM ranges of the four neighbours
+                const u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
+                const u32 moves = q0.w & UNC_PATH_MASK, sa_checked = q0.w >> 31;
+                u32 want = 0, cmask = 0;
+                if (valid) {
+                    const float thr = tb->thresh[32 + d_clz(en - st + 1u)];
+                    if (stays < p.max_consec_stay && sh->probs[kmer] >= thr) cmask = 1u;
+#pragma unroll
+                    for (u32 b = 0; b < 4; b++)
+                        if (!(sh->probs[((kmer << 2) & UNC_KMASK) | b] < thr)) want |= 1u << b;   // `if (prob < thresh) continue;`
+                }
+                if (cmask) stage_r[(u32) lane * 5u] = make_uint2(st, en);
+                if (want) {
+                    // BwaIndex::get_neighbor (reference src/bwa_index.hpp:158-162) over bwt_2occ (submods/bwa/bwt.c:132-163)
+                    // for all four bases: ns = L2[c] + Occ(start-1, c) + 1, ne = L2[c] + Occ(end, c)
+                    const u32 k0 = st - 1u, l0 = en;
+                    const u32 kk = k0 - (k0 >= ix.primary), ll = l0 - (l0 >= ix.primary);
+                    const bool l_is_end = (l0 == ix.seq_len);
+                    const uint4 *bk = ix.occ2 + ((size_t) (kk >> 6) << 1);
+                    const uint4 kc = d_ldg(bk), ks = d_ldg(bk + 1);
+                    uint4 lc = kc, ls = ks;
+                    if (!l_is_end && (ll >> 6) != (kk >> 6)) {
+                        const uint4 *bl = ix.occ2 + ((size_t) (ll >> 6) << 1);
+                        lc = d_ldg(bl); ls = d_ldg(bl + 1);
+                    }
+                    pend_blocks += 1u + ((!l_is_end && (ll >> 7) != (kk >> 7)) ? 1u : 0u);   // in the reference's 128-row blocks
+                    u32 ok[4], ol[4];
+                    unc_occ2_all(kc, ks, kk & 63u, ok);
+                    unc_occ2_all(lc, ls, ll & 63u, ol);
+                    if (l_is_end) { ol[0] = ix.L2[1] - ix.L2[0]; ol[1] = ix.L2[2] - ix.L2[1]; ol[2] = ix.L2[3] - ix.L2[2]; ol[3] = ix.L2[4] - ix.L2[3]; }
+                    // a valid child's range goes to the parent's fixed staging slot lane*5 + 1 + base at once
+#pragma unroll
+                    for (u32 b = 0; b < 4; b++) {
+                        const u32 nsb = ix.L2[b] + ok[b] + 1u, neb = ix.L2[b] + ol[b];
+                        if (((want >> b) & 1u) && nsb <= neb) { cmask |= 2u << b; stage_r[(u32) lane * 5u + 1u + b] = make_uint2(nsb, neb); }
+                    }
+                }
+                const u32 cc = (u32) d_popc(cmask);
+                u32 total;
+                const u32 off = w_exscan(cc, &total);
+                // a childless, not yet SA-checked path may end here with seeds
+                // (reference src/mapper.cpp:513-519 -> update_seeds(path, true), is_seed_valid :842-863)
+                bool ended = false;
+                const u32 mc = (u32) d_popc(moves);
+                if (valid && cc == 0 && !sa_checked) {
+                    const u32 len = en - st + 1u;
+                    ended = plen == UNC_SEED_LEN && u2f(q1.x) >= p.min_seed_prob &&
+                            ((len == 1 && (moves & 1u) && (float) ((plen - mc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f)) ||
+                             (len <= p.max_rep_copy && mc >= p.min_rep_len));
+                }
+                const u32 m_ended = w_ballot(ended);
+                if (ended) W.elist[(size_t) c * 32 + (u32) d_popc(m_ended & lt)] = make_uint4(st, en, mc, off);
+                if (lane == 0) { sh->bcnt[c] = total; sh->ecnt[c] = (u32) d_popc(m_ended); }
+                // -- the chunk's children in emission order: (parent lane | child index << 5), then one child per lane
+                {
+                    u32 pos = off;
+#pragma unroll
+                    for (u32 j = 0; j < 5; j++)
+                        if ((cmask >> j) & 1u) { stage_m[pos] = (u8) ((u32) lane | (j << 5)); pos++; }
+                }
+                w_sync();
+                for (u32 t0 = 0; t0 < total; t0 += 32u) {
+                    const u32 t = t0 + (u32) lane;
+                    const bool act = t < total;
+                    u32 m = 0; uint2 rg = make_uint2(0, 0);
+                    if (act) { m = stage_m[t]; rg = stage_r[(m & 31u) * 5u + (m >> 5)]; }
+                    const int L = (int) (m & 31u);
+                    const u32 j = m >> 5;                                         // 0 = stay, 1..4 = move with base j-1
+                    const u32 pz = w_shfl(q0.z, L), pw = w_shfl(q0.w, L), pC = w_shfl(q1.y, L), poi = w_shfl(oi, L);
+                    if (act) {
+                        const u32 pk = pz & UNC_KMASK, ppl = (pz >> 16) & 0xFFu, pst = (pz >> 24) & 0xFFu;
+                        const u32 ckm = j == 0 ? pk : (((pk << 2) & UNC_KMASK) | (j - 1u));
+                        const float pb = sh->probs[ckm];
+                        const u32 move = j > 0 ? 1u : 0u;
+                        const u32 nlen = ppl + (ppl < UNC_SEED_LEN ? 1u : 0u);
+                        u32 nmoves = (((pw & UNC_PATH_MASK) << 1) | move) & UNC_PATH_MASK;
+                        const u32 nstays = move ? 0u : pst + 1u;
+                        const float newC = f_add(u2f(pC), pb);
+                        const u32 ci = c * K2_CH_SLOTS + t;
+                        float sp = 0.0f;
+                        bool seedable = false;
+                        if (ppl == UNC_SEED_LEN) {
+                            // seed_prob = (C(e) - C(e-22)) / 22 needs the ancestor 22 generations back: deferred
+                            nmoves |= UNC_PATH_TAIL;
+                            W.wlist[s_atomic_add(&sh->wl_cnt, 1u)] = make_uint4(ci, poi, f2u(newC), nmoves);
+                        } else {
+                            sp = f_div(newC, (float) nlen);
+                            // is_seed_valid(path_ended = false) of the child (reference src/mapper.cpp:842-863)
+                            const u32 cmc = (u32) d_popc(nmoves);
+                            seedable = nlen == UNC_SEED_LEN && sp >= p.min_seed_prob && rg.x == rg.y && (nmoves & 1u) &&
+                                       (float) ((nlen - cmc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f);
+                        }
+                        const u32 spb = f2u(sp);
+                        next[(size_t) ci * 2] = make_uint4(rg.x, rg.y, ckm | (nlen << 16) | (nstays << 24), nmoves | (pw & 0x80000000u));
+                        next[(size_t) ci * 2 + 1] = make_uint4(spb, f2u(newC), 0u, 0u);
+                        hist_e[ci] = make_uint2(f2u(newC), poi);
+                        cks[ci] = make_uint4(rg.x, rg.y, spb, ckm | (seedable ? 1u << 10 : 0u) | ((u32) d_popc(nmoves) << 11));
+                        s_atomic_add(&v2->kcnt[v2->krank[ckm]], 1u);
+                    }
+                }
+                w_sync();                                       // the staging area is rewritten by the next chunk
+            }
+        }
+        c_sync_sub(1, (int) nwt);
+        PT_MARK(1)
+        // ---- B1 + B2a + B2b, concurrently.  Worker warp 0: exclusive scan of the chunk counts (restores the
+        //      global emission order and gives the buffer cap, reference src/mapper.cpp:480-482,507-509,521-523:
+        //      extension stops when max_paths children exist), then the seed rows of ended paths.  The last worker
+        //      warp: bucket offsets.  The others: deferred seed_prob of children whose parent was already seed_len
+        //      long -- C(e-22) is the C of the ancestor 22 generations back (21 parent hops from the parent).
+        if (ww == 0) {
+            u32 carry = 0;
+            for (u32 i0 = 0; i0 < nch_prev; i0 += 32) {
+                u32 v = i0 + (u32) lane < nch_prev ? sh->bcnt[i0 + lane] : 0u, t;
+                u32 ex = w_exscan(v, &t);
+                if (i0 + (u32) lane < nch_prev) sh->bcnt[i0 + lane] = carry + ex;
+                carry += t;
+            }
+            if (lane == 0) sh->bc[2] = carry;
+            w_sync();
+            // seed rows of ended paths, in parent order.  A parent counts only if the buffer was not yet full when
+            // the sequential scan reached it (children before it < max_paths).
+            u32 rows = 0;
+            for (u32 i0 = 0; i0 < nch_prev; i0 += 32) {
+                u32 ec = i0 + (u32) lane < nch_prev ? sh->ecnt[i0 + lane] : 0u;
+                u32 m = w_ballot(ec != 0);
+                while (m) {
+                    int l = d_ffs(m) - 1;
+                    m &= m - 1;
+                    u32 c = i0 + (u32) l, n = w_shfl(ec, l), base = sh->bcnt[c];
+                    for (u32 j = 0; j < n; j++) {
+                        uint4 e = W.elist[(size_t) c * 32 + j];
+                        if (base + e.w < maxp) {
+                            u32 len = e.y - e.x + 1u;
+                            if (rows + len <= W.rl_cap) {
+                                for (u32 i = (u32) lane; i < len; i += 32) rlist[rows + i] = make_uint2(e.x + i, e.z | 0x100u);
+                            } else sh->wk_overflow = 1;
+                            rows += len;
+                        }
+                    }
+                }
+            }
+            if (lane == 0) sh->bc[3] = rows;
+        }
+        if (ww == nwk - 1u) {
+            // bucket offsets, assuming the buffer cap does not cut this event's children (else redone below)
+            u32 carry = 0;
+            for (u32 i0 = 0; i0 < UNC_NKMER; i0 += 32) {
+                const u32 v = v2->kcnt[i0 + (u32) lane];
+                u32 t;
+                const u32 ex = w_exscan(v, &t);
+                v2->koff[i0 + (u32) lane] = carry + ex;
+                v2->kcnt[i0 + (u32) lane] = carry + ex;          // becomes the scatter cursor
+                carry += t;
+            }
+        }
+        if (ww != 0 || nwk == 1) {
+            const u32 bt = nwk == 1 ? wt : wt - 32u, nbt = nwk == 1 ? nwt : nwt - 32u;
+            const u32 nwl = *(volatile u32 *) &sh->wl_cnt;
+            for (u32 i = bt; i < nwl; i += nbt) {
+                uint4 w = W.wlist[i];
+                u32 idx = w.y;
+                for (u32 j = 1; j <= 21; j++)
+                    idx = W.hist[(size_t) ((event_i + UNC_NGEN - j) % UNC_NGEN) * gen_recs + idx].y;
+                float oldC = u2f(W.hist[(size_t) ((event_i + UNC_NGEN - 22u) % UNC_NGEN) * gen_recs + idx].x);
+                float sp = f_div(f_sub(u2f(w.z), oldC), 22.0f);
+                uint4 key = cks[w.x];
+                u32 cmc = (u32) d_popc(w.w);
+                bool seedable = sp >= p.min_seed_prob && key.x == key.y && (w.w & 1u) &&
+                                (float) ((UNC_SEED_LEN - cmc) & 0xFFu) <= f_mul(p.max_stay_frac, 22.0f);
+                key.z = f2u(sp);
+                if (seedable) key.w |= 1u << 10;
+                cks[w.x] = key;
+                next[(size_t) w.x * 2 + 1].x = f2u(sp);
+            }
+        }
+        c_sync_sub(1, (int) nwt);
+        if (wt == 0) sh->wl_cnt = 0;
+        const u32 nc_total = nch_prev ? sh->bc[2] : 0u;
+        const u32 nc = nc_total < maxp ? nc_total : maxp;
+        if (nc_total > maxp) {
+            // the cap cut the children: count again, only those that made it (chunk order = emission order)
+            for (u32 k = wt; k < UNC_NKMER; k += nwt) v2->kcnt[k] = 0;
+            c_sync_sub(1, (int) nwt);
+            for (u32 c = ww; c < nch_prev; c += nwk) {
+                const u32 base = sh->bcnt[c];
+                if (base >= nc) break;
+                const u32 end = c + 1 < nch_prev ? sh->bcnt[c + 1] : nc_total;
+                for (u32 i = (u32) lane; base + i < end && base + i < nc; i += 32)
+                    s_atomic_add(&v2->kcnt[v2->krank[cks[(size_t) c * K2_CH_SLOTS + i].w & UNC_KMASK]], 1u);
+            }
+            c_sync_sub(1, (int) nwt);
+            if (ww == 0) {
+                u32 carry = 0;
+                for (u32 i0 = 0; i0 < UNC_NKMER; i0 += 32) {
+                    const u32 v = v2->kcnt[i0 + (u32) lane];
+                    u32 t;
+                    const u32 ex = w_exscan(v, &t);
+                    v2->koff[i0 + (u32) lane] = carry + ex;
+                    v2->kcnt[i0 + (u32) lane] = carry + ex;
+                    carry += t;
+                }
+            }
+            c_sync_sub(1, (int) nwt);
+        }
+        PT_MARK(10)
+        u32 n_rows = sh->bc[3];
+        if (n_rows > W.rl_cap) n_rows = W.rl_cap;
+        const u32 n_ended_rows = n_rows;
+        pend_children = nc;
+
+        if (nc > 0) {
+            // ---- C1. scatter the keys into their k-mer buckets (any order inside a bucket: the record index is
+            //          part of the key); each warp takes the chunks it extended
+            for (u32 c = ww; c < nch_prev; c += nwk) {
+                const u32 base = sh->bcnt[c];
+                if (base >= nc) break;                              // later chunks lie beyond the max_paths cut
+                const u32 end = c + 1 < nch_prev ? sh->bcnt[c + 1] : nc_total;
+                for (u32 i = (u32) lane; base + i < end && base + i < nc; i += 32) {
+                    const u32 ci = c * K2_CH_SLOTS + i;
+                    uint4 key = cks[ci];
+                    const u32 bk = v2->krank[key.w & UNC_KMASK];
+                    key.w = ((key.w >> 10) & 0x3Fu) | (ci << 6);    // seedable | move_count << 1 | record index << 6
+                    ckA[s_atomic_add(&v2->kcnt[bk], 1u)] = key;
+                }
+            }
+            c_sync_sub(1, (int) nwt);
+            PT_MARK(2)
+
+            // ---- C2. sort every bucket (one warp each) and count what its dedup walk will emit.  Buckets are handed
+            //          out 32 ranks at a time, the large ones (> 32 keys) first.
+            for (;;) {
+                const u32 gi = k2v2_grab(&v2->grab[0]);
+                if (gi >= 64u) break;
+                const bool big_sweep = gi < 32u;
+                const u32 rk = (gi & 31u) * 32u + (u32) lane;
+                const u32 bo = v2->koff[rk], bn = v2->kcnt[rk] - bo;
+                u32 todo = w_ballot(big_sweep ? bn > 32u : (bn > 0 && bn <= 32u));
+                while (todo) {
+                    const int l = d_ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const u32 o = w_shfl(bo, l), n = w_shfl(bn, l), rank = (gi & 31u) * 32u + (u32) l;
+                    const u32 kmer = v2->rkmer[rank];
+                    const uint2 kr = tb->kmer_range[kmer];
+                    const bool prob_ok = sh->probs[kmer] >= source_prob;
+                    u32 n_src = 0, n_seed = 0;
+                    if (n <= 32u) {
+                        // rank every key among the bucket's keys, deal the keys out in sorted order
+                        const bool a = (u32) lane < n;
+                        uint4 k = make_uint4(0, 0, 0, 0);
+                        if (a) k = ckA[o + (u32) lane];
+                        u32 rnk = 0;
+                        for (u32 j = 0; j < n; j++) {
+                            const u32 jx = w_shfl(k.x, (int) j), jy = w_shfl(k.y, (int) j), jz = w_shfl(k.z, (int) j), jw = w_shfl(k.w, (int) j);
+                            if (k2v2_less(jx, jy, jz, jw, k.x, k.y, k.z, k.w)) rnk++;
+                        }
+                        uint4 *sst = (uint4 *) stage_r;
+                        if (a) sst[rnk] = k;
+                        w_sync();
+                        uint4 cur = make_uint4(0, 0, 0, 0);
+                        if (a) { cur = sst[lane]; ckA[o + (u32) lane] = cur; }
+                        w_sync();
+                        uint4 nxt;
+                        nxt.x = w_shfl_down(cur.x, 1); nxt.y = w_shfl_down(cur.y, 1); nxt.z = 0; nxt.w = 0;
+                        u32 mxo;
+                        const K2V2Walk wk = k2v2_walk_chunk(cur, nxt, a, (u32) lane + 1u < n, true, 0u, prob_ok, kr, &mxo);
+                        n_src = (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
+                        n_seed = (u32) d_popc(wk.m_seed);
+                    } else {
+                        // span of the bucket's fm_start values -> radix passes
+                        u32 lo = 0xFFFFFFFFu, hi = 0;
+                        for (u32 g = (u32) lane; g < n; g += 32u) { const u32 x = ckA[o + g].x; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+                        hi = w_max(hi);
+                        lo = ~w_max(~lo);
+                        k2v2_sort_big(ckA, ckB, o, n, lo, 32u - (u32) d_clz(hi - lo), whist);
+                        u32 carry_mx = 0;
+                        for (u32 g0 = 0; g0 < n; g0 += 32u) {
+                            const u32 g = g0 + (u32) lane;
+                            const bool a = g < n, has_next = g + 1u < n;
+                            uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+                            if (a) cur = ckA[o + g];
+                            if (has_next) nxt = ckA[o + g + 1u];
+                            u32 mxo;
+                            const K2V2Walk wk = k2v2_walk_chunk(cur, nxt, a, has_next, g0 == 0, carry_mx, prob_ok, kr, &mxo);
+                            carry_mx = mxo;
+                            n_src += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
+                            n_seed += (u32) d_popc(wk.m_seed);
+                        }
+                    }
+                    if (lane == 0) v2->kagg[rank] = n_src | (n_seed << 16);
+                }
+            }
+            c_sync_sub(1, (int) nwt);
+            PT_MARK(3)
+        }
+
+        // ---- D0 + S1, concurrently.  Worker warp 0: prefix sum of the buckets' (sources, seeds), the sources_added_
+        //      flags the run starts set (reference src/mapper.cpp:560-562), and the plan of the fresh sources
+        //      (reference :605-624).  The other warps: suffix-array look-ups of the ended paths' seed rows
+        //      (reference :673-681: sa_end = fmi.size() - fmi.sa(s)).
+        if (ww == 0) {
+            u32 carry = 0;                                   // sources | seeds << 16 before the group
+            for (u32 i0 = 0; i0 < UNC_NKMER; i0 += 32) {
+                const u32 rk = i0 + (u32) lane;
+                const u32 v = v2->kagg[rk];
+                u32 ts, tq;
+                const u32 es = w_exscan(v & 0xFFFFu, &ts), eq = w_exscan(v >> 16, &tq);
+                const u32 sb = (carry & 0xFFFFu) + es, qb = (carry >> 16) + eq;
+                v2->kagg[rk] = sb | (qb << 16);
+                // sources_added_[kmer] is set at a run start while the buffer is not full
+                const bool nonempty = nc > 0 && v2->kcnt[rk] != v2->koff[rk];
+                if (nonempty) {
+                    const u32 kmer = v2->rkmer[rk];
+                    if (sh->probs[kmer] >= source_prob && nc + sb < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
+                }
+                carry = ((carry & 0xFFFFu) + ts) | (((carry >> 16) + tq) << 16);
+            }
+            w_sync();
+            const u32 tot_src = carry & 0xFFFFu;
+            const u32 ns_added = nc + tot_src > maxp ? maxp - nc : tot_src;
+            const u32 nn0 = nc + ns_added;
+            u32 my_mask = 0;
+            for (u32 j = 0; j < 32; j++) {
+                const u32 k = j * 32 + (u32) lane;
+                const uint2 kr = tb->kmer_range[k];
+                const bool add = !((sh->flags[j] >> lane) & 1u) && sh->probs[k] >= source_prob && kr.x <= kr.y;
+                const u32 m_add = w_ballot(add);
+                if ((u32) lane == j) my_mask = m_add;
+            }
+            u32 tot_add;
+            const u32 my_pre = w_exscan((u32) d_popc(my_mask), &tot_add);
+            v2->fresh_mask[lane] = my_mask;
+            v2->fresh_before[lane] = nn0 + my_pre;           // fill level when the serial walk reaches word `lane`
+            if (lane == 0) {
+                sh->bc[1] = nn0 + tot_add < maxp ? nn0 + tot_add : maxp;
+                sh->bc[6] = carry;
+            }
+        }
+        if (ww != 0 || nwk == 1) {
+            const u32 bt = nwk == 1 ? wt : wt - 32u, nbt = nwk == 1 ? nwt : nwt - 32u;
+            for (u32 i = bt; i < n_ended_rows; i += nbt) {
+                uint2 e = rlist[i];
+                e.x = ix.seq_len - unc_sa_lookup(ix, e.x, &pend_steps, &pend_blocks);
+                rlist[i] = e;
+            }
+        }
+        c_sync_sub(1, (int) nwt);
+        PT_MARK(11)
+        const u32 fin = sh->bc[6];
+        const u32 n_child_seeds = nc > 0 ? fin >> 16 : 0u;
+        n_rows = n_ended_rows + n_child_seeds;
+        if (n_rows > W.rl_cap) n_rows = W.rl_cap;
+
+        // ---- D1. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603): every bucket is one k-mer run
+        if (nc > 0) {
+            for (;;) {
+                const u32 gi = k2v2_grab(&v2->grab[1]);
+                if (gi >= 64u) break;
+                const bool big_sweep = gi < 32u;
+                const u32 rk = (gi & 31u) * 32u + (u32) lane;
+                const u32 bo = v2->koff[rk], bn = v2->kcnt[rk] - bo, bpre = v2->kagg[rk];
+                u32 todo = w_ballot(big_sweep ? bn > 32u : (bn > 0 && bn <= 32u));
+                while (todo) {
+                    const int l = d_ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const u32 o = w_shfl(bo, l), n = w_shfl(bn, l), pre = w_shfl(bpre, l), rank = (gi & 31u) * 32u + (u32) l;
+                    const u32 kmer = v2->rkmer[rank];
+                    const uint2 kr = tb->kmer_range[kmer];
+                    const float pkm = sh->probs[kmer];
+                    const bool prob_ok = pkm >= source_prob;
+                    u32 src_before = pre & 0xFFFFu, seeds_before = pre >> 16;
+                    u32 carry_mx = 0;
+                    for (u32 g0 = 0; g0 < n; g0 += 32u) {
+                        const u32 g = g0 + (u32) lane;
+                        const bool a = g < n, has_next = g + 1u < n;
+                        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+                        if (a) cur = ckA[o + g];
+                        if (n <= 32u) { nxt.x = w_shfl_down(cur.x, 1); nxt.y = w_shfl_down(cur.y, 1); }
+                        else if (has_next) nxt = ckA[o + g + 1u];
+                        u32 mxo;
+                        const K2V2Walk wk = k2v2_walk_chunk(cur, nxt, a, has_next, g0 == 0, carry_mx, prob_ok, kr, &mxo);
+                        carry_mx = mxo;
+                        const u32 sidx = src_before + (u32) d_popc(wk.m_b & lt) + (u32) d_popc(wk.m_a & lt);   // sources before this element
+                        if (wk.begin_v && nc + sidx < maxp) {
+                            write_source(next, hist_e, S0 + nc + sidx, kr.x, cur.x - 1u, kmer, pkm);
+                            onext[nc + sidx] = S0 + nc + sidx;
+                        }
+                        const u32 sidx2 = sidx + (wk.begin_v ? 1u : 0u);
+                        if (wk.after_v && nc + sidx2 < maxp) {
+                            write_source(next, hist_e, S0 + nc + sidx2, wk.as, wk.ae, kmer, pkm);
+                            onext[nc + sidx2] = S0 + nc + sidx2;
+                        }
+                        const u32 rec = cur.w >> 6;
+                        if (a) onext[o + g] = rec | (wk.dup ? UNC_INVALID : 0u);
+                        // update_seeds(child, false): unique, move-headed, full-length, probable paths
+                        if (wk.seed) {
+                            d_atomic_or(&((u32 *) (next + (size_t) rec * 2))[3], 0x80000000u);   // sa_checked_
+                            const u32 ri = n_ended_rows + seeds_before + (u32) d_popc(wk.m_seed & lt);
+                            if (ri < W.rl_cap)
+                                rlist[ri] = make_uint2(ix.seq_len - unc_sa_lookup(ix, cur.x, &pend_steps, &pend_blocks), (cur.w >> 1) & 0x1Fu);
+                            else sh->wk_overflow = 1;
+                        }
+                        src_before += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
+                        seeds_before += (u32) d_popc(wk.m_seed);
+                    }
+                }
+            }
+        }
+        // ---- E. fresh sources for every sufficiently probable k-mer without one (reference src/mapper.cpp:605-624):
+        //      word j (32 k-mers) by warp j % nwk, positions and the buffer-full cut from worker warp 0's plan
+        for (u32 j = ww; j < 32; j += nwk) {
+            const u32 before = v2->fresh_before[j];
+            if (before >= maxp) continue;                         // never visited: its flags stay as they are
+            const u32 k = j * 32 + (u32) lane;
+            const u32 fw = sh->flags[j];
+            u32 m_add = v2->fresh_mask[j];
+            const u32 room = maxp - before;
+            u32 visited = 0xFFFFFFFFu;
+            if ((u32) d_popc(m_add) >= room) {
+                // the room-th add fills the buffer; k-mers after it are never visited
+                u32 mm = m_add;
+                for (u32 q = 1; q < room; q++) mm &= mm - 1;
+                int last = d_ffs(mm) - 1;
+                visited = last == 31 ? 0xFFFFFFFFu : ((2u << last) - 1u);
+                m_add &= visited;
+            }
+            const u32 rank = (u32) d_popc(m_add & lt);
+            if ((m_add >> lane) & 1u) {
+                const uint2 kr = tb->kmer_range[k];
+                write_source(next, hist_e, S0 + before + rank, kr.x, kr.y, k, sh->probs[k]);
+                onext[before + rank] = S0 + before + rank;
+            }
+            w_sync();
+            if (lane == 0) sh->flags[j] = fw & ~visited;
+        }
+        if (wt == 0) *(volatile u32 *) &sh->n_rows[event_i & 1u] = n_rows;
+        PT_MARK(5)
+        // ---- hand the event's seeds to the tracker; learn the outcome of the previous event
+        c_sync();                                                     // X_e
+        PT_MARK(6)
+        const u32 nn = sh->bc[1];
+        pend_sources = nn - nc;
+        const u32 v = event_i > n_first ? *(volatile u32 *) &sh->verdict[(event_i - 1u) & 1u] : 0u;
+        if (v) {                                                      // event_i's work is discarded: the Mapper returned
+            if (FLAGS && wt < 32u) sh->flags[wt] = sh->flags_prev[wt];   // after event_i - 1 (reference src/mapper.cpp:633-651)
+            break;
+        }
+        n_children += pend_children; n_sources += pend_sources;
+        my_blocks += pend_blocks; my_steps += pend_steps;
+        pend_children = pend_sources = pend_blocks = pend_steps = 0;
+        prev_size = nn;
+        gen ^= 1u;
+        PT_MARK(8)
+    }
+    if (STREAM && wt == 0) { DevMapState *ms = B.mstate + B.chan[r]; ms->prev_size = prev_size; ms->gen = gen; }
+    PT_FLUSH(B, r)
+    for (int d = 16; d > 0; d >>= 1) { my_blocks += w_shfl(my_blocks, lane ^ d); my_steps += w_shfl(my_steps, lane ^ d); }
+    if (lane == 0) { s_atomic_add(&sh->cnt_blocks, my_blocks); s_atomic_add(&sh->cnt_steps, my_steps); }
+    if (wt == 0) {
+        sh->tot_children[0] = (u32) n_children; sh->tot_children[1] = (u32) (n_children >> 32);
+        sh->tot_sources[0] = (u32) n_sources; sh->tot_sources[1] = (u32) (n_sources >> 32);
+    }
+    c_sync();                                                         // Y: final barrier
+}

@@ -93,7 +93,7 @@ int unc_stream_create(const unc_index *idx, const unc_params *prm, uint32_t n_ch
     ST(cudaStreamCreateWithFlags(&T->stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
     ST(cudaGetDeviceProperties(&prop, idx->device));
-    T->smem = sizeof(K2Shared) + 16 + (size_t) ((prm->max_paths + 31) / 32) * K2_DYN_PER_CHUNK;
+    T->smem = K2_SMEM_BYTES(prm->max_paths);
     ST(cudaFuncSetAttribute(k2_map_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T->smem));
     int per_sm = 0;
     ST(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_map_stream, K2_THREADS, T->smem));

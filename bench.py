@@ -32,13 +32,14 @@ METRIC = "reads/sec mapped (E. coli, 4k-sample reads) at 1/2/4/8 B200 vs CPU ref
 GENOME = "g4m7"
 N_READS = 10000
 N_SAMPLES = 4000
+NOISE_MULT = 1.5          # noise N(0, 1.5 * level_stdv)
 
 
 def workload(rank, n_reads=N_READS):
     import synth
     import synthdata
     prefix, g = synthdata.get_index(GENOME)
-    sig, truth = synth.reads(g, n_reads, N_SAMPLES, seed=7 + 1000 * rank)
+    sig, truth = synth.reads(g, n_reads, N_SAMPLES, seed=7 + 1000 * rank, noise_mult=NOISE_MULT)
     return prefix, sig
 
 
@@ -81,8 +82,37 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_cpus():
+    """CPUs this process can really use: the scheduler affinity capped by the cgroup CPU quota (a GPU lease is often a
+    slice of the host: 128 CPUs visible, a quota of 16)."""
+    import math
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    usable = aff if quota is None else max(1, min(aff, int(math.ceil(quota))))
+    return {"usable": usable, "affinity": aff, "cpu_count": os.cpu_count(), "cgroup_quota_cpus": quota}
+
+
+def cpu_sample_size(threads, n_avail):
+    """Reads of one CPU step: >= 48 per thread so that the last reads' tail stays a few percent, bounded so that a
+    step is about 20 s on either kind of host."""
+    return int(min(n_avail, min(4096, max(256, 48 * threads))))
+
+
 def cpu_reference_run(prefix, sig, threads, budget_reads):
-    """The reference CPU mapper over the first `budget_reads` reads; returns (reads/s, kind)."""
+    """The reference CPU mapper (one long-lived Mapper per thread, as MapPool keeps them) over the first `budget_reads`
+    reads; returns (reads/s, kind, seconds, mapped, PAF keys per read)."""
     import ctypes as C
     import orclib
     n = min(budget_reads, len(sig))
@@ -97,23 +127,74 @@ def cpu_reference_run(prefix, sig, threads, budget_reads):
         R.ref_map_batch_mt(orclib.fp(flat), offs.ctypes.data_as(orclib.u64p), lens.ctypes.data_as(orclib.u32p), n,
                            threads, out)
         dt = time.time() - t
-        return n / dt, "reference", dt, int(sum(r.mapped for r in out))
+        return n / dt, "reference", dt, int(sum(r.mapped for r in out)), [orclib.paf_tuple(r) for r in out]
     O = orclib.Oracle(prefix)
+    O.lib.orc_set_child_sort(1)          # the reference's pdqsort order (oracle/unc_oracle.c)
     t = time.time()
     out = O.map_batch(flat, offs, lens, threads)
     dt = time.time() - t
-    return n / dt, "port", dt, int(sum(r.mapped for r in out))
+    return n / dt, "port", dt, int(sum(r.mapped for r in out)), [orclib.paf_tuple(r) for r in out]
+
+
+def cpu_fresh_mapper_keys(prefix, sig, ids):
+    """PAF keys of single reads mapped by the reference with a FRESH Mapper (ref_map_read): what a read gives when
+    it is the first on its thread."""
+    import orclib
+    res = {}
+    if orclib.ref_available():
+        R = orclib.ref()
+        for i in ids:
+            rec = orclib.RefPaf()
+            a = np.ascontiguousarray(sig[i])
+            R.ref_map_read(orclib.fp(a), len(a), rec)
+            res[i] = orclib.paf_tuple(rec)
+    else:
+        O = orclib.Oracle(prefix)
+        O.lib.orc_set_child_sort(1)
+        for i in ids:
+            res[i] = orclib.paf_tuple(O.map_read(np.ascontiguousarray(sig[i])))
+    return res
+
+
+def parity_report(prefix, sig, ref_keys, gpu_default, gpu_exact):
+    """In-bench parity gate: the GPU records of the CPU sample's reads against the reference's records of the same
+    reads.  The timed reference run keeps one Mapper per thread, so a read may inherit sources_added_ flags from its
+    thread's previous read (thread timing decides which); such reads are re-mapped with a fresh Mapper before they
+    count as a mismatch.  The exact-ties kernel must then equal the reference on every read; the default kernel may
+    differ only where the exact-ties kernel differs from it too (the reference's unstable sort decided a tie)."""
+    import uncalled_b200 as U
+    n = len(ref_keys)
+    kd = [U.paf_key(gpu_default[i]) for i in range(n)]
+    ke = [U.paf_key(gpu_exact[i]) for i in range(n)] if gpu_exact is not None else None
+    diff_d = [i for i in range(n) if kd[i] != ref_keys[i]]
+    diff_e = [i for i in range(n) if ke is not None and ke[i] != ref_keys[i]]
+    fresh = cpu_fresh_mapper_keys(prefix, sig, sorted(set(diff_d) | set(diff_e)))
+    bad_e = [i for i in diff_e if ke[i] != fresh[i]]
+    carry = [i for i in diff_d if kd[i] == fresh[i]]
+    tie = [i for i in diff_d if kd[i] != fresh[i] and ke is not None and ke[i] == fresh[i]]
+    bad_d = [i for i in diff_d if i not in carry and i not in tie]
+    rep = {"reads": n,
+           "default_kernel": {"identical": n - len(diff_d), "differing_ids": diff_d[:32],
+                              "explained_by_mapper_carry": len(carry), "explained_by_tie_order": len(tie),
+                              "unexplained": bad_d[:32]},
+           "exact_ties_kernel": None if ke is None else {"identical": n - len(diff_e), "differing_ids": diff_e[:32],
+                                                         "explained_by_mapper_carry": len(diff_e) - len(bad_e),
+                                                         "unexplained": bad_e[:32]},
+           "fields": "mapped, strand, rid, events, matches, rd_len/st/en, rf_st/en/len",
+           "ok": not bad_d and not bad_e}
+    return rep
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    ncores = os.cpu_count() or 1
-    prefix, sig = workload(0, n_reads=min(2048, max(64, 16 * ncores)))
+    cpus = host_cpus()
+    threads = cpus["usable"]
+    prefix, sig = workload(0, n_reads=cpu_sample_size(threads, N_READS))
     sample = len(sig)
     times = []
     for i in range(args.warmup + args.steps):
-        rps, kind, dt, mapped = cpu_reference_run(prefix, sig, ncores, sample)
+        rps, kind, dt, mapped, _ = cpu_reference_run(prefix, sig, threads, sample)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
@@ -121,10 +202,11 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64+u64", "data": "synthetic",
-            "config": {"workload": "E. coli-sized 4.7 Mb synthetic index, synthetic r9.4 reads x 4000 samples",
-                       "reads_per_step": sample, "note": "bounded sample of the 10k-read workload per step"},
-            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": ncores, "kind": kind,
-                             "sample": "%d reads x %d samples per step, %d threads" % (sample, N_SAMPLES, ncores)},
+            "config": {"workload": "E. coli-sized 4.7 Mb synthetic index, synthetic r9.4 reads x 4000 samples, noise %.1f x level stdv" % NOISE_MULT,
+                       "reads_per_step": sample, "note": "bounded sample (the first reads) of the 10k-read workload per step"},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": kind, "host_cpus": cpus,
+                             "reads_per_s_per_thread": value / threads,
+                             "sample": "%d reads x %d samples per step, %d threads (one long-lived Mapper per thread, as MapPool)" % (sample, N_SAMPLES, threads)},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -171,7 +253,7 @@ def run_stream_workload(args, rank, local_rank, world):
     n_channels, chunk_len = 512, 450
     n_reads = n_channels * args.reads_per_channel
     prefix, g = synthdata.get_index(GENOME)
-    sig, _ = synth.reads(g, n_reads, N_SAMPLES, seed=7 + 1000 * rank)
+    sig, _ = synth.reads(g, n_reads, N_SAMPLES, seed=7 + 1000 * rank, noise_mult=NOISE_MULT)
     sigs = [sig[i] for i in range(n_reads)]
     idx = U.Index(prefix, device=local_rank)
     sm = U.StreamMapper(idx, n_channels, chunk_len)
@@ -217,6 +299,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=N_READS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side modes (two-pool overlap, ordered, exact ties) that ride along at N=1")
     ap.add_argument("--overlap", action="store_true",
                     help="additionally time the steps with two pools used alternately (unc_map_batch_submit / _wait): the "
                          "next batch's CTAs fill the SMs that the previous batch's tail leaves idle; reported under 'overlap'")
@@ -309,8 +392,11 @@ def main():
     assert np.array_equal(out_dev, out_host), "device-resident and host-buffer paths disagree"
     assert int((out_dev["status"] != 0).sum()) == 0, "a read overflowed its device workspace"
 
+    # the side modes ride along at N=1 with their own bounded step counts (the flags force them at N>1 as well)
+    extras = world == 1 and not args.no_extras
+    x_steps = max(1, min(args.steps, 3))
     overlap = None
-    if args.overlap:
+    if args.overlap or extras:
         bm2 = U.BatchMapper(idx, max_reads=n_reads, max_samples=n_reads * N_SAMPLES)
         pools = [bm, bm2]
 
@@ -332,40 +418,42 @@ def main():
             if world > 1:
                 dist.all_reduce(w, op=dist.ReduceOp.MAX)
             return float(w[0]), float(w[1]), outs
-        pipelined(max(2, args.warmup))
-        ov_ms, ov_wall, outs = pipelined(args.steps)
+        ov_steps = max(2, min(args.steps, 4))
+        pipelined(2)
+        ov_ms, ov_wall, outs = pipelined(ov_steps)
         assert all(np.array_equal(o_, out_dev) for o_ in outs), "pipelined batches disagree with the single-pool result"
-        overlap = {"value": world * n_reads * args.steps / (ov_ms / 1e3), "unit": "reads/s", "pools": 2,
-                   "ms_per_step": ov_ms / args.steps, "wall_ms_per_step": ov_wall / args.steps,
+        overlap = {"value": world * n_reads * ov_steps / (ov_ms / 1e3), "unit": "reads/s", "pools": 2, "steps": ov_steps,
+                   "ms_per_step": ov_ms / ov_steps, "wall_ms_per_step": ov_wall / ov_steps,
                    "note": "CUDA events from the first submit to the end of the last batch on either pool, max over ranks; "
                            "the last step's tail is not hidden"}
         bm2.close()
 
     ordered = None
-    if args.ordered:
+    if args.ordered or extras:
         oh = {}
 
         def step_ordered():
             oh["r"] = bm.map_ordered(dev.data_ptr(), descs, on_device=True)
         timed(step_ordered, 1)
-        od_ms, od_wall, _ = timed(step_ordered, args.steps)
+        od_ms, od_wall, _ = timed(step_ordered, x_steps)
         recs_o, _, n_re, n_ro = oh["r"]
-        ordered = {"value": world * n_reads / (od_ms / args.steps / 1e3), "unit": "reads/s", "ms_per_step": od_ms / args.steps,
-                   "wall_ms_per_step": od_wall / args.steps, "reads_mapped_again": n_re, "extra_rounds": n_ro,
+        ordered = {"value": world * n_reads / (od_ms / x_steps / 1e3), "unit": "reads/s", "steps": x_steps, "ms_per_step": od_ms / x_steps,
+                   "wall_ms_per_step": od_wall / x_steps, "reads_mapped_again": n_re, "extra_rounds": n_ro,
                    "records_differing_from_plain_batch": int((recs_o != out_dev).sum()),
                    "note": "device-resident samples; sum of the CUDA-event times of all rounds, max over ranks"}
 
     exact_ties = None
-    if args.exact_ties:
+    recs_e = None
+    if args.exact_ties or extras:
         bm.set_tie_order(1)
         try:
-            timed(step_device, 1)
-            ex_ms, ex_wall, _ = timed(step_device, args.steps)
-            recs_e = out_holder["o"]
+            ex_ms, ex_wall, _ = timed(step_device, 1)      # one step: this mode is a verification mode, several times slower
+            recs_e = out_holder["o"].copy()
         finally:
             bm.set_tie_order(0)
-        exact_ties = {"value": world * n_reads / (ex_ms / args.steps / 1e3), "unit": "reads/s", "ms_per_step": ex_ms / args.steps,
-                      "records_differing_from_default_kernel": int((recs_e != out_dev).sum()),
+        paf_fields = ["mapped", "fwd", "rid", "events_used", "matches", "rd_st", "rd_en", "rf_st", "rf_en"]
+        exact_ties = {"value": world * n_reads / (ex_ms / 1e3), "unit": "reads/s", "steps": 1, "ms_per_step": ex_ms,
+                      "reads_with_a_PAF_field_differing_from_default_kernel": int(np.any([recs_e[k] != out_dev[k] for k in paf_fields], axis=0).sum()),
                       "note": "k2_map_exact, device-resident samples, CUDA events, max over ranks"}
 
     ms_per_step = dev_ms / args.steps
@@ -399,7 +487,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32/f64 events, u32 FM index", "data": "synthetic",
             "config": {"workload": "configs[1]: E. coli-sized 4.7 Mb synthetic index, %d synthetic r9.4 reads x %d "
-                                   "samples per GPU" % (n_reads, N_SAMPLES),
+                                   "samples per GPU, noise %.1f x level stdv (SURVEY 8d)" % (n_reads, N_SAMPLES, NOISE_MULT),
                        "reads_per_gpu": n_reads, "samples_per_read": N_SAMPLES, "parallelism": "reads sharded, replicas x%d" % world,
                        "l2": "inputs (%.0f MB/GPU) larger than L2; per-warp path state (GBs) streams through HBM" % (n_reads * N_SAMPLES * 4 / 1e6),
                        "mapped_fraction": float(o["mapped"].mean())},
@@ -420,12 +508,20 @@ def main():
                             "all_k1_launches_ms": k1_all_ms, "k1_stats(tiles,fsm_rerun_rounds,rerun_lanes,serial_reads)": list(bm.k1_stats()),
                             "algorithmic_bytes_per_launch": k1_bytes},
         }
-        if not args.no_cpu_baseline:
-            ncores = os.cpu_count() or 1
-            sample = min(2048, max(64, 32 * ncores))
-            rps, kind, dt, mapped = cpu_reference_run(prefix, sig, ncores, sample)
-            line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": ncores, "kind": kind,
-                                    "sample": "first %d reads of the same workload, %d threads, %.1f s" % (min(sample, n_reads), ncores, dt)}
+        if not args.no_cpu_baseline and world == 1:
+            cpus = host_cpus()
+            threads = cpus["usable"]
+            sample = cpu_sample_size(threads, n_reads)
+            rps, kind, dt, mapped, ref_keys = cpu_reference_run(prefix, sig, threads, sample)
+            line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": threads, "kind": kind, "host_cpus": cpus,
+                                    "reads_per_s_per_thread": rps / threads,
+                                    "sample": "first %d reads of the same workload, %d threads (one long-lived Mapper per thread, "
+                                              "as MapPool), %.1f s" % (sample, threads, dt)}
+            # parity gate: the same reads, both arms, on this box
+            line["parity"] = parity_report(prefix, sig, ref_keys, out_dev, recs_e)
+            if not line["parity"]["ok"]:
+                print(json.dumps(line), flush=True)
+                raise SystemExit("parity gate failed: GPU records differ from the reference's beyond the documented tie / carry cases")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -828,7 +828,7 @@ struct K2V2 {              // second worker structure (unc_k2v2.cuh)
     u32 kcnt[UNC_NKMER];   // per k-mer bucket: children counted during the extension, then the scatter cursor (= bucket end)
     u32 koff[UNC_NKMER];   // bucket start in the sorted key array
     u32 kagg[UNC_NKMER];   // (gap sources | child seeds << 16) of the bucket, then their exclusive prefix
-    u32 fresh_mask[32], fresh_before[32];   // fresh-source plan per 32-k-mer word
+    u32 fresh_cand[32], fresh_mask[32], fresh_before[32];   // fresh-source candidates / plan per 32-k-mer word
     u32 grab[2];           // bucket hand-out counters (sort pass, emit pass)
 };
 struct K2Shared {          // per CTA
@@ -944,7 +944,11 @@ UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *
         sh->tb.kmer_range[k] = ix.kmer_range[k];
     }
     for (u32 k = (u32) c_tid(); k < 64; k += (u32) c_nthreads()) sh->tb.thresh[k] = ix.thresh[k];
-    for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) { sh->v2.krank[k] = ix.krank[k]; sh->v2.rkmer[k] = ix.rkmer[k]; }
+    for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) {
+        const u32 rk = ix.krank[k];
+        sh->v2.krank[k] = (u16) (((rk & 31u) << 5) | (rk >> 5));   // the bucket's SLOT in the K2V2 arrays (k2v2_slot)
+        sh->v2.rkmer[k] = ix.rkmer[k];
+    }
     for (u32 c = (u32) c_tid(); c < n_slots; c += (u32) c_nthreads()) sh->pre[c] = 0;
 #ifdef K2_DFUSE
     for (u32 c = (u32) c_tid(); c < 2u * n_slots; c += (u32) c_nthreads()) sh->agg2[c] = 0;   // tag 0 = never published (epochs start at 1)

@@ -154,42 +154,97 @@ UNC_DEV void k2v2_sort_big(uint4 *keys, uint4 *tmp, u32 o, u32 n, u32 lo, u32 sp
     }
 }
 
-// What one chunk of <= 32 consecutive sorted keys of ONE k-mer bucket contributes (reference
-// src/mapper.cpp:1153-1194 of the restatement, :527-603 of the reference): lane i holds key g = g0 + i.
+// What 32 consecutive lanes of sorted keys contribute to the dedup walk (reference src/mapper.cpp:527-603; the
+// restatement's :1153-1194).  Every lane holds one key of some k-mer bucket (= one k-mer run); `head` marks the
+// lanes where a bucket's keys start in this pass, `first` the first key of a bucket overall.
 struct K2V2Walk {
-    bool a, dup, begin_v, after_v, seed;
+    bool dup, begin_v, after_v, seed;
     u32 as, ae;          // the after-source's range
     u32 m_b, m_a, m_seed;
 };
-// cur = this lane's key, nxt = the key after it (valid iff has_next), carry_mx = max fm_end over the bucket's
-// earlier chunks (0 for the first).  Returns the chunk's max fm_end (incl. the carry) in *mx_out (uniform).
-UNC_DEV K2V2Walk k2v2_walk_chunk(const uint4 cur, const uint4 nxt, bool a, bool has_next, bool first_chunk, u32 carry_mx,
-                                 bool prob_ok, uint2 kr, u32 *mx_out) {
+// cur = this lane's key, (nx, ny) = fm range of the key after it in the same bucket (valid iff has_next),
+// kr / prob_ok = the bucket's k-mer range and whether the k-mer may get sources.  use_carry (uniform): all
+// active lanes belong to one bucket that started in an earlier pass whose max fm_end so far is carry_mx.
+// *mx_last = the running max at lane 31.
+UNC_DEV K2V2Walk k2v2_walk(const uint4 cur, u32 nx, u32 ny, bool a, bool has_next, bool head, bool first, bool use_carry,
+                           u32 carry_mx, bool prob_ok, uint2 kr, u32 *mx_last) {
     const int lane = w_lane();
     K2V2Walk r;
-    r.a = a;
-    r.dup = has_next && nxt.x == cur.x && nxt.y == cur.y;
-    u32 mx = a ? cur.y : 0u;                          // inclusive prefix max of fm_end (one run: the bucket)
+    r.dup = has_next && nx == cur.x && ny == cur.y;
+    u32 mx = a ? cur.y : 0u;                          // segmented inclusive prefix max of fm_end
+    bool hd = head || !a;
     for (int d = 1; d < 32; d <<= 1) {
-        const u32 omx = w_shfl_up(mx, d);
-        if (lane >= d) mx = omx > mx ? omx : mx;
+        const u32 omx = w_shfl_up(mx, d), ohd = w_shfl_up(hd ? 1u : 0u, d);
+        if (lane >= d && !hd) { mx = omx > mx ? omx : mx; hd = ohd != 0; }
     }
-    if (!first_chunk) mx = mx > carry_mx ? mx : carry_mx;
-    *mx_out = w_shfl(mx, 31);
-    r.begin_v = a && first_chunk && lane == 0 && prob_ok && kr.x <= cur.x - 1u;
+    if (use_carry) mx = mx > carry_mx ? mx : carry_mx;
+    *mx_last = w_shfl(mx, 31);
+    r.begin_v = a && first && prob_ok && kr.x <= cur.x - 1u;
     r.as = mx + 1u;
-    r.ae = has_next ? nxt.x - 1u : kr.y;
+    r.ae = has_next ? nx - 1u : kr.y;
     r.after_v = a && !r.dup && prob_ok && r.as <= r.ae;
     r.seed = a && !r.dup && (cur.w & 1u);
     r.m_b = w_ballot(r.begin_v); r.m_a = w_ballot(r.after_v); r.m_seed = w_ballot(r.seed);
     return r;
 }
 
+// Small buckets (<= 32 keys) are handled several at a time: a PACK is a run of consecutive small buckets of one
+// 32-rank group with at most 32 keys in all, one key per lane.
+struct K2V2Pack {
+    bool a;              // this lane holds a key
+    u32 bl;              // lane (of the group) whose bucket the key belongs to
+    u32 start, pos, n;   // first pack lane of that bucket, position of the key in it, its size
+};
+// cnt = size of this lane's bucket if it is a small one, else 0; P = exclusive prefix of cnt over the lanes;
+// *remaining = lanes whose buckets are not packed yet (non-zero on entry)
+UNC_DEV K2V2Pack k2v2_next_pack(u32 cnt, u32 P, u32 *remaining) {
+    const int lane = w_lane();
+    const int s = d_ffs(*remaining) - 1;
+    const u32 Ps = w_shfl(P, s);
+    const bool fits = ((*remaining >> lane) & 1u) && (P + cnt - Ps <= 32u);
+    const u32 in_pack = w_ballot(fits);               // a prefix of `remaining` (P is non-decreasing); never empty
+    *remaining &= ~in_pack;
+    const int e = 31 - d_clz(in_pack);
+    const u32 T = w_shfl(P + cnt, e) - Ps;
+    K2V2Pack k;
+    k.a = (u32) lane < T;
+    k.bl = (u32) s; k.start = 0;
+    u32 m = in_pack;
+    while (m) {                                        // the last bucket that starts at or before this lane
+        const int b = d_ffs(m) - 1;
+        m &= m - 1;
+        const u32 sb = w_shfl(P, b) - Ps;
+        if ((u32) lane >= sb) { k.bl = (u32) b; k.start = sb; }
+    }
+    k.pos = (u32) lane - k.start;
+    k.n = w_shfl(cnt, (int) k.bl);
+    return k;
+}
+UNC_DEV u32 k2v2_segmask(u32 start, u32 n) { return (n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u)) << start; }
+
+// bucket rank -> index in the K2V2 per-bucket arrays: rank 32g + i sits at i*32 + g, so that a lane that owns 32
+// consecutive ranks (the prefix sums) and a warp that reads one rank per lane... both touch distinct banks or one
+UNC_DEV u32 k2v2_slot(u32 rank) { return ((rank & 31u) << 5) | (rank >> 5); }
+
 // the next group of 32 bucket ranks for this warp (two sweeps of 32 groups: see phase C2)
 UNC_DEV u32 k2v2_grab(u32 *counter) {
     u32 g = 0;
     if (w_lane() == 0) g = s_atomic_add(counter, 1u);
     return w_shfl(g, 0);
+}
+
+// exclusive prefix of the bucket counts (one warp): lane i owns ranks 32i .. 32i+31 = slots j*32 + i
+UNC_DEV void k2v2_bucket_offsets(K2V2 *v2) {
+    const u32 lane = (u32) w_lane();
+    u32 sum = 0;
+    for (u32 j = 0; j < 32; j++) sum += v2->kcnt[j * 32u + lane];
+    u32 tot, run = w_exscan(sum, &tot);
+    for (u32 j = 0; j < 32; j++) {
+        const u32 sl = j * 32u + lane, v = v2->kcnt[sl];
+        v2->koff[sl] = run;
+        v2->kcnt[sl] = run;                              // becomes the scatter cursor
+        run += v;
+    }
 }
 
 template <bool STREAM, bool FLAGS>
@@ -233,6 +288,13 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         for (u32 k = wt; k < UNC_NKMER; k += nwt) {
             sh->probs[k] = unc_match_prob(event, d_ldg(ix.lv_mean + k), d_ldg(ix.lv_var2 + k), d_ldg(ix.lognorm + k));
             v2->kcnt[k] = 0; v2->kagg[k] = 0;
+        }
+        for (u32 j = ww; j < 32; j += nwk) {              // k-mers that may get a fresh source (reference src/mapper.cpp:611-614)
+            const u32 k = j * 32 + (u32) lane;
+            const float pk = unc_match_prob(event, d_ldg(ix.lv_mean + k), d_ldg(ix.lv_var2 + k), d_ldg(ix.lognorm + k));
+            const uint2 kr = tb->kmer_range[k];
+            const u32 m = w_ballot(pk >= source_prob && kr.x <= kr.y);
+            if (lane == 0) v2->fresh_cand[j] = m;
         }
         if (wt == 0) { v2->grab[0] = 0; v2->grab[1] = 0; }
         c_sync_sub(1, (int) nwt);
@@ -410,15 +472,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         }
         if (ww == nwk - 1u) {
             // bucket offsets, assuming the buffer cap does not cut this event's children (else redone below)
-            u32 carry = 0;
-            for (u32 i0 = 0; i0 < UNC_NKMER; i0 += 32) {
-                const u32 v = v2->kcnt[i0 + (u32) lane];
-                u32 t;
-                const u32 ex = w_exscan(v, &t);
-                v2->koff[i0 + (u32) lane] = carry + ex;
-                v2->kcnt[i0 + (u32) lane] = carry + ex;          // becomes the scatter cursor
-                carry += t;
-            }
+            k2v2_bucket_offsets(v2);
         }
         if (ww != 0 || nwk == 1) {
             const u32 bt = nwk == 1 ? wt : wt - 32u, nbt = nwk == 1 ? nwt : nwt - 32u;
@@ -457,15 +511,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
             }
             c_sync_sub(1, (int) nwt);
             if (ww == 0) {
-                u32 carry = 0;
-                for (u32 i0 = 0; i0 < UNC_NKMER; i0 += 32) {
-                    const u32 v = v2->kcnt[i0 + (u32) lane];
-                    u32 t;
-                    const u32 ex = w_exscan(v, &t);
-                    v2->koff[i0 + (u32) lane] = carry + ex;
-                    v2->kcnt[i0 + (u32) lane] = carry + ex;
-                    carry += t;
-                }
+                k2v2_bucket_offsets(v2);
             }
             c_sync_sub(1, (int) nwt);
         }
@@ -493,67 +539,80 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
             c_sync_sub(1, (int) nwt);
             PT_MARK(2)
 
-            // ---- C2. sort every bucket (one warp each) and count what its dedup walk will emit.  Buckets are handed
-            //          out 32 ranks at a time, the large ones (> 32 keys) first.
+            // ---- C2. sort every bucket and count what its dedup walk will emit.  Buckets are handed out 32 ranks (one
+            //          group) at a time: first sweep the large buckets (> 32 keys, one warp each, radix), second sweep
+            //          the small ones, packed several to a warp pass.
             for (;;) {
                 const u32 gi = k2v2_grab(&v2->grab[0]);
                 if (gi >= 64u) break;
-                const bool big_sweep = gi < 32u;
-                const u32 rk = (gi & 31u) * 32u + (u32) lane;
-                const u32 bo = v2->koff[rk], bn = v2->kcnt[rk] - bo;
-                u32 todo = w_ballot(big_sweep ? bn > 32u : (bn > 0 && bn <= 32u));
-                while (todo) {
-                    const int l = d_ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const u32 o = w_shfl(bo, l), n = w_shfl(bn, l), rank = (gi & 31u) * 32u + (u32) l;
-                    const u32 kmer = v2->rkmer[rank];
-                    const uint2 kr = tb->kmer_range[kmer];
-                    const bool prob_ok = sh->probs[kmer] >= source_prob;
-                    u32 n_src = 0, n_seed = 0;
-                    if (n <= 32u) {
-                        // rank every key among the bucket's keys, deal the keys out in sorted order
-                        const bool a = (u32) lane < n;
-                        uint4 k = make_uint4(0, 0, 0, 0);
-                        if (a) k = ckA[o + (u32) lane];
-                        u32 rnk = 0;
-                        for (u32 j = 0; j < n; j++) {
-                            const u32 jx = w_shfl(k.x, (int) j), jy = w_shfl(k.y, (int) j), jz = w_shfl(k.z, (int) j), jw = w_shfl(k.w, (int) j);
-                            if (k2v2_less(jx, jy, jz, jw, k.x, k.y, k.z, k.w)) rnk++;
-                        }
-                        uint4 *sst = (uint4 *) stage_r;
-                        if (a) sst[rnk] = k;
-                        w_sync();
-                        uint4 cur = make_uint4(0, 0, 0, 0);
-                        if (a) { cur = sst[lane]; ckA[o + (u32) lane] = cur; }
-                        w_sync();
-                        uint4 nxt;
-                        nxt.x = w_shfl_down(cur.x, 1); nxt.y = w_shfl_down(cur.y, 1); nxt.z = 0; nxt.w = 0;
-                        u32 mxo;
-                        const K2V2Walk wk = k2v2_walk_chunk(cur, nxt, a, (u32) lane + 1u < n, true, 0u, prob_ok, kr, &mxo);
-                        n_src = (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
-                        n_seed = (u32) d_popc(wk.m_seed);
-                    } else {
+                const u32 grp = gi & 31u;
+                const u32 sl = (u32) lane * 32u + grp;                 // slot of rank 32*grp + lane
+                const u32 bo = v2->koff[sl], bn = v2->kcnt[sl] - bo;
+                if (gi < 32u) {
+                    u32 todo = w_ballot(bn > 32u);
+                    while (todo) {
+                        const int l = d_ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const u32 o = w_shfl(bo, l), n = w_shfl(bn, l);
+                        const u32 kmer = v2->rkmer[grp * 32u + (u32) l];
+                        const uint2 kr = tb->kmer_range[kmer];
+                        const bool prob_ok = sh->probs[kmer] >= source_prob;
                         // span of the bucket's fm_start values -> radix passes
                         u32 lo = 0xFFFFFFFFu, hi = 0;
                         for (u32 g = (u32) lane; g < n; g += 32u) { const u32 x = ckA[o + g].x; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
                         hi = w_max(hi);
                         lo = ~w_max(~lo);
                         k2v2_sort_big(ckA, ckB, o, n, lo, 32u - (u32) d_clz(hi - lo), whist);
-                        u32 carry_mx = 0;
+                        u32 carry_mx = 0, n_src = 0, n_seed = 0;
                         for (u32 g0 = 0; g0 < n; g0 += 32u) {
                             const u32 g = g0 + (u32) lane;
                             const bool a = g < n, has_next = g + 1u < n;
-                            uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+                            uint4 cur = make_uint4(0, 0, 0, 0); u32 nx = 0, ny = 0;
                             if (a) cur = ckA[o + g];
-                            if (has_next) nxt = ckA[o + g + 1u];
+                            if (has_next) { const uint4 t = ckA[o + g + 1u]; nx = t.x; ny = t.y; }
                             u32 mxo;
-                            const K2V2Walk wk = k2v2_walk_chunk(cur, nxt, a, has_next, g0 == 0, carry_mx, prob_ok, kr, &mxo);
+                            const K2V2Walk wk = k2v2_walk(cur, nx, ny, a, has_next, g == 0, g == 0, g0 != 0, carry_mx, prob_ok, kr, &mxo);
                             carry_mx = mxo;
                             n_src += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
                             n_seed += (u32) d_popc(wk.m_seed);
                         }
+                        if (lane == 0) v2->kagg[(u32) l * 32u + grp] = n_src | (n_seed << 16);
                     }
-                    if (lane == 0) v2->kagg[rank] = n_src | (n_seed << 16);
+                } else {
+                    const u32 cnt = (bn > 0 && bn <= 32u) ? bn : 0u;
+                    u32 tot;
+                    const u32 P = w_exscan(cnt, &tot);
+                    u32 remaining = w_ballot(cnt != 0);
+                    while (remaining) {
+                        const K2V2Pack pk = k2v2_next_pack(cnt, P, &remaining);
+                        const u32 addr = w_shfl(bo, (int) pk.bl) + pk.pos;
+                        uint4 k = make_uint4(0, 0, 0, 0);
+                        if (pk.a) k = ckA[addr];
+                        // rank every key among the keys of its bucket, deal the keys out in sorted order
+                        const u32 maxn = w_max(pk.a ? pk.n : 0u);
+                        u32 rnk = 0;
+                        for (u32 q = 0; q < maxn; q++) {
+                            const int src = (int) ((pk.start + q) & 31u);
+                            const u32 jx = w_shfl(k.x, src), jy = w_shfl(k.y, src), jz = w_shfl(k.z, src), jw = w_shfl(k.w, src);
+                            if (pk.a && q < pk.n && k2v2_less(jx, jy, jz, jw, k.x, k.y, k.z, k.w)) rnk++;
+                        }
+                        uint4 *sst = (uint4 *) stage_r;
+                        if (pk.a) sst[pk.start + rnk] = k;
+                        w_sync();
+                        uint4 cur = make_uint4(0, 0, 0, 0);
+                        if (pk.a) { cur = sst[lane]; ckA[addr] = cur; }
+                        w_sync();
+                        const u32 nx = w_shfl_down(cur.x, 1), ny = w_shfl_down(cur.y, 1);
+                        const u32 kmer = v2->rkmer[grp * 32u + pk.bl];
+                        const uint2 kr = tb->kmer_range[kmer];
+                        const bool prob_ok = sh->probs[kmer] >= source_prob;
+                        u32 mxo;
+                        const K2V2Walk wk = k2v2_walk(cur, nx, ny, pk.a, pk.a && pk.pos + 1u < pk.n, pk.pos == 0, pk.pos == 0, false, 0u,
+                                                      prob_ok, kr, &mxo);
+                        const u32 sm = k2v2_segmask(pk.start, pk.n);
+                        if (pk.a && pk.pos == 0)
+                            v2->kagg[pk.bl * 32u + grp] = ((u32) d_popc(wk.m_b & sm) + (u32) d_popc(wk.m_a & sm)) | ((u32) d_popc(wk.m_seed & sm) << 16);
+                    }
                 }
             }
             c_sync_sub(1, (int) nwt);
@@ -565,41 +624,34 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         //      (reference :605-624).  The other warps: suffix-array look-ups of the ended paths' seed rows
         //      (reference :673-681: sa_end = fmi.size() - fmi.sa(s)).
         if (ww == 0) {
-            u32 carry = 0;                                   // sources | seeds << 16 before the group
-            for (u32 i0 = 0; i0 < UNC_NKMER; i0 += 32) {
-                const u32 rk = i0 + (u32) lane;
-                const u32 v = v2->kagg[rk];
-                u32 ts, tq;
-                const u32 es = w_exscan(v & 0xFFFFu, &ts), eq = w_exscan(v >> 16, &tq);
-                const u32 sb = (carry & 0xFFFFu) + es, qb = (carry >> 16) + eq;
-                v2->kagg[rk] = sb | (qb << 16);
+            // lane i owns ranks 32i .. 32i+31 (slots j*32 + i): its sum, a warp scan of the sums, its running prefix
+            u32 sum = 0;
+            for (u32 j = 0; j < 32; j++) sum += v2->kagg[j * 32u + (u32) lane];
+            u32 ts, tq;
+            const u32 es = w_exscan(sum & 0xFFFFu, &ts), eq = w_exscan(sum >> 16, &tq);
+            u32 run = es | (eq << 16);                       // sources | seeds << 16 before the bucket
+            for (u32 j = 0; j < 32; j++) {
+                const u32 sl = j * 32u + (u32) lane, v = v2->kagg[sl];
+                v2->kagg[sl] = run;
                 // sources_added_[kmer] is set at a run start while the buffer is not full
-                const bool nonempty = nc > 0 && v2->kcnt[rk] != v2->koff[rk];
-                if (nonempty) {
-                    const u32 kmer = v2->rkmer[rk];
-                    if (sh->probs[kmer] >= source_prob && nc + sb < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
+                if (nc > 0 && v2->kcnt[sl] != v2->koff[sl]) {
+                    const u32 kmer = v2->rkmer[(u32) lane * 32u + j];
+                    if (sh->probs[kmer] >= source_prob && nc + (run & 0xFFFFu) < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
                 }
-                carry = ((carry & 0xFFFFu) + ts) | (((carry >> 16) + tq) << 16);
+                run = ((run & 0xFFFFu) + (v & 0xFFFFu)) | (((run >> 16) + (v >> 16)) << 16);
             }
             w_sync();
-            const u32 tot_src = carry & 0xFFFFu;
+            const u32 tot_src = ts;
             const u32 ns_added = nc + tot_src > maxp ? maxp - nc : tot_src;
             const u32 nn0 = nc + ns_added;
-            u32 my_mask = 0;
-            for (u32 j = 0; j < 32; j++) {
-                const u32 k = j * 32 + (u32) lane;
-                const uint2 kr = tb->kmer_range[k];
-                const bool add = !((sh->flags[j] >> lane) & 1u) && sh->probs[k] >= source_prob && kr.x <= kr.y;
-                const u32 m_add = w_ballot(add);
-                if ((u32) lane == j) my_mask = m_add;
-            }
+            const u32 my_mask = v2->fresh_cand[lane] & ~sh->flags[lane];   // word `lane` of the fresh-source walk
             u32 tot_add;
             const u32 my_pre = w_exscan((u32) d_popc(my_mask), &tot_add);
             v2->fresh_mask[lane] = my_mask;
             v2->fresh_before[lane] = nn0 + my_pre;           // fill level when the serial walk reaches word `lane`
             if (lane == 0) {
                 sh->bc[1] = nn0 + tot_add < maxp ? nn0 + tot_add : maxp;
-                sh->bc[6] = carry;
+                sh->bc[6] = tq;
             }
         }
         if (ww != 0 || nwk == 1) {
@@ -612,8 +664,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         }
         c_sync_sub(1, (int) nwt);
         PT_MARK(11)
-        const u32 fin = sh->bc[6];
-        const u32 n_child_seeds = nc > 0 ? fin >> 16 : 0u;
+        const u32 n_child_seeds = nc > 0 ? sh->bc[6] : 0u;
         n_rows = n_ended_rows + n_child_seeds;
         if (n_rows > W.rl_cap) n_rows = W.rl_cap;
 
@@ -622,31 +673,46 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
             for (;;) {
                 const u32 gi = k2v2_grab(&v2->grab[1]);
                 if (gi >= 64u) break;
-                const bool big_sweep = gi < 32u;
-                const u32 rk = (gi & 31u) * 32u + (u32) lane;
-                const u32 bo = v2->koff[rk], bn = v2->kcnt[rk] - bo, bpre = v2->kagg[rk];
-                u32 todo = w_ballot(big_sweep ? bn > 32u : (bn > 0 && bn <= 32u));
-                while (todo) {
-                    const int l = d_ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const u32 o = w_shfl(bo, l), n = w_shfl(bn, l), pre = w_shfl(bpre, l), rank = (gi & 31u) * 32u + (u32) l;
-                    const u32 kmer = v2->rkmer[rank];
+                const u32 grp = gi & 31u;
+                const u32 sl = (u32) lane * 32u + grp;
+                const u32 bo = v2->koff[sl], bn = v2->kcnt[sl] - bo, bpre = v2->kagg[sl];
+                const bool small_sweep = gi >= 32u;
+                const u32 cnt = (small_sweep && bn > 0 && bn <= 32u) ? bn : 0u;
+                u32 tot;
+                const u32 P = w_exscan(cnt, &tot);
+                u32 remaining = small_sweep ? w_ballot(cnt != 0) : 0u;
+                u32 todo = small_sweep ? 0u : w_ballot(bn > 32u);
+                while (todo | remaining) {
+                    // one pass: a pack of small buckets, or the next 32 keys of one large bucket
+                    K2V2Pack pk;
+                    u32 o_big = 0, n_big = 0, g0 = 0, carry_mx = 0, src_acc = 0, seed_acc = 0;
+                    int l_big = 0;
+                    if (small_sweep) pk = k2v2_next_pack(cnt, P, &remaining);
+                    else {
+                        l_big = d_ffs(todo) - 1;
+                        todo &= todo - 1;
+                        o_big = w_shfl(bo, l_big); n_big = w_shfl(bn, l_big);
+                        pk.bl = (u32) l_big; pk.start = 0; pk.n = n_big; pk.pos = (u32) lane; pk.a = (u32) lane < n_big;
+                    }
+                    const u32 kmer = v2->rkmer[grp * 32u + pk.bl];
                     const uint2 kr = tb->kmer_range[kmer];
                     const float pkm = sh->probs[kmer];
                     const bool prob_ok = pkm >= source_prob;
-                    u32 src_before = pre & 0xFFFFu, seeds_before = pre >> 16;
-                    u32 carry_mx = 0;
-                    for (u32 g0 = 0; g0 < n; g0 += 32u) {
-                        const u32 g = g0 + (u32) lane;
-                        const bool a = g < n, has_next = g + 1u < n;
-                        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
-                        if (a) cur = ckA[o + g];
-                        if (n <= 32u) { nxt.x = w_shfl_down(cur.x, 1); nxt.y = w_shfl_down(cur.y, 1); }
-                        else if (has_next) nxt = ckA[o + g + 1u];
+                    const u32 pre = w_shfl(bpre, (int) pk.bl), o = w_shfl(bo, (int) pk.bl);
+                    for (;;) {
+                        const u32 pos = small_sweep ? pk.pos : g0 + (u32) lane;
+                        const bool a = small_sweep ? pk.a : pos < n_big;
+                        const bool has_next = a && pos + 1u < pk.n;
+                        uint4 cur = make_uint4(0, 0, 0, 0);
+                        if (a) cur = ckA[o + pos];
+                        u32 nx = w_shfl_down(cur.x, 1), ny = w_shfl_down(cur.y, 1);
+                        if (!small_sweep && lane == 31 && has_next) { const uint4 t = ckA[o + pos + 1u]; nx = t.x; ny = t.y; }
                         u32 mxo;
-                        const K2V2Walk wk = k2v2_walk_chunk(cur, nxt, a, has_next, g0 == 0, carry_mx, prob_ok, kr, &mxo);
+                        const K2V2Walk wk = k2v2_walk(cur, nx, ny, a, has_next, pos == 0, pos == 0, !small_sweep && g0 != 0, carry_mx, prob_ok,
+                                                      kr, &mxo);
                         carry_mx = mxo;
-                        const u32 sidx = src_before + (u32) d_popc(wk.m_b & lt) + (u32) d_popc(wk.m_a & lt);   // sources before this element
+                        const u32 sm = small_sweep ? k2v2_segmask(pk.start, pk.n) : 0xFFFFFFFFu;
+                        const u32 sidx = (pre & 0xFFFFu) + src_acc + (u32) d_popc(wk.m_b & lt & sm) + (u32) d_popc(wk.m_a & lt & sm);   // sources before this element
                         if (wk.begin_v && nc + sidx < maxp) {
                             write_source(next, hist_e, S0 + nc + sidx, kr.x, cur.x - 1u, kmer, pkm);
                             onext[nc + sidx] = S0 + nc + sidx;
@@ -657,17 +723,20 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                             onext[nc + sidx2] = S0 + nc + sidx2;
                         }
                         const u32 rec = cur.w >> 6;
-                        if (a) onext[o + g] = rec | (wk.dup ? UNC_INVALID : 0u);
+                        if (a) onext[o + pos] = rec | (wk.dup ? UNC_INVALID : 0u);
                         // update_seeds(child, false): unique, move-headed, full-length, probable paths
                         if (wk.seed) {
                             d_atomic_or(&((u32 *) (next + (size_t) rec * 2))[3], 0x80000000u);   // sa_checked_
-                            const u32 ri = n_ended_rows + seeds_before + (u32) d_popc(wk.m_seed & lt);
+                            const u32 ri = n_ended_rows + (pre >> 16) + seed_acc + (u32) d_popc(wk.m_seed & lt & sm);
                             if (ri < W.rl_cap)
                                 rlist[ri] = make_uint2(ix.seq_len - unc_sa_lookup(ix, cur.x, &pend_steps, &pend_blocks), (cur.w >> 1) & 0x1Fu);
                             else sh->wk_overflow = 1;
                         }
-                        src_before += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
-                        seeds_before += (u32) d_popc(wk.m_seed);
+                        if (small_sweep) break;
+                        src_acc += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
+                        seed_acc += (u32) d_popc(wk.m_seed);
+                        g0 += 32u;
+                        if (g0 >= n_big) break;
                     }
                 }
             }

@@ -20,7 +20,7 @@ struct EmuIndex {
     std::vector<uint2> kmer_range;
     std::vector<float> lv_mean, lv_var2, lognorm;
     std::vector<uint4> occ2;
-    uint16_t krank[1024], rkmer[1024];
+    K2V2Tab kt;
 };
 
 extern "C" {
@@ -50,8 +50,8 @@ void *emu_index_load(const char *prefix, const char *preset, const char *model_t
         e->occ2.resize((size_t) n_blk * 2);
         for (u32 j = 0; j < n_blk; j++) unc_occ2_build_block(ix.bwt, j, e->occ2.data());
         ix.occ2 = e->occ2.data();
-        hix_kmer_ranks(e->kmer_range.data(), e->krank, e->rkmer);
-        ix.krank = e->krank; ix.rkmer = e->rkmer;
+        if (!hix_k2v2_tab(e->kmer_range.data(), e->kt)) { fprintf(stderr, "emu_index_load: too many overlapping k-mer ranges\n"); delete e; return nullptr; }
+        ix.kt = &e->kt;
     }
     return e;
 }

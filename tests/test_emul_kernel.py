@@ -111,3 +111,22 @@ def test_bench_scale_reads_on_the_4m7_index():
     sig, _ = synth.reads(g, 120, 4000, seed=7, frac_random=0.15)
     recs, _, _, _ = _check(E, O, [sig[100], sig[99]])
     assert recs[0].mapped and not recs[1].mapped and recs[1].n_children > 3000000
+
+
+def test_kmer_ranges_that_overlap_share_a_bucket(g200k):
+    """get_base_range's start (L2[b], not L2[b]+1) lets a k-mer's FM range begin on its predecessor's last row; children of
+    the two k-mers then interleave in the sorted order (first seen on the B200: read 30 of this set, event 63 -- two gap
+    sources short).  The second worker structure keeps such k-mers in one bucket and walks it as the reference does."""
+    prefix, g = g200k
+    sig, _ = synth.reads(g, 31, 4000, seed=7)
+    E = emulib.Emu(prefix)
+    O = orclib.Oracle(prefix)
+    st, en = O.kmer_ranges()
+    ne = st <= en
+    order = np.argsort(st[ne], kind="stable")
+    s, e = st[ne][order], en[ne][order]
+    assert (s[1:] <= e[:-1]).sum() >= 1          # the index has overlapping k-mer ranges
+    recs = E.map_batch([sig[30]])[0]
+    w = O.map_read(sig[30])
+    assert emulib.paf_tuple(recs[0]) == orclib.paf_tuple(w)
+    assert (recs[0].n_children, recs[0].n_sources, recs[0].n_seeds, recs[0].n_clusters) == (w.n_children, w.n_sources, w.n_seeds, w.n_clusters)

@@ -312,7 +312,7 @@ int unc_index_load(const char *bwa_prefix, const char *preset, const char *model
     for (int i = 0; i < 5; i++) ix.L2[i] = (u32) h.L2[i];
     ix.start_bits = 64 - __builtin_clzll(h.seq_len ? h.seq_len : 1);
     ix.sa_full = nullptr;
-    ix.occ2 = nullptr; ix.krank = nullptr; ix.rkmer = nullptr;
+    ix.occ2 = nullptr; ix.kt = nullptr;
     {   // expanded suffix array (4 bytes per FM row); skipped when device memory is short
         size_t free_b = 0, total_b = 0;
         const size_t need = ((size_t) h.seq_len + 1) * 4;
@@ -333,15 +333,14 @@ int unc_index_load(const char *bwa_prefix, const char *preset, const char *model
         if (cudaMalloc(&x->d_occ2, (size_t) n_blk * 32 + 64) != cudaSuccess) { unc_index_free(x); return fail(UNC_E_CUDA, "cudaMalloc occ2"); }
         cudaMemset((char *) x->d_occ2 + (size_t) n_blk * 32, 0, 64);
         k_occ2_build<<<(n_blk + 255) / 256, 256>>>(ix.bwt, (uint4 *) x->d_occ2, n_blk);
-        uint16_t ranks[2048];
-        hix_kmer_ranks(x->kmer_range.data(), ranks, ranks + 1024);
-        if (cudaMalloc(&x->d_krank, sizeof(ranks)) != cudaSuccess ||
-            cudaMemcpy(x->d_krank, ranks, sizeof(ranks), cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaDeviceSynchronize() != cudaSuccess) { unc_index_free(x); return fail(UNC_E_CUDA, "occ2 / k-mer rank tables"); }
+        K2V2Tab kt;
+        if (!hix_k2v2_tab(x->kmer_range.data(), kt)) { unc_index_free(x); return fail(UNC_E_TOO_LARGE, "more overlapping k-mer FM ranges than the bucket table holds"); }
+        if (cudaMalloc(&x->d_krank, sizeof(kt)) != cudaSuccess ||
+            cudaMemcpy(x->d_krank, &kt, sizeof(kt), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaDeviceSynchronize() != cudaSuccess) { unc_index_free(x); return fail(UNC_E_CUDA, "occ2 / k-mer bucket tables"); }
         ix.occ2 = (const uint4 *) x->d_occ2;
-        ix.krank = (const u16 *) x->d_krank;
-        ix.rkmer = ix.krank + 1024;
-        x->device_bytes += (size_t) n_blk * 32 + 64 + sizeof(ranks);
+        ix.kt = (const K2V2Tab *) x->d_krank;
+        x->device_bytes += (size_t) n_blk * 32 + 64 + sizeof(kt);
     }
     *out = x;
     return UNC_OK;

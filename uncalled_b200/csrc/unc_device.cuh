@@ -42,8 +42,21 @@ struct DevIndex {
     u32 start_bits;        // bits needed to represent seq_len (radix-sort passes)
     // GPU-side layouts derived at index load (unc_k2v2.cuh):
     const uint4 *occ2;     // 32-byte Occ blocks: 4 x u32 counts before the block + 64 two-bit BWT symbols
-    const u16 *krank;      // k-mer -> position of its FM range among the 1024 (ranges are disjoint and ordered)
-    const u16 *rkmer;      // the inverse
+    const struct K2V2Tab *kt;   // k-mer buckets of the child sort
+};
+
+// K-mer buckets of the child sort (unc_k2v2.cuh).  Children sorted by fm_start are grouped by k-mer because the
+// k-mers' FM ranges are ordered and disjoint -- except where BwaIndex::get_base_range's start (L2[b], not L2[b]+1:
+// reference src/bwa_index.hpp:172-174) lets a k-mer's range begin on the LAST row of its predecessor's.  K-mers
+// whose ranges overlap share one bucket ("merged group"; a handful per index, two k-mers each in practice), and
+// a key carries its k-mer's position in the group (sub).
+#define K2V2_MAX_MERGED 64u     /* k-mers in merged groups, all groups together */
+struct alignas(16) K2V2Tab {
+    u16 kslot[UNC_NKMER];   // k-mer -> slot of its group in the per-bucket arrays (group rank r sits at (r&31)*32 + (r>>5))
+    u16 gkmer[UNC_NKMER];   // group rank -> its k-mer (single-k-mer groups)
+    u16 gmeta[UNC_NKMER];   // group rank -> 0, or (offset into mk) << 8 | members for a merged group
+    u16 mk[K2V2_MAX_MERGED];   // the merged groups' k-mers, in FM order
+    u8 ksub[UNC_NKMER];     // k-mer -> its position in its group
 };
 
 // L2[c] through selects: a dynamically indexed member would force the whole kernel-parameter
@@ -824,7 +837,8 @@ struct K2Tables {
     float thresh[64];
 };
 struct K2V2 {              // second worker structure (unc_k2v2.cuh)
-    u16 krank[UNC_NKMER], rkmer[UNC_NKMER];
+    K2V2Tab t;
+    u16 mfirst[K2V2_MAX_MERGED];   // per merged-group k-mer: gap sources of its bucket before its first run (0xFFFF: no run)
     u32 kcnt[UNC_NKMER];   // per k-mer bucket: children counted during the extension, then the scatter cursor (= bucket end)
     u32 koff[UNC_NKMER];   // bucket start in the sorted key array
     u32 kagg[UNC_NKMER];   // (gap sources | child seeds << 16) of the bucket, then their exclusive prefix
@@ -944,11 +958,7 @@ UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *
         sh->tb.kmer_range[k] = ix.kmer_range[k];
     }
     for (u32 k = (u32) c_tid(); k < 64; k += (u32) c_nthreads()) sh->tb.thresh[k] = ix.thresh[k];
-    for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) {
-        const u32 rk = ix.krank[k];
-        sh->v2.krank[k] = (u16) (((rk & 31u) << 5) | (rk >> 5));   // the bucket's SLOT in the K2V2 arrays (k2v2_slot)
-        sh->v2.rkmer[k] = ix.rkmer[k];
-    }
+    for (u32 k = (u32) c_tid(); k < (u32) (sizeof(K2V2Tab) / 4); k += (u32) c_nthreads()) ((u32 *) &sh->v2.t)[k] = ((const u32 *) ix.kt)[k];
     for (u32 c = (u32) c_tid(); c < n_slots; c += (u32) c_nthreads()) sh->pre[c] = 0;
 #ifdef K2_DFUSE
     for (u32 c = (u32) c_tid(); c < 2u * n_slots; c += (u32) c_nthreads()) sh->agg2[c] = 0;   // tag 0 = never published (epochs start at 1)

@@ -157,18 +157,38 @@ static inline bool hix_load(HostIndex &h, const std::string &prefix, const std::
     return true;
 }
 
-// k-mer -> position of its FM range among the 1024 ranges ordered by start (the ranges of distinct k-mers are
-// disjoint, so children sorted by fm_start are grouped by k-mer in this order; unc_k2v2.cuh); ties (absent
-// k-mers have an empty range that starts where a present one does) are broken by the k-mer code.
-template <typename R>
-static inline void hix_kmer_ranks(const R *kmer_range, uint16_t krank[1024], uint16_t rkmer[1024]) {
+// The k-mer buckets of the mapper's child sort (K2V2Tab, unc_device.cuh): k-mers in the order of their FM ranges,
+// consecutive k-mers whose ranges overlap (the get_base_range quirk) merged into one group.  T = K2V2Tab.
+// Returns false when the merged groups hold more k-mers than the table has room for (no real index does).
+template <typename R, typename T>
+static inline bool hix_k2v2_tab(const R *kmer_range, T &t) {
+    memset(&t, 0, sizeof(t));
     std::vector<uint32_t> ord(1024);
     for (uint32_t k = 0; k < 1024; k++) ord[k] = k;
+    auto empty = [&](uint32_t k) { return kmer_range[k].x > kmer_range[k].y; };
     std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
         if (kmer_range[a].x != kmer_range[b].x) return kmer_range[a].x < kmer_range[b].x;
-        const bool ea = kmer_range[a].x > kmer_range[a].y, eb = kmer_range[b].x > kmer_range[b].y;   // empty ranges first
-        if (ea != eb) return ea;
+        if (empty(a) != empty(b)) return empty(a);      // empty ranges first
         return a < b;
     });
-    for (uint32_t i = 0; i < 1024; i++) { rkmer[i] = (uint16_t) ord[i]; krank[ord[i]] = (uint16_t) i; }
+    uint32_t n_groups = 0, n_merged = 0;
+    for (uint32_t i = 0; i < 1024;) {
+        uint32_t j = i + 1;
+        if (!empty(ord[i])) {
+            uint64_t hi = kmer_range[ord[i]].y;
+            while (j < 1024 && !empty(ord[j]) && kmer_range[ord[j]].x <= hi) { hi = std::max<uint64_t>(hi, kmer_range[ord[j]].y); j++; }
+        }
+        const uint32_t g = n_groups++, members = j - i;
+        const uint16_t slot = (uint16_t) (((g & 31u) << 5) | (g >> 5));
+        t.gkmer[g] = (uint16_t) ord[i];
+        if (members > 1) {
+            if (n_merged + members > sizeof(t.mk) / sizeof(t.mk[0]) || members > 255) return false;
+            t.gmeta[g] = (uint16_t) ((n_merged << 8) | members);
+            for (uint32_t m = 0; m < members; m++) t.mk[n_merged + m] = (uint16_t) ord[i + m];
+            n_merged += members;
+        }
+        for (uint32_t m = 0; m < members; m++) { t.kslot[ord[i + m]] = slot; t.ksub[ord[i + m]] = (uint8_t) m; }
+        i = j;
+    }
+    return true;
 }

@@ -61,7 +61,7 @@ UNC_DEV void unc_occ2_all(const uint4 cnt, const uint4 sym, u32 p, u32 o[4]) {
 }
 
 // ---- sort keys -----------------------------------------------------------------------------------------
-// key = (fm_start, fm_end, seed_prob bits, seedable | move_count << 1 | record index << 6)
+// key = (fm_start, fm_end, seed_prob bits, seedable | move_count << 1 | k-mer's position in a merged group << 6 | record index << 14)
 // order: fm_start, fm_end, seed_prob, record index (= emission order) -- reference src/mapper.cpp:866-871 plus
 // the documented tie-break.  seed_prob is compared through a monotone integer image of the float so that the
 // order is total whatever the bits are (a NaN cannot make two keys claim one rank); -0 counts as +0.
@@ -74,7 +74,7 @@ UNC_DEV bool k2v2_less(u32 ax, u32 ay, u32 az, u32 aw, u32 bx, u32 by, u32 bz, u
     if (ay != by) return ay < by;
     const u32 fa = k2v2_fkey(az), fb = k2v2_fkey(bz);
     if (fa != fb) return fa < fb;
-    return (aw >> 6) < (bw >> 6);
+    return (aw >> 14) < (bw >> 14);
 }
 
 // One k-mer bucket [o, o+n) of `keys`, n > 32, sorted by ONE warp: LSD radix on (fm_start - lo) over the bits
@@ -233,6 +233,94 @@ UNC_DEV u32 k2v2_grab(u32 *counter) {
     return w_shfl(g, 0);
 }
 
+// <= 32 keys of one bucket sorted in place by one warp: every key ranked among the others, dealt out in order
+UNC_DEV void k2v2_sort_small(uint4 *keys, u32 n, uint4 *sst) {
+    const int lane = w_lane();
+    const bool a = (u32) lane < n;
+    uint4 k = make_uint4(0, 0, 0, 0);
+    if (a) k = keys[lane];
+    u32 rnk = 0;
+    for (u32 j = 0; j < n; j++) {
+        const u32 jx = w_shfl(k.x, (int) j), jy = w_shfl(k.y, (int) j), jz = w_shfl(k.z, (int) j), jw = w_shfl(k.w, (int) j);
+        if (k2v2_less(jx, jy, jz, jw, k.x, k.y, k.z, k.w)) rnk++;
+    }
+    if (a) sst[rnk] = k;
+    w_sync();
+    if (a) keys[lane] = sst[lane];
+    w_sync();
+}
+
+// The dedup walk over the sorted keys of a MERGED group's bucket (k-mers whose FM ranges overlap): the reference's
+// loop statement by statement (src/mapper.cpp:527-603; the restatement's :1153-1194), by ONE lane -- the k-mer
+// runs interleave here, so nothing about them is known in advance.  EMIT == false: count the bucket's gap sources
+// and child seeds and note, per k-mer, how many sources precede its first run (D0 derives the sources_added_
+// flags from that); EMIT == true: write the sources, order entries and seed rows at their final places.
+struct K2V2Emit {
+    uint4 *next; uint2 *hist_e; u32 *onext; uint2 *rlist;
+    u32 S0, nc, maxp, n_ended_rows, rl_cap, pos0;      // pos0: sorted position of the bucket's first key
+    u32 src_before, seeds_before;
+};
+template <bool EMIT>
+UNC_DEV u32 k2v2_walk_merged(const DevIndex &ix, K2Shared *sh, const uint4 *keys, u32 n, u32 moff, float source_prob,
+                             const K2V2Emit &E, u32 *pend_steps, u32 *pend_blocks) {
+    K2V2 *v2 = &sh->v2;
+    u32 nsrc = 0, nseed = 0, prev_sub = 0xFFFFFFFFu, un_st = 1, un_en = 0;
+    for (u32 i = 0; i < n; i++) {
+        const uint4 cur = keys[i];
+        const u32 sub = (cur.w >> 6) & 0xFFu, kmer = v2->t.mk[moff + sub];
+        const uint2 kr = sh->tb.kmer_range[kmer];
+        const float pk = sh->probs[kmer];
+        const bool ok = pk >= source_prob;
+        if (sub != prev_sub) {
+            if (!EMIT && v2->mfirst[moff + sub] == 0xFFFFu) v2->mfirst[moff + sub] = (u16) nsrc;
+            if (ok) {
+                if (kr.x <= cur.x - 1u) {
+                    const u32 sidx = E.src_before + nsrc;
+                    if (EMIT && E.nc + sidx < E.maxp) {
+                        write_source(E.next, E.hist_e, E.S0 + E.nc + sidx, kr.x, cur.x - 1u, kmer, pk);
+                        E.onext[E.nc + sidx] = E.S0 + E.nc + sidx;
+                    }
+                    nsrc++;
+                }
+                un_st = cur.y + 1u; un_en = kr.y;
+            }
+        }
+        prev_sub = sub;
+        const bool has_next = i + 1u < n;
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (has_next) nxt = keys[i + 1u];
+        const bool dup = has_next && nxt.x == cur.x && nxt.y == cur.y;
+        const u32 rec = cur.w >> 14;
+        if (EMIT) E.onext[E.pos0 + i] = rec | (dup ? UNC_INVALID : 0u);
+        if (dup) continue;
+        if (ok) {
+            u32 src_st = un_st, src_en = un_en;
+            if (has_next && ((nxt.w >> 6) & 0xFFu) == sub) {
+                src_en = nxt.x - 1u;
+                if (un_st <= nxt.y) un_st = nxt.y + 1u;
+            }
+            if (src_st <= src_en) {
+                const u32 sidx = E.src_before + nsrc;
+                if (EMIT && E.nc + sidx < E.maxp) {
+                    write_source(E.next, E.hist_e, E.S0 + E.nc + sidx, src_st, src_en, kmer, pk);
+                    E.onext[E.nc + sidx] = E.S0 + E.nc + sidx;
+                }
+                nsrc++;
+            }
+        }
+        if (cur.w & 1u) {
+            if (EMIT) {
+                d_atomic_or(&((u32 *) (E.next + (size_t) rec * 2))[3], 0x80000000u);   // sa_checked_
+                const u32 ri = E.n_ended_rows + E.seeds_before + nseed;
+                if (ri < E.rl_cap) E.rlist[ri] = make_uint2(ix.seq_len - unc_sa_lookup(ix, cur.x, pend_steps, pend_blocks), (cur.w >> 1) & 0x1Fu);
+                else sh->wk_overflow = 1;
+            }
+            nseed++;
+        }
+    }
+    return nsrc | (nseed << 16);
+}
+
 // exclusive prefix of the bucket counts (one warp): lane i owns ranks 32i .. 32i+31 = slots j*32 + i
 UNC_DEV void k2v2_bucket_offsets(K2V2 *v2) {
     const u32 lane = (u32) w_lane();
@@ -273,9 +361,6 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
     uint2 *stage_r = (uint2 *) (sh->v2_stage + (size_t) ww * K2V2_STAGE_BYTES);
     u8 *stage_m = (u8 *) (stage_r + K2_CH_SLOTS);
     u32 *whist = sh->hist_cur + (size_t) ww * 256u;    // warp-private radix counters (big buckets)
-#ifdef UNC_EMUL
-    if (wt == 0 && getenv("UNC_EMU_TRACE_V2")) fprintf(stderr, "k2v2 read %u\n", r);
-#endif
     PT_DECL
 
     for (; event_i < n_limit; event_i++) {
@@ -297,6 +382,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
             if (lane == 0) v2->fresh_cand[j] = m;
         }
         if (wt == 0) { v2->grab[0] = 0; v2->grab[1] = 0; }
+        if (wt < K2V2_MAX_MERGED) v2->mfirst[wt] = 0xFFFFu;
         c_sync_sub(1, (int) nwt);
         PT_MARK(0)
 
@@ -423,7 +509,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         next[(size_t) ci * 2 + 1] = make_uint4(spb, f2u(newC), 0u, 0u);
                         hist_e[ci] = make_uint2(f2u(newC), poi);
                         cks[ci] = make_uint4(rg.x, rg.y, spb, ckm | (seedable ? 1u << 10 : 0u) | ((u32) d_popc(nmoves) << 11));
-                        s_atomic_add(&v2->kcnt[v2->krank[ckm]], 1u);
+                        s_atomic_add(&v2->kcnt[v2->t.kslot[ckm]], 1u);
                     }
                 }
                 w_sync();                                       // the staging area is rewritten by the next chunk
@@ -507,7 +593,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                 if (base >= nc) break;
                 const u32 end = c + 1 < nch_prev ? sh->bcnt[c + 1] : nc_total;
                 for (u32 i = (u32) lane; base + i < end && base + i < nc; i += 32)
-                    s_atomic_add(&v2->kcnt[v2->krank[cks[(size_t) c * K2_CH_SLOTS + i].w & UNC_KMASK]], 1u);
+                    s_atomic_add(&v2->kcnt[v2->t.kslot[cks[(size_t) c * K2_CH_SLOTS + i].w & UNC_KMASK]], 1u);
             }
             c_sync_sub(1, (int) nwt);
             if (ww == 0) {
@@ -531,8 +617,9 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                 for (u32 i = (u32) lane; base + i < end && base + i < nc; i += 32) {
                     const u32 ci = c * K2_CH_SLOTS + i;
                     uint4 key = cks[ci];
-                    const u32 bk = v2->krank[key.w & UNC_KMASK];
-                    key.w = ((key.w >> 10) & 0x3Fu) | (ci << 6);    // seedable | move_count << 1 | record index << 6
+                    const u32 km = key.w & UNC_KMASK;
+                    const u32 bk = v2->t.kslot[km];
+                    key.w = ((key.w >> 10) & 0x3Fu) | ((u32) v2->t.ksub[km] << 6) | (ci << 14);   // seedable | move_count << 1 | sub << 6 | record index << 14
                     ckA[s_atomic_add(&v2->kcnt[bk], 1u)] = key;
                 }
             }
@@ -548,13 +635,34 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                 const u32 grp = gi & 31u;
                 const u32 sl = (u32) lane * 32u + grp;                 // slot of rank 32*grp + lane
                 const u32 bo = v2->koff[sl], bn = v2->kcnt[sl] - bo;
+                const u32 meta = v2->t.gmeta[grp * 32u + (u32) lane];
                 if (gi < 32u) {
-                    u32 todo = w_ballot(bn > 32u);
+                    u32 todo_m = w_ballot(meta != 0 && bn > 0);
+                    while (todo_m) {                                  // merged groups: sort, then one lane walks the bucket
+                        const int l = d_ffs(todo_m) - 1;
+                        todo_m &= todo_m - 1;
+                        const u32 o = w_shfl(bo, l), n = w_shfl(bn, l), moff = w_shfl(meta, l) >> 8;
+                        if (n <= 32u) k2v2_sort_small(ckA + o, n, (uint4 *) stage_r);
+                        else {
+                            u32 lo = 0xFFFFFFFFu, hi = 0;
+                            for (u32 g = (u32) lane; g < n; g += 32u) { const u32 x = ckA[o + g].x; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+                            hi = w_max(hi);
+                            lo = ~w_max(~lo);
+                            k2v2_sort_big(ckA, ckB, o, n, lo, 32u - (u32) d_clz(hi - lo), whist);
+                        }
+                        if (lane == 0) {
+                            K2V2Emit E;
+                            E.src_before = 0; E.seeds_before = 0;
+                            v2->kagg[(u32) l * 32u + grp] = k2v2_walk_merged<false>(ix, sh, ckA + o, n, moff, source_prob, E, &pend_steps, &pend_blocks);
+                        }
+                        w_sync();
+                    }
+                    u32 todo = w_ballot(bn > 32u && meta == 0);
                     while (todo) {
                         const int l = d_ffs(todo) - 1;
                         todo &= todo - 1;
                         const u32 o = w_shfl(bo, l), n = w_shfl(bn, l);
-                        const u32 kmer = v2->rkmer[grp * 32u + (u32) l];
+                        const u32 kmer = v2->t.gkmer[grp * 32u + (u32) l];
                         const uint2 kr = tb->kmer_range[kmer];
                         const bool prob_ok = sh->probs[kmer] >= source_prob;
                         // span of the bucket's fm_start values -> radix passes
@@ -579,7 +687,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         if (lane == 0) v2->kagg[(u32) l * 32u + grp] = n_src | (n_seed << 16);
                     }
                 } else {
-                    const u32 cnt = (bn > 0 && bn <= 32u) ? bn : 0u;
+                    const u32 cnt = (bn > 0 && bn <= 32u && meta == 0) ? bn : 0u;
                     u32 tot;
                     const u32 P = w_exscan(cnt, &tot);
                     u32 remaining = w_ballot(cnt != 0);
@@ -603,7 +711,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         if (pk.a) { cur = sst[lane]; ckA[addr] = cur; }
                         w_sync();
                         const u32 nx = w_shfl_down(cur.x, 1), ny = w_shfl_down(cur.y, 1);
-                        const u32 kmer = v2->rkmer[grp * 32u + pk.bl];
+                        const u32 kmer = v2->t.gkmer[grp * 32u + pk.bl];
                         const uint2 kr = tb->kmer_range[kmer];
                         const bool prob_ok = sh->probs[kmer] >= source_prob;
                         u32 mxo;
@@ -635,8 +743,17 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                 v2->kagg[sl] = run;
                 // sources_added_[kmer] is set at a run start while the buffer is not full
                 if (nc > 0 && v2->kcnt[sl] != v2->koff[sl]) {
-                    const u32 kmer = v2->rkmer[(u32) lane * 32u + j];
-                    if (sh->probs[kmer] >= source_prob && nc + (run & 0xFFFFu) < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
+                    const u32 meta = v2->t.gmeta[(u32) lane * 32u + j];
+                    if (meta == 0) {
+                        const u32 kmer = v2->t.gkmer[(u32) lane * 32u + j];
+                        if (sh->probs[kmer] >= source_prob && nc + (run & 0xFFFFu) < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
+                    } else {
+                        for (u32 m = 0; m < (meta & 0xFFu); m++) {        // every k-mer of the merged group that has a run
+                            const u32 f = v2->mfirst[(meta >> 8) + m], kmer = v2->t.mk[(meta >> 8) + m];
+                            if (f != 0xFFFFu && sh->probs[kmer] >= source_prob && nc + (run & 0xFFFFu) + f < maxp)
+                                s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
+                        }
+                    }
                 }
                 run = ((run & 0xFFFFu) + (v & 0xFFFFu)) | (((run >> 16) + (v >> 16)) << 16);
             }
@@ -677,11 +794,25 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                 const u32 sl = (u32) lane * 32u + grp;
                 const u32 bo = v2->koff[sl], bn = v2->kcnt[sl] - bo, bpre = v2->kagg[sl];
                 const bool small_sweep = gi >= 32u;
-                const u32 cnt = (small_sweep && bn > 0 && bn <= 32u) ? bn : 0u;
+                const u32 meta = v2->t.gmeta[grp * 32u + (u32) lane];
+                u32 todo_m = small_sweep ? 0u : w_ballot(meta != 0 && bn > 0);
+                while (todo_m) {                                      // merged groups: one lane walks the sorted bucket
+                    const int l = d_ffs(todo_m) - 1;
+                    todo_m &= todo_m - 1;
+                    if (lane == l) {
+                        K2V2Emit E;
+                        E.next = next; E.hist_e = hist_e; E.onext = onext; E.rlist = rlist;
+                        E.S0 = S0; E.nc = nc; E.maxp = maxp; E.n_ended_rows = n_ended_rows; E.rl_cap = W.rl_cap; E.pos0 = bo;
+                        E.src_before = bpre & 0xFFFFu; E.seeds_before = bpre >> 16;
+                        k2v2_walk_merged<true>(ix, sh, ckA + bo, bn, meta >> 8, source_prob, E, &pend_steps, &pend_blocks);
+                    }
+                    w_sync();
+                }
+                const u32 cnt = (small_sweep && bn > 0 && bn <= 32u && meta == 0) ? bn : 0u;
                 u32 tot;
                 const u32 P = w_exscan(cnt, &tot);
                 u32 remaining = small_sweep ? w_ballot(cnt != 0) : 0u;
-                u32 todo = small_sweep ? 0u : w_ballot(bn > 32u);
+                u32 todo = small_sweep ? 0u : w_ballot(bn > 32u && meta == 0);
                 while (todo | remaining) {
                     // one pass: a pack of small buckets, or the next 32 keys of one large bucket
                     K2V2Pack pk;
@@ -694,7 +825,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         o_big = w_shfl(bo, l_big); n_big = w_shfl(bn, l_big);
                         pk.bl = (u32) l_big; pk.start = 0; pk.n = n_big; pk.pos = (u32) lane; pk.a = (u32) lane < n_big;
                     }
-                    const u32 kmer = v2->rkmer[grp * 32u + pk.bl];
+                    const u32 kmer = v2->t.gkmer[grp * 32u + pk.bl];
                     const uint2 kr = tb->kmer_range[kmer];
                     const float pkm = sh->probs[kmer];
                     const bool prob_ok = pkm >= source_prob;
@@ -722,7 +853,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                             write_source(next, hist_e, S0 + nc + sidx2, wk.as, wk.ae, kmer, pkm);
                             onext[nc + sidx2] = S0 + nc + sidx2;
                         }
-                        const u32 rec = cur.w >> 6;
+                        const u32 rec = cur.w >> 14;
                         if (a) onext[o + pos] = rec | (wk.dup ? UNC_INVALID : 0u);
                         // update_seeds(child, false): unique, move-headed, full-length, probable paths
                         if (wk.seed) {

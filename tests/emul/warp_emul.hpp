@@ -205,6 +205,7 @@ static inline double d_sqrt(double a) { return sqrt(a); }
 static inline uint32_t f_to_u32_x86(float v) { return (uint32_t) (long long) v; }
 static inline uint64_t f_to_u64(float v) { return (uint64_t) v; }
 template <typename T> static inline T d_ldg(const T *p) { return *p; }
+static inline void d_prefetch(const void *p) { (void) p; }
 static inline uint64_t s_load_u64(const uint64_t *p) { return *p; }
 static inline void s_store_u64(uint64_t *p, uint64_t v) { *p = v; }
 static inline uint4 s_load_v4(const uint4 *p) { return *p; }

@@ -27,8 +27,9 @@ static_assert(sizeof(DevReadDesc) == 32, "DevReadDesc layout");
 #define K2_WARPS 8          /* 1 tracker warp + (K2_WARPS-1) worker warps per read */
 #endif
 #ifndef K2_MIN_CTAS
-#define K2_MIN_CTAS 2
+#define K2_MIN_CTAS 3       /* second worker structure: 80 registers, 3 CTAs x 8 warps per SM */
 #endif
+#define K2_MIN_CTAS_V1 2    /* first structure (exact-ties kernels): 127 registers */
 #define K2_THREADS (K2_WARPS * 32)
 #ifdef K2_TRK_INLINE
 static_assert(K2_WARPS >= 1 && K2_WARPS <= K2_MAXSEG, "worker warps (all of them) must fit the sort segments");
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(128) k1_norm(DevBatch B, DevParams p) {
 // and the thresholds in shared memory, then pulls reads from a global queue; the K2_WARPS warps
 // of the CTA cooperate on every event of the read (chained scans through shared memory).
 #define K2_MAP_KERNEL(NAME, EXACT, FLAGS)                                                                                       \
-    __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)                                                             \
+    __global__ void __launch_bounds__(K2_THREADS, (EXACT) ? K2_MIN_CTAS_V1 : K2_MIN_CTAS)                                  \
     NAME(DevIndex ix, DevParams p, DevBatch B, DevWork W0, size_t paths_stride, size_t hist_stride, size_t ckey_stride,     \
          size_t cks_stride, size_t elist_stride, size_t order_stride, size_t rlist_stride, size_t clu_stride,              \
          size_t dir_stride) {                                                                                              \
@@ -148,6 +149,28 @@ __global__ void k_fm_sa(DevIndex ix, u32 n, const u64 *rows, u64 *out) {
 
 static thread_local std::string g_err;
 static int g_device = 0;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and process-wide (per device): pools with different
+// max_paths need different amounts, so the attribute is only ever RAISED (a running maximum per kernel and device).
+template <typename F>
+static cudaError_t raise_dyn_smem(F kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<std::pair<const void *, int>, size_t>> seen;
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::pair<const void *, int> key((const void *) kernel, dev);
+    for (auto &e : seen)
+        if (e.first == key) {
+            if (e.second >= bytes) return cudaSuccess;
+            cudaError_t r = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+            if (r == cudaSuccess) e.second = bytes;
+            return r;
+        }
+    cudaError_t r = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    if (r == cudaSuccess) seen.push_back({key, bytes});
+    return r;
+}
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -404,7 +427,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     cudaDeviceProp prop;
     PT(cudaGetDeviceProperties(&prop, idx->device));
     P->smem = K2_SMEM_BYTES(prm->max_paths);
-    PT(cudaFuncSetAttribute(k2_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
+    PT(raise_dyn_smem(k2_map, P->smem));
     int per_sm = 0;
     PT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_map, K2_THREADS, P->smem));
     if (per_sm < 1) return bail(UNC_E_CUDA, "k2_map does not fit on an SM");
@@ -413,7 +436,7 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     if (grid > max_reads) grid = max_reads;
     {
         const size_t k1_smem = (size_t) K1_WARPS * sizeof(K1WarpSmem);
-        PT(cudaFuncSetAttribute(k1_events, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k1_smem));
+        PT(raise_dyn_smem(k1_events, k1_smem));
         int k1_per_sm = 0;
         PT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1_per_sm, k1_events, K1_WARPS * 32, k1_smem));
         if (k1_per_sm < 1) return bail(UNC_E_CUDA, "k1_events does not fit on an SM");
@@ -595,7 +618,7 @@ static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, co
             CUDA_TRY(cudaMalloc(&P->d_flags_in, (size_t) P->max_reads * 128));
             CUDA_TRY(cudaMalloc(&P->d_flags_out, (size_t) P->max_reads * 128));
             CUDA_TRY(cudaMalloc(&P->d_cand, (size_t) P->max_reads * 128));
-            CUDA_TRY(cudaFuncSetAttribute(k2_map_ord, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
+            CUDA_TRY(raise_dyn_smem(k2_map_ord, P->smem));
         }
         CUDA_TRY(cudaMemcpyAsync(P->d_flags_in, h_flags_in, (size_t) n * 128, cudaMemcpyHostToDevice, s));
         B.flags_in = P->d_flags_in;
@@ -701,7 +724,7 @@ int unc_pool_set_tie_order(unc_pool *P, int mode) {
     if (P->pending_n) return fail(UNC_E_ARG, "the pool holds a submitted batch");
     if (mode == 1) {
         CUDA_TRY(cudaSetDevice(P->idx->device));
-        CUDA_TRY(cudaFuncSetAttribute(k2_map_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) P->smem));
+        CUDA_TRY(raise_dyn_smem(k2_map_exact, P->smem));
         // CTAs are independent (each pulls reads from the queue into its own slot), so a lower residency than k2_map's
         // only means that the last CTAs of the grid start late and find the queue empty
     }

@@ -70,11 +70,15 @@ UNC_DEV u32 k2v2_fkey(u32 bits) {
     return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
 }
 UNC_DEV bool k2v2_less(u32 ax, u32 ay, u32 az, u32 aw, u32 bx, u32 by, u32 bz, u32 bw) {
-    if (ax != bx) return ax < bx;
-    if (ay != by) return ay < by;
-    const u32 fa = k2v2_fkey(az), fb = k2v2_fkey(bz);
-    if (fa != fb) return fa < fb;
-    return (aw >> 14) < (bw >> 14);
+    const u64 ha = ((u64) ax << 32) | ay, hb = ((u64) bx << 32) | by;
+    const u64 la = ((u64) k2v2_fkey(az) << 32) | (aw >> 14), lb = ((u64) k2v2_fkey(bz) << 32) | (bw >> 14);
+    return ha < hb || (ha == hb && la < lb);
+}
+// the same order on keys whose seed_prob word already holds k2v2_fkey(seed_prob) and whose w holds the record index only
+UNC_DEV bool k2v2_less_pre(u32 ax, u32 ay, u32 af, u32 ar, u32 bx, u32 by, u32 bf, u32 br) {
+    const u64 ha = ((u64) ax << 32) | ay, hb = ((u64) bx << 32) | by;
+    const u64 la = ((u64) af << 32) | ar, lb = ((u64) bf << 32) | br;
+    return ha < hb || (ha == hb && la < lb);
 }
 
 // One k-mer bucket [o, o+n) of `keys`, n > 32, sorted by ONE warp: LSD radix on (fm_start - lo) over the bits
@@ -240,9 +244,10 @@ UNC_DEV void k2v2_sort_small(uint4 *keys, u32 n, uint4 *sst) {
     uint4 k = make_uint4(0, 0, 0, 0);
     if (a) k = keys[lane];
     u32 rnk = 0;
+    const u32 kf = k2v2_fkey(k.z), kr_ = k.w >> 14;
     for (u32 j = 0; j < n; j++) {
-        const u32 jx = w_shfl(k.x, (int) j), jy = w_shfl(k.y, (int) j), jz = w_shfl(k.z, (int) j), jw = w_shfl(k.w, (int) j);
-        if (k2v2_less(jx, jy, jz, jw, k.x, k.y, k.z, k.w)) rnk++;
+        const u32 jx = w_shfl(k.x, (int) j), jy = w_shfl(k.y, (int) j), jf = w_shfl(kf, (int) j), jr = w_shfl(kr_, (int) j);
+        if (k2v2_less_pre(jx, jy, jf, jr, k.x, k.y, kf, kr_)) rnk++;
     }
     if (a) sst[rnk] = k;
     w_sync();
@@ -397,20 +402,33 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         //      children, in emission order, to records / keys [c*160, c*160+count)
         const u32 nch_prev = (prev_size + 31u) >> 5;
         {
-            u32 oi_n = UNC_INVALID; uint4 q0_n = make_uint4(0, 0, 0, 0); uint2 q1_n = make_uint2(0, 0);   // q1: (seed_prob, C)
+            // software pipeline per warp: the order entry of chunk c+2*nwk is loaded (and its record line requested),
+            // the record of chunk c+nwk is loaded (and the Occ block of its row start-1 requested), chunk c is consumed
+            u32 oi_n = UNC_INVALID, oi_nn = UNC_INVALID; uint4 q0_n = make_uint4(0, 0, 0, 0); uint2 q1_n = make_uint2(0, 0);   // q1: (seed_prob, C)
             if (ww < nch_prev) {
                 const u32 pi = ww * 32u + (u32) lane;
                 if (pi < prev_size) oi_n = oprev[pi];
                 if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = *(const uint2 *) (pr + 1); }
             }
+            if (ww + nwk < nch_prev) {
+                const u32 pi = (ww + nwk) * 32u + (u32) lane;
+                if (pi < prev_size) oi_nn = oprev[pi];
+                if (!(oi_nn & UNC_INVALID)) d_prefetch(prev + (size_t) oi_nn * 2);
+            }
             for (u32 c = ww; c < nch_prev; c += nwk) {
                 const u32 oi = oi_n;
                 const uint4 q0 = q0_n; const uint2 q1 = q1_n;
                 const bool valid = !(oi & UNC_INVALID);
-                if (c + nwk < nch_prev) {                       // software prefetch of the next chunk's order entry + record
-                    const u32 pi = (c + nwk) * 32u + (u32) lane;
-                    oi_n = pi < prev_size ? oprev[pi] : UNC_INVALID;
-                    if (!(oi_n & UNC_INVALID)) { const uint4 *pr = prev + (size_t) oi_n * 2; q0_n = pr[0]; q1_n = *(const uint2 *) (pr + 1); }
+                oi_n = oi_nn;
+                if (c + nwk < nch_prev && !(oi_n & UNC_INVALID)) {
+                    const uint4 *pr = prev + (size_t) oi_n * 2;
+                    q0_n = pr[0]; q1_n = *(const uint2 *) (pr + 1);
+                }
+                oi_nn = UNC_INVALID;
+                if (c + 2u * nwk < nch_prev) {
+                    const u32 pi = (c + 2u * nwk) * 32u + (u32) lane;
+                    if (pi < prev_size) oi_nn = oprev[pi];
+                    if (!(oi_nn & UNC_INVALID)) d_prefetch(prev + (size_t) oi_nn * 2);
                 }
                 // -- parent per lane: thresholds, wanted bases, FM ranges of the four neighbours
                 const u32 st = q0.x, en = q0.y, kmer = q0.z & UNC_KMASK, plen = (q0.z >> 16) & 0xFFu, stays = (q0.z >> 24) & 0xFFu;
@@ -512,6 +530,10 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         s_atomic_add(&v2->kcnt[v2->t.kslot[ckm]], 1u);
                     }
                 }
+                if (c + nwk < nch_prev && !(oi_n & UNC_INVALID)) {      // the next chunk's Occ block (row start-1), requested early
+                    const u32 k0n = q0_n.x - 1u;
+                    d_prefetch(ix.occ2 + ((size_t) ((k0n - (k0n >= ix.primary)) >> 6) << 1));
+                }
                 w_sync();                                       // the staging area is rewritten by the next chunk
             }
         }
@@ -610,13 +632,23 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         if (nc > 0) {
             // ---- C1. scatter the keys into their k-mer buckets (any order inside a bucket: the record index is
             //          part of the key); each warp takes the chunks it extended
+            uint4 kpre = make_uint4(0, 0, 0, 0);                     // the first 32 keys of the warp's next chunk, requested early
+            if (ww < nch_prev) {
+                const u32 b0 = sh->bcnt[ww], e0 = ww + 1 < nch_prev ? sh->bcnt[ww + 1] : nc_total;
+                if (b0 + (u32) lane < e0 && b0 + (u32) lane < nc) kpre = cks[(size_t) ww * K2_CH_SLOTS + (u32) lane];
+            }
             for (u32 c = ww; c < nch_prev; c += nwk) {
                 const u32 base = sh->bcnt[c];
                 if (base >= nc) break;                              // later chunks lie beyond the max_paths cut
                 const u32 end = c + 1 < nch_prev ? sh->bcnt[c + 1] : nc_total;
+                const uint4 kcur = kpre;
+                if (c + nwk < nch_prev) {
+                    const u32 bn = sh->bcnt[c + nwk], en = c + nwk + 1 < nch_prev ? sh->bcnt[c + nwk + 1] : nc_total;
+                    if (bn + (u32) lane < en && bn + (u32) lane < nc) kpre = cks[(size_t) (c + nwk) * K2_CH_SLOTS + (u32) lane];
+                }
                 for (u32 i = (u32) lane; base + i < end && base + i < nc; i += 32) {
                     const u32 ci = c * K2_CH_SLOTS + i;
-                    uint4 key = cks[ci];
+                    uint4 key = i < 32u ? kcur : cks[ci];
                     const u32 km = key.w & UNC_KMASK;
                     const u32 bk = v2->t.kslot[km];
                     key.w = ((key.w >> 10) & 0x3Fu) | ((u32) v2->t.ksub[km] << 6) | (ci << 14);   // seedable | move_count << 1 | sub << 6 | record index << 14
@@ -699,10 +731,11 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         // rank every key among the keys of its bucket, deal the keys out in sorted order
                         const u32 maxn = w_max(pk.a ? pk.n : 0u);
                         u32 rnk = 0;
+                        const u32 kf = k2v2_fkey(k.z), kri = k.w >> 14;
                         for (u32 q = 0; q < maxn; q++) {
                             const int src = (int) ((pk.start + q) & 31u);
-                            const u32 jx = w_shfl(k.x, src), jy = w_shfl(k.y, src), jz = w_shfl(k.z, src), jw = w_shfl(k.w, src);
-                            if (pk.a && q < pk.n && k2v2_less(jx, jy, jz, jw, k.x, k.y, k.z, k.w)) rnk++;
+                            const u32 jx = w_shfl(k.x, src), jy = w_shfl(k.y, src), jf = w_shfl(kf, src), jr = w_shfl(kri, src);
+                            if (pk.a && q < pk.n && k2v2_less_pre(jx, jy, jf, jr, k.x, k.y, kf, kri)) rnk++;
                         }
                         uint4 *sst = (uint4 *) stage_r;
                         if (pk.a) sst[pk.start + rnk] = k;

@@ -18,7 +18,7 @@ k2_map_stream(DevIndex ix, DevParams p, DevBatch B, DevWork W0, DevWorkStrides S
 }
 
 // the exact-ties instantiation (unc_stream_set_tie_order): the reference's unstable child sort reproduced, unc_pdqsort.cuh
-__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS_V1)
 k2_map_stream_exact(DevIndex ix, DevParams p, DevBatch B, DevWork W0, DevWorkStrides S) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unc_k2_cta_main_stream<true>(ix, p, B, W0, S, (K2Shared *) smem_raw);
@@ -68,7 +68,7 @@ int unc_stream_set_tie_order(unc_stream *T, int mode) {
     if (!T || (mode != 0 && mode != 1)) return fail(UNC_E_ARG, "bad argument");
     if (mode == 1) {
         CUDA_TRY(cudaSetDevice(T->idx->device));
-        CUDA_TRY(cudaFuncSetAttribute(k2_map_stream_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T->smem));
+        CUDA_TRY(raise_dyn_smem(k2_map_stream_exact, T->smem));
     }
     T->tie_order = mode;
     return UNC_OK;
@@ -94,7 +94,7 @@ int unc_stream_create(const unc_index *idx, const unc_params *prm, uint32_t n_ch
     cudaDeviceProp prop;
     ST(cudaGetDeviceProperties(&prop, idx->device));
     T->smem = K2_SMEM_BYTES(prm->max_paths);
-    ST(cudaFuncSetAttribute(k2_map_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T->smem));
+    ST(raise_dyn_smem(k2_map_stream, T->smem));
     int per_sm = 0;
     ST(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_map_stream, K2_THREADS, T->smem));
     if (per_sm < 1) return bail(UNC_E_CUDA, "k2_map_stream does not fit on an SM");

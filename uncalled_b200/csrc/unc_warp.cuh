@@ -58,6 +58,8 @@ UNC_DEV double d_sqrt(double a) { return __dsqrt_rn(a); }
 UNC_DEV uint32_t f_to_u32_x86(float v) { return (uint32_t) (long long) v; }
 UNC_DEV uint64_t f_to_u64(float v) { return (uint64_t) v; }
 template <typename T> UNC_DEV T d_ldg(const T *p) { return __ldg(p); }
+// hint: bring the line holding *p towards the SM (no register is held while it is in flight)
+UNC_DEV void d_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // single 128-bit volatile shared-memory accesses (one transaction: payload + flag together)
 UNC_DEV uint4 s_load_v4(const uint4 *p) {
     uint4 v;

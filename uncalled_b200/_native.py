@@ -107,6 +107,25 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_pymodule(force=False):
+    """Compile the `_uncalled` extension module (csrc/pyuncalled.cpp, pybind11) next to libunc_b200.so: the reference's
+    Python package imports its C++ core under that name (uncalled/__init__.py:1), so with this directory and the
+    reference's `uncalled/` on PYTHONPATH its own `scripts/uncalled` runs on the B200 path."""
+    import sysconfig
+    import pybind11
+    src = os.path.join(PKG_DIR, "csrc", "pyuncalled.cpp")
+    out = os.path.join(PKG_DIR, "_uncalled" + sysconfig.get_config_var("EXT_SUFFIX"))
+    deps = [src, os.path.join(ROOT, "include", "unc_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
+           src, "-o", out, "-L" + PKG_DIR, "-lunc_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise UncError("g++ failed on pyuncalled.cpp:\n" + r.stdout + r.stderr)
+    return out
+
+
 _lib = None
 
 

@@ -85,7 +85,7 @@ UNC_DEV bool k2v2_less_pre(u32 ax, u32 ay, u32 af, u32 ar, u32 bx, u32 by, u32 b
 // the bucket's span needs, then runs of equal fm_start ordered by (fm_end, seed_prob, record index).
 // `tmp` is the ping-pong partner of `keys` (same index range), `hist` 256 warp-private counters.
 // The sorted keys end in `keys`.
-UNC_DEV void k2v2_sort_big(uint4 *keys, uint4 *tmp, u32 o, u32 n, u32 lo, u32 span_bits, u32 *hist) {
+UNC_DEV_NOINLINE void k2v2_sort_big(uint4 *keys, uint4 *tmp, u32 o, u32 n, u32 lo, u32 span_bits, u32 *hist) {
     const int lane = w_lane();
     const u32 lt = w_lanemask_lt();
     const u32 npass = (span_bits + 7u) >> 3;
@@ -499,6 +499,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                     const int L = (int) (m & 31u);
                     const u32 j = m >> 5;                                         // 0 = stay, 1..4 = move with base j-1
                     const u32 pz = w_shfl(q0.z, L), pw = w_shfl(q0.w, L), pC = w_shfl(q1.y, L), poi = w_shfl(oi, L);
+                    u32 myslot = 0x10000u + (u32) lane;                          // inactive lanes: no peer
                     if (act) {
                         const u32 pk = pz & UNC_KMASK, ppl = (pz >> 16) & 0xFFu, pst = (pz >> 24) & 0xFFu;
                         const u32 ckm = j == 0 ? pk : (((pk << 2) & UNC_KMASK) | (j - 1u));
@@ -527,7 +528,11 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         next[(size_t) ci * 2 + 1] = make_uint4(spb, f2u(newC), 0u, 0u);
                         hist_e[ci] = make_uint2(f2u(newC), poi);
                         cks[ci] = make_uint4(rg.x, rg.y, spb, ckm | (seedable ? 1u << 10 : 0u) | ((u32) d_popc(nmoves) << 11));
-                        s_atomic_add(&v2->kcnt[v2->t.kslot[ckm]], 1u);
+                        myslot = v2->t.kslot[ckm];
+                    }
+                    {   // one shared-memory atomic per distinct bucket among the 32 children (children of neighbouring parents share k-mers)
+                        const u32 peers = w_match(myslot);
+                        if (act && (u32) lane == (u32) d_ffs(peers) - 1u) s_atomic_add(&v2->kcnt[myslot], (u32) d_popc(peers));
                     }
                 }
                 if (c + nwk < nch_prev && !(oi_n & UNC_INVALID)) {      // the next chunk's Occ block (row start-1), requested early
@@ -646,13 +651,25 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                     const u32 bn = sh->bcnt[c + nwk], en = c + nwk + 1 < nch_prev ? sh->bcnt[c + nwk + 1] : nc_total;
                     if (bn + (u32) lane < en && bn + (u32) lane < nc) kpre = cks[(size_t) (c + nwk) * K2_CH_SLOTS + (u32) lane];
                 }
-                for (u32 i = (u32) lane; base + i < end && base + i < nc; i += 32) {
+                const u32 cnt_c = (end < nc ? end : nc) - base;          // this chunk's keys inside the cut (uniform)
+                for (u32 i0 = 0; i0 < cnt_c; i0 += 32) {
+                    const u32 i = i0 + (u32) lane;
+                    const bool a = i < cnt_c;
                     const u32 ci = c * K2_CH_SLOTS + i;
-                    uint4 key = i < 32u ? kcur : cks[ci];
+                    uint4 key = make_uint4(0, 0, 0, 0);
+                    if (a) key = i < 32u ? kcur : cks[ci];
                     const u32 km = key.w & UNC_KMASK;
-                    const u32 bk = v2->t.kslot[km];
-                    key.w = ((key.w >> 10) & 0x3Fu) | ((u32) v2->t.ksub[km] << 6) | (ci << 14);   // seedable | move_count << 1 | sub << 6 | record index << 14
-                    ckA[s_atomic_add(&v2->kcnt[bk], 1u)] = key;
+                    const u32 bk = a ? (u32) v2->t.kslot[km] : 0x10000u + (u32) lane;
+                    // one cursor atomic per distinct bucket; the lanes of a bucket take consecutive places
+                    const u32 peers = w_match(bk);
+                    const int leader = d_ffs(peers) - 1;
+                    u32 pos = 0;
+                    if (a && lane == leader) pos = s_atomic_add(&v2->kcnt[bk], (u32) d_popc(peers));
+                    pos = w_shfl(pos, leader) + (u32) d_popc(peers & lt);
+                    if (a) {
+                        key.w = ((key.w >> 10) & 0x3Fu) | ((u32) v2->t.ksub[km] << 6) | (ci << 14);   // seedable | move_count << 1 | sub << 6 | record index << 14
+                        ckA[pos] = key;
+                    }
                 }
             }
             c_sync_sub(1, (int) nwt);

@@ -185,6 +185,7 @@ static inline uint32_t d_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; 
 static inline uint32_t d_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 static inline uint32_t s_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline uint32_t s_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+static inline uint32_t s_atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
 static inline int d_popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int d_popcll(uint64_t v) { return __builtin_popcountll(v); }
 static inline int d_clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }

@@ -7,13 +7,10 @@ F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 
 rm -rf variants variants_pt; mkdir -p variants variants_pt
 SRC="csrc/unc_abi.cu csrc/unc_index_build.cpp csrc/unc_fast5.cpp -lz"
 build() { nvcc $F "${@:2}" -o "variants/$1.so" $SRC; }
-build v2_c2 -DK2_MIN_CTAS=2 &
-build v2_w12c2 -DK2_WARPS=12 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
-build v2_w16c2 -DK2_WARPS=16 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
-build v2_w10c3 -DK2_WARPS=10 -DK2_MAXSEG=16u -DK2_MIN_CTAS=3 &
+build v2_w8c2 -DK2_WARPS=8 -DK2_MIN_CTAS=2 &
+build v2_w12c2 -DK2_WARPS=12 -DK2_MIN_CTAS=2 &
+build v2_w14c2 -DK2_WARPS=14 -DK2_MIN_CTAS=2 &
+build v2_w16c2 -DK2_WARPS=16 -DK2_MIN_CTAS=2 &
 wait
-build v2_w24c1 -DK2_WARPS=24 -DK2_MAXSEG=32u -DK2_MIN_CTAS=1 &
-build v2_w20c1 -DK2_WARPS=20 -DK2_MAXSEG=32u -DK2_MIN_CTAS=1 &
-build v2_w14c2 -DK2_WARPS=14 -DK2_MAXSEG=16u -DK2_MIN_CTAS=2 &
-wait
-ls -la variants
+nvcc $F -DUNC_PHASE_TIMING -DK2_WARPS=14 -DK2_MIN_CTAS=2 -o variants_pt/v2_w14c2.so $SRC
+ls -la variants variants_pt

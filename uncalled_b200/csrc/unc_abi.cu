@@ -24,12 +24,12 @@ static_assert(sizeof(DevReadDesc) == 32, "DevReadDesc layout");
 // ------------------------------------------------------------------ kernels
 
 #ifndef K2_WARPS
-#define K2_WARPS 8          /* 1 tracker warp + (K2_WARPS-1) worker warps per read */
+#define K2_WARPS 14         /* 1 tracker warp + (K2_WARPS-1) worker warps per read */
 #endif
 #ifndef K2_MIN_CTAS
-#define K2_MIN_CTAS 3       /* second worker structure: 80 registers, 3 CTAs x 8 warps per SM */
+#define K2_MIN_CTAS 2       /* second worker structure: 2 CTAs x 14 warps per SM (72 registers) measured best */
 #endif
-#define K2_MIN_CTAS_V1 2    /* first structure (exact-ties kernels): 127 registers */
+#define K2_MIN_CTAS_V1 (K2_WARPS > 8 ? 1 : 2)    /* first structure (exact-ties kernels): 127 registers */
 #define K2_THREADS (K2_WARPS * 32)
 #ifdef K2_TRK_INLINE
 static_assert(K2_WARPS >= 1 && K2_WARPS <= K2_MAXSEG, "worker warps (all of them) must fit the sort segments");

@@ -37,6 +37,7 @@ UNC_DEV uint32_t d_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v);
 UNC_DEV uint32_t d_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
 UNC_DEV uint32_t s_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 UNC_DEV uint32_t s_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
+UNC_DEV uint32_t s_atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
 UNC_DEV int d_popc(uint32_t v) { return __popc(v); }
 UNC_DEV int d_popcll(uint64_t v) { return __popcll(v); }
 UNC_DEV int d_clz(uint32_t v) { return __clz((int) v); }

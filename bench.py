@@ -213,8 +213,9 @@ def run_reference_arm(args, rank, world):
 
 def stream_job(sm, sigs, steps, warmup, barrier, on_timed_start=None):
     """W untimed + K timed passes of all reads through a stream mapper (anything with .step and .map_reads);
-    returns (total ms of the K passes, per-pass counters of the C-ABI steps, the last pass's results)."""
+    returns (total ms of the K passes, per-pass counters of the C-ABI steps, the last pass's results, step latencies)."""
     counters = {"steps": 0, "chunks": 0, "bytes": 0}
+    lat = []
     inner = sm.step
 
     def counting_step(descs, n, flat, res):
@@ -222,11 +223,14 @@ def stream_job(sm, sigs, steps, warmup, barrier, on_timed_start=None):
         counters["chunks"] += sum(1 for i in range(n) if descs[i].n_samples)
         counters["bytes"] += int(flat.nbytes)
         inner(descs, n, flat, res)
+        if hasattr(sm, "last_step_ms"):
+            lat.append(sm.last_step_ms())
     sm.step = counting_step
     for _ in range(warmup):
         sm.map_reads(sigs)
     for k in counters:
         counters[k] = 0
+    del lat[:]
     if on_timed_start:
         on_timed_start()
     barrier()
@@ -237,20 +241,51 @@ def stream_job(sm, sigs, steps, warmup, barrier, on_timed_start=None):
     barrier()
     ms = (time.perf_counter() - t0) * 1e3
     sm.step = inner
-    return ms, counters, res
+    return ms, counters, res, lat
+
+
+def cpu_stream_run(prefix, sigs, n_channels, chunk_len, threads):
+    """The reference's streaming path on the CPU (oracle/_ref: one Mapper per channel, chunk by chunk through
+    Mapper::new_read / add_chunk / process_chunk / map_chunk, channels on `threads` worker threads) over the same reads."""
+    import ctypes as C
+    import orclib
+    n = len(sigs)
+    flat = np.ascontiguousarray(np.concatenate(sigs), np.float32)
+    lens = np.array([len(x) for x in sigs], np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.uint64)]).astype(np.uint64)
+    if not orclib.ref_available():
+        return None
+    R = orclib.ref()
+    R.ref_load(prefix.encode(), b"default")
+    out = (orclib.RefPaf * n)()
+    nch = (C.c_uint32 * n)()
+    en = (C.c_int32 * n)()
+    t = time.time()
+    R.ref_stream_channels_mt(orclib.fp(flat), offs.ctypes.data_as(orclib.u64p), lens.ctypes.data_as(orclib.u32p), n, n_channels,
+                             chunk_len / float(bench_sample_rate()), 1000000, threads, out, nch, en)
+    dt = time.time() - t
+    keys = [(orclib.paf_tuple(out[i]), int(nch[i]), int(en[i])) for i in range(n)]
+    return n / dt, dt, int(sum(nch)), keys
+
+
+def bench_sample_rate():
+    return 4000.0
 
 
 def run_stream_workload(args, rank, local_rank, world):
-    """configs[4]-like: chunk streaming (450-sample chunks = chunk_time 0.1125 s) over 512 channels with persistent
-    per-channel device state (unc_stream_step), reads following each other on every channel.  A step = all reads
-    of the workload streamed to completion.  Every chunk crosses the host boundary (pageable host buffer -> H2D inside
-    unc_stream_step), so there is only an end-to-end number: `value` repeats it and says so."""
+    """configs[4]: chunk streaming (450-sample chunks = chunk_time 0.1125 s) over 512 channels of one flow cell with
+    persistent per-channel device state (unc_stream_step), reads following each other on every channel; with --gpus N the
+    channels are dealt out c -> rank c mod N (64 per GPU at N = 8).  A step of the metric = all reads of the workload
+    streamed to completion.  Every chunk crosses the host boundary (host buffer -> H2D inside unc_stream_step), so there is
+    only an end-to-end number: `value` repeats it and says so.  Also reported: chunks/s and the per-step wall-clock time
+    (the decision latency a ReadUntil client sees for every chunk of the step)."""
     import torch
     import torch.distributed as dist
     import synth
     import synthdata
     import uncalled_b200 as U
-    n_channels, chunk_len = 512, 450
+    total_channels, chunk_len = 512, 450
+    n_channels = (total_channels + world - 1 - rank) // world       # channel c lives on rank c % world
     n_reads = n_channels * args.reads_per_channel
     prefix, g = synthdata.get_index(GENOME)
     sig, _ = synth.reads(g, n_reads, N_SAMPLES, seed=7 + 1000 * rank, noise_mult=NOISE_MULT)
@@ -263,27 +298,52 @@ def run_stream_workload(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    ms, counters, res = stream_job(sm, sigs, args.steps, args.warmup, barrier, sampler.start if rank == 0 else None)
+    ms, counters, res, lat = stream_job(sm, sigs, args.steps, args.warmup, barrier, sampler.start if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     v = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_reads), float(counters["chunks"]) / args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms = float(v[0]) / args.steps
-    value = world * n_reads / (ms / 1e3)
+    all_reads, all_chunks = float(tot[0]), float(tot[1])
+    value = all_reads / (ms / 1e3)
     if rank == 0:
         mapped = sum(1 for r in res if r is not None and r[0] == 2)
+        la = np.array(lat) if lat else np.zeros(1)
         line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32/f64 events, u32 FM index", "data": "synthetic",
-                "config": {"workload": "configs[4]-like chunk streaming: %d channels x %d-sample chunks, %d reads x %d samples "
-                                       "per GPU, 4.7 Mb synthetic index" % (n_channels, chunk_len, n_reads, N_SAMPLES),
+                "config": {"workload": "configs[4]: chunk streaming, %d channels x %d-sample chunks (%d channels on this GPU), %d reads x %d "
+                                       "samples per channel, 4.7 Mb synthetic index, noise %.1f x level stdv"
+                                       % (total_channels, chunk_len, n_channels, args.reads_per_channel, N_SAMPLES, NOISE_MULT),
                            "timing": "wall clock around the whole streamed job, barrier + cuda.synchronize on both sides "
                                      "(every step is a synchronous C-ABI call); value == e2e (no device-resident variant)",
-                           "chunk_steps_per_job": counters["steps"] / args.steps, "chunks_per_job": counters["chunks"] / args.steps,
+                           "chunk_steps_per_job": counters["steps"] / args.steps, "chunks_per_job": all_chunks,
                            "mapped_fraction": mapped / n_reads},
+                "chunks_per_s": all_chunks / (ms / 1e3),
+                "step_latency_ms": {"p50": float(np.percentile(la, 50)), "p99": float(np.percentile(la, 99)), "max": float(la.max()),
+                                    "note": "wall clock of one unc_stream_step on rank 0 (H2D of the chunks, event detection + mapping of all "
+                                            "their events, D2H of the results): every chunk of the step gets its decision after this long"},
                 "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": int(counters["bytes"] / args.steps),
                         "d2h_bytes_per_step": int(counters["chunks"] / args.steps * 160), "ms_per_step": ms},
                 "gpu_launches": int(2 * counters["steps"]), "clocks": clocks}
+        if not args.no_cpu_baseline and world == 1:
+            cpus = host_cpus()
+            nsub = min(n_channels, max(16, 2 * cpus["usable"]))          # a bounded number of whole channels
+            sub = [sigs[i] for i in range(n_reads) if i % n_channels < nsub]
+            r = cpu_stream_run(prefix, sub, nsub, chunk_len, cpus["usable"])
+            if r is not None:
+                rps, dt, nchunks, keys = r
+                import orclib
+                # parity on the same channels: the channels [0, nsub) of the GPU run are exactly these reads in this order
+                gpu = [res[i] for i in range(n_reads) if i % n_channels < nsub]
+                bad = [j for j in range(len(sub)) if gpu[j] is None or (U.paf_key(gpu[j][3]), int(gpu[j][2]), int(gpu[j][1])) != keys[j]]
+                line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "chunks_per_s": nchunks / dt, "cores": cpus["usable"], "kind": "reference",
+                                        "host_cpus": cpus, "sample": "%d channels x %d reads (the first channels of the same workload), %d threads, "
+                                                                     "%.1f s; one Mapper per channel as RealtimePool" % (nsub, args.reads_per_channel, cpus["usable"], dt)}
+                line["parity"] = {"reads": len(sub), "identical": len(sub) - len(bad), "differing_ids": bad[:32],
+                                  "fields": "PAF fields, chunks used, ended; default kernel vs the unmodified reference (tie order may differ, DESIGN.md section 2)"}
         print(json.dumps(line), flush=True)
     sm.close()
     if world > 1:

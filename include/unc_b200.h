@@ -257,6 +257,13 @@ int unc_stream_step(unc_stream *st, const unc_chunk_desc *chunks, uint32_t n, co
 /* Tie order of the per-event child sort for this stream's steps: see unc_pool_set_tie_order (1 = the reference's pdqsort
  * reproduced; applies from the next step on, the per-channel state is unaffected). */
 int unc_stream_set_tie_order(unc_stream *st, int mode);
+/* Mapper::PRMS.chunk_timeout (src/mapper.cpp:40,384-390; default there 4000 ms, FLT_MAX for `uncalled map` / sim,
+ * conf.hpp:89-90): a read whose chunk has been with the mapper for longer fails and is marked ended.  Here a chunk is with
+ * the mapper for the duration of the step that maps it, so the test is made once per step on the step's wall-clock time
+ * (off until set).  The reference's evt_timeout only makes a thread yield and has no counterpart.  unc_stream_last_step_ms:
+ * wall-clock time of the last step, copies included (the per-chunk decision latency a ReadUntil client sees). */
+int unc_stream_set_chunk_timeout(unc_stream *st, float ms);
+float unc_stream_last_step_ms(const unc_stream *st);
 void unc_stream_free(unc_stream *st);
 
 /* ---- `uncalled index` after the BWA build ----------------------------------------------------------

@@ -253,6 +253,39 @@ int ref_stream_channel(const float *samples, const uint64_t *offsets, const uint
     return 0;
 }
 
+// A flow cell's worth of channels on n_threads worker threads: read i sits on channel i % n_channels, the reads of a
+// channel follow each other through that channel's ONE Mapper (RealtimePool keeps one Mapper per channel and hands the
+// channels to its threads, reference src/realtime_pool.cpp:38-72).  Used for timing the streaming path's CPU arm.
+int ref_stream_channels_mt(const float *samples, const uint64_t *offsets, const uint32_t *lens, uint32_t n_reads,
+                           uint32_t n_channels, float chunk_time, uint32_t max_chunks, int n_threads, ref_paf_rec *out,
+                           uint32_t *n_chunks_used, int32_t *ended) {
+    Mapper::PRMS.evt_timeout = 1e30f;
+    Mapper::PRMS.chunk_timeout = 1e30f;
+    float old_ct = ReadBuffer::PRMS.chunk_time;
+    u32 old_mc = ReadBuffer::PRMS.max_chunks;
+    ReadBuffer::PRMS.chunk_time = chunk_time;
+    ReadBuffer::PRMS.max_chunks = max_chunks;
+    if (n_threads < 1) n_threads = 1;
+    std::atomic<uint32_t> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) {
+        th.emplace_back([&]() {
+            for (;;) {
+                uint32_t c = next.fetch_add(1);
+                if (c >= n_channels) break;
+                Mapper m;
+                uint32_t number = 0;
+                for (uint32_t i = c; i < n_reads; i += n_channels)
+                    stream_one(m, samples + offsets[i], lens[i], ++number, out + i, n_chunks_used ? n_chunks_used + i : nullptr,
+                               ended ? ended + i : nullptr);
+            }
+        });
+    }
+    for (auto &t : th) t.join();
+    ReadBuffer::PRMS.chunk_time = old_ct; ReadBuffer::PRMS.max_chunks = old_mc;
+    return 0;
+}
+
 // self_align (reference src/self_align_ref.cpp:34-91) as `uncalled index` calls it: FM range lengths along
 // the reference from deterministically sampled start positions.  Returns the number of paths; a second call
 // with buffers copies them out (CSR: offsets[n+1], values[offsets[n]]).

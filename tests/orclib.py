@@ -270,6 +270,8 @@ def ref(stable_sort=False):
         lib.ref_map_batch_mt.argtypes = [f32p, u64p, u32p, C.c_uint32, C.c_int, C.POINTER(RefPaf)]
         lib.ref_stream_channel.argtypes = [f32p, u64p, u32p, C.c_uint32, C.c_float, C.c_uint32, C.POINTER(RefPaf),
                                            C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
+        lib.ref_stream_channels_mt.argtypes = [f32p, u64p, u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, C.c_int,
+                                               C.POINTER(RefPaf), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
         lib.ref_stream_read.argtypes = [f32p, C.c_uint32, C.c_float, C.c_uint32, C.POINTER(RefPaf),
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
         lib.ref_index_build.argtypes = [C.c_char_p, C.c_char_p]

@@ -319,3 +319,25 @@ def test_stream_with_exact_ties(U):
     finally:
         lib.orc_set_child_sort(0)
     assert (2, 0) in st
+
+
+@pytest.mark.gpu
+def test_stream_chunk_timeout_fails_the_reads_still_mapping():
+    """Mapper::PRMS.chunk_timeout (reference src/mapper.cpp:40,384-390): a read whose chunk stayed with the mapper longer
+    than the limit fails and is marked ended.  With an impossible limit every read that does not map within its first
+    chunk ends FAILURE + ended after that step; without a limit the same reads go on."""
+    import synth
+    import synthdata
+    import uncalled_b200 as U
+    from uncalled_b200 import stream as S
+    prefix, g = synthdata.get_index("g200k")
+    sig, _ = synth.reads(g, 6, 4000, seed=3, frac_random=1.0)          # random reads: nothing maps in one chunk
+    idx = U.Index(prefix, device=0)
+    sm = U.StreamMapper(idx, 6, 450)
+    free = sm.map_reads([sig[i] for i in range(6)])
+    assert all(r is not None and r[2] > 1 for r in free)               # several chunks consumed
+    assert sm.last_step_ms() > 0
+    sm.set_chunk_timeout(1e-6)
+    cut = sm.map_reads([sig[i] for i in range(6)])
+    assert all(r is not None and r[0] == S.FAILURE and r[1] == 1 and r[2] == 1 for r in cut)
+    sm.close()

@@ -51,6 +51,12 @@ def get_parser(conf):
     p.add_argument("--batch-reads", type=int, default=conf.batch_reads, help="Reads per GPU batch")
     p.add_argument("--ordered", action="store_const", const=1, default=conf.ordered, help=type(conf).ordered.__doc__)
     p.add_argument("--exact-ties", action="store_const", const=1, default=conf.exact_ties, help=type(conf).exact_ties.__doc__)
+
+    p = sp.add_parser("pafstats", help="Computes speed and accuracy of UNCALLED mappings.", formatter_class=fmt)
+    p.add_argument("infile", type=str, help="PAF file output by UNCALLED")          # uncalled/pafstats.py:165-169
+    p.add_argument("-n", "--max-reads", required=False, type=int, default=None, help="Will only look at first n reads if specified")
+    p.add_argument("-r", "--ref-paf", required=False, type=str, default=None, help="Reference PAF file. Will output percent true/false "
+                   "positives/negatives with respect to reference. Reads not mapped in reference PAF will be classified as NA.")
     return parser
 
 
@@ -151,6 +157,9 @@ def main(argv=None):
         index_cmd(args)
     elif args.subcmd == "map":
         map_cmd(conf, args)
+    elif args.subcmd == "pafstats":
+        from . import pafstats
+        pafstats.run(args.infile, args.ref_paf, args.max_reads)
     else:
         parser.print_help()
     return 0

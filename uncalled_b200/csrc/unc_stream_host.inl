@@ -38,6 +38,8 @@ struct unc_stream {
     size_t smem = 0;
     uint32_t grid = 0;
     int tie_order = 0;           // unc_stream_set_tie_order
+    float chunk_timeout_ms = 3.0e38f;   // unc_stream_set_chunk_timeout (Mapper::PRMS.chunk_timeout; off by default, as `uncalled map` / sim set FLT_MAX)
+    float last_step_ms = 0.0f;
     // per-call buffers (capacity n_channels items)
     void *d_samples = nullptr;
     DevReadDesc *d_reads = nullptr, *h_reads = nullptr;
@@ -73,6 +75,17 @@ int unc_stream_set_tie_order(unc_stream *T, int mode) {
     T->tie_order = mode;
     return UNC_OK;
 }
+
+// Mapper::PRMS.chunk_timeout (reference src/mapper.cpp:40,384-390): a read whose chunk has been with the mapper for longer
+// than this fails and is marked ended.  A chunk is "with the mapper" for the duration of the step that maps it (the step
+// returns when all of its chunks' events are mapped; the reference's per-call evt_timeout only yields a thread and has
+// no effect on results), so the test is made once per step, on the step's wall-clock time.
+int unc_stream_set_chunk_timeout(unc_stream *T, float ms) {
+    if (!T || !(ms > 0)) return fail(UNC_E_ARG, "bad argument");
+    T->chunk_timeout_ms = ms;
+    return UNC_OK;
+}
+float unc_stream_last_step_ms(const unc_stream *T) { return T ? T->last_step_ms : 0.0f; }
 
 int unc_stream_create(const unc_index *idx, const unc_params *prm, uint32_t n_channels, uint32_t max_chunk_len,
                       uint32_t max_chunks, unc_stream **out) {
@@ -166,15 +179,27 @@ int unc_stream_step(unc_stream *T, const unc_chunk_desc *chunks, uint32_t n, con
     uint32_t m = 0;
     uint64_t hi = 0;
     uint32_t dtype = 0xFFFFFFFFu;
+    // validate every descriptor before any channel's bookkeeping changes (an error leaves the stream as it was)
     for (uint32_t i = 0; i < n; i++) {
         const unc_chunk_desc &c = chunks[i];
         if (c.channel >= T->n_channels) return fail(UNC_E_ARG, "channel out of range");
         if (seen[c.channel]) return fail(UNC_E_ARG, "two chunks for one channel in one step");
         seen[c.channel] = 1;
         if (c.n_samples > T->max_chunk_len) return fail(UNC_E_TOO_LARGE, "chunk longer than max_chunk_len");
+        if (c.dtype > 1) return fail(UNC_E_ARG, "unknown dtype");
+        if (c.n_samples || c.new_read) {
+            if (dtype == 0xFFFFFFFFu) dtype = c.dtype;
+            if (c.dtype != dtype) return fail(UNC_E_ARG, "mixed dtype in a step");
+            hi = std::max<uint64_t>(hi, c.offset + c.n_samples);
+        }
+    }
+    if (hi > (uint64_t) T->n_channels * T->max_chunk_len) return fail(UNC_E_TOO_LARGE, "samples exceed the staging buffer");
+    if (dtype == 0xFFFFFFFFu) dtype = 0;
+    hi = 0;
+    const auto t_step0 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < n; i++) {
+        const unc_chunk_desc &c = chunks[i];
         if (!stream_admit(T->ch[c.channel], c, T->max_chunks)) continue;
-        if (dtype == 0xFFFFFFFFu) dtype = c.dtype;
-        if (c.dtype != dtype || dtype > 1) return fail(UNC_E_ARG, "mixed or unknown dtype in a step");
         DevReadDesc &d = T->h_reads[m];
         d.offset = c.offset; d.n_samples = c.n_samples; d.dtype = c.dtype;
         d.cal_range = c.cal_range; d.cal_offset = c.cal_offset; d.cal_digit = c.cal_digit; d.pad = 0;
@@ -183,7 +208,6 @@ int unc_stream_step(unc_stream *T, const unc_chunk_desc *chunks, uint32_t n, con
         item_of[i] = (int) m++;
     }
     if (m) {
-        if (hi > (uint64_t) T->n_channels * T->max_chunk_len) return fail(UNC_E_TOO_LARGE, "samples exceed the staging buffer");
         cudaStream_t s = T->stream;
         const uint64_t span = hi * (dtype == UNC_DTYPE_F32 ? 4 : 2);
         CUDA_TRY(cudaMemcpyAsync(T->d_samples, samples, span, cudaMemcpyHostToDevice, s));
@@ -212,6 +236,8 @@ int unc_stream_step(unc_stream *T, const unc_chunk_desc *chunks, uint32_t n, con
         CUDA_TRY(cudaMemcpyAsync(T->h_flags, T->d_flags, (size_t) m * 4, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
     }
+    T->last_step_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_step0).count();
+    const bool timed_out = T->last_step_ms > T->chunk_timeout_ms;
     int worst = UNC_OK;
     for (uint32_t i = 0; i < n; i++) {
         HostChan &h = T->ch[chunks[i].channel];
@@ -219,6 +245,7 @@ int unc_stream_step(unc_stream *T, const unc_chunk_desc *chunks, uint32_t n, con
             const unc_paf_rec &r = T->h_out[item_of[i]];
             stream_settle(h, r, T->h_flags[item_of[i]], T->prm.max_events, T->max_chunks);
             if (r.status != 0) worst = UNC_E_OVERFLOW;
+            if (timed_out && h.state == UNC_STREAM_MAPPING) { h.state = UNC_STREAM_FAILURE; h.ended = 1; }   // map_chunk's first test
         }
         stream_result(h, bp_per_samp, &out[i]);
     }

@@ -91,6 +91,15 @@ class StreamMapper:
         """1: the reference's unstable child sort reproduced (exact-ties kernel), 0: emission order (default)."""
         N.check(self.L.unc_stream_set_tie_order(self.h, int(mode)))
 
+    def set_chunk_timeout(self, ms):
+        """Mapper::PRMS.chunk_timeout (reference src/mapper.cpp:40,384-390): reads still mapping after a step that took
+        longer than `ms` of wall-clock time fail and are marked ended.  Off until set."""
+        N.check(self.L.unc_stream_set_chunk_timeout(self.h, float(ms)))
+
+    def last_step_ms(self):
+        """Wall-clock time of the last step (copies included): the decision latency of its chunks."""
+        return float(self.L.unc_stream_last_step_ms(self.h))
+
     def step(self, descs, n, flat, res):
         flat = np.ascontiguousarray(flat)
         rc = self.L.unc_stream_step(self.h, descs, n, flat.ctypes.data, res)

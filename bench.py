@@ -351,6 +351,96 @@ def run_stream_workload(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_fast5_workload(args, rank, local_rank, world):
+    """configs[2]/[3] as written: multi-read fast5 files (4000 reads x 4000 samples each, gzip int16; bench_data/
+    bench_reads_4000x4000.fast5 from tools/make_bench_fast5.py) -> the product's own fast5 reader on the host threads ->
+    int16 over PCIe -> calibration + event detection + mapping on the GPU -> PAF records, through the public MapPool
+    (uncalled_b200/api.py: what `python -m uncalled_b200 map` drives).  With --gpus N the files are dealt out round-robin
+    to the ranks (one process per GPU, no collective), --files is the TOTAL number of files (x 4000 reads).  The same
+    file is queued repeatedly: decode work and PCIe traffic are real every time.  A step = all files once."""
+    import torch
+    import torch.distributed as dist
+    import synthdata
+    import uncalled_b200 as U
+    from uncalled_b200 import api
+    from uncalled_b200.fast5 import Fast5File
+    path = os.path.join(ROOT, "bench_data", "bench_reads_4000x4000.fast5")
+    if not os.path.exists(path):
+        raise SystemExit("bench_data/bench_reads_4000x4000.fast5 is missing: run tools/make_bench_fast5.py where /root/reference exists")
+    prefix, _ = synthdata.get_index(GENOME)
+    cpus = host_cpus()
+    threads = max(1, cpus["usable"] // world)
+    my_files = [path for i in range(args.files) if i % world == rank]
+    n_mine = 4000 * len(my_files)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_pass():
+        conf = api.Conf()
+        conf.bwa_prefix, conf.threads, conf.device, conf.batch_reads = prefix, threads, local_rank, args.batch_reads
+        pool = api.MapPool(conf)
+        for f in my_files:
+            pool.add_fast5(f)
+        n = mapped = 0
+        while pool.running():
+            for p in pool.update():
+                n += 1
+                mapped += 1 if p.is_mapped() else 0
+        pool.stop()
+        return n, mapped
+    for _ in range(min(args.warmup, 1)):
+        one_pass()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    n = mapped = 0
+    for _ in range(args.steps):
+        a, b = one_pass()
+        n += a
+        mapped += b
+    barrier()
+    ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    assert n == n_mine * args.steps
+    # decode alone on this rank's threads (the host stage's capacity)
+    t1 = time.perf_counter()
+    F = Fast5File(path)
+    F.load(0, F.n_reads, threads=threads)
+    F.close()
+    decode_rps = 4000 / (time.perf_counter() - t1)
+    v = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    w = torch.tensor([float(n), float(mapped), decode_rps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    ms = float(v[0]) / args.steps
+    total = float(w[0]) / args.steps
+    value = total / (ms / 1e3)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "i16 DAC in, f32/f64 events, u32 FM index", "data": "synthetic",
+                "config": {"workload": "configs[2]/[3]: %d multi-read fast5 files x 4000 reads x 4000 samples (%d reads) through MapPool: host fast5 "
+                                       "decode (%d threads per rank) -> i16 over PCIe -> GPU; 4.7 Mb synthetic index, noise 1.5 x level stdv"
+                                       % (args.files, int(total), threads),
+                           "timing": "wall clock around the whole job incl. file reading and inflate, barrier + cuda.synchronize on both sides",
+                           "batch_reads": args.batch_reads, "mapped_fraction": float(w[1]) / float(w[0])},
+                "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": int(total * 8000), "d2h_bytes_per_step": int(total * 120), "ms_per_step": ms},
+                "stages": {"host_decode_reads_per_s_all_ranks": float(w[2]), "host_cpus": cpus,
+                           "note": "decode capacity measured alone on the same threads; the GPU stage's capacity is the default workload's `value`; "
+                                   "the slower of the two bounds this number"},
+                "gpu_launches": int(4 * ((n_mine + args.batch_reads - 1) // args.batch_reads)) * world, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -369,8 +459,11 @@ def main():
     ap.add_argument("--exact-ties", action="store_true",
                     help="additionally time the exact-ties kernel (unc_pool_set_tie_order(1): the reference's unstable pdqsort "
                          "reproduced serially per event); reported under 'exact_ties'")
-    ap.add_argument("--workload", default="batch", choices=["batch", "stream"],
-                    help="batch: configs[1] (the headline); stream: chunk streaming over 512 channels (configs[4]-like)")
+    ap.add_argument("--workload", default="batch", choices=["batch", "stream", "fast5"],
+                    help="batch: configs[1] (the headline); stream: chunk streaming over 512 channels (configs[4]); "
+                         "fast5: multi-read fast5 files through MapPool, decode included (configs[2]/[3] as written)")
+    ap.add_argument("--files", type=int, default=16, help="fast5 workload: total number of 4000-read files (all ranks together)")
+    ap.add_argument("--batch-reads", type=int, default=8000, help="fast5 workload: reads per GPU batch")
     ap.add_argument("--reads-per-channel", type=int, default=2)
     args = ap.parse_args()
 
@@ -394,6 +487,9 @@ def main():
 
     if args.workload == "stream":
         run_stream_workload(args, rank, local_rank, world)
+        return
+    if args.workload == "fast5":
+        run_fast5_workload(args, rank, local_rank, world)
         return
 
     n_reads = args.reads

@@ -788,6 +788,12 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         u32 mxo;
                         const K2V2Walk wk = k2v2_walk(cur, nx, ny, pk.a, pk.a && pk.pos + 1u < pk.n, pk.pos == 0, pk.pos == 0, false, 0u,
                                                       prob_ok, kr, &mxo);
+                        // every bucket's own counts go out first (state 1), so that the packs behind this one never wait for
+                        // this pack's look-back: they add these counts up and go on looking for a finished prefix
+                        const u32 sm = k2v2_segmask(pk.start, pk.n);
+                        if (pk.a && pk.pos == 0)
+                            k2v2_publish(v2, pk.bl * 32u + grp, epoch, 1u,
+                                         ((u32) d_popc(wk.m_b & sm) + (u32) d_popc(wk.m_a & sm)) | ((u32) d_popc(wk.m_seed & sm) << 16));
                         // the pack's place: everything before its first bucket
                         const u32 excl = k2v2_lookback(v2, grp * 32u + (u32) s0, epoch);
                         const u32 sidx = (excl & 0xFFFFu) + (u32) d_popc(wk.m_b & lt) + (u32) d_popc(wk.m_a & lt);   // sources before this element
@@ -795,7 +801,6 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         if (pk.a && pk.pos == 0) {
                             // sources_added_[kmer] is set at a run start while the buffer is not full
                             if (prob_ok && nc + sidx < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
-                            const u32 sm = k2v2_segmask(pk.start, pk.n);
                             const u32 incl = (sidx + (u32) d_popc(wk.m_b & sm) + (u32) d_popc(wk.m_a & sm)) | ((qidx + (u32) d_popc(wk.m_seed & sm)) << 16);
                             k2v2_publish(v2, pk.bl * 32u + grp, epoch, 2u, incl);
                             s_atomic_max(&v2->tot, incl);

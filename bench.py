@@ -336,8 +336,11 @@ def run_stream_workload(args, rank, local_rank, world):
             if r is not None:
                 rps, dt, nchunks, keys = r
                 import orclib
-                # parity on the same channels: the channels [0, nsub) of the GPU run are exactly these reads in this order
-                gpu = [res[i] for i in range(n_reads) if i % n_channels < nsub]
+                # parity on the same channels, both sides starting from fresh per-channel state (the timed passes above
+                # reuse one stream, whose channels carry their normaliser statistics and flags from pass to pass)
+                sm2 = U.StreamMapper(idx, nsub, chunk_len)
+                gpu = sm2.map_reads(sub)
+                sm2.close()
                 bad = [j for j in range(len(sub)) if gpu[j] is None or (U.paf_key(gpu[j][3]), int(gpu[j][2]), int(gpu[j][1])) != keys[j]]
                 line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "chunks_per_s": nchunks / dt, "cores": cpus["usable"], "kind": "reference",
                                         "host_cpus": cpus, "sample": "%d channels x %d reads (the first channels of the same workload), %d threads, "

@@ -25,9 +25,9 @@ N.check(L.unc_pool_debug_phases(bm.h, n_reads, ph2.ctypes.data))
 names = ["A probs", "B extend + B1 deferred seed_prob", "B2 scan/ended rows/key compaction", "C radix sort + fix-up", "D dedup/src", "S sa + E",
          "X barrier(tracker)", "head: event load + scaling", "head: verdict + bookkeeping", "head: loop back-edge"]
 if os.environ.get("UNC_PHASES_V1") is None:     # the second worker structure (unc_k2v2.cuh) marks its own phases
-    names = ["A probs + counter reset", "B extension", "C1 scatter into k-mer buckets", "C2+D bucket sort / dedup / sources / seeds (look-back) + S1", "(unused)", "E fresh sources",
+    names = ["A probs + counter reset", "B extension", "C1 scatter into k-mer buckets", "C2 bucket sort + count", "(unused)", "D1 dedup/sources/seeds + E fresh",
              "X barrier(tracker)", "head: event load + scaling", "head: verdict + bookkeeping", "head: loop back-edge",
-             "B2 chunk scan / ended rows / bucket offsets / deferred seed_prob"]
+             "B2 chunk scan / ended rows / bucket offsets / deferred seed_prob", "D0 bucket prefix + flags + fresh plan | S1 SA of ended rows"]
 ev = out["events_used"].astype(np.float64) + 1
 for title, ph in (("worker warp 0, thread 0 (also runs the single-warp sections)", ph2[:, :len(names)]),
                   ("last worker warp, lane 0 (its barrier waits expose the single-warp sections)", ph2[:, 16:16 + len(names)])):

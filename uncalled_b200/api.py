@@ -206,6 +206,7 @@ class MapPool:
         self._queue = []
         self._mappers, self._caps, self._inflight = [None, None], [(0, 0), (0, 0)], None   # two pools: batches overlap
         self._n_added, self._stopped = 0, False
+        self.n_overflowed = 0                                 # reads whose device workspace overflowed (warned about, reported unmapped)
         self._carry = None                                    # conf.ordered: sources_added_ words after the last read mapped
         self._files, self._open, self._next = [], None, 0
         self._future, self._executor = None, None          # fast5 decoding of the NEXT batch overlaps the mapping
@@ -219,7 +220,7 @@ class MapPool:
     def _max_len(self):
         # the fast5 constructor truncates the signal to max_chunks * chunk_len samples
         # (reference src/read_buffer.cpp:229-234; chunk_len = chunk_time * sample_rate, read_buffer.hpp:135-137)
-        chunk_len = int(np.float32(self.conf.chunk_time) * np.float32(self.conf.sample_rate))
+        chunk_len = int(np.float32(self.conf.chunk_time) * np.float32(self.conf.sample_rate)) & 0xFFFF   # chunk_len() returns u16
         return int(self.conf.max_chunks) * chunk_len
 
     def add_read(self, read_id, signal, channel=0, number=0, start_sample=0, calibration=None):
@@ -347,6 +348,12 @@ class MapPool:
         ms = (time.time() - job["t0"]) * 1e3 / len(batch)
         out = []
         for r, rec in zip(batch, recs):
+            if int(rec["status"] if isinstance(rec, np.void) else rec.status) != 0:
+                # the read overflowed its per-read device workspace (seed rows of one event / cluster blocks): its record
+                # is an unmapped one, and that must not pass silently -- the reference would have gone on mapping it
+                self.n_overflowed += 1
+                sys.stderr.write("Warning: read %s overflowed its device workspace (status %d); reported unmapped\n"
+                                 % (r.id, int(rec["status"] if isinstance(rec, np.void) else rec.status)))
             p = _paf_from_rec(self.index.seqs, rec, r.id, r.channel, r.start)
             p.set_float(Paf.Tag.MAP_TIME, ms)
             out.append(p)
@@ -548,6 +555,9 @@ class RealtimePool:
                 if r.state == S.MAPPING or self._read[ch] is None:
                     continue
                 rid, number, start = self._read[ch]
+                if int(r.rec.status) != 0:          # the channel's device workspace overflowed: never silent
+                    sys.stderr.write("Warning: read %s (channel %d) overflowed its device workspace (status %d); reported unmapped\n"
+                                     % (rid, ch + 1, int(r.rec.status)))
                 p = _paf_from_rec(self.index.seqs if self.index is not None else [], r.rec, rid, ch + 1, start)
                 if r.ended:
                     p._ended = True        # Paf::set_ended

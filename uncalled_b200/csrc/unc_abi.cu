@@ -62,7 +62,10 @@ __global__ void k_sa_expand(DevIndex ix, u32 *out, u32 n_rows) {
 #ifndef K1_WARPS
 #define K1_WARPS 4
 #endif
-__global__ void __launch_bounds__(K1_WARPS * 32) k1_events(DevBatch B, DevParams p) {
+#ifndef K1_MIN_CTAS
+#define K1_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(K1_WARPS * 32, K1_MIN_CTAS) k1_events(DevBatch B, DevParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K1WarpSmem *sm = (K1WarpSmem *) smem_raw + (threadIdx.x >> 5);
     unc_k1_warp_main(B, p, sm);
@@ -770,6 +773,7 @@ int unc_map_batch_ordered(unc_pool *P, const unc_read_desc *reads, uint32_t n, c
 int unc_events_batch(unc_pool *P, const unc_read_desc *reads, uint32_t n, const void *samples, uint32_t stride,
                      float *events, float *normed, uint32_t *n_events, float *mean_event_len) {
     if (!P || !reads || !samples) return fail(UNC_E_ARG, "null argument");
+    if (P->pending_n) return fail(UNC_E_ARG, "the pool holds a submitted batch (its staging buffers are in use): call unc_map_batch_wait first");
     CUDA_TRY(cudaSetDevice(P->idx->device));
     uint64_t span = 0;
     uint32_t mx = 0;
@@ -861,6 +865,7 @@ int unc_pool_debug_phases(const unc_pool *P, uint32_t n, unsigned long long *out
 
 int unc_pool_k1_stats(const unc_pool *P, uint32_t out[4]) {
     if (!P || !out) return fail(UNC_E_ARG, "null argument");
+    if (P->pending_n) return fail(UNC_E_ARG, "the pool holds a submitted batch: call unc_map_batch_wait first");
     CUDA_TRY(cudaMemcpy(out, P->d_queue + 2, 16, cudaMemcpyDeviceToHost));
     return UNC_OK;
 }

@@ -840,11 +840,10 @@ struct K2V2 {              // second worker structure (unc_k2v2.cuh)
     K2V2Tab t;
     u32 kcnt[UNC_NKMER];   // per k-mer bucket: children counted during the extension, then the scatter cursor (= bucket end)
     u32 koff[UNC_NKMER];   // bucket start in the sorted key array
-    u64 kpre[UNC_NKMER];   // per bucket: (epoch << 2 | state) << 32 | sources | seeds << 16; state 1: the bucket's own counts, 2: inclusive prefix
-    u32 fresh_cand[32];    // per 32-k-mer word: k-mers that may get a fresh source this event
-    u32 grab[2];           // bucket hand-out counter
-    u32 epoch;             // event counter of this CTA (tags kpre)
-    u32 tot;               // inclusive prefix of the last bucket so far (sources | seeds << 16)
+    u32 kagg[UNC_NKMER];   // (gap sources | child seeds << 16) of the bucket, then their exclusive prefix
+    u32 fresh_cand[32], fresh_mask[32], fresh_before[32];   // fresh-source candidates / plan per 32-k-mer word
+    u32 grab[2];           // bucket hand-out counters (sort pass, emit pass)
+    u16 mfirst[K2V2_MAX_MERGED];   // per merged-group k-mer: gap sources of its bucket before its first run (0xFFFF: no run)
 };
 struct K2Shared {          // per CTA
     K2Tables tb;
@@ -960,8 +959,6 @@ UNC_DEV void unc_k2_cta_setup(const DevIndex &ix, const DevParams &p, K2Shared *
     }
     for (u32 k = (u32) c_tid(); k < 64; k += (u32) c_nthreads()) sh->tb.thresh[k] = ix.thresh[k];
     for (u32 k = (u32) c_tid(); k < (u32) (sizeof(K2V2Tab) / 4); k += (u32) c_nthreads()) ((u32 *) &sh->v2.t)[k] = ((const u32 *) ix.kt)[k];
-    for (u32 k = (u32) c_tid(); k < UNC_NKMER; k += (u32) c_nthreads()) sh->v2.kpre[k] = 0;     // tag 0 = never published (epochs start at 1)
-    if (c_tid() == 0) sh->v2.epoch = 0;
     for (u32 c = (u32) c_tid(); c < n_slots; c += (u32) c_nthreads()) sh->pre[c] = 0;
 #ifdef K2_DFUSE
     for (u32 c = (u32) c_tid(); c < 2u * n_slots; c += (u32) c_nthreads()) sh->agg2[c] = 0;   // tag 0 = never published (epochs start at 1)

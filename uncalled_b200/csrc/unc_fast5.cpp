@@ -97,6 +97,7 @@ struct H5File {
     uint64_t len_at(const uint8_t *p) const { return le(p, L); }
     const uint8_t *abs(uint64_t a, uint64_t n) const {
         if (a == UNDEF) throw H5Error("undefined address");
+        if (base > size || a > size - base) throw H5Error("truncated or corrupt file (address beyond end)");   // no wrap-around in base + a
         return at(base + a, n);
     }
 
@@ -354,7 +355,7 @@ struct H5File {
                 const uint32_t oi = (uint32_t) le(g + q, 2);
                 const uint64_t osz = len_at(g + q + 8);
                 if (oi == 0) break;
-                if (q + 8 + L + osz > csize) throw H5Error("corrupt global heap object");
+                if (osz > csize - (q + 8 + L)) throw H5Error("corrupt global heap object");     // subtraction form: no wrap-around
                 if (oi == index) {
                     const char *s = (const char *) g + q + 8 + L;
                     return std::string(s, strnlen(s, (size_t) osz));

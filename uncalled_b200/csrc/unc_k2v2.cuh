@@ -85,7 +85,12 @@ UNC_DEV bool k2v2_less_pre(u32 ax, u32 ay, u32 af, u32 ar, u32 bx, u32 by, u32 b
 // the bucket's span needs, then runs of equal fm_start ordered by (fm_end, seed_prob, record index).
 // `tmp` is the ping-pong partner of `keys` (same index range), `hist` 256 warp-private counters.
 // The sorted keys end in `keys`.
-UNC_DEV_NOINLINE void k2v2_sort_big(uint4 *keys, uint4 *tmp, u32 o, u32 n, u32 lo, u32 span_bits, u32 *hist) {
+#ifdef K2V2_SORT_NOINLINE
+UNC_DEV_NOINLINE
+#else
+UNC_DEV
+#endif
+void k2v2_sort_big(uint4 *keys, uint4 *tmp, u32 o, u32 n, u32 lo, u32 span_bits, u32 *hist) {
     const int lane = w_lane();
     const u32 lt = w_lanemask_lt();
     const u32 npass = (span_bits + 7u) >> 3;
@@ -201,15 +206,11 @@ struct K2V2Pack {
 };
 // cnt = size of this lane's bucket if it is a small one, else 0; P = exclusive prefix of cnt over the lanes;
 // *remaining = lanes whose buckets are not packed yet (non-zero on entry)
-// blockers: lanes whose (non-empty) buckets are not small ones -- a pack never spans one, so that between the buckets of a
-// pack there are only empty buckets and the pack's own counts are all its later buckets need besides the pack's prefix
-UNC_DEV K2V2Pack k2v2_next_pack(u32 cnt, u32 P, u32 *remaining, u32 blockers) {
+UNC_DEV K2V2Pack k2v2_next_pack(u32 cnt, u32 P, u32 *remaining) {
     const int lane = w_lane();
     const int s = d_ffs(*remaining) - 1;
     const u32 Ps = w_shfl(P, s);
-    const u32 blk_after = blockers & ~((2u << s) - 1u);                 // blockers above lane s
-    const u32 stop = blk_after ? (u32) d_ffs(blk_after) - 1u : 32u;      // the pack ends before this lane
-    const bool fits = ((*remaining >> lane) & 1u) && (u32) lane < stop && (P + cnt - Ps <= 32u);
+    const bool fits = ((*remaining >> lane) & 1u) && (P + cnt - Ps <= 32u);
     const u32 in_pack = w_ballot(fits);               // a prefix of `remaining` (P is non-decreasing); never empty
     *remaining &= ~in_pack;
     const int e = 31 - d_clz(in_pack);
@@ -233,41 +234,6 @@ UNC_DEV u32 k2v2_segmask(u32 start, u32 n) { return (n >= 32u ? 0xFFFFFFFFu : ((
 // bucket rank -> index in the K2V2 per-bucket arrays: rank 32g + i sits at i*32 + g, so that a lane that owns 32
 // consecutive ranks (the prefix sums) and a warp that reads one rank per lane... both touch distinct banks or one
 UNC_DEV u32 k2v2_slot(u32 rank) { return ((rank & 31u) << 5) | (rank >> 5); }
-
-// Decoupled look-back over the buckets (one warp): (sources | seeds << 16) of all buckets of rank < r0.  A bucket's word
-// in kpre carries the event's epoch once published: state 1 = the bucket's own counts, 2 = inclusive prefix; empty buckets
-// (end == start) count nothing and are never published.  Waiting is safe: buckets are taken in rank order within a sweep
-// and the first sweep (which publishes the large buckets' counts) waits for nobody.
-UNC_DEV u32 k2v2_lookback(K2V2 *v2, u32 r0, u32 epoch) {
-    const int lane = w_lane();
-    u32 excl = 0;
-    int look = (int) r0;                                   // ranks [0, look) are still to be added
-    while (look > 0) {
-        const int j = look - 1 - lane;
-        u32 state = 0, val = 0;
-        if (j >= 0) {
-            const u32 sl = k2v2_slot((u32) j);
-            if (*(volatile u32 *) &v2->kcnt[sl] != *(volatile u32 *) &v2->koff[sl]) {
-                for (;;) {
-                    const u64 w = s_load_u64(&v2->kpre[sl]);
-                    if ((u32) (w >> 34) == (epoch & 0x3FFFFFFFu)) { state = (u32) (w >> 32) & 3u; val = (u32) w; break; }
-                    w_spin();
-                }
-            }
-        }
-        const u32 mP = w_ballot(j >= 0 && state == 2u);
-        const u32 upto = mP ? (u32) d_ffs(mP) : 32u;       // lanes [0, upto) contribute (the first prefix found included)
-        u32 c = (j >= 0 && (u32) lane < upto) ? val : 0u;  // the 16-bit fields cannot carry into each other (see the scan of v1's D2)
-        for (int d = 16; d > 0; d >>= 1) c += w_shfl(c, lane ^ d);
-        excl += c;
-        if (mP) break;
-        look -= 32;
-    }
-    return excl;
-}
-UNC_DEV void k2v2_publish(K2V2 *v2, u32 slot, u32 epoch, u32 state, u32 val) {
-    s_store_u64(&v2->kpre[slot], ((u64) (((epoch & 0x3FFFFFFFu) << 2) | state) << 32) | val);
-}
 
 // the next group of 32 bucket ranks for this warp (two sweeps of 32 groups: see phase C2)
 UNC_DEV u32 k2v2_grab(u32 *counter) {
@@ -297,8 +263,8 @@ UNC_DEV void k2v2_sort_small(uint4 *keys, u32 n, uint4 *sst) {
 // The dedup walk over the sorted keys of a MERGED group's bucket (k-mers whose FM ranges overlap): the reference's
 // loop statement by statement (src/mapper.cpp:527-603; the restatement's :1153-1194), by ONE lane -- the k-mer
 // runs interleave here, so nothing about them is known in advance.  EMIT == false: count the bucket's gap sources
-// and child seeds; EMIT == true: set the sources_added_ flags, write the sources, order entries and seed rows at their
-// final places.
+// and child seeds and note, per k-mer, how many sources precede its first run (D0 derives the sources_added_
+// flags from that); EMIT == true: write the sources, order entries and seed rows at their final places.
 struct K2V2Emit {
     uint4 *next; uint2 *hist_e; u32 *onext; uint2 *rlist;
     u32 S0, nc, maxp, n_ended_rows, rl_cap, pos0;      // pos0: sorted position of the bucket's first key
@@ -316,8 +282,8 @@ UNC_DEV u32 k2v2_walk_merged(const DevIndex &ix, K2Shared *sh, const uint4 *keys
         const float pk = sh->probs[kmer];
         const bool ok = pk >= source_prob;
         if (sub != prev_sub) {
+            if (!EMIT && v2->mfirst[moff + sub] == 0xFFFFu) v2->mfirst[moff + sub] = (u16) nsrc;
             if (ok) {
-                if (EMIT && E.nc + E.src_before + nsrc < E.maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));   // sources_added_
                 if (kr.x <= cur.x - 1u) {
                     const u32 sidx = E.src_before + nsrc;
                     if (EMIT && E.nc + sidx < E.maxp) {
@@ -416,7 +382,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         if (FLAGS && wt < 32u) sh->flags_prev[wt] = sh->flags[wt];      // what the read ends with if this event is discarded
         for (u32 k = wt; k < UNC_NKMER; k += nwt) {
             sh->probs[k] = unc_match_prob(event, d_ldg(ix.lv_mean + k), d_ldg(ix.lv_var2 + k), d_ldg(ix.lognorm + k));
-            v2->kcnt[k] = 0;
+            v2->kcnt[k] = 0; v2->kagg[k] = 0;
         }
         for (u32 j = ww; j < 32; j += nwk) {              // k-mers that may get a fresh source (reference src/mapper.cpp:611-614)
             const u32 k = j * 32 + (u32) lane;
@@ -425,7 +391,8 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
             const u32 m = w_ballot(pk >= source_prob && kr.x <= kr.y);
             if (lane == 0) v2->fresh_cand[j] = m;
         }
-        if (wt == 0) { v2->grab[0] = 0; v2->tot = 0; v2->epoch++; }
+        if (wt == 0) { v2->grab[0] = 0; v2->grab[1] = 0; }
+        if (wt < K2V2_MAX_MERGED) v2->mfirst[wt] = 0xFFFFu;
         c_sync_sub(1, (int) nwt);
         PT_MARK(0)
 
@@ -565,7 +532,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         next[(size_t) ci * 2 + 1] = make_uint4(spb, f2u(newC), 0u, 0u);
                         hist_e[ci] = make_uint2(f2u(newC), poi);
                         cks[ci] = make_uint4(rg.x, rg.y, spb, ckm | (seedable ? 1u << 10 : 0u) | ((u32) d_popc(nmoves) << 11));
-                        s_atomic_add(&v2->kcnt[v2->t.kslot[ckm]], 1u);   // (a match.any-aggregated add measured 8 % slower)
+                        s_atomic_add(&v2->kcnt[v2->t.kslot[ckm]], 1u);
                     }
                 }
                 if (c + nwk < nch_prev && !(oi_n & UNC_INVALID)) {      // the next chunk's Occ block (row start-1), requested early
@@ -696,75 +663,76 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
             c_sync_sub(1, (int) nwt);
             PT_MARK(2)
 
-            // ---- C2 + D. sort every bucket; dedup, gap sources, child seeds (reference src/mapper.cpp:527-603).  A bucket is
-            //      one k-mer run.  Buckets are handed out 32 ranks (one group) at a time, in three sweeps:
-            //        1. large (> 32 keys) and merged buckets: sorted by one warp each, their counts published;
-            //        2. small buckets, packed several to a warp pass: sorted in registers, walked, and -- once the
-            //           look-back over the earlier buckets has given the pack its place -- emitted at once;
-            //        3. large and merged buckets again: place from the look-back, then the emitting walk.
-            const u32 epoch = v2->epoch;
+            // ---- C2. sort every bucket and count what its dedup walk will emit.  Buckets are handed out 32 ranks (one
+            //          group) at a time: first sweep the large buckets (> 32 keys, one warp each, radix), second sweep
+            //          the small ones, packed several to a warp pass.
             for (;;) {
                 const u32 gi = k2v2_grab(&v2->grab[0]);
-                if (gi >= 96u) break;
-                const u32 sweep = gi >> 5, grp = gi & 31u;
+                if (gi >= 64u) break;
+                const u32 grp = gi & 31u;
                 const u32 sl = (u32) lane * 32u + grp;                 // slot of rank 32*grp + lane
                 const u32 bo = v2->koff[sl], bn = v2->kcnt[sl] - bo;
                 const u32 meta = v2->t.gmeta[grp * 32u + (u32) lane];
-                const u32 blockers = w_ballot(bn > 0 && (bn > 32u || meta != 0));
-                if (sweep == 0) {
-                    u32 todo = blockers;
-                    while (todo) {
-                        const int l = d_ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const u32 o = w_shfl(bo, l), n = w_shfl(bn, l), mt = w_shfl(meta, l);
+                if (gi < 32u) {
+                    u32 todo_m = w_ballot(meta != 0 && bn > 0);
+                    while (todo_m) {                                  // merged groups: sort, then one lane walks the bucket
+                        const int l = d_ffs(todo_m) - 1;
+                        todo_m &= todo_m - 1;
+                        const u32 o = w_shfl(bo, l), n = w_shfl(bn, l), moff = w_shfl(meta, l) >> 8;
                         if (n <= 32u) k2v2_sort_small(ckA + o, n, (uint4 *) stage_r);
                         else {
-                            u32 lo = 0xFFFFFFFFu, hi = 0;                  // span of the bucket's fm_start values -> radix passes
+                            u32 lo = 0xFFFFFFFFu, hi = 0;
                             for (u32 g = (u32) lane; g < n; g += 32u) { const u32 x = ckA[o + g].x; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
                             hi = w_max(hi);
                             lo = ~w_max(~lo);
                             k2v2_sort_big(ckA, ckB, o, n, lo, 32u - (u32) d_clz(hi - lo), whist);
                         }
-                        u32 agg = 0;
-                        if (mt != 0) {                                   // merged group: one lane walks the bucket
-                            if (lane == 0) {
-                                K2V2Emit E;
-                                E.src_before = 0; E.seeds_before = 0;
-                                agg = k2v2_walk_merged<false>(ix, sh, ckA + o, n, mt >> 8, source_prob, E, &pend_steps, &pend_blocks);
-                            }
-                            agg = w_shfl(agg, 0);
-                        } else {
-                            const u32 kmer = v2->t.gkmer[grp * 32u + (u32) l];
-                            const uint2 kr = tb->kmer_range[kmer];
-                            const bool prob_ok = sh->probs[kmer] >= source_prob;
-                            u32 carry_mx = 0, n_src = 0, n_seed = 0;
-                            for (u32 g0 = 0; g0 < n; g0 += 32u) {
-                                const u32 g = g0 + (u32) lane;
-                                const bool a = g < n, has_next = g + 1u < n;
-                                uint4 cur = make_uint4(0, 0, 0, 0); u32 nx = 0, ny = 0;
-                                if (a) cur = ckA[o + g];
-                                if (has_next) { const uint4 t = ckA[o + g + 1u]; nx = t.x; ny = t.y; }
-                                u32 mxo;
-                                const K2V2Walk wk = k2v2_walk(cur, nx, ny, a, has_next, g == 0, g == 0, g0 != 0, carry_mx, prob_ok, kr, &mxo);
-                                carry_mx = mxo;
-                                n_src += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
-                                n_seed += (u32) d_popc(wk.m_seed);
-                            }
-                            agg = n_src | (n_seed << 16);
+                        if (lane == 0) {
+                            K2V2Emit E;
+                            E.src_before = 0; E.seeds_before = 0;
+                            v2->kagg[(u32) l * 32u + grp] = k2v2_walk_merged<false>(ix, sh, ckA + o, n, moff, source_prob, E, &pend_steps, &pend_blocks);
                         }
-                        if (lane == 0) k2v2_publish(v2, (u32) l * 32u + grp, epoch, 1u, agg);
+                        w_sync();
                     }
-                } else if (sweep == 1) {
+                    u32 todo = w_ballot(bn > 32u && meta == 0);
+                    while (todo) {
+                        const int l = d_ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const u32 o = w_shfl(bo, l), n = w_shfl(bn, l);
+                        const u32 kmer = v2->t.gkmer[grp * 32u + (u32) l];
+                        const uint2 kr = tb->kmer_range[kmer];
+                        const bool prob_ok = sh->probs[kmer] >= source_prob;
+                        // span of the bucket's fm_start values -> radix passes
+                        u32 lo = 0xFFFFFFFFu, hi = 0;
+                        for (u32 g = (u32) lane; g < n; g += 32u) { const u32 x = ckA[o + g].x; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+                        hi = w_max(hi);
+                        lo = ~w_max(~lo);
+                        k2v2_sort_big(ckA, ckB, o, n, lo, 32u - (u32) d_clz(hi - lo), whist);
+                        u32 carry_mx = 0, n_src = 0, n_seed = 0;
+                        for (u32 g0 = 0; g0 < n; g0 += 32u) {
+                            const u32 g = g0 + (u32) lane;
+                            const bool a = g < n, has_next = g + 1u < n;
+                            uint4 cur = make_uint4(0, 0, 0, 0); u32 nx = 0, ny = 0;
+                            if (a) cur = ckA[o + g];
+                            if (has_next) { const uint4 t = ckA[o + g + 1u]; nx = t.x; ny = t.y; }
+                            u32 mxo;
+                            const K2V2Walk wk = k2v2_walk(cur, nx, ny, a, has_next, g == 0, g == 0, g0 != 0, carry_mx, prob_ok, kr, &mxo);
+                            carry_mx = mxo;
+                            n_src += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
+                            n_seed += (u32) d_popc(wk.m_seed);
+                        }
+                        if (lane == 0) v2->kagg[(u32) l * 32u + grp] = n_src | (n_seed << 16);
+                    }
+                } else {
                     const u32 cnt = (bn > 0 && bn <= 32u && meta == 0) ? bn : 0u;
                     u32 tot;
                     const u32 P = w_exscan(cnt, &tot);
                     u32 remaining = w_ballot(cnt != 0);
                     while (remaining) {
-                        const int s0 = d_ffs(remaining) - 1;                       // the pack's first bucket
-                        const K2V2Pack pk = k2v2_next_pack(cnt, P, &remaining, blockers);
-                        const u32 o = w_shfl(bo, (int) pk.bl);
+                        const K2V2Pack pk = k2v2_next_pack(cnt, P, &remaining);
+                        const u32 addr = w_shfl(bo, (int) pk.bl) + pk.pos;
                         uint4 k = make_uint4(0, 0, 0, 0);
-                        if (pk.a) k = ckA[o + pk.pos];
+                        if (pk.a) k = ckA[addr];
                         // rank every key among the keys of its bucket, deal the keys out in sorted order
                         const u32 maxn = w_max(pk.a ? pk.n : 0u);
                         u32 rnk = 0;
@@ -778,33 +746,142 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                         if (pk.a) sst[pk.start + rnk] = k;
                         w_sync();
                         uint4 cur = make_uint4(0, 0, 0, 0);
-                        if (pk.a) cur = sst[lane];
+                        if (pk.a) { cur = sst[lane]; ckA[addr] = cur; }
                         w_sync();
                         const u32 nx = w_shfl_down(cur.x, 1), ny = w_shfl_down(cur.y, 1);
                         const u32 kmer = v2->t.gkmer[grp * 32u + pk.bl];
                         const uint2 kr = tb->kmer_range[kmer];
-                        const float pkm = sh->probs[kmer];
-                        const bool prob_ok = pkm >= source_prob;
+                        const bool prob_ok = sh->probs[kmer] >= source_prob;
                         u32 mxo;
                         const K2V2Walk wk = k2v2_walk(cur, nx, ny, pk.a, pk.a && pk.pos + 1u < pk.n, pk.pos == 0, pk.pos == 0, false, 0u,
                                                       prob_ok, kr, &mxo);
-                        // every bucket's own counts go out first (state 1), so that the packs behind this one never wait for
-                        // this pack's look-back: they add these counts up and go on looking for a finished prefix
                         const u32 sm = k2v2_segmask(pk.start, pk.n);
                         if (pk.a && pk.pos == 0)
-                            k2v2_publish(v2, pk.bl * 32u + grp, epoch, 1u,
-                                         ((u32) d_popc(wk.m_b & sm) + (u32) d_popc(wk.m_a & sm)) | ((u32) d_popc(wk.m_seed & sm) << 16));
-                        // the pack's place: everything before its first bucket
-                        const u32 excl = k2v2_lookback(v2, grp * 32u + (u32) s0, epoch);
-                        const u32 sidx = (excl & 0xFFFFu) + (u32) d_popc(wk.m_b & lt) + (u32) d_popc(wk.m_a & lt);   // sources before this element
-                        const u32 qidx = (excl >> 16) + (u32) d_popc(wk.m_seed & lt);                                    // child seeds before it
-                        if (pk.a && pk.pos == 0) {
-                            // sources_added_[kmer] is set at a run start while the buffer is not full
-                            if (prob_ok && nc + sidx < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
-                            const u32 incl = (sidx + (u32) d_popc(wk.m_b & sm) + (u32) d_popc(wk.m_a & sm)) | ((qidx + (u32) d_popc(wk.m_seed & sm)) << 16);
-                            k2v2_publish(v2, pk.bl * 32u + grp, epoch, 2u, incl);
-                            s_atomic_max(&v2->tot, incl);
+                            v2->kagg[pk.bl * 32u + grp] = ((u32) d_popc(wk.m_b & sm) + (u32) d_popc(wk.m_a & sm)) | ((u32) d_popc(wk.m_seed & sm) << 16);
+                    }
+                }
+            }
+            c_sync_sub(1, (int) nwt);
+            PT_MARK(3)
+        }
+
+        // ---- D0 + S1, concurrently.  Worker warp 0: prefix sum of the buckets' (sources, seeds), the sources_added_
+        //      flags the run starts set (reference src/mapper.cpp:560-562), and the plan of the fresh sources
+        //      (reference :605-624).  The other warps: suffix-array look-ups of the ended paths' seed rows
+        //      (reference :673-681: sa_end = fmi.size() - fmi.sa(s)).
+        if (ww == 0) {
+            // lane i owns ranks 32i .. 32i+31 (slots j*32 + i): its sum, a warp scan of the sums, its running prefix
+            u32 sum = 0;
+            for (u32 j = 0; j < 32; j++) sum += v2->kagg[j * 32u + (u32) lane];
+            u32 ts, tq;
+            const u32 es = w_exscan(sum & 0xFFFFu, &ts), eq = w_exscan(sum >> 16, &tq);
+            u32 run = es | (eq << 16);                       // sources | seeds << 16 before the bucket
+            for (u32 j = 0; j < 32; j++) {
+                const u32 sl = j * 32u + (u32) lane, v = v2->kagg[sl];
+                v2->kagg[sl] = run;
+                // sources_added_[kmer] is set at a run start while the buffer is not full
+                if (nc > 0 && v2->kcnt[sl] != v2->koff[sl]) {
+                    const u32 meta = v2->t.gmeta[(u32) lane * 32u + j];
+                    if (meta == 0) {
+                        const u32 kmer = v2->t.gkmer[(u32) lane * 32u + j];
+                        if (sh->probs[kmer] >= source_prob && nc + (run & 0xFFFFu) < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
+                    } else {
+                        for (u32 m = 0; m < (meta & 0xFFu); m++) {        // every k-mer of the merged group that has a run
+                            const u32 f = v2->mfirst[(meta >> 8) + m], kmer = v2->t.mk[(meta >> 8) + m];
+                            if (f != 0xFFFFu && sh->probs[kmer] >= source_prob && nc + (run & 0xFFFFu) + f < maxp)
+                                s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));
                         }
+                    }
+                }
+                run = ((run & 0xFFFFu) + (v & 0xFFFFu)) | (((run >> 16) + (v >> 16)) << 16);
+            }
+            w_sync();
+            const u32 tot_src = ts;
+            const u32 ns_added = nc + tot_src > maxp ? maxp - nc : tot_src;
+            const u32 nn0 = nc + ns_added;
+            const u32 my_mask = v2->fresh_cand[lane] & ~sh->flags[lane];   // word `lane` of the fresh-source walk
+            u32 tot_add;
+            const u32 my_pre = w_exscan((u32) d_popc(my_mask), &tot_add);
+            v2->fresh_mask[lane] = my_mask;
+            v2->fresh_before[lane] = nn0 + my_pre;           // fill level when the serial walk reaches word `lane`
+            if (lane == 0) {
+                sh->bc[1] = nn0 + tot_add < maxp ? nn0 + tot_add : maxp;
+                sh->bc[6] = tq;
+            }
+        }
+        if (ww != 0 || nwk == 1) {
+            const u32 bt = nwk == 1 ? wt : wt - 32u, nbt = nwk == 1 ? nwt : nwt - 32u;
+            for (u32 i = bt; i < n_ended_rows; i += nbt) {
+                uint2 e = rlist[i];
+                e.x = ix.seq_len - unc_sa_lookup(ix, e.x, &pend_steps, &pend_blocks);
+                rlist[i] = e;
+            }
+        }
+        c_sync_sub(1, (int) nwt);
+        PT_MARK(11)
+        const u32 n_child_seeds = nc > 0 ? sh->bc[6] : 0u;
+        n_rows = n_ended_rows + n_child_seeds;
+        if (n_rows > W.rl_cap) n_rows = W.rl_cap;
+
+        // ---- D1. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603): every bucket is one k-mer run
+        if (nc > 0) {
+            for (;;) {
+                const u32 gi = k2v2_grab(&v2->grab[1]);
+                if (gi >= 64u) break;
+                const u32 grp = gi & 31u;
+                const u32 sl = (u32) lane * 32u + grp;
+                const u32 bo = v2->koff[sl], bn = v2->kcnt[sl] - bo, bpre = v2->kagg[sl];
+                const bool small_sweep = gi >= 32u;
+                const u32 meta = v2->t.gmeta[grp * 32u + (u32) lane];
+                u32 todo_m = small_sweep ? 0u : w_ballot(meta != 0 && bn > 0);
+                while (todo_m) {                                      // merged groups: one lane walks the sorted bucket
+                    const int l = d_ffs(todo_m) - 1;
+                    todo_m &= todo_m - 1;
+                    if (lane == l) {
+                        K2V2Emit E;
+                        E.next = next; E.hist_e = hist_e; E.onext = onext; E.rlist = rlist;
+                        E.S0 = S0; E.nc = nc; E.maxp = maxp; E.n_ended_rows = n_ended_rows; E.rl_cap = W.rl_cap; E.pos0 = bo;
+                        E.src_before = bpre & 0xFFFFu; E.seeds_before = bpre >> 16;
+                        k2v2_walk_merged<true>(ix, sh, ckA + bo, bn, meta >> 8, source_prob, E, &pend_steps, &pend_blocks);
+                    }
+                    w_sync();
+                }
+                const u32 cnt = (small_sweep && bn > 0 && bn <= 32u && meta == 0) ? bn : 0u;
+                u32 tot;
+                const u32 P = w_exscan(cnt, &tot);
+                u32 remaining = small_sweep ? w_ballot(cnt != 0) : 0u;
+                u32 todo = small_sweep ? 0u : w_ballot(bn > 32u && meta == 0);
+                while (todo | remaining) {
+                    // one pass: a pack of small buckets, or the next 32 keys of one large bucket
+                    K2V2Pack pk;
+                    u32 o_big = 0, n_big = 0, g0 = 0, carry_mx = 0, src_acc = 0, seed_acc = 0;
+                    int l_big = 0;
+                    if (small_sweep) pk = k2v2_next_pack(cnt, P, &remaining);
+                    else {
+                        l_big = d_ffs(todo) - 1;
+                        todo &= todo - 1;
+                        o_big = w_shfl(bo, l_big); n_big = w_shfl(bn, l_big);
+                        pk.bl = (u32) l_big; pk.start = 0; pk.n = n_big; pk.pos = (u32) lane; pk.a = (u32) lane < n_big;
+                    }
+                    const u32 kmer = v2->t.gkmer[grp * 32u + pk.bl];
+                    const uint2 kr = tb->kmer_range[kmer];
+                    const float pkm = sh->probs[kmer];
+                    const bool prob_ok = pkm >= source_prob;
+                    const u32 pre = w_shfl(bpre, (int) pk.bl), o = w_shfl(bo, (int) pk.bl);
+                    for (;;) {
+                        const u32 pos = small_sweep ? pk.pos : g0 + (u32) lane;
+                        const bool a = small_sweep ? pk.a : pos < n_big;
+                        const bool has_next = a && pos + 1u < pk.n;
+                        uint4 cur = make_uint4(0, 0, 0, 0);
+                        if (a) cur = ckA[o + pos];
+                        u32 nx = w_shfl_down(cur.x, 1), ny = w_shfl_down(cur.y, 1);
+                        if (!small_sweep && lane == 31 && has_next) { const uint4 t = ckA[o + pos + 1u]; nx = t.x; ny = t.y; }
+                        u32 mxo;
+                        const K2V2Walk wk = k2v2_walk(cur, nx, ny, a, has_next, pos == 0, pos == 0, !small_sweep && g0 != 0, carry_mx, prob_ok,
+                                                      kr, &mxo);
+                        carry_mx = mxo;
+                        const u32 sm = small_sweep ? k2v2_segmask(pk.start, pk.n) : 0xFFFFFFFFu;
+                        const u32 sidx = (pre & 0xFFFFu) + src_acc + (u32) d_popc(wk.m_b & lt & sm) + (u32) d_popc(wk.m_a & lt & sm);   // sources before this element
                         if (wk.begin_v && nc + sidx < maxp) {
                             write_source(next, hist_e, S0 + nc + sidx, kr.x, cur.x - 1u, kmer, pkm);
                             onext[nc + sidx] = S0 + nc + sidx;
@@ -815,132 +892,50 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                             onext[nc + sidx2] = S0 + nc + sidx2;
                         }
                         const u32 rec = cur.w >> 14;
-                        if (pk.a) onext[o + pk.pos] = rec | (wk.dup ? UNC_INVALID : 0u);
+                        if (a) onext[o + pos] = rec | (wk.dup ? UNC_INVALID : 0u);
                         // update_seeds(child, false): unique, move-headed, full-length, probable paths
                         if (wk.seed) {
                             d_atomic_or(&((u32 *) (next + (size_t) rec * 2))[3], 0x80000000u);   // sa_checked_
-                            const u32 ri = n_ended_rows + qidx;
+                            const u32 ri = n_ended_rows + (pre >> 16) + seed_acc + (u32) d_popc(wk.m_seed & lt & sm);
                             if (ri < W.rl_cap)
                                 rlist[ri] = make_uint2(ix.seq_len - unc_sa_lookup(ix, cur.x, &pend_steps, &pend_blocks), (cur.w >> 1) & 0x1Fu);
                             else sh->wk_overflow = 1;
                         }
-                    }
-                } else {
-                    u32 todo = blockers;
-                    while (todo) {
-                        const int l = d_ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const u32 o = w_shfl(bo, l), n = w_shfl(bn, l), mt = w_shfl(meta, l);
-                        const u32 excl = k2v2_lookback(v2, grp * 32u + (u32) l, epoch);
-                        u32 own;
-                        for (;;) {                                    // the bucket's own counts (sweep 1 may still be sorting it on another warp)
-                            const u64 w = s_load_u64(&v2->kpre[(u32) l * 32u + grp]);
-                            if ((u32) (w >> 34) == (epoch & 0x3FFFFFFFu)) { own = (u32) w; break; }
-                            w_spin();
-                        }
-                        const u32 incl = ((excl & 0xFFFFu) + (own & 0xFFFFu)) | (((excl >> 16) + (own >> 16)) << 16);
-                        if (lane == 0) { k2v2_publish(v2, (u32) l * 32u + grp, epoch, 2u, incl); s_atomic_max(&v2->tot, incl); }
-                        if (mt != 0) {
-                            if (lane == 0) {
-                                K2V2Emit E;
-                                E.next = next; E.hist_e = hist_e; E.onext = onext; E.rlist = rlist;
-                                E.S0 = S0; E.nc = nc; E.maxp = maxp; E.n_ended_rows = n_ended_rows; E.rl_cap = W.rl_cap; E.pos0 = o;
-                                E.src_before = excl & 0xFFFFu; E.seeds_before = excl >> 16;
-                                k2v2_walk_merged<true>(ix, sh, ckA + o, n, mt >> 8, source_prob, E, &pend_steps, &pend_blocks);
-                            }
-                            w_sync();
-                            continue;
-                        }
-                        const u32 kmer = v2->t.gkmer[grp * 32u + (u32) l];
-                        const uint2 kr = tb->kmer_range[kmer];
-                        const float pkm = sh->probs[kmer];
-                        const bool prob_ok = pkm >= source_prob;
-                        if (lane == 0 && prob_ok && nc + (excl & 0xFFFFu) < maxp) s_atomic_or(&sh->flags[kmer >> 5], 1u << (kmer & 31u));   // sources_added_
-                        u32 carry_mx = 0, src_acc = excl & 0xFFFFu, seed_acc = excl >> 16;
-                        for (u32 g0 = 0; g0 < n; g0 += 32u) {
-                            const u32 pos = g0 + (u32) lane;
-                            const bool a = pos < n, has_next = pos + 1u < n;
-                            uint4 cur = make_uint4(0, 0, 0, 0);
-                            if (a) cur = ckA[o + pos];
-                            u32 nx = w_shfl_down(cur.x, 1), ny = w_shfl_down(cur.y, 1);
-                            if (lane == 31 && has_next) { const uint4 t = ckA[o + pos + 1u]; nx = t.x; ny = t.y; }
-                            u32 mxo;
-                            const K2V2Walk wk = k2v2_walk(cur, nx, ny, a, has_next, pos == 0, pos == 0, g0 != 0, carry_mx, prob_ok, kr, &mxo);
-                            carry_mx = mxo;
-                            const u32 sidx = src_acc + (u32) d_popc(wk.m_b & lt) + (u32) d_popc(wk.m_a & lt);   // sources before this element
-                            if (wk.begin_v && nc + sidx < maxp) {
-                                write_source(next, hist_e, S0 + nc + sidx, kr.x, cur.x - 1u, kmer, pkm);
-                                onext[nc + sidx] = S0 + nc + sidx;
-                            }
-                            const u32 sidx2 = sidx + (wk.begin_v ? 1u : 0u);
-                            if (wk.after_v && nc + sidx2 < maxp) {
-                                write_source(next, hist_e, S0 + nc + sidx2, wk.as, wk.ae, kmer, pkm);
-                                onext[nc + sidx2] = S0 + nc + sidx2;
-                            }
-                            const u32 rec = cur.w >> 14;
-                            if (a) onext[o + pos] = rec | (wk.dup ? UNC_INVALID : 0u);
-                            if (wk.seed) {
-                                d_atomic_or(&((u32 *) (next + (size_t) rec * 2))[3], 0x80000000u);   // sa_checked_
-                                const u32 ri = n_ended_rows + seed_acc + (u32) d_popc(wk.m_seed & lt);
-                                if (ri < W.rl_cap)
-                                    rlist[ri] = make_uint2(ix.seq_len - unc_sa_lookup(ix, cur.x, &pend_steps, &pend_blocks), (cur.w >> 1) & 0x1Fu);
-                                else sh->wk_overflow = 1;
-                            }
-                            src_acc += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
-                            seed_acc += (u32) d_popc(wk.m_seed);
-                        }
+                        if (small_sweep) break;
+                        src_acc += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
+                        seed_acc += (u32) d_popc(wk.m_seed);
+                        g0 += 32u;
+                        if (g0 >= n_big) break;
                     }
                 }
             }
         }
-        // ---- S1. suffix-array look-ups of the ended paths' seed rows (reference :673-681: sa_end = fmi.size() - fmi.sa(s))
-        for (u32 i = wt; i < n_ended_rows; i += nwt) {
-            uint2 e = rlist[i];
-            e.x = ix.seq_len - unc_sa_lookup(ix, e.x, &pend_steps, &pend_blocks);
-            rlist[i] = e;
-        }
-        c_sync_sub(1, (int) nwt);
-        PT_MARK(3)
-        const u32 tot = nc > 0 ? *(volatile u32 *) &v2->tot : 0u;
-        const u32 n_child_seeds = tot >> 16;
-        n_rows = n_ended_rows + n_child_seeds;
-        if (n_rows > W.rl_cap) n_rows = W.rl_cap;
-
-        // ---- E. fresh sources for every sufficiently probable k-mer without one (reference src/mapper.cpp:605-624).  The
-        //      plan -- word j's candidates and the buffer fill level the serial walk has when it reaches word j -- is
-        //      derived by every warp for itself (lane j holds word j); word j is then written by warp j % nwk.
-        {
-            const u32 tot_src = tot & 0xFFFFu;
-            const u32 ns_added = nc + tot_src > maxp ? maxp - nc : tot_src;
-            const u32 nn0 = nc + ns_added;
-            const u32 my_mask = v2->fresh_cand[lane] & ~sh->flags[lane];
-            u32 tot_add;
-            const u32 my_before = nn0 + w_exscan((u32) d_popc(my_mask), &tot_add);
-            if (wt == 0) sh->bc[1] = nn0 + tot_add < maxp ? nn0 + tot_add : maxp;
-            c_sync_sub(1, (int) nwt);                            // every warp has read the flags before any word is rewritten
-            for (u32 j = ww; j < 32; j += nwk) {
-                const u32 before = w_shfl(my_before, (int) j);
-                u32 m_add = w_shfl(my_mask, (int) j);
-                if (before >= maxp) continue;                         // never visited: its flags stay as they are
-                const u32 k = j * 32 + (u32) lane;
-                const u32 room = maxp - before;
-                u32 visited = 0xFFFFFFFFu;
-                if ((u32) d_popc(m_add) >= room) {
-                    // the room-th add fills the buffer; k-mers after it are never visited
-                    u32 mm = m_add;
-                    for (u32 q = 1; q < room; q++) mm &= mm - 1;
-                    int last = d_ffs(mm) - 1;
-                    visited = last == 31 ? 0xFFFFFFFFu : ((2u << last) - 1u);
-                    m_add &= visited;
-                }
-                const u32 rank = (u32) d_popc(m_add & lt);
-                if ((m_add >> lane) & 1u) {
-                    const uint2 kr = tb->kmer_range[k];
-                    write_source(next, hist_e, S0 + before + rank, kr.x, kr.y, k, sh->probs[k]);
-                    onext[before + rank] = S0 + before + rank;
-                }
-                if (lane == 0) sh->flags[j] &= ~visited;
+        // ---- E. fresh sources for every sufficiently probable k-mer without one (reference src/mapper.cpp:605-624):
+        //      word j (32 k-mers) by warp j % nwk, positions and the buffer-full cut from worker warp 0's plan
+        for (u32 j = ww; j < 32; j += nwk) {
+            const u32 before = v2->fresh_before[j];
+            if (before >= maxp) continue;                         // never visited: its flags stay as they are
+            const u32 k = j * 32 + (u32) lane;
+            const u32 fw = sh->flags[j];
+            u32 m_add = v2->fresh_mask[j];
+            const u32 room = maxp - before;
+            u32 visited = 0xFFFFFFFFu;
+            if ((u32) d_popc(m_add) >= room) {
+                // the room-th add fills the buffer; k-mers after it are never visited
+                u32 mm = m_add;
+                for (u32 q = 1; q < room; q++) mm &= mm - 1;
+                int last = d_ffs(mm) - 1;
+                visited = last == 31 ? 0xFFFFFFFFu : ((2u << last) - 1u);
+                m_add &= visited;
             }
+            const u32 rank = (u32) d_popc(m_add & lt);
+            if ((m_add >> lane) & 1u) {
+                const uint2 kr = tb->kmer_range[k];
+                write_source(next, hist_e, S0 + before + rank, kr.x, kr.y, k, sh->probs[k]);
+                onext[before + rank] = S0 + before + rank;
+            }
+            w_sync();
+            if (lane == 0) sh->flags[j] = fw & ~visited;
         }
         if (wt == 0) *(volatile u32 *) &sh->n_rows[event_i & 1u] = n_rows;
         PT_MARK(5)

@@ -12,6 +12,30 @@
 // (:123-148), partition_right / partition_left (:340-408), the loop with its median selection, pattern-breaking swaps
 // and heapsort fallback (:411-504, libstdc++'s make_heap / sort_heap).  The recursion on the left part is an explicit
 // stack in global memory (the right part is pushed, the left one continued, so the order of work is the header's).
+// ---------------------------------------------------------------------------------------------------------------
+// This file is an ALTERED version of pdqsort.h (index-based device code for 16-byte sort keys, explicit stack instead
+// of recursion, the non-branchless variant only); it is not the original software.  The original's notice, which may
+// not be removed from any source distribution:
+//
+//     pdqsort.h - Pattern-defeating quicksort.
+//
+//     Copyright (c) 2015 Orson Peters
+//
+//     This software is provided 'as-is', without any express or implied warranty. In no event will the
+//     authors be held liable for any damages arising from the use of this software.
+//
+//     Permission is granted to anyone to use this software for any purpose, including commercial
+//     applications, and to alter it and redistribute it freely, subject to the following restrictions:
+//
+//     1. The origin of this software must not be misrepresented; you must not claim that you wrote the
+//        original software. If you use this software in a product, an acknowledgment in the product
+//        documentation would be appreciated but is not required.
+//
+//     2. Altered source versions must be plainly marked as such, and must not be misrepresented as
+//        being the original software.
+//
+//     3. This notice may not be removed or altered from any source distribution.
+// ---------------------------------------------------------------------------------------------------------------
 #pragma once
 
 #ifdef UNC_EMUL

@@ -37,7 +37,7 @@ class Fast5File:
         self._h = C.c_void_p()
         if self._L.unc_fast5_open(os.fsencode(path), C.byref(self._h)) != 0:
             self._h = None
-            raise Fast5Error(self._L.unc_fast5_last_error().decode())
+            raise Fast5Error(self._L.unc_fast5_last_error().decode("utf-8", "replace"))
         n, single = C.c_uint32(), C.c_int()
         self._L.unc_fast5_count(self._h, C.byref(n), C.byref(single))
         self.n_reads, self.single_read_format, self.path = n.value, bool(single.value), path
@@ -61,7 +61,7 @@ class Fast5File:
     def info(self, i):
         r = N.Fast5Read()
         if self._L.unc_fast5_info(self._h, i, C.byref(r)) != 0:
-            raise Fast5Error(self._L.unc_fast5_last_error().decode())
+            raise Fast5Error(self._L.unc_fast5_last_error().decode("utf-8", "replace"))
         return Fast5Read(r, None)
 
     def load(self, first=0, n=None, max_samples_per_read=0, threads=0):
@@ -71,12 +71,12 @@ class Fast5File:
         total = 0
         for i in range(n):
             if self._L.unc_fast5_info(self._h, first + i, C.byref(infos[i])) != 0:
-                raise Fast5Error(self._L.unc_fast5_last_error().decode())
+                raise Fast5Error(self._L.unc_fast5_last_error().decode("utf-8", "replace"))
             ns = infos[i].n_samples
             total += min(ns, max_samples_per_read) if max_samples_per_read else ns
         buf = np.zeros(max(total, 1), np.int16)
         if self._L.unc_fast5_load(self._h, first, n, int(max_samples_per_read), buf.ctypes.data_as(C.c_void_p), total,
                                   infos, threads) != 0:
-            raise Fast5Error(self._L.unc_fast5_last_error().decode())
+            raise Fast5Error(self._L.unc_fast5_last_error().decode("utf-8", "replace"))
         return [Fast5Read(infos[i], buf[infos[i].sample_offset:infos[i].sample_offset + infos[i].n_samples])
                 for i in range(n)]

@@ -101,7 +101,7 @@ def test_bench_stream_job_logic(g200k):
             return feed_reads(self.step, 2, sigs, 450)
     sm = SM()
     calls = []
-    ms, counters, res = bench.stream_job(sm, [sig[0], sig[1]], 1, 1, lambda: calls.append("b"), lambda: calls.append("s"))
+    ms, counters, res, lat = bench.stream_job(sm, [sig[0], sig[1]], 1, 1, lambda: calls.append("b"), lambda: calls.append("s"))
     assert calls == ["s", "b", "b"] and ms > 0
     assert 2 <= counters["chunks"] <= 6 and counters["steps"] >= 2 and counters["bytes"] >= counters["chunks"] * 450 * 4
     assert len(res) == 2 and all(r is not None and r[0] in (2, 3) for r in res)

@@ -58,6 +58,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--dir", default=os.path.join(ROOT, "bench_data"))
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--reuse", action="store_true", help="use the index files of an earlier --keep run if they are there")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle parity and the CPU arm (profiling runs)")
     args = ap.parse_args()
 
     import torch
@@ -75,15 +77,23 @@ def main():
     info = {}
     t = time.time()
     g, masked, runs = make_genome(n_bases, 4242, n_runs=max(1, n_bases // 1_000_000), run_len=5000)
-    write_fasta(prefix + ".fa", masked)
-    info["genome_fasta_s"] = time.time() - t
-    t = time.time()
-    N.check(N.lib().unc_index_build((prefix + ".fa").encode(), prefix.encode()))
-    info["fm_index_build_s"] = time.time() - t
+    have = args.reuse and all(os.path.exists(prefix + e) for e in (".bwt", ".sa", ".pac", ".ann", ".amb", ".uncl"))
+    if not have:
+        write_fasta(prefix + ".fa", masked)
+        info["genome_fasta_s"] = time.time() - t
+        t = time.time()
+        N.check(N.lib().unc_index_build((prefix + ".fa").encode(), prefix.encode()))
+        info["fm_index_build_s"] = time.time() - t
+        t = time.time()
+        off, val = UI.self_align_csr(prefix, UI.IP.sample_distance(UI.IP.reference_length(prefix), UI.IP.DEFAULTS["max_sample_dist"],
+                                                                UI.IP.DEFAULTS["min_samples"], UI.IP.DEFAULTS["max_samples"]))
+        info["self_align_gpu_s"] = time.time() - t           # unc_self_align: index load + the two kernels + copy back
+        info["self_align_paths"] = int(len(off) - 1)
+        t = time.time()
+        with open(prefix + UI.UNCL_SUFF, "w") as f:
+            f.write(UI.IP.uncl_text(off, val))                # the parameter search of `uncalled index` (host, numpy)
+        info["uncl_param_search_s"] = time.time() - t
     info["fm_index_files_mb"] = sum(os.path.getsize(prefix + e) for e in (".bwt", ".sa", ".pac")) / 1e6
-    t = time.time()
-    UI.write_uncl(prefix)                                   # unc_self_align on the GPU + parameter search -> .uncl
-    info["uncl_self_align_and_param_search_s"] = time.time() - t
 
     # reads: starts outside the masked stretches (bwa fills N with random bases the generator does not know)
     rng = np.random.default_rng(99)
@@ -123,14 +133,19 @@ def main():
 
     # parity: the first reads against the oracle (CPU restatement), PAF fields and counters
     import orclib
+    if args.no_cpu:
+        args.parity_reads = args.cpu_reads = 0
     npar = min(args.parity_reads, args.reads)
-    O = orclib.Oracle(prefix)
-    O.params.max_events = 30000
     cpus = bench.host_cpus()
-    t = time.time()
-    offs = np.arange(npar, dtype=np.uint64) * L
-    want = O.map_batch(np.ascontiguousarray(sig[:npar]).ravel(), offs, np.full(npar, L, np.uint32), cpus["usable"])
-    info["oracle_parity_s"] = time.time() - t
+    want, O = [], None
+    if npar or args.cpu_reads:
+        O = orclib.Oracle(prefix)
+        O.params.max_events = 30000
+    if npar:
+        t = time.time()
+        offs = np.arange(npar, dtype=np.uint64) * L
+        want = O.map_batch(np.ascontiguousarray(sig[:npar]).ravel(), offs, np.full(npar, L, np.uint32), cpus["usable"])
+        info["oracle_parity_s"] = time.time() - t
     bad = []
     for i in range(npar):
         a, b = orclib.paf_tuple(want[i]), U.paf_key(out[i])

@@ -18,7 +18,7 @@ d = U.make_descs([4000] * n_reads)
 for it in range(2):
     out = bm.map(sig.ravel(), d)
     print("iter", it, bm.timing())
-ph2 = np.zeros((n_reads, 32), np.uint64)
+ph2 = np.zeros((n_reads, 64), np.uint64)
 L = N.lib()
 L.unc_pool_debug_phases.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
 N.check(L.unc_pool_debug_phases(bm.h, n_reads, ph2.ctypes.data))
@@ -26,16 +26,24 @@ names = ["A probs", "B extend + B1 deferred seed_prob", "B2 scan/ended rows/key 
          "X barrier(tracker)", "head: event load + scaling", "head: verdict + bookkeeping", "head: loop back-edge"]
 if os.environ.get("UNC_PHASES_V1") is None:     # the second worker structure (unc_k2v2.cuh) marks its own phases
     names = ["A probs + counter reset", "B extension", "C1 scatter into k-mer buckets", "C2 bucket sort + count", "(unused)", "D1 dedup/sources/seeds + E fresh",
-             "X barrier(tracker)", "head: event load + scaling", "head: verdict + bookkeeping", "head: loop back-edge",
-             "B2 chunk scan / ended rows / bucket offsets / deferred seed_prob", "D0 bucket prefix + flags + fresh plan | S1 SA of ended rows"]
+             "X barrier wait (slowest warp of D1/E, tracker)", "head: event load + scaling", "head: verdict + bookkeeping", "head: loop back-edge",
+             "B2 chunk scan / ended rows / bucket offsets / deferred seed_prob", "D0 bucket prefix + flags + fresh plan | S1 SA of ended rows",
+             "cut-case recount", "", "", "",
+             "  wait at the barrier after A", "  wait after B", "  wait after C1", "  wait after C2", "", "", "", "", "", "", "  wait after B2", "  wait after D0", "", "", "", ""]
 ev = out["events_used"].astype(np.float64) + 1
-for title, ph in (("worker warp 0, thread 0 (also runs the single-warp sections)", ph2[:, :len(names)]),
-                  ("last worker warp, lane 0 (its barrier waits expose the single-warp sections)", ph2[:, 16:16 + len(names)])):
+for title, ph in (("worker warp 0, thread 0 (also runs the single-warp sections)", ph2[:, :32]),
+                  ("last worker warp, lane 0 (its barrier waits expose the single-warp sections)", ph2[:, 32:64])):
     tot = ph.sum(axis=0).astype(np.float64)
     print("--", title)
     print("total events", ev.sum())
     for i, nm in enumerate(names):
+        if not nm or i >= ph.shape[1]:
+            continue
         print("%-36s %6.1f%%  %8.0f cycles/event" % (nm, 100 * tot[i] / max(tot.sum(), 1), tot[i] / ev.sum()))
     print("cycles/event total %.0f" % (tot.sum() / ev.sum()))
+    if ph.shape[1] >= 32 and title.startswith("last"):
+        t = ph2[:, 60:64].astype(np.float64)
+        print("tracker warp: busy %.0f cycles/event (mean), slowest event of a read %.0f cycles (mean over reads; max %.0f), events above 200k cycles: %.2f %%, seeds/event %.2f"
+              % (t[:, 0].sum() / ev.sum(), t[:, 1].mean(), t[:, 1].max(), 100 * t[:, 2].sum() / ev.sum(), t[:, 3].sum() / ev.sum()))
     nm_ = out["mapped"] == 0
     print("non-mapping reads: cycles/event %.0f ; mapping: %.0f" % (ph[nm_].sum() / ev[nm_].sum(), ph[~nm_].sum() / ev[~nm_].sum()))

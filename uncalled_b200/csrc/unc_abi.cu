@@ -502,8 +502,8 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     PT(cudaMalloc(&P->d_k1_flags, (size_t) max_reads * 4));
     PT(cudaMalloc(&P->d_out, (size_t) max_reads * sizeof(DevRec)));
 #ifdef UNC_PHASE_TIMING
-    PT(cudaMalloc(&P->d_dbg, (size_t) max_reads * 256));
-    PT(cudaMemset(P->d_dbg, 0, (size_t) max_reads * 256));
+    PT(cudaMalloc(&P->d_dbg, (size_t) max_reads * 512));
+    PT(cudaMemset(P->d_dbg, 0, (size_t) max_reads * 512));
 #endif
     PT(cudaMallocHost(&P->h_out, (size_t) max_reads * sizeof(unc_paf_rec)));
 #undef PT
@@ -614,6 +614,7 @@ static int batch_enqueue(unc_pool *P, const unc_read_desc *reads, uint32_t n, co
     }
     CUDA_TRY(cudaMemcpyAsync(P->d_reads, P->h_reads, (size_t) n * sizeof(DevReadDesc), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(P->d_queue, 0, 32, s));
+    if (P->d_dbg) CUDA_TRY(cudaMemsetAsync(P->d_dbg, 0, (size_t) n * 512, s));      // phase-timing builds only
     CUDA_TRY(cudaEventRecord(P->ev[1], s));
     // the pool's own staging buffer is padded, so whole 16-byte bulk copies may run past `span`
     DevBatch B = make_batch(P, d_samples, on_device ? span : ((span + 15) & ~(uint64_t) 15), n, false);
@@ -859,7 +860,7 @@ int unc_fm_sa(const unc_index *x, uint32_t n, const uint64_t *rows, uint64_t *ou
 // debug builds (-DUNC_PHASE_TIMING): per-read cycle counters of the mapper's phases
 int unc_pool_debug_phases(const unc_pool *P, uint32_t n, unsigned long long *out) {
     if (!P || !out || !P->d_dbg) return fail(UNC_E_ARG, "phase timing not compiled in");
-    CUDA_TRY(cudaMemcpy(out, P->d_dbg, (size_t) n * 256, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out, P->d_dbg, (size_t) n * 512, cudaMemcpyDeviceToHost));
     return UNC_OK;
 }
 

@@ -843,6 +843,7 @@ struct K2V2 {              // second worker structure (unc_k2v2.cuh)
     u32 kagg[UNC_NKMER];   // (gap sources | child seeds << 16) of the bucket, then their exclusive prefix
     u32 fresh_cand[32], fresh_mask[32], fresh_before[32];   // fresh-source candidates / plan per 32-k-mer word
     u32 grab[2];           // bucket hand-out counters (sort pass, emit pass)
+    u32 n_units;           // 32-key chunks of large buckets listed for the emit pass (W.elist)
     u16 mfirst[K2V2_MAX_MERGED];   // per merged-group k-mer: gap sources of its bucket before its first run (0xFFFF: no run)
 };
 struct K2Shared {          // per CTA
@@ -1012,6 +1013,22 @@ UNC_DEV void unc_k2_write_record(const DevIndex &ix, const DevParams &p, const D
     B.out[r] = o;
 }
 
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+// cycle counter with a compiler memory barrier, so that loads/stores of a phase are not scheduled across a mark
+UNC_DEV long long pt_clock() { long long v; asm volatile("mov.u64 %0, %%clock64;" : "=l"(v) :: "memory"); return v; }
+#define PT_DECL unsigned long long pt_acc[32]; for (int _i = 0; _i < 32; _i++) pt_acc[_i] = 0; long long pt_t = pt_clock();
+#define PT_MARK(i) { long long _n = pt_clock(); pt_acc[i] += (unsigned long long) (_n - pt_t); pt_t = _n; }
+// two observers per read: thread 0 of worker warp 0 (which also runs the single-warp sections: chunk scan,
+// ended rows, fresh sources) -> counters 0..7, and lane 0 of the LAST worker warp (never runs them, so its
+// barrier waits expose them) -> counters 16..31.  Marks 0..6 = phases A..X, 8 = verdict + bookkeeping after the event
+// barrier, 9 = loop back-edge, 7 = the event's load and scaling (8 + 9 + 7 = the former "loop head")
+#define PT_FLUSH(B, r) if ((B).dbg && (wt == 0 || wt == nwt - 32u)) { for (int _i = 0; _i < 32; _i++) (B).dbg[(size_t) (r) * 64 + (wt == 0 ? 0 : 32) + _i] = pt_acc[_i]; }
+#else
+#define PT_DECL
+#define PT_MARK(i)
+#define PT_FLUSH(B, r)
+#endif
+
 // ---- tracker warp (warp 0): reference src/mapper.cpp:513-519,601 (update_seeds order),
 //      :631-653 (get_final -> set_ref_loc), :708-728, bwa_index.hpp:213-220
 template <bool STREAM>
@@ -1041,11 +1058,21 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
         const u32 n = *(volatile u32 *) &sh->n_rows[i & 1u];
         // seed clustering is sequential: ended paths' seeds (event i-1) in parent order, then the
         // children's (event i) in sorted order
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+        const long long trk_t0 = pt_clock();
+#endif
         for (u32 j = 0; j < n; j++) {
             uint2 e = rl[j];
             trk_add_seed(trk, p, e.x, e.y & 0xFFu, (e.y & 0x100u) ? i - 1u : i);
         }
         n_seeds += n;
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+        if (B.dbg && lane == 0) {      // the tracker's own time per event: total, maximum, events above 200 k cycles
+            const unsigned long long busy = (unsigned long long) (pt_clock() - trk_t0);
+            unsigned long long *d = B.dbg + (size_t) r * 64 + 60;
+            d[0] += busy; if (busy > d[1]) d[1] = busy; if (busy > 200000ull) d[2]++; d[3] += n;
+        }
+#endif
         u32 v = (trk.overflow || *(volatile u32 *) &sh->wk_overflow) ? 2u : (trk_get_final(trk, p) ? 1u : 0u);
         if (v) { verdict = v; final_event = i; }
         if (lane == 0) *(volatile u32 *) &sh->verdict[i & 1u] = v;
@@ -1063,21 +1090,6 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
     if (lane == 0) unc_k2_write_record(ix, p, B, sh, r, trk, verdict, final_event, n_seeds);
 }
 
-#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
-// cycle counter with a compiler memory barrier, so that loads/stores of a phase are not scheduled across a mark
-UNC_DEV long long pt_clock() { long long v; asm volatile("mov.u64 %0, %%clock64;" : "=l"(v) :: "memory"); return v; }
-#define PT_DECL unsigned long long pt_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t = pt_clock();
-#define PT_MARK(i) { long long _n = pt_clock(); pt_acc[i] += (unsigned long long) (_n - pt_t); pt_t = _n; }
-// two observers per read: thread 0 of worker warp 0 (which also runs the single-warp sections: chunk scan,
-// ended rows, fresh sources) -> counters 0..7, and lane 0 of the LAST worker warp (never runs them, so its
-// barrier waits expose them) -> counters 16..31.  Marks 0..6 = phases A..X, 8 = verdict + bookkeeping after the event
-// barrier, 9 = loop back-edge, 7 = the event's load and scaling (8 + 9 + 7 = the former "loop head")
-#define PT_FLUSH(B, r) if ((B).dbg && (wt == 0 || wt == nwt - 32u)) { for (int _i = 0; _i < 16; _i++) (B).dbg[(size_t) (r) * 32 + (wt == 0 ? 0 : 16) + _i] = pt_acc[_i]; }
-#else
-#define PT_DECL
-#define PT_MARK(i)
-#define PT_FLUSH(B, r)
-#endif
 
 // ---- worker warps: reference src/mapper.cpp:433-663 (map_next) minus the seed clustering
 //

@@ -270,13 +270,23 @@ struct K2V2Emit {
     u32 S0, nc, maxp, n_ended_rows, rl_cap, pos0;      // pos0: sorted position of the bucket's first key
     u32 src_before, seeds_before;
 };
+// Called by the whole warp: the keys pass through the warp's staging area 32 at a time (a lane walking them straight
+// from global memory pays two dependent loads per key: measured as the tail of both bucket phases), lane 0 walks.
 template <bool EMIT>
 UNC_DEV u32 k2v2_walk_merged(const DevIndex &ix, K2Shared *sh, const uint4 *keys, u32 n, u32 moff, float source_prob,
-                             const K2V2Emit &E, u32 *pend_steps, u32 *pend_blocks) {
+                             const K2V2Emit &E, u32 *pend_steps, u32 *pend_blocks, uint4 *sst) {
     K2V2 *v2 = &sh->v2;
-    u32 nsrc = 0, nseed = 0, prev_sub = 0xFFFFFFFFu, un_st = 1, un_en = 0;
-    for (u32 i = 0; i < n; i++) {
-        const uint4 cur = keys[i];
+    const u32 lane = (u32) w_lane();
+    u32 nsrc = 0, nseed = 0, prev_sub = 0xFFFFFFFFu, un_st = 1, un_en = 0;      // the walk's state (lane 0)
+  for (u32 g0 = 0; g0 < n; g0 += 32u) {
+    const u32 cnt = n - g0 < 32u ? n - g0 : 32u;
+    if (lane < cnt) sst[lane] = keys[g0 + lane];
+    if (lane == 0 && g0 + cnt < n) sst[32] = keys[g0 + cnt];                     // the key after the window
+    w_sync();
+    if (lane == 0)
+    for (u32 j = 0; j < cnt; j++) {
+        const u32 i = g0 + j;
+        const uint4 cur = sst[j];
         const u32 sub = (cur.w >> 6) & 0xFFu, kmer = v2->t.mk[moff + sub];
         const uint2 kr = sh->tb.kmer_range[kmer];
         const float pk = sh->probs[kmer];
@@ -298,7 +308,7 @@ UNC_DEV u32 k2v2_walk_merged(const DevIndex &ix, K2Shared *sh, const uint4 *keys
         prev_sub = sub;
         const bool has_next = i + 1u < n;
         uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (has_next) nxt = keys[i + 1u];
+        if (has_next) nxt = sst[j + 1u];
         const bool dup = has_next && nxt.x == cur.x && nxt.y == cur.y;
         const u32 rec = cur.w >> 14;
         if (EMIT) E.onext[E.pos0 + i] = rec | (dup ? UNC_INVALID : 0u);
@@ -328,15 +338,19 @@ UNC_DEV u32 k2v2_walk_merged(const DevIndex &ix, K2Shared *sh, const uint4 *keys
             nseed++;
         }
     }
-    return nsrc | (nseed << 16);
+    w_sync();
+  }
+    return w_shfl(nsrc | (nseed << 16), 0);
 }
 
 // exclusive prefix of the bucket counts (one warp): lane i owns ranks 32i .. 32i+31 = slots j*32 + i
 UNC_DEV void k2v2_bucket_offsets(K2V2 *v2) {
     const u32 lane = (u32) w_lane();
     u32 sum = 0;
+#pragma unroll 1
     for (u32 j = 0; j < 32; j++) sum += v2->kcnt[j * 32u + lane];
     u32 tot, run = w_exscan(sum, &tot);
+#pragma unroll 1
     for (u32 j = 0; j < 32; j++) {
         const u32 sl = j * 32u + lane, v = v2->kcnt[sl];
         v2->koff[sl] = run;
@@ -391,10 +405,11 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
             const u32 m = w_ballot(pk >= source_prob && kr.x <= kr.y);
             if (lane == 0) v2->fresh_cand[j] = m;
         }
-        if (wt == 0) { v2->grab[0] = 0; v2->grab[1] = 0; }
+        if (wt == 0) { v2->grab[0] = 0; v2->grab[1] = 0; v2->n_units = 0; }
         if (wt < K2V2_MAX_MERGED) v2->mfirst[wt] = 0xFFFFu;
-        c_sync_sub(1, (int) nwt);
         PT_MARK(0)
+        c_sync_sub(1, (int) nwt);
+        PT_MARK(16)
 
         uint4 *prev = W.paths + (size_t) gen * gen_recs * 2, *next = W.paths + (size_t) (gen ^ 1u) * gen_recs * 2;
         uint2 *hist_e = W.hist + (size_t) (event_i % UNC_NGEN) * gen_recs;
@@ -542,22 +557,25 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                 w_sync();                                       // the staging area is rewritten by the next chunk
             }
         }
-        c_sync_sub(1, (int) nwt);
         PT_MARK(1)
+        c_sync_sub(1, (int) nwt);
+        PT_MARK(17)
         // ---- B1 + B2a + B2b, concurrently.  Worker warp 0: exclusive scan of the chunk counts (restores the
         //      global emission order and gives the buffer cap, reference src/mapper.cpp:480-482,507-509,521-523:
         //      extension stops when max_paths children exist), then the seed rows of ended paths.  The last worker
         //      warp: bucket offsets.  The others: deferred seed_prob of children whose parent was already seed_len
         //      long -- C(e-22) is the C of the ancestor 22 generations back (21 parent hops from the parent).
         if (ww == 0) {
-            u32 carry = 0;
-            for (u32 i0 = 0; i0 < nch_prev; i0 += 32) {
-                u32 v = i0 + (u32) lane < nch_prev ? sh->bcnt[i0 + lane] : 0u, t;
-                u32 ex = w_exscan(v, &t);
-                if (i0 + (u32) lane < nch_prev) sh->bcnt[i0 + lane] = carry + ex;
-                carry += t;
+            {   // every lane owns a run of consecutive chunks: its sum, one warp scan, its running prefix
+                const u32 per = (nch_prev + 31u) >> 5, c_lo = (u32) lane * per, c_hi = c_lo + per < nch_prev ? c_lo + per : nch_prev;
+                u32 sum = 0;
+#pragma unroll 1
+                for (u32 c = c_lo; c < c_hi; c++) sum += sh->bcnt[c];
+                u32 tot, run = w_exscan(sum, &tot);
+#pragma unroll 1
+                for (u32 c = c_lo; c < c_hi; c++) { const u32 v = sh->bcnt[c]; sh->bcnt[c] = run; run += v; }
+                if (lane == 0) sh->bc[2] = tot;
             }
-            if (lane == 0) sh->bc[2] = carry;
             w_sync();
             // seed rows of ended paths, in parent order.  A parent counts only if the buffer was not yet full when
             // the sequential scan reached it (children before it < max_paths).
@@ -607,28 +625,38 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                 next[(size_t) w.x * 2 + 1].x = f2u(sp);
             }
         }
+        PT_MARK(10)
         c_sync_sub(1, (int) nwt);
+        PT_MARK(26)
         if (wt == 0) sh->wl_cnt = 0;
         const u32 nc_total = nch_prev ? sh->bc[2] : 0u;
         const u32 nc = nc_total < maxp ? nc_total : maxp;
         if (nc_total > maxp) {
-            // the cap cut the children: count again, only those that made it (chunk order = emission order)
-            for (u32 k = wt; k < UNC_NKMER; k += nwt) v2->kcnt[k] = 0;
-            c_sync_sub(1, (int) nwt);
+            // the cap cut the children (chunk order = emission order): take the dropped ones -- emission index >= max_paths,
+            // all in the last chunks -- out of the bucket counts instead of counting everything again.  kagg is still zero.
             for (u32 c = ww; c < nch_prev; c += nwk) {
-                const u32 base = sh->bcnt[c];
-                if (base >= nc) break;
-                const u32 end = c + 1 < nch_prev ? sh->bcnt[c + 1] : nc_total;
-                for (u32 i = (u32) lane; base + i < end && base + i < nc; i += 32)
-                    s_atomic_add(&v2->kcnt[v2->t.kslot[cks[(size_t) c * K2_CH_SLOTS + i].w & UNC_KMASK]], 1u);
+                const u32 base = sh->bcnt[c], end = c + 1 < nch_prev ? sh->bcnt[c + 1] : nc_total;
+                if (end <= nc) continue;
+                for (u32 i = (base < nc ? nc - base : 0u) + (u32) lane; base + i < end; i += 32)
+                    s_atomic_add(&v2->kagg[v2->t.kslot[cks[(size_t) c * K2_CH_SLOTS + i].w & UNC_KMASK]], 1u);
             }
             c_sync_sub(1, (int) nwt);
             if (ww == 0) {
+                // counts = differences of the offsets the optimistic scan left, minus the dropped; then the offsets again
+                const u32 l = (u32) lane;
+#pragma unroll 1
+                for (u32 j = 0; j < 32; j++) {
+                    const u32 sl = j * 32u + l;                                         // rank 32*l + j
+                    const u32 nxt = j < 31u ? v2->koff[sl + 32u] : (l < 31u ? v2->koff[l + 1u] : nc_total);
+                    v2->kcnt[sl] = nxt - v2->koff[sl] - v2->kagg[sl];
+                    v2->kagg[sl] = 0;
+                }
+                w_sync();
                 k2v2_bucket_offsets(v2);
             }
             c_sync_sub(1, (int) nwt);
         }
-        PT_MARK(10)
+        PT_MARK(12)
         u32 n_rows = sh->bc[3];
         if (n_rows > W.rl_cap) n_rows = W.rl_cap;
         const u32 n_ended_rows = n_rows;
@@ -660,21 +688,25 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                     ckA[s_atomic_add(&v2->kcnt[bk], 1u)] = key;
                 }
             }
-            c_sync_sub(1, (int) nwt);
             PT_MARK(2)
+            c_sync_sub(1, (int) nwt);
+            PT_MARK(18)
 
             // ---- C2. sort every bucket and count what its dedup walk will emit.  Buckets are handed out 32 ranks (one
             //          group) at a time: first sweep the large buckets (> 32 keys, one warp each, radix), second sweep
             //          the small ones, packed several to a warp pass.
+            uint4 *csum = W.elist;                                     // per 32-key chunk of a large bucket: what D1 needs to take it alone
             for (;;) {
                 const u32 gi = k2v2_grab(&v2->grab[0]);
-                if (gi >= 64u) break;
+                if (gi >= 96u) break;
                 const u32 grp = gi & 31u;
                 const u32 sl = (u32) lane * 32u + grp;                 // slot of rank 32*grp + lane
                 const u32 bo = v2->koff[sl], bn = v2->kcnt[sl] - bo;
                 const u32 meta = v2->t.gmeta[grp * 32u + (u32) lane];
-                if (gi < 32u) {
-                    u32 todo_m = w_ballot(meta != 0 && bn > 0);
+                if (gi < 64u) {
+                    // sweeps 0 and 1: the largest buckets (> 256 keys) start first, then the other large ones (longest job first)
+                    const bool huge_sweep = gi < 32u;
+                    u32 todo_m = huge_sweep ? w_ballot(meta != 0 && bn > 0) : 0u;
                     while (todo_m) {                                  // merged groups: sort, then one lane walks the bucket
                         const int l = d_ffs(todo_m) - 1;
                         todo_m &= todo_m - 1;
@@ -687,19 +719,22 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                             lo = ~w_max(~lo);
                             k2v2_sort_big(ckA, ckB, o, n, lo, 32u - (u32) d_clz(hi - lo), whist);
                         }
-                        if (lane == 0) {
+                        {
                             K2V2Emit E;
                             E.src_before = 0; E.seeds_before = 0;
-                            v2->kagg[(u32) l * 32u + grp] = k2v2_walk_merged<false>(ix, sh, ckA + o, n, moff, source_prob, E, &pend_steps, &pend_blocks);
+                            const u32 agg = k2v2_walk_merged<false>(ix, sh, ckA + o, n, moff, source_prob, E, &pend_steps, &pend_blocks, (uint4 *) stage_r);
+                            if (lane == 0) v2->kagg[(u32) l * 32u + grp] = agg;
                         }
-                        w_sync();
                     }
-                    u32 todo = w_ballot(bn > 32u && meta == 0);
+                    u32 todo = w_ballot(meta == 0 && (huge_sweep ? bn > 256u : (bn > 32u && bn <= 256u)));
                     while (todo) {
                         const int l = d_ffs(todo) - 1;
                         todo &= todo - 1;
                         const u32 o = w_shfl(bo, l), n = w_shfl(bn, l);
                         const u32 kmer = v2->t.gkmer[grp * 32u + (u32) l];
+                        u32 ubase = 0;                                 // this bucket's chunks in the unit list
+                        if (lane == 0) ubase = s_atomic_add(&v2->n_units, (n + 31u) >> 5);
+                        ubase = w_shfl(ubase, 0);
                         const uint2 kr = tb->kmer_range[kmer];
                         const bool prob_ok = sh->probs[kmer] >= source_prob;
                         // span of the bucket's fm_start values -> radix passes
@@ -715,6 +750,8 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                             uint4 cur = make_uint4(0, 0, 0, 0); u32 nx = 0, ny = 0;
                             if (a) cur = ckA[o + g];
                             if (has_next) { const uint4 t = ckA[o + g + 1u]; nx = t.x; ny = t.y; }
+                            // the chunk as a unit of the emit phase: max fm_end and the bucket's counts before it, bucket slot | chunk
+                            if (lane == 0) csum[ubase + (g0 >> 5)] = make_uint4(carry_mx, n_src, n_seed, ((u32) l * 32u + grp) | ((g0 >> 5) << 10));
                             u32 mxo;
                             const K2V2Walk wk = k2v2_walk(cur, nx, ny, a, has_next, g == 0, g == 0, g0 != 0, carry_mx, prob_ok, kr, &mxo);
                             carry_mx = mxo;
@@ -761,8 +798,9 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                     }
                 }
             }
-            c_sync_sub(1, (int) nwt);
             PT_MARK(3)
+            c_sync_sub(1, (int) nwt);
+            PT_MARK(19)
         }
 
         // ---- D0 + S1, concurrently.  Worker warp 0: prefix sum of the buckets' (sources, seeds), the sources_added_
@@ -772,10 +810,12 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         if (ww == 0) {
             // lane i owns ranks 32i .. 32i+31 (slots j*32 + i): its sum, a warp scan of the sums, its running prefix
             u32 sum = 0;
+#pragma unroll 1
             for (u32 j = 0; j < 32; j++) sum += v2->kagg[j * 32u + (u32) lane];
             u32 ts, tq;
             const u32 es = w_exscan(sum & 0xFFFFu, &ts), eq = w_exscan(sum >> 16, &tq);
             u32 run = es | (eq << 16);                       // sources | seeds << 16 before the bucket
+#pragma unroll 1
             for (u32 j = 0; j < 32; j++) {
                 const u32 sl = j * 32u + (u32) lane, v = v2->kagg[sl];
                 v2->kagg[sl] = run;
@@ -817,95 +857,113 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                 rlist[i] = e;
             }
         }
-        c_sync_sub(1, (int) nwt);
         PT_MARK(11)
+        c_sync_sub(1, (int) nwt);
+        PT_MARK(27)
         const u32 n_child_seeds = nc > 0 ? sh->bc[6] : 0u;
         n_rows = n_ended_rows + n_child_seeds;
         if (n_rows > W.rl_cap) n_rows = W.rl_cap;
 
-        // ---- D1. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603): every bucket is one k-mer run
+        // ---- D1. dedup, gap sources, child seeds (reference src/mapper.cpp:527-603): every bucket is one k-mer run.  Work is
+        //      handed out through one counter: first the 32-key chunks of the large buckets, one at a time and in any order
+        //      (C2 left each chunk its running max and counts), then the groups' merged buckets and packs of small ones.
         if (nc > 0) {
+            const uint4 *csum = W.elist;
+            const u32 n_units = *(volatile u32 *) &v2->n_units;
             for (;;) {
                 const u32 gi = k2v2_grab(&v2->grab[1]);
-                if (gi >= 64u) break;
-                const u32 grp = gi & 31u;
+                if (gi >= n_units + 32u) break;
+                if (gi < n_units) {
+                    const uint4 u = csum[gi];
+                    const u32 sl_u = u.w & 1023u, g0 = (u.w >> 10) << 5;
+                    const u32 o = v2->koff[sl_u], n = v2->kcnt[sl_u] - o, pre = v2->kagg[sl_u];
+                    const u32 kmer = v2->t.gkmer[((sl_u & 31u) << 5) | (sl_u >> 5)];
+                    const uint2 kr = tb->kmer_range[kmer];
+                    const float pkm = sh->probs[kmer];
+                    const bool prob_ok = pkm >= source_prob;
+                    const u32 pos = g0 + (u32) lane;
+                    const bool a = pos < n, has_next = pos + 1u < n;
+                    uint4 cur = make_uint4(0, 0, 0, 0);
+                    if (a) cur = ckA[o + pos];
+                    u32 nx = w_shfl_down(cur.x, 1), ny = w_shfl_down(cur.y, 1);
+                    if (lane == 31 && has_next) { const uint4 t = ckA[o + pos + 1u]; nx = t.x; ny = t.y; }
+                    u32 mxo;
+                    const K2V2Walk wk = k2v2_walk(cur, nx, ny, a, has_next, pos == 0, pos == 0, g0 != 0, u.x, prob_ok, kr, &mxo);
+                    const u32 sidx = (pre & 0xFFFFu) + u.y + (u32) d_popc(wk.m_b & lt) + (u32) d_popc(wk.m_a & lt);   // sources before this element
+                    if (wk.begin_v && nc + sidx < maxp) {
+                        write_source(next, hist_e, S0 + nc + sidx, kr.x, cur.x - 1u, kmer, pkm);
+                        onext[nc + sidx] = S0 + nc + sidx;
+                    }
+                    const u32 sidx2 = sidx + (wk.begin_v ? 1u : 0u);
+                    if (wk.after_v && nc + sidx2 < maxp) {
+                        write_source(next, hist_e, S0 + nc + sidx2, wk.as, wk.ae, kmer, pkm);
+                        onext[nc + sidx2] = S0 + nc + sidx2;
+                    }
+                    const u32 rec = cur.w >> 14;
+                    if (a) onext[o + pos] = rec | (wk.dup ? UNC_INVALID : 0u);
+                    if (wk.seed) {                                     // update_seeds(child, false)
+                        d_atomic_or(&((u32 *) (next + (size_t) rec * 2))[3], 0x80000000u);   // sa_checked_
+                        const u32 ri = n_ended_rows + (pre >> 16) + u.z + (u32) d_popc(wk.m_seed & lt);
+                        if (ri < W.rl_cap)
+                            rlist[ri] = make_uint2(ix.seq_len - unc_sa_lookup(ix, cur.x, &pend_steps, &pend_blocks), (cur.w >> 1) & 0x1Fu);
+                        else sh->wk_overflow = 1;
+                    }
+                    continue;
+                }
+                const u32 grp = gi - n_units;
                 const u32 sl = (u32) lane * 32u + grp;
                 const u32 bo = v2->koff[sl], bn = v2->kcnt[sl] - bo, bpre = v2->kagg[sl];
-                const bool small_sweep = gi >= 32u;
                 const u32 meta = v2->t.gmeta[grp * 32u + (u32) lane];
-                u32 todo_m = small_sweep ? 0u : w_ballot(meta != 0 && bn > 0);
+                u32 todo_m = w_ballot(meta != 0 && bn > 0);
                 while (todo_m) {                                      // merged groups: one lane walks the sorted bucket
                     const int l = d_ffs(todo_m) - 1;
                     todo_m &= todo_m - 1;
-                    if (lane == l) {
+                    {
+                        const u32 o_m = w_shfl(bo, l), n_m = w_shfl(bn, l), pre_m = w_shfl(bpre, l), mt_m = w_shfl(meta, l);
                         K2V2Emit E;
                         E.next = next; E.hist_e = hist_e; E.onext = onext; E.rlist = rlist;
-                        E.S0 = S0; E.nc = nc; E.maxp = maxp; E.n_ended_rows = n_ended_rows; E.rl_cap = W.rl_cap; E.pos0 = bo;
-                        E.src_before = bpre & 0xFFFFu; E.seeds_before = bpre >> 16;
-                        k2v2_walk_merged<true>(ix, sh, ckA + bo, bn, meta >> 8, source_prob, E, &pend_steps, &pend_blocks);
+                        E.S0 = S0; E.nc = nc; E.maxp = maxp; E.n_ended_rows = n_ended_rows; E.rl_cap = W.rl_cap; E.pos0 = o_m;
+                        E.src_before = pre_m & 0xFFFFu; E.seeds_before = pre_m >> 16;
+                        k2v2_walk_merged<true>(ix, sh, ckA + o_m, n_m, mt_m >> 8, source_prob, E, &pend_steps, &pend_blocks, (uint4 *) stage_r);
                     }
-                    w_sync();
                 }
-                const u32 cnt = (small_sweep && bn > 0 && bn <= 32u && meta == 0) ? bn : 0u;
+                const u32 cnt = (bn > 0 && bn <= 32u && meta == 0) ? bn : 0u;
                 u32 tot;
                 const u32 P = w_exscan(cnt, &tot);
-                u32 remaining = small_sweep ? w_ballot(cnt != 0) : 0u;
-                u32 todo = small_sweep ? 0u : w_ballot(bn > 32u && meta == 0);
-                while (todo | remaining) {
-                    // one pass: a pack of small buckets, or the next 32 keys of one large bucket
-                    K2V2Pack pk;
-                    u32 o_big = 0, n_big = 0, g0 = 0, carry_mx = 0, src_acc = 0, seed_acc = 0;
-                    int l_big = 0;
-                    if (small_sweep) pk = k2v2_next_pack(cnt, P, &remaining);
-                    else {
-                        l_big = d_ffs(todo) - 1;
-                        todo &= todo - 1;
-                        o_big = w_shfl(bo, l_big); n_big = w_shfl(bn, l_big);
-                        pk.bl = (u32) l_big; pk.start = 0; pk.n = n_big; pk.pos = (u32) lane; pk.a = (u32) lane < n_big;
-                    }
+                u32 remaining = w_ballot(cnt != 0);
+                while (remaining) {
+                    const K2V2Pack pk = k2v2_next_pack(cnt, P, &remaining);
                     const u32 kmer = v2->t.gkmer[grp * 32u + pk.bl];
                     const uint2 kr = tb->kmer_range[kmer];
                     const float pkm = sh->probs[kmer];
                     const bool prob_ok = pkm >= source_prob;
                     const u32 pre = w_shfl(bpre, (int) pk.bl), o = w_shfl(bo, (int) pk.bl);
-                    for (;;) {
-                        const u32 pos = small_sweep ? pk.pos : g0 + (u32) lane;
-                        const bool a = small_sweep ? pk.a : pos < n_big;
-                        const bool has_next = a && pos + 1u < pk.n;
-                        uint4 cur = make_uint4(0, 0, 0, 0);
-                        if (a) cur = ckA[o + pos];
-                        u32 nx = w_shfl_down(cur.x, 1), ny = w_shfl_down(cur.y, 1);
-                        if (!small_sweep && lane == 31 && has_next) { const uint4 t = ckA[o + pos + 1u]; nx = t.x; ny = t.y; }
-                        u32 mxo;
-                        const K2V2Walk wk = k2v2_walk(cur, nx, ny, a, has_next, pos == 0, pos == 0, !small_sweep && g0 != 0, carry_mx, prob_ok,
-                                                      kr, &mxo);
-                        carry_mx = mxo;
-                        const u32 sm = small_sweep ? k2v2_segmask(pk.start, pk.n) : 0xFFFFFFFFu;
-                        const u32 sidx = (pre & 0xFFFFu) + src_acc + (u32) d_popc(wk.m_b & lt & sm) + (u32) d_popc(wk.m_a & lt & sm);   // sources before this element
-                        if (wk.begin_v && nc + sidx < maxp) {
-                            write_source(next, hist_e, S0 + nc + sidx, kr.x, cur.x - 1u, kmer, pkm);
-                            onext[nc + sidx] = S0 + nc + sidx;
-                        }
-                        const u32 sidx2 = sidx + (wk.begin_v ? 1u : 0u);
-                        if (wk.after_v && nc + sidx2 < maxp) {
-                            write_source(next, hist_e, S0 + nc + sidx2, wk.as, wk.ae, kmer, pkm);
-                            onext[nc + sidx2] = S0 + nc + sidx2;
-                        }
-                        const u32 rec = cur.w >> 14;
-                        if (a) onext[o + pos] = rec | (wk.dup ? UNC_INVALID : 0u);
-                        // update_seeds(child, false): unique, move-headed, full-length, probable paths
-                        if (wk.seed) {
-                            d_atomic_or(&((u32 *) (next + (size_t) rec * 2))[3], 0x80000000u);   // sa_checked_
-                            const u32 ri = n_ended_rows + (pre >> 16) + seed_acc + (u32) d_popc(wk.m_seed & lt & sm);
-                            if (ri < W.rl_cap)
-                                rlist[ri] = make_uint2(ix.seq_len - unc_sa_lookup(ix, cur.x, &pend_steps, &pend_blocks), (cur.w >> 1) & 0x1Fu);
-                            else sh->wk_overflow = 1;
-                        }
-                        if (small_sweep) break;
-                        src_acc += (u32) d_popc(wk.m_b) + (u32) d_popc(wk.m_a);
-                        seed_acc += (u32) d_popc(wk.m_seed);
-                        g0 += 32u;
-                        if (g0 >= n_big) break;
+                    uint4 cur = make_uint4(0, 0, 0, 0);
+                    if (pk.a) cur = ckA[o + pk.pos];
+                    const u32 nx = w_shfl_down(cur.x, 1), ny = w_shfl_down(cur.y, 1);
+                    u32 mxo;
+                    const K2V2Walk wk = k2v2_walk(cur, nx, ny, pk.a, pk.a && pk.pos + 1u < pk.n, pk.pos == 0, pk.pos == 0, false, 0u, prob_ok,
+                                                  kr, &mxo);
+                    const u32 sm = k2v2_segmask(pk.start, pk.n);
+                    const u32 sidx = (pre & 0xFFFFu) + (u32) d_popc(wk.m_b & lt & sm) + (u32) d_popc(wk.m_a & lt & sm);   // sources before this element
+                    if (wk.begin_v && nc + sidx < maxp) {
+                        write_source(next, hist_e, S0 + nc + sidx, kr.x, cur.x - 1u, kmer, pkm);
+                        onext[nc + sidx] = S0 + nc + sidx;
+                    }
+                    const u32 sidx2 = sidx + (wk.begin_v ? 1u : 0u);
+                    if (wk.after_v && nc + sidx2 < maxp) {
+                        write_source(next, hist_e, S0 + nc + sidx2, wk.as, wk.ae, kmer, pkm);
+                        onext[nc + sidx2] = S0 + nc + sidx2;
+                    }
+                    const u32 rec = cur.w >> 14;
+                    if (pk.a) onext[o + pk.pos] = rec | (wk.dup ? UNC_INVALID : 0u);
+                    // update_seeds(child, false): unique, move-headed, full-length, probable paths
+                    if (wk.seed) {
+                        d_atomic_or(&((u32 *) (next + (size_t) rec * 2))[3], 0x80000000u);   // sa_checked_
+                        const u32 ri = n_ended_rows + (pre >> 16) + (u32) d_popc(wk.m_seed & lt & sm);
+                        if (ri < W.rl_cap)
+                            rlist[ri] = make_uint2(ix.seq_len - unc_sa_lookup(ix, cur.x, &pend_steps, &pend_blocks), (cur.w >> 1) & 0x1Fu);
+                        else sh->wk_overflow = 1;
                     }
                 }
             }

@@ -36,6 +36,8 @@ asm(".text\n"
 #define UNC_FULL 0xffffffffu
 
 struct uint2 { uint32_t x, y; };
+struct uint3 { uint32_t x, y, z; };
+static inline uint3 make_uint3(uint32_t x, uint32_t y, uint32_t z) { uint3 r = {x, y, z}; return r; }
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = {x, y}; return r; }
@@ -143,6 +145,14 @@ static inline void c_sync_sub(int id, int count) {
             emu_yield();
             if (++spins > 50000000L) { fprintf(stderr, "warp_emul: deadlock at named barrier %d (thread %d)\n", id, w->cur); abort(); }
         }
+    }
+}
+// bar.arrive id, count : count towards the named barrier without waiting for it
+static inline void c_arrive_sub(int id, int count) {
+    WarpEmu *w = g_warp;
+    if (++w->sub_arrived[id] == count) {
+        w->sub_arrived[id] = 0;
+        w->sub_gen[id]++;
     }
 }
 // inside a spin-wait on shared memory written by another warp: let the others run

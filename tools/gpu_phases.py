@@ -34,6 +34,12 @@ ev = out["events_used"].astype(np.float64) + 1
 for title, ph in (("worker warp 0, thread 0 (also runs the single-warp sections)", ph2[:, :32]),
                   ("last worker warp, lane 0 (its barrier waits expose the single-warp sections)", ph2[:, 32:64])):
     tot = ph.sum(axis=0).astype(np.float64)
+    per_warp = tot.copy()
+    if os.environ.get("UNC_PHASES_V1") is None:
+        tot[[13, 14, 15, 20, 21, 22, 23, 24, 25]] = 0      # not intervals: the worker warps' own times (slowest / mean), below
+        ph = ph.copy(); ph[:, [13, 14, 15, 20, 21, 22, 23, 24, 25]] = 0
+        if title.startswith("last"):
+            ph[:, 28:32] = 0; tot[28:32] = 0           # the tracker's counters
     print("--", title)
     print("total events", ev.sum())
     for i, nm in enumerate(names):
@@ -41,9 +47,14 @@ for title, ph in (("worker warp 0, thread 0 (also runs the single-warp sections)
             continue
         print("%-36s %6.1f%%  %8.0f cycles/event" % (nm, 100 * tot[i] / max(tot.sum(), 1), tot[i] / ev.sum()))
     print("cycles/event total %.0f" % (tot.sum() / ev.sum()))
+    if os.environ.get("UNC_PHASES_V1") is None and title.startswith("worker"):
+        print("   event barrier: now - release stamp of the last-released worker warp %.0f, of the first-released %.0f" % (per_warp[13] / ev.sum(), per_warp[14] / ev.sum()))
+        for nm, a, b in (("C2 sort + count", 15, 20), ("D1 emit", 21, 22)):
+            print("   %-18s slowest worker warp %8.0f cycles/event, mean warp %8.0f" % (nm, per_warp[a] / ev.sum(), per_warp[b] / ev.sum()))
+        print("   event barrier: released %.0f cycles after the last worker warp arrived, %.0f after the first, %.0f after the tracker warp" % (per_warp[23] / ev.sum(), per_warp[24] / ev.sum(), per_warp[25] / ev.sum()))
     if ph.shape[1] >= 32 and title.startswith("last"):
         t = ph2[:, 60:64].astype(np.float64)
-        print("tracker warp: busy %.0f cycles/event (mean), slowest event of a read %.0f cycles (mean over reads; max %.0f), events above 200k cycles: %.2f %%, seeds/event %.2f"
-              % (t[:, 0].sum() / ev.sum(), t[:, 1].mean(), t[:, 1].max(), 100 * t[:, 2].sum() / ev.sum(), t[:, 3].sum() / ev.sum()))
+        ns = max(t[:, 3].sum(), 1)
+        print("tracker warp: %.1f seeds/event; cycles per seed: search %.0f, scan %.0f, update/insert %.0f" % (t[:, 3].sum() / ev.sum(), t[:, 0].sum() / ns, t[:, 1].sum() / ns, t[:, 2].sum() / ns))
     nm_ = out["mapped"] == 0
     print("non-mapping reads: cycles/event %.0f ; mapping: %.0f" % (ph[nm_].sum() / ev[nm_].sum(), ph[~nm_].sum() / ev[~nm_].sum()))

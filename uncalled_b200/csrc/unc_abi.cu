@@ -502,8 +502,8 @@ int unc_pool_create(const unc_index *idx, const unc_params *prm, uint32_t max_re
     PT(cudaMalloc(&P->d_k1_flags, (size_t) max_reads * 4));
     PT(cudaMalloc(&P->d_out, (size_t) max_reads * sizeof(DevRec)));
 #ifdef UNC_PHASE_TIMING
-    PT(cudaMalloc(&P->d_dbg, (size_t) max_reads * 512));
-    PT(cudaMemset(P->d_dbg, 0, (size_t) max_reads * 512));
+    PT(cudaMalloc(&P->d_dbg, (size_t) max_reads * 512 + UNC_PT_TRACE_BYTES));     // counters per read, then the timeline of one read
+    PT(cudaMemset(P->d_dbg, 0, (size_t) max_reads * 512 + UNC_PT_TRACE_BYTES));
 #endif
     PT(cudaMallocHost(&P->h_out, (size_t) max_reads * sizeof(unc_paf_rec)));
 #undef PT
@@ -861,6 +861,14 @@ int unc_fm_sa(const unc_index *x, uint32_t n, const uint64_t *rows, uint64_t *ou
 int unc_pool_debug_phases(const unc_pool *P, uint32_t n, unsigned long long *out) {
     if (!P || !out || !P->d_dbg) return fail(UNC_E_ARG, "phase timing not compiled in");
     CUDA_TRY(cudaMemcpy(out, P->d_dbg, (size_t) n * 512, cudaMemcpyDeviceToHost));
+    return UNC_OK;
+}
+// ... and the timeline of read UNC_PT_TRACE_READ of a batch of n reads: [event][warp][mark] clock values (UNC_PT_TRACE_BYTES)
+int unc_pool_debug_trace(const unc_pool *P, uint32_t n, unsigned long long *out) {
+    if (!P || !out || !P->d_dbg) return fail(UNC_E_ARG, "phase timing not compiled in");
+#ifdef UNC_PHASE_TIMING
+    CUDA_TRY(cudaMemcpy(out, P->d_dbg + (size_t) n * 64, UNC_PT_TRACE_BYTES, cudaMemcpyDeviceToHost));
+#endif
     return UNC_OK;
 }
 

@@ -474,9 +474,22 @@ UNC_DEV bool clu_less(u32 as, u32 ae, u32 bs, u32 be) { return as > bs || (as ==
 
 struct Clu { u32 ren_start, evt_en, ref_st, ren_end, evt_st, total_len; };
 
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+UNC_DEV long long trk_clock() { long long v; asm volatile("mov.u64 %0, %%clock64;" : "=l"(v) :: "memory"); return v; }
+#define PT_TRK0(t) (t).pt_t = trk_clock();
+#define PT_TRK(t, i) { const long long _n = trk_clock(); (t).pt[i] += (unsigned long long) (_n - (t).pt_t); (t).pt_t = _n; }
+#else
+#define PT_TRK0(t)
+#define PT_TRK(t, i)
+#endif
 struct Tracker {     // all fields warp-uniform (replicated in every lane)
     uint4 *blocks;   // slot base: block b entry i at blocks[(b*32 + i)*2 + {0,1}]
-    uint4 *dir;      // sorted directory: (first ren_start, first evt_en, block id, count)
+    uint4 *dir;      // sorted directory: (first ren_start, first evt_en, block id, count) -- in shared memory while it fits
+    uint4 *dir_glob; // its home in the slot's workspace (== dir once it has outgrown the shared copy, or when there is none)
+    u32 dir_cap;     // entries the shared copy holds
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+    unsigned long long pt[3]; long long pt_t;   // phase-timing builds: cycles in search / scan / update of add_seed
+#endif
     u32 nb, n_alloc, max_blocks;
     u32 n_live, n_lens, top1, top2;
     float len_sum;
@@ -528,12 +541,20 @@ UNC_DEV void trk_lower_bound(const Tracker &t, u32 ks, u32 ke, u32 *d_out, u32 *
     uint4 de = t.dir[d];
     u32 blk = de.z, cnt = de.w;
     Clu m; m.ren_start = 0; m.evt_en = 0; m.ref_st = 0; m.ren_end = 0; m.evt_st = 0; m.total_len = 0;
-    bool less = false;
-    if ((u32) lane < cnt) { m = trk_load(t, blk, (u32) lane); less = clu_less(m.ren_start, m.evt_en, ks, ke); }
+    if ((u32) lane < cnt) m = trk_load(t, blk, (u32) lane);
+    const bool less = (u32) lane < cnt && clu_less(m.ren_start, m.evt_en, ks, ke);
     *pos_out = (u32) d_popc(w_ballot(less));
     *d_out = d; *blk_out = blk; *cnt_out = cnt; *mine = m;
 }
 
+// room for one more directory entry: a directory that outgrows its shared-memory copy moves to the workspace for good
+UNC_DEV void trk_dir_reserve(Tracker &t) {
+    if (t.dir != t.dir_glob && t.nb + 1u > t.dir_cap) {
+        for (u32 i = (u32) w_lane(); i < t.nb; i += 32u) t.dir_glob[i] = t.dir[i];
+        w_sync();
+        t.dir = t.dir_glob;
+    }
+}
 // shift directory entries [from, nb) up by one (warp memmove, top-down)
 UNC_DEV void trk_dir_open(Tracker &t, u32 from) {
     int lane = w_lane();
@@ -588,8 +609,12 @@ UNC_DEV void trk_erase(Tracker &t, u32 d, u32 pos) {
     }
 }
 
-// std::set::insert (unique keys): returns false when an equivalent key is already present
-UNC_DEV bool trk_insert_unique(Tracker &t, const Clu &c) {
+// What trk_lower_bound found for a key: directory index, position in the block, the block and its entries (one per lane)
+struct TrkBound { u32 d, pos, blk, cnt; Clu m; };
+
+// std::set::insert (unique keys): returns false when an equivalent key is already present.  `known` = the lower bound
+// of c's key in the set as it is now (the caller has searched for exactly this key), or null.
+UNC_DEV bool trk_insert_unique(Tracker &t, const Clu &c, const TrkBound *known = nullptr) {
     int lane = w_lane();
     if (t.nb == 0) {
         if (t.n_alloc >= t.max_blocks) { t.overflow = 1; return false; }
@@ -601,7 +626,8 @@ UNC_DEV bool trk_insert_unique(Tracker &t, const Clu &c) {
     }
     for (;;) {
         u32 d, pos, blk, cnt; Clu m;
-        trk_lower_bound(t, c.ren_start, c.evt_en, &d, &pos, &blk, &cnt, &m);
+        if (known) { d = known->d; pos = known->pos; blk = known->blk; cnt = known->cnt; m = known->m; known = nullptr; }
+        else trk_lower_bound(t, c.ren_start, c.evt_en, &d, &pos, &blk, &cnt, &m);
         // element at the bound
         u32 bs, be; bool have_bound = true;
         if (pos < cnt) { bs = w_shfl(m.ren_start, (int) pos); be = w_shfl(m.evt_en, (int) pos); }
@@ -625,6 +651,7 @@ UNC_DEV bool trk_insert_unique(Tracker &t, const Clu &c) {
         u32 nblk = t.n_alloc++;
         if (lane >= 16) trk_store(t, nblk, (u32) lane - 16, m);
         w_sync();
+        trk_dir_reserve(t);
         trk_dir_open(t, d + 1);
         u32 s16 = w_shfl(m.ren_start, 16), e16 = w_shfl(m.evt_en, 16);
         u32 s0 = w_shfl(m.ren_start, 0), e0 = w_shfl(m.evt_en, 0);
@@ -679,9 +706,14 @@ UNC_DEV void trk_add_seed(Tracker &t, const DevParams &p, u32 ref_en, u32 ref_le
     const u32 e2 = evt, r2 = ns.ren_start;
     bool found = false; u32 md = 0, mpos = 0, best_len = 0;
 
+    TrkBound lb;                                   // where the new seed's own key would go: the scan starts there
+    bool have_lb = false;
+    PT_TRK0(t)
     if (t.nb > 0) {
         u32 d, pos, blk, cnt; Clu m;
         trk_lower_bound(t, ns.ren_start, ns.evt_en, &d, &pos, &blk, &cnt, &m);
+        PT_TRK(t, 0)
+        lb.d = d; lb.pos = pos; lb.blk = blk; lb.cnt = cnt; lb.m = m; have_lb = true;
         int lane = w_lane();
         bool broke = false;
         u32 first = pos;
@@ -712,9 +744,21 @@ UNC_DEV void trk_add_seed(Tracker &t, const DevParams &p, u32 ref_en, u32 ref_le
         }
     }
 
+    PT_TRK(t, 1)
     if (found) {
-        uint4 de = t.dir[md];
-        Clu a = trk_load(t, de.z, mpos);
+        // the matched cluster's block: still in registers when it is the block the scan started in
+        const int lane = w_lane();
+        u32 blk, cnt; Clu mm;
+        if (md == lb.d) { blk = lb.blk; cnt = lb.cnt; mm = lb.m; }
+        else {
+            uint4 de = t.dir[md];
+            blk = de.z; cnt = de.w;
+            mm.ren_start = 0; mm.evt_en = 0; mm.ref_st = 0; mm.ren_end = 0; mm.evt_st = 0; mm.total_len = 0;
+            if ((u32) lane < cnt) mm = trk_load(t, blk, (u32) lane);
+        }
+        Clu a;
+        a.ren_start = w_shfl(mm.ren_start, (int) mpos); a.evt_en = w_shfl(mm.evt_en, (int) mpos); a.ref_st = w_shfl(mm.ref_st, (int) mpos);
+        a.ren_end = w_shfl(mm.ren_end, (int) mpos); a.evt_st = w_shfl(mm.evt_st, (int) mpos); a.total_len = w_shfl(mm.total_len, (int) mpos);
         u32 prev_len = a.total_len;
         clu_update(a, ns);
         if (a.total_len != prev_len) {
@@ -722,14 +766,33 @@ UNC_DEV void trk_add_seed(Tracker &t, const DevParams &p, u32 ref_en, u32 ref_le
             lens_replace(t, prev_len, a.total_len);
             if (a.total_len >= p.min_map_len && a.total_len > t.max_map.total_len) t.max_map = a;
         }
-        trk_erase(t, md, mpos);
-        trk_insert_unique(t, a);
+        // erase + insert (reference src/seed_tracker.cpp:205-213).  The key only moves towards the front of the set
+        // (ren_start never decreases; with it equal, evt_en does not); while it stays behind its predecessor the
+        // cluster keeps its place and is rewritten where it is.  An equal predecessor (the insert would fail) and the
+        // first entry of a later block take the general path.
+        bool in_place = false;
+        if (mpos > 0) {
+            const u32 ps = w_shfl(mm.ren_start, (int) mpos - 1), pe = w_shfl(mm.evt_en, (int) mpos - 1);
+            in_place = clu_less(ps, pe, a.ren_start, a.evt_en);
+        } else in_place = md == 0;
+        if (in_place) {
+            w_sync();
+            if (lane == 0) {
+                trk_store(t, blk, mpos, a);
+                if (mpos == 0) t.dir[md] = make_uint4(a.ren_start, a.evt_en, blk, cnt);
+            }
+            w_sync();
+        } else {
+            trk_erase(t, md, mpos);
+            trk_insert_unique(t, a);
+        }
     } else {
         lens_insert(t, ns.total_len);
         t.len_sum = f_add(t.len_sum, (float) ns.total_len);
         if (ns.total_len >= p.min_map_len && ns.total_len > t.max_map.total_len) t.max_map = ns;
-        trk_insert_unique(t, ns);
+        trk_insert_unique(t, ns, have_lb ? &lb : nullptr);
     }
+    PT_TRK(t, 2)
 }
 
 // SeedTracker::get_final + check_map_conf (reference src/seed_tracker.cpp:129-143,259-262)
@@ -768,7 +831,7 @@ UNC_DEV void trk_state_load(const u32 *w, Tracker &t) {
 UNC_DEV_NOINLINE u32 unc_k2_track_event(uint4 *clu, uint4 *dir, u32 max_blocks, u32 min_map_len, float min_mean_conf,
                                         float min_top_conf, const uint2 *rl, u32 n, u32 evt, u32 wk_overflow, u32 *state) {
     Tracker trk;
-    trk.blocks = clu; trk.dir = dir; trk.max_blocks = max_blocks;
+    trk.blocks = clu; trk.dir = trk.dir_glob = dir; trk.dir_cap = 0; trk.max_blocks = max_blocks;
     trk_state_load(state, trk);
     DevParams pp;
     pp.min_map_len = min_map_len; pp.min_mean_conf = min_mean_conf; pp.min_top_conf = min_top_conf;
@@ -845,6 +908,9 @@ struct K2V2 {              // second worker structure (unc_k2v2.cuh)
     u32 grab[2];           // bucket hand-out counters (sort pass, emit pass)
     u32 n_units;           // 32-key chunks of large buckets listed for the emit pass (W.elist)
     u16 mfirst[K2V2_MAX_MERGED];   // per merged-group k-mer: gap sources of its bucket before its first run (0xFFFF: no run)
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+    u32 pt_dur[4][K2_MAXSEG];      // phase-timing builds: every worker warp's own time in B / C2 / D1 / E of the event
+#endif
 };
 struct K2Shared {          // per CTA
     K2Tables tb;
@@ -1017,26 +1083,62 @@ UNC_DEV void unc_k2_write_record(const DevIndex &ix, const DevParams &p, const D
 // cycle counter with a compiler memory barrier, so that loads/stores of a phase are not scheduled across a mark
 UNC_DEV long long pt_clock() { long long v; asm volatile("mov.u64 %0, %%clock64;" : "=l"(v) :: "memory"); return v; }
 #define PT_DECL unsigned long long pt_acc[32]; for (int _i = 0; _i < 32; _i++) pt_acc[_i] = 0; long long pt_t = pt_clock();
-#define PT_MARK(i) { long long _n = pt_clock(); pt_acc[i] += (unsigned long long) (_n - pt_t); pt_t = _n; }
+// timeline of one read: events UNC_PT_TRACE_E0 .. +8, every warp's clock at every mark (behind the per-read counters)
+#define UNC_PT_TRACE_READ 40u
+#define UNC_PT_TRACE_E0 60u
+#define UNC_PT_TRACE_BYTES (8u * 16u * 32u * 8u)
+#define PT_TRACE(ev, i, t) if ((B).dbg && r == UNC_PT_TRACE_READ && (ev) - UNC_PT_TRACE_E0 < 8u && (c_tid() & 31) == 0) \
+        (B).dbg[(size_t) (B).n_reads * 64 + ((size_t) ((ev) - UNC_PT_TRACE_E0) * 16 + (c_tid() >> 5)) * 32 + (i)] = (unsigned long long) (t);
+#define PT_MARK(i) { long long _n = pt_clock(); pt_acc[i] += (unsigned long long) (_n - pt_t); pt_t = _n; PT_TRACE(event_i, i, _n) }
 // two observers per read: thread 0 of worker warp 0 (which also runs the single-warp sections: chunk scan,
 // ended rows, fresh sources) -> counters 0..7, and lane 0 of the LAST worker warp (never runs them, so its
 // barrier waits expose them) -> counters 16..31.  Marks 0..6 = phases A..X, 8 = verdict + bookkeeping after the event
 // barrier, 9 = loop back-edge, 7 = the event's load and scaling (8 + 9 + 7 = the former "loop head")
-#define PT_FLUSH(B, r) if ((B).dbg && (wt == 0 || wt == nwt - 32u)) { for (int _i = 0; _i < 32; _i++) (B).dbg[(size_t) (r) * 64 + (wt == 0 ? 0 : 32) + _i] = pt_acc[_i]; }
+#define PT_FLUSH(B, r) if ((B).dbg && (wt == 0 || wt == nwt - 32u)) { for (int _i = 0; _i < (wt == 0 ? 32 : 28); _i++) (B).dbg[(size_t) (r) * 64 + (wt == 0 ? 0 : 32) + _i] = pt_acc[_i]; }
+// A warp leaves BAR.SYNC.DEFER_BLOCKING before the barrier completes and stalls at its next memory instruction, so a clock
+// read right behind a barrier does not contain the wait.  PT_FENCE = the same barrier once more (nobody can arrive at it
+// before the first has completed): the read behind it does.  PT_WB / PT_WE(ph): every worker warp times its own share of
+// a phase; PT_WR(ph, s_max, s_mean): after the next barrier the observer adds the slowest warp's and the mean time.
+#define PT_FENCE c_sync_sub(1, (int) nwt);
+#define PT_WDECL long long pt_w0 = 0;
+#define PT_WB pt_w0 = pt_clock();
+#define PT_WE(ph) if (lane == 0) v2->pt_dur[ph][ww] = (u32) (pt_clock() - pt_w0);
+#define PT_WARR(ph) if (lane == 0) v2->pt_dur[ph][ww] = (u32) pt_clock(); w_sync(); s_atomic_max(&v2->pt_dur[ph][ww], (u32) pt_clock());   /* arrival of the warp's last lane at the barrier that follows */
+#define PT_WREL(ph) if (lane == 0 && *(volatile u32 *) &v2->grab[0] != 0xFFFFFFFFu) { const long long _t = pt_clock(); v2->pt_dur[ph][ww] = (u32) _t; PT_TRACE(event_i, 30, _t) }      /* the warp's release from the barrier before */
+#define PT_WLAG(ph, s_last, s_first) if (wt == 0) { const u32 _now = (u32) pt_clock(); u32 _mn = 0xFFFFFFFFu, _mx = 0; for (u32 _w = 0; _w < nwk; _w++) { \
+        const u32 _d = _now - *(volatile u32 *) &v2->pt_dur[ph][_w]; _mn = _d < _mn ? _d : _mn; _mx = _d > _mx ? _d : _mx; } pt_acc[s_last] += _mn; pt_acc[s_first] += _mx; }
+#define PT_WTRK(ph, s) if (wt == 0) pt_acc[s] += (u32) pt_clock() - *(volatile u32 *) &v2->pt_dur[ph][K2_MAXSEG - 2 + (event_i & 1u)];
+#define PT_WR(ph, s_max, s_mean) if (wt == 0) { u32 _mx = 0, _sm = 0; for (u32 _w = 0; _w < nwk; _w++) { const u32 _d = *(volatile u32 *) &v2->pt_dur[ph][_w]; \
+        _mx = _d > _mx ? _d : _mx; _sm += _d; } pt_acc[s_max] += _mx; pt_acc[s_mean] += _sm / nwk; }
 #else
 #define PT_DECL
 #define PT_MARK(i)
 #define PT_FLUSH(B, r)
+#define PT_FENCE
+#define PT_WDECL
+#define PT_WB
+#define PT_WE(ph)
+#define PT_WARR(ph)
+#define PT_WLAG(ph, s_last, s_first)
+#define PT_WTRK(ph, s)
+#define PT_WREL(ph)
+#define PT_WR(ph, s_max, s_mean)
 #endif
 
 // ---- tracker warp (warp 0): reference src/mapper.cpp:513-519,601 (update_seeds order),
 //      :631-653 (get_final -> set_ref_loc), :708-728, bwa_index.hpp:213-220
+#ifdef K2_V1
+#define K2_V2_ACTIVE false
+#else
+#define K2_V2_ACTIVE true
+#endif
 template <bool STREAM>
 UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBatch &B, const DevWork &W,
-                            K2Shared *sh, u32 r, u32 n_first, u32 n_limit) {
+                            K2Shared *sh, u32 r, u32 n_first, u32 n_limit, uint4 *dir_smem, u32 dir_smem_cap) {
     const int lane = w_lane();
     Tracker trk;
-    trk.blocks = W.clu; trk.dir = W.dir; trk.max_blocks = W.max_blocks;
+    trk.blocks = W.clu; trk.dir_glob = W.dir; trk.max_blocks = W.max_blocks;
+    trk.dir = dir_smem ? dir_smem : W.dir; trk.dir_cap = dir_smem ? dir_smem_cap : 0u;   // the directory's fast copy (searched for every seed)
     trk_reset(trk);
     DevMapState *ms = nullptr;
     if (STREAM) {
@@ -1046,38 +1148,56 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
             trk.top1 = ms->t_top1; trk.top2 = ms->t_top2; trk.overflow = ms->t_overflow; trk.len_sum = ms->t_len_sum;
             trk.max_map.ren_start = ms->t_max_map[0]; trk.max_map.evt_en = ms->t_max_map[1]; trk.max_map.ref_st = ms->t_max_map[2];
             trk.max_map.ren_end = ms->t_max_map[3]; trk.max_map.evt_st = ms->t_max_map[4]; trk.max_map.total_len = ms->t_max_map[5];
+            if (trk.dir != trk.dir_glob) {          // the directory as the previous chunk left it
+                if (trk.nb <= trk.dir_cap) { for (u32 j = (u32) lane; j < trk.nb; j += 32u) trk.dir[j] = trk.dir_glob[j]; w_sync(); }
+                else trk.dir = trk.dir_glob;
+            }
         }
     }
     u32 verdict = 0, i = n_first, final_event = n_limit;
     u64 n_seeds = 0;
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+    trk.pt[0] = trk.pt[1] = trk.pt[2] = 0;
+#endif
     for (;;) {
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+        if (lane == 0) *(volatile u32 *) &sh->v2.pt_dur[3][K2_MAXSEG - 2 + (i & 1u)] = (u32) pt_clock();   // the tracker's arrival at the event barrier
+        PT_TRACE(i, 0, pt_clock())
+#endif
         c_sync();                                  // b_i: workers finished event i (or this is the final barrier)
         if (i == n_limit) break;
         if (verdict) { c_sync(); break; }          // event i is discarded; final barrier
         const uint2 *rl = W.rlist + (size_t) (i & 1u) * W.rl_cap;
-        const u32 n = *(volatile u32 *) &sh->n_rows[i & 1u];
-        // seed clustering is sequential: ended paths' seeds (event i-1) in parent order, then the
-        // children's (event i) in sorted order
 #if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
         const long long trk_t0 = pt_clock();
+        PT_TRACE(i, 1, trk_t0)
 #endif
-        for (u32 j = 0; j < n; j++) {
-            uint2 e = rl[j];
-            trk_add_seed(trk, p, e.x, e.y & 0xFFu, (e.y & 0x100u) ? i - 1u : i);
+        const u32 n = *(volatile u32 *) &sh->n_rows[i & 1u];
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+        PT_TRACE(i, 2, pt_clock())
+        PT_TRACE(i, 4, n)
+#endif
+        // seed clustering is sequential: ended paths' seeds (event i-1) in parent order, then the
+        // children's (event i) in sorted order
+        for (u32 j0 = 0; j0 < n; j0 += 32u) {         // 32 rows per load
+            uint2 mine = make_uint2(0, 0);
+            if (j0 + (u32) lane < n) mine = rl[j0 + (u32) lane];
+            const u32 nj = n - j0 < 32u ? n - j0 : 32u;
+            for (u32 j = 0; j < nj; j++) {
+                const u32 ex = w_shfl(mine.x, (int) j), ey = w_shfl(mine.y, (int) j);
+                trk_add_seed(trk, p, ex, ey & 0xFFu, (ey & 0x100u) ? i - 1u : i);
+            }
         }
         n_seeds += n;
-#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
-        if (B.dbg && lane == 0) {      // the tracker's own time per event: total, maximum, events above 200 k cycles
-            const unsigned long long busy = (unsigned long long) (pt_clock() - trk_t0);
-            unsigned long long *d = B.dbg + (size_t) r * 64 + 60;
-            d[0] += busy; if (busy > d[1]) d[1] = busy; if (busy > 200000ull) d[2]++; d[3] += n;
-        }
-#endif
         u32 v = (trk.overflow || *(volatile u32 *) &sh->wk_overflow) ? 2u : (trk_get_final(trk, p) ? 1u : 0u);
         if (v) { verdict = v; final_event = i; }
         if (lane == 0) *(volatile u32 *) &sh->verdict[i & 1u] = v;
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+        PT_TRACE(i, 3, pt_clock())
+#endif
         i++;
     }
+    if (STREAM && trk.dir != trk.dir_glob) { for (u32 j = (u32) lane; j < trk.nb; j += 32u) trk.dir_glob[j] = trk.dir[j]; w_sync(); }
     if (STREAM && lane == 0) {                      // what the next map_chunk of this read resumes from
         ms->t_nb = trk.nb; ms->t_n_alloc = trk.n_alloc; ms->t_n_live = trk.n_live; ms->t_n_lens = trk.n_lens;
         ms->t_top1 = trk.top1; ms->t_top2 = trk.top2; ms->t_overflow = trk.overflow; ms->t_len_sum = trk.len_sum;
@@ -1086,6 +1206,9 @@ UNC_DEV void unc_k2_tracker(const DevIndex &ix, const DevParams &p, const DevBat
         ms->event_i = final_event;
         ms->started = 1;
     }
+#if defined(UNC_PHASE_TIMING) && !defined(UNC_EMUL)
+    if (B.dbg && lane == 0) { unsigned long long *d = B.dbg + (size_t) r * 64 + 60; d[0] = trk.pt[0]; d[1] = trk.pt[1]; d[2] = trk.pt[2]; d[3] = n_seeds; }
+#endif
     // all workers have passed the final barrier: their counters are in shared memory
     if (lane == 0) unc_k2_write_record(ix, p, B, sh, r, trk, verdict, final_event, n_seeds);
 }
@@ -2111,7 +2234,7 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
 #ifdef K2_TRK_INLINE
         sh->bc[4] = 0;
         Tracker t0;
-        t0.blocks = W.clu; t0.dir = W.dir; t0.max_blocks = W.max_blocks;
+        t0.blocks = W.clu; t0.dir = t0.dir_glob = W.dir; t0.dir_cap = 0; t0.max_blocks = W.max_blocks;
         trk_reset(t0);
         if (STREAM) {
             const DevMapState *ms = B.mstate + B.chan[r];
@@ -2133,7 +2256,7 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
     c_sync();
     if (tid == 0) {
         Tracker t1;
-        t1.blocks = W.clu; t1.dir = W.dir; t1.max_blocks = W.max_blocks;
+        t1.blocks = W.clu; t1.dir = t1.dir_glob = W.dir; t1.dir_cap = 0; t1.max_blocks = W.max_blocks;
         trk_state_load(sh->trk_state, t1);
         const u32 verdict = sh->trk_state[21], final_event = sh->trk_state[22];
         if (STREAM) {
@@ -2148,7 +2271,8 @@ UNC_DEV void unc_k2_map_read(const DevIndex &ix, const DevParams &p, const DevBa
         unc_k2_write_record(ix, p, B, sh, r, t1, verdict, final_event, ((u64) sh->trk_state[20] << 32) | sh->trk_state[19]);
     }
 #else
-    if (tid < 32) unc_k2_tracker<STREAM>(ix, p, B, W, sh, r, n_first, n_limit);
+    if (tid < 32) unc_k2_tracker<STREAM>(ix, p, B, W, sh, r, n_first, n_limit,
+                                                              K2_V2_ACTIVE && !EXACT ? (uint4 *) sh->hist_next : nullptr, K2_RB * K2_MAXSEG / 4u);   // (the radix counters the first worker structure sorts with)
 #ifndef K2_V1
     else if (!EXACT) unc_k2_workers_v2<STREAM, FLAGS>(ix, p, B, W, sh, r, n_first, n_limit);
 #endif

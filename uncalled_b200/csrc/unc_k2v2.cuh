@@ -386,6 +386,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
     u8 *stage_m = (u8 *) (stage_r + K2_CH_SLOTS);
     u32 *whist = sh->hist_cur + (size_t) ww * 256u;    // warp-private radix counters (big buckets)
     PT_DECL
+    PT_WDECL
 
     for (; event_i < n_limit; event_i++) {
         PT_MARK(9)
@@ -409,6 +410,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         if (wt < K2V2_MAX_MERGED) v2->mfirst[wt] = 0xFFFFu;
         PT_MARK(0)
         c_sync_sub(1, (int) nwt);
+        PT_FENCE
         PT_MARK(16)
 
         uint4 *prev = W.paths + (size_t) gen * gen_recs * 2, *next = W.paths + (size_t) (gen ^ 1u) * gen_recs * 2;
@@ -559,6 +561,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         }
         PT_MARK(1)
         c_sync_sub(1, (int) nwt);
+        PT_FENCE
         PT_MARK(17)
         // ---- B1 + B2a + B2b, concurrently.  Worker warp 0: exclusive scan of the chunk counts (restores the
         //      global emission order and gives the buffer cap, reference src/mapper.cpp:480-482,507-509,521-523:
@@ -627,6 +630,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         }
         PT_MARK(10)
         c_sync_sub(1, (int) nwt);
+        PT_FENCE
         PT_MARK(26)
         if (wt == 0) sh->wl_cnt = 0;
         const u32 nc_total = nch_prev ? sh->bc[2] : 0u;
@@ -690,7 +694,9 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
             }
             PT_MARK(2)
             c_sync_sub(1, (int) nwt);
+            PT_FENCE
             PT_MARK(18)
+            PT_WB
 
             // ---- C2. sort every bucket and count what its dedup walk will emit.  Buckets are handed out 32 ranks (one
             //          group) at a time: first sweep the large buckets (> 32 keys, one warp each, radix), second sweep
@@ -798,9 +804,12 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                     }
                 }
             }
+            PT_WE(1)
             PT_MARK(3)
             c_sync_sub(1, (int) nwt);
+            PT_FENCE
             PT_MARK(19)
+            PT_WR(1, 15, 20)
         }
 
         // ---- D0 + S1, concurrently.  Worker warp 0: prefix sum of the buckets' (sources, seeds), the sources_added_
@@ -859,7 +868,9 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
         }
         PT_MARK(11)
         c_sync_sub(1, (int) nwt);
+        PT_FENCE
         PT_MARK(27)
+        PT_WB
         const u32 n_child_seeds = nc > 0 ? sh->bc[6] : 0u;
         n_rows = n_ended_rows + n_child_seeds;
         if (n_rows > W.rl_cap) n_rows = W.rl_cap;
@@ -968,6 +979,7 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
                 }
             }
         }
+        PT_WE(2)
         // ---- E. fresh sources for every sufficiently probable k-mer without one (reference src/mapper.cpp:605-624):
         //      word j (32 k-mers) by warp j % nwk, positions and the buffer-full cut from worker warp 0's plan
         for (u32 j = ww; j < 32; j += nwk) {
@@ -996,10 +1008,17 @@ UNC_DEV void unc_k2_workers_v2(const DevIndex &ix, const DevParams &p, const Dev
             if (lane == 0) sh->flags[j] = fw & ~visited;
         }
         if (wt == 0) *(volatile u32 *) &sh->n_rows[event_i & 1u] = n_rows;
+        PT_WARR(3)
         PT_MARK(5)
         // ---- hand the event's seeds to the tracker; learn the outcome of the previous event
         c_sync();                                                     // X_e
+        PT_WREL(0)
+        PT_FENCE
         PT_MARK(6)
+        PT_WR(2, 21, 22)
+        PT_WLAG(3, 23, 24)
+        PT_WLAG(0, 13, 14)
+        PT_WTRK(3, 25)
         const u32 nn = sh->bc[1];
         pend_sources = nn - nc;
         const u32 v = event_i > n_first ? *(volatile u32 *) &sh->verdict[(event_i - 1u) & 1u] : 0u;

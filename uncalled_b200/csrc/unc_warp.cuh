@@ -21,6 +21,7 @@ UNC_DEV int c_nthreads() { return (int) blockDim.x; }
 UNC_DEV void c_sync() { __syncthreads(); }
 // named barrier `id` (1..15) over `count` threads (a multiple of 32): bar.sync id, count
 UNC_DEV void c_sync_sub(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+UNC_DEV void c_arrive_sub(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 UNC_DEV void c_fence() { __threadfence_block(); }
 #ifndef K2_SPIN_NS
 #define K2_SPIN_NS 40

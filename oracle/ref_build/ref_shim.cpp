@@ -68,6 +68,24 @@ int ref_load(const char *bwa_prefix, const char *preset) {
     return 0;
 }
 
+// The reference's SeedTracker alone, seed by seed (src/seed_tracker.cpp:129-143,157-232); out as orc_tracker_run (oracle/unc_oracle.c).
+int ref_tracker_run(uint32_t min_map_len, float min_mean_conf, float min_top_conf, const uint64_t *ref_en, const uint32_t *ref_len,
+                    const uint32_t *evt, uint32_t n, uint32_t *out) {
+    SeedTracker::Params prm = {min_map_len, min_mean_conf, min_top_conf};
+    SeedTracker t(prm);
+    for (uint32_t i = 0; i < n; i++) {
+        t.add_seed(ref_en[i], ref_len[i], evt[i]);
+        SeedCluster f = t.get_final();
+        out[6 * i + 0] = (uint32_t) t.seed_clusters_.size();
+        out[6 * i + 1] = t.max_map_.total_len_;
+        out[6 * i + 2] = (uint32_t) t.max_map_.ref_en_.start_;
+        out[6 * i + 3] = t.max_map_.evt_en_;
+        out[6 * i + 4] = f.is_valid() ? f.total_len_ : 0u;
+        out[6 * i + 5] = (uint32_t) t.all_lens_.size();
+    }
+    return 0;
+}
+
 void ref_set_max_events(uint32_t v) { Mapper::PRMS.max_events = v; }
 void ref_set_max_paths(uint32_t v) { Mapper::PRMS.max_paths = v; }
 uint32_t ref_get_max_events() { return Mapper::PRMS.max_events; }

@@ -740,6 +740,29 @@ static cluster_t trk_get_final(const tracker_t *t, const orc_params *p) {
     return NULL_ALN;
 }
 
+/* The seed tracker alone (test hook): feeds the seeds one by one; after seed i out[6i..6i+6) = clusters in the set,
+ * max_map (total_len, low word of ren_start, evt_en), total_len of get_final() (0 = none), multiset size.
+ * Reference src/seed_tracker.cpp:129-143,157-232. */
+int orc_tracker_run(const orc_params *p, const uint64_t *ref_en, const uint32_t *ref_len, const uint32_t *evt, uint32_t n,
+                    uint32_t *out) {
+    tracker_t t;
+    memset(&t, 0, sizeof(t));
+    trk_reset(&t);
+    for (uint32_t i = 0; i < n; i++) {
+        trk_add_seed(&t, p, ref_en[i], ref_len[i], evt[i]);
+        cluster_t f = trk_get_final(&t, p);
+        out[6 * i + 0] = t.n;
+        out[6 * i + 1] = t.max_map.total_len;
+        out[6 * i + 2] = (uint32_t) t.max_map.ren_start;
+        out[6 * i + 3] = t.max_map.evt_en;
+        out[6 * i + 4] = f.total_len;
+        out[6 * i + 5] = t.n_lens;
+    }
+    free(t.set);
+    free(t.lens);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ mapper */
 
 typedef struct {

@@ -75,6 +75,39 @@ static uint32_t g_k1_stats[4];
 extern "C" void emu_k1_stats(uint32_t *out) { memcpy(out, g_k1_stats, sizeof(g_k1_stats)); }
 
 static int g_tie_order = 0;       // emu_set_tie_order: 1 = the exact-ties kernel (k2_map_exact of unc_abi.cu)
+// The device seed tracker alone under the emulator (one warp): the seeds one by one through trk_add_seed, after each the state
+// the oracle's orc_tracker_run reports.  `dir_fast_cap` entries of the directory live in a separate ("shared memory") array
+// first, so that a small value exercises its move to the workspace.
+struct TrkArgs { DevParams p; const u32 *ref_en, *ref_len, *evt; u32 n; u32 *out; uint4 *clu, *dir, *dir_fast; u32 max_blocks, dir_fast_cap; u32 overflow; };
+static void trk_entry(void *vp) {
+    TrkArgs *a = (TrkArgs *) vp;
+    Tracker t;
+    t.blocks = a->clu; t.dir_glob = a->dir; t.max_blocks = a->max_blocks;
+    t.dir = a->dir_fast_cap ? a->dir_fast : a->dir; t.dir_cap = a->dir_fast_cap;
+    trk_reset(t);
+    for (u32 i = 0; i < a->n; i++) {
+        trk_add_seed(t, a->p, a->ref_en[i], a->ref_len[i], a->evt[i]);
+        if (w_lane() == 0) {
+            u32 *o = a->out + (size_t) 6 * i;
+            o[0] = t.n_live; o[1] = t.max_map.total_len; o[2] = t.max_map.ren_start; o[3] = t.max_map.evt_en;
+            o[4] = trk_get_final(t, a->p) ? t.max_map.total_len : 0u; o[5] = t.n_lens;
+        }
+        w_sync();
+    }
+    if (w_lane() == 0) a->overflow = t.overflow | ((t.dir == t.dir_glob ? 1u : 0u) << 1);
+}
+extern "C" int emu_tracker_run(uint32_t min_map_len, float min_mean_conf, float min_top_conf, const uint32_t *ref_en, const uint32_t *ref_len,
+                               const uint32_t *evt, uint32_t n, uint32_t *out, uint32_t max_blocks, uint32_t dir_fast_cap) {
+    TrkArgs a;
+    memset(&a.p, 0, sizeof(a.p));
+    a.p.min_map_len = min_map_len; a.p.min_mean_conf = min_mean_conf; a.p.min_top_conf = min_top_conf;
+    a.ref_en = ref_en; a.ref_len = ref_len; a.evt = evt; a.n = n; a.out = out;
+    std::vector<uint4> clu((size_t) max_blocks * 32 * 2), dir(max_blocks + 1), fast(dir_fast_cap + 1);
+    a.clu = clu.data(); a.dir = dir.data(); a.dir_fast = fast.data(); a.max_blocks = max_blocks; a.dir_fast_cap = dir_fast_cap; a.overflow = 0;
+    emu_run_warp(trk_entry, &a);
+    return (int) a.overflow;      // bit 0: block store overflowed, bit 1: the directory ended in the workspace
+}
+
 extern "C" void emu_set_tie_order(int mode) { g_tie_order = mode; }
 extern "C" void emu_tie_stats(unsigned long *out, int reset) {
     out[0] = g_emu_tie_stats[0]; out[1] = g_emu_tie_stats[1];

@@ -279,6 +279,23 @@ int unc_self_align(const char *bwa_prefix, uint32_t sample_dist, uint64_t *n_pat
                    uint64_t **values);
 void unc_free(void *p);
 
+/* ---- DTW of event means against reference k-mers (analysis) ----------------------
+ *   unc_dtw_batch       DTWr94p(means, kmers, prms) / DTWr94d(...) + get_path() / score()
+ *                                                      src/dtw.hpp:31-183 (DTW<float, u16, Func>), :188-232 (the two
+ *                                                      instances), bound at src/pybinder.cpp:75-91
+ * Rows = k-mers, columns = event means.  cost_kind 0 = DTWr94p (cost = -match_prob of the r9.4 TEMPLATE model), 1 = DTWr94d
+ * (cost = abs(e - mean_k) as the reference compiles it: int abs(int), the difference truncated towards zero first).
+ * model_means_stdvs = the 1024 (mean, stdv) pairs of src/model_r94.inl (uncalled_b200/data/r94_5mer_template.f32).
+ * unc_dtw_params = DTWParams (subseq: DTWSubSeq NONE 0 / ROW 1 / COL 2; dw, hw, vw).  Problem p: event means
+ * means[mean_off[p] .. mean_off[p+1]), k-mers kmers[kmer_off[p] .. kmer_off[p+1]).  Out, per problem: get_path() as
+ * (column, row) u64 pairs from the end cell back to the start at path[2*path_off[p] ...] (path_off[p+1] - path_off[p] >=
+ * rows + columns), their number in path_len[p], score() in score[p]; mean_score() = score / path_len.  The matrices of
+ * one call (one byte per cell) must fit the device memory: UNC_E_NOMEM otherwise. */
+typedef struct { int32_t subseq; float dw, hw, vw; } unc_dtw_params;
+int unc_dtw_batch(const float *model_means_stdvs, int cost_kind, const unc_dtw_params *prm, uint32_t n_problems,
+                  const float *means, const uint64_t *mean_off, const uint16_t *kmers, const uint64_t *kmer_off,
+                  uint64_t *path, const uint64_t *path_off, uint64_t *path_len, float *score);
+
 /* ---- fast5 input (host; no libhdf5 needed) -------------------------------------------------------------
  *   unc_fast5_open      Fast5Reader::open_next: format detection and the list of reads
  *                                                      src/fast5_reader.cpp:134-177

@@ -45,6 +45,8 @@
 #include "mapper.hpp"
 #undef private
 #include "self_align_ref.hpp"
+#include "model_r94.inl"
+#include "dtw.hpp"
 
 extern "C" {
 
@@ -65,6 +67,20 @@ int ref_load(const char *bwa_prefix, const char *preset) {
     Mapper::PRMS.idx_preset = preset ? preset : "default";
     Mapper m;  // triggers Mapper::load_static()
     g_seqs = Mapper::fmi.get_seqs();
+    return 0;
+}
+
+// The reference's DTW classes (src/dtw.hpp:188-232) on one problem; path = get_path() as (first, second) pairs.
+int ref_dtw(int cost_kind, int subseq, float dw, float hw, float vw, const float *means, uint32_t n_cols, const uint16_t *kmers,
+            uint32_t n_rows, uint64_t *path, uint64_t *path_len, float *score, float *mean_score) {
+    std::vector<float> m(means, means + n_cols);
+    std::vector<u16> k(kmers, kmers + n_rows);
+    DTWParams prm = {subseq == 1 ? DTWSubSeq::ROW : (subseq == 2 ? DTWSubSeq::COL : DTWSubSeq::NONE), dw, hw, vw};
+    std::vector<std::pair<u64, u64>> p;
+    if (cost_kind == 0) { DTWr94p d(m, k, prm); p = d.get_path(); *score = d.score(); *mean_score = d.mean_score(); }
+    else { DTWr94d d(m, k, prm); p = d.get_path(); *score = d.score(); *mean_score = d.mean_score(); }
+    for (size_t i = 0; i < p.size(); i++) { path[2 * i] = p[i].first; path[2 * i + 1] = p[i].second; }
+    *path_len = p.size();
     return 0;
 }
 

@@ -763,6 +763,60 @@ int orc_tracker_run(const orc_params *p, const uint64_t *ref_en, const uint32_t 
     return 0;
 }
 
+/* ------------------------------------------------------------------ DTW
+ * reference src/dtw.hpp: DTW<float,u16,Func> :31-183 -- rows = k-mers, columns = event means; compute_matrix :49-74,
+ * traceback :76-122, boundary scores :153-173; costs DTWr94p :188-190 (-match_prob of the TEMPLATE model), DTWr94d :212-214
+ * (|e - mean_k|).  Path pairs are (column, row) from the end cell back to the start, as get_path() returns them. */
+#define DTW_MAX_COST (FLT_MAX / 2.0f)
+int orc_dtw(const orc_model *tmpl, int cost_kind, int subseq, float dw, float hw, float vw, const float *means, uint32_t n_cols,
+            const uint16_t *kmers, uint32_t n_rows, uint64_t *path, uint64_t *path_len, float *score) {
+    const u64 R = n_rows, Cn = n_cols;
+    if (R == 0 || Cn == 0) return -1;
+    float *mat = (float *) malloc(R * Cn * sizeof(float));
+    u8 *bc = (u8 *) malloc(R * Cn);
+    if (!mat || !bc) { free(mat); free(bc); return -2; }
+    u64 k = 0;
+    for (u64 i = 0; i < R; i++) {
+        for (u64 j = 0; j < Cn; j++) {
+            /* DTWr94d: `abs(e - mean)` in src/dtw.hpp:213 binds to int abs(int) -- the float difference is truncated towards zero
+             * first (verified against oracle/_ref: all its r94d scores are whole numbers) */
+            float cost = cost_kind == 0 ? -orc_match_prob(tmpl, means[j], kmers[i]) : (float) abs((int) (means[j] - tmpl->lv_mean[kmers[i]]));
+            float dsc, hsc, vsc;
+            if (j > 0 && i > 0) dsc = mat[Cn * (i - 1) + j - 1];
+            else if (j == i || (i == 0 && subseq == 2) || (j == 0 && subseq == 1)) dsc = 0;
+            else dsc = DTW_MAX_COST;
+            if (j > 0) hsc = mat[Cn * i + j - 1];
+            else hsc = subseq == 1 ? 0 : DTW_MAX_COST;
+            if (i > 0) vsc = mat[Cn * (i - 1) + j];
+            else vsc = subseq == 2 ? 0 : DTW_MAX_COST;
+            float ds = dsc + (dw * cost), hs = hsc + (hw * cost), vs = vsc + (vw * cost);
+            if (ds <= hs && ds <= vs) { mat[k] = ds; bc[k++] = 0; }      /* Move::D */
+            else if (hs <= vs) { mat[k] = hs; bc[k++] = 1; }             /* Move::H */
+            else { mat[k] = vs; bc[k++] = 2; }                           /* Move::V */
+        }
+    }
+    u64 i = R - 1, j = Cn - 1;
+    if (subseq == 1) {                     /* ROW: best cell of the last column */
+        for (u64 q = 0; q < R; q++) if (mat[q * Cn + j] < mat[i * Cn + j]) i = q;
+    } else if (subseq == 2) {              /* COL: best cell of the last row */
+        for (u64 q = 0; q < Cn; q++) if (mat[i * Cn + q] < mat[i * Cn + j]) j = q;
+    }
+    *score = mat[i * Cn + j];
+    u64 n = 0;
+    path[2 * n] = j; path[2 * n + 1] = i; n++;
+    k = i * Cn + j;
+    while (!(i == 0 || subseq == 1) || !(j == 0 || subseq == 2)) {
+        if (i == 0 || bc[k] == 1) { k--; j--; }
+        else if (j == 0 || bc[k] == 2) { k -= Cn; i--; }
+        else { k -= Cn + 1; i--; j--; }
+        path[2 * n] = j; path[2 * n + 1] = i; n++;
+    }
+    *path_len = n;
+    free(mat);
+    free(bc);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ mapper */
 
 typedef struct {

@@ -40,6 +40,11 @@ def test_module_exports_the_names_the_reference_cli_uses():
     assert (c.bwa_prefix, c.max_chunks) == ("x", 3)
     assert int(m.RealtimePool.DEPLETE) == 0 and int(m.RealtimePool.ENRICH) == 1 and int(m.RealtimePool.ODD) == 2
     assert int(m.Paf.ENDED) == 10 and int(m.Paf.KEEP) == 11
+    # the DTW classes and presets of src/pybinder.cpp:75-91 (DTW_RAW_QSUB / _RSUB are bound to the EVENT presets there)
+    for name in ("DTWr94p", "DTWr94d", "DTWParams", "DTW_EVENT_GLOB", "DTW_RAW_GLOB", "DTW_EVENT_QSUB", "DTW_EVENT_RSUB", "DTW_RAW_QSUB", "DTW_RAW_RSUB"):
+        assert hasattr(m, name), name
+    assert (m.DTW_EVENT_GLOB.dw, m.DTW_EVENT_GLOB.hw, m.DTW_EVENT_GLOB.vw) == (2, 1, 100)
+    assert (m.DTW_RAW_GLOB.dw, m.DTW_RAW_GLOB.vw, m.DTW_RAW_QSUB.dw, m.DTW_RAW_RSUB.vw) == (10, 1000, 2, 100)
 
 
 def test_paf_line_formatting_matches_the_golden_line():

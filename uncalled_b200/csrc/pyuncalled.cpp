@@ -381,6 +381,34 @@ static std::vector<std::vector<u64>> self_align(const std::string &prefix, u32 s
     unc_free(off); unc_free(val);
     return ret;
 }
+// ------------------------------------------------------------------ DTW (reference src/dtw.hpp:9-28,188-232, src/pybinder.cpp:75-91)
+struct DTWParams { int32_t subseq; float dw, hw, vw; };          // = unc_dtw_params; subseq: DTWSubSeq NONE 0, ROW 1, COL 2
+static const DTWParams DTW_EVENT_GLOB = {0, 2, 1, 100}, DTW_EVENT_QSUB = {2, 2, 1, 100}, DTW_EVENT_RSUB = {1, 2, 1, 100},
+                       DTW_RAW_GLOB = {0, 10, 1, 1000};
+template <int COST>
+class DTWr94 {
+    std::vector<std::pair<u64, u64>> path_;
+    float score_ = 0;
+  public:
+    DTWr94(const std::vector<float> &means, const std::vector<uint16_t> &kmers, const DTWParams &p) {
+        std::string table = Engine::default_model_table();
+        std::vector<float> model(2048);
+        FILE *fp = fopen(table.c_str(), "rb");
+        if (!fp || fread(model.data(), 4, 2048, fp) != 2048) { if (fp) fclose(fp); throw std::runtime_error("cannot read " + table); }
+        fclose(fp);
+        const uint64_t moff[2] = {0, means.size()}, koff[2] = {0, kmers.size()}, poff[2] = {0, means.size() + kmers.size()};
+        std::vector<uint64_t> path(2 * poff[1] + 2);
+        uint64_t n = 0;
+        unc_dtw_params prm = {p.subseq, p.dw, p.hw, p.vw};
+        check(unc_dtw_batch(model.data(), COST, &prm, 1, means.data(), moff, kmers.data(), koff, path.data(), poff, &n, &score_), "unc_dtw_batch");
+        path_.resize(n);
+        for (uint64_t i = 0; i < n; i++) path_[i] = {path[2 * i], path[2 * i + 1]};
+    }
+    std::vector<std::pair<u64, u64>> get_path() { return path_; }
+    float score() { return score_; }
+    float mean_score() { return score_ / path_.size(); }
+};
+
 struct ClientSim {
     explicit ClientSim(Conf &) { throw std::runtime_error("ClientSim (`uncalled sim`) is outside the scope of the B200 module"); }
 };
@@ -475,4 +503,16 @@ PYBIND11_MODULE(_uncalled, m) {
     py::class_<ClientSim>(m, "ClientSim").def(py::init<Conf &>());
     py::class_<BwaIndex>(m, "BwaIndex").def_static("create", &BwaIndex::create);
     m.def("self_align", &self_align);
+
+    py::class_<DTWr94<0>>(m, "DTWr94p").def(py::init<const std::vector<float> &, const std::vector<uint16_t> &, const DTWParams &>())
+        .def("get_path", &DTWr94<0>::get_path).def("score", &DTWr94<0>::score).def("mean_score", &DTWr94<0>::mean_score);
+    py::class_<DTWr94<1>>(m, "DTWr94d").def(py::init<const std::vector<float> &, const std::vector<uint16_t> &, const DTWParams &>())
+        .def("get_path", &DTWr94<1>::get_path).def("score", &DTWr94<1>::score).def("mean_score", &DTWr94<1>::mean_score);
+    py::class_<DTWParams>(m, "DTWParams").def_readwrite("dw", &DTWParams::dw).def_readwrite("hw", &DTWParams::hw).def_readwrite("vw", &DTWParams::vw);
+    m.attr("DTW_EVENT_GLOB") = py::cast(DTW_EVENT_GLOB);
+    m.attr("DTW_RAW_GLOB") = py::cast(DTW_RAW_GLOB);
+    m.attr("DTW_EVENT_QSUB") = py::cast(DTW_EVENT_QSUB);
+    m.attr("DTW_EVENT_RSUB") = py::cast(DTW_EVENT_RSUB);
+    m.attr("DTW_RAW_QSUB") = py::cast(DTW_EVENT_QSUB);        // as bound by the reference (src/pybinder.cpp:90-91): the EVENT presets
+    m.attr("DTW_RAW_RSUB") = py::cast(DTW_EVENT_RSUB);
 }

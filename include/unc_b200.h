@@ -295,6 +295,10 @@ typedef struct { int32_t subseq; float dw, hw, vw; } unc_dtw_params;
 int unc_dtw_batch(const float *model_means_stdvs, int cost_kind, const unc_dtw_params *prm, uint32_t n_problems,
                   const float *means, const uint64_t *mean_off, const uint16_t *kmers, const uint64_t *kmer_off,
                   uint64_t *path, const uint64_t *path_off, uint64_t *path_len, float *score);
+/* The device workspace of unc_dtw_batch is kept between calls and grown on demand; unc_dtw_release (also called by
+ * unc_shutdown) frees it.  unc_dtw_last_kernel_ms: CUDA-event time of the last call's sweep kernel. */
+void unc_dtw_release(void);
+float unc_dtw_last_kernel_ms(void);
 
 /* ---- fast5 input (host; no libhdf5 needed) -------------------------------------------------------------
  *   unc_fast5_open      Fast5Reader::open_next: format detection and the list of reads

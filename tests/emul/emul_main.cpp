@@ -130,7 +130,7 @@ extern "C" int emu_dtw_batch(const float *model_means_stdvs, int cost_kind, int 
         DevDtwProblem &P = prob[i];
         P.mean_off = mean_off[i]; P.kmer_off = kmer_off[i]; P.n_cols = (u32) nc; P.n_rows = (u32) nr;
         P.bc_off = bc_total; P.diag_off = diag_total; P.edge_off = edge_total; P.path_off = path_off[i];
-        bc_total += nr * nc; diag_total += 3 * nr; edge_total += nr + nc;
+        bc_total += nr * nc; diag_total += UNC_DTW_WORK_FLOATS(nr, nc); edge_total += nr + nc;
     }
     std::vector<unsigned char> bc(bc_total + 1);
     std::vector<float> diag(diag_total + 1), edge(edge_total + 1);

@@ -267,6 +267,7 @@ int unc_init(int device) {
 int unc_shutdown(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) == cudaSuccess && g_device < n && cudaSetDevice(g_device) == cudaSuccess) {
+        unc_dtw_release();
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) return fail(UNC_E_CUDA, std::string("cudaDeviceSynchronize: ") + cudaGetErrorString(e));
     }

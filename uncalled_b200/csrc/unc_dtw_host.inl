@@ -15,14 +15,17 @@ __global__ void __launch_bounds__(256) k_dtw(DevDtw D) {
 }
 
 namespace {
-struct DtwBuffers {                  // frees whatever was allocated, on every exit path
-    void *model = nullptr, *means = nullptr, *kmers = nullptr, *prob = nullptr, *bc = nullptr, *diag = nullptr, *edge = nullptr,
-         *path = nullptr, *path_len = nullptr, *score = nullptr, *queue = nullptr;
-    ~DtwBuffers() {
-        cudaFree(model); cudaFree(means); cudaFree(kmers); cudaFree(prob); cudaFree(bc); cudaFree(diag); cudaFree(edge);
-        cudaFree(path); cudaFree(path_len); cudaFree(score); cudaFree(queue);
-    }
+// One device workspace, kept between calls and grown on demand (cudaMalloc / cudaFree of the breadcrumb matrix cost more than
+// the sweep); released by unc_shutdown.  Calls are serialised by g_dtw_mutex.
+struct DtwWorkspace {
+    void *p = nullptr;
+    size_t cap = 0;
+    int device = -1;
+    float last_kernel_ms = 0;
 };
+DtwWorkspace g_dtw_ws;
+std::mutex g_dtw_mutex;
+size_t dtw_align(size_t x) { return (x + 255) & ~(size_t) 255; }
 }  // namespace
 
 extern "C" int unc_dtw_batch(const float *model_means_stdvs, int cost_kind, const unc_dtw_params *prm, uint32_t n_problems,
@@ -55,7 +58,7 @@ extern "C" int unc_dtw_batch(const float *model_means_stdvs, int cost_kind, cons
         DevDtwProblem &P = prob[i];
         P.mean_off = mean_off[i]; P.kmer_off = kmer_off[i]; P.n_cols = (u32) nc; P.n_rows = (u32) nr;
         P.bc_off = bc_total; P.diag_off = diag_total; P.edge_off = edge_total; P.path_off = path_off[i];
-        bc_total += nr * nc; diag_total += 3 * nr; edge_total += nr + nc;
+        bc_total += nr * nc; diag_total += UNC_DTW_WORK_FLOATS(nr, nc); edge_total += nr + nc;
     }
     for (uint64_t k = kmer_off[0]; k < kmer_off[n_problems]; k++)
         if (kmers[k] >= 1024) return fail(UNC_E_ARG, "k-mer code out of range (5-mers: 0..1023)");
@@ -64,35 +67,58 @@ extern "C" int unc_dtw_batch(const float *model_means_stdvs, int cost_kind, cons
     const uint64_t n_means = mean_off[n_problems], n_kmers = kmer_off[n_problems], n_path = path_off[n_problems];
     if (bc_total + 4 * (diag_total + edge_total + n_means) + 2 * n_kmers + 16 * n_path + (64u << 20) > free_b)
         return fail(UNC_E_NOMEM, "the DTW matrices of this batch do not fit the device memory: pass fewer problems per call");
-    DtwBuffers b;
-    size_t dummy = 0;
-    int rc;
-    if ((rc = upload(&b.model, model.data(), model.size() * 4, 0, &dummy)) != UNC_OK) return rc;
-    if ((rc = upload(&b.means, means, n_means * 4, 0, &dummy)) != UNC_OK) return rc;
-    if ((rc = upload(&b.kmers, kmers, n_kmers * 2, 0, &dummy)) != UNC_OK) return rc;
-    if ((rc = upload(&b.prob, prob.data(), prob.size() * sizeof(DevDtwProblem), 0, &dummy)) != UNC_OK) return rc;
-    CUDA_TRY(cudaMalloc(&b.bc, bc_total));
-    CUDA_TRY(cudaMalloc(&b.diag, diag_total * 4));
-    CUDA_TRY(cudaMalloc(&b.edge, edge_total * 4));
-    CUDA_TRY(cudaMalloc(&b.path, n_path * 16));
-    CUDA_TRY(cudaMalloc(&b.path_len, (size_t) n_problems * 8));
-    CUDA_TRY(cudaMalloc(&b.score, (size_t) n_problems * 4));
-    CUDA_TRY(cudaMalloc(&b.queue, 4));
-    CUDA_TRY(cudaMemset(b.queue, 0, 4));
+    std::lock_guard<std::mutex> lock(g_dtw_mutex);
+    // carve the workspace
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += dtw_align(bytes); return o; };
+    const size_t o_model = take(model.size() * 4), o_means = take(n_means * 4), o_kmers = take(n_kmers * 2),
+                 o_prob = take(prob.size() * sizeof(DevDtwProblem)), o_bc = take(bc_total), o_diag = take(diag_total * 4),
+                 o_edge = take(edge_total * 4), o_path = take(n_path * 16), o_plen = take((size_t) n_problems * 8),
+                 o_score = take((size_t) n_problems * 4), o_queue = take(4);
+    if (g_dtw_ws.cap < off || g_dtw_ws.device != g_device) {
+        if (g_dtw_ws.p) { cudaFree(g_dtw_ws.p); g_dtw_ws.p = nullptr; g_dtw_ws.cap = 0; }
+        CUDA_TRY(cudaMalloc(&g_dtw_ws.p, off));
+        g_dtw_ws.cap = off; g_dtw_ws.device = g_device;
+    }
+    char *w = (char *) g_dtw_ws.p;
+    CUDA_TRY(cudaMemcpy(w + o_model, model.data(), model.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(w + o_means, means, n_means * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(w + o_kmers, kmers, n_kmers * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(w + o_prob, prob.data(), prob.size() * sizeof(DevDtwProblem), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(w + o_queue, 0, 4));
     DevDtw D;
-    D.model = (const float *) b.model; D.means = (const float *) b.means; D.kmers = (const u16 *) b.kmers;
-    D.prob = (const DevDtwProblem *) b.prob; D.n_prob = n_problems;
-    D.bc = (unsigned char *) b.bc; D.diag = (float *) b.diag; D.edge = (float *) b.edge;
-    D.path = (u64 *) b.path; D.path_len = (u64 *) b.path_len; D.score = (float *) b.score;
+    D.model = (const float *) (w + o_model); D.means = (const float *) (w + o_means); D.kmers = (const u16 *) (w + o_kmers);
+    D.prob = (const DevDtwProblem *) (w + o_prob); D.n_prob = n_problems;
+    D.bc = (unsigned char *) (w + o_bc); D.diag = (float *) (w + o_diag); D.edge = (float *) (w + o_edge);
+    D.path = (u64 *) (w + o_path); D.path_len = (u64 *) (w + o_plen); D.score = (float *) (w + o_score);
     D.cost_kind = cost_kind; D.subseq = prm->subseq; D.dw = prm->dw; D.hw = prm->hw; D.vw = prm->vw;
-    D.queue = (u32 *) b.queue;
+    D.queue = (u32 *) (w + o_queue);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, g_device));
     const uint32_t grid = std::min<uint32_t>(n_problems, (uint32_t) prop.multiProcessorCount * 4u);   // persistent CTAs, problems from a queue
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    cudaEventRecord(e0);
     k_dtw<<<grid, 256>>>(D);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpy(path_len, b.path_len, (size_t) n_problems * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(score, b.score, (size_t) n_problems * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(path + 2 * path_off[0], (u64 *) b.path + 2 * path_off[0], (n_path - path_off[0]) * 16, cudaMemcpyDeviceToHost));
+    cudaEventRecord(e1);
+    cudaError_t le = cudaGetLastError();
+    if (le == cudaSuccess) le = cudaEventSynchronize(e1);
+    if (le == cudaSuccess) cudaEventElapsedTime(&g_dtw_ws.last_kernel_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(le);
+    CUDA_TRY(cudaMemcpy(path_len, w + o_plen, (size_t) n_problems * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(score, w + o_score, (size_t) n_problems * 4, cudaMemcpyDeviceToHost));
+    // only the pairs that were written travel back
+    for (uint32_t i = 0; i < n_problems; i++)
+        CUDA_TRY(cudaMemcpy(path + 2 * path_off[i], (u64 *) (w + o_path) + 2 * path_off[i], (size_t) path_len[i] * 16, cudaMemcpyDeviceToHost));
     return UNC_OK;
+}
+
+// wall-clock-free timing of the last call's sweep (CUDA events around k_dtw), for tools/bench_dtw.py
+extern "C" float unc_dtw_last_kernel_ms(void) { return g_dtw_ws.last_kernel_ms; }
+extern "C" void unc_dtw_release(void) {
+    std::lock_guard<std::mutex> lock(g_dtw_mutex);
+    if (g_dtw_ws.p) cudaFree(g_dtw_ws.p);
+    g_dtw_ws.p = nullptr; g_dtw_ws.cap = 0;
 }

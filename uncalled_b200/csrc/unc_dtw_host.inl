@@ -109,9 +109,7 @@ extern "C" int unc_dtw_batch(const float *model_means_stdvs, int cost_kind, cons
     CUDA_TRY(le);
     CUDA_TRY(cudaMemcpy(path_len, w + o_plen, (size_t) n_problems * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(score, w + o_score, (size_t) n_problems * 4, cudaMemcpyDeviceToHost));
-    // only the pairs that were written travel back
-    for (uint32_t i = 0; i < n_problems; i++)
-        CUDA_TRY(cudaMemcpy(path + 2 * path_off[i], (u64 *) (w + o_path) + 2 * path_off[i], (size_t) path_len[i] * 16, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(path + 2 * path_off[0], (u64 *) (w + o_path) + 2 * path_off[0], (n_path - path_off[0]) * 16, cudaMemcpyDeviceToHost));
     return UNC_OK;
 }
 

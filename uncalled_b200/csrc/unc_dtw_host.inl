@@ -62,11 +62,7 @@ extern "C" int unc_dtw_batch(const float *model_means_stdvs, int cost_kind, cons
     }
     for (uint64_t k = kmer_off[0]; k < kmer_off[n_problems]; k++)
         if (kmers[k] >= 1024) return fail(UNC_E_ARG, "k-mer code out of range (5-mers: 0..1023)");
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t n_means = mean_off[n_problems], n_kmers = kmer_off[n_problems], n_path = path_off[n_problems];
-    if (bc_total + 4 * (diag_total + edge_total + n_means) + 2 * n_kmers + 16 * n_path + (64u << 20) > free_b)
-        return fail(UNC_E_NOMEM, "the DTW matrices of this batch do not fit the device memory: pass fewer problems per call");
     std::lock_guard<std::mutex> lock(g_dtw_mutex);
     // carve the workspace
     size_t off = 0;
@@ -77,6 +73,10 @@ extern "C" int unc_dtw_batch(const float *model_means_stdvs, int cost_kind, cons
                  o_score = take((size_t) n_problems * 4), o_queue = take(4);
     if (g_dtw_ws.cap < off || g_dtw_ws.device != g_device) {
         if (g_dtw_ws.p) { cudaFree(g_dtw_ws.p); g_dtw_ws.p = nullptr; g_dtw_ws.cap = 0; }
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        if (off + (64u << 20) > free_b)
+            return fail(UNC_E_NOMEM, "the DTW matrices of this batch do not fit the device memory: pass fewer problems per call");
         CUDA_TRY(cudaMalloc(&g_dtw_ws.p, off));
         g_dtw_ws.cap = off; g_dtw_ws.device = g_device;
     }

@@ -202,8 +202,11 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64+u64", "data": "synthetic",
-            "config": {"workload": "E. coli-sized 4.7 Mb synthetic index, synthetic r9.4 reads x 4000 samples, noise %.1f x level stdv" % NOISE_MULT,
-                       "reads_per_step": sample, "note": "bounded sample (the first reads) of the 10k-read workload per step"},
+            "config": {"workload": "configs[1]: E. coli-sized 4.7 Mb synthetic index, %d synthetic r9.4 reads x %d "
+                                   "samples per GPU, noise %.1f x level stdv (SURVEY 8d)" % (N_READS, N_SAMPLES, NOISE_MULT),
+                       "reads_per_gpu": N_READS, "samples_per_read": N_SAMPLES,
+                       "reads_per_step": sample, "note": "each step is a bounded sample (the first reads) of that workload, on the host CPUs this "
+                                                         "process can use; rank 0 only"},
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": kind, "host_cpus": cpus,
                              "reads_per_s_per_thread": value / threads,
                              "sample": "%d reads x %d samples per step, %d threads (one long-lived Mapper per thread, as MapPool)" % (sample, N_SAMPLES, threads)},

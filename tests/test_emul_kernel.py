@@ -46,7 +46,7 @@ def test_synthetic_reads_and_ragged_batch(g200k):
     _check(E, O, [sig[i, :L] for i, L in enumerate(lens)])
 
 
-@pytest.mark.parametrize("n_warps", [2, 5, 16])
+@pytest.mark.parametrize("n_warps", [2, 5, 14, 16])      # 14 = the shape the GPU build runs (K2_WARPS)
 def test_cta_shapes(g200k, n_warps):
     prefix, g = g200k
     E, O = emulib.Emu(prefix), orclib.Oracle(prefix)

@@ -168,3 +168,13 @@ def test_gpu_dtw_through_the_uncalled_module():
             wp, ws = _oracle(M, kind, sub, (2, 1, 100), means, km)
             assert d.get_path() == [(int(a), int(b)) for a, b in wp] and d.score() == ws
             assert d.mean_score() == float(np.float32(ws) / np.float32(len(wp)))
+
+
+def test_dtw_fails_loudly_without_a_gpu():
+    """No CPU path: without a CUDA device the call reports UNC_E_NO_DEVICE (it must never fall back to the oracle)."""
+    import uncalled_b200._native as N
+    from uncalled_b200 import dtw as D
+    if N.lib().unc_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(N.UncError, match="no CUDA device"):
+        D.DTWr94p(np.array([80.0, 90.0], np.float32), np.array([1, 2, 3], np.uint16), D.DTW_EVENT_GLOB)

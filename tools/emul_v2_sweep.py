@@ -1,6 +1,6 @@
 """CPU sweep of the mapper kernel's second structure (unc_k2v2.cuh) under the emulator: many bench-like reads per
 index, PAF fields and the children / sources / seeds / clusters counters against the oracle, in parallel processes.
-    python tools/emul_v2_sweep.py <index name> <first read> <n reads> [seed [noise_mult [max_paths]]]"""
+    python tools/emul_v2_sweep.py <index name> <first read> <n reads> [seed [noise_mult [max_paths [warps per CTA]]]]"""
 import os
 import sys
 import time
@@ -15,6 +15,7 @@ n = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 seed = int(sys.argv[4]) if len(sys.argv) > 4 else 7
 noise = float(sys.argv[5]) if len(sys.argv) > 5 else 1.0
 maxp = int(sys.argv[6]) if len(sys.argv) > 6 else 10000
+n_warps = int(sys.argv[7]) if len(sys.argv) > 7 else 8
 
 
 def work(job):
@@ -28,7 +29,7 @@ def work(job):
     cnt = lambda r: (r.n_children, r.n_sources, r.n_seeds, r.n_clusters)
     bad = []
     sigs = [sig[i] for i in range(lo, hi)]
-    recs = E.map_batch(sigs)[0]
+    recs = E.map_batch(sigs, n_warps=n_warps)[0]
     for i, r in zip(range(lo, hi), recs):
         w = O.map_read(sig[i])
         if (emulib.paf_tuple(r), cnt(r)) != (orclib.paf_tuple(w), cnt(w)) or r.status != 0:
